@@ -1,0 +1,302 @@
+"""TEST INFRASTRUCTURE — build-container only.
+
+Runs the UNMODIFIED reference (`/root/reference/humanoid/...`) on the CPU so that
+(a) the oracle restatement in `oracle/hector_oracle.py` can be pinned against it and
+(b) golden vectors can be generated for `tests/golden/` (see `oracle/make_golden.py`).
+
+`/root/reference` does not exist on the GPU box, so nothing under `tests/ -m gpu`,
+`bench.py` or `__graft_entry__.smoke()` imports this module.  No reference source is
+copied into this repository: the reference is imported from where it lies.
+
+How: the reference needs the closed third-party `isaacgym` package.
+We register stub modules for it — `isaacgym.torch_utils` is a restatement of the
+well-known public definitions of the 7 helpers the hot path calls — build
+`HectorFreeEnv` with `__new__` (skipping `create_sim`, which needs the simulator),
+seed the attributes `_create_envs` would have produced, and then call the reference's
+own `_parse_cfg / _init_buffers / _prepare_reward_function / reset_idx / step`.
+
+Random draws are injected: `torch.rand`, `torch.randn_like` and `torch_rand_float`
+are patched to replay env-indexed tapes (`isaac_b200.synthetic.NoiseFrame`), which is
+the contract the CUDA path implements ("noise injected as a supplied tensor").
+"""
+from __future__ import annotations
+
+import contextlib
+import math
+import sys
+import types
+from unittest.mock import MagicMock
+
+import numpy as np
+import torch
+
+REFERENCE_ROOT = "/root/reference"
+
+
+# --------------------------------------------------------------------------------------
+# isaacgym.torch_utils restatement (public definitions; SURVEY.md §8c "parity unpinned"
+# for these helpers: Isaac Gym preview4 is not in the image, cross-checked against scipy
+# in tests/test_oracle_pinning.py)
+# --------------------------------------------------------------------------------------
+def _quat_rotate_inverse(q, v):
+    shape = q.shape
+    q_w = q[:, -1]
+    q_vec = q[:, :3]
+    a = v * (2.0 * q_w ** 2 - 1.0).unsqueeze(-1)
+    b = torch.cross(q_vec, v, dim=-1) * q_w.unsqueeze(-1) * 2.0
+    c = q_vec * torch.bmm(q_vec.view(shape[0], 1, 3), v.view(shape[0], 3, 1)).squeeze(-1) * 2.0
+    return a - b + c
+
+
+def _quat_apply(a, b):
+    shape = b.shape
+    a = a.reshape(-1, 4)
+    b = b.reshape(-1, 3)
+    xyz = a[:, :3]
+    t = xyz.cross(b, dim=-1) * 2
+    return (b + a[:, 3:] * t + xyz.cross(t, dim=-1)).view(shape)
+
+
+def _copysign(a, b):
+    a = torch.tensor(a, device=b.device, dtype=torch.float).repeat(b.shape[0])
+    return torch.abs(a) * torch.sign(b)
+
+
+def _get_euler_xyz(q):
+    qx, qy, qz, qw = 0, 1, 2, 3
+    sinr_cosp = 2.0 * (q[:, qw] * q[:, qx] + q[:, qy] * q[:, qz])
+    cosr_cosp = q[:, qw] * q[:, qw] - q[:, qx] * q[:, qx] - q[:, qy] * q[:, qy] + q[:, qz] * q[:, qz]
+    roll = torch.atan2(sinr_cosp, cosr_cosp)
+    sinp = 2.0 * (q[:, qw] * q[:, qy] - q[:, qz] * q[:, qx])
+    pitch = torch.where(torch.abs(sinp) >= 1, _copysign(np.pi / 2.0, sinp), torch.asin(sinp))
+    siny_cosp = 2.0 * (q[:, qw] * q[:, qz] + q[:, qx] * q[:, qy])
+    cosy_cosp = q[:, qw] * q[:, qw] + q[:, qx] * q[:, qx] - q[:, qy] * q[:, qy] - q[:, qz] * q[:, qz]
+    yaw = torch.atan2(siny_cosp, cosy_cosp)
+    return roll % (2 * np.pi), pitch % (2 * np.pi), yaw % (2 * np.pi)
+
+
+def _torch_rand_float(lower, upper, shape, device):
+    return (upper - lower) * torch.rand(*shape, device=device) + lower
+
+
+def _to_torch(x, dtype=torch.float, device="cpu", requires_grad=False):
+    return torch.tensor(x, dtype=dtype, device=device, requires_grad=requires_grad)
+
+
+def _get_axis_params(value, axis_idx, x_value=0.0, dtype=float, n_dims=3):
+    zs = np.zeros((n_dims,))
+    zs[axis_idx] = 1.0
+    params = np.where(zs == 1.0, value, zs)
+    params[0] = x_value
+    return list(params.astype(dtype))
+
+
+def _normalize(x, eps: float = 1e-9):
+    return x / x.norm(p=2, dim=-1).clamp(min=eps, max=None).unsqueeze(-1)
+
+
+def install_isaacgym_stub():
+    if "isaacgym" in sys.modules:
+        return
+    tu = types.ModuleType("isaacgym.torch_utils")
+    tu.quat_rotate_inverse = _quat_rotate_inverse
+    tu.quat_apply = _quat_apply
+    tu.get_euler_xyz = _get_euler_xyz
+    tu.torch_rand_float = _torch_rand_float
+    tu.to_torch = _to_torch
+    tu.get_axis_params = _get_axis_params
+    tu.normalize = _normalize
+    tu.__all__ = ["quat_rotate_inverse", "quat_apply", "get_euler_xyz", "torch_rand_float",
+                  "to_torch", "get_axis_params", "normalize"]
+    gymtorch = types.ModuleType("isaacgym.gymtorch")
+    gymtorch.wrap_tensor = lambda t: t
+    gymtorch.unwrap_tensor = lambda t: t
+    pkg = types.ModuleType("isaacgym")
+    pkg.torch_utils, pkg.gymtorch = tu, gymtorch
+    for name in ("gymapi", "gymutil", "terrain_utils"):
+        m = MagicMock(name=f"isaacgym.{name}")
+        setattr(pkg, name, m)
+        sys.modules[f"isaacgym.{name}"] = m
+    sys.modules["isaacgym"] = pkg
+    sys.modules["isaacgym.torch_utils"] = tu
+    sys.modules["isaacgym.gymtorch"] = gymtorch
+    for name in ("matplotlib", "matplotlib.pyplot"):   # utils/logger.py:32 imports pyplot
+        try:
+            __import__(name)
+        except ImportError:
+            sys.modules[name] = MagicMock(name=name)
+    if REFERENCE_ROOT not in sys.path:
+        sys.path.insert(0, REFERENCE_ROOT)
+
+
+# --------------------------------------------------------------------------------------
+# Reference env built on synthetic gym tensors
+# --------------------------------------------------------------------------------------
+DOF_NAMES = ["L_hip_joint", "L_hip_roll_joint", "L_thigh_joint", "L_calf_joint", "L_toe_joint",
+             "R_hip_joint", "R_hip_roll_joint", "R_thigh_joint", "R_calf_joint", "R_toe_joint"]
+EFFORT = [33.5, 33.5, 33.5, 67.0, 33.5] * 2     # robot.urdf:124,166,217,291,320
+
+
+class ReferenceEnv:
+    """The reference HectorFreeEnv, stepping on supplied physics frames and noise tapes."""
+
+    def __init__(self, statics, first_frame, first_noise):
+        install_isaacgym_stub()
+        from humanoid.envs.custom.hector_env import HectorFreeEnv
+        from humanoid.envs.custom.hector_config import HectorCfg
+        import humanoid.envs.base.legged_robot as lr_mod
+        import humanoid.envs.custom.hector_env as he_mod
+        self._mods = (lr_mod, he_mod)
+
+        n = statics.p_gains.shape[0]
+        e = HectorFreeEnv.__new__(HectorFreeEnv)
+        cfg = HectorCfg()
+        cfg.env.num_envs = n
+        e.cfg = cfg
+        e.sim_params = types.SimpleNamespace(dt=cfg.sim.dt)
+        e.height_samples = None
+        e.debug_viz = False
+        e.init_done = False
+        e._parse_cfg(cfg)
+        # --- what BaseTask.__init__ allocates (base_task.py:43-92) ---
+        e.gym = MagicMock(name="gym")
+        e.sim = MagicMock(name="sim")
+        e.device = "cpu"
+        e.headless = True
+        e.viewer = None
+        e.num_envs = n
+        e.num_obs = cfg.env.num_observations
+        e.num_privileged_obs = cfg.env.num_privileged_obs
+        e.num_actions = cfg.env.num_actions
+        e.obs_buf = torch.zeros(n, e.num_obs)
+        e.rew_buf = torch.zeros(n)
+        e.reset_buf = torch.ones(n, dtype=torch.long)
+        e.episode_length_buf = torch.zeros(n, dtype=torch.long)
+        e.time_out_buf = torch.zeros(n, dtype=torch.bool)
+        e.privileged_obs_buf = torch.zeros(n, e.num_privileged_obs)
+        e.extras = {}
+        # --- what create_sim/_create_envs produce (hector_env.py:114-132, legged_robot.py:587-681) ---
+        e.up_axis_idx = 2
+        e.num_dof = e.num_dofs = 10
+        e.num_bodies = 11
+        e.dof_names = list(DOF_NAMES)
+        e.feet_indices = torch.tensor([5, 10], dtype=torch.long)
+        e.knee_indices = torch.tensor([4, 9], dtype=torch.long)
+        e.penalised_contact_indices = torch.tensor([0, 3, 8], dtype=torch.long)
+        e.termination_contact_indices = torch.tensor([0, 3, 8], dtype=torch.long)
+        e.torque_limits = torch.tensor(EFFORT) * cfg.safety.torque_limit
+        e.env_frictions = statics.env_frictions.clone()
+        e.body_mass = statics.body_mass.clone()
+        e.custom_origins = True
+        e.env_origins = statics.env_origins.clone()
+        e.terrain_levels = torch.zeros(n, dtype=torch.long)
+        base_init = cfg.init_state.pos + cfg.init_state.rot + cfg.init_state.lin_vel + cfg.init_state.ang_vel
+        e.base_init_state = torch.tensor(base_init, dtype=torch.float)
+        # --- gym tensors ---
+        self.root_states = first_frame.root_states.clone()
+        self.dof_state = first_frame.dof_state.clone()
+        self.contact_forces = first_frame.contact_forces.clone()
+        self.rigid_state = first_frame.rigid_state.clone()
+        e.gym.acquire_actor_root_state_tensor.return_value = self.root_states
+        e.gym.acquire_dof_state_tensor.return_value = self.dof_state
+        e.gym.acquire_net_contact_force_tensor.return_value = self.contact_forces.view(-1, 3)
+        e.gym.acquire_rigid_body_state_tensor.return_value = self.rigid_state.view(-1, 13)
+        e._init_buffers()
+        e.p_gains[:] = statics.p_gains       # constants by default; randomised for BASELINE config 3
+        e.d_gains[:] = statics.d_gains
+        e._prepare_reward_function()
+        e.init_done = True
+        self.env = e
+        self._noise = first_noise
+        self._ctx = None
+        self._install_rng_patches()
+        # HectorFreeEnv.__init__ tail (hector_env.py:48-51)
+        e.last_feet_z = 0.05
+        e.feet_height = torch.zeros((n, 2))
+        e.reset_idx(torch.tensor(range(n)))
+        with self._patched_torch_rng(first_noise):
+            e.compute_observations()
+        e.episode_length_buf[:] = statics.episode_length0   # on_policy_runner.py:103-106
+
+    # -- RNG injection -----------------------------------------------------------------
+    def _install_rng_patches(self):
+        e = self.env
+        harness = self
+
+        def tape_rand_float(lower, upper, shape, device):
+            kind, ids, col = harness._ctx
+            u = getattr(harness._noise, kind)[ids, col:col + shape[1]]
+            assert u.shape == tuple(shape), (u.shape, shape, kind)
+            harness._ctx = (kind, ids, col + shape[1])
+            return (upper - lower) * u + lower
+
+        for mod in self._mods:
+            mod.torch_rand_float = tape_rand_float
+
+        orig_resample = e._resample_commands
+        orig_reset_dofs = e._reset_dofs
+        orig_reset_root = e._reset_root_states
+        orig_push = e._push_robots
+
+        def resample(env_ids):
+            if harness._ctx is None:            # called from _post_physics_step_callback
+                harness._ctx = ("u_cmd", env_ids, 0)
+                orig_resample(env_ids)
+                harness._ctx = None
+            else:                               # called from reset_idx (ctx continues at column 12)
+                orig_resample(env_ids)
+
+        def reset_dofs(env_ids):
+            harness._ctx = ("u_reset", env_ids, 0)
+            orig_reset_dofs(env_ids)
+
+        def reset_root(env_ids):
+            orig_reset_root(env_ids)
+
+        def push():
+            harness._ctx = ("u_push", torch.arange(e.num_envs), 0)
+            orig_push()
+            harness._ctx = None
+
+        e._resample_commands = resample
+        e._reset_dofs = reset_dofs
+        e._reset_root_states = reset_root
+        e._push_robots = push
+        orig_reset_idx = type(e).reset_idx
+
+        def reset_idx(env_ids):
+            orig_reset_idx(e, env_ids)
+            harness._ctx = None
+        e.reset_idx = reset_idx
+
+    def step(self, frame, noise):
+        """One reference `step()` on the given physics frame with the given draws."""
+        self._noise = noise
+        self.root_states.copy_(frame.root_states)
+        self.dof_state.copy_(frame.dof_state)
+        self.contact_forces.copy_(frame.contact_forces)
+        self.rigid_state.copy_(frame.rigid_state)
+        with self._patched_torch_rng(noise):
+            return self.env.step(noise.actions.clone())
+
+    @staticmethod
+    @contextlib.contextmanager
+    def _patched_torch_rng(noise):
+        """Replay `torch.rand` (action delay) and `torch.randn_like` (action / obs noise)."""
+        real_rand, real_randn_like = torch.rand, torch.randn_like
+
+        def fake_rand(*shape, **kw):
+            assert tuple(shape[0]) == tuple(noise.u_delay.shape), shape
+            return noise.u_delay.clone()
+
+        def fake_randn_like(t, **kw):
+            if t.shape == noise.z_action.shape:
+                return noise.z_action.clone()
+            assert t.shape == noise.z_obs.shape, t.shape
+            return noise.z_obs.clone()
+
+        torch.rand, torch.randn_like = fake_rand, fake_randn_like
+        try:
+            yield
+        finally:
+            torch.rand, torch.randn_like = real_rand, real_randn_like
