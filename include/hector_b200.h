@@ -1,0 +1,213 @@
+/*
+ * hector_b200.h — C ABI of libhectorb200.so
+ *
+ * B200 (sm_100a) implementation of the data-parallel per-environment hot path of the
+ * DRCL-USC/isaac `hector` task (humanoid-gym / legged_gym / rsl_rl fork).  The reference is
+ * pure Python/PyTorch and has no FFI of its own; every entry point below replaces a span of
+ * the reference's Python (cited as file:line relative to /root/reference/humanoid) and is what
+ * a ctypes binding on the reference side would call (INTEGRATION.md shows the stubs).
+ *
+ * Conventions
+ *   - plain C: raw device pointers, sizes, POD structs, a CUDA stream passed as void*
+ *     (cudaStream_t; NULL = legacy default stream).  No torch types.
+ *   - every function returns HB_OK (0) or a negative hb_status; nothing throws or aborts.
+ *     hb_last_error() gives a static, thread-local message for the last failure.
+ *   - all floating tensors are fp32, row-major, and live in device memory owned by the
+ *     caller.  The gym tensors (root_states, dof_state, contact_forces, rigid_state) are
+ *     owned by PhysX and are read / written in place (envs/base/legged_robot.py:437-456).
+ *   - calls are asynchronous on `stream`; the only host-visible result is `host_count` of
+ *     hb_env_post_physics (a pinned int the kernel writes; wait on the stream before reading).
+ */
+#ifndef HECTOR_B200_H
+#define HECTOR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HB_ABI_VERSION 1
+
+typedef enum hb_status {
+    HB_OK = 0,
+    HB_ERR_BAD_ARG = -1,     /* null pointer, misaligned pointer, unsupported dimension */
+    HB_ERR_CUDA = -2,        /* cudaGetLastError() after a launch, or a failed runtime call */
+    HB_ERR_UNSUPPORTED = -3  /* device is not sm_100 / feature not built */
+} hb_status;
+
+#define HB_MAX_DOF 16
+#define HB_MAX_OBS 48
+#define HB_NUM_REWARDS 18
+#define HB_MAX_CONTACT_BODIES 4
+
+/* Reward terms in the reference's accumulation order: alphabetical, because
+ * utils/helpers.py:47 walks dir() (envs/base/legged_robot.py:517-540). */
+enum hb_reward_id {
+    HB_R_ACTION_SMOOTHNESS = 0, HB_R_BASE_ACC, HB_R_BASE_HEIGHT, HB_R_COLLISION,
+    HB_R_DEFAULT_JOINT_POS, HB_R_DOF_ACC, HB_R_DOF_VEL, HB_R_FEET_AIR_TIME,
+    HB_R_FEET_CLEARANCE, HB_R_FEET_CONTACT_FORCES, HB_R_FEET_CONTACT_NUMBER,
+    HB_R_FEET_DISTANCE, HB_R_FOOT_SLIP, HB_R_KNEE_DISTANCE, HB_R_ORIENTATION,
+    HB_R_TORQUES, HB_R_TRACKING_ANG_VEL, HB_R_TRACKING_LIN_VEL
+};
+
+/* Task constants (envs/custom/hector_config.py:4-200, resolved the way
+ * LeggedRobot._parse_cfg / _init_buffers / _prepare_reward_function do). */
+typedef struct hb_env_params {
+    int32_t abi_version;            /* = HB_ABI_VERSION */
+    int32_t num_envs;
+    int32_t num_dof;                /* 10 */
+    int32_t num_bodies;             /* 11 after collapse_fixed_joints */
+    int32_t num_single_obs;         /* 41 */
+    int32_t frame_stack;            /* 15 */
+    int32_t num_single_priv;        /* 70 */
+    int32_t c_frame_stack;          /* 15 */
+    int32_t feet[2];                /* rigid-body rows of the feet   (legged_robot.py:668-671) */
+    int32_t knees[2];               /* rigid-body rows of the knees  (:672-674) */
+    int32_t n_term;                 /* termination_contact_indices   (:680-682) */
+    int32_t term_bodies[HB_MAX_CONTACT_BODIES];
+    int32_t n_pen;                  /* penalised_contact_indices     (:676-678) */
+    int32_t pen_bodies[HB_MAX_CONTACT_BODIES];
+    int32_t max_episode_length;     /* ceil(episode_length_s / dt)   (:717-718) */
+    int32_t resample_interval;      /* int(resampling_time / dt)     (:308) */
+    int32_t heading_command;        /* commands.heading_command */
+    int32_t add_noise;              /* noise.add_noise */
+    int32_t only_positive_rewards;
+    int32_t custom_origins;         /* root xy jitter at reset (:381-384) */
+    /* control (legged_robot.py:339-355) */
+    float action_scale;
+    float clip_actions;
+    float clip_observations;
+    float action_delay;             /* domain_rand.action_delay  (hector_env.py:166) */
+    float action_noise;             /* domain_rand.action_noise  (hector_env.py:168) */
+    float default_dof_pos[HB_MAX_DOF];
+    float torque_limits[HB_MAX_DOF];
+    /* time */
+    float dt;                       /* decimation * sim.dt */
+    float cycle_time;
+    float max_episode_length_s;
+    /* uniform draws: value = span * u + lo, u in [0,1)  (isaacgym torch_rand_float) */
+    float cmd_lo[3], cmd_span[3];   /* lin_vel_x, lin_vel_y, heading */
+    float push_lin_lo, push_lin_span, push_ang_lo, push_ang_span;
+    float reset_dof_lo, reset_dof_span;   /* -0.15 .. 0.15 (legged_robot.py:366) */
+    float reset_xy_lo, reset_xy_span;     /* -1 .. 1       (:384) */
+    float base_init_state[13];
+    /* observation scaling (hector_env.py:172-254) */
+    float obs_lin_vel, obs_ang_vel, obs_dof_pos, obs_dof_vel, obs_quat;
+    float noise_level;
+    float noise_scale_vec[HB_MAX_OBS];
+    /* rewards: scale already multiplied by dt; 0 = term disabled */
+    float reward_scale[HB_NUM_REWARDS];
+    float base_height_target, min_dist, max_dist, target_feet_height, tracking_sigma, max_contact_force;
+} hb_env_params;
+
+/* Device buffers of one env shard.  Pointers marked (gym) are PhysX-owned. */
+typedef struct hb_env_buffers {
+    /* (gym) */
+    float *root_states;             /* [N,13]  pos quat(xyzw) linvel angvel */
+    float *dof_state;               /* [N*ndof,2] (pos,vel) interleaved */
+    const float *contact_forces;    /* [N,nbody,3] */
+    const float *rigid_state;       /* [N,nbody,13] */
+    /* per-env constants */
+    const float *p_gains, *d_gains; /* [N,ndof] */
+    const float *env_frictions;     /* [N,1] */
+    const float *body_mass;         /* [N,1] */
+    const float *env_origins;       /* [N,3] */
+    /* env state */
+    float *actions, *last_actions, *last_last_actions;   /* [N,ndof] */
+    float *last_dof_vel;            /* [N,ndof] */
+    float *last_root_vel;           /* [N,6] */
+    float *torques;                 /* [N,ndof] */
+    float *commands;                /* [N,4] */
+    float *base_lin_vel, *base_ang_vel, *projected_gravity, *base_euler_xyz;   /* [N,3] */
+    float *feet_air_time;           /* [N,2] */
+    uint8_t *last_contacts;         /* [N,2] bool */
+    float *feet_height, *last_feet_z;   /* [N,2] */
+    float *rand_push_force, *rand_push_torque;   /* [N,3] */
+    float *episode_sums;            /* [HB_NUM_REWARDS, N] */
+    int64_t *episode_length_buf;    /* [N] */
+    uint8_t *reset_buf;             /* [N] bool */
+    uint8_t *time_out_buf;          /* [N] bool */
+    float *rew_buf;                 /* [N] */
+    /* reset compaction results */
+    int32_t *reset_env_ids;         /* [N] ascending ids of the envs reset this step */
+    int32_t *reset_count;           /* [1] device */
+    float *episode_means;           /* [HB_NUM_REWARDS] mean(episode_sums[k][ids]) / max_episode_length_s; on a step
+                                       without resets the values of episode_means_prev are carried over */
+    const float *episode_means_prev;/* [HB_NUM_REWARDS] or NULL */
+    uint8_t *time_outs_latched;     /* [N] copy of time_out_buf taken only on steps with >=1 reset (extras["time_outs"]) */
+    /* scratch: ceil(N/32) words + ceil(N/32)*HB_NUM_REWARDS floats + 1 ticket */
+    uint32_t *scratch_ballots;
+    float *scratch_partials;
+    uint32_t *scratch_ticket;
+} hb_env_buffers;
+
+/* Per-step random draws, indexed by env (NULL = that draw is not needed / treated as 0). */
+typedef struct hb_env_noise {
+    const float *u_delay;           /* [N]    torch.rand((N,1))            hector_env.py:166 */
+    const float *z_action;          /* [N,ndof] torch.randn_like(actions)  hector_env.py:168 */
+    const float *u_cmd;             /* [N,3]  command resampling           legged_robot.py:327-330 */
+    const float *u_push;            /* [N,5]  push lin xy + ang xyz        hector_env.py:58-63 */
+    const float *u_reset;           /* [N,15] dof(10) root xy(2) cmd(3)    legged_robot.py:366,384,327-330 */
+    const float *z_obs;             /* [N,41] torch.randn_like(obs_buf)    hector_env.py:241 */
+} hb_env_noise;
+
+/* stage mask for hb_env_post_physics */
+#define HB_STAGE_STEP      0x1   /* the whole of post_physics_step (legged_robot.py:118-153) */
+#define HB_STAGE_RESET_ALL 0x2   /* reset_idx(all envs) + compute_observations (hector_env.py:50-51) */
+#define HB_STAGE_PUSH      0x4   /* this is a push step (common_step_counter % push_interval == 0) */
+#define HB_STAGE_OBS       0x8   /* emit the newest frames even without HB_STAGE_STEP */
+#define HB_STAGE_RESET_MASK 0x20 /* reset_idx(env_ids): reset the envs whose reset_buf was set by the caller */
+#define HB_STAGE_DERIVE    0x10  /* _init_buffers: base_lin_vel / base_ang_vel / gravity of the initial state (:477-479) */
+
+const char *hb_last_error(void);
+int hb_abi_version(void);
+/* Number of kernels this library has launched since load / since the last reset (bench bookkeeping). */
+int64_t hb_launch_count(void);
+void hb_launch_count_reset(void);
+/* Tuning switches ("env_bulk_staging": 1 = 1-D bulk async copies (default), 0 = vector loads). */
+int hb_set_option(const char *name, int value);
+
+/* HectorFreeEnv.step prologue: clip, action delay, action noise, clip
+ * (envs/custom/hector_env.py:158-169 + envs/base/legged_robot.py:90-91).
+ * actions_in [N,ndof] -> buf->actions (which also supplies the previous actions). */
+int hb_env_action_prologue(const hb_env_params *p, const hb_env_buffers *buf, const float *actions_in,
+                           const hb_env_noise *noise, void *stream);
+
+/* LeggedRobot._compute_torques (envs/base/legged_robot.py:339-355): one decimation sub-step.
+ * Reads buf->actions, dof_state, p_gains, d_gains; writes buf->torques. */
+int hb_env_compute_torques(const hb_env_params *p, const hb_env_buffers *buf, void *stream);
+
+/* LeggedRobot.post_physics_step without the observation stacking
+ * (envs/base/legged_robot.py:118-153,155-234,303-335,358-396; hector_env.py:53-88,256-539):
+ * derived base quantities, command resampling + heading command, push, termination, the 18
+ * reward terms, reset bookkeeping, the newest observation / privileged frames and the last_*
+ * copies.  The newest frames are written (clipped) into the last frame slot of obs_new /
+ * priv_new; hb_env_stack_observations fills the other slots.
+ * host_count: optional pinned host int that receives the reset count. */
+int hb_env_post_physics(const hb_env_params *p, const hb_env_buffers *buf, const hb_env_noise *noise,
+                        float *obs_new, float *priv_new, int32_t stages, int32_t *host_count, void *stream);
+
+/* Frame stacking of HectorFreeEnv.compute_observations + the history zeroing of reset_idx
+ * (envs/custom/hector_env.py:246-261): slots 0..S-2 of obs_new/priv_new <- slots 1..S-1 of
+ * obs_prev/priv_prev, or zeros for envs whose reset_buf is set. */
+int hb_env_stack_observations(const hb_env_params *p, const hb_env_buffers *buf,
+                              const float *obs_prev, const float *priv_prev,
+                              float *obs_new, float *priv_new, void *stream);
+
+/* RolloutStorage.compute_returns (algo/ppo/rollout_storage.py:122-136).
+ * rewards, values, returns, advantages: [T,N] fp32; dones [T,N] uint8; last_values [N].
+ * Pass 1 writes returns and the raw advantages (returns - values) and accumulates
+ * (sum, sum of squares) in fp64 into stats[0..1]; pass 2 normalises
+ * with the unbiased std.  Multi-GPU callers all-reduce `stats` between the two passes. */
+int hb_gae_returns(const float *rewards, const float *values, const uint8_t *dones, const float *last_values,
+                   float *returns, float *advantages, double *stats, int32_t T, int32_t N,
+                   float gamma, float lam, void *stream);
+int hb_gae_normalize(float *advantages, const double *stats, int64_t count, void *stream);
+/* Same, when `stats` were summed over `stat_count` samples (all ranks) and this rank holds `count`. */
+int hb_gae_normalize_n(float *advantages, const double *stats, int64_t stat_count, int64_t count, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HECTOR_B200_H */

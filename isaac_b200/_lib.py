@@ -1,0 +1,141 @@
+"""ctypes binding of libhectorb200.so (the C ABI declared in include/hector_b200.h).
+
+There is no CPU fallback: if the library is missing or the device is not sm_100,
+`load()` raises.  Structures mirror the header field by field; `load()` checks
+`sizeof` against the library so a drift between header and mirror fails loudly.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+HB_ABI_VERSION = 1
+HB_MAX_DOF = 16
+HB_MAX_OBS = 48
+HB_NUM_REWARDS = 18
+HB_MAX_CONTACT_BODIES = 4
+
+HB_STAGE_STEP = 0x1
+HB_STAGE_RESET_ALL = 0x2
+HB_STAGE_PUSH = 0x4
+HB_STAGE_OBS = 0x8
+HB_STAGE_DERIVE = 0x10
+HB_STAGE_RESET_MASK = 0x20
+
+# alphabetical = the reference's accumulation order (utils/helpers.py:47)
+REWARD_NAMES = ("action_smoothness", "base_acc", "base_height", "collision", "default_joint_pos", "dof_acc",
+                "dof_vel", "feet_air_time", "feet_clearance", "feet_contact_forces", "feet_contact_number",
+                "feet_distance", "foot_slip", "knee_distance", "orientation", "torques", "tracking_ang_vel",
+                "tracking_lin_vel")
+assert len(REWARD_NAMES) == HB_NUM_REWARDS and list(REWARD_NAMES) == sorted(REWARD_NAMES)
+
+_f, _i = C.c_float, C.c_int32
+_fp = C.c_void_p   # device pointers travel as integers
+
+
+class EnvParams(C.Structure):
+    _fields_ = [
+        ("abi_version", _i), ("num_envs", _i), ("num_dof", _i), ("num_bodies", _i),
+        ("num_single_obs", _i), ("frame_stack", _i), ("num_single_priv", _i), ("c_frame_stack", _i),
+        ("feet", _i * 2), ("knees", _i * 2),
+        ("n_term", _i), ("term_bodies", _i * HB_MAX_CONTACT_BODIES),
+        ("n_pen", _i), ("pen_bodies", _i * HB_MAX_CONTACT_BODIES),
+        ("max_episode_length", _i), ("resample_interval", _i), ("heading_command", _i), ("add_noise", _i),
+        ("only_positive_rewards", _i), ("custom_origins", _i),
+        ("action_scale", _f), ("clip_actions", _f), ("clip_observations", _f), ("action_delay", _f),
+        ("action_noise", _f),
+        ("default_dof_pos", _f * HB_MAX_DOF), ("torque_limits", _f * HB_MAX_DOF),
+        ("dt", _f), ("cycle_time", _f), ("max_episode_length_s", _f),
+        ("cmd_lo", _f * 3), ("cmd_span", _f * 3),
+        ("push_lin_lo", _f), ("push_lin_span", _f), ("push_ang_lo", _f), ("push_ang_span", _f),
+        ("reset_dof_lo", _f), ("reset_dof_span", _f), ("reset_xy_lo", _f), ("reset_xy_span", _f),
+        ("base_init_state", _f * 13),
+        ("obs_lin_vel", _f), ("obs_ang_vel", _f), ("obs_dof_pos", _f), ("obs_dof_vel", _f), ("obs_quat", _f),
+        ("noise_level", _f), ("noise_scale_vec", _f * HB_MAX_OBS),
+        ("reward_scale", _f * HB_NUM_REWARDS),
+        ("base_height_target", _f), ("min_dist", _f), ("max_dist", _f), ("target_feet_height", _f),
+        ("tracking_sigma", _f), ("max_contact_force", _f),
+    ]
+
+
+_BUFFER_FIELDS = (
+    "root_states", "dof_state", "contact_forces", "rigid_state", "p_gains", "d_gains", "env_frictions",
+    "body_mass", "env_origins", "actions", "last_actions", "last_last_actions", "last_dof_vel", "last_root_vel",
+    "torques", "commands", "base_lin_vel", "base_ang_vel", "projected_gravity", "base_euler_xyz", "feet_air_time",
+    "last_contacts", "feet_height", "last_feet_z", "rand_push_force", "rand_push_torque", "episode_sums",
+    "episode_length_buf", "reset_buf", "time_out_buf", "rew_buf", "reset_env_ids", "reset_count", "episode_means",
+    "episode_means_prev", "time_outs_latched", "scratch_ballots", "scratch_partials", "scratch_ticket")
+
+
+class EnvBuffers(C.Structure):
+    _fields_ = [(name, _fp) for name in _BUFFER_FIELDS]
+
+
+_NOISE_FIELDS = ("u_delay", "z_action", "u_cmd", "u_push", "u_reset", "z_obs")
+
+
+class EnvNoise(C.Structure):
+    _fields_ = [(name, _fp) for name in _NOISE_FIELDS]
+
+
+class HectorB200Error(RuntimeError):
+    pass
+
+
+_LIB: Optional[C.CDLL] = None
+LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libhectorb200.so")
+
+_SIGNATURES = {
+    "hb_last_error": (C.c_char_p, []),
+    "hb_abi_version": (C.c_int, []),
+    "hb_launch_count": (C.c_int64, []),
+    "hb_launch_count_reset": (None, []),
+    "hb_set_option": (C.c_int, [C.c_char_p, C.c_int]),
+    "hb_sizeof_env_params": (C.c_int, []),
+    "hb_sizeof_env_buffers": (C.c_int, []),
+    "hb_sizeof_env_noise": (C.c_int, []),
+    "hb_check_device": (C.c_int, []),
+    "hb_env_action_prologue": (C.c_int, [C.POINTER(EnvParams), C.POINTER(EnvBuffers), _fp, C.POINTER(EnvNoise), _fp]),
+    "hb_env_compute_torques": (C.c_int, [C.POINTER(EnvParams), C.POINTER(EnvBuffers), _fp]),
+    "hb_env_post_physics": (C.c_int, [C.POINTER(EnvParams), C.POINTER(EnvBuffers), C.POINTER(EnvNoise), _fp, _fp,
+                                      C.c_int32, _fp, _fp]),
+    "hb_env_stack_observations": (C.c_int, [C.POINTER(EnvParams), C.POINTER(EnvBuffers), _fp, _fp, _fp, _fp, _fp]),
+    "hb_gae_returns": (C.c_int, [_fp, _fp, _fp, _fp, _fp, _fp, _fp, C.c_int32, C.c_int32, C.c_float, C.c_float, _fp]),
+    "hb_gae_normalize": (C.c_int, [_fp, _fp, C.c_int64, _fp]),
+    "hb_gae_normalize_n": (C.c_int, [_fp, _fp, C.c_int64, C.c_int64, _fp]),
+}
+
+
+def load(check_device: bool = False) -> C.CDLL:
+    """Load the shared library (raises if it has not been built: no fallback exists)."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise HectorB200Error(
+                f"{LIB_PATH} is missing: build it with `python -m isaac_b200.build` "
+                "(the env/GAE/PPO hot path has no CPU or eager-torch fallback)")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(lib, name)      # AttributeError = symbol missing = broken build
+            fn.restype, fn.argtypes = res, args
+        if lib.hb_abi_version() != HB_ABI_VERSION:
+            raise HectorB200Error("ABI version mismatch between libhectorb200.so and isaac_b200/_lib.py")
+        for fn, cls in ((lib.hb_sizeof_env_params, EnvParams), (lib.hb_sizeof_env_buffers, EnvBuffers),
+                        (lib.hb_sizeof_env_noise, EnvNoise)):
+            if fn() != C.sizeof(cls):
+                raise HectorB200Error(f"struct {cls.__name__}: header says {fn()} bytes, ctypes mirror {C.sizeof(cls)}")
+        _LIB = lib
+    if check_device:
+        check(_LIB.hb_check_device(), "hb_check_device")
+    return _LIB
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = _LIB.hb_last_error().decode() if _LIB is not None else ""
+        raise HectorB200Error(f"{what} failed (status {rc}): {msg}")
+
+
+def exported_symbols():
+    return tuple(_SIGNATURES)

@@ -1,0 +1,124 @@
+"""`RolloutStorage` with the reference's interface (algo/ppo/rollout_storage.py:35-182); GAE runs
+in the CUDA scan kernel `hb_gae_returns` + `hb_gae_normalize` (C ABI, include/hector_b200.h).
+
+Layout: time-major `[T, N, ·]` fp32 tensors in HBM like the reference.  The observation
+buffers keep a padded leading dimension (616 / 1052 floats) so that every row starts on a
+16-byte boundary — the alignment TMA tensor maps need for the MLP GEMMs — and expose
+`[T, N, 615]` / `[T, N, 1050]` views under the reference's attribute names.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from .. import _lib
+
+
+def _pad4(n: int) -> int:
+    return (n + 3) // 4 * 4
+
+
+def gae_compute_returns(rewards, values, dones, last_values, returns, advantages, gamma, lam,
+                        stats: Optional[torch.Tensor] = None, reduce_stats=None):
+    """rollout_storage.py:122-136 on `[T,N,1]` (or `[T,N]`) CUDA tensors, in place into returns/advantages.
+    `reduce_stats(stats, count) -> count` lets a multi-GPU caller all-reduce (sum, sum sq) and the
+    sample count across ranks before the normalisation pass."""
+    lib = _lib.load()
+    T, N = rewards.shape[0], rewards.shape[1]
+    for t in (rewards, values, dones, last_values, returns, advantages):
+        if not (t.is_cuda and t.is_contiguous()):
+            raise ValueError("gae_compute_returns needs contiguous CUDA tensors")
+    if dones.dtype not in (torch.uint8, torch.bool):
+        raise TypeError("dones must be uint8/bool")
+    if stats is None:
+        stats = torch.empty(2, dtype=torch.float64, device=rewards.device)
+    st = torch.cuda.current_stream(rewards.device).cuda_stream
+    _lib.check(lib.hb_gae_returns(rewards.data_ptr(), values.data_ptr(), dones.data_ptr(), last_values.data_ptr(),
+                                  returns.data_ptr(), advantages.data_ptr(), stats.data_ptr(), T, N,
+                                  float(gamma), float(lam), st), "hb_gae_returns")
+    count = T * N                       # samples behind `stats` (all ranks after reduce_stats)
+    if reduce_stats is not None:
+        count = reduce_stats(stats, count)
+    if count > 1:
+        _lib.check(lib.hb_gae_normalize_n(advantages.data_ptr(), stats.data_ptr(), int(count), T * N, st),
+                   "hb_gae_normalize_n")
+    return returns, advantages
+
+
+class RolloutStorage:
+    class Transition:
+        def __init__(self):
+            self.observations = None
+            self.critic_observations = None
+            self.actions = None
+            self.rewards = None
+            self.dones = None
+            self.values = None
+            self.actions_log_prob = None
+            self.action_mean = None
+            self.action_sigma = None
+            self.hidden_states = None
+
+        def clear(self):
+            self.__init__()
+
+    def __init__(self, num_envs, num_transitions_per_env, obs_shape, privileged_obs_shape, actions_shape,
+                 device="cuda:0"):
+        self.device = device
+        self.obs_shape, self.privileged_obs_shape, self.actions_shape = obs_shape, privileged_obs_shape, actions_shape
+        T, N = num_transitions_per_env, num_envs
+        z = lambda *s, **kw: torch.zeros(*s, device=device, **kw)
+        self.obs_ld = _pad4(obs_shape[0])
+        self._observations = z(T, N, self.obs_ld)
+        self.observations = self._observations[..., :obs_shape[0]]
+        if privileged_obs_shape[0] is not None:
+            self.priv_ld = _pad4(privileged_obs_shape[0])
+            self._privileged_observations = z(T, N, self.priv_ld)
+            self.privileged_observations = self._privileged_observations[..., :privileged_obs_shape[0]]
+        else:
+            self.privileged_observations = None
+        self.rewards = z(T, N, 1)
+        self.actions = z(T, N, *actions_shape)
+        self.dones = z(T, N, 1, dtype=torch.uint8)
+        self.actions_log_prob = z(T, N, 1)
+        self.values = z(T, N, 1)
+        self.returns = z(T, N, 1)
+        self.advantages = z(T, N, 1)
+        self.mu = z(T, N, *actions_shape)
+        self.sigma = z(T, N, *actions_shape)
+        self.num_transitions_per_env, self.num_envs = T, N
+        self.saved_hidden_states_a = self.saved_hidden_states_c = None
+        self.step = 0
+        self.reduce_stats = None          # set by the multi-GPU wrapper
+
+    def add_transitions(self, transition: "RolloutStorage.Transition"):
+        if self.step >= self.num_transitions_per_env:
+            raise AssertionError("Rollout buffer overflow")
+        t = self.step
+        self.observations[t].copy_(transition.observations)
+        if self.privileged_observations is not None:
+            self.privileged_observations[t].copy_(transition.critic_observations)
+        self.actions[t].copy_(transition.actions)
+        self.rewards[t].copy_(transition.rewards.view(-1, 1))
+        self.dones[t].copy_(transition.dones.view(-1, 1))
+        self.values[t].copy_(transition.values)
+        self.actions_log_prob[t].copy_(transition.actions_log_prob.view(-1, 1))
+        self.mu[t].copy_(transition.action_mean)
+        self.sigma[t].copy_(transition.action_sigma)
+        self.step += 1
+
+    def clear(self):
+        self.step = 0
+
+    def compute_returns(self, last_values, gamma, lam):
+        gae_compute_returns(self.rewards, self.values, self.dones, last_values.contiguous(), self.returns,
+                            self.advantages, gamma, lam, reduce_stats=self.reduce_stats)
+
+    def get_statistics(self):
+        done = self.dones
+        done[-1] = 1
+        flat_dones = done.permute(1, 0, 2).reshape(-1, 1)
+        done_indices = torch.cat((flat_dones.new_tensor([-1], dtype=torch.int64), flat_dones.nonzero(as_tuple=False)[:, 0]))
+        trajectory_lengths = done_indices[1:] - done_indices[:-1]
+        return trajectory_lengths.float().mean(), self.rewards.mean()

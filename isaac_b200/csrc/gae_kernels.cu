@@ -1,0 +1,156 @@
+// GAE: RolloutStorage.compute_returns, algo/ppo/rollout_storage.py:122-136.
+//
+//   delta_t = r_t + (nnt_t*gamma) * V_{t+1} - V_t,  A_t = delta_t + ((nnt_t*gamma)*lam) * A_{t+1},
+//   returns_t = A_t + V_t, advantages = (returns - V) normalised by mean / unbiased std over T*N.
+//
+// Layout [T, N]: time-major, so a (t, 32 envs) row is one 128-byte line.  The recurrence
+// A_t = d_t + c_t*A_{t+1} is a first-order linear scan over t: composing the affine maps
+// (c, d) is associative, so one warp scans 32 time steps of one env with 5 shuffle rounds.
+// A CTA takes a tile of 32 envs: the [T x 32] slab is loaded row by row (coalesced) into
+// shared memory, every warp scans envs of the tile (lane = time step, chunks of 32 steps with a
+// carry for T > 32), results go back through shared memory and are written row by row.
+// Compiled with --fmad=false (same op sequence as the reference within one step).
+#include "hb_common.cuh"
+
+namespace {
+
+constexpr int ENVS = 32;       // envs per CTA tile
+constexpr int WARPS = 8;
+
+__global__ void __launch_bounds__(WARPS * 32)
+gae_scan_kernel(const float *__restrict__ rewards, const float *__restrict__ values,
+                const uint8_t *__restrict__ dones, const float *__restrict__ last_values,
+                float *__restrict__ returns, float *__restrict__ advantages, double *__restrict__ stats, int T, int N,
+                float gamma, float lam) {
+    extern __shared__ float sm[];
+    // per (t, e): c = nnt*gamma*lam (scan multiplier), d = delta; then overwritten with A_t
+    float *sc = sm;                       // [T][ENVS+1]
+    float *sd = sm + (size_t)T * (ENVS + 1);
+    float *sv = sd + (size_t)T * (ENVS + 1);
+    __shared__ double red[2][WARPS];
+    const int env0 = blockIdx.x * ENVS;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int e = env0 + lane;
+    const bool ok = e < N;
+
+    // phase 1: coalesced loads; lane = env, warps stride over t
+    for (int t = warp; t < T; t += WARPS) {
+        float r = 0.f, v = 0.f, vn = 0.f, nnt = 0.f;
+        if (ok) {
+            const size_t i = (size_t)t * N + e;
+            r = rewards[i];
+            v = values[i];
+            vn = (t == T - 1) ? last_values[e] : values[i + N];
+            nnt = 1.0f - (float)dones[i];
+        }
+        const float g = nnt * gamma;
+        sd[t * (ENVS + 1) + lane] = (r + g * vn) - v;
+        sc[t * (ENVS + 1) + lane] = g * lam;
+        sv[t * (ENVS + 1) + lane] = v;
+    }
+    __syncthreads();
+
+    // phase 2: lane = time step (reversed so that the scan runs from T-1 down to 0)
+    for (int el = warp; el < ENVS; el += WARPS) {
+        float carry = 0.0f;                                   // A_{t+1} entering the chunk
+        for (int base = 0; base < T; base += 32) {
+            const int k = base + lane;                        // k-th step counted from the end
+            const int t = T - 1 - k;
+            float c = 0.f, d = 0.f;
+            if (k < T) c = sc[t * (ENVS + 1) + el], d = sd[t * (ENVS + 1) + el];
+            // inclusive scan of affine maps f_k(x) = d + c*x composed as f_k o f_{k-1} ... : result (C, D)
+            float C = c, D = d;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const float Cp = __shfl_up_sync(0xffffffffu, C, o);
+                const float Dp = __shfl_up_sync(0xffffffffu, D, o);
+                if (lane >= o) {
+                    D = D + C * Dp;
+                    C = C * Cp;
+                }
+            }
+            const float A = D + C * carry;
+            if (k < T) sd[t * (ENVS + 1) + el] = A;
+            carry = __shfl_sync(0xffffffffu, A, 31);
+        }
+    }
+    __syncthreads();
+
+    // phase 3: coalesced stores + statistics of the raw advantages
+    double s1 = 0.0, s2 = 0.0;
+    for (int t = warp; t < T; t += WARPS) {
+        if (ok) {
+            const size_t i = (size_t)t * N + e;
+            const float v = sv[t * (ENVS + 1) + lane];
+            const float ret = sd[t * (ENVS + 1) + lane] + v;
+            const float adv = ret - v;
+            returns[i] = ret;
+            advantages[i] = adv;
+            s1 += (double)adv;
+            s2 += (double)adv * (double)adv;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    if (lane == 0) red[0][warp] = s1, red[1][warp] = s2;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0.0, q = 0.0;
+        for (int w = 0; w < WARPS; ++w) a += red[0][w], q += red[1][w];
+        atomicAdd(stats, a);
+        atomicAdd(stats + 1, q);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+gae_normalize_kernel(float *__restrict__ adv, const double *__restrict__ stats, long long stat_count,
+                     long long count) {
+    // mean and unbiased std from (sum, sum of squares), rollout_storage.py:136
+    const double n = (double)stat_count;
+    const double mean = stats[0] / n;
+    double var = (stats[1] - n * mean * mean) / (n - 1.0);
+    if (var < 0.0) var = 0.0;
+    const float m = (float)mean;
+    const float denom = (float)sqrt(var) + 1e-8f;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) adv[i] = (adv[i] - m) / denom;
+}
+
+}  // namespace
+
+extern "C" {
+
+int hb_gae_returns(const float *rewards, const float *values, const uint8_t *dones, const float *last_values,
+                   float *returns, float *advantages, double *stats, int32_t T, int32_t N, float gamma, float lam,
+                   void *stream) {
+    HB_REQUIRE(rewards && values && dones && last_values && returns && advantages && stats, "hb_gae_returns: null buffer");
+    HB_REQUIRE(T > 0 && N > 0, "hb_gae_returns: T and N must be positive");
+    const size_t smem = (size_t)3 * T * (ENVS + 1) * sizeof(float);
+    HB_REQUIRE(smem <= 200 * 1024, "hb_gae_returns: T=%d too long for one tile", T);
+    cudaStream_t st = (cudaStream_t)stream;
+    HB_CUDA(cudaMemsetAsync(stats, 0, 2 * sizeof(double), st));
+    if (smem > 48 * 1024) {
+        HB_CUDA(cudaFuncSetAttribute(gae_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+    gae_scan_kernel<<<(N + ENVS - 1) / ENVS, WARPS * 32, smem, st>>>(rewards, values, dones, last_values, returns,
+                                                                     advantages, stats, T, N, gamma, lam);
+    HB_CHECK_LAUNCH("gae_scan_kernel");
+    return HB_OK;
+}
+
+int hb_gae_normalize_n(float *advantages, const double *stats, int64_t stat_count, int64_t count, void *stream) {
+    HB_REQUIRE(advantages && stats && stat_count > 1 && count > 0, "hb_gae_normalize: bad arguments");
+    gae_normalize_kernel<<<(int)((count + 255) / 256), 256, 0, (cudaStream_t)stream>>>(advantages, stats, stat_count,
+                                                                                     count);
+    HB_CHECK_LAUNCH("gae_normalize_kernel");
+    return HB_OK;
+}
+
+int hb_gae_normalize(float *advantages, const double *stats, int64_t count, void *stream) {
+    return hb_gae_normalize_n(advantages, stats, count, count, stream);
+}
+
+}  // extern "C"

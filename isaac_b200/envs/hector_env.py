@@ -1,0 +1,399 @@
+"""`HectorFreeEnvB200` — drop-in for the reference's `HectorFreeEnv` / `LeggedRobot` hot path.
+
+Same contract as the reference env (algo/vec_env.py:37-60; envs/base/legged_robot.py:84-153;
+envs/custom/hector_env.py:158-261):
+
+    step(actions[N,10]) -> obs[N,615], privileged_obs[N,1050], rew[N], reset[N] bool, extras
+    reset() -> obs, privileged_obs;  get_observations();  get_privileged_observations()
+
+and the same attribute names the runner and `play.py` read (dof_pos, dof_vel, torques,
+commands, base_lin_vel, base_ang_vel, contact_forces, feet_indices, episode_sums, ...).
+The per-step work is four kinds of kernel launch through the C ABI (include/hector_b200.h):
+
+    hb_env_action_prologue      x1   hector_env.py:158-169
+    hb_env_compute_torques      x decimation, around the opaque physics.simulate()
+    hb_env_post_physics         x1   legged_robot.py:118-234,303-396 + newest obs frames
+    hb_env_stack_observations   x1   hector_env.py:246-261 (frame stacking, ping-pong buffers)
+
+There is no torch/eager fallback: without libhectorb200.so construction fails.
+`step()` never blocks on the GPU; the one host-visible value the reference needs (the reset
+count for `gym.set_*_tensor_indexed`) is written to pinned memory by the kernel and consumed
+right before the next `physics.simulate()`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from .. import _lib
+from .._lib import (EnvBuffers, EnvNoise, EnvParams, HB_NUM_REWARDS, HB_STAGE_DERIVE, HB_STAGE_OBS, HB_STAGE_PUSH,
+                    HB_STAGE_RESET_ALL, HB_STAGE_RESET_MASK, HB_STAGE_STEP, REWARD_NAMES)
+from .hector_config import class_to_dict
+
+_EXTRAS_RING = 256       # >= num_steps_per_env: episode-mean slots handed out through extras["episode"]
+
+
+def _find(names, patterns):
+    return [i for p in patterns for i, s in enumerate(names) if p in s]
+
+
+def build_env_params(cfg, num_envs: int, num_bodies: int, body_names, dof_names, dof_effort) -> EnvParams:
+    """Resolve the config the way LeggedRobot._parse_cfg / _init_buffers / _prepare_reward_function /
+    _get_noise_scale_vec do (legged_robot.py:433-540,711-722; hector_env.py:135-155); Python-double
+    arithmetic first, fp32 at the end, exactly like scalars reach torch kernels in the reference."""
+    p = EnvParams()
+    p.abi_version = _lib.HB_ABI_VERSION
+    p.num_envs, p.num_dof, p.num_bodies = num_envs, cfg.env.num_actions, num_bodies
+    p.num_single_obs, p.frame_stack = cfg.env.num_single_obs, cfg.env.frame_stack
+    p.num_single_priv, p.c_frame_stack = cfg.env.single_num_privileged_obs, cfg.env.c_frame_stack
+    feet = _find(body_names, [cfg.asset.foot_name])
+    knees = _find(body_names, [cfg.asset.knee_name])
+    term = _find(body_names, cfg.asset.terminate_after_contacts_on)
+    pen = _find(body_names, cfg.asset.penalize_contacts_on)
+    if len(feet) != 2 or len(knees) != 2:
+        raise ValueError(f"hector layout expects 2 feet and 2 knees, found {feet} / {knees}")
+    if len(term) > _lib.HB_MAX_CONTACT_BODIES or len(pen) > _lib.HB_MAX_CONTACT_BODIES:
+        raise ValueError("too many termination / penalised contact bodies")
+    p.feet[:], p.knees[:] = feet, knees
+    p.n_term, p.n_pen = len(term), len(pen)
+    for i, b in enumerate(term):
+        p.term_bodies[i] = b
+    for i, b in enumerate(pen):
+        p.pen_bodies[i] = b
+    dt = cfg.control.decimation * cfg.sim.dt
+    p.dt = dt
+    p.max_episode_length = int(np.ceil(cfg.env.episode_length_s / dt))
+    p.max_episode_length_s = cfg.env.episode_length_s
+    p.resample_interval = int(cfg.commands.resampling_time / dt)
+    p.heading_command = int(cfg.commands.heading_command)
+    p.add_noise = int(cfg.noise.add_noise)
+    p.only_positive_rewards = int(cfg.rewards.only_positive_rewards)
+    p.custom_origins = int(cfg.terrain.mesh_type in ("heightfield", "trimesh"))
+    p.action_scale = cfg.control.action_scale
+    p.clip_actions = cfg.normalization.clip_actions
+    p.clip_observations = cfg.normalization.clip_observations
+    p.action_delay = cfg.domain_rand.action_delay
+    p.action_noise = cfg.domain_rand.action_noise
+    for j, name in enumerate(dof_names):
+        p.default_dof_pos[j] = cfg.init_state.default_joint_angles[name]
+        p.torque_limits[j] = dof_effort[j] * cfg.safety.torque_limit
+    p.cycle_time = cfg.rewards.cycle_time
+    r = cfg.commands.ranges
+    for k, rng in enumerate((r.lin_vel_x, r.lin_vel_y, r.heading)):
+        p.cmd_lo[k], p.cmd_span[k] = rng[0], rng[1] - rng[0]
+    dr = cfg.domain_rand
+    p.push_lin_lo, p.push_lin_span = -dr.max_push_vel_xy, dr.max_push_vel_xy - (-dr.max_push_vel_xy)
+    p.push_ang_lo, p.push_ang_span = -dr.max_push_ang_vel, dr.max_push_ang_vel - (-dr.max_push_ang_vel)
+    p.reset_dof_lo, p.reset_dof_span = -0.15, 0.15 - (-0.15)
+    p.reset_xy_lo, p.reset_xy_span = -1.0, 1.0 - (-1.0)
+    init = cfg.init_state.pos + cfg.init_state.rot + cfg.init_state.lin_vel + cfg.init_state.ang_vel
+    for k in range(13):
+        p.base_init_state[k] = init[k]
+    os_ = cfg.normalization.obs_scales
+    p.obs_lin_vel, p.obs_ang_vel, p.obs_dof_pos, p.obs_dof_vel, p.obs_quat = (
+        os_.lin_vel, os_.ang_vel, os_.dof_pos, os_.dof_vel, os_.quat)
+    p.noise_level = cfg.noise.noise_level
+    ns = cfg.noise.noise_scales
+    nd = p.num_dof
+    vec = np.zeros(p.num_single_obs, dtype=np.float32)          # hector_env.py:145-155 builds it in fp32
+    vec[5:5 + nd] = ns.dof_pos * os_.dof_pos
+    vec[5 + nd:5 + 2 * nd] = ns.dof_vel * os_.dof_vel
+    vec[5 + 3 * nd:5 + 3 * nd + 3] = ns.ang_vel * os_.ang_vel
+    vec[5 + 3 * nd + 3:] = ns.quat * os_.quat
+    for k in range(p.num_single_obs):
+        p.noise_scale_vec[k] = float(vec[k])
+    scales = class_to_dict(cfg.rewards.scales)
+    unknown = [k for k, v in scales.items() if v != 0 and k not in REWARD_NAMES]
+    if unknown:
+        raise ValueError(f"reward terms without a kernel implementation have non-zero scale: {unknown}")
+    for k, name in enumerate(REWARD_NAMES):
+        p.reward_scale[k] = scales.get(name, 0.0) * dt
+    rw = cfg.rewards
+    p.base_height_target, p.min_dist, p.max_dist = rw.base_height_target, rw.min_dist, rw.max_dist
+    p.target_feet_height, p.tracking_sigma, p.max_contact_force = (
+        rw.target_feet_height, rw.tracking_sigma, rw.max_contact_force)
+    return p
+
+
+class HectorFreeEnvB200:
+    def __init__(self, cfg, sim_params=None, physics_engine=None, sim_device="cuda:0", headless=True, *,
+                 physics, statics=None, body_names=None, dof_names=None, dof_effort=None,
+                 initial_noise=None):
+        """`physics`: the opaque stage (isaac_b200.physics).  `statics`: per-env constants that the
+        reference collects while creating actors (legged_robot.py:256-301,683-709); defaults are the
+        config constants.  body/dof names default to what Isaac Gym reports for the hector URDF."""
+        self._lib = _lib.load(check_device=True)
+        self.cfg = cfg
+        self.sim_params = sim_params
+        self.physics = physics
+        self.device = torch.device(sim_device)
+        self.headless = headless
+        self.num_envs = N = physics.num_envs
+        self.num_obs = cfg.env.num_observations
+        self.num_privileged_obs = cfg.env.num_privileged_obs
+        self.num_actions = cfg.env.num_actions
+        self.num_dof = self.num_dofs = physics.num_dof
+        self.num_bodies = physics.num_bodies
+        body_names = body_names or cfg.asset.body_names
+        self.dof_names = dof_names or cfg.asset.dof_names
+        dof_effort = dof_effort or cfg.asset.dof_effort
+        self._p = build_env_params(cfg, N, self.num_bodies, body_names, self.dof_names, dof_effort)
+        # _parse_cfg (legged_robot.py:711-722)
+        self.dt = cfg.control.decimation * cfg.sim.dt
+        self.obs_scales = cfg.normalization.obs_scales
+        self.max_episode_length_s = cfg.env.episode_length_s
+        self.max_episode_length = np.ceil(self.max_episode_length_s / self.dt)
+        self.push_interval = np.ceil(cfg.domain_rand.push_interval_s / self.dt)
+        self.reward_scales = {k: v * self.dt for k, v in class_to_dict(cfg.rewards.scales).items() if v != 0}
+        self.reward_names = [k for k in self.reward_scales if k != "termination"]
+        dev, f32 = self.device, dict(dtype=torch.float32, device=self.device)
+        z = lambda *s, **kw: torch.zeros(*s, **{**f32, **kw})
+        # gym tensors (owned by the physics stage, used in place)
+        self.root_states, self.dof_state = physics.root_states, physics.dof_state
+        self.contact_forces, self.rigid_state = physics.contact_forces, physics.rigid_state
+        self.dof_pos = self.dof_state.view(N, self.num_dof, 2)[..., 0]
+        self.dof_vel = self.dof_state.view(N, self.num_dof, 2)[..., 1]
+        self.base_quat = self.root_states[:, 3:7]
+        as_idx = lambda v: torch.tensor(list(v), dtype=torch.long, device=dev)
+        self.feet_indices, self.knee_indices = as_idx(self._p.feet), as_idx(self._p.knees)
+        self.termination_contact_indices = as_idx(self._p.term_bodies[:self._p.n_term])
+        self.penalised_contact_indices = as_idx(self._p.pen_bodies[:self._p.n_pen])
+        self.torque_limits = torch.tensor(list(self._p.torque_limits[:self.num_dof]), **f32)
+        self.default_dof_pos = torch.tensor(list(self._p.default_dof_pos[:self.num_dof]), **f32).unsqueeze(0)
+        self.default_joint_pd_target = self.default_dof_pos.clone()
+        # per-env constants
+        self.p_gains, self.d_gains = z(N, self.num_dof), z(N, self.num_dof)
+        for i, name in enumerate(self.dof_names):            # legged_robot.py:485-500
+            for key in cfg.control.stiffness:
+                if key in name:
+                    self.p_gains[:, i] = cfg.control.stiffness[key]
+                    self.d_gains[:, i] = cfg.control.damping[key]
+        self.env_frictions, self.body_mass, self.env_origins = z(N, 1), z(N, 1), z(N, 3)
+        self.custom_origins = bool(self._p.custom_origins)
+        self.terrain_levels = torch.zeros(N, dtype=torch.long, device=dev)
+        if statics is not None:
+            self.p_gains.copy_(statics.p_gains), self.d_gains.copy_(statics.d_gains)
+            self.env_frictions.copy_(statics.env_frictions), self.body_mass.copy_(statics.body_mass)
+            self.env_origins.copy_(statics.env_origins)
+        # env state (legged_robot.py:458-515, base_task.py:72-92)
+        self.actions, self.last_actions, self.last_last_actions = z(N, 10), z(N, 10), z(N, 10)
+        self.last_dof_vel, self.last_root_vel, self.torques = z(N, 10), z(N, 6), z(N, 10)
+        self.commands = z(N, cfg.commands.num_commands)
+        self.commands_scale = torch.tensor([self.obs_scales.lin_vel, self.obs_scales.lin_vel, self.obs_scales.ang_vel], **f32)
+        self.base_lin_vel, self.base_ang_vel = z(N, 3), z(N, 3)
+        self.projected_gravity, self.base_euler_xyz = z(N, 3), z(N, 3)
+        self.feet_air_time, self.feet_height = z(N, 2), z(N, 2)
+        self.last_feet_z = torch.full((N, 2), 0.05, **f32)                 # hector_env.py:48
+        self.last_contacts = torch.zeros(N, 2, dtype=torch.bool, device=dev)
+        self.rand_push_force, self.rand_push_torque = z(N, 3), z(N, 3)
+        self._episode_sums = z(HB_NUM_REWARDS, N)
+        self.episode_sums = {k: self._episode_sums[i] for i, k in enumerate(REWARD_NAMES) if k in self.reward_scales}
+        self.episode_length_buf = torch.zeros(N, dtype=torch.long, device=dev)
+        self.reset_buf = torch.ones(N, dtype=torch.bool, device=dev)
+        self.time_out_buf = torch.zeros(N, dtype=torch.bool, device=dev)
+        self.rew_buf = z(N)
+        self.noise_scale_vec = torch.tensor(list(self._p.noise_scale_vec[:self._p.num_single_obs]), **f32)
+        self.add_noise = bool(cfg.noise.add_noise)
+        self.gravity_vec = torch.tensor([0.0, 0.0, -1.0], **f32).repeat(N, 1)
+        self.forward_vec = torch.tensor([1.0, 0.0, 0.0], **f32).repeat(N, 1)
+        # ping-pong observation buffers: the tensor returned by step() stays valid until the step
+        # after next (PPO.act keeps references until process_env_step, ppo.py:99-100,111)
+        self._obs = [z(N, self.num_obs), z(N, self.num_obs)]
+        self._priv = [z(N, self.num_privileged_obs), z(N, self.num_privileged_obs)]
+        self._cur = 0
+        # reset compaction + extras
+        self.reset_env_ids = torch.zeros(N, dtype=torch.int32, device=dev)
+        self._reset_count = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._host_count = torch.zeros(1, dtype=torch.int32).pin_memory() if dev.type == "cuda" else torch.zeros(1, dtype=torch.int32)
+        self._episode_means = z(_EXTRAS_RING, HB_NUM_REWARDS)
+        self._time_outs_latched = torch.zeros(N, dtype=torch.bool, device=dev)
+        tiles = (N + 31) // 32
+        self._scratch_ballots = torch.zeros(tiles, dtype=torch.int32, device=dev)
+        self._scratch_partials = z(tiles, HB_NUM_REWARDS)
+        self._scratch_ticket = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._terrain_level_mean = torch.zeros((), **f32)
+        self.extras: Dict = {}
+        self.common_step_counter = 0
+        self._step_index = 0
+        self._pending_event: Optional[torch.cuda.Event] = None
+        self._injected = initial_noise      # draws consumed by the constructor's reset_idx(all)
+        self._rng = torch.Generator(device=dev)
+        self._rng.manual_seed(0)
+        self._b = EnvBuffers()
+        self._nz = EnvNoise()
+        self._bind_buffers()
+        self.init_done = True
+        # HectorFreeEnv.__init__ tail (hector_env.py:48-51): reset_idx(all) + compute_observations,
+        # preceded by the derived quantities of _init_buffers (legged_robot.py:452,477-479)
+        self._launch_post(HB_STAGE_DERIVE | HB_STAGE_RESET_ALL | HB_STAGE_OBS)
+        self._apply_pending_resets()
+
+    # ------------------------------------------------------------------ plumbing
+    def _bind_buffers(self):
+        b = self._b
+        for name, t in dict(
+                root_states=self.root_states, dof_state=self.dof_state, contact_forces=self.contact_forces,
+                rigid_state=self.rigid_state, p_gains=self.p_gains, d_gains=self.d_gains,
+                env_frictions=self.env_frictions, body_mass=self.body_mass, env_origins=self.env_origins,
+                actions=self.actions, last_actions=self.last_actions, last_last_actions=self.last_last_actions,
+                last_dof_vel=self.last_dof_vel, last_root_vel=self.last_root_vel, torques=self.torques,
+                commands=self.commands, base_lin_vel=self.base_lin_vel, base_ang_vel=self.base_ang_vel,
+                projected_gravity=self.projected_gravity, base_euler_xyz=self.base_euler_xyz,
+                feet_air_time=self.feet_air_time, last_contacts=self.last_contacts, feet_height=self.feet_height,
+                last_feet_z=self.last_feet_z, rand_push_force=self.rand_push_force,
+                rand_push_torque=self.rand_push_torque, episode_sums=self._episode_sums,
+                episode_length_buf=self.episode_length_buf, reset_buf=self.reset_buf, time_out_buf=self.time_out_buf,
+                rew_buf=self.rew_buf, reset_env_ids=self.reset_env_ids, reset_count=self._reset_count,
+                time_outs_latched=self._time_outs_latched, scratch_ballots=self._scratch_ballots,
+                scratch_partials=self._scratch_partials, scratch_ticket=self._scratch_ticket).items():
+            if not t.is_contiguous():
+                raise ValueError(f"{name} must be contiguous")
+            setattr(b, name, t.data_ptr())
+        self._pp, self._pb, self._pn = C.byref(self._p), C.byref(self._b), C.byref(self._nz)
+
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def inject_noise(self, frame) -> None:
+        """Use the supplied draws (isaac_b200.synthetic.NoiseFrame on this device) for the next step
+        instead of the env's own generator — "noise injected as a supplied tensor"."""
+        self._injected = frame
+
+    def _draw_noise(self, push: bool):
+        N, nz = self.num_envs, self._nz
+        if self._injected is not None:
+            f = self._injected
+            self._noise_keepalive = f
+            nz.u_delay, nz.z_action = f.u_delay.data_ptr(), f.z_action.data_ptr()
+            nz.u_cmd, nz.u_push, nz.u_reset, nz.z_obs = (f.u_cmd.data_ptr(), f.u_push.data_ptr(),
+                                                         f.u_reset.data_ptr(), f.z_obs.data_ptr())
+            return
+        dev = self.device
+        nu = 18 + (5 if push else 0) + (1 if self._p.action_delay != 0.0 else 0)
+        u = torch.rand(N * nu, device=dev, generator=self._rng)
+        zn = torch.randn(N * 51, device=dev, generator=self._rng)
+        self._noise_keepalive = (u, zn)
+        base = u.data_ptr()
+        nz.u_reset, nz.u_cmd = base, base + N * 15 * 4
+        off = N * 18
+        nz.u_push = base + off * 4 if push else None
+        off += N * 5 if push else 0
+        nz.u_delay = base + off * 4 if self._p.action_delay != 0.0 else None
+        nz.z_action, nz.z_obs = zn.data_ptr(), zn.data_ptr() + N * 10 * 4
+
+    # ------------------------------------------------------------------ the hot path
+    def step(self, actions: torch.Tensor):
+        """hector_env.py:158-169 + legged_robot.py:84-108."""
+        lib, st = self._lib, self._stream()
+        actions = actions.to(self.device, dtype=torch.float32).contiguous()
+        self.common_step_counter += 1
+        push = bool(self.cfg.domain_rand.push_robots) and (self.common_step_counter % self.push_interval == 0)
+        self._draw_noise(push)
+        _lib.check(lib.hb_env_action_prologue(self._pp, self._pb, actions.data_ptr(), self._pn, st),
+                   "hb_env_action_prologue")
+        for i in range(self.cfg.control.decimation):
+            self._compute_torques()
+            self.physics.set_dof_actuation_force(self.torques)
+            if i == 0:
+                self._apply_pending_resets()      # gym.set_*_indexed of the previous step's resets
+            self.physics.simulate()
+            self.physics.refresh_dof_state()
+        self.post_physics_step(push)
+        return self.obs_buf, self.privileged_obs_buf, self.rew_buf, self.reset_buf, self.extras
+
+    def _compute_torques(self, actions=None):
+        """legged_robot.py:339-355 on self.actions (one decimation sub-step)."""
+        _lib.check(self._lib.hb_env_compute_torques(self._pp, self._pb, self._stream()), "hb_env_compute_torques")
+        return self.torques
+
+    def post_physics_step(self, push: bool = False):
+        """legged_robot.py:118-153 (termination, rewards, resets, observations, last_* copies)."""
+        self.physics.refresh_post_physics()
+        self._launch_post(HB_STAGE_STEP | (HB_STAGE_PUSH if push else 0))
+        if push:
+            self.physics.set_root_state()
+
+    def _launch_post(self, stages: int):
+        lib, st = self._lib, self._stream()
+        if self._nz.u_reset is None:
+            self._draw_noise(False)
+        prev, cur = self._cur, self._cur ^ 1
+        emit = bool(stages & (HB_STAGE_STEP | HB_STAGE_OBS))
+        slot = self._step_index % _EXTRAS_RING
+        prev_slot = (self._step_index - 1) % _EXTRAS_RING
+        self._b.episode_means = self._episode_means[slot].data_ptr()
+        self._b.episode_means_prev = self._episode_means[prev_slot].data_ptr() if self._step_index > 0 else None
+        host_count = self._host_count.data_ptr()
+        _lib.check(lib.hb_env_post_physics(self._pp, self._pb, self._pn, self._obs[cur].data_ptr(),
+                                           self._priv[cur].data_ptr(), stages, host_count, st), "hb_env_post_physics")
+        if emit:
+            _lib.check(lib.hb_env_stack_observations(self._pp, self._pb, self._obs[prev].data_ptr(),
+                                                     self._priv[prev].data_ptr(), self._obs[cur].data_ptr(),
+                                                     self._priv[cur].data_ptr(), st), "hb_env_stack_observations")
+            self._cur = cur
+        if self.device.type == "cuda":
+            self._pending_event = torch.cuda.Event()
+            self._pending_event.record(torch.cuda.current_stream(self.device))
+        means = self._episode_means[slot]
+        self.extras["episode"] = {"rew_" + k: means[i] for i, k in enumerate(REWARD_NAMES) if k in self.reward_scales}
+        if self.cfg.terrain.mesh_type == "trimesh":
+            self.extras["episode"]["terrain_level"] = self._terrain_level_mean
+        if self.cfg.env.send_timeouts:
+            self.extras["time_outs"] = self._time_outs_latched
+        self._step_index += 1
+        self._injected = None
+        self._nz.u_reset = None
+
+    def _apply_pending_resets(self):
+        """The two opaque calls of _reset_dofs/_reset_root_states (legged_robot.py:370-372,394-396) need
+        the reset count on the host; it is read from pinned memory once the producing kernel is done."""
+        if self._pending_event is None:
+            return
+        self._pending_event.synchronize()
+        self._pending_event = None
+        n = int(self._host_count[0])
+        self.last_reset_count = n
+        if n > 0:
+            self.physics.set_dof_state_indexed(self.reset_env_ids, n)
+            self.physics.set_root_state_indexed(self.reset_env_ids, n)
+
+    # ------------------------------------------------------------------ reference-named API
+    @property
+    def obs_buf(self):
+        return self._obs[self._cur]
+
+    @property
+    def privileged_obs_buf(self):
+        return self._priv[self._cur]
+
+    def get_observations(self):
+        return self.obs_buf
+
+    def get_privileged_observations(self):
+        return self.privileged_obs_buf
+
+    def reset_idx(self, env_ids):
+        """legged_robot.py:162-214 + hector_env.py:256-261 for an explicit id list (outside step())."""
+        env_ids = torch.as_tensor(env_ids, device=self.device, dtype=torch.long)
+        if env_ids.numel() == 0:
+            return
+        self.reset_buf.zero_()
+        self.reset_buf[env_ids] = True
+        self._launch_post(HB_STAGE_RESET_MASK)
+        for hist in (*self._obs, *self._priv):
+            hist[env_ids] = 0.0
+        self._apply_pending_resets()
+
+    def reset(self):
+        """legged_robot.py:111-116: reset all robots, then one step with zero actions."""
+        self.reset_idx(torch.arange(self.num_envs, device=self.device))
+        obs, priv, _, _, _ = self.step(torch.zeros(self.num_envs, self.num_actions, device=self.device))
+        return obs, priv
+
+    @property
+    def last_rigid_state(self):
+        """Never read by the hector task: materialised on demand only."""
+        return self.rigid_state.clone()

@@ -1,0 +1,168 @@
+"""TEST INFRASTRUCTURE — build-container only: writes tests/golden/*.npz.
+
+Runs the UNMODIFIED reference from /root/reference (through `oracle/ref_harness.py`) on
+seeded synthetic tapes and records what it produced.  The GPU box has no
+/root/reference; there the oracle and the CUDA path are checked against these files.
+
+    python -m oracle.make_golden            # regenerate everything
+
+Inputs are not stored: they are regenerated from the seed by
+`isaac_b200.synthetic.make_tape` / `golden_ppo_inputs` (same torch build on both
+machines); each file carries float64 checksums of the inputs so that a drift in the
+generator is reported as such instead of as a parity failure.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from isaac_b200.synthetic import make_tape  # noqa: E402
+from oracle.ppo_oracle import PARAM_ORDER, init_actor_critic_params  # noqa: E402
+
+GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+
+ENV_CASE = dict(n=32, steps=40, seed=20261018, fall_prob=0.01, step_counter0=393)
+ENV_EP0 = [2395, 2399, 2400, 795, 798, 799, 1599, 0]       # forces time-outs and command resampling
+PPO_CASE = dict(n=16, t=8, seed=11, param_seed=3)
+PPO_ALG = dict(value_loss_coef=1.0, use_clipped_value_loss=True, clip_param=0.2, entropy_coef=0.001,
+               num_learning_epochs=2, num_mini_batches=4, learning_rate=1e-3, schedule="adaptive",
+               gamma=0.994, lam=0.9, desired_kl=0.01, max_grad_norm=1.0)
+PPO_POLICY = dict(init_noise_std=1.0, actor_hidden_dims=[512, 256, 128], critic_hidden_dims=[768, 256, 128])
+
+
+def env_golden_tape():
+    c = ENV_CASE
+    tape = make_tape(c["n"], c["steps"], seed=c["seed"], fall_prob=c["fall_prob"], randomize_gains=True)
+    tape.statics.episode_length0[:len(ENV_EP0)] = torch.tensor(ENV_EP0)
+    return tape
+
+
+def tape_checksum(tape) -> np.ndarray:
+    acc = [float(t.double().sum()) for fr in tape.physics
+           for t in (fr.root_states, fr.dof_state, fr.contact_forces, fr.rigid_state)]
+    acc += [float(t.double().sum()) for nz in tape.noise
+            for t in (nz.actions, nz.u_delay, nz.z_action, nz.u_cmd, nz.u_push, nz.u_reset, nz.z_obs)]
+    acc += [float(t.double().sum()) for t in (tape.statics.p_gains, tape.statics.d_gains, tape.statics.env_frictions,
+                                              tape.statics.body_mass, tape.statics.env_origins,
+                                              tape.statics.episode_length0)]
+    return np.array(acc, dtype=np.float64)
+
+
+ENV_STATE_KEYS = ("torques", "commands", "feet_air_time", "feet_height", "last_contacts", "episode_length_buf",
+                  "last_root_vel", "last_dof_vel", "last_actions", "last_last_actions", "base_lin_vel",
+                  "base_ang_vel", "base_euler_xyz", "projected_gravity", "rand_push_force", "rand_push_torque",
+                  "actions")
+
+
+def record_env_step(rec, env_like, out, root_states, dof_state):
+    """Append one step's observable results (same recorder for reference, oracle and CUDA path)."""
+    obs, priv, rew, reset, extras = out
+    rec.setdefault("obs_frame", []).append(obs[:, -41:].numpy().copy())
+    rec.setdefault("priv_frame", []).append(priv[:, -70:].numpy().copy())
+    rec.setdefault("rew", []).append(rew.numpy().copy())
+    rec.setdefault("reset", []).append(reset.numpy().astype(np.uint8))
+    rec.setdefault("time_outs", []).append(extras["time_outs"].numpy().astype(np.uint8))
+    rec.setdefault("episode_extras", []).append(
+        np.array([float(extras["episode"]["rew_" + k]) for k in sorted(env_like.episode_sums)], dtype=np.float32))
+    rec.setdefault("episode_sums", []).append(
+        np.stack([env_like.episode_sums[k].numpy() for k in sorted(env_like.episode_sums)]))
+    rec.setdefault("root_states", []).append(root_states.numpy().copy())
+    rec.setdefault("dof_state", []).append(dof_state.numpy().copy())
+    for k in ENV_STATE_KEYS:
+        v = getattr(env_like, k)
+        rec.setdefault(k, []).append(v.numpy().astype(np.uint8 if v.dtype == torch.bool else v.numpy().dtype).copy())
+
+
+def make_env_golden():
+    from oracle.ref_harness import ReferenceEnv
+    tape = env_golden_tape()
+    ref = ReferenceEnv(tape.statics, tape.physics[0], tape.noise[0])
+    ref.env.common_step_counter = ENV_CASE["step_counter0"]
+    rec = {"obs_init": ref.env.obs_buf.numpy().copy(), "priv_init": ref.env.privileged_obs_buf.numpy().copy()}
+    for t in range(1, ENV_CASE["steps"]):
+        out = ref.step(tape.physics[t], tape.noise[t])
+        record_env_step(rec, ref.env, out, ref.root_states, ref.dof_state)
+    final = {"obs_final": out[0].numpy().copy(), "priv_final": out[1].numpy().copy()}
+    arrays = {k: (np.stack(v) if isinstance(v, list) else v) for k, v in rec.items()}
+    arrays.update(final)
+    arrays["input_checksum"] = tape_checksum(tape)
+    arrays["reward_names"] = np.array(sorted(ref.env.episode_sums))
+    path = os.path.join(GOLDEN_DIR, "env_rollout_ref.npz")
+    np.savez_compressed(path, **arrays)
+    n_reset = int(arrays["reset"].sum())
+    print(f"wrote {path}: {os.path.getsize(path) / 1e6:.2f} MB, resets={n_reset}, "
+          f"time_outs={int(arrays['time_outs'].sum())}")
+
+
+def golden_ppo_inputs():
+    """Seeded rollout inputs for the PPO golden case (regenerated on both sides)."""
+    c = PPO_CASE
+    g = torch.Generator().manual_seed(c["seed"])
+    steps = []
+    for _ in range(c["t"]):
+        obs = torch.randn(c["n"], 615, generator=g)
+        cobs = torch.randn(c["n"], 1050, generator=g)
+        eps = torch.randn(c["n"], 10, generator=g)
+        rew = torch.rand(c["n"], generator=g)
+        dones = torch.rand(c["n"], generator=g) < 0.1
+        time_outs = dones & (torch.rand(c["n"], generator=g) < 0.5)
+        steps.append((obs, cobs, eps, rew, dones, time_outs))
+    last = torch.randn(c["n"], 1050, generator=g)
+    perm = torch.randperm(c["n"] * c["t"], generator=g)
+    return steps, last, perm
+
+
+def param_digest(params) -> dict:
+    """Strided sample + float64 statistics of every tensor (keeps the fixture small)."""
+    out = {}
+    for k in PARAM_ORDER:
+        v = params[k].detach().double().flatten()
+        out[f"p/{k}/sample"] = v[::97].float().numpy()
+        out[f"p/{k}/stats"] = np.array([float(v.sum()), float(v.abs().sum()), float((v * v).sum())])
+    return out
+
+
+def make_ppo_golden():
+    from oracle.ref_harness import ReferencePPO
+    c = PPO_CASE
+    params = init_actor_critic_params(seed=c["param_seed"])
+    ref = ReferencePPO(params, c["n"], c["t"], PPO_ALG, PPO_POLICY)
+    steps, last, perm = golden_ppo_inputs()
+    arrays = {"input_checksum": np.array([float(sum(float(x.double().sum()) for x in s)) for s in steps]
+                                         + [float(last.double().sum()), float(perm.double().sum())]
+                                         + [float(params[k].double().sum()) for k in PARAM_ORDER])}
+    for obs, cobs, eps, rew, dones, tos in steps:
+        ref.act(obs, cobs, eps)
+        ref.process_env_step(rew, dones, {"time_outs": tos})
+    ref.compute_returns(last)
+    st = ref.alg.storage
+    for k in ("actions", "values", "actions_log_prob", "mu", "sigma", "rewards", "dones", "returns", "advantages"):
+        arrays["st/" + k] = getattr(st, k).numpy().copy()
+    # one fixed-lr update (continuous in its inputs) and one adaptive-lr update (quirk 10)
+    import copy
+    for tag, sched in (("fixed", "fixed"), ("adaptive", "adaptive")):
+        r = ReferencePPO(params, c["n"], c["t"], dict(PPO_ALG, schedule=sched), PPO_POLICY)
+        for obs, cobs, eps, rew, dones, tos in steps:
+            r.act(obs, cobs, eps)
+            r.process_env_step(rew, dones, {"time_outs": tos})
+        r.compute_returns(last)
+        losses = r.update(perm)
+        arrays[f"{tag}/losses"] = np.array(losses, dtype=np.float64)
+        arrays[f"{tag}/lr"] = np.array([r.alg.learning_rate], dtype=np.float64)
+        for k, v in param_digest(dict(r.alg.actor_critic.state_dict())).items():
+            arrays[f"{tag}/{k}"] = v
+    path = os.path.join(GOLDEN_DIR, "ppo_update_ref.npz")
+    np.savez_compressed(path, **arrays)
+    print(f"wrote {path}: {os.path.getsize(path) / 1e6:.2f} MB")
+
+
+if __name__ == "__main__":
+    os.makedirs(GOLDEN_DIR, exist_ok=True)
+    make_env_golden()
+    make_ppo_golden()

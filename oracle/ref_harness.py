@@ -300,3 +300,62 @@ class ReferenceEnv:
             yield
         finally:
             torch.rand, torch.randn_like = real_rand, real_randn_like
+
+
+# --------------------------------------------------------------------------------------
+# Reference PPO (rsl_rl fork) with injected draws
+# --------------------------------------------------------------------------------------
+class ReferencePPO:
+    """The reference `PPO` + `ActorCritic` + `RolloutStorage`, unmodified, on CPU.
+    `torch.normal` (the Normal.sample() draw, actor_critic.py:115-117) and `torch.randperm`
+    (rollout_storage.py:149) are replayed from supplied tensors."""
+
+    def __init__(self, params, num_envs, num_steps, alg_cfg, policy_cfg):
+        install_isaacgym_stub()
+        from humanoid.algo import PPO, ActorCritic
+        nobs = params["actor.0.weight"].shape[1]
+        npriv = params["critic.0.weight"].shape[1]
+        nact = params["std"].shape[0]
+        ac = ActorCritic(nobs, npriv, nact, **policy_cfg)
+        ac.load_state_dict({k: v.clone() for k, v in params.items()})
+        self.alg = PPO(ac, device="cpu", **alg_cfg)
+        self.alg.init_storage(num_envs, num_steps, [nobs], [npriv], [nact])
+        self._eps = None
+        self._perm = None
+
+    @contextlib.contextmanager
+    def _patched(self):
+        real_normal, real_randperm = torch.normal, torch.randperm
+        h = self
+
+        def fake_normal(mean, std, **kw):
+            eps = h._eps if (h._eps is not None and h._eps.shape == mean.shape) else torch.zeros_like(mean)
+            return mean + std * eps
+
+        def fake_randperm(n, **kw):
+            assert h._perm is not None and h._perm.numel() == n
+            return h._perm.clone()
+
+        torch.normal, torch.randperm = fake_normal, fake_randperm
+        try:
+            yield
+        finally:
+            torch.normal, torch.randperm = real_normal, real_randperm
+
+    def act(self, obs, critic_obs, eps):
+        self._eps = eps
+        with self._patched(), torch.inference_mode():
+            return self.alg.act(obs, critic_obs)
+
+    def process_env_step(self, rewards, dones, infos):
+        with torch.inference_mode():
+            self.alg.process_env_step(rewards, dones, infos)
+
+    def compute_returns(self, last_critic_obs):
+        with torch.inference_mode():
+            self.alg.compute_returns(last_critic_obs)
+
+    def update(self, perm):
+        self._perm, self._eps = perm, None
+        with self._patched():
+            return self.alg.update()

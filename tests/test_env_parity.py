@@ -1,0 +1,197 @@
+"""Parity of the CUDA env stage (through the C ABI) with the reference's outputs.
+
+- against the golden vectors the UNMODIFIED reference produced (tests/golden/env_rollout_ref.npz)
+- against the CPU oracle on fresh seeded tapes (ragged N, both staging paths)
+- size-independent properties at BASELINE sizes (frame-stack shift, ascending reset ids, ...)
+Bit-exact: termination masks, reset env_ids, episode counters.  fp32 tensors: rtol 1e-5, atol 1e-6.
+"""
+import numpy as np
+import pytest
+import torch
+
+from _util import GOLDEN, assert_close, assert_equal, to_np
+from isaac_b200.envs.hector_config import HectorCfg
+from isaac_b200.synthetic import make_tape
+from oracle import make_golden as mg
+
+pytestmark = pytest.mark.gpu
+
+EXACT = ("reset", "time_outs", "episode_length_buf", "last_contacts")
+
+
+def make_cuda_env(tape, dev, cfg=None):
+    from isaac_b200.envs.hector_env import HectorFreeEnvB200
+    from isaac_b200.physics import SyntheticPhysics
+    n = tape.statics.p_gains.shape[0]
+    phys = SyntheticPhysics(n, device=dev)
+    phys.load_frame(tape.physics[0].to(dev))
+    env = HectorFreeEnvB200(cfg or HectorCfg(), sim_device=str(dev), physics=phys, statics=tape.statics,
+                            initial_noise=tape.noise[0].to(dev))
+    env.episode_length_buf.copy_(tape.statics.episode_length0)
+    return env, phys
+
+
+def cuda_step(env, phys, frame, noise, dev):
+    phys.load_frame(frame.to(dev))
+    nz = noise.to(dev)
+    env.inject_noise(nz)
+    return env.step(nz.actions)
+
+
+class _View:
+    """Adapts the CUDA env to oracle.make_golden.record_env_step (CPU copies of its attributes)."""
+
+    def __init__(self, env):
+        self._env = env
+        self.episode_sums = {k: v.cpu() for k, v in env.episode_sums.items()}
+
+    def __getattr__(self, k):
+        return getattr(self._env, k).cpu()
+
+
+def run_cuda_case(tape, dev, step_counter0=0):
+    env, phys = make_cuda_env(tape, dev)
+    env.common_step_counter = step_counter0
+    rec = {"obs_init": to_np(env.obs_buf), "priv_init": to_np(env.privileged_obs_buf)}
+    ids_per_step, out = [], None
+    for t in range(1, len(tape.physics)):
+        out = cuda_step(env, phys, tape.physics[t], tape.noise[t], dev)
+        cpu_out = tuple(o.cpu() for o in out[:4]) + ({"time_outs": out[4]["time_outs"].cpu(),
+                                                     "episode": {k: v.cpu() for k, v in out[4]["episode"].items()}},)
+        mg.record_env_step(rec, _View(env), cpu_out, env.root_states.cpu(), env.dof_state.cpu())
+        n = int(env._reset_count.item())
+        ids_per_step.append(env.reset_env_ids[:n].cpu().numpy().copy())
+    rec = {k: (np.stack(v) if isinstance(v, list) else v) for k, v in rec.items()}
+    rec["obs_final"], rec["priv_final"] = to_np(out[0]), to_np(out[1])
+    return rec, ids_per_step, env, phys
+
+
+def compare_records(got, want):
+    for k in EXACT:
+        assert_equal(k, got[k], want[k])
+    for k in want:
+        if k in EXACT or k in ("input_checksum", "reward_names"):
+            continue
+        assert_close(k, got[k], want[k])
+
+
+@pytest.mark.parametrize("bulk", [1, 0])
+def test_env_matches_reference_golden(lib, cuda_device, bulk):
+    assert lib.hb_set_option(b"env_bulk_staging", bulk) == 0
+    g = dict(np.load(f"{GOLDEN}/env_rollout_ref.npz"))
+    tape = mg.env_golden_tape()
+    np.testing.assert_array_equal(mg.tape_checksum(tape), g["input_checksum"])
+    rec, ids, env, phys = run_cuda_case(tape, cuda_device, mg.ENV_CASE["step_counter0"])
+    compare_records(rec, g)
+    for t, got in enumerate(ids):
+        assert_equal(f"reset_env_ids@{t}", got, np.nonzero(g["reset"][t])[0].astype(np.int32))
+    assert phys.calls["set_root_state"] >= 1, "the golden case crosses a push step"
+    lib.hb_set_option(b"env_bulk_staging", 1)
+
+
+@pytest.mark.parametrize("n,bulk", [(257, 1), (257, 0), (31, 1), (1024, 1)])
+def test_env_matches_oracle_ragged(lib, cuda_device, n, bulk):
+    from oracle.hector_oracle import OracleHectorEnv
+    assert lib.hb_set_option(b"env_bulk_staging", bulk) == 0
+    steps = 12
+    tape = make_tape(n, steps, seed=1000 + n, fall_prob=0.03, randomize_gains=True)
+    tape.statics.episode_length0[:5] = torch.tensor([2399, 2400, 798, 799, 1599])
+    ora = OracleHectorEnv(HectorCfg(), tape.statics, tape.physics[0], tape.noise[0])
+    ora.common_step_counter = 395
+    want = {"obs_init": ora.obs_buf.numpy().copy(), "priv_init": ora.privileged_obs_buf.numpy().copy()}
+    want_ids, out = [], None
+    for t in range(1, steps):
+        out = ora.step(tape.physics[t], tape.noise[t])
+        mg.record_env_step(want, ora, out, ora.root_states, ora.dof_state)
+        want_ids.append(ora.last_reset_ids.numpy().astype(np.int32))
+    want = {k: (np.stack(v) if isinstance(v, list) else v) for k, v in want.items()}
+    want["obs_final"], want["priv_final"] = out[0].numpy(), out[1].numpy()
+    rec, ids, _, _ = run_cuda_case(tape, cuda_device, 395)
+    compare_records(rec, want)
+    for t, (a, b) in enumerate(zip(ids, want_ids)):
+        assert_equal(f"reset_env_ids@{t}", a, b)
+    assert sum(len(i) for i in want_ids) > 0
+    lib.hb_set_option(b"env_bulk_staging", 1)
+
+
+def test_pd_torque_law(lib, cuda_device):
+    """legged_robot.py:339-355 alone, including clipping at the URDF effort limits."""
+    from oracle.hector_oracle import OracleHectorEnv
+    tape = make_tape(1000, 2, seed=5, randomize_gains=True)
+    env, phys = make_cuda_env(tape, cuda_device)
+    ora = OracleHectorEnv(HectorCfg(), tape.statics, tape.physics[0], tape.noise[0])
+    a = 8.0 * torch.randn(1000, 10, generator=torch.Generator().manual_seed(1))
+    fr = tape.physics[1]
+    phys.load_frame(fr.to(cuda_device))
+    ora.dof_state.copy_(fr.dof_state)
+    env.actions.copy_(a)
+    tau = env._compute_torques().cpu()
+    want = ora.compute_torques(a)
+    assert_close("torques", tau.numpy(), want.numpy())
+    assert (want.abs() == ora.torque_limits).any(), "case must hit the torque limits"
+
+
+@pytest.mark.parametrize("n", [4096, 65536])
+def test_step_properties_at_baseline_sizes(lib, cuda_device, n):
+    """Size-independent properties at BASELINE.json sizes (the oracle would take minutes here)."""
+    dev = cuda_device
+    tape = make_tape(n, 3, seed=7, fall_prob=0.01)
+    env, phys = make_cuda_env(tape, dev)
+    prev_obs, prev_priv = env.obs_buf.clone(), env.privileged_obs_buf.clone()
+    for t in (1, 2):
+        ep_before = env.episode_length_buf.clone()
+        obs, priv, rew, reset, extras = cuda_step(env, phys, tape.physics[t], tape.noise[t], dev)
+        torch.cuda.synchronize()
+        keep = ~reset
+        # frame stacking: slots 0..13 are last step's slots 1..14; reset envs restart from zeros
+        assert torch.equal(obs[keep][:, :574], prev_obs[keep][:, 41:])
+        assert torch.equal(priv[keep][:, :980], prev_priv[keep][:, 70:])
+        assert (obs[reset][:, :574] == 0).all() and (priv[reset][:, :980] == 0).all()
+        # termination mask = contact on base/thigh bodies or time-out (legged_robot.py:155-160)
+        f = tape.physics[t].contact_forces.to(dev)
+        want_reset = (f[:, [0, 3, 8]].norm(dim=-1) > 1.0).any(dim=1) | (ep_before + 1 > 2400)
+        assert torch.equal(reset, want_reset)
+        # reset ids: ascending, exactly nonzero(reset); counters restart
+        cnt = int(env._reset_count.item())
+        assert cnt == int(reset.sum()) and cnt > 0
+        assert torch.equal(env.reset_env_ids[:cnt].long(), reset.nonzero().flatten())
+        assert (env.episode_length_buf[reset] == 0).all()
+        assert torch.equal(env.episode_length_buf[keep], ep_before[keep] + 1)
+        assert (rew >= 0).all() and torch.isfinite(obs).all() and torch.isfinite(priv).all()
+        assert obs.abs().max() <= 100 and priv.abs().max() <= 100
+        prev_obs, prev_priv = obs.clone(), priv.clone()
+    env._apply_pending_resets()
+    assert env.last_reset_count == cnt and phys.calls["set_dof_state_indexed"] >= 1
+
+
+def test_returned_observations_survive_the_next_step(lib, cuda_device):
+    """PPO.act keeps references to obs until process_env_step (ppo.py:99-100,111): ping-pong buffers."""
+    tape = make_tape(64, 3, seed=3)
+    env, phys = make_cuda_env(tape, cuda_device)
+    o1 = cuda_step(env, phys, tape.physics[1], tape.noise[1], cuda_device)[0]
+    snap = o1.clone()
+    o2 = cuda_step(env, phys, tape.physics[2], tape.noise[2], cuda_device)[0]
+    assert o1.data_ptr() != o2.data_ptr() and torch.equal(o1, snap)
+
+
+def test_reset_then_step_matches_reference_reset(lib, cuda_device):
+    """LeggedRobot.reset(): reset_idx(all) then step(zeros) (legged_robot.py:111-116)."""
+    from oracle.hector_oracle import OracleHectorEnv
+    tape = make_tape(96, 4, seed=11)
+    env, phys = make_cuda_env(tape, cuda_device)
+    ora = OracleHectorEnv(HectorCfg(), tape.statics, tape.physics[0], tape.noise[0])
+    cuda_step(env, phys, tape.physics[1], tape.noise[1], cuda_device)
+    ora.step(tape.physics[1], tape.noise[1])
+    # reset_idx(all) with tape 2, then a zero-action step on frame 3
+    nz2 = tape.noise[2].to(cuda_device)
+    env.inject_noise(nz2)
+    env.reset_idx(torch.arange(96))
+    ora.reset_idx(torch.arange(96), tape.noise[2])
+    import dataclasses
+    nz3 = dataclasses.replace(tape.noise[3], actions=torch.zeros(96, 10))
+    out = cuda_step(env, phys, tape.physics[3], nz3, cuda_device)
+    want = ora.step(tape.physics[3], nz3)
+    assert_close("obs", to_np(out[0]), want[0].numpy())
+    assert_close("priv", to_np(out[1]), want[1].numpy())
+    assert_close("rew", to_np(out[2]), want[2].numpy())
+    assert_equal("reset", to_np(out[3]), to_np(want[3]))
