@@ -1,0 +1,356 @@
+#!/usr/bin/env python
+"""Benchmark of the hector hot path on B200 (contract: one JSON line on stdout from rank 0).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--envs E] [--impl reference]
+
+A "step" is one `env.step(actions)` over E environments per GPU with the opaque physics stage
+stubbed: action prologue, `decimation`=10 PD-torque launches, the fused
+post-physics kernel (termination, 18 reward terms, resets, newest observation frames) and the
+frame-stacking kernel, including the reset count written to pinned host memory.
+metric = env-steps/s summed over all GPUs (weak scaling: E envs per GPU, no data-path collective).
+The same run also times GAE over [T=24, E] and reports it under "gae".
+
+value      device time: per-step CUDA events on the launching stream, all inputs resident in HBM,
+           L2 flushed between steps (a 256 MiB write outside the timed events), max over ranks.
+e2e        the public `HectorFreeEnvB200.step()` with HOST buffers: per step the physics state and the
+           actions are copied from pinned host memory, the env draws its own noise, and obs /
+           privileged obs / rewards / resets are copied back to pinned host memory; wall clock.
+roofline   the dominant kernel (privileged-observation frame stacking) against MEASURED_PEAKS.json.
+cpu_baseline / --impl reference: the CPU oracle port of the reference's torch code
+           (oracle/hector_oracle.py, torch CPU, all host threads) on the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+B_ENV_STEP = 16450          # algorithmic bytes per env-step
+FRAME_OBS, STACK_OBS, FRAME_PRIV, STACK_PRIV = 41, 15, 70, 15
+T_GAE = 24
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """SM clock + throttle reasons during the measurement (NVML; the recipe's nvidia-smi fields)."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.sm, self.sm_max, self.reasons = index, [], None, set()
+        self.stop_flag = threading.Event()
+        self.error = None
+
+    def run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.sm_max = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                nv.nvmlDeviceGetCurrentClocksThrottleReasons
+            names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+            while not self.stop_flag.is_set():
+                self.sm.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                r = get_reasons(h)
+                self.reasons |= {n for bit, n in names.items() if r & bit}
+                self.stop_flag.wait(0.02)
+        except Exception as e:          # no NVML: report it instead of inventing clocks
+            self.error = repr(e)
+
+    def summary(self):
+        self.stop_flag.set()
+        self.join(timeout=2)
+        sm = sorted(self.sm)
+        out = {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons),
+               "samples": len(sm)}
+        if self.error:
+            out["error"] = self.error
+        return out
+
+
+def make_workload(n, frames, seed):
+    from isaac_b200.synthetic import make_tape
+    return make_tape(n, frames, seed=seed, fall_prob=0.005, randomize_gains=True)
+
+
+# ------------------------------------------------------------------------------------ reference arm
+def run_reference(args, rank):
+    """The reference's own torch CPU implementation of the path, restated in oracle/ (the reference is
+    Python and cannot travel to the GPU box; oracle/hector_oracle.py is pinned bit-for-bit against it)."""
+    if rank != 0:
+        return
+    from isaac_b200.envs.hector_config import HectorCfg
+    from oracle.hector_oracle import OracleHectorEnv
+    from oracle.ppo_oracle import gae_returns
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    n = args.envs
+    frames = 4
+    tape = make_workload(n, frames, 1234)
+    env = OracleHectorEnv(HectorCfg(), tape.statics, tape.physics[0], tape.noise[0])
+    for i in range(args.warmup):
+        env.step(tape.physics[i % frames], tape.noise[i % frames])
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        env.step(tape.physics[i % frames], tape.noise[i % frames])
+    dt = time.perf_counter() - t0
+    value = n * args.steps / dt
+    g = torch.Generator().manual_seed(0)
+    r, v = torch.rand(T_GAE, n, 1, generator=g), torch.randn(T_GAE, n, 1, generator=g)
+    d, lv = (torch.rand(T_GAE, n, 1, generator=g) < 0.005).byte(), torch.randn(n, 1, generator=g)
+    gae_returns(r, v, d, lv, 0.994, 0.9)
+    t0 = time.perf_counter()
+    for _ in range(5):
+        gae_returns(r, v, d, lv, 0.994, 0.9)
+    gae_s = (time.perf_counter() - t0) / 5
+    line = {"impl": "reference", "metric": "env-steps/s", "value": value, "unit": "env-steps/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"hector task, {n} envs, env.step with stubbed physics (BASELINE configs[1])",
+                       "envs_per_gpu": n, "decimation": 10},
+            "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port",
+                             "sample": f"{args.steps} steps of {n} envs after {args.warmup} warm-up, torch CPU {torch.__version__}"},
+            "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gae": {"value": T_GAE * n / gae_s, "unit": "samples/s", "T": T_GAE},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------ B200 arm
+def cpu_baseline(n, budget_s=15.0):
+    from isaac_b200.envs.hector_config import HectorCfg
+    from oracle.hector_oracle import OracleHectorEnv
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    tape = make_workload(n, 3, 1234)
+    env = OracleHectorEnv(HectorCfg(), tape.statics, tape.physics[0], tape.noise[0])
+    for i in range(2):
+        env.step(tape.physics[i % 3], tape.noise[i % 3])
+    steps, t0 = 0, time.perf_counter()
+    while time.perf_counter() - t0 < budget_s and steps < 200:
+        env.step(tape.physics[steps % 3], tape.noise[steps % 3])
+        steps += 1
+    dt = time.perf_counter() - t0
+    return {"value": n * steps / dt, "unit": "env-steps/s", "cores": cores, "kind": "port",
+            "sample": f"{steps} steps of {n} envs ({dt:.1f} s), torch CPU oracle port, {cores} threads"}
+
+
+def run_b200(args, rank, world):
+    import torch.distributed as dist
+    from isaac_b200 import _lib
+    from isaac_b200.algo.rollout_storage import gae_compute_returns
+    from isaac_b200.envs.hector_config import HectorCfg
+    from isaac_b200.envs.hector_env import HectorFreeEnvB200
+    from isaac_b200.physics import SyntheticPhysics
+
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    lib = _lib.load(check_device=True)
+    n = args.envs
+    frames = 4
+    tape = make_workload(n, frames, 1234 + rank)
+    phys_frames = [f.to(dev) for f in tape.physics]
+    noise_frames = [f.to(dev) for f in tape.noise]
+    phys = SyntheticPhysics(n, device=dev)
+    phys.load_frame(phys_frames[0])
+    env = HectorFreeEnvB200(HectorCfg(), sim_device=str(dev), physics=phys, statics=tape.statics,
+                            initial_noise=noise_frames[0])
+    env.episode_length_buf.copy_(tape.statics.episode_length0)
+    if not args.no_graph:
+        for i in range(3):          # eager warm-up (lazy module load, cudaFuncSetAttribute) before capture
+            env.step(noise_frames[0].actions)
+        env.enable_cuda_graph()
+    flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)     # > 126 MB L2
+    stream = torch.cuda.current_stream(dev)
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+
+    def one_step(i, timed):
+        f = i % frames
+        phys.load_frame(phys_frames[f])
+        flush.fill_(float(i))
+        if args.no_graph:
+            env.inject_noise(noise_frames[f])   # eager path: noise tensors already resident in HBM
+        if timed:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+        env.step(noise_frames[f].actions)
+        if timed:
+            e1.record(stream)
+            return e0, e1
+
+    sampler = ClockSampler(local)       # samples through warm-up, the timed steps and the per-kernel timings
+    sampler.start()
+    for i in range(args.warmup):
+        one_step(i, False)
+    barrier()
+    lib.hb_launch_count_reset()
+    t0 = time.perf_counter()
+    evs = [one_step(args.warmup + i, True) for i in range(args.steps)]
+    barrier()
+    wall = time.perf_counter() - t0
+    launches = lib.hb_launch_count() + (0 if args.no_graph else args.steps * env.graph_launches_per_step)
+    dev_ms = sum(a.elapsed_time(b) for a, b in evs)
+
+    # ---- per-kernel timings for the roofline (each launch alone, L2 flushed before it) ----
+    def time_launch(fn, reps=10):
+        tot = 0.0
+        for r in range(reps + 2):
+            flush.fill_(float(r))
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            fn()
+            b.record(stream)
+            b.synchronize()
+            if r >= 2:
+                tot += a.elapsed_time(b)
+        return tot / reps
+
+    st = stream.cuda_stream
+    cur, prev = env._cur, env._cur ^ 1
+    P, B = env._pp, env._pb
+    rb = env.reset_buf.data_ptr()
+    k_priv = time_launch(lambda: lib.hb_stack_shift(env._priv[prev].data_ptr(), env._priv[cur].data_ptr(), rb, n,
+                                                    STACK_PRIV * FRAME_PRIV, FRAME_PRIV, st))
+    k_obs = time_launch(lambda: lib.hb_stack_shift(env._obs[prev].data_ptr(), env._obs[cur].data_ptr(), rb, n,
+                                                   STACK_OBS * FRAME_OBS, FRAME_OBS, st))
+    k_pd = time_launch(lambda: lib.hb_env_compute_torques(P, B, st))
+    env.inject_noise(noise_frames[0])
+    env._draw_noise(False)
+    k_post = time_launch(lambda: lib.hb_env_post_physics(P, B, env._pn, env._obs[cur].data_ptr(), env._priv[cur].data_ptr(),
+                                                         _lib.HB_STAGE_STEP, env._host_count.data_ptr(), st))
+    k_stack = time_launch(lambda: lib.hb_env_stack_observations(P, B, env._obs[prev].data_ptr(), env._priv[prev].data_ptr(),
+                                                                env._obs[cur].data_ptr(), env._priv[cur].data_ptr(), st))
+    # GAE
+    g = torch.Generator().manual_seed(rank)
+    r_, v_ = torch.rand(T_GAE, n, 1, generator=g).to(dev), torch.randn(T_GAE, n, 1, generator=g).to(dev)
+    d_, lv_ = (torch.rand(T_GAE, n, 1, generator=g) < 0.005).byte().to(dev), torch.randn(n, 1, generator=g).to(dev)
+    ret_, adv_ = torch.empty_like(r_), torch.empty_like(r_)
+    k_gae = time_launch(lambda: gae_compute_returns(r_, v_, d_, lv_, ret_, adv_, 0.994, 0.9))
+    clocks = sampler.summary()
+
+    # ---- e2e: host buffers in, host buffers out, env's own noise ----
+    host_frames = [type(f)(*(t.cpu().pin_memory() for t in (f.root_states, f.dof_state, f.contact_forces, f.rigid_state)))
+                   for f in tape.physics]
+    host_actions = [f.actions.pin_memory() for f in tape.noise]
+    out_host = [torch.empty(n, 615).pin_memory(), torch.empty(n, 1050).pin_memory(), torch.empty(n).pin_memory(),
+                torch.empty(n, dtype=torch.bool).pin_memory()]
+    act_dev = torch.empty(n, 10, device=dev)
+
+    def e2e_step(i):
+        f = i % frames
+        phys.load_frame(host_frames[f])
+        act_dev.copy_(host_actions[f], non_blocking=True)
+        out = env.step(act_dev)
+        for h, d in zip(out_host, out[:4]):
+            h.copy_(d, non_blocking=True)
+        torch.cuda.synchronize(dev)      # the caller needs the results of this step
+
+    for i in range(max(3, args.warmup)):
+        e2e_step(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        e2e_step(i)
+    barrier()
+    e2e_wall = time.perf_counter() - t0
+    h2d = sum(t.numel() * t.element_size() for t in (host_frames[0].root_states, host_frames[0].dof_state,
+                                                      host_frames[0].contact_forces, host_frames[0].rigid_state,
+                                                      host_actions[0]))
+    d2h = sum(t.numel() * t.element_size() for t in out_host)
+
+    t = torch.tensor([dev_ms, wall, e2e_wall, k_priv, k_obs, k_pd, k_gae, k_post, k_stack], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, wall, e2e_wall, k_priv, k_obs, k_pd, k_gae, k_post, k_stack = t.tolist()
+    if rank != 0:
+        return
+    peak, peak_src = peaks()
+    total_envs = n * world
+    value = total_envs * args.steps / (dev_ms * 1e-3)
+    hist_priv = n * 2 * (STACK_PRIV - 1) * FRAME_PRIV * 4          # read + write of the carried frames
+    hist_obs = n * 2 * (STACK_OBS - 1) * FRAME_OBS * 4
+    ach = hist_priv / (k_priv * 1e-3) / 1e9
+    line = {
+        "metric": "env-steps/s", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"hector task, {n} envs per GPU, env.step with stubbed physics (BASELINE configs[1])",
+                   "envs_per_gpu": n, "decimation": 10, "frame_stack": 15,
+                   "launch": "eager, noise tensors resident in HBM" if args.no_graph else
+                             "CUDA-graph replay (2 graphs/step around the reset-count hand-off), noise drawn on device inside the graph",
+                   "timing": "per-step CUDA events, L2 flushed between steps (256 MiB write outside the events)",
+                   "wall_ms_per_step_incl_flush": 1e3 * wall / args.steps},
+        "clocks": clocks,
+        "e2e": {"value": total_envs * args.steps / e2e_wall, "unit": "env-steps/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_wall / args.steps},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "kernel": "stack_shift_kernel (privileged obs, 14 carried frames of 70 floats)",
+                     "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                     "peak_source": peak_src, "algorithmic_bytes_per_launch": hist_priv,
+                     "launch_ms": k_priv},
+        "roofline_step": {"bytes_per_env_step": B_ENV_STEP, "achieved": value / world * B_ENV_STEP / 1e9,
+                          "peak": peak, "unit": "GB/s", "frac": value / world * B_ENV_STEP / 1e9 / peak},
+        "kernels": {"post_physics_ms": k_post, "stack_pair_ms": k_stack,
+                    "stack_pair_gbs": (hist_obs + hist_priv) / (k_stack * 1e-3) / 1e9,
+                    "stack_priv_ms": k_priv, "stack_obs_ms": k_obs,
+                    "stack_obs_gbs": hist_obs / (k_obs * 1e-3) / 1e9, "pd_ms": k_pd,
+                    "pd_gbs": n * 240 / (k_pd * 1e-3) / 1e9, "gae_ms": k_gae,
+                    "gae_gbs": n * T_GAE * 25 / (k_gae * 1e-3) / 1e9},
+        "gae": {"value": total_envs * T_GAE / (k_gae * 1e-3), "unit": "samples/s", "T": T_GAE},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(n)
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--envs", type=int, default=4096, help="envs per GPU")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly from Python")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", 0)))
+        dist.init_process_group("nccl")
+    try:
+        run_b200(args, rank, world)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

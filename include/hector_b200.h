@@ -99,6 +99,9 @@ typedef struct hb_env_params {
     /* rewards: scale already multiplied by dt; 0 = term disabled */
     float reward_scale[HB_NUM_REWARDS];
     float base_height_target, min_dist, max_dist, target_feet_height, tracking_sigma, max_contact_force;
+    /* get_euler_xyz_tensor / quat_rotate_inverse(gravity) of base_init_state's quaternion: what
+     * reset_idx recomputes for a freshly reset env (legged_robot.py:211-214); same for every env */
+    float reset_euler[3], reset_gravity[3];
 } hb_env_params;
 
 /* Device buffers of one env shard.  Pointers marked (gym) are PhysX-owned. */
@@ -194,6 +197,11 @@ int hb_env_post_physics(const hb_env_params *p, const hb_env_buffers *buf, const
 int hb_env_stack_observations(const hb_env_params *p, const hb_env_buffers *buf,
                               const float *obs_prev, const float *priv_prev,
                               float *obs_new, float *priv_new, void *stream);
+
+/* One frame-stack shift on its own (what hb_env_stack_observations launches twice):
+ * next[:, 0:row-frame] = reset_buf ? 0 : prev[:, frame:row]; next[:, row-frame:row] is left alone. */
+int hb_stack_shift(const float *prev, float *next, const uint8_t *reset_buf, int32_t num_envs, int32_t row,
+                   int32_t frame, void *stream);
 
 /* RolloutStorage.compute_returns (algo/ppo/rollout_storage.py:122-136).
  * rewards, values, returns, advantages: [T,N] fp32; dones [T,N] uint8; last_values [N].

@@ -56,6 +56,7 @@ class EnvParams(C.Structure):
         ("reward_scale", _f * HB_NUM_REWARDS),
         ("base_height_target", _f), ("min_dist", _f), ("max_dist", _f), ("target_feet_height", _f),
         ("tracking_sigma", _f), ("max_contact_force", _f),
+        ("reset_euler", _f * 3), ("reset_gravity", _f * 3),
     ]
 
 
@@ -101,6 +102,7 @@ _SIGNATURES = {
     "hb_env_post_physics": (C.c_int, [C.POINTER(EnvParams), C.POINTER(EnvBuffers), C.POINTER(EnvNoise), _fp, _fp,
                                       C.c_int32, _fp, _fp]),
     "hb_env_stack_observations": (C.c_int, [C.POINTER(EnvParams), C.POINTER(EnvBuffers), _fp, _fp, _fp, _fp, _fp]),
+    "hb_stack_shift": (C.c_int, [_fp, _fp, _fp, C.c_int32, C.c_int32, C.c_int32, _fp]),
     "hb_gae_returns": (C.c_int, [_fp, _fp, _fp, _fp, _fp, _fp, _fp, C.c_int32, C.c_int32, C.c_float, C.c_float, _fp]),
     "hb_gae_normalize": (C.c_int, [_fp, _fp, C.c_int64, _fp]),
     "hb_gae_normalize_n": (C.c_int, [_fp, _fp, C.c_int64, C.c_int64, _fp]),

@@ -62,26 +62,6 @@ __device__ __forceinline__ float py_mod(float a, float m) {
     return r;
 }
 
-// get_euler_xyz_tensor (envs/base/legged_robot.py:50-55) over isaacgym get_euler_xyz
-__device__ __forceinline__ Vec3 euler_xyz_wrapped(const float q[4]) {
-    const float x = q[0], y = q[1], z = q[2], w = q[3];
-    float roll = atan2f(2.0f * (w * x + y * z), ((w * w - x * x) - y * y) + z * z);
-    const float sinp = 2.0f * (w * y - z * x);
-    float pitch;
-    if (fabsf(sinp) >= 1.0f) {
-        const float sg = (sinp > 0.0f) ? 1.0f : ((sinp < 0.0f) ? -1.0f : 0.0f);
-        pitch = HALF_PI_F * sg;
-    } else {
-        pitch = asinf(sinp);
-    }
-    float yaw = atan2f(2.0f * (w * z + x * y), ((w * w + x * x) - y * y) - z * z);
-    roll = py_mod(roll, TWO_PI_F), pitch = py_mod(pitch, TWO_PI_F), yaw = py_mod(yaw, TWO_PI_F);
-    if (roll > PI_F) roll -= TWO_PI_F;
-    if (pitch > PI_F) pitch -= TWO_PI_F;
-    if (yaw > PI_F) yaw -= TWO_PI_F;
-    return {roll, pitch, yaw};
-}
-
 __device__ __forceinline__ float clampf(float v, float lo, float hi) { return fminf(fmaxf(v, lo), hi); }
 
 // ------------------------------------------------------------------------------------------
@@ -139,12 +119,28 @@ pd_torque_scalar_kernel(const float *__restrict__ dof_state, const float *__rest
 }
 
 // ------------------------------------------------------------------------------------------
-// a3-a9: post_physics_step, one warp per 32-env tile, one lane per env
+// a3-a9: post_physics_step.  One CTA = one 32-env tile, four specialised warps, lane = env.
+//
+//   warp 0 "base"    root quaternion work: base_lin_vel / base_ang_vel / projected_gravity / euler,
+//                    command resampling + heading command, push; rewards base_acc, orientation,
+//                    tracking_ang_vel, tracking_lin_vel
+//   warp 1 "joints"  dof / action terms: action_smoothness, default_joint_pos, dof_acc, dof_vel, torques
+//   warp 2 "feet"    gait phase, contacts, termination + time-out -> reset flag; base_height, collision,
+//                    feet_air_time, feet_clearance, feet_contact_forces, feet_contact_number,
+//                    feet_distance, foot_slip, knee_distance
+//   warp 3 "ledger"  episode sums; after the barrier: alphabetical reward accumulation
+//                    (legged_robot.py:216-234), reset compaction and episode means
+//
+// Every warp stays convergent (all lanes run the same code on different envs), the serial chain
+// per env is a quarter of the fused version, and each warp only fetches its own slice of code.
+// Phase A (rewards, reset flag) | barrier | phase B (reset_idx effects, newest frames, write-back)
+// | barrier | coalesced store of the frames.
 // ------------------------------------------------------------------------------------------
-struct TileLayout {          // float offsets into the warp's shared-memory tile
+struct TileLayout {          // float offsets into the CTA's shared-memory tile
     int root, dof, contact, actions, last_actions, last_last_actions, last_dof_vel, torques, last_root_vel,
-        commands, z_obs, total;
+        commands, z_obs, terms, gait_s, gait_c, flags, so, sp, total;
 };
+constexpr int PRIV_PAD = PRIV + 1;     // odd row stride: conflict-free lane-per-row writes
 
 __host__ __device__ inline TileLayout make_layout(int nbody, bool with_noise) {
     TileLayout L;
@@ -160,567 +156,582 @@ __host__ __device__ inline TileLayout make_layout(int nbody, bool with_noise) {
     L.last_root_vel = o, o += TILE * 6;
     L.commands = o, o += TILE * 4;
     L.z_obs = o, o += with_noise ? TILE * OBS : 0;
-    const int out = TILE * (OBS + PRIV);      // the frames are staged over the consumed inputs
-    L.total = o > out ? o : out;
+    L.terms = o, o += HB_NUM_REWARDS * TILE;
+    L.gait_s = o, o += TILE;
+    L.gait_c = o, o += TILE;
+    L.flags = o, o += TILE;
+    L.so = o, o += TILE * OBS;
+    L.sp = o, o += TILE * PRIV_PAD;
+    L.total = o;
     return L;
 }
 
-__device__ __forceinline__ void stage_ldg(float *dst, const float *__restrict__ src, int count, int lane, bool vec) {
-    if (vec) {
-        const float4 *s4 = reinterpret_cast<const float4 *>(src);
-        float4 *d4 = reinterpret_cast<float4 *>(dst);
-        for (int i = lane; i < count / 4; i += 32) d4[i] = __ldg(s4 + i);
+// all four warps of the tile (named barrier 1: the roles meet at different program points)
+__device__ __forceinline__ void tile_barrier() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+__device__ __forceinline__ float norm3(const float *f) { return sqrtf((f[0] * f[0] + f[1] * f[1]) + f[2] * f[2]); }
+
+// torch.remainder(a, 2*pi) for |a| < 2*pi (every angle here), general fmodf path kept out of line
+__device__ __noinline__ float py_mod_slow(float a, float m) { return py_mod(a, m); }
+__device__ __forceinline__ float mod_two_pi(float a) {
+    if (fabsf(a) < TWO_PI_F) return (a < 0.0f) ? a + TWO_PI_F : a;
+    return py_mod_slow(a, TWO_PI_F);
+}
+// get_euler_xyz_tensor (envs/base/legged_robot.py:50-55) over isaacgym get_euler_xyz
+__device__ __noinline__ Vec3 euler_xyz_wrapped_nl(float x, float y, float z, float w) {
+    float roll = atan2f(2.0f * (w * x + y * z), ((w * w - x * x) - y * y) + z * z);
+    const float sinp = 2.0f * (w * y - z * x);
+    float pitch;
+    if (fabsf(sinp) >= 1.0f) {
+        const float sg = (sinp > 0.0f) ? 1.0f : ((sinp < 0.0f) ? -1.0f : 0.0f);
+        pitch = HALF_PI_F * sg;
     } else {
-        for (int i = lane; i < count; i += 32) dst[i] = __ldg(src + i);
+        pitch = asinf(sinp);
     }
+    float yaw = atan2f(2.0f * (w * z + x * y), ((w * w + x * x) - y * y) - z * z);
+    roll = mod_two_pi(roll), pitch = mod_two_pi(pitch), yaw = mod_two_pi(yaw);
+    if (roll > PI_F) roll -= TWO_PI_F;
+    if (pitch > PI_F) pitch -= TWO_PI_F;
+    if (yaw > PI_F) yaw -= TWO_PI_F;
+    return {roll, pitch, yaw};
 }
 
 template <bool kBulk>
-__global__ void __launch_bounds__(TILE)
+__global__ void __launch_bounds__(4 * TILE)
 post_physics_kernel(const __grid_constant__ hb_env_params p, const __grid_constant__ hb_env_buffers b,
                     const __grid_constant__ hb_env_noise nz, float *__restrict__ obs_new,
                     float *__restrict__ priv_new, int stages, int32_t *host_count) {
     extern __shared__ __align__(128) float sm[];
     __shared__ __align__(8) uint64_t bar;
     __shared__ int s_is_last;
-    const int lane = threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int N = p.num_envs;
     const int env0 = blockIdx.x * TILE;
     const int nv = min(TILE, N - env0);
     const int env = env0 + lane;
     const bool valid = lane < nv;
+    const int ln = valid ? lane : 0;
     const bool do_step = stages & HB_STAGE_STEP;
-    const bool reset_all = stages & HB_STAGE_RESET_ALL;
+    const bool derive = do_step || (stages & HB_STAGE_DERIVE);
+    const bool emit_obs = do_step || (stages & HB_STAGE_OBS);
     const bool with_noise = p.add_noise && nz.z_obs != nullptr;
     const TileLayout L = make_layout(p.num_bodies, with_noise);
     const int crow = p.num_bodies * 3;
+    const float dt = p.dt;
+    const float clip = p.clip_observations;
+    float *terms = sm + L.terms;
+    float *so = sm + L.so, *sp = sm + L.sp;
+    int *flags = reinterpret_cast<int *>(sm + L.flags);
 
     // ---------------- stage the tile's input slabs into shared memory ----------------
+    const size_t e0 = env0;
     const bool full = (nv == TILE);
-    if (kBulk && full) {
-        if (lane == 0) {
-            hb::mbar_init(&bar, 1);
-            hb::fence_mbar_init();
-        }
-        __syncwarp();
-        if (lane == 0) {
-            uint32_t bytes = TILE * 4u * (13 + 2 * NDOF + crow + 5 * NDOF + 6 + 4 + (with_noise ? OBS : 0));
-            hb::mbar_expect_tx(&bar, bytes);
-            const size_t e = env0;
-            hb::bulk_g2s(sm + L.root, b.root_states + e * 13, TILE * 13 * 4, &bar);
-            hb::bulk_g2s(sm + L.dof, b.dof_state + e * NDOF * 2, TILE * NDOF * 2 * 4, &bar);
-            hb::bulk_g2s(sm + L.contact, b.contact_forces + e * crow, TILE * crow * 4, &bar);
-            hb::bulk_g2s(sm + L.actions, b.actions + e * NDOF, TILE * NDOF * 4, &bar);
-            hb::bulk_g2s(sm + L.last_actions, b.last_actions + e * NDOF, TILE * NDOF * 4, &bar);
-            hb::bulk_g2s(sm + L.last_last_actions, b.last_last_actions + e * NDOF, TILE * NDOF * 4, &bar);
-            hb::bulk_g2s(sm + L.last_dof_vel, b.last_dof_vel + e * NDOF, TILE * NDOF * 4, &bar);
-            hb::bulk_g2s(sm + L.torques, b.torques + e * NDOF, TILE * NDOF * 4, &bar);
-            hb::bulk_g2s(sm + L.last_root_vel, b.last_root_vel + e * 6, TILE * 6 * 4, &bar);
-            hb::bulk_g2s(sm + L.commands, b.commands + e * 4, TILE * 4 * 4, &bar);
-            if (with_noise) hb::bulk_g2s(sm + L.z_obs, nz.z_obs + e * OBS, TILE * OBS * 4, &bar);
-        }
-    } else {
-        const size_t e = env0;
-        stage_ldg(sm + L.root, b.root_states + e * 13, nv * 13, lane, full);
-        stage_ldg(sm + L.dof, b.dof_state + e * NDOF * 2, nv * NDOF * 2, lane, full);
-        stage_ldg(sm + L.contact, b.contact_forces + e * crow, nv * crow, lane, full);
-        stage_ldg(sm + L.actions, b.actions + e * NDOF, nv * NDOF, lane, full);
-        stage_ldg(sm + L.last_actions, b.last_actions + e * NDOF, nv * NDOF, lane, full);
-        stage_ldg(sm + L.last_last_actions, b.last_last_actions + e * NDOF, nv * NDOF, lane, full);
-        stage_ldg(sm + L.last_dof_vel, b.last_dof_vel + e * NDOF, nv * NDOF, lane, full);
-        stage_ldg(sm + L.torques, b.torques + e * NDOF, nv * NDOF, lane, full);
-        stage_ldg(sm + L.last_root_vel, b.last_root_vel + e * 6, nv * 6, lane, full);
-        stage_ldg(sm + L.commands, b.commands + e * 4, nv * 4, lane, full);
-        if (with_noise) stage_ldg(sm + L.z_obs, nz.z_obs + e * OBS, nv * OBS, lane, full);
+    const bool bulk = kBulk && full;
+    if (bulk && threadIdx.x == 0) {
+        hb::mbar_init(&bar, 1);
+        hb::fence_mbar_init();
+        hb::mbar_expect_tx(&bar, TILE * 4u * (13 + 2 * NDOF + crow + 5 * NDOF + 6 + 4 + (with_noise ? OBS : 0)));
     }
+    auto stage = [&](const float *src, int dst, int row) {
+        if (bulk) {
+            if (threadIdx.x == 0) hb::bulk_g2s(sm + dst, src, TILE * 4u * row, &bar);
+        } else {
+            const int count = nv * row;
+            for (int k = threadIdx.x; k < count; k += blockDim.x) sm[dst + k] = __ldg(src + k);
+        }
+    };
+    stage(b.root_states + e0 * 13, L.root, 13);
+    stage(b.dof_state + e0 * NDOF * 2, L.dof, NDOF * 2);
+    stage(b.contact_forces + e0 * crow, L.contact, crow);
+    stage(b.actions + e0 * NDOF, L.actions, NDOF);
+    stage(b.last_actions + e0 * NDOF, L.last_actions, NDOF);
+    stage(b.last_last_actions + e0 * NDOF, L.last_last_actions, NDOF);
+    stage(b.last_dof_vel + e0 * NDOF, L.last_dof_vel, NDOF);
+    stage(b.torques + e0 * NDOF, L.torques, NDOF);
+    stage(b.last_root_vel + e0 * 6, L.last_root_vel, 6);
+    stage(b.commands + e0 * 4, L.commands, 4);
+    if (with_noise) stage(nz.z_obs + e0 * OBS, L.z_obs, OBS);
 
-    // ---------------- per-lane direct loads that overlap the staging ----------------
-    // rigid body rows: feet pos(0:3)+lin vel(7:10), knees xy (strided 52-byte rows; 16 of 143 floats)
-    float foot_pos[2][3], foot_vel[2][3], knee_xy[2][2];
-    float sums[HB_NUM_REWARDS];
-    long long ep_len = 0;
-    float air[2], fh[2], lz[2];
+    // ---------------- per-warp global loads that overlap the staging ----------------
+    long long ep_len = 0;                       // warps 0 and 2
+    float sums[HB_NUM_REWARDS];                 // warp 3
+    float foot_pos[2][3], foot_vel[2][3], knee_xy[2][2], air[2], fh[2], lz[2];   // warp 2
     bool last_ct[2];
-    float push_f[2], push_t[3];
+    float push_f[2], push_t[3];                 // warp 0
     if (valid) {
-        const float *rs = b.rigid_state + (size_t)env * p.num_bodies * 13;
+        if (warp == 0 || warp == 2) ep_len = b.episode_length_buf[env];
+        if (warp == 0) {
+            push_f[0] = b.rand_push_force[env * 3], push_f[1] = b.rand_push_force[env * 3 + 1];
 #pragma unroll
-        for (int f = 0; f < 2; ++f) {
-            const float *r = rs + p.feet[f] * 13;
+            for (int k = 0; k < 3; ++k) push_t[k] = b.rand_push_torque[env * 3 + k];
+        } else if (warp == 2) {
+            const float *rs = b.rigid_state + (size_t)env * p.num_bodies * 13;
 #pragma unroll
-            for (int k = 0; k < 3; ++k) foot_pos[f][k] = __ldg(r + k), foot_vel[f][k] = __ldg(r + 7 + k);
-            const float *kr = rs + p.knees[f] * 13;
-            knee_xy[f][0] = __ldg(kr), knee_xy[f][1] = __ldg(kr + 1);
-            air[f] = b.feet_air_time[env * 2 + f];
-            fh[f] = b.feet_height[env * 2 + f];
-            lz[f] = b.last_feet_z[env * 2 + f];
-            last_ct[f] = b.last_contacts[env * 2 + f] != 0;
-        }
-        ep_len = b.episode_length_buf[env];
+            for (int f = 0; f < 2; ++f) {
+                const float *r = rs + p.feet[f] * 13;
 #pragma unroll
-        for (int k = 0; k < HB_NUM_REWARDS; ++k) sums[k] = b.episode_sums[(size_t)k * N + env];
-        push_f[0] = b.rand_push_force[env * 3], push_f[1] = b.rand_push_force[env * 3 + 1];
+                for (int k = 0; k < 3; ++k) foot_pos[f][k] = __ldg(r + k), foot_vel[f][k] = __ldg(r + 7 + k);
+                const float *kr = rs + p.knees[f] * 13;
+                knee_xy[f][0] = __ldg(kr), knee_xy[f][1] = __ldg(kr + 1);
+                air[f] = b.feet_air_time[env * 2 + f];
+                fh[f] = b.feet_height[env * 2 + f];
+                lz[f] = b.last_feet_z[env * 2 + f];
+                last_ct[f] = b.last_contacts[env * 2 + f] != 0;
+            }
+        } else if (warp == 3) {
 #pragma unroll
-        for (int k = 0; k < 3; ++k) push_t[k] = b.rand_push_torque[env * 3 + k];
-    }
-
-    if (kBulk && full) {
-        hb::mbar_wait(&bar, 0);
-    }
-    __syncwarp();
-
-    // ---------------- unpack this lane's rows ----------------
-    const int ln = valid ? lane : 0;
-    float root[13], q[NDOF], qd[NDOF], act[NDOF], lact[NDOF], llact[NDOF], ldv[NDOF], tau[NDOF], lrv[6], cmd[4];
-#pragma unroll
-    for (int k = 0; k < 13; ++k) root[k] = sm[L.root + ln * 13 + k];
-#pragma unroll
-    for (int j = 0; j < NDOF; ++j) {
-        q[j] = sm[L.dof + ln * NDOF * 2 + 2 * j];
-        qd[j] = sm[L.dof + ln * NDOF * 2 + 2 * j + 1];
-        act[j] = sm[L.actions + ln * NDOF + j];
-        lact[j] = sm[L.last_actions + ln * NDOF + j];
-        llact[j] = sm[L.last_last_actions + ln * NDOF + j];
-        ldv[j] = sm[L.last_dof_vel + ln * NDOF + j];
-        tau[j] = sm[L.torques + ln * NDOF + j];
-    }
-#pragma unroll
-    for (int k = 0; k < 6; ++k) lrv[k] = sm[L.last_root_vel + ln * 6 + k];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) cmd[k] = sm[L.commands + ln * 4 + k];
-    const float *cf = sm + L.contact + ln * crow;
-    float foot_f[2][3];
-#pragma unroll
-    for (int f = 0; f < 2; ++f)
-#pragma unroll
-        for (int k = 0; k < 3; ++k) foot_f[f][k] = cf[p.feet[f] * 3 + k];
-    float term_norm[HB_MAX_CONTACT_BODIES], pen_norm[HB_MAX_CONTACT_BODIES];
-#pragma unroll
-    for (int i = 0; i < HB_MAX_CONTACT_BODIES; ++i) {
-        term_norm[i] = pen_norm[i] = 0.0f;
-        if (i < p.n_term) {
-            const float *f3 = cf + p.term_bodies[i] * 3;
-            term_norm[i] = sqrtf((f3[0] * f3[0] + f3[1] * f3[1]) + f3[2] * f3[2]);
-        }
-        if (i < p.n_pen) {
-            const float *f3 = cf + p.pen_bodies[i] * 3;
-            pen_norm[i] = sqrtf((f3[0] * f3[0] + f3[1] * f3[1]) + f3[2] * f3[2]);
+            for (int k = 0; k < HB_NUM_REWARDS; ++k) sums[k] = b.episode_sums[(size_t)k * N + env];
         }
     }
-    float zobs[OBS];
+    __syncthreads();                             // mbarrier init / plain staging visible to every warp
+    if (bulk) hb::mbar_wait(&bar, 0);
+
+    // =========================================================================================
+    if (warp == 0) {
+        float root[13], cmd[4];
 #pragma unroll
-    for (int k = 0; k < OBS; ++k) zobs[k] = with_noise ? sm[L.z_obs + ln * OBS + k] : 0.0f;
-    __syncwarp();      // inputs consumed: the tile memory is reused for the output frames below
-
-    Vec3 lin = {0.f, 0.f, 0.f}, ang = {0.f, 0.f, 0.f}, grav = {0.f, 0.f, 0.f}, eul = {0.f, 0.f, 0.f};
-    bool reset = false, time_out = false;
-    float rew = 0.0f;
-    const float dt = p.dt;
-
-    if (do_step) {
-        // -------- legged_robot.py:127-135 --------
-        ep_len += 1;
+        for (int k = 0; k < 13; ++k) root[k] = sm[L.root + ln * 13 + k];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) cmd[k] = sm[L.commands + ln * 4 + k];
+        Vec3 lin = {0.f, 0.f, 0.f}, ang = {0.f, 0.f, 0.f}, grav = {0.f, 0.f, 0.f}, eul = {0.f, 0.f, 0.f};
         const float *quat = root + 3;
-        lin = quat_rotate_inverse(quat, {root[7], root[8], root[9]});
-        ang = quat_rotate_inverse(quat, {root[10], root[11], root[12]});
-        grav = quat_rotate_inverse(quat, {0.0f, 0.0f, -1.0f});
-        eul = euler_xyz_wrapped(quat);
-
-        // -------- _post_physics_step_callback, legged_robot.py:303-335 --------
-        if (valid && (ep_len % p.resample_interval) == 0 && nz.u_cmd) {
-            const float *u = nz.u_cmd + (size_t)env * 3;
-            cmd[0] = p.cmd_span[0] * u[0] + p.cmd_lo[0];
-            cmd[1] = p.cmd_span[1] * u[1] + p.cmd_lo[1];
-            cmd[3] = p.cmd_span[2] * u[2] + p.cmd_lo[2];
+        if (derive) {        // legged_robot.py:127-135 (and _init_buffers :452,477-479)
+            lin = quat_rotate_inverse(quat, {root[7], root[8], root[9]});
+            ang = quat_rotate_inverse(quat, {root[10], root[11], root[12]});
+            grav = quat_rotate_inverse(quat, {0.0f, 0.0f, -1.0f});
+        } else if (valid) {  // reset / observation-only pass: keep the stored values
+            lin = {b.base_lin_vel[env * 3], b.base_lin_vel[env * 3 + 1], b.base_lin_vel[env * 3 + 2]};
+            ang = {b.base_ang_vel[env * 3], b.base_ang_vel[env * 3 + 1], b.base_ang_vel[env * 3 + 2]};
+            grav = {b.projected_gravity[env * 3], b.projected_gravity[env * 3 + 1], b.projected_gravity[env * 3 + 2]};
+        }
+        eul = euler_xyz_wrapped_nl(quat[0], quat[1], quat[2], quat[3]);
+        if (do_step) {
+            ep_len += 1;
+            // -------- _post_physics_step_callback, legged_robot.py:303-335 --------
+            if (valid && (ep_len % p.resample_interval) == 0 && nz.u_cmd) {
+                const float *u = nz.u_cmd + (size_t)env * 3;
+                cmd[0] = p.cmd_span[0] * u[0] + p.cmd_lo[0];
+                cmd[1] = p.cmd_span[1] * u[1] + p.cmd_lo[1];
+                cmd[3] = p.cmd_span[2] * u[2] + p.cmd_lo[2];
+                const float keep = (sqrtf(cmd[0] * cmd[0] + cmd[1] * cmd[1]) > 0.2f) ? 1.0f : 0.0f;
+                cmd[0] *= keep, cmd[1] *= keep;
+            }
+            if (p.heading_command) {
+                const Vec3 fwd = quat_apply(quat, {1.0f, 0.0f, 0.0f});
+                const float heading = atan2f(fwd.y, fwd.x);
+                float e = mod_two_pi(cmd[3] - heading);                 // wrap_to_pi, utils/math.py:46-49
+                e = e - TWO_PI_F * ((e > PI_F) ? 1.0f : 0.0f);
+                cmd[2] = clampf(0.5f * e, -1.0f, 1.0f);
+            }
+            if ((stages & HB_STAGE_PUSH) && valid && nz.u_push) {       // _push_robots, hector_env.py:53-68
+                const float *u = nz.u_push + (size_t)env * 5;
+                push_f[0] = p.push_lin_span * u[0] + p.push_lin_lo;
+                push_f[1] = p.push_lin_span * u[1] + p.push_lin_lo;
+                root[7] = push_f[0], root[8] = push_f[1];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    push_t[k] = p.push_ang_span * u[2 + k] + p.push_ang_lo;
+                    root[10 + k] = push_t[k];
+                }
+                b.rand_push_force[env * 3] = push_f[0], b.rand_push_force[env * 3 + 1] = push_f[1];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) b.rand_push_torque[env * 3 + k] = push_t[k];
+            }
+            {   // base_acc, hector_env.py:385-392 (root velocity after the push)
+                float ss = 0.f;
+#pragma unroll
+                for (int k = 0; k < 6; ++k) {
+                    const float d = sm[L.last_root_vel + ln * 6 + k] - root[7 + k];
+                    ss += d * d;
+                }
+                terms[HB_R_BASE_ACC * TILE + lane] = expf(-sqrtf(ss) * 3.0f);
+            }
+            {   // orientation, :341-348
+                const float a = expf(-(fabsf(eul.x) + fabsf(eul.y)) * 10.0f);
+                const float g = expf(-sqrtf(grav.x * grav.x + grav.y * grav.y) * 20.0f);
+                terms[HB_R_ORIENTATION * TILE + lane] = (a + g) / 2.0f;
+            }
+            {   // tracking_ang_vel :435-443, tracking_lin_vel :426-433
+                const float ea = (cmd[2] - ang.z) * (cmd[2] - ang.z);
+                terms[HB_R_TRACKING_ANG_VEL * TILE + lane] = expf(-ea * p.tracking_sigma);
+                const float ex = cmd[0] - lin.x, ey = cmd[1] - lin.y;
+                terms[HB_R_TRACKING_LIN_VEL * TILE + lane] = expf(-(ex * ex + ey * ey) * p.tracking_sigma);
+            }
+        }
+        tile_barrier();                                           // ---- barrier 1 ----
+        const bool reset = valid && (flags[lane] & 1);
+        const float gs = reset ? 0.0f : sm[L.gait_s + lane], gc = reset ? 1.0f : sm[L.gait_c + lane];
+        if (reset) {         // _reset_root_states + _resample_commands + the gravity/euler fix-up (:373-396,321-335,211-214)
+            const float *u = nz.u_reset + (size_t)env * 15;
+#pragma unroll
+            for (int k = 0; k < 13; ++k) root[k] = p.base_init_state[k];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) root[k] += b.env_origins[env * 3 + k];
+            if (p.custom_origins) {
+                root[0] += p.reset_xy_span * u[10] + p.reset_xy_lo;
+                root[1] += p.reset_xy_span * u[11] + p.reset_xy_lo;
+            }
+            cmd[0] = p.cmd_span[0] * u[12] + p.cmd_lo[0];
+            cmd[1] = p.cmd_span[1] * u[13] + p.cmd_lo[1];
+            cmd[3] = p.cmd_span[2] * u[14] + p.cmd_lo[2];
             const float keep = (sqrtf(cmd[0] * cmd[0] + cmd[1] * cmd[1]) > 0.2f) ? 1.0f : 0.0f;
             cmd[0] *= keep, cmd[1] *= keep;
+            grav = {p.reset_gravity[0], p.reset_gravity[1], p.reset_gravity[2]};
+            eul = {p.reset_euler[0], p.reset_euler[1], p.reset_euler[2]};
         }
-        if (p.heading_command) {
-            const Vec3 fwd = quat_apply(quat, {1.0f, 0.0f, 0.0f});
-            const float heading = atan2f(fwd.y, fwd.x);
-            float e = py_mod(cmd[3] - heading, TWO_PI_F);          // wrap_to_pi, utils/math.py:46-49
-            e = e - TWO_PI_F * ((e > PI_F) ? 1.0f : 0.0f);
-            cmd[2] = clampf(0.5f * e, -1.0f, 1.0f);
-        }
-        if ((stages & HB_STAGE_PUSH) && valid && nz.u_push) {       // _push_robots, hector_env.py:53-68
-            const float *u = nz.u_push + (size_t)env * 5;
-            push_f[0] = p.push_lin_span * u[0] + p.push_lin_lo;
-            push_f[1] = p.push_lin_span * u[1] + p.push_lin_lo;
-            root[7] = push_f[0], root[8] = push_f[1];
+        if (valid) {
+            if (reset) {
 #pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                push_t[k] = p.push_ang_span * u[2 + k] + p.push_ang_lo;
-                root[10 + k] = push_t[k];
+                for (int k = 0; k < 13; ++k) b.root_states[(size_t)env * 13 + k] = root[k];
+            } else if (stages & HB_STAGE_PUSH) {
+                b.root_states[(size_t)env * 13 + 7] = root[7], b.root_states[(size_t)env * 13 + 8] = root[8];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) b.root_states[(size_t)env * 13 + 10 + k] = root[10 + k];
             }
-            b.root_states[(size_t)env * 13 + 7] = root[7];
-            b.root_states[(size_t)env * 13 + 8] = root[8];
+            if (derive) {
+                b.base_lin_vel[env * 3] = lin.x, b.base_lin_vel[env * 3 + 1] = lin.y, b.base_lin_vel[env * 3 + 2] = lin.z;
+                b.base_ang_vel[env * 3] = ang.x, b.base_ang_vel[env * 3 + 1] = ang.y, b.base_ang_vel[env * 3 + 2] = ang.z;
+            }
+            if (do_step) {
 #pragma unroll
-            for (int k = 0; k < 3; ++k) b.root_states[(size_t)env * 13 + 10 + k] = root[10 + k];
-            b.rand_push_force[env * 3] = push_f[0], b.rand_push_force[env * 3 + 1] = push_f[1];
+                for (int k = 0; k < 6; ++k) b.last_root_vel[(size_t)env * 6 + k] = root[7 + k];
+            }
+            b.projected_gravity[env * 3] = grav.x, b.projected_gravity[env * 3 + 1] = grav.y, b.projected_gravity[env * 3 + 2] = grav.z;
+            b.base_euler_xyz[env * 3] = eul.x, b.base_euler_xyz[env * 3 + 1] = eul.y, b.base_euler_xyz[env * 3 + 2] = eul.z;
 #pragma unroll
-            for (int k = 0; k < 3; ++k) b.rand_push_torque[env * 3 + k] = push_t[k];
+            for (int k = 0; k < 4; ++k) b.commands[(size_t)env * 4 + k] = cmd[k];
         }
-
-        // -------- check_termination, legged_robot.py:155-160 --------
+        if (emit_obs) {      // command input, base velocities, euler, root position, push (hector_env.py:186-226)
+            constexpr int B0 = 5 + 3 * NDOF;
+            float o[11];
+            o[0] = gs, o[1] = gc;
+            o[2] = cmd[0] * p.obs_lin_vel, o[3] = cmd[1] * p.obs_lin_vel, o[4] = cmd[2] * p.obs_ang_vel;
+            o[5] = ang.x * p.obs_ang_vel, o[6] = ang.y * p.obs_ang_vel, o[7] = ang.z * p.obs_ang_vel;
+            o[8] = eul.x * p.obs_quat, o[9] = eul.y * p.obs_quat, o[10] = eul.z * p.obs_quat;
 #pragma unroll
-        for (int i = 0; i < HB_MAX_CONTACT_BODIES; ++i) reset |= (i < p.n_term) && (term_norm[i] > 1.0f);
-        time_out = ep_len > (long long)p.max_episode_length;
-        reset |= time_out;
-
-        // -------- gait phase (hector_env.py:70-88) and contacts --------
-        const float phase = ((float)ep_len * dt) / p.cycle_time;
-        const float s = sinf(TWO_PI_F * phase);
-        float st[2] = {(s >= 0.0f) ? 1.0f : 0.0f, (s < 0.0f) ? 1.0f : 0.0f};
-        if (fabsf(s) < 0.1f) st[0] = st[1] = 1.0f;
-        const bool ct[2] = {foot_f[0][2] > 5.0f, foot_f[1][2] > 5.0f};
-
-        // -------- compute_reward (legged_robot.py:216-234): alphabetical accumulation --------
-        float term[HB_NUM_REWARDS];
-        {   // action_smoothness, hector_env.py:529-539
-            float t1 = 0.f, t2 = 0.f, t3 = 0.f;
+            for (int k = 0; k < 5; ++k) {
+                so[lane * OBS + k] = clampf(o[k], -clip, clip);        // noise scale of the command slots is 0
+                sp[lane * PRIV_PAD + k] = clampf(o[k], -clip, clip);
+            }
+#pragma unroll
+            for (int k = 0; k < 6; ++k) {
+                float v = o[5 + k];
+                sp[lane * PRIV_PAD + B0 + 3 + k] = clampf(v, -clip, clip);
+                if (with_noise) v = v + (sm[L.z_obs + ln * OBS + B0 + k] * p.noise_scale_vec[B0 + k]) * p.noise_level;
+                so[lane * OBS + B0 + k] = clampf(v, -clip, clip);
+            }
+            sp[lane * PRIV_PAD + B0] = clampf(lin.x * p.obs_lin_vel, -clip, clip);
+            sp[lane * PRIV_PAD + B0 + 1] = clampf(lin.y * p.obs_lin_vel, -clip, clip);
+            sp[lane * PRIV_PAD + B0 + 2] = clampf(lin.z * p.obs_lin_vel, -clip, clip);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) sp[lane * PRIV_PAD + B0 + 21 + k] = clampf(root[k], -clip, clip);
+            sp[lane * PRIV_PAD + B0 + 24] = clampf(push_f[0], -clip, clip);
+            sp[lane * PRIV_PAD + B0 + 25] = clampf(push_f[1], -clip, clip);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) sp[lane * PRIV_PAD + B0 + 26 + k] = clampf(push_t[k], -clip, clip);
+        }
+    } else if (warp == 1) {
+        // ================================ joints ================================
+        float q[NDOF], qd[NDOF], act[NDOF], lact[NDOF], llact[NDOF], ldv[NDOF];
+#pragma unroll
+        for (int j = 0; j < NDOF; ++j) {
+            q[j] = sm[L.dof + ln * NDOF * 2 + 2 * j];
+            qd[j] = sm[L.dof + ln * NDOF * 2 + 2 * j + 1];
+            act[j] = sm[L.actions + ln * NDOF + j];
+            lact[j] = sm[L.last_actions + ln * NDOF + j];
+            llact[j] = sm[L.last_last_actions + ln * NDOF + j];
+            ldv[j] = sm[L.last_dof_vel + ln * NDOF + j];
+        }
+        if (do_step) {
+            float t1 = 0.f, t2 = 0.f, t3 = 0.f, ss = 0.f, acc = 0.f, vel = 0.f, tq = 0.f, d[NDOF];
 #pragma unroll
             for (int j = 0; j < NDOF; ++j) {
-                const float d1 = lact[j] - act[j];
+                const float d1 = lact[j] - act[j];                     // action_smoothness, hector_env.py:529-539
                 t1 += d1 * d1;
                 const float d2 = (act[j] + llact[j]) - 2.0f * lact[j];
                 t2 += d2 * d2;
                 t3 += fabsf(act[j]);
+                d[j] = q[j] - p.default_dof_pos[j];                    // default_joint_pos, :357-367
+                ss += d[j] * d[j];
+                const float a = (ldv[j] - qd[j]) / dt;                 // dof_acc :515-520
+                acc += a * a;
+                vel += qd[j] * qd[j];                                  // dof_vel :508-513
+                const float tau = sm[L.torques + ln * NDOF + j];       // torques :501-506
+                tq += tau * tau;
             }
-            term[HB_R_ACTION_SMOOTHNESS] = (t1 + t2) + 0.05f * t3;
-        }
-        {   // base_acc, :385-392
-            float ss = 0.f;
-#pragma unroll
-            for (int k = 0; k < 6; ++k) {
-                const float d = lrv[k] - root[7 + k];
-                ss += d * d;
-            }
-            term[HB_R_BASE_ACC] = expf(-sqrtf(ss) * 3.0f);
-        }
-        {   // base_height, :369-383
-            const float ground = (foot_pos[0][2] * st[0] + foot_pos[1][2] * st[1]) / (st[0] + st[1]);
-            const float h = root[2] - (ground - 0.05f);
-            term[HB_R_BASE_HEIGHT] = expf(-fabsf(h - p.base_height_target) * 100.0f);
-        }
-        {   // collision, :522-527
-            float c = 0.f;
-#pragma unroll
-            for (int i = 0; i < HB_MAX_CONTACT_BODIES; ++i) c += ((i < p.n_pen) && (pen_norm[i] > 0.1f)) ? 1.0f : 0.0f;
-            term[HB_R_COLLISION] = c;
-        }
-        {   // default_joint_pos, :357-367
-            float d[NDOF], ss = 0.f;
-#pragma unroll
-            for (int j = 0; j < NDOF; ++j) d[j] = q[j] - p.default_dof_pos[j], ss += d[j] * d[j];
+            terms[HB_R_ACTION_SMOOTHNESS * TILE + lane] = (t1 + t2) + 0.05f * t3;
             float yr = sqrtf(d[0] * d[0] + d[1] * d[1]) + sqrtf(d[5] * d[5] + d[6] * d[6]);
             yr = clampf(yr - 0.1f, 0.0f, 50.0f);
-            term[HB_R_DEFAULT_JOINT_POS] = expf(-yr * 100.0f) - 0.01f * sqrtf(ss);
+            terms[HB_R_DEFAULT_JOINT_POS * TILE + lane] = expf(-yr * 100.0f) - 0.01f * sqrtf(ss);
+            terms[HB_R_DOF_ACC * TILE + lane] = acc;
+            terms[HB_R_DOF_VEL * TILE + lane] = vel;
+            terms[HB_R_TORQUES * TILE + lane] = tq;
         }
-        {   // dof_acc :515-520, dof_vel :508-513, torques :501-506
-            float acc = 0.f, vel = 0.f, tq = 0.f;
+        tile_barrier();                                           // ---- barrier 1 ----
+        const bool reset = valid && (flags[lane] & 1);
+        if (reset) {         // _reset_dofs (legged_robot.py:358-372) + buffer zeroing (:186-191)
+            const float *u = nz.u_reset + (size_t)env * 15;
 #pragma unroll
             for (int j = 0; j < NDOF; ++j) {
-                const float a = (ldv[j] - qd[j]) / dt;
-                acc += a * a;
-                vel += qd[j] * qd[j];
-                tq += tau[j] * tau[j];
-            }
-            term[HB_R_DOF_ACC] = acc, term[HB_R_DOF_VEL] = vel, term[HB_R_TORQUES] = tq;
-        }
-        {   // feet_air_time, :315-329 (stateful)
-            float r = 0.f;
-#pragma unroll
-            for (int f = 0; f < 2; ++f) {
-                const bool filt = ct[f] || (st[f] != 0.0f) || last_ct[f];
-                last_ct[f] = ct[f];
-                const bool first = (air[f] > 0.0f) && filt;
-                air[f] += dt;
-                r += clampf(air[f], 0.0f, 0.5f) * (first ? 1.0f : 0.0f);
-                air[f] *= filt ? 0.0f : 1.0f;
-            }
-            term[HB_R_FEET_AIR_TIME] = r;
-        }
-        {   // feet_clearance, :445-466 (stateful)
-            float r = 0.f;
-#pragma unroll
-            for (int f = 0; f < 2; ++f) {
-                const float z = foot_pos[f][2] - 0.05f;
-                fh[f] += z - lz[f];
-                lz[f] = z;
-                const float hit = (fabsf(fh[f] - p.target_feet_height) < 0.01f) ? 1.0f : 0.0f;
-                r += hit * (1.0f - st[f]);
-                fh[f] *= ct[f] ? 0.0f : 1.0f;
-            }
-            term[HB_R_FEET_CLEARANCE] = r;
-        }
-        {   // feet_contact_forces :350-355, feet_contact_number :331-339, foot_slip :303-313
-            float cfz = 0.f, num = 0.f, slip = 0.f;
-#pragma unroll
-            for (int f = 0; f < 2; ++f) {
-                const float nf = sqrtf((foot_f[f][0] * foot_f[f][0] + foot_f[f][1] * foot_f[f][1]) + foot_f[f][2] * foot_f[f][2]);
-                cfz += clampf(nf - p.max_contact_force, 0.0f, 400.0f);
-                num += (ct[f] == (st[f] != 0.0f)) ? 1.0f : -0.3f;
-                const float sp = sqrtf(sqrtf(foot_vel[f][0] * foot_vel[f][0] + foot_vel[f][1] * foot_vel[f][1]));
-                slip += sp * (ct[f] ? 1.0f : 0.0f);
-            }
-            term[HB_R_FEET_CONTACT_FORCES] = cfz;
-            term[HB_R_FEET_CONTACT_NUMBER] = num / 2.0f;
-            term[HB_R_FOOT_SLIP] = slip;
-        }
-        {   // feet_distance :277-287, knee_distance :290-300
-            float dx = foot_pos[0][0] - foot_pos[1][0], dy = foot_pos[0][1] - foot_pos[1][1];
-            float d = sqrtf(dx * dx + dy * dy);
-            float dmin = clampf(d - p.min_dist, -0.5f, 0.0f), dmax = clampf(d - p.max_dist, 0.0f, 0.5f);
-            term[HB_R_FEET_DISTANCE] = (expf(-fabsf(dmin) * 100.0f) + expf(-fabsf(dmax) * 100.0f)) / 2.0f;
-            dx = knee_xy[0][0] - knee_xy[1][0], dy = knee_xy[0][1] - knee_xy[1][1];
-            d = sqrtf(dx * dx + dy * dy);
-            dmin = clampf(d - p.min_dist, -0.5f, 0.0f), dmax = clampf(d - p.max_dist / 2.0f, 0.0f, 0.5f);
-            term[HB_R_KNEE_DISTANCE] = (expf(-fabsf(dmin) * 100.0f) + expf(-fabsf(dmax) * 100.0f)) / 2.0f;
-        }
-        {   // orientation, :341-348
-            const float a = expf(-(fabsf(eul.x) + fabsf(eul.y)) * 10.0f);
-            const float g = expf(-sqrtf(grav.x * grav.x + grav.y * grav.y) * 20.0f);
-            term[HB_R_ORIENTATION] = (a + g) / 2.0f;
-        }
-        {   // tracking_ang_vel :435-443, tracking_lin_vel :426-433
-            const float ea = (cmd[2] - ang.z) * (cmd[2] - ang.z);
-            term[HB_R_TRACKING_ANG_VEL] = expf(-ea * p.tracking_sigma);
-            const float ex = cmd[0] - lin.x, ey = cmd[1] - lin.y;
-            term[HB_R_TRACKING_LIN_VEL] = expf(-(ex * ex + ey * ey) * p.tracking_sigma);
-        }
-#pragma unroll
-        for (int k = 0; k < HB_NUM_REWARDS; ++k) {
-            if (p.reward_scale[k] != 0.0f) {
-                const float r = term[k] * p.reward_scale[k];
-                rew += r;
-                sums[k] += r;
+                q[j] = p.default_dof_pos[j] + (p.reset_dof_span * u[j] + p.reset_dof_lo);
+                qd[j] = 0.0f;
+                b.dof_state[((size_t)env * NDOF + j) * 2] = q[j];
+                b.dof_state[((size_t)env * NDOF + j) * 2 + 1] = 0.0f;
+                act[j] = lact[j] = llact[j] = 0.0f;
+                b.actions[(size_t)env * NDOF + j] = 0.0f;
             }
         }
-        if (p.only_positive_rewards) rew = fmaxf(rew, 0.0f);
-    } else if (stages & HB_STAGE_DERIVE) {
-        // _init_buffers (legged_robot.py:452,477-479): derived quantities of the initial state
-        const float *quat = root + 3;
-        lin = quat_rotate_inverse(quat, {root[7], root[8], root[9]});
-        ang = quat_rotate_inverse(quat, {root[10], root[11], root[12]});
-        grav = quat_rotate_inverse(quat, {0.0f, 0.0f, -1.0f});
-        eul = euler_xyz_wrapped(quat);
-    } else if (valid) {
-        // reset / observation-only pass: derived quantities keep their stored values
-        lin = {b.base_lin_vel[env * 3], b.base_lin_vel[env * 3 + 1], b.base_lin_vel[env * 3 + 2]};
-        ang = {b.base_ang_vel[env * 3], b.base_ang_vel[env * 3 + 1], b.base_ang_vel[env * 3 + 2]};
-        grav = {b.projected_gravity[env * 3], b.projected_gravity[env * 3 + 1], b.projected_gravity[env * 3 + 2]};
-        eul = euler_xyz_wrapped(root + 3);
-    }
-    if (reset_all) reset = true;
-    if ((stages & HB_STAGE_RESET_MASK) && valid) reset = reset || (b.reset_buf[env] != 0);   // reset_idx(env_ids)
-    reset = reset && valid;
-
-    // ---------------- reset_idx (legged_robot.py:162-214,358-396) ----------------
-    const unsigned ballot = __ballot_sync(0xffffffffu, reset);
-    float my_sums[HB_NUM_REWARDS];
+        if (valid) {         // legged_robot.py:146-148
 #pragma unroll
-    for (int k = 0; k < HB_NUM_REWARDS; ++k) my_sums[k] = reset ? sums[k] : 0.0f;
-    if (reset) {
-        const float *u = nz.u_reset + (size_t)env * 15;
-#pragma unroll
-        for (int j = 0; j < NDOF; ++j) {
-            q[j] = p.default_dof_pos[j] + (p.reset_dof_span * u[j] + p.reset_dof_lo);
-            qd[j] = 0.0f;
-            b.dof_state[((size_t)env * NDOF + j) * 2] = q[j];
-            b.dof_state[((size_t)env * NDOF + j) * 2 + 1] = 0.0f;
-            act[j] = lact[j] = llact[j] = 0.0f;
-        }
-#pragma unroll
-        for (int k = 0; k < 13; ++k) root[k] = p.base_init_state[k];
-#pragma unroll
-        for (int k = 0; k < 3; ++k) root[k] += b.env_origins[env * 3 + k];
-        if (p.custom_origins) {
-            root[0] += p.reset_xy_span * u[10] + p.reset_xy_lo;
-            root[1] += p.reset_xy_span * u[11] + p.reset_xy_lo;
-        }
-#pragma unroll
-        for (int k = 0; k < 13; ++k) b.root_states[(size_t)env * 13 + k] = root[k];
-        cmd[0] = p.cmd_span[0] * u[12] + p.cmd_lo[0];
-        cmd[1] = p.cmd_span[1] * u[13] + p.cmd_lo[1];
-        cmd[3] = p.cmd_span[2] * u[14] + p.cmd_lo[2];
-        const float keep = (sqrtf(cmd[0] * cmd[0] + cmd[1] * cmd[1]) > 0.2f) ? 1.0f : 0.0f;
-        cmd[0] *= keep, cmd[1] *= keep;
-        air[0] = air[1] = 0.0f;
-        ep_len = 0;
-#pragma unroll
-        for (int k = 0; k < HB_NUM_REWARDS; ++k) sums[k] = 0.0f;
-        grav = quat_rotate_inverse(root + 3, {0.0f, 0.0f, -1.0f});
-        eul = euler_xyz_wrapped(root + 3);
-    }
-
-    // ---------------- compute_observations, newest frames (hector_env.py:172-254) ----------------
-    const bool emit_obs = do_step || (stages & HB_STAGE_OBS);
-    if (emit_obs) {
-        const float phase = ((float)ep_len * dt) / p.cycle_time;
-        const float arg = TWO_PI_F * phase;
-        const float s = sinf(arg), c = cosf(arg);
-        float st[2] = {(s >= 0.0f) ? 1.0f : 0.0f, (s < 0.0f) ? 1.0f : 0.0f};
-        if (fabsf(s) < 0.1f) st[0] = st[1] = 1.0f;
-        float fr[PRIV];
-        fr[0] = s, fr[1] = c;
-        fr[2] = cmd[0] * p.obs_lin_vel, fr[3] = cmd[1] * p.obs_lin_vel, fr[4] = cmd[2] * p.obs_ang_vel;
-#pragma unroll
-        for (int j = 0; j < NDOF; ++j) {
-            fr[5 + j] = (q[j] - p.default_dof_pos[j]) * p.obs_dof_pos;
-            fr[5 + NDOF + j] = qd[j] * p.obs_dof_vel;
-            fr[5 + 2 * NDOF + j] = act[j];
-        }
-        constexpr int B0 = 5 + 3 * NDOF;
-        const float clip = p.clip_observations;
-        float *so = sm, *sp = sm + TILE * OBS;
-        {   // actor frame: ... ang_vel, euler, plus scaled noise
-            float o[OBS];
-#pragma unroll
-            for (int k = 0; k < B0; ++k) o[k] = fr[k];
-            o[B0] = ang.x * p.obs_ang_vel, o[B0 + 1] = ang.y * p.obs_ang_vel, o[B0 + 2] = ang.z * p.obs_ang_vel;
-            o[B0 + 3] = eul.x * p.obs_quat, o[B0 + 4] = eul.y * p.obs_quat, o[B0 + 5] = eul.z * p.obs_quat;
-#pragma unroll
-            for (int k = 0; k < OBS; ++k) {
-                float v = o[k];
-                if (with_noise) v = v + (zobs[k] * p.noise_scale_vec[k]) * p.noise_level;
-                so[lane * OBS + k] = clampf(v, -clip, clip);
+            for (int j = 0; j < NDOF; ++j) {
+                b.last_last_actions[(size_t)env * NDOF + j] = do_step ? lact[j] : llact[j];
+                b.last_actions[(size_t)env * NDOF + j] = do_step ? act[j] : lact[j];
+                b.last_dof_vel[(size_t)env * NDOF + j] = (do_step || reset) ? qd[j] : ldv[j];
             }
         }
-        fr[B0] = lin.x * p.obs_lin_vel, fr[B0 + 1] = lin.y * p.obs_lin_vel, fr[B0 + 2] = lin.z * p.obs_lin_vel;
-        fr[B0 + 3] = ang.x * p.obs_ang_vel, fr[B0 + 4] = ang.y * p.obs_ang_vel, fr[B0 + 5] = ang.z * p.obs_ang_vel;
-        fr[B0 + 6] = eul.x * p.obs_quat, fr[B0 + 7] = eul.y * p.obs_quat, fr[B0 + 8] = eul.z * p.obs_quat;
+        if (emit_obs) {
+#pragma unroll
+            for (int j = 0; j < NDOF; ++j) {
+                float v0 = (q[j] - p.default_dof_pos[j]) * p.obs_dof_pos, v1 = qd[j] * p.obs_dof_vel;
+                sp[lane * PRIV_PAD + 5 + j] = clampf(v0, -clip, clip);
+                sp[lane * PRIV_PAD + 5 + NDOF + j] = clampf(v1, -clip, clip);
+                sp[lane * PRIV_PAD + 5 + 2 * NDOF + j] = clampf(act[j], -clip, clip);
+                if (with_noise) {
+                    v0 = v0 + (sm[L.z_obs + ln * OBS + 5 + j] * p.noise_scale_vec[5 + j]) * p.noise_level;
+                    v1 = v1 + (sm[L.z_obs + ln * OBS + 5 + NDOF + j] * p.noise_scale_vec[5 + NDOF + j]) * p.noise_level;
+                }
+                float v2 = act[j];
+                if (with_noise)
+                    v2 = v2 + (sm[L.z_obs + ln * OBS + 5 + 2 * NDOF + j] * p.noise_scale_vec[5 + 2 * NDOF + j]) * p.noise_level;
+                so[lane * OBS + 5 + j] = clampf(v0, -clip, clip);
+                so[lane * OBS + 5 + NDOF + j] = clampf(v1, -clip, clip);
+                so[lane * OBS + 5 + 2 * NDOF + j] = clampf(v2, -clip, clip);
+            }
+        }
+    } else if (warp == 2) {
+        // ================================ feet / contacts / gait ================================
+        const float *cf = sm + L.contact + ln * crow;
+        float foot_f[2][3];
 #pragma unroll
         for (int f = 0; f < 2; ++f)
 #pragma unroll
-            for (int k = 0; k < 3; ++k) fr[B0 + 9 + f * 3 + k] = foot_pos[f][k], fr[B0 + 15 + f * 3 + k] = foot_vel[f][k];
-        fr[B0 + 21] = root[0], fr[B0 + 22] = root[1], fr[B0 + 23] = root[2];
-        fr[B0 + 24] = push_f[0], fr[B0 + 25] = push_f[1];
-        fr[B0 + 26] = push_t[0], fr[B0 + 27] = push_t[1], fr[B0 + 28] = push_t[2];
-        fr[B0 + 29] = valid ? b.env_frictions[env] : 0.0f;
-        fr[B0 + 30] = (valid ? b.body_mass[env] : 0.0f) / 30.0f;
-        fr[B0 + 31] = st[0], fr[B0 + 32] = st[1];
-        fr[B0 + 33] = (foot_f[0][2] > 5.0f) ? 1.0f : 0.0f, fr[B0 + 34] = (foot_f[1][2] > 5.0f) ? 1.0f : 0.0f;
+            for (int k = 0; k < 3; ++k) foot_f[f][k] = cf[p.feet[f] * 3 + k];
+        const float root_z = sm[L.root + ln * 13 + 2];
+        bool reset = false, time_out = false;
+        float gs = 0.0f, gc = 1.0f, st[2] = {1.0f, 1.0f};
+        const bool ct[2] = {foot_f[0][2] > 5.0f, foot_f[1][2] > 5.0f};
+        if (do_step) {
+            ep_len += 1;
+            // -------- check_termination, legged_robot.py:155-160 --------
+            float coll = 0.f;
+#pragma unroll 1
+            for (int i = 0; i < p.n_term; ++i) reset |= norm3(cf + p.term_bodies[i] * 3) > 1.0f;
+#pragma unroll 1
+            for (int i = 0; i < p.n_pen; ++i) coll += (norm3(cf + p.pen_bodies[i] * 3) > 0.1f) ? 1.0f : 0.0f;
+            time_out = ep_len > (long long)p.max_episode_length;
+            reset |= time_out;
+            terms[HB_R_COLLISION * TILE + lane] = coll;                 // :522-527
+        }
+        {   // -------- gait phase, hector_env.py:70-88 --------
+            const float arg = TWO_PI_F * (((float)ep_len * dt) / p.cycle_time);
+            sincosf(arg, &gs, &gc);
+            st[0] = (gs >= 0.0f) ? 1.0f : 0.0f, st[1] = (gs < 0.0f) ? 1.0f : 0.0f;
+            if (fabsf(gs) < 0.1f) st[0] = st[1] = 1.0f;
+        }
+        if (do_step) {
+            {   // base_height, :369-383
+                const float ground = (foot_pos[0][2] * st[0] + foot_pos[1][2] * st[1]) / (st[0] + st[1]);
+                const float h = root_z - (ground - 0.05f);
+                terms[HB_R_BASE_HEIGHT * TILE + lane] = expf(-fabsf(h - p.base_height_target) * 100.0f);
+            }
+            float r_air = 0.f, r_clr = 0.f, cfz = 0.f, num = 0.f, slip = 0.f;
 #pragma unroll
-        for (int k = 0; k < PRIV; ++k) sp[lane * PRIV + k] = clampf(fr[k], -clip, clip);
+            for (int f = 0; f < 2; ++f) {
+                {   // feet_air_time, :315-329 (stateful)
+                    const bool filt = ct[f] || (st[f] != 0.0f) || last_ct[f];
+                    last_ct[f] = ct[f];
+                    const bool first = (air[f] > 0.0f) && filt;
+                    air[f] += dt;
+                    r_air += clampf(air[f], 0.0f, 0.5f) * (first ? 1.0f : 0.0f);
+                    air[f] *= filt ? 0.0f : 1.0f;
+                }
+                {   // feet_clearance, :445-466 (stateful)
+                    const float z = foot_pos[f][2] - 0.05f;
+                    fh[f] += z - lz[f];
+                    lz[f] = z;
+                    const float hit = (fabsf(fh[f] - p.target_feet_height) < 0.01f) ? 1.0f : 0.0f;
+                    r_clr += hit * (1.0f - st[f]);
+                    fh[f] *= ct[f] ? 0.0f : 1.0f;
+                }
+                // feet_contact_forces :350-355, feet_contact_number :331-339, foot_slip :303-313
+                cfz += clampf(norm3(foot_f[f]) - p.max_contact_force, 0.0f, 400.0f);
+                num += (ct[f] == (st[f] != 0.0f)) ? 1.0f : -0.3f;
+                const float spd = sqrtf(sqrtf(foot_vel[f][0] * foot_vel[f][0] + foot_vel[f][1] * foot_vel[f][1]));
+                slip += spd * (ct[f] ? 1.0f : 0.0f);
+            }
+            terms[HB_R_FEET_AIR_TIME * TILE + lane] = r_air;
+            terms[HB_R_FEET_CLEARANCE * TILE + lane] = r_clr;
+            terms[HB_R_FEET_CONTACT_FORCES * TILE + lane] = cfz;
+            terms[HB_R_FEET_CONTACT_NUMBER * TILE + lane] = num / 2.0f;
+            terms[HB_R_FOOT_SLIP * TILE + lane] = slip;
+            {   // feet_distance :277-287, knee_distance :290-300
+                float dx = foot_pos[0][0] - foot_pos[1][0], dy = foot_pos[0][1] - foot_pos[1][1];
+                float d = sqrtf(dx * dx + dy * dy);
+                float dmin = clampf(d - p.min_dist, -0.5f, 0.0f), dmax = clampf(d - p.max_dist, 0.0f, 0.5f);
+                terms[HB_R_FEET_DISTANCE * TILE + lane] = (expf(-fabsf(dmin) * 100.0f) + expf(-fabsf(dmax) * 100.0f)) / 2.0f;
+                dx = knee_xy[0][0] - knee_xy[1][0], dy = knee_xy[0][1] - knee_xy[1][1];
+                d = sqrtf(dx * dx + dy * dy);
+                dmin = clampf(d - p.min_dist, -0.5f, 0.0f), dmax = clampf(d - p.max_dist / 2.0f, 0.0f, 0.5f);
+                terms[HB_R_KNEE_DISTANCE * TILE + lane] = (expf(-fabsf(dmin) * 100.0f) + expf(-fabsf(dmax) * 100.0f)) / 2.0f;
+            }
+        }
+        if (stages & HB_STAGE_RESET_ALL) reset = true;
+        if ((stages & HB_STAGE_RESET_MASK) && valid) reset = reset || (b.reset_buf[env] != 0);   // reset_idx(env_ids)
+        reset = reset && valid;
+        flags[lane] = (reset ? 1 : 0) | (time_out ? 2 : 0);
+        sm[L.gait_s + lane] = gs, sm[L.gait_c + lane] = gc;
+        tile_barrier();                                           // ---- barrier 1 ----
+        if (reset) {
+            ep_len = 0, air[0] = air[1] = 0.0f;
+            st[0] = st[1] = 1.0f;                                   // phase 0: sin = 0 -> double support
+        }
+        if (valid) {
+            b.feet_air_time[env * 2] = air[0], b.feet_air_time[env * 2 + 1] = air[1];
+            b.episode_length_buf[env] = ep_len;
+            b.reset_buf[env] = reset ? 1 : 0;
+            if (do_step) {
+                b.time_out_buf[env] = time_out ? 1 : 0;
+#pragma unroll
+                for (int f = 0; f < 2; ++f) {
+                    b.last_contacts[env * 2 + f] = last_ct[f] ? 1 : 0;
+                    b.feet_height[env * 2 + f] = fh[f];
+                    b.last_feet_z[env * 2 + f] = lz[f];
+                }
+            }
+        }
+        if (emit_obs) {
+            constexpr int B0 = 5 + 3 * NDOF;
+#pragma unroll
+            for (int f = 0; f < 2; ++f)
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    sp[lane * PRIV_PAD + B0 + 9 + f * 3 + k] = clampf(foot_pos[f][k], -clip, clip);
+                    sp[lane * PRIV_PAD + B0 + 15 + f * 3 + k] = clampf(foot_vel[f][k], -clip, clip);
+                }
+            sp[lane * PRIV_PAD + B0 + 29] = clampf(valid ? b.env_frictions[env] : 0.0f, -clip, clip);
+            sp[lane * PRIV_PAD + B0 + 30] = clampf((valid ? b.body_mass[env] : 0.0f) / 30.0f, -clip, clip);
+            sp[lane * PRIV_PAD + B0 + 31] = st[0], sp[lane * PRIV_PAD + B0 + 32] = st[1];
+            sp[lane * PRIV_PAD + B0 + 33] = ct[0] ? 1.0f : 0.0f, sp[lane * PRIV_PAD + B0 + 34] = ct[1] ? 1.0f : 0.0f;
+        }
+    } else {
+        // ================================ ledger ================================
+        tile_barrier();                                           // ---- barrier 1 ----
+        const bool reset = valid && (flags[lane] & 1);
+        if (do_step) {       // compute_reward, legged_robot.py:216-234: alphabetical accumulation
+            float rew = 0.0f;
+#pragma unroll
+            for (int k = 0; k < HB_NUM_REWARDS; ++k) {
+                if (p.reward_scale[k] != 0.0f) {
+                    const float r = terms[k * TILE + lane] * p.reward_scale[k];
+                    rew += r;
+                    sums[k] += r;
+                }
+            }
+            if (p.only_positive_rewards) rew = fmaxf(rew, 0.0f);
+            if (valid) b.rew_buf[env] = rew;
+        }
+        const unsigned ballot = __ballot_sync(0xffffffffu, reset);
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < HB_NUM_REWARDS; ++k) {
+            terms[k * TILE + lane] = reset ? sums[k] : 0.0f;        // episode sums of the envs being reset (:198-201)
+            if (reset) sums[k] = 0.0f;
+            if (valid) b.episode_sums[(size_t)k * N + env] = sums[k];
+        }
+        __syncwarp();
+        // ---------------- ordered compaction of the reset ids + episode means ----------------
+        // Each tile publishes its ballot and the per-term sums of its reset envs; the last CTA to
+        // finish scans the ballots in tile order (ascending env ids, like reset_buf.nonzero()).
+        if (ballot && lane < HB_NUM_REWARDS) {
+            float v = 0.0f;
+#pragma unroll 1
+            for (int e = 0; e < TILE; ++e) v += terms[lane * TILE + ((e + lane) & 31)];
+            b.scratch_partials[(size_t)blockIdx.x * HB_NUM_REWARDS + lane] = v;
+        }
+        if (lane == 0) b.scratch_ballots[blockIdx.x] = ballot;
+        __threadfence();                          // publish ballot + partials before this CTA takes its ticket
     }
-    __syncwarp();
-    if (emit_obs) {   // coalesced-by-row store of the newest frames into the last slot of the stacked buffers
+
+    // ---------------- coalesced store of the newest frames into the last slot of the stacked buffers ----------------
+    __syncthreads();                                              // ---- barrier 2 ----
+    if (threadIdx.x == 0) s_is_last = (atomicAdd(b.scratch_ticket, 1u) == gridDim.x - 1);
+    if (emit_obs) {
         const int ostride = p.frame_stack * OBS, pstride = p.c_frame_stack * PRIV;
-        const float *so = sm, *sp = sm + TILE * OBS;
-        for (int i = lane; i < nv * OBS; i += 32) {
+        for (int i = threadIdx.x; i < nv * OBS; i += blockDim.x) {
             const int r = i / OBS, c = i - r * OBS;
             obs_new[(size_t)(env0 + r) * ostride + (ostride - OBS) + c] = so[i];
         }
-        for (int i = lane; i < nv * PRIV; i += 32) {
+        for (int i = threadIdx.x; i < nv * PRIV; i += blockDim.x) {
             const int r = i / PRIV, c = i - r * PRIV;
-            priv_new[(size_t)(env0 + r) * pstride + (pstride - PRIV) + c] = sp[i];
+            priv_new[(size_t)(env0 + r) * pstride + (pstride - PRIV) + c] = sp[r * PRIV_PAD + c];
         }
     }
+    __syncthreads();
+    if (!s_is_last) return;
 
-    // ---------------- state write-back (incl. legged_robot.py:146-150) ----------------
-    if (valid) {
-#pragma unroll
-        for (int j = 0; j < NDOF; ++j) {
-            b.last_last_actions[(size_t)env * NDOF + j] = do_step ? lact[j] : llact[j];
-            b.last_actions[(size_t)env * NDOF + j] = do_step ? act[j] : lact[j];
-            b.last_dof_vel[(size_t)env * NDOF + j] = (do_step || reset) ? qd[j] : ldv[j];
-            if (reset) b.actions[(size_t)env * NDOF + j] = 0.0f;
-        }
-        if (do_step || (stages & HB_STAGE_DERIVE)) {
-            b.base_lin_vel[env * 3] = lin.x, b.base_lin_vel[env * 3 + 1] = lin.y, b.base_lin_vel[env * 3 + 2] = lin.z;
-            b.base_ang_vel[env * 3] = ang.x, b.base_ang_vel[env * 3 + 1] = ang.y, b.base_ang_vel[env * 3 + 2] = ang.z;
-        }
-        if (do_step) {
-#pragma unroll
-            for (int k = 0; k < 6; ++k) b.last_root_vel[(size_t)env * 6 + k] = root[7 + k];
-            b.rew_buf[env] = rew;
-            b.time_out_buf[env] = time_out ? 1 : 0;
-#pragma unroll
-            for (int f = 0; f < 2; ++f) {
-                b.last_contacts[env * 2 + f] = last_ct[f] ? 1 : 0;
-                b.feet_height[env * 2 + f] = fh[f];
-                b.last_feet_z[env * 2 + f] = lz[f];
-            }
-        }
-        b.projected_gravity[env * 3] = grav.x, b.projected_gravity[env * 3 + 1] = grav.y, b.projected_gravity[env * 3 + 2] = grav.z;
-        b.base_euler_xyz[env * 3] = eul.x, b.base_euler_xyz[env * 3 + 1] = eul.y, b.base_euler_xyz[env * 3 + 2] = eul.z;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) b.commands[(size_t)env * 4 + k] = cmd[k];
-        b.feet_air_time[env * 2] = air[0], b.feet_air_time[env * 2 + 1] = air[1];
-        b.episode_length_buf[env] = ep_len;
-        b.reset_buf[env] = reset ? 1 : 0;
-#pragma unroll
-        for (int k = 0; k < HB_NUM_REWARDS; ++k) b.episode_sums[(size_t)k * N + env] = sums[k];
+    // ---------------- last CTA: ordered compaction of the reset ids + episode means ----------------
+    // Every tile has published its ballot and the per-term sums of its reset envs.  The whole CTA
+    // scans the ballots in tile order (ascending env ids, like reset_buf.nonzero()): thread t owns a
+    // contiguous run of tiles, so ids and the fp64 partial sums are combined in a fixed order.
+    __threadfence();
+    int *scan = reinterpret_cast<int *>(sm);                     // [128] tile-run counts (tile memory is free now)
+    double *red = reinterpret_cast<double *>(sm + 256);          // [HB_NUM_REWARDS][128]
+    const int tiles = gridDim.x;
+    const int per = (tiles + blockDim.x - 1) / blockDim.x;
+    const int t_lo = min((int)threadIdx.x * per, tiles), t_hi = min(t_lo + per, tiles);
+    int cnt = 0;
+    for (int t = t_lo; t < t_hi; ++t) cnt += __popc(__ldcg(b.scratch_ballots + t));
+    scan[threadIdx.x] = cnt;
+    __syncthreads();
+    int off = 0, total = 0;
+    for (int i = 0; i < (int)blockDim.x; ++i) {
+        const int c = scan[i];
+        off += (i < (int)threadIdx.x) ? c : 0;
+        total += c;
     }
-
-    // ---------------- ordered compaction of the reset ids + episode means ----------------
-    // Each warp publishes its ballot and the per-term sums of its reset envs; the last CTA to
-    // finish scans the ballots in tile order (ascending env ids, like reset_buf.nonzero()).
-    if (ballot) {
+    double acc[HB_NUM_REWARDS];
 #pragma unroll
-        for (int k = 0; k < HB_NUM_REWARDS; ++k) {
-            float v = my_sums[k];
+    for (int k = 0; k < HB_NUM_REWARDS; ++k) acc[k] = 0.0;
+    for (int t = t_lo; t < t_hi; ++t) {
+        unsigned m = __ldcg(b.scratch_ballots + t);
+        if (!m) continue;
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            if (lane == 0) b.scratch_partials[(size_t)blockIdx.x * HB_NUM_REWARDS + k] = v;
+        for (int k = 0; k < HB_NUM_REWARDS; ++k) acc[k] += (double)__ldcg(b.scratch_partials + (size_t)t * HB_NUM_REWARDS + k);
+        while (m) {
+            const int bit = __ffs(m) - 1;
+            m &= m - 1;
+            b.reset_env_ids[off++] = t * TILE + bit;
         }
     }
-    if (lane == 0) {
-        b.scratch_ballots[blockIdx.x] = ballot;
-        __threadfence();
-        const unsigned t = atomicAdd(b.scratch_ticket, 1u);
-        s_is_last = (t == gridDim.x - 1);
+#pragma unroll
+    for (int k = 0; k < HB_NUM_REWARDS; ++k) red[k * blockDim.x + threadIdx.x] = acc[k];
+    __syncthreads();
+    // extras["episode"] is only refreshed on steps with >= 1 reset (quirk 4): otherwise the previous
+    // values are carried into this step's slot.
+    if (threadIdx.x < HB_NUM_REWARDS) {
+        const int k = threadIdx.x;
+        if (total > 0) {
+            double v = 0.0;
+            for (int i = 0; i < (int)blockDim.x; ++i) v += red[k * blockDim.x + i];
+            b.episode_means[k] = (float)(v / (double)total) / p.max_episode_length_s;
+        } else if (b.episode_means_prev && b.episode_means_prev != b.episode_means) {
+            b.episode_means[k] = b.episode_means_prev[k];
+        }
     }
-    __syncwarp();
-    if (s_is_last) {
-        __threadfence();
-        const int tiles = gridDim.x;
-        int base = 0;
-        double acc[HB_NUM_REWARDS];
-#pragma unroll
-        for (int k = 0; k < HB_NUM_REWARDS; ++k) acc[k] = 0.0;
-        for (int t0 = 0; t0 < tiles; t0 += 32) {
-            const int t = t0 + lane;
-            const unsigned m = (t < tiles) ? __ldcg(b.scratch_ballots + t) : 0u;
-            const int cnt = __popc(m);
-            int incl = cnt;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int v = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += v;
-            }
-            int off = base + incl - cnt;
-            unsigned mm = m;
-            while (mm) {
-                const int bit = __ffs(mm) - 1;
-                mm &= mm - 1;
-                b.reset_env_ids[off++] = t * TILE + bit;
-            }
-            if (m) {
-#pragma unroll
-                for (int k = 0; k < HB_NUM_REWARDS; ++k)
-                    acc[k] += (double)__ldcg(b.scratch_partials + (size_t)t * HB_NUM_REWARDS + k);
-            }
-            base += __shfl_sync(0xffffffffu, incl, 31);
-        }
-        // extras["episode"] is only refreshed on steps with >= 1 reset (quirk 4): otherwise the
-        // previous values are carried into this step's slot.
-#pragma unroll
-        for (int k = 0; k < HB_NUM_REWARDS; ++k) {
-            double v = acc[k];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            if (lane == 0) {
-                if (base > 0) b.episode_means[k] = (float)(v / (double)base) / p.max_episode_length_s;
-                else if (b.episode_means_prev && b.episode_means_prev != b.episode_means)
-                    b.episode_means[k] = b.episode_means_prev[k];
-            }
-        }
-        if (lane == 0) {
-            *b.reset_count = base;
-            if (host_count) *host_count = base;
-            *b.scratch_ticket = 0u;      // re-arm for the next launch
-        }
+    if (threadIdx.x == 0) {
+        *b.reset_count = total;
+        if (host_count) *host_count = total;
+        *b.scratch_ticket = 0u;          // re-arm for the next launch
     }
 }
 
@@ -732,23 +743,25 @@ post_physics_kernel(const __grid_constant__ hb_env_params p, const __grid_consta
 // and takes the missing float from its neighbour lane (shuffle); F % 4 picks the rotation.
 // ------------------------------------------------------------------------------------------
 template <int UNROLL>
-__global__ void __launch_bounds__(256)
-stack_shift_kernel(const float *__restrict__ prev, float *__restrict__ next, const uint8_t *__restrict__ reset_buf,
-                   long long total_vec, int row, int frame, const uint8_t *__restrict__ latch_src,
-                   uint8_t *__restrict__ latch_dst, const int32_t *__restrict__ reset_count, int num_envs) {
+__device__ __forceinline__ void
+stack_shift_body(const float *__restrict__ prev, float *__restrict__ next, const uint8_t *__restrict__ reset_buf,
+                 long long total, int row, int frame, const uint8_t *__restrict__ latch_src,
+                 uint8_t *__restrict__ latch_dst, const int32_t *__restrict__ reset_count, int num_envs,
+                 const unsigned blk, const unsigned nblk) {
     const int lane = threadIdx.x & 31;
     const int keep = row - frame;                       // floats of a row that are carried over
     const int rot = frame & 3;                          // source misalignment in floats
     const int fvec = frame >> 2;                        // whole vectors of shift
-    const long long warp_base = ((long long)blockIdx.x * blockDim.x + threadIdx.x - lane) * UNROLL;
+    const long long warp_base = ((long long)blk * blockDim.x + threadIdx.x - lane) * UNROLL;
     // extras["time_outs"] latch (legged_robot.py:208-209 only runs when >= 1 env was reset)
     if (latch_dst && *reset_count > 0) {
-        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < num_envs;
-             i += (long long)gridDim.x * blockDim.x)
+        for (long long i = (long long)blk * blockDim.x + threadIdx.x; i < num_envs; i += (long long)nblk * blockDim.x)
             latch_dst[i] = latch_src[i];
     }
     const float4 *p4 = reinterpret_cast<const float4 *>(prev);
     float4 *n4 = reinterpret_cast<float4 *>(next);
+    const long long total_vec = total >> 2;             // whole vectors; a ragged tail (N*row % 4) goes scalar
+    const long long tail_vec = (total + 3) >> 2;
     float4 v[UNROLL];
     float nx31[UNROLL][3];
     // all loads first (UNROLL independent 16-byte requests in flight per thread)
@@ -756,13 +769,21 @@ stack_shift_kernel(const float *__restrict__ prev, float *__restrict__ next, con
     for (int u = 0; u < UNROLL; ++u) {
         const long long i = warp_base + (long long)u * 32 + lane;      // destination vector index
         const long long s = i + fvec;                                   // aligned source vector below the window
-        v[u] = (s < total_vec) ? hb::ld_stream4(p4 + s) : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (s < total_vec) {
+            v[u] = hb::ld_stream4(p4 + s);
+        } else {                                                        // ragged last vector of the buffer
+            const long long e = s * 4;
+            v[u].x = (e < total) ? __ldg(prev + e) : 0.0f;
+            v[u].y = (e + 1 < total) ? __ldg(prev + e + 1) : 0.0f;
+            v[u].z = (e + 2 < total) ? __ldg(prev + e + 2) : 0.0f;
+            v[u].w = 0.0f;
+        }
         nx31[u][0] = nx31[u][1] = nx31[u][2] = 0.0f;
-        if (lane == 31 && rot != 0 && s + 1 < total_vec) {              // no neighbour lane: fetch the spill-over
-            const float *e = prev + (s + 1) * 4;
-            nx31[u][0] = __ldg(e);
-            if (rot > 1) nx31[u][1] = __ldg(e + 1);
-            if (rot > 2) nx31[u][2] = __ldg(e + 2);
+        if (lane == 31 && rot != 0) {                                   // no neighbour lane: fetch the spill-over
+            const long long e = (s + 1) * 4;
+            if (e < total) nx31[u][0] = __ldg(prev + e);
+            if (rot > 1 && e + 1 < total) nx31[u][1] = __ldg(prev + e + 1);
+            if (rot > 2 && e + 2 < total) nx31[u][2] = __ldg(prev + e + 2);
         }
     }
 #pragma unroll
@@ -772,7 +793,7 @@ stack_shift_kernel(const float *__restrict__ prev, float *__restrict__ next, con
         float nx1 = __shfl_down_sync(0xffffffffu, v[u].y, 1);
         float nx2 = __shfl_down_sync(0xffffffffu, v[u].z, 1);
         if (lane == 31) nx0 = nx31[u][0], nx1 = nx31[u][1], nx2 = nx31[u][2];
-        if (i >= total_vec) continue;
+        if (i >= tail_vec) continue;
         float4 o;
         if (rot == 0) o = v[u];
         else if (rot == 1) o = make_float4(v[u].y, v[u].z, v[u].w, nx0);
@@ -781,7 +802,7 @@ stack_shift_kernel(const float *__restrict__ prev, float *__restrict__ next, con
         const long long e0 = i * 4;                      // first destination float
         const int r0 = (int)(e0 / row);
         const int c0 = (int)(e0 - (long long)r0 * row);
-        if (c0 + 3 < keep) {                             // whole vector inside the carried part of one row
+        if (c0 + 3 < keep && i < total_vec) {            // whole vector inside the carried part of one row
             if (reset_buf[r0]) o = make_float4(0.f, 0.f, 0.f, 0.f);
             hb::st_stream4(n4 + i, o);
         } else {                                         // touches the newest-frame hole or a row boundary
@@ -790,17 +811,45 @@ stack_shift_kernel(const float *__restrict__ prev, float *__restrict__ next, con
             for (int k = 0; k < 4; ++k) {
                 int r = r0, c = c0 + k;
                 if (c >= row) c -= row, r += 1;
-                if (c < keep) next[e0 + k] = reset_buf[r] ? 0.0f : ov[k];
+                if (c < keep && e0 + k < total) next[e0 + k] = reset_buf[r] ? 0.0f : ov[k];
             }
         }
     }
 }
 
+template <int UNROLL>
+__global__ void __launch_bounds__(256)
+stack_shift_kernel(const float *__restrict__ prev, float *__restrict__ next, const uint8_t *__restrict__ reset_buf,
+                   long long total, int row, int frame, const uint8_t *__restrict__ latch_src,
+                   uint8_t *__restrict__ latch_dst, const int32_t *__restrict__ reset_count, int num_envs) {
+    stack_shift_body<UNROLL>(prev, next, reset_buf, total, row, frame, latch_src, latch_dst, reset_count, num_envs,
+                             blockIdx.x, gridDim.x);
+}
+
+// actor and critic histories in one launch: blocks [0, blocks_a) shift buffer a, the rest buffer b
+template <int UNROLL>
+__global__ void __launch_bounds__(256)
+stack_shift_pair_kernel(const float *__restrict__ prev_a, float *__restrict__ next_a, long long total_a, int row_a,
+                        int frame_a, unsigned blocks_a, const float *__restrict__ prev_b, float *__restrict__ next_b,
+                        long long total_b, int row_b, int frame_b, const uint8_t *__restrict__ reset_buf,
+                        const uint8_t *__restrict__ latch_src, uint8_t *__restrict__ latch_dst,
+                        const int32_t *__restrict__ reset_count, int num_envs) {
+    if (blockIdx.x < blocks_a)
+        stack_shift_body<UNROLL>(prev_a, next_a, reset_buf, total_a, row_a, frame_a, latch_src, latch_dst, reset_count,
+                                 num_envs, blockIdx.x, blocks_a);
+    else
+        stack_shift_body<UNROLL>(prev_b, next_b, reset_buf, total_b, row_b, frame_b, nullptr, nullptr, nullptr, num_envs,
+                                 blockIdx.x - blocks_a, gridDim.x - blocks_a);
+}
+
 // generic fallback (rows not a multiple of 4 floats in total, or unaligned buffers)
 __global__ void __launch_bounds__(256)
 stack_shift_scalar_kernel(const float *__restrict__ prev, float *__restrict__ next,
-                          const uint8_t *__restrict__ reset_buf, long long total, int row, int frame) {
+                          const uint8_t *__restrict__ reset_buf, long long total, int row, int frame,
+                          const uint8_t *__restrict__ latch_src, uint8_t *__restrict__ latch_dst,
+                          const int32_t *__restrict__ reset_count, int num_envs) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (latch_dst && *reset_count > 0 && i < num_envs) latch_dst[i] = latch_src[i];
     if (i >= total) return;
     const int r = (int)(i / row), c = (int)(i - (long long)r * row);
     if (c < row - frame) next[i] = reset_buf[r] ? 0.0f : prev[i + frame];
@@ -901,14 +950,14 @@ int hb_env_post_physics(const hb_env_params *p, const hb_env_buffers *buf, const
             HB_CUDA(cudaFuncSetAttribute(post_physics_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
             attr_set[1] = true;
         }
-        post_physics_kernel<true><<<tiles, TILE, smem, (cudaStream_t)stream>>>(*p, *buf, *noise, obs_new, priv_new,
+        post_physics_kernel<true><<<tiles, 4 * TILE, smem, (cudaStream_t)stream>>>(*p, *buf, *noise, obs_new, priv_new,
                                                                                stages, host_count);
     } else {
         if (!attr_set[0]) {
             HB_CUDA(cudaFuncSetAttribute(post_physics_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
             attr_set[0] = true;
         }
-        post_physics_kernel<false><<<tiles, TILE, smem, (cudaStream_t)stream>>>(*p, *buf, *noise, obs_new, priv_new,
+        post_physics_kernel<false><<<tiles, 4 * TILE, smem, (cudaStream_t)stream>>>(*p, *buf, *noise, obs_new, priv_new,
                                                                                 stages, host_count);
     }
     HB_CHECK_LAUNCH("post_physics_kernel");
@@ -918,17 +967,27 @@ int hb_env_post_physics(const hb_env_params *p, const hb_env_buffers *buf, const
 static int launch_stack(const float *prev, float *next, const uint8_t *reset_buf, int n, int row, int frame,
                         const uint8_t *latch_src, uint8_t *latch_dst, const int32_t *reset_count, cudaStream_t st) {
     const long long total = (long long)n * row;
-    if ((total % 4) == 0 && hb::aligned16(prev) && hb::aligned16(next)) {
+    if (hb::aligned16(prev) && hb::aligned16(next)) {
         constexpr int UNROLL = 4;
-        const long long total_vec = total / 4;
-        const long long threads = (total_vec + UNROLL - 1) / UNROLL;
+        const long long vecs = (total + 3) / 4;
+        const long long threads = (vecs + UNROLL - 1) / UNROLL;
         const int blocks = (int)((threads + 255) / 256);
-        stack_shift_kernel<UNROLL><<<blocks, 256, 0, st>>>(prev, next, reset_buf, total_vec, row, frame, latch_src,
+        stack_shift_kernel<UNROLL><<<blocks, 256, 0, st>>>(prev, next, reset_buf, total, row, frame, latch_src,
                                                             latch_dst, reset_count, n);
     } else {
-        stack_shift_scalar_kernel<<<(int)((total + 255) / 256), 256, 0, st>>>(prev, next, reset_buf, total, row, frame);
+        stack_shift_scalar_kernel<<<(int)((total + 255) / 256), 256, 0, st>>>(prev, next, reset_buf, total, row, frame,
+                                                                               latch_src, latch_dst, reset_count, n);
     }
     return 0;
+}
+
+int hb_stack_shift(const float *prev, float *next, const uint8_t *reset_buf, int32_t num_envs, int32_t row,
+                   int32_t frame, void *stream) {
+    HB_REQUIRE(prev && next && reset_buf && prev != next, "hb_stack_shift: null or aliasing buffers");
+    HB_REQUIRE(num_envs > 0 && frame > 0 && row > frame, "hb_stack_shift: bad shape");
+    launch_stack(prev, next, reset_buf, num_envs, row, frame, nullptr, nullptr, nullptr, (cudaStream_t)stream);
+    HB_CHECK_LAUNCH("stack_shift_kernel");
+    return HB_OK;
 }
 
 int hb_env_stack_observations(const hb_env_params *p, const hb_env_buffers *buf, const float *obs_prev,
@@ -937,6 +996,19 @@ int hb_env_stack_observations(const hb_env_params *p, const hb_env_buffers *buf,
     HB_REQUIRE(obs_prev && priv_prev && obs_new && priv_new && buf->reset_buf, "hb_env_stack_observations: null buffer");
     HB_REQUIRE(obs_prev != obs_new && priv_prev != priv_new, "hb_env_stack_observations: prev and new must not alias");
     cudaStream_t st = (cudaStream_t)stream;
+    if (hb::aligned16(obs_prev) && hb::aligned16(obs_new) && hb::aligned16(priv_prev) && hb::aligned16(priv_new)) {
+        constexpr int UNROLL = 4;
+        const int row_a = p->frame_stack * p->num_single_obs, row_b = p->c_frame_stack * p->num_single_priv;
+        const long long total_a = (long long)p->num_envs * row_a, total_b = (long long)p->num_envs * row_b;
+        const unsigned blocks_a = (unsigned)(((total_a + 3) / 4 + UNROLL * 256 - 1) / (UNROLL * 256));
+        const unsigned blocks_b = (unsigned)(((total_b + 3) / 4 + UNROLL * 256 - 1) / (UNROLL * 256));
+        stack_shift_pair_kernel<UNROLL><<<blocks_a + blocks_b, 256, 0, st>>>(
+            obs_prev, obs_new, total_a, row_a, p->num_single_obs, blocks_a, priv_prev, priv_new, total_b, row_b,
+            p->num_single_priv, buf->reset_buf, buf->time_out_buf, buf->time_outs_latched, buf->reset_count,
+            p->num_envs);
+        HB_CHECK_LAUNCH("stack_shift_pair_kernel");
+        return HB_OK;
+    }
     launch_stack(obs_prev, obs_new, buf->reset_buf, p->num_envs, p->frame_stack * p->num_single_obs, p->num_single_obs,
                  buf->time_out_buf, buf->time_outs_latched, buf->reset_count, st);
     HB_CHECK_LAUNCH("stack_shift_kernel(obs)");

@@ -40,6 +40,28 @@ def _find(names, patterns):
     return [i for p in patterns for i, s in enumerate(names) if p in s]
 
 
+def _reset_pose_constants(quat_xyzw):
+    """Euler angles and projected gravity of the reset pose, in fp32 and in the reference's operation
+    order (get_euler_xyz_tensor, legged_robot.py:50-55; quat_rotate_inverse of (0,0,-1)): every reset
+    env gets base_init_state's quaternion, so reset_idx's recomputation (:211-214) is a constant."""
+    f = np.float32
+    x, y, z, w = (f(v) for v in quat_xyzw)
+    two_pi, pi = f(2 * np.pi), f(np.pi)
+    roll = np.arctan2(f(2.0) * (w * x + y * z), ((w * w - x * x) - y * y) + z * z, dtype=f)
+    sinp = f(2.0) * (w * y - z * x)
+    pitch = f(np.pi / 2.0) * np.sign(sinp) if abs(sinp) >= 1 else np.arcsin(sinp, dtype=f)
+    yaw = np.arctan2(f(2.0) * (w * z + x * y), ((w * w + x * x) - y * y) - z * z, dtype=f)
+    eul = []
+    for a in (roll, pitch, yaw):
+        a = f(np.remainder(f(a), two_pi))
+        eul.append(a - two_pi if a > pi else a)
+    u, v = np.array([x, y, z], dtype=f), np.array([0.0, 0.0, -1.0], dtype=f)
+    a = v * (f(2.0) * w * w - f(1.0))
+    b = np.cross(u, v).astype(f) * w * f(2.0)
+    c = u * f(np.dot(u, v)) * f(2.0)
+    return eul, (a - b) + c
+
+
 def build_env_params(cfg, num_envs: int, num_bodies: int, body_names, dof_names, dof_effort) -> EnvParams:
     """Resolve the config the way LeggedRobot._parse_cfg / _init_buffers / _prepare_reward_function /
     _get_noise_scale_vec do (legged_robot.py:433-540,711-722; hector_env.py:135-155); Python-double
@@ -92,6 +114,9 @@ def build_env_params(cfg, num_envs: int, num_bodies: int, body_names, dof_names,
     init = cfg.init_state.pos + cfg.init_state.rot + cfg.init_state.lin_vel + cfg.init_state.ang_vel
     for k in range(13):
         p.base_init_state[k] = init[k]
+    eul, grav = _reset_pose_constants(init[3:7])
+    for k in range(3):
+        p.reset_euler[k], p.reset_gravity[k] = float(eul[k]), float(grav[k])
     os_ = cfg.normalization.obs_scales
     p.obs_lin_vel, p.obs_ang_vel, p.obs_dof_pos, p.obs_dof_vel, p.obs_quat = (
         os_.lin_vel, os_.ang_vel, os_.dof_pos, os_.dof_vel, os_.quat)
@@ -215,10 +240,20 @@ class HectorFreeEnvB200:
         self._scratch_partials = z(tiles, HB_NUM_REWARDS)
         self._scratch_ticket = torch.zeros(1, dtype=torch.int32, device=dev)
         self._terrain_level_mean = torch.zeros((), **f32)
+        # extras["episode"] dicts are prebuilt views into the ring (no per-step tensor indexing)
+        self._extras_episode = []
+        for slot in range(_EXTRAS_RING):
+            d = {"rew_" + k: self._episode_means[slot, i] for i, k in enumerate(REWARD_NAMES) if k in self.reward_scales}
+            if cfg.terrain.mesh_type == "trimesh":
+                d["terrain_level"] = self._terrain_level_mean          # mean(terrain_levels): no curriculum -> constant
+            self._extras_episode.append(d)
+        self._events = [torch.cuda.Event(), torch.cuda.Event()] if dev.type == "cuda" else []
         self.extras: Dict = {}
         self.common_step_counter = 0
         self._step_index = 0
         self._pending_event: Optional[torch.cuda.Event] = None
+        self._graphs = None
+        self._last_means_slot = None
         self._injected = initial_noise      # draws consumed by the constructor's reset_idx(all)
         self._rng = torch.Generator(device=dev)
         self._rng.manual_seed(0)
@@ -288,20 +323,103 @@ class HectorFreeEnvB200:
     def step(self, actions: torch.Tensor):
         """hector_env.py:158-169 + legged_robot.py:84-108."""
         lib, st = self._lib, self._stream()
-        actions = actions.to(self.device, dtype=torch.float32).contiguous()
+        self._st = st
+        if actions.device != self.device or actions.dtype != torch.float32 or not actions.is_contiguous():
+            actions = actions.to(self.device, dtype=torch.float32).contiguous()
         self.common_step_counter += 1
         push = bool(self.cfg.domain_rand.push_robots) and (self.common_step_counter % self.push_interval == 0)
+        if self._graphs is not None and not push and self._injected is None:
+            return self._step_graph(actions)
         self._draw_noise(push)
         _lib.check(lib.hb_env_action_prologue(self._pp, self._pb, actions.data_ptr(), self._pn, st),
                    "hb_env_action_prologue")
+        phys, torques, pd, pp, pb = self.physics, self.torques, lib.hb_env_compute_torques, self._pp, self._pb
         for i in range(self.cfg.control.decimation):
-            self._compute_torques()
-            self.physics.set_dof_actuation_force(self.torques)
+            rc = pd(pp, pb, st)                   # _compute_torques, legged_robot.py:94
+            if rc:
+                _lib.check(rc, "hb_env_compute_torques")
+            phys.set_dof_actuation_force(torques)
             if i == 0:
                 self._apply_pending_resets()      # gym.set_*_indexed of the previous step's resets
-            self.physics.simulate()
-            self.physics.refresh_dof_state()
+            phys.simulate()
+            phys.refresh_dof_state()
         self.post_physics_step(push)
+        return self.obs_buf, self.privileged_obs_buf, self.rew_buf, self.reset_buf, self.extras
+
+    # ------------------------------------------------------------------ CUDA-graph replay of the step
+    def enable_cuda_graph(self):
+        """Capture the step's launch sequence for physics stages that need no host work between the
+        decimation sub-steps (`physics.capturable`, e.g. the synthetic stage used by tests and bench.py).
+        Two graphs per ping-pong parity: A = noise draws, action prologue, first PD launch; then the host
+        hands the previous step's reset ids to the physics stage (legged_robot.py:370-372,394-396) while A
+        runs; B = the remaining PD launches, post-physics and frame stacking.  Push steps (every
+        `push_interval`) and steps with injected noise take the eager path."""
+        if not getattr(self.physics, "capturable", False):
+            raise ValueError("this physics stage needs host calls between sub-steps; CUDA-graph replay is not possible")
+        if self.device.type != "cuda":
+            raise ValueError("CUDA graphs need a CUDA device")
+        N = self.num_envs
+        self._g_actions = torch.zeros(N, self.num_actions, device=self.device)
+        self._g_means = torch.zeros(2, HB_NUM_REWARDS, device=self.device)
+        self._apply_pending_resets()
+        torch.cuda.synchronize(self.device)
+        saved = (self._cur, self._step_index, self._pending_event)
+        graphs, pool = {}, None
+        lib = self._lib
+        dec = self.cfg.control.decimation
+        for parity in (0, 1):
+            self._cur = parity
+            ga, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            with torch.cuda.graph(ga, pool=pool):
+                st = self._stream()
+                u = torch.rand(N * (19 if self._p.action_delay != 0.0 else 18), device=self.device)
+                zn = torch.randn(N * 51, device=self.device)
+                nz = EnvNoise()
+                base = u.data_ptr()
+                nz.u_reset, nz.u_cmd = base, base + N * 15 * 4
+                nz.u_delay = base + N * 18 * 4 if self._p.action_delay != 0.0 else None
+                nz.z_action, nz.z_obs = zn.data_ptr(), zn.data_ptr() + N * 10 * 4
+                _lib.check(lib.hb_env_action_prologue(self._pp, self._pb, self._g_actions.data_ptr(), C.byref(nz), st),
+                           "hb_env_action_prologue")
+                _lib.check(lib.hb_env_compute_torques(self._pp, self._pb, st), "hb_env_compute_torques")
+            pool = pool or ga.pool()
+            with torch.cuda.graph(gb, pool=pool):
+                st = self._stream()
+                for _ in range(dec - 1):
+                    _lib.check(lib.hb_env_compute_torques(self._pp, self._pb, st), "hb_env_compute_torques")
+                prev, cur = parity, parity ^ 1
+                self._b.episode_means = self._g_means[cur].data_ptr()
+                self._b.episode_means_prev = self._g_means[prev].data_ptr()
+                _lib.check(lib.hb_env_post_physics(self._pp, self._pb, C.byref(nz), self._obs[cur].data_ptr(),
+                                                   self._priv[cur].data_ptr(), HB_STAGE_STEP,
+                                                   self._host_count.data_ptr(), st), "hb_env_post_physics")
+                _lib.check(lib.hb_env_stack_observations(self._pp, self._pb, self._obs[prev].data_ptr(),
+                                                         self._priv[prev].data_ptr(), self._obs[cur].data_ptr(),
+                                                         self._priv[cur].data_ptr(), st), "hb_env_stack_observations")
+            graphs[parity] = (ga, gb, u, zn)
+        self._cur, self._step_index, self._pending_event = saved
+        self._graphs = graphs
+        self.graph_launches_per_step = 1 + dec + 2     # this library's kernels per replayed step (prologue, PD, post, stack)
+
+    def _step_graph(self, actions):
+        ga, gb, _, _ = self._graphs[self._cur]
+        self._g_actions.copy_(actions, non_blocking=True)
+        slot = self._step_index % _EXTRAS_RING
+        if self._step_index > 0 and self._last_means_slot is not None:
+            # the previous step ran eagerly: hand its episode means to the graph's carry-over slot
+            self._g_means[self._cur].copy_(self._episode_means[self._last_means_slot], non_blocking=True)
+        ga.replay()
+        self._apply_pending_resets()          # gym.set_*_indexed of the previous step's resets
+        gb.replay()
+        self._cur ^= 1
+        self._episode_means[slot].copy_(self._g_means[self._cur], non_blocking=True)
+        self._last_means_slot = None
+        self._pending_event = self._events[self._step_index & 1]
+        self._pending_event.record(torch.cuda.current_stream(self.device))
+        self.extras["episode"] = self._extras_episode[slot]
+        if self.cfg.env.send_timeouts:
+            self.extras["time_outs"] = self._time_outs_latched
+        self._step_index += 1
         return self.obs_buf, self.privileged_obs_buf, self.rew_buf, self.reset_buf, self.extras
 
     def _compute_torques(self, actions=None):
@@ -324,8 +442,9 @@ class HectorFreeEnvB200:
         emit = bool(stages & (HB_STAGE_STEP | HB_STAGE_OBS))
         slot = self._step_index % _EXTRAS_RING
         prev_slot = (self._step_index - 1) % _EXTRAS_RING
-        self._b.episode_means = self._episode_means[slot].data_ptr()
-        self._b.episode_means_prev = self._episode_means[prev_slot].data_ptr() if self._step_index > 0 else None
+        means0 = self._episode_means.data_ptr()
+        self._b.episode_means = means0 + slot * HB_NUM_REWARDS * 4
+        self._b.episode_means_prev = means0 + prev_slot * HB_NUM_REWARDS * 4 if self._step_index > 0 else None
         host_count = self._host_count.data_ptr()
         _lib.check(lib.hb_env_post_physics(self._pp, self._pb, self._pn, self._obs[cur].data_ptr(),
                                            self._priv[cur].data_ptr(), stages, host_count, st), "hb_env_post_physics")
@@ -334,15 +453,13 @@ class HectorFreeEnvB200:
                                                      self._priv[prev].data_ptr(), self._obs[cur].data_ptr(),
                                                      self._priv[cur].data_ptr(), st), "hb_env_stack_observations")
             self._cur = cur
-        if self.device.type == "cuda":
-            self._pending_event = torch.cuda.Event()
+        if self._events:
+            self._pending_event = self._events[self._step_index & 1]
             self._pending_event.record(torch.cuda.current_stream(self.device))
-        means = self._episode_means[slot]
-        self.extras["episode"] = {"rew_" + k: means[i] for i, k in enumerate(REWARD_NAMES) if k in self.reward_scales}
-        if self.cfg.terrain.mesh_type == "trimesh":
-            self.extras["episode"]["terrain_level"] = self._terrain_level_mean
+        self.extras["episode"] = self._extras_episode[slot]
         if self.cfg.env.send_timeouts:
             self.extras["time_outs"] = self._time_outs_latched
+        self._last_means_slot = slot
         self._step_index += 1
         self._injected = None
         self._nz.u_reset = None

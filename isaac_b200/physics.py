@@ -25,6 +25,8 @@ import torch
 class SyntheticPhysics:
     """Gym-layout state tensors on `device`; `simulate()` is a no-op."""
 
+    capturable = True      # no host work between decimation sub-steps: the env step may be replayed as a CUDA graph
+
     def __init__(self, num_envs: int, num_dof: int = 10, num_bodies: int = 11, device="cuda:0"):
         self.num_envs, self.num_dof, self.num_bodies = num_envs, num_dof, num_bodies
         self.device = torch.device(device)

@@ -72,7 +72,10 @@ def compare_records(got, want):
     for k in want:
         if k in EXACT or k in ("input_checksum", "reward_names"):
             continue
-        assert_close(k, got[k], want[k])
+        w = want[k]
+        if k.endswith("_init"):      # the constructor's compute_observations() is not clipped by the reference
+            w = np.clip(w, -100.0, 100.0)   # (only step() clips, legged_robot.py:104-107); history frames are equal after the clip
+        assert_close(k, got[k], w)
 
 
 @pytest.mark.parametrize("bulk", [1, 0])
@@ -195,3 +198,38 @@ def test_reset_then_step_matches_reference_reset(lib, cuda_device):
     assert_close("priv", to_np(out[1]), want[1].numpy())
     assert_close("rew", to_np(out[2]), want[2].numpy())
     assert_equal("reset", to_np(out[3]), to_np(want[3]))
+
+
+def test_cuda_graph_replay_equals_eager(lib, cuda_device):
+    """The captured step (2 graphs per ping-pong parity) must produce exactly what the eager launches
+    produce from the same state and the same draws."""
+    import copy
+    from isaac_b200.synthetic import NoiseFrame
+    dev = cuda_device
+    n = 512
+    tape = make_tape(n, 6, seed=21, fall_prob=0.02)
+    env_g, phys_g = make_cuda_env(tape, dev)
+    env_e, phys_e = make_cuda_env(tape, dev)
+    env_g.enable_cuda_graph()
+    for t in range(1, 6):
+        fr = tape.physics[t].to(dev)
+        phys_g.load_frame(fr), phys_e.load_frame(fr)
+        actions = tape.noise[t].actions.to(dev)
+        parity = env_g._cur
+        out_g = env_g.step(actions)
+        _, _, u, zn = env_g._graphs[parity]
+        nz = NoiseFrame(actions=actions, u_delay=torch.zeros(n, 1, device=dev), z_action=zn[:n * 10].view(n, 10),
+                        u_cmd=u[n * 15:n * 18].view(n, 3), u_push=torch.zeros(n, 5, device=dev),
+                        u_reset=u[:n * 15].view(n, 15), z_obs=zn[n * 10:].view(n, 41))
+        env_e.inject_noise(nz)
+        out_e = env_e.step(actions)
+        torch.cuda.synchronize()
+        for a, b, name in zip(out_g[:4], out_e[:4], ("obs", "priv", "rew", "reset")):
+            assert torch.equal(a, b), f"{name} differs at step {t}"
+        assert torch.equal(out_g[4]["time_outs"], out_e[4]["time_outs"])
+        for k in out_e[4]["episode"]:
+            assert torch.equal(out_g[4]["episode"][k], out_e[4]["episode"][k]), k
+        assert torch.equal(env_g.episode_length_buf, env_e.episode_length_buf)
+        assert torch.equal(env_g._episode_sums, env_e._episode_sums)
+    env_g._apply_pending_resets()
+    assert phys_g.calls["set_dof_state_indexed"] >= 1
