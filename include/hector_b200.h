@@ -215,6 +215,88 @@ int hb_gae_normalize(float *advantages, const double *stats, int64_t count, void
 /* Same, when `stats` were summed over `stat_count` samples (all ranks) and this rank holds `count`. */
 int hb_gae_normalize_n(float *advantages, const double *stats, int64_t stat_count, int64_t count, void *stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * PPO update (algo/ppo/ppo.py:119-184, actor_critic.py:36-128, rollout_storage.py:146-182)
+ * ---------------------------------------------------------------------------------------------- */
+
+/* One GEMM of the ActorCritic MLPs on the tcgen05 tensor cores (TF32 operands read from fp32
+ * storage through TMA, fp32 accumulation in TMEM):   D[M,N] (+)= A[M,K] * B[N,K]^T.
+ * K-major operand: memory is [rows(M or N), K] row-major.  MN-major operand (a_mn_major /
+ * b_mn_major = 1): memory is [K, rows] row-major, i.e. the same row-major activations / weights
+ * seen from the backward pass; no transposed copies are made.  Leading dimensions are in floats
+ * and must be multiples of 4; base pointers 16-byte aligned. */
+enum hb_gemm_epilogue {
+    HB_EPI_STORE = 0,      /* D = acc */
+    HB_EPI_BIAS = 1,       /* D = acc + bias[n]                       nn.Linear (actor_critic.py:62,74) */
+    HB_EPI_BIAS_ELU = 2,   /* D = elu(acc + bias[n])                  nn.Linear + nn.ELU (:56-60) */
+    HB_EPI_ELU_BWD = 3,    /* D = acc * elu'(z) with H = elu(z)       autograd of the above */
+    HB_EPI_ATOMIC_ADD = 4  /* D += acc (split-K weight gradients; D must be zeroed by the caller) */
+};
+typedef struct hb_gemm_desc {
+    const float *A, *B;
+    float *D;
+    int32_t M, N, K;
+    int32_t lda, ldb, ldd;
+    int32_t a_mn_major, b_mn_major;
+    int32_t epilogue;            /* hb_gemm_epilogue */
+    const float *bias;           /* bias[n * bias_stride] */
+    int32_t bias_stride;
+    const float *H;              /* HB_EPI_ELU_BWD: forward activations [M, ldh] */
+    int32_t ldh;
+    int32_t split_k;             /* >1: split the contraction over gridDim.z (HB_EPI_ATOMIC_ADD only) */
+    int32_t tile_n;              /* 0 = automatic; 128 forces 128-wide tiles */
+} hb_gemm_desc;
+int hb_gemm_tf32(const hb_gemm_desc *desc, void *stream);
+
+/* mini_batch_generator's index gathers (rollout_storage.py:165-180), done once per update because the
+ * permutation is drawn once and reused by every epoch (:149): dst[i, 0:cols] = src[perm[i], 0:cols];
+ * if ones_col >= 0, dst[i, ones_col] = 1 (the constant column that turns bias gradients into one more
+ * column of the weight-gradient GEMM). */
+int hb_ppo_gather_rows(const float *src, int32_t ld_src, float *dst, int32_t ld_dst, const int64_t *perm,
+                       int64_t rows, int32_t cols, int32_t ones_col, void *stream);
+
+/* Per-sample record, gathered in minibatch order: actions[10] old_mu[10] old_sigma[10] old_value advantage
+ * return old_log_prob (HB_PPO_REC floats). */
+#define HB_PPO_ACT 10
+#define HB_PPO_REC 36
+int hb_ppo_pack_samples(const int64_t *perm, int64_t rows, const float *actions, const float *mu, const float *sigma,
+                        const float *values, const float *advantages, const float *returns, const float *log_prob,
+                        float *records, void *stream);
+
+typedef struct hb_ppo_loss_params {
+    float clip_param, value_loss_coef, entropy_coef;
+    int32_t use_clipped_value_loss;
+} hb_ppo_loss_params;
+/* Loss head and its analytic backward for one minibatch (ppo.py:130-168): Gaussian log-prob, ratio,
+ * clipped surrogate, clipped value loss, entropy bonus, KL to the behaviour policy.
+ * mu [mb, ld_mu] (first 10 columns), value [mb, ld_v] (first column), std[10], records [mb, HB_PPO_REC].
+ * Writes d_mu [mb, ld_mu] and d_value [mb, ld_v] (padding columns zeroed), accumulates d_std[10] and
+ * stats[4] = {sum surrogate, sum value loss, sum kl, sum entropy} (fp64; caller zeroes both). */
+int hb_ppo_loss_head(const float *mu, int32_t ld_mu, const float *value, int32_t ld_v, const float *std,
+                     const float *records, int64_t mb, int64_t mb_global, const hb_ppo_loss_params *lp, float *d_mu,
+                     float *d_value, float *d_std, double *stats, void *stream);
+
+/* PPO.act head (ppo.py:91-101, actor_critic.py:111-120): a = mu + sigma*eps, log-prob, copies of mu/sigma. */
+int hb_ppo_act_head(const float *mu, int32_t ld_mu, const float *std, const float *eps, int64_t n, float *actions,
+                    float *log_prob, float *mu_out, float *sigma_out, void *stream);
+
+typedef struct hb_adam_params {
+    float beta1, beta2, eps;
+    float max_grad_norm;          /* clip_grad_norm_ (ppo.py:173); <= 0 disables clipping */
+    double bias_correction1;      /* 1 - beta1^t */
+    double bias_correction2;      /* 1 - beta2^t */
+    /* adaptive learning rate (ppo.py:136-148), evaluated on the device from the KL sum of the loss head */
+    int32_t adaptive;             /* 1: schedule == 'adaptive' and desired_kl is set */
+    double desired_kl;
+    int64_t kl_count;             /* samples behind stats[2] */
+} hb_adam_params;
+/* clip_grad_norm_ + torch.optim.Adam.step (defaults, no weight decay) over one flat parameter buffer.
+ * grad_sumsq: fp64 scalar (zeroed by the caller) that hb_grad_sumsq fills; lr_io: fp64 learning rate on
+ * the device, updated in place by the adaptive schedule from kl_stats[2].  Gradients are zeroed. */
+int hb_grad_sumsq(const float *grads, int64_t n, double *grad_sumsq, void *stream);
+int hb_adam_step(float *params, float *grads, float *exp_avg, float *exp_avg_sq, int64_t n, const hb_adam_params *ap,
+                 const double *grad_sumsq, const double *kl_stats, double *lr_io, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

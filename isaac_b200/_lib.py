@@ -80,6 +80,25 @@ class EnvNoise(C.Structure):
     _fields_ = [(name, _fp) for name in _NOISE_FIELDS]
 
 
+HB_EPI_STORE, HB_EPI_BIAS, HB_EPI_BIAS_ELU, HB_EPI_ELU_BWD, HB_EPI_ATOMIC_ADD = range(5)
+HB_PPO_ACT, HB_PPO_REC = 10, 36
+
+
+class GemmDesc(C.Structure):
+    _fields_ = [("A", _fp), ("B", _fp), ("D", _fp), ("M", _i), ("N", _i), ("K", _i), ("lda", _i), ("ldb", _i),
+                ("ldd", _i), ("a_mn_major", _i), ("b_mn_major", _i), ("epilogue", _i), ("bias", _fp),
+                ("bias_stride", _i), ("H", _fp), ("ldh", _i), ("split_k", _i), ("tile_n", _i)]
+
+
+class PpoLossParams(C.Structure):
+    _fields_ = [("clip_param", _f), ("value_loss_coef", _f), ("entropy_coef", _f), ("use_clipped_value_loss", _i)]
+
+
+class AdamParams(C.Structure):
+    _fields_ = [("beta1", _f), ("beta2", _f), ("eps", _f), ("max_grad_norm", _f), ("bias_correction1", C.c_double),
+                ("bias_correction2", C.c_double), ("adaptive", _i), ("desired_kl", C.c_double), ("kl_count", C.c_int64)]
+
+
 class HectorB200Error(RuntimeError):
     pass
 
@@ -103,6 +122,14 @@ _SIGNATURES = {
                                       C.c_int32, _fp, _fp]),
     "hb_env_stack_observations": (C.c_int, [C.POINTER(EnvParams), C.POINTER(EnvBuffers), _fp, _fp, _fp, _fp, _fp]),
     "hb_stack_shift": (C.c_int, [_fp, _fp, _fp, C.c_int32, C.c_int32, C.c_int32, _fp]),
+    "hb_gemm_tf32": (C.c_int, [C.POINTER(GemmDesc), _fp]),
+    "hb_ppo_gather_rows": (C.c_int, [_fp, C.c_int32, _fp, C.c_int32, _fp, C.c_int64, C.c_int32, C.c_int32, _fp]),
+    "hb_ppo_pack_samples": (C.c_int, [_fp, C.c_int64, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp]),
+    "hb_ppo_loss_head": (C.c_int, [_fp, C.c_int32, _fp, C.c_int32, _fp, _fp, C.c_int64, C.c_int64,
+                                   C.POINTER(PpoLossParams), _fp, _fp, _fp, _fp, _fp]),
+    "hb_ppo_act_head": (C.c_int, [_fp, C.c_int32, _fp, _fp, C.c_int64, _fp, _fp, _fp, _fp, _fp]),
+    "hb_grad_sumsq": (C.c_int, [_fp, C.c_int64, _fp, _fp]),
+    "hb_adam_step": (C.c_int, [_fp, _fp, _fp, _fp, C.c_int64, C.POINTER(AdamParams), _fp, _fp, _fp, _fp]),
     "hb_gae_returns": (C.c_int, [_fp, _fp, _fp, _fp, _fp, _fp, _fp, C.c_int32, C.c_int32, C.c_float, C.c_float, _fp]),
     "hb_gae_normalize": (C.c_int, [_fp, _fp, C.c_int64, _fp]),
     "hb_gae_normalize_n": (C.c_int, [_fp, _fp, C.c_int64, C.c_int64, _fp]),

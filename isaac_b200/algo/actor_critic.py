@@ -1,0 +1,245 @@
+"""`ActorCritic` with the reference's interface (algo/ppo/actor_critic.py:36-128) on the tcgen05 GEMM path.
+
+Parameters live in ONE flat fp32 buffer so that gradient all-reduce, clip_grad_norm_ and Adam are single
+passes.  Each `nn.Linear` is a packed matrix `P[out_pad, ld]` = `[W | b | 0-pad]` with `ld = pad4(in + 1)`:
+  * the forward GEMM reads `W` through a TMA tensor map with K extent `in` and takes the bias from column `in`;
+  * the weight-gradient GEMM multiplies by the activations extended with a constant ones column, so the bias
+    gradient is simply column `in` of the packed gradient — no separate reduction kernel;
+  * rows are 16-byte aligned (615*4 and 1050*4 are not, SURVEY.md §7 hard part 2).
+`state_dict()` / `load_state_dict()` use the reference's keys (`actor.{0,2,4,6}.{weight,bias}`,
+`critic.{0,2,4,6}.{weight,bias}`, `std`), so checkpoints interchange.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from collections import OrderedDict
+from typing import Dict, List, Optional
+
+import torch
+
+from .. import _lib
+from .._lib import (GemmDesc, HB_EPI_ATOMIC_ADD, HB_EPI_BIAS, HB_EPI_BIAS_ELU, HB_EPI_ELU_BWD, HB_PPO_ACT)
+
+
+def pad4(n: int) -> int:
+    return (n + 3) // 4 * 4
+
+
+class _Layer:
+    __slots__ = ("net", "index", "fan_in", "fan_out", "rows", "ld", "offset", "last")
+
+    def __init__(self, net, index, fan_in, fan_out, last, offset):
+        self.net, self.index, self.fan_in, self.fan_out, self.last, self.offset = net, index, fan_in, fan_out, last, offset
+        self.rows = 16 if last else fan_out          # output layers are padded to the smallest UMMA N
+        self.ld = pad4(fan_in + 1)
+
+    @property
+    def numel(self):
+        return self.rows * self.ld
+
+
+def gemm(lib, st, **kw):
+    d = GemmDesc()
+    for k, v in kw.items():
+        setattr(d, k, v)
+    _lib.check(lib.hb_gemm_tf32(C.byref(d), st), "hb_gemm_tf32")
+
+
+class ActorCritic:
+    is_recurrent = False
+
+    def __init__(self, num_actor_obs, num_critic_obs, num_actions, actor_hidden_dims=(256, 256, 256),
+                 critic_hidden_dims=(256, 256, 256), init_noise_std=1.0, activation=None, device="cuda:0", **kwargs):
+        if kwargs:
+            print("ActorCritic.__init__ got unexpected arguments, which will be ignored: " + str(list(kwargs)))
+        if num_actions != HB_PPO_ACT:
+            raise ValueError(f"the loss-head kernels are built for {HB_PPO_ACT} actions (hector)")
+        if len(actor_hidden_dims) != 3 or len(critic_hidden_dims) != 3:
+            raise ValueError("three hidden layers per network (hector_config.py:207-210)")
+        self._lib = _lib.load()
+        self.device = torch.device(device)
+        self.num_actor_obs, self.num_critic_obs, self.num_actions = num_actor_obs, num_critic_obs, num_actions
+        self.layers: List[_Layer] = []
+        off = 0
+        for net, dims in (("actor", (num_actor_obs, *actor_hidden_dims, num_actions)),
+                          ("critic", (num_critic_obs, *critic_hidden_dims, 1))):
+            for i in range(4):
+                L = _Layer(net, 2 * i, dims[i], dims[i + 1], i == 3, off)
+                self.layers.append(L)
+                off += L.numel
+        self._std_offset = off
+        off += 16
+        self.flat = torch.zeros(off, device=self.device)
+        self.grad = torch.zeros(off, device=self.device)
+        # default nn.Linear initialisation, drawn in the reference's module construction order
+        # (actor layers, critic layers, then std: actor_critic.py:54-83) so the same torch seed gives the same net
+        for L in self.layers:
+            lin = torch.nn.Linear(L.fan_in, L.fan_out)
+            self._matrix(self.flat, L)[:L.fan_out, :L.fan_in] = lin.weight.detach().to(self.device)
+            self._matrix(self.flat, L)[:L.fan_out, L.fan_in] = lin.bias.detach().to(self.device)
+        self.flat[self._std_offset:self._std_offset + num_actions] = init_noise_std
+        self.distribution = None
+        self._ws: Dict[int, dict] = {}
+        self._last: Optional[dict] = None
+
+    # ------------------------------------------------------------------ parameter views
+    def _matrix(self, flat, L):
+        return flat[L.offset:L.offset + L.numel].view(L.rows, L.ld)
+
+    @property
+    def std(self):
+        return self.flat[self._std_offset:self._std_offset + self.num_actions]
+
+    def named_parameters(self):
+        """Views in the order of the reference module's `parameters()` (std first, then actor, critic)."""
+        yield "std", self.std
+        for L in self.layers:
+            P = self._matrix(self.flat, L)
+            yield f"{L.net}.{L.index}.weight", P[:L.fan_out, :L.fan_in]
+            yield f"{L.net}.{L.index}.bias", P[:L.fan_out, L.fan_in]
+
+    def named_gradients(self):
+        yield "std", self.grad[self._std_offset:self._std_offset + self.num_actions]
+        for L in self.layers:
+            G = self._matrix(self.grad, L)
+            yield f"{L.net}.{L.index}.weight", G[:L.fan_out, :L.fan_in]
+            yield f"{L.net}.{L.index}.bias", G[:L.fan_out, L.fan_in]
+
+    def parameters(self):
+        return [p for _, p in self.named_parameters()]
+
+    def state_dict(self):
+        return OrderedDict((k, v.detach().clone().contiguous()) for k, v in self.named_parameters())
+
+    def load_state_dict(self, sd, strict=True):
+        views = dict(self.named_parameters())
+        if strict and set(sd) != set(views):
+            raise KeyError(f"state_dict keys differ: {sorted(set(sd) ^ set(views))}")
+        for k, v in sd.items():
+            if k in views:
+                views[k].copy_(v.to(self.device))
+
+    def to(self, device):
+        if torch.device(device) != self.device:
+            raise ValueError("ActorCritic lives on the device it was created on")
+        return self
+
+    def train(self, mode=True):
+        return self
+
+    def eval(self):
+        return self
+
+    def reset(self, dones=None):
+        pass
+
+    def forward(self):
+        raise NotImplementedError
+
+    # ------------------------------------------------------------------ workspaces
+    def workspace(self, m: int) -> dict:
+        """Activation buffers for a batch of m rows; hidden activations carry the constant ones column at
+        index `width` that feeds the bias gradients."""
+        ws = self._ws.get(m)
+        if ws is None:
+            z = lambda r, c: torch.zeros(r, c, device=self.device)
+            ws = {"m": m}
+            for net in ("actor", "critic"):
+                Ls = [L for L in self.layers if L.net == net]
+                hs = []
+                for L in Ls[:-1]:
+                    h = z(m, pad4(L.fan_out + 1))
+                    h[:, L.fan_out] = 1.0
+                    hs.append(h)
+                ws[net] = {"h": hs, "out": z(m, 16), "d_out": z(m, 16),
+                           "dz": [z(m, L.fan_out) for L in Ls[:-1]]}
+            self._ws[m] = ws
+        return ws
+
+    # ------------------------------------------------------------------ forward
+    def _mlp_forward(self, net: str, x: torch.Tensor, ws: dict):
+        """x: [m, ld] with ld % 4 == 0 (only the first fan_in columns are read).  Returns out [m,16]."""
+        lib, st = self._lib, torch.cuda.current_stream(self.device).cuda_stream
+        Ls = [L for L in self.layers if L.net == net]
+        a, lda = x, x.stride(0)
+        m = x.shape[0]
+        for i, L in enumerate(Ls):
+            P = self._matrix(self.flat, L)
+            d = ws[net]["out"] if L.last else ws[net]["h"][i]
+            gemm(lib, st, A=a.data_ptr(), B=P.data_ptr(), D=d.data_ptr(), M=m, N=L.rows if L.last else L.fan_out,
+                 K=L.fan_in, lda=lda, ldb=L.ld, ldd=d.stride(0), epilogue=HB_EPI_BIAS if L.last else HB_EPI_BIAS_ELU,
+                 bias=P.data_ptr() + L.fan_in * 4, bias_stride=L.ld)
+            a, lda = d, d.stride(0)
+        return ws[net]["out"]
+
+    def _mlp_backward(self, net: str, x: torch.Tensor, ws: dict):
+        """Gradients of every packed matrix of `net` from d_out (filled by the loss head); accumulates into
+        self.grad with split-K atomics (the buffer is zero on entry: Adam zeroes it)."""
+        lib, st = self._lib, torch.cuda.current_stream(self.device).cuda_stream
+        Ls = [L for L in self.layers if L.net == net]
+        m = x.shape[0]
+        kb_total = (m + 31) // 32
+        d_cur, ld_cur = ws[net]["d_out"], 16               # gradient w.r.t. the layer's pre-activation output
+        for i in reversed(range(4)):
+            L = Ls[i]
+            G = self._matrix(self.grad, L)
+            act_in = x if i == 0 else ws[net]["h"][i - 1]      # [m, fan_in (+ ones column)]
+            n_w = L.fan_in + 1
+            tiles = ((L.rows + 127) // 128) * ((n_w + 255) // 256)
+            splits = max(1, min(kb_total, (2 * 148) // tiles))
+            # weight gradient: G[rows, fan_in + 1] += d_cur^T [rows, m] * [act_in | 1] [m, fan_in + 1]
+            gemm(lib, st, A=d_cur.data_ptr(), B=act_in.data_ptr(), D=G.data_ptr(), M=L.rows, N=n_w, K=m, lda=ld_cur,
+                 ldb=act_in.stride(0), ldd=L.ld, a_mn_major=1, b_mn_major=1, epilogue=HB_EPI_ATOMIC_ADD, split_k=splits)
+            if i == 0:
+                break
+            # data gradient through the previous ELU: dz_prev = (d_cur * W) . elu'(h_prev)
+            P = self._matrix(self.flat, L)
+            h_prev, dz = ws[net]["h"][i - 1], ws[net]["dz"][i - 1]
+            gemm(lib, st, A=d_cur.data_ptr(), B=P.data_ptr(), D=dz.data_ptr(), M=m, N=L.fan_in, K=L.rows, lda=ld_cur,
+                 ldb=L.ld, ldd=dz.stride(0), b_mn_major=1, epilogue=HB_EPI_ELU_BWD, H=h_prev.data_ptr(),
+                 ldh=h_prev.stride(0))
+            d_cur, ld_cur = dz, dz.stride(0)
+
+    def _as_operand(self, x: torch.Tensor, width: int) -> torch.Tensor:
+        """TMA needs 16-byte aligned rows: use x in place when its row stride allows, else stage a padded copy."""
+        if x.is_cuda and x.dtype == torch.float32 and x.stride(-1) == 1 and x.stride(0) % 4 == 0 and x.data_ptr() % 16 == 0:
+            return x
+        buf = torch.zeros(x.shape[0], pad4(width + 1), device=self.device)
+        buf[:, :width] = x
+        return buf
+
+    # ------------------------------------------------------------------ reference-named API
+    def act_inference(self, observations):
+        ws = self.workspace(observations.shape[0])
+        out = self._mlp_forward("actor", self._as_operand(observations, self.num_actor_obs), ws)
+        return out[:, :self.num_actions].clone()
+
+    def evaluate(self, critic_observations, **kwargs):
+        ws = self.workspace(critic_observations.shape[0])
+        out = self._mlp_forward("critic", self._as_operand(critic_observations, self.num_critic_obs), ws)
+        return out[:, :1].clone()
+
+    def update_distribution(self, observations):
+        ws = self.workspace(observations.shape[0])
+        out = self._mlp_forward("actor", self._as_operand(observations, self.num_actor_obs), ws)
+        mean = out[:, :self.num_actions]
+        self.distribution = torch.distributions.Normal(mean, mean * 0.0 + self.std, validate_args=False)
+
+    def act(self, observations, **kwargs):
+        self.update_distribution(observations)
+        return self.distribution.sample()
+
+    def get_actions_log_prob(self, actions):
+        return self.distribution.log_prob(actions).sum(dim=-1)
+
+    @property
+    def action_mean(self):
+        return self.distribution.mean
+
+    @property
+    def action_std(self):
+        return self.distribution.stddev
+
+    @property
+    def entropy(self):
+        return self.distribution.entropy().sum(dim=-1)

@@ -1,0 +1,218 @@
+"""`PPO` with the reference's interface (algo/ppo/ppo.py:38-184) on the B200 kernels.
+
+    act / process_env_step / compute_returns / update       same signatures and semantics
+    actor_critic, optimizer.state_dict(), learning_rate, storage, transition   same attributes
+
+Per minibatch step: 8 forward GEMMs (tcgen05, TF32 operands, fused bias+ELU), one loss-head kernel
+(log-prob, clipped surrogate, clipped value loss, entropy, KL and their analytic gradients), 6 data-gradient
+GEMMs (fused ELU'), 8 split-K weight-gradient GEMMs (bias gradients ride along as one more column), one
+gradient-norm reduction and one fused clip + Adam kernel that also applies the adaptive-KL learning-rate rule
+on the device (no `.item()` sync per minibatch; the reference needs ~22).  The minibatch
+permutation is drawn once per update and reused by every epoch (rollout_storage.py:149), so the index gathers
+of `mini_batch_generator` are done once per update into minibatch-ordered buffers.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from .. import _lib
+from .._lib import AdamParams, HB_PPO_REC, PpoLossParams
+from .actor_critic import ActorCritic, pad4
+from .rollout_storage import RolloutStorage
+
+
+class _AdamState:
+    """torch.optim.Adam-compatible view of the fused optimizer state (on_policy_runner.py:281-282,291-293)."""
+
+    def __init__(self, ppo: "PPO"):
+        self._ppo = ppo
+        self.param_groups = [{"lr": ppo._lr_host, "betas": (0.9, 0.999), "eps": 1e-8, "weight_decay": 0,
+                              "amsgrad": False, "params": list(range(17))}]
+
+    def _views(self, flat):
+        ac = self._ppo.actor_critic
+        saved = ac.flat
+        try:
+            ac.flat = flat
+            return [v for _, v in ac.named_parameters()]
+        finally:
+            ac.flat = saved
+
+    def state_dict(self):
+        p = self._ppo
+        state = {}
+        if p._step > 0:
+            for i, (m, v) in enumerate(zip(self._views(p._exp_avg), self._views(p._exp_avg_sq))):
+                state[i] = {"step": torch.tensor(float(p._step)), "exp_avg": m.clone().contiguous(),
+                            "exp_avg_sq": v.clone().contiguous()}
+        groups = [dict(self.param_groups[0], lr=p.learning_rate)]
+        return {"state": state, "param_groups": groups}
+
+    def load_state_dict(self, sd):
+        p = self._ppo
+        for i, (m, v) in enumerate(zip(self._views(p._exp_avg), self._views(p._exp_avg_sq))):
+            if i in sd["state"]:
+                m.copy_(sd["state"][i]["exp_avg"].to(m.device))
+                v.copy_(sd["state"][i]["exp_avg_sq"].to(v.device))
+                p._step = int(sd["state"][i]["step"])
+        p.learning_rate = sd["param_groups"][0]["lr"]
+
+
+class PPO:
+    actor_critic: ActorCritic
+
+    def __init__(self, actor_critic, num_learning_epochs=1, num_mini_batches=1, clip_param=0.2, gamma=0.998,
+                 lam=0.95, value_loss_coef=1.0, entropy_coef=0.0, learning_rate=1e-3, max_grad_norm=1.0,
+                 use_clipped_value_loss=True, schedule="fixed", desired_kl=0.01, device="cuda:0"):
+        self._lib = _lib.load(check_device=True)
+        self.device = torch.device(device)
+        self.desired_kl, self.schedule = desired_kl, schedule
+        self.actor_critic = actor_critic
+        self.actor_critic.to(self.device)
+        self.storage: Optional[RolloutStorage] = None
+        self.transition = RolloutStorage.Transition()
+        self.clip_param, self.num_learning_epochs, self.num_mini_batches = clip_param, num_learning_epochs, num_mini_batches
+        self.value_loss_coef, self.entropy_coef = value_loss_coef, entropy_coef
+        self.gamma, self.lam, self.max_grad_norm = gamma, lam, max_grad_norm
+        self.use_clipped_value_loss = use_clipped_value_loss
+        n = actor_critic.flat.numel()
+        self._exp_avg = torch.zeros(n, device=self.device)
+        self._exp_avg_sq = torch.zeros(n, device=self.device)
+        self._step = 0
+        self._lr_host = float(learning_rate)
+        self._lr_dev = torch.tensor([learning_rate], dtype=torch.float64, device=self.device)
+        self._lr_dirty = False
+        self._sumsq = torch.zeros(1, dtype=torch.float64, device=self.device)
+        self._stats = torch.zeros(4, dtype=torch.float64, device=self.device)
+        self._loss_acc = torch.zeros(4, dtype=torch.float64, device=self.device)
+        self.optimizer = _AdamState(self)
+        self.grad_allreduce = None          # multi-GPU hook: fn(flat_grad) sums gradients over ranks
+        self.world_size = 1
+        self.injected_eps = None            # parity: the Normal.sample() draw of the next act()
+        self.injected_perm = None           # parity: the randperm of the next update()
+
+    # ------------------------------------------------------------------ learning rate (device-resident)
+    @property
+    def learning_rate(self) -> float:
+        if self._lr_dirty:
+            self._lr_host = float(self._lr_dev.item())
+            self._lr_dirty = False
+        return self._lr_host
+
+    @learning_rate.setter
+    def learning_rate(self, v: float):
+        self._lr_host = float(v)
+        self._lr_dev.fill_(float(v))
+        self._lr_dirty = False
+
+    def init_storage(self, num_envs, num_transitions_per_env, actor_obs_shape, critic_obs_shape, action_shape):
+        self.storage = RolloutStorage(num_envs, num_transitions_per_env, actor_obs_shape, critic_obs_shape,
+                                      action_shape, self.device)
+
+    def test_mode(self):
+        self.actor_critic.eval()
+
+    def train_mode(self):
+        self.actor_critic.train()
+
+    # ------------------------------------------------------------------ rollout (ppo.py:91-117)
+    def act(self, obs, critic_obs):
+        ac, lib = self.actor_critic, self._lib
+        n = obs.shape[0]
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        ws = ac.workspace(n)
+        mu16 = ac._mlp_forward("actor", ac._as_operand(obs, ac.num_actor_obs), ws)
+        v16 = ac._mlp_forward("critic", ac._as_operand(critic_obs, ac.num_critic_obs), ws)
+        eps = self.injected_eps if self.injected_eps is not None else torch.randn(n, ac.num_actions, device=self.device)
+        self.injected_eps = None
+        actions = torch.empty(n, ac.num_actions, device=self.device)
+        logp = torch.empty(n, device=self.device)
+        mu, sigma = torch.empty_like(actions), torch.empty_like(actions)
+        _lib.check(lib.hb_ppo_act_head(mu16.data_ptr(), 16, ac.std.data_ptr(), eps.contiguous().data_ptr(), n,
+                                       actions.data_ptr(), logp.data_ptr(), mu.data_ptr(), sigma.data_ptr(), st),
+                   "hb_ppo_act_head")
+        t = self.transition
+        t.actions, t.values, t.actions_log_prob = actions, v16[:, :1].clone(), logp
+        t.action_mean, t.action_sigma = mu, sigma
+        t.observations, t.critic_observations = obs, critic_obs          # recorded before env.step() (ppo.py:98-100)
+        return t.actions
+
+    def process_env_step(self, rewards, dones, infos):
+        t = self.transition
+        t.rewards = rewards.clone()
+        t.dones = dones
+        if "time_outs" in infos:          # bootstrapping on time outs (ppo.py:106-108)
+            t.rewards += self.gamma * torch.squeeze(t.values * infos["time_outs"].unsqueeze(1).to(self.device), 1)
+        self.storage.add_transitions(t)
+        t.clear()
+        self.actor_critic.reset(dones)
+
+    def compute_returns(self, last_critic_obs):
+        last_values = self.actor_critic.evaluate(last_critic_obs)
+        self.storage.compute_returns(last_values, self.gamma, self.lam)
+
+    # ------------------------------------------------------------------ update (ppo.py:119-184)
+    def update(self):
+        ac, lib, s = self.actor_critic, self._lib, self.storage
+        dev = self.device
+        st = torch.cuda.current_stream(dev).cuda_stream
+        B = s.num_envs * s.num_transitions_per_env
+        mb = B // self.num_mini_batches
+        used = mb * self.num_mini_batches
+        perm = self.injected_perm if self.injected_perm is not None else torch.randperm(used, device=dev)
+        self.injected_perm = None
+        perm = perm.to(dev, dtype=torch.int64).contiguous()
+        # --- mini_batch_generator (rollout_storage.py:146-182): gathers, once per update ---
+        ld_a, ld_c = pad4(ac.num_actor_obs + 1), pad4(ac.num_critic_obs + 1)
+        if getattr(self, "_xa", None) is None or self._xa.shape[0] != used:
+            self._xa = torch.zeros(used, ld_a, device=dev)
+            self._xc = torch.zeros(used, ld_c, device=dev)
+            self._rec = torch.zeros(used, HB_PPO_REC, device=dev)
+        _lib.check(lib.hb_ppo_gather_rows(s._observations.data_ptr(), s.obs_ld, self._xa.data_ptr(), ld_a,
+                                          perm.data_ptr(), used, ac.num_actor_obs, ac.num_actor_obs, st), "gather obs")
+        _lib.check(lib.hb_ppo_gather_rows(s._privileged_observations.data_ptr(), s.priv_ld, self._xc.data_ptr(), ld_c,
+                                          perm.data_ptr(), used, ac.num_critic_obs, ac.num_critic_obs, st), "gather priv")
+        _lib.check(lib.hb_ppo_pack_samples(perm.data_ptr(), used, s.actions.data_ptr(), s.mu.data_ptr(),
+                                           s.sigma.data_ptr(), s.values.data_ptr(), s.advantages.data_ptr(),
+                                           s.returns.data_ptr(), s.actions_log_prob.data_ptr(), self._rec.data_ptr(), st),
+                   "hb_ppo_pack_samples")
+        ws = ac.workspace(mb)
+        lp = PpoLossParams(self.clip_param, self.value_loss_coef, self.entropy_coef, int(self.use_clipped_value_loss))
+        adaptive = int(self.desired_kl is not None and self.schedule == "adaptive")
+        self._loss_acc.zero_()
+        n_flat = ac.flat.numel()
+        std_grad = ac.grad[ac._std_offset:]
+        for _ in range(self.num_learning_epochs):
+            for i in range(self.num_mini_batches):
+                xa, xc, rec = self._xa[i * mb:(i + 1) * mb], self._xc[i * mb:(i + 1) * mb], self._rec[i * mb:(i + 1) * mb]
+                mu16 = ac._mlp_forward("actor", xa, ws)
+                v16 = ac._mlp_forward("critic", xc, ws)
+                self._stats.zero_()
+                _lib.check(lib.hb_ppo_loss_head(mu16.data_ptr(), 16, v16.data_ptr(), 16, ac.std.data_ptr(),
+                                                rec.data_ptr(), mb, mb * self.world_size, C.byref(lp),
+                                                ws["actor"]["d_out"].data_ptr(), ws["critic"]["d_out"].data_ptr(),
+                                                std_grad.data_ptr(), self._stats.data_ptr(), st), "hb_ppo_loss_head")
+                ac._mlp_backward("actor", xa, ws)
+                ac._mlp_backward("critic", xc, ws)
+                if self.grad_allreduce is not None:
+                    self.grad_allreduce(ac.grad, self._stats)        # sums over ranks (grads already carry 1/global_mb)
+                self._loss_acc += self._stats
+                self._sumsq.zero_()
+                _lib.check(lib.hb_grad_sumsq(ac.grad.data_ptr(), n_flat, self._sumsq.data_ptr(), st), "hb_grad_sumsq")
+                self._step += 1
+                ap = AdamParams(0.9, 0.999, 1e-8, float(self.max_grad_norm or 0.0), 1.0 - 0.9 ** self._step,
+                                1.0 - 0.999 ** self._step, adaptive, float(self.desired_kl or 0.0), mb * self.world_size)
+                _lib.check(lib.hb_adam_step(ac.flat.data_ptr(), ac.grad.data_ptr(), self._exp_avg.data_ptr(),
+                                            self._exp_avg_sq.data_ptr(), n_flat, C.byref(ap), self._sumsq.data_ptr(),
+                                            self._stats.data_ptr(), self._lr_dev.data_ptr(), st), "hb_adam_step")
+        self._lr_dirty = bool(adaptive)
+        num_updates = self.num_learning_epochs * self.num_mini_batches
+        acc = self._loss_acc.cpu()              # the single host sync of the update (the reference's .item() calls)
+        denom = num_updates * mb * self.world_size
+        mean_surrogate_loss, mean_value_loss = float(acc[0]) / denom, float(acc[1]) / denom
+        self.last_mean_kl = float(acc[2]) / denom
+        self.storage.clear()
+        return mean_value_loss, mean_surrogate_loss

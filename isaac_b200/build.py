@@ -27,6 +27,8 @@ UNITS = {
     "api.cu": [],
     "env_kernels.cu": ["--fmad=false"],
     "gae_kernels.cu": ["--fmad=false"],
+    "ppo_kernels.cu": [],
+    "mlp_gemm.cu": [],
 }
 
 

@@ -1,0 +1,372 @@
+// tcgen05 / TMEM / TMA GEMM for the ActorCritic MLPs, sm_100a only.
+//
+//   D[M,N] (+)= A[M,K] * B[N,K]^T          fp32 storage, TF32 tensor-core math, fp32 accumulation in TMEM
+//
+// One CTA computes one 128 x BN output tile (optionally one K-split of it):
+//   warp 4      TMA producer: 2-D tiled tensor maps, 128-byte swizzle, NSTAGE-deep mbarrier ring
+//   warp 5      allocates TMEM and issues tcgen05.mma.cta_group::1.kind::tf32 (one elected lane);
+//               tcgen05.commit releases smem stages and finally signals the epilogue
+//   warps 0-3   epilogue: tcgen05.ld the accumulator quarter that belongs to the warp (lane = row) and
+//               apply the fused tail: bias + ELU (forward), ELU' (dgrad), plain store, or atomic
+//               accumulate (split-K wgrad)
+//
+// Operand layouts.  "K-major" = the contraction index is contiguous in memory (activations
+// [rows, features] as A, nn.Linear weights [out, in] as B: the forward pass).  "MN-major" = the
+// M/N index is contiguous (weights as B of dgrad, activations / gradients as A and B of wgrad), so
+// backward needs no transposed copies: the same row-major tensors are read through a different
+// tensor map + UMMA descriptor (LayoutType SWIZZLE_128B, a_major/b_major bits of the instruction
+// descriptor).
+#include <cuda.h>
+
+#include "hb_common.cuh"
+
+namespace {
+
+constexpr int BM = 128;           // UMMA M (cta_group::1)
+constexpr int BK = 32;            // floats per k-block = one 128-byte swizzle row
+constexpr int UMMA_K = 8;         // tf32: 32 bytes of K per instruction
+constexpr int GEMM_THREADS = 192;
+
+enum Epilogue { EPI_STORE = 0, EPI_BIAS = 1, EPI_BIAS_ELU = 2, EPI_ELU_BWD = 3, EPI_ATOMIC = 4 };
+
+struct GemmArgs {
+    int M, N, K;                  // logical sizes (K = contraction length)
+    int kb_per_split;             // k-blocks handled by one CTA (gridDim.z splits)
+    float *D;                     // [M, ldd]
+    int ldd;
+    const float *bias;            // bias[n * bias_stride] (weights and bias share one packed matrix)
+    int bias_stride;
+    const float *H;               // EPI_ELU_BWD: forward activations [M, ldh]
+    int ldh;
+};
+
+// ---- PTX wrappers ---------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_load_2d(void *smem, const CUtensorMap *map, int c0, int c1, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(hb::smem_u32(smem)), "l"(map), "r"(c0), "r"(c1), "r"(hb::smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap *map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(hb::smem_u32(dst_smem)),
+                 "r"(cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(hb::smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float *v) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+// UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor): start address, leading / stride byte
+// offsets in 16-byte units, version 1 (Blackwell), layout type in bits [61,64).
+//   K-major operands : LayoutType SWIZZLE_128B (2): rows of 32 tf32 = 128 bytes, 16-byte chunks XOR-ed with
+//                      (row % 8); SBO = 1024 bytes between 8-row groups.
+//   MN-major operands: 32-bit types only exist as SWIZZLE_128B_BASE32B (1) (CUTLASS: "for mn-major tf32
+//                      operands, SW128_32B is the only available smem layout"): rows of 32 MN-elements,
+//                      32-byte chunks XOR-ed with (row % 4); LBO = stride between 32-element MN blocks,
+//                      SBO = 512 bytes between 4-row K groups.
+constexpr uint32_t LAYOUT_SW128 = 2, LAYOUT_SW128_BASE32B = 1;
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)layout << 61;
+    return d;
+}
+
+// Instruction descriptor (cute::UMMA::InstrDescriptor): F32 accumulate, TF32 x TF32.
+__host__ __device__ constexpr uint32_t make_idesc(int n, bool a_mn, bool b_mn) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+           ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+template <int BN>
+__host__ __device__ constexpr int stages_for() { return BN >= 256 ? 4 : (BN >= 128 ? 6 : 8); }
+
+template <int BN, bool A_MN, bool B_MN, int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                 const __grid_constant__ GemmArgs g) {
+    constexpr int NSTAGE = stages_for<BN>();
+    constexpr int A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4;
+    constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t *sa = smem, *sb = smem + NSTAGE * A_BYTES;
+    __shared__ __align__(8) uint64_t full_bar[NSTAGE], empty_bar[NSTAGE], acc_bar;
+    __shared__ uint32_t tmem_base_smem;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+    const int kb_total = (g.K + BK - 1) / BK;
+    const int kb_begin = blockIdx.z * g.kb_per_split;
+    const int kb_end = min(kb_begin + g.kb_per_split, kb_total);
+    const int nkb = kb_end - kb_begin;
+
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < NSTAGE; ++s) hb::mbar_init(&full_bar[s], 1), hb::mbar_init(&empty_bar[s], 1);
+        hb::mbar_init(&acc_bar, 1);
+        hb::fence_mbar_init();
+    }
+    if (warp == 4 && lane == 0) prefetch_tmap(&map_a), prefetch_tmap(&map_b);
+    if (warp == 5) tmem_alloc(&tmem_base_smem, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_acc = tmem_base_smem;
+
+    if (warp == 4) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            for (int i = 0; i < nkb; ++i) {
+                const int s = i % NSTAGE, ph = (i / NSTAGE) & 1;
+                hb::mbar_wait(&empty_bar[s], ph ^ 1);
+                hb::mbar_expect_tx(&full_bar[s], A_BYTES + B_BYTES);
+                const int k0 = (kb_begin + i) * BK;
+                if (A_MN) {      // tensor map dims (M, K): boxes of 32 m x 32 k, one 4 KB swizzle block each
+#pragma unroll
+                    for (int j = 0; j < BM / 32; ++j) tma_load_2d(sa + s * A_BYTES + j * 4096, &map_a, m0 + 32 * j, k0, &full_bar[s]);
+                } else {         // tensor map dims (K, M): one box of 32 k x 128 rows
+                    tma_load_2d(sa + s * A_BYTES, &map_a, k0, m0, &full_bar[s]);
+                }
+                if (B_MN) {
+#pragma unroll
+                    for (int j = 0; j < BN / 32; ++j) tma_load_2d(sb + s * B_BYTES + j * 4096, &map_b, n0 + 32 * j, k0, &full_bar[s]);
+                } else {
+                    tma_load_2d(sb + s * B_BYTES, &map_b, k0, n0, &full_bar[s]);
+                }
+            }
+        }
+    } else if (warp == 5) {
+        // ===================== MMA issuer =====================
+        constexpr uint32_t idesc = make_idesc(BN < 16 ? 16 : BN, A_MN, B_MN);
+        for (int i = 0; i < nkb; ++i) {
+            const int s = i % NSTAGE, ph = (i / NSTAGE) & 1;
+            hb::mbar_wait(&full_bar[s], ph);
+            tc_fence_after();
+            if (lane == 0) {
+                const uint32_t a_addr = hb::smem_u32(sa + s * A_BYTES), b_addr = hb::smem_u32(sb + s * B_BYTES);
+#pragma unroll
+                for (int k = 0; k < BK / UMMA_K; ++k) {
+                    // K-major: 8 tf32 = 32 bytes further along the swizzled 128-byte row;
+                    // MN-major: 8 k-rows = one 1024-byte swizzle atom further
+                    const uint64_t ad = A_MN ? make_desc(a_addr + k * 1024, 4096, 512, LAYOUT_SW128_BASE32B)
+                                             : make_desc(a_addr + k * 32, 16, 1024, LAYOUT_SW128);
+                    const uint64_t bd = B_MN ? make_desc(b_addr + k * 1024, 4096, 512, LAYOUT_SW128_BASE32B)
+                                             : make_desc(b_addr + k * 32, 16, 1024, LAYOUT_SW128);
+                    umma_tf32(tmem_acc, ad, bd, idesc, (i > 0 || k > 0) ? 1u : 0u);
+                }
+                umma_commit(&empty_bar[s]);                  // frees the smem stage once the MMAs have read it
+                if (i == nkb - 1) umma_commit(&acc_bar);     // accumulator complete -> epilogue
+            }
+            __syncwarp();
+        }
+    } else {
+        // ===================== epilogue (warps 0-3: TMEM lanes 32*warp .. 32*warp+31) =====================
+        if (nkb > 0) {
+            hb::mbar_wait(&acc_bar, 0);
+            tc_fence_after();
+        }
+        const int m = m0 + warp * 32 + lane;
+        const bool row_ok = m < g.M;
+        float *drow = g.D + (size_t)m * g.ldd;
+        const float *hrow = (EPI == EPI_ELU_BWD) ? g.H + (size_t)m * g.ldh : nullptr;
+#pragma unroll 1
+        for (int c = 0; c < BN; c += 16) {
+            float v[16];
+            if (nkb > 0) {
+                tmem_ld16(tmem_acc + ((uint32_t)(warp * 32) << 16) + (uint32_t)c, v);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = 0.0f;
+            }
+            const int n = n0 + c;
+            if (!row_ok || n >= g.N) continue;
+            if (EPI == EPI_BIAS || EPI == EPI_BIAS_ELU) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    if (n + i < g.N) {
+                        float x = v[i] + __ldg(g.bias + (size_t)(n + i) * g.bias_stride);
+                        if (EPI == EPI_BIAS_ELU) x = x > 0.0f ? x : expf(x) - 1.0f;      // nn.ELU(alpha=1)
+                        v[i] = x;
+                    }
+                }
+            } else if (EPI == EPI_ELU_BWD) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    if (n + i < g.N) {
+                        const float h = hrow[n + i];                  // h = elu(z): elu'(z) = z > 0 ? 1 : h + 1
+                        v[i] = v[i] * (h > 0.0f ? 1.0f : h + 1.0f);
+                    }
+                }
+            }
+            if (EPI == EPI_ATOMIC) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                    if (n + i < g.N) atomicAdd(drow + n + i, v[i]);
+            } else if (n + 16 <= g.N && ((reinterpret_cast<uintptr_t>(drow + n) & 15u) == 0)) {
+#pragma unroll
+                for (int i = 0; i < 16; i += 4)
+                    *reinterpret_cast<float4 *>(drow + n + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                    if (n + i < g.N) drow[n + i] = v[i];
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 5) tmem_dealloc(tmem_acc, TMEM_COLS);
+}
+
+// ---- host side --------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// 2-D fp32 tensor map over a row-major matrix [rows, cols] with leading dimension ld (floats).
+// K-major operand: inner = contraction (cols), box = 32 x box_rows.
+// MN-major operand: the matrix is [K rows, MN cols]; inner = MN (cols), box = 32 x 32.
+int make_map(CUtensorMap *map, const float *base, int rows, int cols, int ld, int box_inner, int box_outer,
+             bool mn_major) {
+    EncodeTiledFn enc = encode_fn();
+    if (!enc) {
+        hb::set_error("cuTensorMapEncodeTiled is not available from this driver");
+        return HB_ERR_UNSUPPORTED;
+    }
+    if ((reinterpret_cast<uintptr_t>(base) & 15u) || (ld % 4) != 0) {
+        hb::set_error("TMA operand needs a 16-byte aligned base and a leading dimension that is a multiple of 4 floats "
+                      "(base=%p ld=%d)", (const void *)base, ld);
+        return HB_ERR_BAD_ARG;
+    }
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+    cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        hb::set_error("cuTensorMapEncodeTiled failed (%d) rows=%d cols=%d ld=%d box=%dx%d", (int)r, rows, cols, ld,
+                      box_inner, box_outer);
+        return HB_ERR_CUDA;
+    }
+    return HB_OK;
+}
+
+template <int BN, bool A_MN, bool B_MN, int EPI>
+int launch(const hb_gemm_desc *d, cudaStream_t st) {
+    constexpr int NSTAGE = stages_for<BN>();
+    constexpr size_t SMEM = (size_t)NSTAGE * (BM * BK * 4 + BN * BK * 4) + 1024;
+    static bool attr = false;
+    auto kern = gemm_tf32_kernel<BN, A_MN, B_MN, EPI>;
+    if (!attr) {
+        HB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+        attr = true;
+    }
+    alignas(64) CUtensorMap ma, mb;
+    int rc;
+    // A: K-major  -> memory [M, K] ;  MN-major -> memory [K, M]
+    rc = A_MN ? make_map(&ma, d->A, d->K, d->M, d->lda, 32, 32, true) : make_map(&ma, d->A, d->M, d->K, d->lda, BK, BM, false);
+    if (rc) return rc;
+    rc = B_MN ? make_map(&mb, d->B, d->K, d->N, d->ldb, 32, 32, true) : make_map(&mb, d->B, d->N, d->K, d->ldb, BK, BN, false);
+    if (rc) return rc;
+    GemmArgs g;
+    g.M = d->M, g.N = d->N, g.K = d->K;
+    const int kb_total = (d->K + BK - 1) / BK;
+    int splits = d->split_k > 0 ? d->split_k : 1;
+    if (splits > kb_total) splits = kb_total > 0 ? kb_total : 1;
+    g.kb_per_split = (kb_total + splits - 1) / splits;
+    splits = g.kb_per_split > 0 ? (kb_total + g.kb_per_split - 1) / g.kb_per_split : 1;
+    g.D = d->D, g.ldd = d->ldd, g.bias = d->bias, g.bias_stride = d->bias_stride, g.H = d->H, g.ldh = d->ldh;
+    dim3 grid((d->M + BM - 1) / BM, (d->N + BN - 1) / BN, splits);
+    kern<<<grid, GEMM_THREADS, SMEM, st>>>(ma, mb, g);
+    HB_CHECK_LAUNCH("gemm_tf32_kernel");
+    return HB_OK;
+}
+
+template <int BN, int EPI>
+int dispatch_major(const hb_gemm_desc *d, cudaStream_t st) {
+    if (!d->a_mn_major && !d->b_mn_major) return launch<BN, false, false, EPI>(d, st);
+    if (!d->a_mn_major && d->b_mn_major) return launch<BN, false, true, EPI>(d, st);
+    if (d->a_mn_major && d->b_mn_major) return launch<BN, true, true, EPI>(d, st);
+    hb::set_error("hb_gemm_tf32: A MN-major with B K-major is not instantiated");
+    return HB_ERR_UNSUPPORTED;
+}
+
+template <int BN>
+int dispatch_epi(const hb_gemm_desc *d, cudaStream_t st) {
+    switch (d->epilogue) {
+        case HB_EPI_STORE: return dispatch_major<BN, EPI_STORE>(d, st);
+        case HB_EPI_BIAS: return dispatch_major<BN, EPI_BIAS>(d, st);
+        case HB_EPI_BIAS_ELU: return dispatch_major<BN, EPI_BIAS_ELU>(d, st);
+        case HB_EPI_ELU_BWD: return dispatch_major<BN, EPI_ELU_BWD>(d, st);
+        case HB_EPI_ATOMIC_ADD: return dispatch_major<BN, EPI_ATOMIC>(d, st);
+    }
+    hb::set_error("hb_gemm_tf32: unknown epilogue %d", d->epilogue);
+    return HB_ERR_BAD_ARG;
+}
+
+}  // namespace
+
+extern "C" int hb_gemm_tf32(const hb_gemm_desc *d, void *stream) {
+    HB_REQUIRE(d && d->A && d->B && d->D, "hb_gemm_tf32: null descriptor/operand");
+    HB_REQUIRE(d->M > 0 && d->N > 0 && d->K > 0, "hb_gemm_tf32: empty problem %dx%dx%d", d->M, d->N, d->K);
+    HB_REQUIRE((d->epilogue != HB_EPI_BIAS && d->epilogue != HB_EPI_BIAS_ELU) || d->bias, "hb_gemm_tf32: bias epilogue without bias");
+    HB_REQUIRE(d->epilogue != HB_EPI_ELU_BWD || d->H, "hb_gemm_tf32: ELU backward epilogue without activations");
+    HB_REQUIRE(d->split_k <= 1 || d->epilogue == HB_EPI_ATOMIC_ADD, "hb_gemm_tf32: split-K needs the atomic epilogue");
+    HB_REQUIRE(!d->b_mn_major || d->N > 64, "hb_gemm_tf32: MN-major B needs N > 64 (32-wide TMA boxes per 128-byte swizzle row)");
+    cudaStream_t st = (cudaStream_t)stream;
+    // tile width: the widest UMMA N that does not waste more than half a tile
+    if (d->N <= 16) return dispatch_epi<16>(d, st);
+    if (d->N <= 64) return dispatch_epi<64>(d, st);
+    if (d->N <= 128 || d->tile_n == 128) return dispatch_epi<128>(d, st);
+    return dispatch_epi<256>(d, st);
+}

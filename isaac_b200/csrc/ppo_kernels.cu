@@ -1,0 +1,305 @@
+// PPO update kernels around the tcgen05 GEMMs, sm_100a.
+//   - minibatch gathers (rollout_storage.py:146-182), done once per update
+//   - loss head + analytic backward (ppo.py:130-168) and the PPO.act sampling head (ppo.py:91-101)
+//   - clip_grad_norm_ + Adam with the adaptive-KL learning rate evaluated on the device (ppo.py:136-148,171-174)
+#include <math.h>
+
+#include "hb_common.cuh"
+
+namespace {
+
+constexpr int NA = HB_PPO_ACT;
+constexpr float HALF_LOG_2PI = 0.91893853320467274178f;     // log(sqrt(2*pi))
+
+__global__ void __launch_bounds__(256)
+gather_rows_kernel(const float *__restrict__ src, int ld_src, float *__restrict__ dst, int ld_dst,
+                   const int64_t *__restrict__ perm, long long rows, int cols, int ones_col) {
+    const int lane = threadIdx.x & 31;
+    const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;      // one warp per row
+    if (row >= rows) return;
+    const float *s = src + (size_t)perm[row] * ld_src;
+    float *d = dst + (size_t)row * ld_dst;
+    const int vec = cols >> 2;
+    const float4 *s4 = reinterpret_cast<const float4 *>(s);
+    float4 *d4 = reinterpret_cast<float4 *>(d);
+    for (int i = lane; i < vec; i += 32) hb::st_stream4(d4 + i, hb::ld_stream4(s4 + i));
+    for (int i = (vec << 2) + lane; i < cols; i += 32) d[i] = s[i];
+    if (ones_col >= 0 && lane == 0) d[ones_col] = 1.0f;
+}
+
+__global__ void __launch_bounds__(256)
+pack_samples_kernel(const int64_t *__restrict__ perm, long long rows, const float *__restrict__ actions,
+                    const float *__restrict__ mu, const float *__restrict__ sigma, const float *__restrict__ values,
+                    const float *__restrict__ adv, const float *__restrict__ ret, const float *__restrict__ logp,
+                    float *__restrict__ rec) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows) return;
+    const long long j = perm[i];
+    float *r = rec + i * HB_PPO_REC;
+#pragma unroll
+    for (int k = 0; k < NA; ++k) {
+        r[k] = actions[j * NA + k];
+        r[NA + k] = mu[j * NA + k];
+        r[2 * NA + k] = sigma[j * NA + k];
+    }
+    r[3 * NA] = values[j], r[3 * NA + 1] = adv[j], r[3 * NA + 2] = ret[j], r[3 * NA + 3] = logp[j];
+    r[3 * NA + 4] = 0.0f, r[3 * NA + 5] = 0.0f;
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ppo.py:130-168 and its gradient w.r.t. mu, value and std.  One thread per sample.
+__global__ void __launch_bounds__(256)
+loss_head_kernel(const float *__restrict__ mu, int ld_mu, const float *__restrict__ value, int ld_v,
+                 const float *__restrict__ stdp, const float *__restrict__ rec, long long mb, double inv_b,
+                 float ent_scale, hb_ppo_loss_params lp, float *__restrict__ d_mu, float *__restrict__ d_value,
+                 float *__restrict__ d_std, double *__restrict__ stats) {
+    __shared__ float s_dstd[8][NA];
+    __shared__ double s_stat[8][4];
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float sig[NA];
+#pragma unroll
+    for (int j = 0; j < NA; ++j) sig[j] = stdp[j];
+    float g_std[NA];
+#pragma unroll
+    for (int j = 0; j < NA; ++j) g_std[j] = 0.0f;
+    double st_s = 0.0, st_v = 0.0, st_k = 0.0, st_e = 0.0;
+    if (i < mb) {
+        const float *r = rec + i * HB_PPO_REC;
+        const float *m = mu + i * ld_mu;
+        float lp_new = 0.0f, kl = 0.0f, ent = 0.0f, diff[NA];
+#pragma unroll
+        for (int j = 0; j < NA; ++j) {
+            const float var = sig[j] * sig[j];
+            diff[j] = r[j] - m[j];
+            lp_new += (-(diff[j] * diff[j]) / (2.0f * var) - logf(sig[j])) - HALF_LOG_2PI;      // Normal.log_prob
+            const float so = r[2 * NA + j], dm = r[NA + j] - m[j];
+            kl += (logf(sig[j] / so + 1.e-5f) + (so * so + dm * dm) / (2.0f * var)) - 0.5f;      // ppo.py:138-139
+            ent += (0.5f + HALF_LOG_2PI) + logf(sig[j]);                                          // Normal.entropy
+        }
+        const float v_old = r[3 * NA], adv = r[3 * NA + 1], ret = r[3 * NA + 2], lp_old = r[3 * NA + 3];
+        // clipped surrogate (ppo.py:152-156); torch.max splits the gradient evenly on ties
+        const float ratio = expf(lp_new - lp_old);
+        const float lo = 1.0f - lp.clip_param, hi = 1.0f + lp.clip_param;
+        const float s1 = -adv * ratio, s2 = -adv * fminf(fmaxf(ratio, lo), hi);
+        const float inr = (ratio >= lo && ratio <= hi) ? 1.0f : 0.0f;
+        const float w1 = s1 > s2 ? 1.0f : (s1 == s2 ? 0.5f : 0.0f);
+        const float g_ratio = -adv * (w1 + (1.0f - w1) * inr);
+        const float g_lp = (float)((double)(g_ratio * ratio) * inv_b);
+        st_s = (double)fmaxf(s1, s2);
+        // value loss (ppo.py:158-166)
+        const float v = value[i * ld_v];
+        float g_v;
+        if (lp.use_clipped_value_loss) {
+            const float dv = v - v_old;
+            const float vc = v_old + fminf(fmaxf(dv, -lp.clip_param), lp.clip_param);
+            const float l1 = (v - ret) * (v - ret), l2 = (vc - ret) * (vc - ret);
+            const float inv = (dv >= -lp.clip_param && dv <= lp.clip_param) ? 1.0f : 0.0f;
+            const float u1 = l1 > l2 ? 1.0f : (l1 == l2 ? 0.5f : 0.0f);
+            g_v = 2.0f * (v - ret) * u1 + 2.0f * (vc - ret) * inv * (1.0f - u1);
+            st_v = (double)fmaxf(l1, l2);
+        } else {
+            g_v = -2.0f * (ret - v);
+            st_v = (double)((ret - v) * (ret - v));
+        }
+        st_k = (double)kl, st_e = (double)ent;
+        float *dm_out = d_mu + i * ld_mu;
+#pragma unroll
+        for (int j = 0; j < NA; ++j) {
+            const float var = sig[j] * sig[j];
+            dm_out[j] = g_lp * (diff[j] / var);
+            g_std[j] = g_lp * ((diff[j] * diff[j]) / (var * sig[j]) - 1.0f / sig[j]);
+        }
+        for (int j = NA; j < ld_mu; ++j) dm_out[j] = 0.0f;
+        float *dv_out = d_value + i * ld_v;
+        dv_out[0] = (float)((double)(lp.value_loss_coef * g_v) * inv_b);
+        for (int j = 1; j < ld_v; ++j) dv_out[j] = 0.0f;
+    }
+#pragma unroll
+    for (int j = 0; j < NA; ++j) {
+        const float s = warp_sum(g_std[j]);
+        if (lane == 0) s_dstd[warp][j] = s;
+    }
+    st_s = warp_sum(st_s), st_v = warp_sum(st_v), st_k = warp_sum(st_k), st_e = warp_sum(st_e);
+    if (lane == 0) s_stat[warp][0] = st_s, s_stat[warp][1] = st_v, s_stat[warp][2] = st_k, s_stat[warp][3] = st_e;
+    __syncthreads();
+    if (threadIdx.x < NA) {
+        float s = 0.0f;
+        for (int w = 0; w < 8; ++w) s += s_dstd[w][threadIdx.x];
+        // entropy bonus: -entropy_coef * mean(entropy) -> d/dsigma_j = -coef / sigma_j (added once, by block 0)
+        // (ent_scale = local / global minibatch size, so that the sum over ranks counts it once)
+        if (blockIdx.x == 0) s += ent_scale * (-lp.entropy_coef / sig[threadIdx.x]);
+        atomicAdd(d_std + threadIdx.x, s);
+    } else if (threadIdx.x >= 32 && threadIdx.x < 36) {
+        const int k = threadIdx.x - 32;
+        double s = 0.0;
+        for (int w = 0; w < 8; ++w) s += s_stat[w][k];
+        atomicAdd(stats + k, s);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+act_head_kernel(const float *__restrict__ mu, int ld_mu, const float *__restrict__ stdp, const float *__restrict__ eps,
+                long long n, float *__restrict__ actions, float *__restrict__ logp, float *__restrict__ mu_out,
+                float *__restrict__ sigma_out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float lp = 0.0f;
+#pragma unroll
+    for (int j = 0; j < NA; ++j) {
+        const float m = mu[i * ld_mu + j];
+        const float s = m * 0.0f + stdp[j];                         // actor_critic.py:113
+        const float a = m + s * eps[i * NA + j];                    // Normal.sample with the draw supplied
+        const float d = a - m;
+        lp += (-(d * d) / (2.0f * (s * s)) - logf(s)) - HALF_LOG_2PI;
+        actions[i * NA + j] = a, mu_out[i * NA + j] = m, sigma_out[i * NA + j] = s;
+    }
+    logp[i] = lp;
+}
+
+__global__ void __launch_bounds__(256)
+grad_sumsq_kernel(const float *__restrict__ g, long long n, double *__restrict__ out) {
+    __shared__ double s[8];
+    double acc = 0.0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const double v = (double)g[i];
+        acc += v * v;
+    }
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += s[w];
+        atomicAdd(out, t);
+    }
+}
+
+// torch.optim.Adam (single-tensor semantics, no amsgrad / weight decay) after clip_grad_norm_.
+__global__ void __launch_bounds__(256)
+adam_kernel(float *__restrict__ p, float *__restrict__ g, float *__restrict__ m, float *__restrict__ v, long long n,
+            hb_adam_params ap, const double *__restrict__ sumsq, const double *__restrict__ kl_stats,
+            double *__restrict__ lr_io) {
+    // adaptive learning rate from the KL mean of this minibatch (ppo.py:140-148); every thread derives the
+    // same value from the same inputs, thread 0 of block 0 stores it after everyone has read the old one
+    double lr = *lr_io;
+    if (ap.adaptive) {
+        const double kl = kl_stats[2] / (double)ap.kl_count;
+        if (kl > ap.desired_kl * 2.0) lr = fmax(1e-5, lr / 1.5);
+        else if (kl < ap.desired_kl / 2.0 && kl > 0.0) lr = fmin(1e-2, lr * 1.5);
+    }
+    float scale = 1.0f;
+    if (ap.max_grad_norm > 0.0f) {            // clip_grad_norm_: coef = max_norm / (total_norm + 1e-6), clamped to 1
+        const float total = (float)sqrt(*sumsq);
+        const float coef = ap.max_grad_norm / (total + 1e-6f);
+        scale = coef < 1.0f ? coef : 1.0f;
+    }
+    const float step_size = (float)(lr / ap.bias_correction1);
+    const float bc2_sqrt = (float)sqrt(ap.bias_correction2);
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const float gi = g[i] * scale;
+        float mi = m[i], vi = v[i];
+        mi = mi + (gi - mi) * (1.0f - ap.beta1);                    // exp_avg.lerp_(grad, 1 - beta1)
+        vi = vi * ap.beta2 + (1.0f - ap.beta2) * gi * gi;           // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
+        const float denom = sqrtf(vi) / bc2_sqrt + ap.eps;
+        p[i] = p[i] - step_size * (mi / denom);                     // param.addcdiv_(exp_avg, denom, value=-step_size)
+        m[i] = mi, v[i] = vi, g[i] = 0.0f;                          // optimizer.zero_grad() for the next minibatch
+    }
+    if (ap.adaptive) {
+        // the new rate is published by a second, tiny launch (hb_adam_step) once every block has read the old one
+    }
+}
+
+__global__ void lr_update_kernel(hb_adam_params ap, const double *__restrict__ kl_stats, double *__restrict__ lr_io) {
+    double lr = *lr_io;
+    const double kl = kl_stats[2] / (double)ap.kl_count;
+    if (kl > ap.desired_kl * 2.0) lr = fmax(1e-5, lr / 1.5);
+    else if (kl < ap.desired_kl / 2.0 && kl > 0.0) lr = fmin(1e-2, lr * 1.5);
+    *lr_io = lr;
+}
+
+}  // namespace
+
+extern "C" {
+
+int hb_ppo_gather_rows(const float *src, int32_t ld_src, float *dst, int32_t ld_dst, const int64_t *perm, int64_t rows,
+                       int32_t cols, int32_t ones_col, void *stream) {
+    HB_REQUIRE(src && dst && perm && rows > 0 && cols > 0, "hb_ppo_gather_rows: bad arguments");
+    HB_REQUIRE(hb::aligned16(src) && hb::aligned16(dst) && ld_src % 4 == 0 && ld_dst % 4 == 0,
+               "hb_ppo_gather_rows: rows must start on 16-byte boundaries");
+    HB_REQUIRE(ones_col < ld_dst, "hb_ppo_gather_rows: ones_col outside the destination row");
+    const long long threads = rows * 32;
+    gather_rows_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(src, ld_src, dst, ld_dst, perm,
+                                                                                          rows, cols, ones_col);
+    HB_CHECK_LAUNCH("gather_rows_kernel");
+    return HB_OK;
+}
+
+int hb_ppo_pack_samples(const int64_t *perm, int64_t rows, const float *actions, const float *mu, const float *sigma,
+                        const float *values, const float *advantages, const float *returns, const float *log_prob,
+                        float *records, void *stream) {
+    HB_REQUIRE(perm && actions && mu && sigma && values && advantages && returns && log_prob && records && rows > 0,
+               "hb_ppo_pack_samples: bad arguments");
+    pack_samples_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        perm, rows, actions, mu, sigma, values, advantages, returns, log_prob, records);
+    HB_CHECK_LAUNCH("pack_samples_kernel");
+    return HB_OK;
+}
+
+int hb_ppo_loss_head(const float *mu, int32_t ld_mu, const float *value, int32_t ld_v, const float *std,
+                     const float *records, int64_t mb, int64_t mb_global, const hb_ppo_loss_params *lp, float *d_mu,
+                     float *d_value, float *d_std, double *stats, void *stream) {
+    HB_REQUIRE(mu && value && std && records && lp && d_mu && d_value && d_std && stats, "hb_ppo_loss_head: null buffer");
+    HB_REQUIRE(mb > 0 && mb_global >= mb && ld_mu >= HB_PPO_ACT && ld_v >= 1, "hb_ppo_loss_head: bad sizes");
+    loss_head_kernel<<<(unsigned)((mb + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        mu, ld_mu, value, ld_v, std, records, mb, 1.0 / (double)mb_global, (float)((double)mb / (double)mb_global), *lp, d_mu,
+        d_value, d_std, stats);
+    HB_CHECK_LAUNCH("loss_head_kernel");
+    return HB_OK;
+}
+
+int hb_ppo_act_head(const float *mu, int32_t ld_mu, const float *std, const float *eps, int64_t n, float *actions,
+                    float *log_prob, float *mu_out, float *sigma_out, void *stream) {
+    HB_REQUIRE(mu && std && eps && actions && log_prob && mu_out && sigma_out && n > 0 && ld_mu >= HB_PPO_ACT,
+               "hb_ppo_act_head: bad arguments");
+    act_head_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(mu, ld_mu, std, eps, n, actions,
+                                                                                  log_prob, mu_out, sigma_out);
+    HB_CHECK_LAUNCH("act_head_kernel");
+    return HB_OK;
+}
+
+int hb_grad_sumsq(const float *grads, int64_t n, double *grad_sumsq, void *stream) {
+    HB_REQUIRE(grads && grad_sumsq && n > 0, "hb_grad_sumsq: bad arguments");
+    const int blocks = (int)((n + 256 * 8 - 1) / (256 * 8));
+    grad_sumsq_kernel<<<blocks < 1184 ? blocks : 1184, 256, 0, (cudaStream_t)stream>>>(grads, n, grad_sumsq);
+    HB_CHECK_LAUNCH("grad_sumsq_kernel");
+    return HB_OK;
+}
+
+int hb_adam_step(float *params, float *grads, float *exp_avg, float *exp_avg_sq, int64_t n, const hb_adam_params *ap,
+                 const double *grad_sumsq, const double *kl_stats, double *lr_io, void *stream) {
+    HB_REQUIRE(params && grads && exp_avg && exp_avg_sq && ap && lr_io && n > 0, "hb_adam_step: bad arguments");
+    HB_REQUIRE(ap->max_grad_norm <= 0.0f || grad_sumsq, "hb_adam_step: clipping needs grad_sumsq");
+    HB_REQUIRE(!ap->adaptive || (kl_stats && ap->kl_count > 0), "hb_adam_step: adaptive schedule needs kl_stats");
+    adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, n, *ap,
+                                                                             grad_sumsq, kl_stats, lr_io);
+    HB_CHECK_LAUNCH("adam_kernel");
+    if (ap->adaptive) {
+        lr_update_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(*ap, kl_stats, lr_io);
+        HB_CHECK_LAUNCH("lr_update_kernel");
+    }
+    return HB_OK;
+}
+
+}  // extern "C"

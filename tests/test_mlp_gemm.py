@@ -1,0 +1,117 @@
+"""tcgen05 TF32 GEMM (hb_gemm_tf32) against an exact emulation of TF32 operands.
+
+The tensor core reads fp32 storage as TF32 (10 explicit mantissa bits) and accumulates in fp32.  The
+reference here is an fp64 matmul of operands reduced to TF32 the same way, so a correct kernel agrees to
+fp32-accumulation accuracy (1e-5 relative to |a|.|b|) — any descriptor / swizzle / layout mistake is O(1).
+Against the unreduced fp32 product the expected deviation is the TF32 input rounding itself (<= 2^-10
+relative per operand), which is the tolerance the PPO parity tests inherit."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def tf32_trunc(x):
+    return (x.view(torch.int32) & ~0x1FFF).view(torch.float32)
+
+
+def tf32_round(x):
+    i = x.view(torch.int32)
+    return ((i + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
+def run_gemm(lib, dev, A, B, M, N, K, a_mn=False, b_mn=False, epilogue=0, bias=None, H=None, split_k=1, D0=None,
+             ldd=None):
+    from isaac_b200 import _lib
+    d = _lib.GemmDesc()
+    ldd = ldd or (N + 3) // 4 * 4
+    D = torch.zeros(M, ldd, device=dev) if D0 is None else D0
+    d.A, d.B, d.D = A.data_ptr(), B.data_ptr(), D.data_ptr()
+    d.M, d.N, d.K = M, N, K
+    d.lda, d.ldb, d.ldd = A.stride(0), B.stride(0), D.stride(0)
+    d.a_mn_major, d.b_mn_major, d.epilogue, d.split_k = int(a_mn), int(b_mn), epilogue, split_k
+    if bias is not None:
+        d.bias, d.bias_stride = bias.data_ptr(), 1
+    if H is not None:
+        d.H, d.ldh = H.data_ptr(), H.stride(0)
+    _lib.check(lib.hb_gemm_tf32(C.byref(d), torch.cuda.current_stream(dev).cuda_stream), "hb_gemm_tf32")
+    torch.cuda.synchronize()
+    return D[:, :N]
+
+
+def check_product(got, a, b, name):
+    """got ~ a @ b.T where a [M,K], b [N,K] are the logical fp32 operands."""
+    scale = (a.double().abs() @ b.double().abs().T).clamp_min(1e-30)
+    exact = {n: f(a).double() @ f(b).double().T for n, f in (("trunc", tf32_trunc), ("round", tf32_round))}
+    errs = {n: ((got.double() - e).abs() / scale).max().item() for n, e in exact.items()}
+    best = min(errs, key=errs.get)
+    assert errs[best] < 2e-5, f"{name}: not a TF32 product of the operands (rel err {errs})"
+    full = ((got.double() - a.double() @ b.double().T).abs() / scale).max().item()
+    assert full < 2.5e-3, f"{name}: deviation from the fp32 product {full}"
+    return best, errs[best], full
+
+
+def padded(rows, cols, dev, gen, pad_to=4, extra=0):
+    ld = (cols + extra + pad_to - 1) // pad_to * pad_to
+    t = torch.zeros(rows, ld, device=dev)
+    t[:, :cols] = torch.randn(rows, cols, generator=gen).to(dev)
+    return t
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (384, 512, 615), (200, 128, 96), (4096, 768, 1050), (32, 16, 128),
+                                   (1000, 64, 257), (24576, 256, 512)])
+def test_forward_k_major(lib, cuda_device, M, N, K):
+    g = torch.Generator().manual_seed(M + N + K)
+    A, B = padded(M, K, cuda_device, g, extra=1), padded(N, K, cuda_device, g, extra=1)
+    got = run_gemm(lib, cuda_device, A, B, M, N, K)
+    mode, e, full = check_product(got, A[:, :K], B[:, :K], f"fwd {M}x{N}x{K}")
+    print(f"fwd {M}x{N}x{K}: tf32-{mode} err {e:.2e}, vs fp32 {full:.2e}")
+
+
+def test_forward_bias_elu_epilogue(lib, cuda_device):
+    M, N, K = 300, 512, 615
+    g = torch.Generator().manual_seed(1)
+    A, B = padded(M, K, cuda_device, g, extra=1), padded(N, K, cuda_device, g, extra=1)
+    A[:, :K] *= 0.2
+    bias = torch.randn(N, generator=g).to(cuda_device)
+    got = run_gemm(lib, cuda_device, A, B, M, N, K, epilogue=2, bias=bias)
+    z = tf32_trunc(A[:, :K]).double() @ tf32_trunc(B[:, :K]).double().T + bias.double()
+    z2 = tf32_round(A[:, :K]).double() @ tf32_round(B[:, :K]).double().T + bias.double()
+    want, want2 = torch.nn.functional.elu(z), torch.nn.functional.elu(z2)
+    err = min((got.double() - want).abs().max().item(), (got.double() - want2).abs().max().item())
+    assert err < 1e-4, err
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 128, 16), (384, 512, 256), (1000, 768, 256), (24576, 128, 16)])
+def test_dgrad_b_mn_major_with_elu_backward(lib, cuda_device, M, N, K):
+    """dZ_prev[M,N] = (dZ[M,K] @ W[K,N]) * elu'(H): W is the row-major nn.Linear weight (MN-major B)."""
+    g = torch.Generator().manual_seed(7 + M)
+    dZ = padded(M, K, cuda_device, g)
+    W = padded(K, N, cuda_device, g, extra=1)
+    H = torch.nn.functional.elu(padded(M, N, cuda_device, g, extra=1))
+    got = run_gemm(lib, cuda_device, dZ, W, M, N, K, b_mn=True, epilogue=3, H=H)
+    dh = torch.where(H[:, :N] > 0, torch.ones_like(H[:, :N]), H[:, :N] + 1)
+    a, b = dZ[:, :K], W[:K, :N].T.contiguous()
+    scale = (a.double().abs() @ b.double().abs().T).clamp_min(1e-30)
+    errs = [(((got.double() - (f(a).double() @ f(b).double().T) * dh.double()).abs()) / scale).max().item()
+            for f in (tf32_trunc, tf32_round)]
+    assert min(errs) < 2e-5, errs
+
+
+@pytest.mark.parametrize("M,N,K,split", [(512, 616, 4096, 8), (16, 129, 1024, 4), (768, 1051, 3000, 5), (128, 257, 160, 1),
+                                         (256, 513, 24576, 16)])
+def test_wgrad_both_mn_major_split_k(lib, cuda_device, M, N, K, split):
+    """G[M,N] += dZ^T[M,K] @ X[K,N]: both operands are the row-major [K, *] tensors of the forward pass."""
+    g = torch.Generator().manual_seed(11 + N)
+    dZ = padded(K, M, cuda_device, g)
+    X = padded(K, N, cuda_device, g)
+    G0 = torch.zeros(M, (N + 3) // 4 * 4, device=cuda_device)
+    got = run_gemm(lib, cuda_device, dZ, X, M, N, K, a_mn=True, b_mn=True, epilogue=4, split_k=split, D0=G0)
+    a, b = dZ[:K, :M].T.contiguous(), X[:K, :N].T.contiguous()
+    scale = (a.double().abs() @ b.double().abs().T).clamp_min(1e-30)
+    errs = [((got.double() - f(a).double() @ f(b).double().T).abs() / scale).max().item() for f in (tf32_trunc, tf32_round)]
+    assert min(errs) < 5e-5, errs
+    assert (G0[:, N:] == 0).all(), "padding columns of the packed gradient must stay zero"

@@ -1,0 +1,191 @@
+"""PPO stage (act / process_env_step / compute_returns / update) on the B200 kernels against the CPU oracle
+(which is pinned bit-for-bit to the reference's rsl_rl fork).
+
+Tolerances.  The MLP GEMMs run on the tensor cores with TF32 operands (fp32 storage, fp32 accumulate): every
+product carries <= 2^-10 relative operand rounding, so
+  * forward quantities (mu, values, log-prob) agree to ~1e-3 of their scale,
+  * gradients agree to 5e-3 relative L2 per tensor,
+  * post-update weights: Adam normalises the step to ~lr per element, so |w_cuda - w_ref| <= 2*lr*steps
+    element-wise by construction; the test demands 0.25 of that bound in relative-L2 form per tensor.
+The adaptive-KL learning-rate rule is a discontinuous function of a reduced scalar (SURVEY.md §7 hard part 3):
+the fixed schedule is compared exactly, the adaptive one only when the KL is away from the thresholds."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from _util import assert_close
+from oracle import make_golden as mg
+from oracle.ppo_oracle import OraclePPO, PARAM_ORDER, init_actor_critic_params, mlp
+
+pytestmark = pytest.mark.gpu
+
+
+def make_pair(dev, n, t, alg_cfg, seed=3):
+    from isaac_b200.algo.actor_critic import ActorCritic
+    from isaac_b200.algo.ppo import PPO
+    params = init_actor_critic_params(seed=seed)
+    ac = ActorCritic(615, 1050, 10, actor_hidden_dims=[512, 256, 128], critic_hidden_dims=[768, 256, 128], device=dev)
+    ac.load_state_dict(params)
+    alg = PPO(ac, device=dev, **alg_cfg)
+    alg.init_storage(n, t, [615], [1050], [10])
+    ora = OraclePPO(params, n, t, **alg_cfg)
+    return alg, ora, params
+
+
+def rel_l2(a, b):
+    a, b = a.double().flatten(), b.double().flatten()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def test_state_dict_round_trip_and_forward(lib, cuda_device):
+    alg, ora, params = make_pair(cuda_device, 64, 4, dict(mg.PPO_ALG, schedule="fixed"))
+    sd = alg.actor_critic.state_dict()
+    assert list(sd) == PARAM_ORDER
+    for k in PARAM_ORDER:
+        assert torch.equal(sd[k].cpu(), params[k]), k
+    g = torch.Generator().manual_seed(0)
+    obs, cobs = torch.randn(200, 615, generator=g), torch.randn(200, 1050, generator=g)
+    mu = alg.actor_critic.act_inference(obs.to(cuda_device)).cpu()
+    v = alg.actor_critic.evaluate(cobs.to(cuda_device)).cpu()
+    with torch.no_grad():
+        w_mu, w_v = mlp(ora.params, "actor", obs), mlp(ora.params, "critic", cobs)
+    assert rel_l2(mu, w_mu) < 2e-3 and rel_l2(v, w_v) < 2e-3
+
+
+def run_rollout(alg, ora, dev, steps_inputs, last):
+    for obs, cobs, eps, rew, dones, tos in steps_inputs:
+        alg.injected_eps = eps.to(dev)
+        a = alg.act(obs.to(dev), cobs.to(dev))
+        a_ref = ora.act(obs, cobs, eps)
+        alg.process_env_step(rew.to(dev), dones.to(dev), {"time_outs": tos.to(dev)})
+        ora.process_env_step(rew, dones, {"time_outs": tos})
+    alg.compute_returns(last.to(dev))
+    ora.compute_returns(last)
+
+
+def test_rollout_storage_and_gae_match_oracle(lib, cuda_device):
+    alg, ora, _ = make_pair(cuda_device, mg.PPO_CASE["n"], mg.PPO_CASE["t"], dict(mg.PPO_ALG, schedule="fixed"))
+    steps, last, perm = mg.golden_ppo_inputs()
+    run_rollout(alg, ora, cuda_device, steps, last)
+    s = alg.storage
+    for k, tol in (("actions", 2e-3), ("values", 2e-3), ("mu", 2e-3), ("actions_log_prob", 2e-3), ("returns", 3e-3),
+                   ("advantages", 5e-3)):
+        got, want = getattr(s, k).cpu(), ora.st[k]
+        assert rel_l2(got, want) < tol, (k, rel_l2(got, want))
+    assert torch.equal(s.dones.cpu(), ora.st["dones"]) and torch.equal(s.sigma.cpu(), ora.st["sigma"])
+    assert torch.equal(s.observations.cpu(), ora.st["observations"])
+    g = np.load(f"{mg.GOLDEN_DIR}/ppo_update_ref.npz")
+    assert rel_l2(s.returns.cpu(), torch.from_numpy(g["st/returns"])) < 3e-3      # the reference's own numbers
+
+
+def test_minibatch_gradients_match_autograd(lib, cuda_device):
+    """One minibatch: forward GEMMs, loss head, dgrad / wgrad GEMMs vs torch autograd on the oracle's loss."""
+    dev = cuda_device
+    n, t = 64, 8
+    cfg = dict(mg.PPO_ALG, schedule="fixed", num_mini_batches=1, num_learning_epochs=1)
+    alg, ora, _ = make_pair(dev, n, t, cfg)
+    g = torch.Generator().manual_seed(5)
+    steps = [(torch.randn(n, 615, generator=g), torch.randn(n, 1050, generator=g), torch.randn(n, 10, generator=g),
+              torch.rand(n, generator=g), torch.rand(n, generator=g) < 0.1, torch.zeros(n, dtype=torch.bool))
+             for _ in range(t)]
+    run_rollout(alg, ora, dev, steps, torch.randn(n, 1050, generator=g))
+    # give the CUDA side exactly the oracle's storage so that only the update path is compared
+    for k in ("actions", "values", "returns", "advantages", "actions_log_prob", "mu", "sigma"):
+        getattr(alg.storage, k).copy_(ora.st[k])
+    # perturb the policy so that ratio != 1 and the clipping branches are exercised
+    with torch.no_grad():
+        for k in PARAM_ORDER:
+            ora.params[k] += 0.02 * torch.randn(ora.params[k].shape, generator=g) * ora.params[k].abs().mean()
+    alg.actor_critic.load_state_dict({k: v.detach() for k, v in ora.params.items()})
+    B = n * t
+    perm = torch.randperm(B, generator=g)
+    # ---- oracle loss + autograd (same expressions as OraclePPO.update) ----
+    from oracle.ppo_oracle import gaussian_entropy, gaussian_log_prob
+    flat = {k: v.flatten(0, 1) for k, v in ora.st.items()}
+    idx = perm
+    mu = mlp(ora.params, "actor", flat["observations"][idx])
+    sigma = mu * 0.0 + ora.params["std"]
+    lp = gaussian_log_prob(flat["actions"][idx], mu, sigma)
+    v = mlp(ora.params, "critic", flat["privileged_observations"][idx])
+    ratio = torch.exp(lp - flat["actions_log_prob"][idx].squeeze())
+    adv = flat["advantages"][idx].squeeze()
+    surrogate = torch.max(-adv * ratio, -adv * torch.clamp(ratio, 0.8, 1.2)).mean()
+    v_old, ret = flat["values"][idx], flat["returns"][idx]
+    v_clip = v_old + (v - v_old).clamp(-0.2, 0.2)
+    value_loss = torch.max((v - ret).pow(2), (v_clip - ret).pow(2)).mean()
+    loss = surrogate + 1.0 * value_loss - 0.001 * gaussian_entropy(sigma).mean()
+    loss.backward()
+    assert ((ratio < 0.8) | (ratio > 1.2)).float().mean() > 0.02, "case must exercise the clipped branch"
+    # ---- CUDA path, pieces of PPO.update ----
+    from isaac_b200 import _lib
+    from isaac_b200.algo.actor_critic import pad4
+    ac, s = alg.actor_critic, alg.storage
+    st = torch.cuda.current_stream(dev).cuda_stream
+    permd = perm.to(dev)
+    xa, xc = torch.zeros(B, pad4(616), device=dev), torch.zeros(B, pad4(1051), device=dev)
+    rec = torch.zeros(B, 36, device=dev)
+    _lib.check(lib.hb_ppo_gather_rows(s._observations.data_ptr(), s.obs_ld, xa.data_ptr(), xa.stride(0), permd.data_ptr(), B, 615, 615, st), "g")
+    _lib.check(lib.hb_ppo_gather_rows(s._privileged_observations.data_ptr(), s.priv_ld, xc.data_ptr(), xc.stride(0), permd.data_ptr(), B, 1050, 1050, st), "g")
+    _lib.check(lib.hb_ppo_pack_samples(permd.data_ptr(), B, s.actions.data_ptr(), s.mu.data_ptr(), s.sigma.data_ptr(), s.values.data_ptr(),
+                                       s.advantages.data_ptr(), s.returns.data_ptr(), s.actions_log_prob.data_ptr(), rec.data_ptr(), st), "p")
+    assert torch.equal(xa[:, :615].cpu(), flat["observations"][idx]) and (xa[:, 615] == 1).all()
+    ws = ac.workspace(B)
+    mu16, v16 = ac._mlp_forward("actor", xa, ws), ac._mlp_forward("critic", xc, ws)
+    stats = torch.zeros(4, dtype=torch.float64, device=dev)
+    lpp = _lib.PpoLossParams(0.2, 1.0, 0.001, 1)
+    _lib.check(lib.hb_ppo_loss_head(mu16.data_ptr(), 16, v16.data_ptr(), 16, ac.std.data_ptr(), rec.data_ptr(), B, B, C.byref(lpp),
+                                    ws["actor"]["d_out"].data_ptr(), ws["critic"]["d_out"].data_ptr(),
+                                    ac.grad[ac._std_offset:].data_ptr(), stats.data_ptr(), st), "head")
+    ac._mlp_backward("actor", xa, ws)
+    ac._mlp_backward("critic", xc, ws)
+    torch.cuda.synchronize()
+    assert abs(stats[0].item() / B - surrogate.item()) < 2e-3 * max(1.0, abs(surrogate.item()))
+    assert abs(stats[1].item() / B - value_loss.item()) < 3e-3 * max(1.0, abs(value_loss.item()))
+    grads = dict(ac.named_gradients())
+    worst = {}
+    for k in PARAM_ORDER:
+        worst[k] = rel_l2(grads[k].cpu(), ora.params[k].grad)
+    print("gradient rel-L2 errors:", {k: f"{v:.1e}" for k, v in worst.items()})
+    assert max(worst.values()) < 5e-3, worst
+    # packed-gradient padding stays zero (it is part of the flat Adam buffer)
+    for L in ac.layers:
+        G = ac._matrix(ac.grad, L)
+        assert (G[:, L.fan_in + 1:] == 0).all() and (G[L.fan_out:, :] == 0).all()
+
+
+@pytest.mark.parametrize("schedule", ["fixed", "adaptive"])
+def test_update_matches_reference_golden(lib, cuda_device, schedule):
+    """Full update() on the golden case: the reference's own post-update weights (digests) and losses."""
+    dev = cuda_device
+    c = mg.PPO_CASE
+    alg, ora, params = make_pair(dev, c["n"], c["t"], dict(mg.PPO_ALG, schedule=schedule), seed=c["param_seed"])
+    steps, last, perm = mg.golden_ppo_inputs()
+    run_rollout(alg, ora, dev, steps, last)
+    for k in ("actions", "values", "returns", "advantages", "actions_log_prob", "mu", "sigma", "rewards"):
+        getattr(alg.storage, k).copy_(ora.st[k])          # isolate the update: identical rollout data
+    alg.injected_perm = perm
+    v_loss, s_loss = alg.update()
+    w_v, w_s = ora.update(perm)
+    g = np.load(f"{mg.GOLDEN_DIR}/ppo_update_ref.npz")
+    np.testing.assert_allclose([w_v, w_s], g[f"{schedule}/losses"], rtol=1e-5)       # oracle == reference
+    assert abs(v_loss - w_v) < 5e-3 * max(1.0, abs(w_v)) and abs(s_loss - w_s) < 5e-3
+    sd = alg.actor_critic.state_dict()
+    steps_taken = mg.PPO_ALG["num_learning_epochs"] * mg.PPO_ALG["num_mini_batches"]
+    if schedule == "adaptive":
+        kls = np.array(ora.kl_trace)
+        margin = np.minimum(np.abs(kls - 0.02), np.abs(kls - 0.005)).min()
+        if margin < 2e-3:
+            pytest.skip(f"KL {kls} too close to a schedule threshold for a discontinuous comparison")
+        assert abs(alg.learning_rate - ora.learning_rate) < 1e-12 * max(1, ora.learning_rate) + 1e-15
+        assert abs(alg.learning_rate - float(g["adaptive/lr"][0])) < 1e-12
+    lr_max = max(ora.lr_trace)
+    for k in PARAM_ORDER:
+        got, want, init = sd[k].cpu().double(), ora.params[k].detach().double(), params[k].double()
+        moved = (want - init).abs().max().item()
+        assert (got - want).abs().max().item() <= 2.0 * lr_max * steps_taken * 1.01 + 1e-9, k     # Adam bound
+        err = float((got - want).norm() / (want - init).norm().clamp_min(1e-30))
+        assert err < 0.25, f"{k}: update direction error {err:.3f} (moved {moved:.2e})"
+        sample = torch.from_numpy(g[f"{schedule}/p/{k}/sample"]).double()
+        assert float((got.flatten()[::97] - sample).abs().max()) <= 2.0 * lr_max * steps_taken * 1.01 + 1e-9
