@@ -89,6 +89,20 @@ def make_workload(n, frames, seed):
     return make_tape(n, frames, seed=seed, fall_prob=0.005, randomize_gains=True)
 
 
+def fill_storage_cpu(st, seed):
+    g = torch.Generator().manual_seed(seed)
+    T, N = st["rewards"].shape[:2]
+    st["observations"].copy_(torch.randn(T, N, 615, generator=g))
+    st["privileged_observations"].copy_(torch.randn(T, N, 1050, generator=g))
+    st["actions"].copy_(torch.randn(T, N, 10, generator=g))
+    st["mu"].copy_(st["actions"] + 0.3 * torch.randn(T, N, 10, generator=g))
+    st["sigma"].fill_(1.0)
+    st["rewards"].copy_(torch.rand(T, N, 1, generator=g) * 0.05)
+    st["values"].copy_(torch.randn(T, N, 1, generator=g) * 0.5)
+    st["dones"].copy_((torch.rand(T, N, 1, generator=g) < 0.005).to(torch.uint8))
+    st["actions_log_prob"].copy_(-0.5 * ((st["actions"] - st["mu"]) ** 2).sum(-1, keepdim=True) - 9.19)
+
+
 # ------------------------------------------------------------------------------------ reference arm
 def run_reference(args, rank):
     """The reference's own torch CPU implementation of the path, restated in oracle/ (the reference is
@@ -119,6 +133,14 @@ def run_reference(args, rank):
     for _ in range(5):
         gae_returns(r, v, d, lv, 0.994, 0.9)
     gae_s = (time.perf_counter() - t0) / 5
+    # PPO update on the CPU: a bounded sample (1 epoch x 4 minibatches of the same [24, n] rollout)
+    from oracle.ppo_oracle import OraclePPO, init_actor_critic_params
+    ora = OraclePPO(init_actor_critic_params(seed=5), n, T_GAE, **dict(PPO_CFG, num_learning_epochs=1))
+    fill_storage_cpu(ora.st, 100)
+    ora.compute_returns(torch.randn(n, 1050, generator=g))
+    t0 = time.perf_counter()
+    ora.update(torch.randperm(n * T_GAE, generator=g))
+    ppo_s = time.perf_counter() - t0
     line = {"impl": "reference", "metric": "env-steps/s", "value": value, "unit": "env-steps/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -128,6 +150,8 @@ def run_reference(args, rank):
                              "sample": f"{args.steps} steps of {n} envs after {args.warmup} warm-up, torch CPU {torch.__version__}"},
             "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gae": {"value": T_GAE * n / gae_s, "unit": "samples/s", "T": T_GAE},
+            "ppo": {"value": T_GAE * n / (ppo_s * 5), "unit": "samples/s", "sample_passes_per_s": T_GAE * n / ppo_s,
+                    "sample": f"1 epoch x 4 minibatches of [{T_GAE},{n}] timed ({ppo_s:.1f} s), x5 epochs extrapolated"},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
@@ -149,6 +173,75 @@ def cpu_baseline(n, budget_s=15.0):
     dt = time.perf_counter() - t0
     return {"value": n * steps / dt, "unit": "env-steps/s", "cores": cores, "kind": "port",
             "sample": f"{steps} steps of {n} envs ({dt:.1f} s), torch CPU oracle port, {cores} threads"}
+
+
+PPO_FLOP_PER_SAMPLE_PASS = 6.853e6        # fwd 3.032 + bwd 3.821 MFLOP
+PPO_CFG = dict(num_learning_epochs=5, num_mini_batches=4, clip_param=0.2, gamma=0.994, lam=0.9, value_loss_coef=1.0,
+               entropy_coef=0.001, learning_rate=1e-5, max_grad_norm=1.0, use_clipped_value_loss=True,
+               schedule="adaptive", desired_kl=0.01)
+
+
+def fill_storage(st, gen_seed, device):
+    """PPO sweep inputs: N(0,1) observations, dones ~ Bernoulli(0.005)."""
+    g = torch.Generator(device=device).manual_seed(gen_seed)
+    T, N = st.num_transitions_per_env, st.num_envs
+    st.observations.copy_(torch.randn(T, N, 615, device=device, generator=g))
+    st.privileged_observations.copy_(torch.randn(T, N, 1050, device=device, generator=g))
+    st.actions.copy_(torch.randn(T, N, 10, device=device, generator=g))
+    st.mu.copy_(st.actions + 0.3 * torch.randn(T, N, 10, device=device, generator=g))
+    st.sigma.fill_(1.0)
+    st.rewards.copy_(torch.rand(T, N, 1, device=device, generator=g) * 0.05)
+    st.values.copy_(torch.randn(T, N, 1, device=device, generator=g) * 0.5)
+    st.dones.copy_((torch.rand(T, N, 1, device=device, generator=g) < 0.005).to(torch.uint8))
+    st.actions_log_prob.copy_(-0.5 * ((st.actions - st.mu) ** 2).sum(-1, keepdim=True) - 9.19)
+
+
+def bench_ppo(args, dev, n, world, rank):
+    """compute_returns + update() on [T=24, n] rollouts: PPO samples/s (BASELINE configs[1]/[4])."""
+    import torch.distributed as dist
+    from isaac_b200.algo.actor_critic import ActorCritic
+    from isaac_b200.algo.ppo import PPO
+    torch.manual_seed(5)
+    ac = ActorCritic(615, 1050, 10, actor_hidden_dims=[512, 256, 128], critic_hidden_dims=[768, 256, 128], device=dev)
+    alg = PPO(ac, device=dev, **PPO_CFG)
+    alg.init_storage(n, T_GAE, [615], [1050], [10])
+    if world > 1:
+        from isaac_b200.parallel import attach_data_parallel
+        attach_data_parallel(alg)
+    last = torch.randn(n, 1050, device=dev)
+    stream = torch.cuda.current_stream(dev)
+    times = []
+    reps = max(2, args.ppo_updates)
+    for r in range(reps + 1):
+        fill_storage(alg.storage, 100 + rank, dev)
+        alg.storage.step = T_GAE
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        alg.compute_returns(last)
+        alg.update()
+        b.record(stream)
+        b.synchronize()
+        if r > 0:
+            times.append(a.elapsed_time(b))
+    ms = sum(times) / len(times)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    samples = n * T_GAE * world
+    passes = samples * PPO_CFG["num_learning_epochs"]
+    tflops = passes * PPO_FLOP_PER_SAMPLE_PASS / (ms * 1e-3) / 1e12
+    peak_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    bf16 = json.load(open(peak_path))["bf16_tflops_sustained"] if os.path.exists(peak_path) else 1400.0
+    return {"value": samples / (ms * 1e-3), "unit": "samples/s", "sample_passes_per_s": passes / (ms * 1e-3),
+            "ms_per_update": ms, "T": T_GAE, "epochs": 5, "mini_batches": 4, "dtype": "tf32 operands, f32 accumulate",
+            "tensor_tflops": tflops, "tensor_peak_tflops": bf16 * world / 2,
+            "tensor_frac": tflops / (bf16 * world / 2),
+            "tensor_peak_source": "half of measured sustained bf16 (MEASURED_PEAKS.json); TF32 rate = 1/2 bf16",
+            "mean_kl": alg.last_mean_kl, "learning_rate": alg.learning_rate}
 
 
 def run_b200(args, rank, world):
@@ -247,6 +340,7 @@ def run_b200(args, rank, world):
     d_, lv_ = (torch.rand(T_GAE, n, 1, generator=g) < 0.005).byte().to(dev), torch.randn(n, 1, generator=g).to(dev)
     ret_, adv_ = torch.empty_like(r_), torch.empty_like(r_)
     k_gae = time_launch(lambda: gae_compute_returns(r_, v_, d_, lv_, ret_, adv_, 0.994, 0.9))
+    ppo = bench_ppo(args, dev, n, world, rank)
     clocks = sampler.summary()
 
     # ---- e2e: host buffers in, host buffers out, env's own noise ----
@@ -318,6 +412,7 @@ def run_b200(args, rank, world):
                     "pd_gbs": n * 240 / (k_pd * 1e-3) / 1e9, "gae_ms": k_gae,
                     "gae_gbs": n * T_GAE * 25 / (k_gae * 1e-3) / 1e9},
         "gae": {"value": total_envs * T_GAE / (k_gae * 1e-3), "unit": "samples/s", "T": T_GAE},
+        "ppo": ppo,
     }
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(n)
@@ -333,6 +428,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly from Python")
+    ap.add_argument("--ppo-updates", type=int, default=3, help="timed PPO updates (after one warm-up)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))

@@ -195,56 +195,93 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         }
     } else {
         // ===================== epilogue (warps 0-3: TMEM lanes 32*warp .. 32*warp+31) =====================
+        // The accumulator arrives with lane = row.  Global traffic wants lane = column (128-byte rows), so
+        // every 32 x 32 block goes through a padded shared-memory tile (the pipeline stages are idle once
+        // the accumulator barrier has fired): activations for ELU' come in coalesced, results leave coalesced.
         if (nkb > 0) {
             hb::mbar_wait(&acc_bar, 0);
             tc_fence_after();
         }
-        const int m = m0 + warp * 32 + lane;
-        const bool row_ok = m < g.M;
-        float *drow = g.D + (size_t)m * g.ldd;
-        const float *hrow = (EPI == EPI_ELU_BWD) ? g.H + (size_t)m * g.ldh : nullptr;
+        float *tile = reinterpret_cast<float *>(smem) + warp * (32 * 33);
+        const int mw = m0 + warp * 32;                     // first row of this warp
 #pragma unroll 1
-        for (int c = 0; c < BN; c += 16) {
-            float v[16];
+        for (int c = 0; c < BN; c += 32) {
+            const int n = n0 + c;
+            if (n >= g.N || mw >= g.M) break;
+            float v[32];
             if (nkb > 0) {
                 tmem_ld16(tmem_acc + ((uint32_t)(warp * 32) << 16) + (uint32_t)c, v);
+                if (BN > 16) tmem_ld16(tmem_acc + ((uint32_t)(warp * 32) << 16) + (uint32_t)(c + 16), v + 16);
             } else {
 #pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] = 0.0f;
+                for (int i = 0; i < 32; ++i) v[i] = 0.0f;
             }
-            const int n = n0 + c;
-            if (!row_ok || n >= g.N) continue;
+            const int ncols = min(32, g.N - n), nrows = min(32, g.M - mw);
+            const bool col_ok = lane < ncols;
             if (EPI == EPI_BIAS || EPI == EPI_BIAS_ELU) {
+                const float bl = col_ok ? __ldg(g.bias + (size_t)(n + lane) * g.bias_stride) : 0.0f;
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    if (n + i < g.N) {
-                        float x = v[i] + __ldg(g.bias + (size_t)(n + i) * g.bias_stride);
-                        if (EPI == EPI_BIAS_ELU) x = x > 0.0f ? x : expf(x) - 1.0f;      // nn.ELU(alpha=1)
-                        v[i] = x;
-                    }
+                for (int i = 0; i < 32; ++i) {
+                    float x = v[i] + __shfl_sync(0xffffffffu, bl, i);
+                    if (EPI == EPI_BIAS_ELU) x = x > 0.0f ? x : expf(x) - 1.0f;          // nn.ELU(alpha=1)
+                    v[i] = x;
                 }
             } else if (EPI == EPI_ELU_BWD) {
+                // rows of H, coalesced: 8 lanes x float4 per row, 4 rows per instruction, all 8 loads in flight
+                const int rr = lane >> 3, c4 = (lane & 7) * 4;
+                const bool fast = (ncols == 32) && ((g.ldh & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.H) & 15u) == 0);
+                if (fast) {
+                    float4 h4[8];
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    if (n + i < g.N) {
-                        const float h = hrow[n + i];                  // h = elu(z): elu'(z) = z > 0 ? 1 : h + 1
-                        v[i] = v[i] * (h > 0.0f ? 1.0f : h + 1.0f);
+                    for (int it = 0; it < 8; ++it) {
+                        const int r = it * 4 + rr;
+                        h4[it] = (r < nrows) ? __ldg(reinterpret_cast<const float4 *>(g.H + (size_t)(mw + r) * g.ldh + n + c4))
+                                             : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+#pragma unroll
+                    for (int it = 0; it < 8; ++it) {
+                        float *t = tile + (it * 4 + rr) * 33 + c4;
+                        t[0] = h4[it].x, t[1] = h4[it].y, t[2] = h4[it].z, t[3] = h4[it].w;
+                    }
+                } else {
+                    for (int r = 0; r < nrows; ++r)
+                        tile[r * 33 + lane] = col_ok ? __ldg(g.H + (size_t)(mw + r) * g.ldh + n + lane) : 0.0f;
+                }
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const float h = tile[lane * 33 + i];           // h = elu(z): elu'(z) = z > 0 ? 1 : h + 1
+                    v[i] = v[i] * (h > 0.0f ? 1.0f : h + 1.0f);
+                }
+                __syncwarp();
+            }
+#pragma unroll
+            for (int i = 0; i < 32; ++i) tile[lane * 33 + i] = v[i];
+            __syncwarp();
+            const bool fast_out = (ncols == 32) && ((g.ldd & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.D) & 15u) == 0);
+            if (fast_out) {
+                const int rr = lane >> 3, c4 = (lane & 7) * 4;
+#pragma unroll
+                for (int it = 0; it < 8; ++it) {
+                    const int r = it * 4 + rr;
+                    if (r < nrows) {
+                        const float *t = tile + r * 33 + c4;
+                        float *dst = g.D + (size_t)(mw + r) * g.ldd + n + c4;
+                        if (EPI == EPI_ATOMIC) {
+                            atomicAdd(dst, t[0]), atomicAdd(dst + 1, t[1]), atomicAdd(dst + 2, t[2]), atomicAdd(dst + 3, t[3]);
+                        } else {
+                            *reinterpret_cast<float4 *>(dst) = make_float4(t[0], t[1], t[2], t[3]);
+                        }
                     }
                 }
+            } else if (col_ok) {
+                for (int r = 0; r < nrows; ++r) {
+                    float *dst = g.D + (size_t)(mw + r) * g.ldd + n + lane;
+                    if (EPI == EPI_ATOMIC) atomicAdd(dst, tile[r * 33 + lane]);
+                    else *dst = tile[r * 33 + lane];
+                }
             }
-            if (EPI == EPI_ATOMIC) {
-#pragma unroll
-                for (int i = 0; i < 16; ++i)
-                    if (n + i < g.N) atomicAdd(drow + n + i, v[i]);
-            } else if (n + 16 <= g.N && ((reinterpret_cast<uintptr_t>(drow + n) & 15u) == 0)) {
-#pragma unroll
-                for (int i = 0; i < 16; i += 4)
-                    *reinterpret_cast<float4 *>(drow + n + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-            } else {
-#pragma unroll
-                for (int i = 0; i < 16; ++i)
-                    if (n + i < g.N) drow[n + i] = v[i];
-            }
+            __syncwarp();
         }
     }
     tc_fence_before();
