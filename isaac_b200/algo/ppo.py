@@ -155,17 +155,51 @@ class PPO:
         self.storage.compute_returns(last_values, self.gamma, self.lam)
 
     # ------------------------------------------------------------------ update (ppo.py:119-184)
-    def update(self):
+    def minibatch_gradients(self, i: int):
+        """Forward, loss head and backward of minibatch i of the gathered buffers (ppo.py:128-172): leaves the
+        global-batch gradient in actor_critic.grad (all-reduced over ranks) and the loss sums in self._stats."""
+        ac, lib, mb = self.actor_critic, self._lib, self._mb
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        ws = ac.workspace(mb)
+        xa, xc, rec = self._xa[i * mb:(i + 1) * mb], self._xc[i * mb:(i + 1) * mb], self._rec[i * mb:(i + 1) * mb]
+        mu16 = ac._mlp_forward("actor", xa, ws)
+        v16 = ac._mlp_forward("critic", xc, ws)
+        self._stats.zero_()
+        _lib.check(lib.hb_ppo_loss_head(mu16.data_ptr(), 16, v16.data_ptr(), 16, ac.std.data_ptr(), rec.data_ptr(), mb,
+                                        mb * self.world_size, C.byref(self._lp), ws["actor"]["d_out"].data_ptr(),
+                                        ws["critic"]["d_out"].data_ptr(), ac.grad[ac._std_offset:].data_ptr(),
+                                        self._stats.data_ptr(), st), "hb_ppo_loss_head")
+        ac._mlp_backward("actor", xa, ws)
+        ac._mlp_backward("critic", xc, ws)
+        if self.grad_allreduce is not None:
+            self.grad_allreduce(ac.grad, self._stats)        # sums over ranks (grads already carry 1/global_mb)
+
+    def optimizer_step(self, adaptive: int):
+        """clip_grad_norm_ + Adam.step + zero_grad (ppo.py:171-174) with the adaptive-KL rule of :136-148."""
+        ac, lib = self.actor_critic, self._lib
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        n_flat = ac.flat.numel()
+        self._sumsq.zero_()
+        _lib.check(lib.hb_grad_sumsq(ac.grad.data_ptr(), n_flat, self._sumsq.data_ptr(), st), "hb_grad_sumsq")
+        self._step += 1
+        ap = AdamParams(0.9, 0.999, 1e-8, float(self.max_grad_norm or 0.0), 1.0 - 0.9 ** self._step,
+                        1.0 - 0.999 ** self._step, adaptive, float(self.desired_kl or 0.0), self._mb * self.world_size)
+        _lib.check(lib.hb_adam_step(ac.flat.data_ptr(), ac.grad.data_ptr(), self._exp_avg.data_ptr(),
+                                    self._exp_avg_sq.data_ptr(), n_flat, C.byref(ap), self._sumsq.data_ptr(),
+                                    self._stats.data_ptr(), self._lr_dev.data_ptr(), st), "hb_adam_step")
+
+    def prepare_minibatches(self, perm=None):
+        """mini_batch_generator's gathers (rollout_storage.py:146-182), once per update (the permutation is
+        reused by every epoch, :149)."""
         ac, lib, s = self.actor_critic, self._lib, self.storage
         dev = self.device
         st = torch.cuda.current_stream(dev).cuda_stream
         B = s.num_envs * s.num_transitions_per_env
         mb = B // self.num_mini_batches
         used = mb * self.num_mini_batches
-        perm = self.injected_perm if self.injected_perm is not None else torch.randperm(used, device=dev)
-        self.injected_perm = None
+        if perm is None:
+            perm = torch.randperm(used, device=dev)
         perm = perm.to(dev, dtype=torch.int64).contiguous()
-        # --- mini_batch_generator (rollout_storage.py:146-182): gathers, once per update ---
         ld_a, ld_c = pad4(ac.num_actor_obs + 1), pad4(ac.num_critic_obs + 1)
         if getattr(self, "_xa", None) is None or self._xa.shape[0] != used:
             self._xa = torch.zeros(used, ld_a, device=dev)
@@ -179,35 +213,22 @@ class PPO:
                                            s.sigma.data_ptr(), s.values.data_ptr(), s.advantages.data_ptr(),
                                            s.returns.data_ptr(), s.actions_log_prob.data_ptr(), self._rec.data_ptr(), st),
                    "hb_ppo_pack_samples")
-        ws = ac.workspace(mb)
-        lp = PpoLossParams(self.clip_param, self.value_loss_coef, self.entropy_coef, int(self.use_clipped_value_loss))
+        self._mb = mb
+        self._lp = PpoLossParams(self.clip_param, self.value_loss_coef, self.entropy_coef, int(self.use_clipped_value_loss))
+        return mb
+
+    def update(self):
+        perm, self.injected_perm = self.injected_perm, None
+        mb = self.prepare_minibatches(perm)
+        self._mb, self._lp = mb, PpoLossParams(self.clip_param, self.value_loss_coef, self.entropy_coef,
+                                                int(self.use_clipped_value_loss))
         adaptive = int(self.desired_kl is not None and self.schedule == "adaptive")
         self._loss_acc.zero_()
-        n_flat = ac.flat.numel()
-        std_grad = ac.grad[ac._std_offset:]
         for _ in range(self.num_learning_epochs):
             for i in range(self.num_mini_batches):
-                xa, xc, rec = self._xa[i * mb:(i + 1) * mb], self._xc[i * mb:(i + 1) * mb], self._rec[i * mb:(i + 1) * mb]
-                mu16 = ac._mlp_forward("actor", xa, ws)
-                v16 = ac._mlp_forward("critic", xc, ws)
-                self._stats.zero_()
-                _lib.check(lib.hb_ppo_loss_head(mu16.data_ptr(), 16, v16.data_ptr(), 16, ac.std.data_ptr(),
-                                                rec.data_ptr(), mb, mb * self.world_size, C.byref(lp),
-                                                ws["actor"]["d_out"].data_ptr(), ws["critic"]["d_out"].data_ptr(),
-                                                std_grad.data_ptr(), self._stats.data_ptr(), st), "hb_ppo_loss_head")
-                ac._mlp_backward("actor", xa, ws)
-                ac._mlp_backward("critic", xc, ws)
-                if self.grad_allreduce is not None:
-                    self.grad_allreduce(ac.grad, self._stats)        # sums over ranks (grads already carry 1/global_mb)
+                self.minibatch_gradients(i)
                 self._loss_acc += self._stats
-                self._sumsq.zero_()
-                _lib.check(lib.hb_grad_sumsq(ac.grad.data_ptr(), n_flat, self._sumsq.data_ptr(), st), "hb_grad_sumsq")
-                self._step += 1
-                ap = AdamParams(0.9, 0.999, 1e-8, float(self.max_grad_norm or 0.0), 1.0 - 0.9 ** self._step,
-                                1.0 - 0.999 ** self._step, adaptive, float(self.desired_kl or 0.0), mb * self.world_size)
-                _lib.check(lib.hb_adam_step(ac.flat.data_ptr(), ac.grad.data_ptr(), self._exp_avg.data_ptr(),
-                                            self._exp_avg_sq.data_ptr(), n_flat, C.byref(ap), self._sumsq.data_ptr(),
-                                            self._stats.data_ptr(), self._lr_dev.data_ptr(), st), "hb_adam_step")
+                self.optimizer_step(adaptive)
         self._lr_dirty = bool(adaptive)
         num_updates = self.num_learning_epochs * self.num_mini_batches
         acc = self._loss_acc.cpu()              # the single host sync of the update (the reference's .item() calls)

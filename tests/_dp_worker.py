@@ -1,0 +1,118 @@
+"""torchrun worker for tests/test_multi_gpu.py: data-parallel PPO update on G ranks == single-GPU update on the
+concatenated batch with the equivalent minibatch index tape (SURVEY.md §8e parity definition)."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch
+import torch.distributed as dist
+
+from isaac_b200.algo.actor_critic import ActorCritic
+from isaac_b200.algo.ppo import PPO
+from isaac_b200.parallel import attach_data_parallel, shard_range
+
+CFG = dict(num_learning_epochs=2, num_mini_batches=2, clip_param=0.2, gamma=0.994, lam=0.9, value_loss_coef=1.0,
+           entropy_coef=0.001, learning_rate=1e-3, max_grad_norm=1.0, use_clipped_value_loss=True, schedule="fixed")
+T, N = 8, 64
+
+
+def global_rollout():
+    g = torch.Generator().manual_seed(1)
+    return dict(obs=torch.randn(T, N, 615, generator=g), priv=torch.randn(T, N, 1050, generator=g),
+                actions=torch.randn(T, N, 10, generator=g), mu=torch.randn(T, N, 10, generator=g),
+                rewards=torch.rand(T, N, 1, generator=g), values=torch.randn(T, N, 1, generator=g),
+                dones=(torch.rand(T, N, 1, generator=g) < 0.05).to(torch.uint8),
+                logp=-10 + torch.randn(T, N, 1, generator=g) * 0.1, last=torch.randn(N, 1, generator=g))
+
+
+def make_alg(dev, n_local):
+    torch.manual_seed(7)
+    ac = ActorCritic(615, 1050, 10, actor_hidden_dims=[512, 256, 128], critic_hidden_dims=[768, 256, 128], device=dev)
+    alg = PPO(ac, device=dev, **CFG)
+    alg.init_storage(n_local, T, [615], [1050], [10])
+    return alg
+
+
+def load(alg, R, lo, hi, dev):
+    s = alg.storage
+    s.observations.copy_(R["obs"][:, lo:hi]), s.privileged_observations.copy_(R["priv"][:, lo:hi])
+    s.actions.copy_(R["actions"][:, lo:hi]), s.mu.copy_(R["mu"][:, lo:hi]), s.sigma.fill_(1.0)
+    s.rewards.copy_(R["rewards"][:, lo:hi]), s.values.copy_(R["values"][:, lo:hi]), s.dones.copy_(R["dones"][:, lo:hi])
+    s.actions_log_prob.copy_(R["logp"][:, lo:hi])
+    s.compute_returns(R["last"][lo:hi].to(dev), CFG["gamma"], CFG["lam"])
+
+
+def main():
+    dist.init_process_group("nccl")
+    rank, world = dist.get_rank(), dist.get_world_size()
+    dev = torch.device("cuda", int(os.environ["LOCAL_RANK"]))
+    torch.cuda.set_device(dev)
+    R = global_rollout()
+    lo, hi = shard_range(N, rank, world)
+    nl = hi - lo
+    alg = make_alg(dev, nl)
+    attach_data_parallel(alg)
+    load(alg, R, lo, hi, dev)
+    g = torch.Generator().manual_seed(100 + rank)
+    local_perm = torch.randperm(T * nl, generator=g)
+    perms = [torch.empty_like(local_perm, device=dev) for _ in range(world)]
+    dist.all_gather(perms, local_perm.to(dev))
+    # equivalent global permutation: minibatch k = rank-wise concatenation of the local minibatches k
+    mbl = (T * nl) // CFG["num_mini_batches"]
+    chunks = []
+    for k in range(CFG["num_mini_batches"]):
+        for r in range(world):
+            p = perms[r].cpu()[k * mbl:(k + 1) * mbl]
+            t, e = p // nl, p % nl                      # local flat index -> (t, env)
+            chunks.append(t * N + (e + r * nl))
+    global_perm = torch.cat(chunks)
+    # (1) gradients of minibatch 0: all-reduced DP gradient == single-GPU gradient of the concatenated minibatch
+    alg.prepare_minibatches(local_perm)
+    alg.minibatch_gradients(0)
+    g_dp = alg.actor_critic.grad.clone()
+    alg.actor_critic.grad.zero_()
+    ok = True
+    ref = init = None
+    if rank == 0:
+        ref = make_alg(dev, N)
+        init = {k: v.clone() for k, v in ref.actor_critic.state_dict().items()}
+        load(ref, R, 0, N, dev)
+        assert torch.allclose(alg.storage.advantages, ref.storage.advantages[:, lo:hi], rtol=1e-5, atol=1e-6), \
+            "global advantage normalisation"
+        ref.prepare_minibatches(global_perm)
+        ref.minibatch_gradients(0)
+        g_ref = ref.actor_critic.grad.clone()
+        ref.actor_critic.grad.zero_()
+        rel = float((g_dp - g_ref).double().norm() / g_ref.double().norm())
+        print(f"gradient DP vs single: rel L2 {rel:.3e}")
+        ok = ok and rel < 1e-4
+    # (2) full update
+    alg.injected_perm = local_perm
+    alg.update()
+    torch.cuda.synchronize()
+    if rank == 0:
+        ref.injected_perm = global_perm
+        ref.update()
+        a, b = alg.actor_critic.state_dict(), ref.actor_critic.state_dict()
+        worst = 0.0
+        for k in a:
+            moved = (b[k] - init[k]).double().norm().clamp_min(1e-30)
+            worst = max(worst, float((a[k] - b[k]).double().norm() / moved))
+        print(f"worst relative update difference DP vs single: {worst:.3e}")
+        # Adam divides by sqrt(v): elements with near-zero gradient amplify the (1e-5-level) summation-order
+        # differences, so the updates agree to a few percent of the distance moved, not to 1e-5
+        ok = ok and worst < 0.1
+    # replicas must stay bit-identical
+    flat = alg.actor_critic.flat.clone()
+    dist.broadcast(flat, 0)
+    same = torch.equal(flat, alg.actor_critic.flat)
+    flag = torch.tensor([int(ok and same)], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    dist.destroy_process_group()
+    sys.exit(0 if int(flag.item()) == 1 else 1)
+
+
+if __name__ == "__main__":
+    main()
