@@ -15,7 +15,7 @@ value      device time: per-step CUDA events on the launching stream, all inputs
 e2e        the public `HectorFreeEnvB200.step()` with HOST buffers: per step the physics state and the
            actions are copied from pinned host memory, the env draws its own noise, and obs /
            privileged obs / rewards / resets are copied back to pinned host memory; wall clock.
-roofline   the dominant kernel (privileged-observation frame stacking) against MEASURED_PEAKS.json.
+roofline   the dominant kernel (frame stacking of both observation histories) against MEASURED_PEAKS.json.
 cpu_baseline / --impl reference: the CPU oracle port of the reference's torch code
            (oracle/hector_oracle.py, torch CPU, all host threads) on the same workload.
 """
@@ -384,7 +384,11 @@ def run_b200(args, rank, world):
     value = total_envs * args.steps / (dev_ms * 1e-3)
     hist_priv = n * 2 * (STACK_PRIV - 1) * FRAME_PRIV * 4          # read + write of the carried frames
     hist_obs = n * 2 * (STACK_OBS - 1) * FRAME_OBS * 4
-    ach = hist_priv / (k_priv * 1e-3) / 1e9
+    ach = (hist_priv + hist_obs) / (k_stack * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tpath):           # dram bytes of one launch from the committed ncu --set full capture, scaled to n envs
+        traffic = json.load(open(tpath))["bytes_per_env"] * n
     line = {
         "metric": "env-steps/s", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -399,10 +403,11 @@ def run_b200(args, rank, world):
         "e2e": {"value": total_envs * args.steps / e2e_wall, "unit": "env-steps/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_wall / args.steps},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "kernel": "stack_shift_kernel (privileged obs, 14 carried frames of 70 floats)",
-                     "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
-                     "peak_source": peak_src, "algorithmic_bytes_per_launch": hist_priv,
-                     "launch_ms": k_priv},
+        "roofline": {"bound": "hbm",
+                     "kernel": "stack_shift_pair_kernel (frame stacking: 14 carried frames of 41 + 70 floats, read + write)",
+                     "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
+                     "peak_source": peak_src, "algorithmic_bytes_per_launch": hist_priv + hist_obs,
+                     "launch_ms": k_stack},
         "roofline_step": {"bytes_per_env_step": B_ENV_STEP, "achieved": value / world * B_ENV_STEP / 1e9,
                           "peak": peak, "unit": "GB/s", "frac": value / world * B_ENV_STEP / 1e9 / peak},
         "kernels": {"post_physics_ms": k_post, "stack_pair_ms": k_stack,
