@@ -5,8 +5,8 @@
 
 A "step" is one `env.step(actions)` over E environments per GPU with the opaque physics stage
 stubbed: action prologue, `decimation`=10 PD-torque launches, the fused
-post-physics kernel (termination, 18 reward terms, resets, newest observation frames) and the
-frame-stacking kernel, including the reset count written to pinned host memory.
+post-physics kernel (termination, 18 reward terms, resets, newest observation frames), the
+frame-stacking kernel and the reset finalisation (ids, count to pinned host memory, episode means).
 metric = env-steps/s summed over all GPUs (weak scaling: E envs per GPU, no data-path collective).
 The same run also times GAE over [T=24, E] and reports it under "gae".
 
@@ -256,6 +256,9 @@ def run_b200(args, rank, world):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     lib = _lib.load(check_device=True)
+    for kv in args.opt:
+        k, v = kv.split("=")
+        _lib.check(lib.hb_set_option(k.encode(), int(v)), f"hb_set_option({kv})")
     n = args.envs
     frames = 4
     tape = make_workload(n, frames, 1234 + rank)
@@ -271,7 +274,15 @@ def run_b200(args, rank, world):
             env.step(noise_frames[0].actions)
         env.enable_cuda_graph()
     flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)     # > 126 MB L2
+    flush_sink = torch.zeros(1, device=dev)
     stream = torch.cuda.current_stream(dev)
+
+    def flush_l2(i):
+        """Outside every timed region: a 256 MiB write evicts the step's data, then a 256 MiB read leaves L2
+        full of CLEAN lines - after a write-only flush the next kernel would pay for writing ~126 MB of dirty
+        flush lines back to HBM inside its own timed region."""
+        flush.fill_(float(i))
+        flush_sink.copy_(flush.sum())
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -281,7 +292,7 @@ def run_b200(args, rank, world):
     def one_step(i, timed):
         f = i % frames
         phys.load_frame(phys_frames[f])
-        flush.fill_(float(i))
+        flush_l2(i)
         if args.no_graph:
             env.inject_noise(noise_frames[f])   # eager path: noise tensors already resident in HBM
         if timed:
@@ -307,40 +318,49 @@ def run_b200(args, rank, world):
 
     # ---- per-kernel timings for the roofline (each launch alone, L2 flushed before it) ----
     def time_launch(fn, reps=10):
+        """One launch, replayed from a single-node CUDA graph so that the host-side launch path (ctypes,
+        argument marshalling) stays out of the event interval; L2 flushed before every replay."""
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            rc = fn(torch.cuda.current_stream(dev).cuda_stream)
+        if rc not in (0, None):
+            _lib.check(rc, "time_launch")
         tot = 0.0
         for r in range(reps + 2):
-            flush.fill_(float(r))
+            flush_l2(r)
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record(stream)
-            fn()
+            g.replay()
             b.record(stream)
             b.synchronize()
             if r >= 2:
                 tot += a.elapsed_time(b)
         return tot / reps
 
-    st = stream.cuda_stream
     cur, prev = env._cur, env._cur ^ 1
     P, B = env._pp, env._pb
-    rb = env.reset_buf.data_ptr()
-    k_priv = time_launch(lambda: lib.hb_stack_shift(env._priv[prev].data_ptr(), env._priv[cur].data_ptr(), rb, n,
+    rb = None            # unconditional shift (reset envs are zeroed by hb_env_reset_finalize)
+    k_priv = time_launch(lambda st: lib.hb_stack_shift(env._priv[prev].data_ptr(), env._priv[cur].data_ptr(), rb, n,
                                                     STACK_PRIV * FRAME_PRIV, FRAME_PRIV, st))
-    k_obs = time_launch(lambda: lib.hb_stack_shift(env._obs[prev].data_ptr(), env._obs[cur].data_ptr(), rb, n,
+    k_obs = time_launch(lambda st: lib.hb_stack_shift(env._obs[prev].data_ptr(), env._obs[cur].data_ptr(), rb, n,
                                                    STACK_OBS * FRAME_OBS, FRAME_OBS, st))
-    k_pd = time_launch(lambda: lib.hb_env_compute_torques(P, B, st))
+    k_pd = time_launch(lambda st: lib.hb_env_compute_torques(P, B, st))
     env.inject_noise(noise_frames[0])
     env._draw_noise(False)
-    k_post = time_launch(lambda: lib.hb_env_post_physics(P, B, env._pn, env._obs[cur].data_ptr(), env._priv[cur].data_ptr(),
-                                                         _lib.HB_STAGE_STEP, env._host_count.data_ptr(), st))
-    k_stack = time_launch(lambda: lib.hb_env_stack_observations(P, B, env._obs[prev].data_ptr(), env._priv[prev].data_ptr(),
+    k_post = time_launch(lambda st: lib.hb_env_post_physics(P, B, env._pn, env._obs[cur].data_ptr(), env._priv[cur].data_ptr(),
+                                                         _lib.HB_STAGE_STEP, st))
+    k_fin = time_launch(lambda st: lib.hb_env_reset_finalize(P, B, env._obs[cur].data_ptr(), env._priv[cur].data_ptr(),
+                                                          env._host_count.data_ptr(), st))
+    k_stack = time_launch(lambda st: lib.hb_env_stack_observations(P, B, env._obs[prev].data_ptr(), env._priv[prev].data_ptr(),
                                                                 env._obs[cur].data_ptr(), env._priv[cur].data_ptr(), st))
     # GAE
     g = torch.Generator().manual_seed(rank)
     r_, v_ = torch.rand(T_GAE, n, 1, generator=g).to(dev), torch.randn(T_GAE, n, 1, generator=g).to(dev)
     d_, lv_ = (torch.rand(T_GAE, n, 1, generator=g) < 0.005).byte().to(dev), torch.randn(n, 1, generator=g).to(dev)
     ret_, adv_ = torch.empty_like(r_), torch.empty_like(r_)
-    k_gae = time_launch(lambda: gae_compute_returns(r_, v_, d_, lv_, ret_, adv_, 0.994, 0.9))
-    ppo = bench_ppo(args, dev, n, world, rank)
+    gae_stats = torch.zeros(2, dtype=torch.float64, device=dev)
+    k_gae = time_launch(lambda st: gae_compute_returns(r_, v_, d_, lv_, ret_, adv_, 0.994, 0.9, stats=gae_stats) and None)
+    ppo = None if args.skip_ppo else bench_ppo(args, dev, n, world, rank)
     clocks = sampler.summary()
 
     # ---- e2e: host buffers in, host buffers out, env's own noise ----
@@ -373,10 +393,10 @@ def run_b200(args, rank, world):
                                                       host_actions[0]))
     d2h = sum(t.numel() * t.element_size() for t in out_host)
 
-    t = torch.tensor([dev_ms, wall, e2e_wall, k_priv, k_obs, k_pd, k_gae, k_post, k_stack], dtype=torch.float64, device=dev)
+    t = torch.tensor([dev_ms, wall, e2e_wall, k_priv, k_obs, k_pd, k_gae, k_post, k_stack, k_fin], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, wall, e2e_wall, k_priv, k_obs, k_pd, k_gae, k_post, k_stack = t.tolist()
+    dev_ms, wall, e2e_wall, k_priv, k_obs, k_pd, k_gae, k_post, k_stack, k_fin = t.tolist()
     if rank != 0:
         return
     peak, peak_src = peaks()
@@ -397,7 +417,7 @@ def run_b200(args, rank, world):
                    "envs_per_gpu": n, "decimation": 10, "frame_stack": 15,
                    "launch": "eager, noise tensors resident in HBM" if args.no_graph else
                              "CUDA-graph replay (2 graphs/step around the reset-count hand-off), noise drawn on device inside the graph",
-                   "timing": "per-step CUDA events, L2 flushed between steps (256 MiB write outside the events)",
+                   "timing": "per-step CUDA events, L2 flushed between steps (256 MiB write then 256 MiB read, outside the events)",
                    "wall_ms_per_step_incl_flush": 1e3 * wall / args.steps},
         "clocks": clocks,
         "e2e": {"value": total_envs * args.steps / e2e_wall, "unit": "env-steps/s", "h2d_bytes_per_step": h2d,
@@ -410,7 +430,7 @@ def run_b200(args, rank, world):
                      "launch_ms": k_stack},
         "roofline_step": {"bytes_per_env_step": B_ENV_STEP, "achieved": value / world * B_ENV_STEP / 1e9,
                           "peak": peak, "unit": "GB/s", "frac": value / world * B_ENV_STEP / 1e9 / peak},
-        "kernels": {"post_physics_ms": k_post, "stack_pair_ms": k_stack,
+        "kernels": {"post_physics_ms": k_post, "reset_finalize_ms": k_fin, "stack_pair_ms": k_stack,
                     "stack_pair_gbs": (hist_obs + hist_priv) / (k_stack * 1e-3) / 1e9,
                     "stack_priv_ms": k_priv, "stack_obs_ms": k_obs,
                     "stack_obs_gbs": hist_obs / (k_obs * 1e-3) / 1e9, "pd_ms": k_pd,
@@ -433,6 +453,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly from Python")
+    ap.add_argument("--opt", action="append", default=[], help="library tuning switch name=value (hb_set_option)")
+    ap.add_argument("--skip-ppo", action="store_true", help="env stage only (tuning sweeps)")
     ap.add_argument("--ppo-updates", type=int, default=3, help="timed PPO updates (after one warm-up)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))

@@ -16,7 +16,7 @@
  *     caller.  The gym tensors (root_states, dof_state, contact_forces, rigid_state) are
  *     owned by PhysX and are read / written in place (envs/base/legged_robot.py:437-456).
  *   - calls are asynchronous on `stream`; the only host-visible result is `host_count` of
- *     hb_env_post_physics (a pinned int the kernel writes; wait on the stream before reading).
+ *     hb_env_reset_finalize (a pinned int the kernel writes; wait on the stream before reading).
  */
 #ifndef HECTOR_B200_H
 #define HECTOR_B200_H
@@ -139,10 +139,10 @@ typedef struct hb_env_buffers {
                                        without resets the values of episode_means_prev are carried over */
     const float *episode_means_prev;/* [HB_NUM_REWARDS] or NULL */
     uint8_t *time_outs_latched;     /* [N] copy of time_out_buf taken only on steps with >=1 reset (extras["time_outs"]) */
-    /* scratch: ceil(N/32) words + ceil(N/32)*HB_NUM_REWARDS floats + 1 ticket */
+    /* scratch: ceil(N/32) ballot words (one per 32-env tile) and HB_NUM_REWARDS fp64 accumulators (zeroed
+     * once by the caller; hb_env_reset_finalize re-arms them) */
     uint32_t *scratch_ballots;
-    float *scratch_partials;
-    uint32_t *scratch_ticket;
+    double *scratch_sums;
 } hb_env_buffers;
 
 /* Per-step random draws, indexed by env (NULL = that draw is not needed / treated as 0). */
@@ -168,7 +168,8 @@ int hb_abi_version(void);
 /* Number of kernels this library has launched since load / since the last reset (bench bookkeeping). */
 int64_t hb_launch_count(void);
 void hb_launch_count_reset(void);
-/* Tuning switches ("env_bulk_staging": 1 = 1-D bulk async copies (default), 0 = vector loads). */
+/* Tuning switches: "env_bulk_staging" 1 = 1-D bulk async copies (default), 0 = vector loads;
+ * "stack_unroll" 4 (default) or 8 = 16-byte vectors in flight per thread of the frame-stack shift. */
 int hb_set_option(const char *name, int value);
 
 /* HectorFreeEnv.step prologue: clip, action delay, action noise, clip
@@ -184,22 +185,35 @@ int hb_env_compute_torques(const hb_env_params *p, const hb_env_buffers *buf, vo
 /* LeggedRobot.post_physics_step without the observation stacking
  * (envs/base/legged_robot.py:118-153,155-234,303-335,358-396; hector_env.py:53-88,256-539):
  * derived base quantities, command resampling + heading command, push, termination, the 18
- * reward terms, reset bookkeeping, the newest observation / privileged frames and the last_*
- * copies.  The newest frames are written (clipped) into the last frame slot of obs_new /
- * priv_new; hb_env_stack_observations fills the other slots.
- * host_count: optional pinned host int that receives the reset count. */
+ * reward terms, per-env reset bookkeeping, the newest observation / privileged frames and the
+ * last_* copies.  The newest frames are written (noise added, clipped) into the last frame slot of
+ * obs_new / priv_new; hb_env_stack_observations fills the other slots.  Shard-wide results of
+ * reset_idx (id list, count, episode means) are produced by hb_env_reset_finalize, which must
+ * follow every call of this function. */
 int hb_env_post_physics(const hb_env_params *p, const hb_env_buffers *buf, const hb_env_noise *noise,
-                        float *obs_new, float *priv_new, int32_t stages, int32_t *host_count, void *stream);
+                        float *obs_new, float *priv_new, int32_t stages, void *stream);
 
-/* Frame stacking of HectorFreeEnv.compute_observations + the history zeroing of reset_idx
- * (envs/custom/hector_env.py:246-261): slots 0..S-2 of obs_new/priv_new <- slots 1..S-1 of
- * obs_prev/priv_prev, or zeros for envs whose reset_buf is set. */
+/* Frame stacking of HectorFreeEnv.compute_observations (envs/custom/hector_env.py:246-254):
+ * slots 0..S-2 of obs_new/priv_new <- slots 1..S-1 of obs_prev/priv_prev, for every env.  The shift
+ * does not depend on this step's physics: it may be launched any time after the previous step, before
+ * hb_env_reset_finalize. */
 int hb_env_stack_observations(const hb_env_params *p, const hb_env_buffers *buf,
                               const float *obs_prev, const float *priv_prev,
                               float *obs_new, float *priv_new, void *stream);
 
-/* One frame-stack shift on its own (what hb_env_stack_observations launches twice):
- * next[:, 0:row-frame] = reset_buf ? 0 : prev[:, frame:row]; next[:, row-frame:row] is left alone. */
+/* The shard-wide half of reset_idx (envs/base/legged_robot.py:142,162-214; hector_env.py:256-261), after
+ * hb_env_post_physics and hb_env_stack_observations of the same step:
+ *   reset_env_ids / reset_count = reset_buf.nonzero() in ascending order (+ *host_count, an optional
+ *   pinned host int: gym.set_*_tensor_indexed need the count on the host, legged_robot.py:370-372,394-396);
+ *   episode_means (extras["episode"], :198-201) and time_outs_latched (extras["time_outs"], :208-209),
+ *   both only refreshed on steps with >= 1 reset like the reference;
+ *   slots 0..S-2 of obs_new/priv_new zeroed for the reset envs (pass NULL for both to skip: reset_idx
+ *   called outside step()). */
+int hb_env_reset_finalize(const hb_env_params *p, const hb_env_buffers *buf, float *obs_new, float *priv_new,
+                          int32_t *host_count, void *stream);
+
+/* One frame-stack shift on its own: next[:, 0:row-frame] = prev[:, frame:row] (zeros for envs whose
+ * reset_buf byte is set, if reset_buf is not NULL); next[:, row-frame:row] is left alone. */
 int hb_stack_shift(const float *prev, float *next, const uint8_t *reset_buf, int32_t num_envs, int32_t row,
                    int32_t frame, void *stream);
 

@@ -66,7 +66,7 @@ _BUFFER_FIELDS = (
     "torques", "commands", "base_lin_vel", "base_ang_vel", "projected_gravity", "base_euler_xyz", "feet_air_time",
     "last_contacts", "feet_height", "last_feet_z", "rand_push_force", "rand_push_torque", "episode_sums",
     "episode_length_buf", "reset_buf", "time_out_buf", "rew_buf", "reset_env_ids", "reset_count", "episode_means",
-    "episode_means_prev", "time_outs_latched", "scratch_ballots", "scratch_partials", "scratch_ticket")
+    "episode_means_prev", "time_outs_latched", "scratch_ballots", "scratch_sums")
 
 
 class EnvBuffers(C.Structure):
@@ -119,8 +119,9 @@ _SIGNATURES = {
     "hb_env_action_prologue": (C.c_int, [C.POINTER(EnvParams), C.POINTER(EnvBuffers), _fp, C.POINTER(EnvNoise), _fp]),
     "hb_env_compute_torques": (C.c_int, [C.POINTER(EnvParams), C.POINTER(EnvBuffers), _fp]),
     "hb_env_post_physics": (C.c_int, [C.POINTER(EnvParams), C.POINTER(EnvBuffers), C.POINTER(EnvNoise), _fp, _fp,
-                                      C.c_int32, _fp, _fp]),
+                                      C.c_int32, _fp]),
     "hb_env_stack_observations": (C.c_int, [C.POINTER(EnvParams), C.POINTER(EnvBuffers), _fp, _fp, _fp, _fp, _fp]),
+    "hb_env_reset_finalize": (C.c_int, [C.POINTER(EnvParams), C.POINTER(EnvBuffers), _fp, _fp, _fp, _fp]),
     "hb_stack_shift": (C.c_int, [_fp, _fp, _fp, C.c_int32, C.c_int32, C.c_int32, _fp]),
     "hb_gemm_tf32": (C.c_int, [C.POINTER(GemmDesc), _fp]),
     "hb_ppo_gather_rows": (C.c_int, [_fp, C.c_int32, _fp, C.c_int32, _fp, C.c_int64, C.c_int32, C.c_int32, _fp]),

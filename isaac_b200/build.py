@@ -51,7 +51,8 @@ def _digest() -> str:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    digest = _digest()
+    extra_all = os.environ.get("HB_EXTRA_NVCC_FLAGS", "").split()      # debug builds, e.g. -DHB_POST_TIMING
+    digest = _digest() + "".join(extra_all)
     if not force and os.path.exists(LIB) and os.path.exists(STAMP) and open(STAMP).read().strip() == digest:
         return LIB
     nvcc = _nvcc()
@@ -59,7 +60,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     procs = []
     for unit, extra in UNITS.items():
         obj = os.path.join(CSRC, unit.replace(".cu", ".o"))
-        cmd = [nvcc, *ARCH, *COMMON, *extra, "-c", os.path.join(CSRC, unit), "-o", obj]
+        cmd = [nvcc, *ARCH, *COMMON, *extra, *extra_all, "-c", os.path.join(CSRC, unit), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
             print(" ".join(cmd), flush=True)

@@ -140,8 +140,11 @@ struct TileLayout {          // float offsets into the CTA's shared-memory tile
     int root, dof, contact, actions, last_actions, last_last_actions, last_dof_vel, torques, last_root_vel,
         commands, z_obs, terms, gait_s, gait_c, flags, so, sp, total;
 };
-constexpr int PRIV_PAD = PRIV + 1;     // odd row stride: conflict-free lane-per-row writes
+constexpr int PRIV_PAD = PRIV;         // even row stride: the store loop reads 8-byte pairs (2-way conflicts on the role writes)
 
+// The staged inputs are dead once every role has passed barrier 1 (each lane keeps its env's values in
+// registers), so the newest-frame staging tiles so/sp reuse the same bytes: ~19 KB per CTA instead of
+// ~38 KB, which is what bounds the number of resident tiles per SM.
 __host__ __device__ inline TileLayout make_layout(int nbody, bool with_noise) {
     TileLayout L;
     int o = 0;
@@ -155,13 +158,15 @@ __host__ __device__ inline TileLayout make_layout(int nbody, bool with_noise) {
     L.torques = o, o += TILE * NDOF;
     L.last_root_vel = o, o += TILE * 6;
     L.commands = o, o += TILE * 4;
-    L.z_obs = o, o += with_noise ? TILE * OBS : 0;
+    L.so = 0;
+    L.sp = TILE * OBS;
+    const int out_end = TILE * (OBS + PRIV_PAD);
+    o = o > out_end ? o : out_end;
+    L.z_obs = o, o += with_noise ? TILE * OBS : 0;      // read by the store loop: must outlive the inputs
     L.terms = o, o += HB_NUM_REWARDS * TILE;
     L.gait_s = o, o += TILE;
     L.gait_c = o, o += TILE;
     L.flags = o, o += TILE;
-    L.so = o, o += TILE * OBS;
-    L.sp = o, o += TILE * PRIV_PAD;
     L.total = o;
     return L;
 }
@@ -196,14 +201,35 @@ __device__ __noinline__ Vec3 euler_xyz_wrapped_nl(float x, float y, float z, flo
     return {roll, pitch, yaw};
 }
 
+#ifdef HB_POST_TIMING
+// debug build: per-(tile, warp) SM-clock stamps at the phase boundaries of post_physics_kernel
+__device__ long long g_post_stamps[4096 * 4 * 8];
+__device__ unsigned long long g_post_gt[4096 * 3];          // globaltimer ns: CTA start, stores done, tail done
+__device__ __forceinline__ unsigned long long gtime() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+#define HB_GT(slot)                                                                        \
+    do {                                                                                   \
+        if (threadIdx.x == 0 && blockIdx.x < 4096) g_post_gt[blockIdx.x * 3 + (slot)] = gtime(); \
+    } while (0)
+#define HB_STAMP(slot)                                                                                   \
+    do {                                                                                                 \
+        if (lane == 0 && blockIdx.x < 4096) g_post_stamps[(blockIdx.x * 4 + warp) * 8 + (slot)] = clock64(); \
+    } while (0)
+#else
+#define HB_STAMP(slot) do { } while (0)
+#define HB_GT(slot) do { } while (0)
+#endif
+
 template <bool kBulk>
-__global__ void __launch_bounds__(4 * TILE)
+__global__ void __launch_bounds__(4 * TILE, 8)
 post_physics_kernel(const __grid_constant__ hb_env_params p, const __grid_constant__ hb_env_buffers b,
                     const __grid_constant__ hb_env_noise nz, float *__restrict__ obs_new,
-                    float *__restrict__ priv_new, int stages, int32_t *host_count) {
+                    float *__restrict__ priv_new, int stages) {
     extern __shared__ __align__(128) float sm[];
     __shared__ __align__(8) uint64_t bar;
-    __shared__ int s_is_last;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int N = p.num_envs;
     const int env0 = blockIdx.x * TILE;
@@ -215,12 +241,20 @@ post_physics_kernel(const __grid_constant__ hb_env_params p, const __grid_consta
     const bool derive = do_step || (stages & HB_STAGE_DERIVE);
     const bool emit_obs = do_step || (stages & HB_STAGE_OBS);
     const bool with_noise = p.add_noise && nz.z_obs != nullptr;
+    HB_STAMP(0);
+    HB_GT(0);
     const TileLayout L = make_layout(p.num_bodies, with_noise);
     const int crow = p.num_bodies * 3;
     const float dt = p.dt;
     const float clip = p.clip_observations;
     float *terms = sm + L.terms;
     float *so = sm + L.so, *sp = sm + L.sp;
+    // obs_now = frame + (randn * noise_scale_vec) * noise_level, then the +-clip of step() (hector_env.py:241-243,
+    // legged_robot.py:104-105); k is a compile-time column after unrolling
+    auto noisy_clip = [&](float v, int k) {
+        if (with_noise) v = v + (sm[L.z_obs + ln * OBS + k] * p.noise_scale_vec[k]) * p.noise_level;
+        return clampf(v, -clip, clip);
+    };
     int *flags = reinterpret_cast<int *>(sm + L.flags);
 
     // ---------------- stage the tile's input slabs into shared memory ----------------
@@ -252,42 +286,21 @@ post_physics_kernel(const __grid_constant__ hb_env_params p, const __grid_consta
     stage(b.commands + e0 * 4, L.commands, 4);
     if (with_noise) stage(nz.z_obs + e0 * OBS, L.z_obs, OBS);
 
-    // ---------------- per-warp global loads that overlap the staging ----------------
-    long long ep_len = 0;                       // warps 0 and 2
-    float sums[HB_NUM_REWARDS];                 // warp 3
-    float foot_pos[2][3], foot_vel[2][3], knee_xy[2][2], air[2], fh[2], lz[2];   // warp 2
-    bool last_ct[2];
-    float push_f[2], push_t[3];                 // warp 0
-    if (valid) {
-        if (warp == 0 || warp == 2) ep_len = b.episode_length_buf[env];
-        if (warp == 0) {
-            push_f[0] = b.rand_push_force[env * 3], push_f[1] = b.rand_push_force[env * 3 + 1];
-#pragma unroll
-            for (int k = 0; k < 3; ++k) push_t[k] = b.rand_push_torque[env * 3 + k];
-        } else if (warp == 2) {
-            const float *rs = b.rigid_state + (size_t)env * p.num_bodies * 13;
-#pragma unroll
-            for (int f = 0; f < 2; ++f) {
-                const float *r = rs + p.feet[f] * 13;
-#pragma unroll
-                for (int k = 0; k < 3; ++k) foot_pos[f][k] = __ldg(r + k), foot_vel[f][k] = __ldg(r + 7 + k);
-                const float *kr = rs + p.knees[f] * 13;
-                knee_xy[f][0] = __ldg(kr), knee_xy[f][1] = __ldg(kr + 1);
-                air[f] = b.feet_air_time[env * 2 + f];
-                fh[f] = b.feet_height[env * 2 + f];
-                lz[f] = b.last_feet_z[env * 2 + f];
-                last_ct[f] = b.last_contacts[env * 2 + f] != 0;
-            }
-        } else if (warp == 3) {
-#pragma unroll
-            for (int k = 0; k < HB_NUM_REWARDS; ++k) sums[k] = b.episode_sums[(size_t)k * N + env];
-        }
-    }
     __syncthreads();                             // mbarrier init / plain staging visible to every warp
-    if (bulk) hb::mbar_wait(&bar, 0);
+    // Each role first issues its own global loads (they overlap the bulk copies), then waits for the tile.
 
     // =========================================================================================
     if (warp == 0) {
+        long long ep_len = 0;
+        float push_f[2] = {0.f, 0.f}, push_t[3] = {0.f, 0.f, 0.f};
+        if (valid) {
+            ep_len = b.episode_length_buf[env];
+            push_f[0] = b.rand_push_force[env * 3], push_f[1] = b.rand_push_force[env * 3 + 1];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) push_t[k] = b.rand_push_torque[env * 3 + k];
+        }
+        if (bulk) hb::mbar_wait(&bar, 0);
+        HB_STAMP(1);
         float root[13], cmd[4];
 #pragma unroll
         for (int k = 0; k < 13; ++k) root[k] = sm[L.root + ln * 13 + k];
@@ -358,7 +371,9 @@ post_physics_kernel(const __grid_constant__ hb_env_params p, const __grid_consta
                 terms[HB_R_TRACKING_LIN_VEL * TILE + lane] = expf(-(ex * ex + ey * ey) * p.tracking_sigma);
             }
         }
+        HB_STAMP(2);
         tile_barrier();                                           // ---- barrier 1 ----
+        HB_STAMP(3);
         const bool reset = valid && (flags[lane] & 1);
         const float gs = reset ? 0.0f : sm[L.gait_s + lane], gc = reset ? 1.0f : sm[L.gait_c + lane];
         if (reset) {         // _reset_root_states + _resample_commands + the gravity/euler fix-up (:373-396,321-335,211-214)
@@ -410,15 +425,13 @@ post_physics_kernel(const __grid_constant__ hb_env_params p, const __grid_consta
             o[8] = eul.x * p.obs_quat, o[9] = eul.y * p.obs_quat, o[10] = eul.z * p.obs_quat;
 #pragma unroll
             for (int k = 0; k < 5; ++k) {
-                so[lane * OBS + k] = clampf(o[k], -clip, clip);        // noise scale of the command slots is 0
+                so[lane * OBS + k] = noisy_clip(o[k], k);
                 sp[lane * PRIV_PAD + k] = clampf(o[k], -clip, clip);
             }
 #pragma unroll
             for (int k = 0; k < 6; ++k) {
-                float v = o[5 + k];
-                sp[lane * PRIV_PAD + B0 + 3 + k] = clampf(v, -clip, clip);
-                if (with_noise) v = v + (sm[L.z_obs + ln * OBS + B0 + k] * p.noise_scale_vec[B0 + k]) * p.noise_level;
-                so[lane * OBS + B0 + k] = clampf(v, -clip, clip);
+                sp[lane * PRIV_PAD + B0 + 3 + k] = clampf(o[5 + k], -clip, clip);
+                so[lane * OBS + B0 + k] = noisy_clip(o[5 + k], B0 + k);
             }
             sp[lane * PRIV_PAD + B0] = clampf(lin.x * p.obs_lin_vel, -clip, clip);
             sp[lane * PRIV_PAD + B0 + 1] = clampf(lin.y * p.obs_lin_vel, -clip, clip);
@@ -432,42 +445,56 @@ post_physics_kernel(const __grid_constant__ hb_env_params p, const __grid_consta
         }
     } else if (warp == 1) {
         // ================================ joints ================================
-        float q[NDOF], qd[NDOF], act[NDOF], lact[NDOF], llact[NDOF], ldv[NDOF];
+        if (bulk) hb::mbar_wait(&bar, 0);
+        HB_STAMP(1);
+        // Only q, qd and the actions stay live across the barrier; the previous-step buffers are consumed
+        // (and, on a step, rolled forward: legged_robot.py:146-148) joint by joint before it.
+        float q[NDOF], qd[NDOF], act[NDOF];
 #pragma unroll
         for (int j = 0; j < NDOF; ++j) {
             q[j] = sm[L.dof + ln * NDOF * 2 + 2 * j];
             qd[j] = sm[L.dof + ln * NDOF * 2 + 2 * j + 1];
             act[j] = sm[L.actions + ln * NDOF + j];
-            lact[j] = sm[L.last_actions + ln * NDOF + j];
-            llact[j] = sm[L.last_last_actions + ln * NDOF + j];
-            ldv[j] = sm[L.last_dof_vel + ln * NDOF + j];
         }
         if (do_step) {
-            float t1 = 0.f, t2 = 0.f, t3 = 0.f, ss = 0.f, acc = 0.f, vel = 0.f, tq = 0.f, d[NDOF];
+            float t1 = 0.f, t2 = 0.f, t3 = 0.f, ss = 0.f, acc = 0.f, vel = 0.f, tq = 0.f;
+            float dy[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
             for (int j = 0; j < NDOF; ++j) {
-                const float d1 = lact[j] - act[j];                     // action_smoothness, hector_env.py:529-539
+                const float lact = sm[L.last_actions + ln * NDOF + j];
+                const float llact = sm[L.last_last_actions + ln * NDOF + j];
+                const float ldv = sm[L.last_dof_vel + ln * NDOF + j];
+                const float d1 = lact - act[j];                        // action_smoothness, hector_env.py:529-539
                 t1 += d1 * d1;
-                const float d2 = (act[j] + llact[j]) - 2.0f * lact[j];
+                const float d2 = (act[j] + llact) - 2.0f * lact;
                 t2 += d2 * d2;
                 t3 += fabsf(act[j]);
-                d[j] = q[j] - p.default_dof_pos[j];                    // default_joint_pos, :357-367
-                ss += d[j] * d[j];
-                const float a = (ldv[j] - qd[j]) / dt;                 // dof_acc :515-520
+                const float d = q[j] - p.default_dof_pos[j];           // default_joint_pos, :357-367
+                ss += d * d;
+                if (j == 0 || j == 1) dy[j] = d;
+                if (j == 5 || j == 6) dy[j - 3] = d;
+                const float a = (ldv - qd[j]) / dt;                    // dof_acc :515-520
                 acc += a * a;
                 vel += qd[j] * qd[j];                                  // dof_vel :508-513
                 const float tau = sm[L.torques + ln * NDOF + j];       // torques :501-506
                 tq += tau * tau;
+                if (valid) {                                           // legged_robot.py:146-148 (reset envs: zeroed below)
+                    b.last_last_actions[(size_t)env * NDOF + j] = lact;
+                    b.last_actions[(size_t)env * NDOF + j] = act[j];
+                    b.last_dof_vel[(size_t)env * NDOF + j] = qd[j];
+                }
             }
             terms[HB_R_ACTION_SMOOTHNESS * TILE + lane] = (t1 + t2) + 0.05f * t3;
-            float yr = sqrtf(d[0] * d[0] + d[1] * d[1]) + sqrtf(d[5] * d[5] + d[6] * d[6]);
+            float yr = sqrtf(dy[0] * dy[0] + dy[1] * dy[1]) + sqrtf(dy[2] * dy[2] + dy[3] * dy[3]);
             yr = clampf(yr - 0.1f, 0.0f, 50.0f);
             terms[HB_R_DEFAULT_JOINT_POS * TILE + lane] = expf(-yr * 100.0f) - 0.01f * sqrtf(ss);
             terms[HB_R_DOF_ACC * TILE + lane] = acc;
             terms[HB_R_DOF_VEL * TILE + lane] = vel;
             terms[HB_R_TORQUES * TILE + lane] = tq;
         }
+        HB_STAMP(2);
         tile_barrier();                                           // ---- barrier 1 ----
+        HB_STAMP(3);
         const bool reset = valid && (flags[lane] & 1);
         if (reset) {         // _reset_dofs (legged_robot.py:358-372) + buffer zeroing (:186-191)
             const float *u = nz.u_reset + (size_t)env * 15;
@@ -475,18 +502,13 @@ post_physics_kernel(const __grid_constant__ hb_env_params p, const __grid_consta
             for (int j = 0; j < NDOF; ++j) {
                 q[j] = p.default_dof_pos[j] + (p.reset_dof_span * u[j] + p.reset_dof_lo);
                 qd[j] = 0.0f;
+                act[j] = 0.0f;
                 b.dof_state[((size_t)env * NDOF + j) * 2] = q[j];
                 b.dof_state[((size_t)env * NDOF + j) * 2 + 1] = 0.0f;
-                act[j] = lact[j] = llact[j] = 0.0f;
                 b.actions[(size_t)env * NDOF + j] = 0.0f;
-            }
-        }
-        if (valid) {         // legged_robot.py:146-148
-#pragma unroll
-            for (int j = 0; j < NDOF; ++j) {
-                b.last_last_actions[(size_t)env * NDOF + j] = do_step ? lact[j] : llact[j];
-                b.last_actions[(size_t)env * NDOF + j] = do_step ? act[j] : lact[j];
-                b.last_dof_vel[(size_t)env * NDOF + j] = (do_step || reset) ? qd[j] : ldv[j];
+                b.last_actions[(size_t)env * NDOF + j] = 0.0f;
+                b.last_last_actions[(size_t)env * NDOF + j] = 0.0f;
+                b.last_dof_vel[(size_t)env * NDOF + j] = 0.0f;
             }
         }
         if (emit_obs) {
@@ -496,20 +518,37 @@ post_physics_kernel(const __grid_constant__ hb_env_params p, const __grid_consta
                 sp[lane * PRIV_PAD + 5 + j] = clampf(v0, -clip, clip);
                 sp[lane * PRIV_PAD + 5 + NDOF + j] = clampf(v1, -clip, clip);
                 sp[lane * PRIV_PAD + 5 + 2 * NDOF + j] = clampf(act[j], -clip, clip);
-                if (with_noise) {
-                    v0 = v0 + (sm[L.z_obs + ln * OBS + 5 + j] * p.noise_scale_vec[5 + j]) * p.noise_level;
-                    v1 = v1 + (sm[L.z_obs + ln * OBS + 5 + NDOF + j] * p.noise_scale_vec[5 + NDOF + j]) * p.noise_level;
-                }
-                float v2 = act[j];
-                if (with_noise)
-                    v2 = v2 + (sm[L.z_obs + ln * OBS + 5 + 2 * NDOF + j] * p.noise_scale_vec[5 + 2 * NDOF + j]) * p.noise_level;
-                so[lane * OBS + 5 + j] = clampf(v0, -clip, clip);
-                so[lane * OBS + 5 + NDOF + j] = clampf(v1, -clip, clip);
-                so[lane * OBS + 5 + 2 * NDOF + j] = clampf(v2, -clip, clip);
+                so[lane * OBS + 5 + j] = noisy_clip(v0, 5 + j);
+                so[lane * OBS + 5 + NDOF + j] = noisy_clip(v1, 5 + NDOF + j);
+                so[lane * OBS + 5 + 2 * NDOF + j] = noisy_clip(act[j], 5 + 2 * NDOF + j);
             }
         }
     } else if (warp == 2) {
         // ================================ feet / contacts / gait ================================
+        long long ep_len = 0;
+        float foot_pos[2][3], foot_vel[2][3], knee_xy[2][2], air[2], fh[2], lz[2];
+        bool last_ct[2];
+        float friction, mass;
+        {
+            const int ev = valid ? env : env0;         // invalid lanes of a ragged tile mirror the tile's first env
+            ep_len = b.episode_length_buf[ev];
+            friction = b.env_frictions[ev], mass = b.body_mass[ev];
+            const float *rs = b.rigid_state + (size_t)ev * p.num_bodies * 13;
+#pragma unroll
+            for (int f = 0; f < 2; ++f) {
+                const float *r = rs + p.feet[f] * 13;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) foot_pos[f][k] = __ldg(r + k), foot_vel[f][k] = __ldg(r + 7 + k);
+                const float *kr = rs + p.knees[f] * 13;
+                knee_xy[f][0] = __ldg(kr), knee_xy[f][1] = __ldg(kr + 1);
+                air[f] = b.feet_air_time[ev * 2 + f];
+                fh[f] = b.feet_height[ev * 2 + f];
+                lz[f] = b.last_feet_z[ev * 2 + f];
+                last_ct[f] = b.last_contacts[ev * 2 + f] != 0;
+            }
+        }
+        if (bulk) hb::mbar_wait(&bar, 0);
+        HB_STAMP(1);
         const float *cf = sm + L.contact + ln * crow;
         float foot_f[2][3];
 #pragma unroll
@@ -590,7 +629,9 @@ post_physics_kernel(const __grid_constant__ hb_env_params p, const __grid_consta
         reset = reset && valid;
         flags[lane] = (reset ? 1 : 0) | (time_out ? 2 : 0);
         sm[L.gait_s + lane] = gs, sm[L.gait_c + lane] = gc;
+        HB_STAMP(2);
         tile_barrier();                                           // ---- barrier 1 ----
+        HB_STAMP(3);
         if (reset) {
             ep_len = 0, air[0] = air[1] = 0.0f;
             st[0] = st[1] = 1.0f;                                   // phase 0: sin = 0 -> double support
@@ -618,14 +659,19 @@ post_physics_kernel(const __grid_constant__ hb_env_params p, const __grid_consta
                     sp[lane * PRIV_PAD + B0 + 9 + f * 3 + k] = clampf(foot_pos[f][k], -clip, clip);
                     sp[lane * PRIV_PAD + B0 + 15 + f * 3 + k] = clampf(foot_vel[f][k], -clip, clip);
                 }
-            sp[lane * PRIV_PAD + B0 + 29] = clampf(valid ? b.env_frictions[env] : 0.0f, -clip, clip);
-            sp[lane * PRIV_PAD + B0 + 30] = clampf((valid ? b.body_mass[env] : 0.0f) / 30.0f, -clip, clip);
+            sp[lane * PRIV_PAD + B0 + 29] = clampf(friction, -clip, clip);
+            sp[lane * PRIV_PAD + B0 + 30] = clampf(mass / 30.0f, -clip, clip);
             sp[lane * PRIV_PAD + B0 + 31] = st[0], sp[lane * PRIV_PAD + B0 + 32] = st[1];
             sp[lane * PRIV_PAD + B0 + 33] = ct[0] ? 1.0f : 0.0f, sp[lane * PRIV_PAD + B0 + 34] = ct[1] ? 1.0f : 0.0f;
         }
     } else {
         // ================================ ledger ================================
+        float sums[HB_NUM_REWARDS];
+#pragma unroll
+        for (int k = 0; k < HB_NUM_REWARDS; ++k) sums[k] = valid ? b.episode_sums[(size_t)k * N + env] : 0.0f;
+        HB_STAMP(2);
         tile_barrier();                                           // ---- barrier 1 ----
+        HB_STAMP(3);
         const bool reset = valid && (flags[lane] & 1);
         if (do_step) {       // compute_reward, legged_robot.py:216-234: alphabetical accumulation
             float rew = 0.0f;
@@ -649,213 +695,288 @@ post_physics_kernel(const __grid_constant__ hb_env_params p, const __grid_consta
             if (valid) b.episode_sums[(size_t)k * N + env] = sums[k];
         }
         __syncwarp();
-        // ---------------- ordered compaction of the reset ids + episode means ----------------
-        // Each tile publishes its ballot and the per-term sums of its reset envs; the last CTA to
-        // finish scans the ballots in tile order (ascending env ids, like reset_buf.nonzero()).
+        // ---------------- reset ids + episode means ----------------
+        // Each tile publishes its ballot; reset_finalize_kernel turns the ballots into the ascending id
+        // list (like reset_buf.nonzero()) and the count.  The per-term sums of the reset envs
+        // (legged_robot.py:198-201) go straight into 18 fp64 accumulators: fp64 addition of these
+        // fp32 values is order-independent far below fp32 resolution.
         if (ballot && lane < HB_NUM_REWARDS) {
             float v = 0.0f;
-#pragma unroll 1
+#pragma unroll 8
             for (int e = 0; e < TILE; ++e) v += terms[lane * TILE + ((e + lane) & 31)];
-            b.scratch_partials[(size_t)blockIdx.x * HB_NUM_REWARDS + lane] = v;
+            atomicAdd(b.scratch_sums + lane, (double)v);
         }
-        if (lane == 0) b.scratch_ballots[blockIdx.x] = ballot;
-        __threadfence();                          // publish ballot + partials before this CTA takes its ticket
+        if (lane == 0) b.scratch_ballots[blockIdx.x] = ballot;     // consumed by reset_finalize_kernel
     }
 
     // ---------------- coalesced store of the newest frames into the last slot of the stacked buffers ----------------
-    __syncthreads();                                              // ---- barrier 2 ----
-    if (threadIdx.x == 0) s_is_last = (atomicAdd(b.scratch_ticket, 1u) == gridDim.x - 1);
-    if (emit_obs) {
-        const int ostride = p.frame_stack * OBS, pstride = p.c_frame_stack * PRIV;
-        for (int i = threadIdx.x; i < nv * OBS; i += blockDim.x) {
-            const int r = i / OBS, c = i - r * OBS;
-            obs_new[(size_t)(env0 + r) * ostride + (ostride - OBS) + c] = so[i];
-        }
-        for (int i = threadIdx.x; i < nv * PRIV; i += blockDim.x) {
-            const int r = i / PRIV, c = i - r * PRIV;
-            priv_new[(size_t)(env0 + r) * pstride + (pstride - PRIV) + c] = sp[r * PRIV_PAD + c];
-        }
-    }
-    __syncthreads();
-    if (!s_is_last) return;
-
-    // ---------------- last CTA: ordered compaction of the reset ids + episode means ----------------
-    // Every tile has published its ballot and the per-term sums of its reset envs.  The whole CTA
-    // scans the ballots in tile order (ascending env ids, like reset_buf.nonzero()): thread t owns a
-    // contiguous run of tiles, so ids and the fp64 partial sums are combined in a fixed order.
-    __threadfence();
-    int *scan = reinterpret_cast<int *>(sm);                     // [128] tile-run counts (tile memory is free now)
-    double *red = reinterpret_cast<double *>(sm + 256);          // [HB_NUM_REWARDS][128]
-    const int tiles = gridDim.x;
-    const int per = (tiles + blockDim.x - 1) / blockDim.x;
-    const int t_lo = min((int)threadIdx.x * per, tiles), t_hi = min(t_lo + per, tiles);
-    int cnt = 0;
-    for (int t = t_lo; t < t_hi; ++t) cnt += __popc(__ldcg(b.scratch_ballots + t));
-    scan[threadIdx.x] = cnt;
-    __syncthreads();
-    int off = 0, total = 0;
-    for (int i = 0; i < (int)blockDim.x; ++i) {
-        const int c = scan[i];
-        off += (i < (int)threadIdx.x) ? c : 0;
-        total += c;
-    }
-    double acc[HB_NUM_REWARDS];
-#pragma unroll
-    for (int k = 0; k < HB_NUM_REWARDS; ++k) acc[k] = 0.0;
-    for (int t = t_lo; t < t_hi; ++t) {
-        unsigned m = __ldcg(b.scratch_ballots + t);
-        if (!m) continue;
-#pragma unroll
-        for (int k = 0; k < HB_NUM_REWARDS; ++k) acc[k] += (double)__ldcg(b.scratch_partials + (size_t)t * HB_NUM_REWARDS + k);
-        while (m) {
-            const int bit = __ffs(m) - 1;
-            m &= m - 1;
-            b.reset_env_ids[off++] = t * TILE + bit;
+    // by the three roles that wrote them (named barrier 2, 96 threads); the ledger warp is busy with its ticket
+    HB_STAMP(4);
+    if (warp < 3) {
+        asm volatile("bar.sync 2, 96;" ::: "memory");             // ---- barrier 2 ----
+        HB_STAMP(5);
+        if (emit_obs) {
+            // 96 threads walk the tile's frames with (row, column) advanced incrementally: no per-element division.
+            // Privileged frames leave as 8-byte pairs (row starts are 8-byte aligned: 4200 r + 3920 bytes).
+            constexpr int NT = 3 * TILE, P2 = PRIV / 2;
+            const int ostride = p.frame_stack * OBS, pstride = p.c_frame_stack * PRIV;
+            const int t = threadIdx.x;
+            if ((pstride & 1) == 0 && (reinterpret_cast<uintptr_t>(priv_new) & 7u) == 0) {
+                int r = t / P2, c2 = t - r * P2;
+                float2 *dst = reinterpret_cast<float2 *>(priv_new + (size_t)env0 * pstride + (pstride - PRIV));
+                const float2 *src = reinterpret_cast<const float2 *>(sp);
+                const int half = pstride / 2;
+                while (r < nv) {
+                    dst[(size_t)r * half + c2] = src[r * P2 + c2];
+                    r += NT / P2, c2 += NT % P2;
+                    if (c2 >= P2) c2 -= P2, r += 1;
+                }
+            } else {
+                int r = t / PRIV, c = t - r * PRIV;
+                while (r < nv) {
+                    priv_new[(size_t)(env0 + r) * pstride + (pstride - PRIV) + c] = sp[r * PRIV + c];
+                    r += NT / PRIV, c += NT % PRIV;
+                    if (c >= PRIV) c -= PRIV, r += 1;
+                }
+            }
+            int r = t / OBS, c = t - r * OBS;
+            float *dst = obs_new + (size_t)env0 * ostride + (ostride - OBS);
+            while (r < nv) {
+                dst[(size_t)r * ostride + c] = so[r * OBS + c];
+                r += NT / OBS, c += NT % OBS;
+                if (c >= OBS) c -= OBS, r += 1;
+            }
         }
     }
-#pragma unroll
-    for (int k = 0; k < HB_NUM_REWARDS; ++k) red[k * blockDim.x + threadIdx.x] = acc[k];
-    __syncthreads();
-    // extras["episode"] is only refreshed on steps with >= 1 reset (quirk 4): otherwise the previous
-    // values are carried into this step's slot.
-    if (threadIdx.x < HB_NUM_REWARDS) {
-        const int k = threadIdx.x;
-        if (total > 0) {
-            double v = 0.0;
-            for (int i = 0; i < (int)blockDim.x; ++i) v += red[k * blockDim.x + i];
-            b.episode_means[k] = (float)(v / (double)total) / p.max_episode_length_s;
-        } else if (b.episode_means_prev && b.episode_means_prev != b.episode_means) {
-            b.episode_means[k] = b.episode_means_prev[k];
-        }
-    }
-    if (threadIdx.x == 0) {
-        *b.reset_count = total;
-        if (host_count) *host_count = total;
-        *b.scratch_ticket = 0u;          // re-arm for the next launch
-    }
+    HB_STAMP(6);
+    HB_GT(1);
 }
 
 // ------------------------------------------------------------------------------------------
-// a8 (stacking): new[:, 0:(S-1)*F] = reset ? 0 : prev[:, F:S*F]  — a flat copy shifted by one
-// frame with a hole of F floats per row (the newest frame, written by post_physics_kernel).
+// a8 (stacking): new[:, 0:(S-1)*F] = prev[:, F:S*F]  — a flat copy shifted by one frame with a
+// hole of F floats per row (the newest frame, written by post_physics_kernel).  The shift does
+// not depend on this step's physics, so it runs on a forked stream while the PD sub-steps, the
+// physics and post_physics_kernel run; the (rare) reset envs get their carried frames zeroed
+// afterwards by reset_fixup_kernel (reset_idx, hector_env.py:256-261).
 // Destination vectors are 16-byte aligned; the source is 4*F bytes further on, which is only
 // 4-byte aligned for F = 41, so each thread loads the aligned vector below its source window
-// and takes the missing float from its neighbour lane (shuffle); F % 4 picks the rotation.
+// and takes the missing floats from its neighbour lane (shuffle); F % 4 picks the rotation.
+// ROW and FRAME are compile-time constants for the hector layout: the per-vector row/column
+// split is a multiply-shift, indices are 32-bit.
 // ------------------------------------------------------------------------------------------
-template <int UNROLL>
+__device__ __forceinline__ float4 ld_vec_guarded(const float *__restrict__ prev, uint32_t s, uint32_t total) {
+    const uint32_t e = s * 4u;                         // ragged last vector of the buffer (N*row % 4 != 0)
+    float4 v;
+    v.x = (e < total) ? __ldg(prev + e) : 0.0f;
+    v.y = (e + 1 < total) ? __ldg(prev + e + 1) : 0.0f;
+    v.z = (e + 2 < total) ? __ldg(prev + e + 2) : 0.0f;
+    v.w = (e + 3 < total) ? __ldg(prev + e + 3) : 0.0f;
+    return v;
+}
+
+template <int ROW, int FRAME, int UNROLL>
 __device__ __forceinline__ void
-stack_shift_body(const float *__restrict__ prev, float *__restrict__ next, const uint8_t *__restrict__ reset_buf,
-                 long long total, int row, int frame, const uint8_t *__restrict__ latch_src,
-                 uint8_t *__restrict__ latch_dst, const int32_t *__restrict__ reset_count, int num_envs,
-                 const unsigned blk, const unsigned nblk) {
-    const int lane = threadIdx.x & 31;
-    const int keep = row - frame;                       // floats of a row that are carried over
-    const int rot = frame & 3;                          // source misalignment in floats
-    const int fvec = frame >> 2;                        // whole vectors of shift
-    const long long warp_base = ((long long)blk * blockDim.x + threadIdx.x - lane) * UNROLL;
-    // extras["time_outs"] latch (legged_robot.py:208-209 only runs when >= 1 env was reset)
-    if (latch_dst && *reset_count > 0) {
-        for (long long i = (long long)blk * blockDim.x + threadIdx.x; i < num_envs; i += (long long)nblk * blockDim.x)
-            latch_dst[i] = latch_src[i];
-    }
+stack_shift_fixed(const float *__restrict__ prev, float *__restrict__ next, const uint32_t total, const uint32_t blk) {
+    constexpr uint32_t KEEP = ROW - FRAME;              // floats of a row that are carried over
+    constexpr int ROT = FRAME & 3;                      // source misalignment in floats
+    constexpr uint32_t FVEC = FRAME >> 2;               // whole vectors of shift
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t total_vec = total >> 2;              // whole vectors
+    const uint32_t tail_vec = (total + 3u) >> 2;
+    const uint32_t warp_base = (blk * blockDim.x + (threadIdx.x - lane)) * UNROLL;
     const float4 *p4 = reinterpret_cast<const float4 *>(prev);
     float4 *n4 = reinterpret_cast<float4 *>(next);
-    const long long total_vec = total >> 2;             // whole vectors; a ragged tail (N*row % 4) goes scalar
-    const long long tail_vec = (total + 3) >> 2;
-    float4 v[UNROLL];
-    float nx31[UNROLL][3];
+    float4 v[UNROLL], w[UNROLL];
     // all loads first (UNROLL independent 16-byte requests in flight per thread)
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u) {
-        const long long i = warp_base + (long long)u * 32 + lane;      // destination vector index
-        const long long s = i + fvec;                                   // aligned source vector below the window
-        if (s < total_vec) {
-            v[u] = hb::ld_stream4(p4 + s);
-        } else {                                                        // ragged last vector of the buffer
-            const long long e = s * 4;
-            v[u].x = (e < total) ? __ldg(prev + e) : 0.0f;
-            v[u].y = (e + 1 < total) ? __ldg(prev + e + 1) : 0.0f;
-            v[u].z = (e + 2 < total) ? __ldg(prev + e + 2) : 0.0f;
-            v[u].w = 0.0f;
-        }
-        nx31[u][0] = nx31[u][1] = nx31[u][2] = 0.0f;
-        if (lane == 31 && rot != 0) {                                   // no neighbour lane: fetch the spill-over
-            const long long e = (s + 1) * 4;
-            if (e < total) nx31[u][0] = __ldg(prev + e);
-            if (rot > 1 && e + 1 < total) nx31[u][1] = __ldg(prev + e + 1);
-            if (rot > 2 && e + 2 < total) nx31[u][2] = __ldg(prev + e + 2);
-        }
+        const uint32_t s = warp_base + u * 32u + lane + FVEC;          // aligned source vector below the window
+        v[u] = (s < total_vec) ? hb::ld_stream4(p4 + s) : ld_vec_guarded(prev, s, total);
+        if (ROT != 0 && lane == 31u)                                    // no neighbour lane: fetch the spill-over
+            w[u] = (s + 1u < total_vec) ? hb::ld_stream4(p4 + s + 1u) : ld_vec_guarded(prev, s + 1u, total);
     }
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u) {
-        const long long i = warp_base + (long long)u * 32 + lane;
-        float nx0 = __shfl_down_sync(0xffffffffu, v[u].x, 1);           // first floats of vector s+1
-        float nx1 = __shfl_down_sync(0xffffffffu, v[u].y, 1);
-        float nx2 = __shfl_down_sync(0xffffffffu, v[u].z, 1);
-        if (lane == 31) nx0 = nx31[u][0], nx1 = nx31[u][1], nx2 = nx31[u][2];
+        const uint32_t i = warp_base + u * 32u + lane;                  // destination vector index
+        float4 o = v[u];
+        if (ROT != 0) {
+            float nx0 = __shfl_down_sync(0xffffffffu, v[u].x, 1);       // first floats of vector s+1
+            float nx1 = ROT > 1 ? __shfl_down_sync(0xffffffffu, v[u].y, 1) : 0.0f;
+            float nx2 = ROT > 2 ? __shfl_down_sync(0xffffffffu, v[u].z, 1) : 0.0f;
+            if (lane == 31u) nx0 = w[u].x, nx1 = w[u].y, nx2 = w[u].z;
+            if (ROT == 1) o = make_float4(v[u].y, v[u].z, v[u].w, nx0);
+            else if (ROT == 2) o = make_float4(v[u].z, v[u].w, nx0, nx1);
+            else o = make_float4(v[u].w, nx0, nx1, nx2);
+        }
         if (i >= tail_vec) continue;
-        float4 o;
-        if (rot == 0) o = v[u];
-        else if (rot == 1) o = make_float4(v[u].y, v[u].z, v[u].w, nx0);
-        else if (rot == 2) o = make_float4(v[u].z, v[u].w, nx0, nx1);
-        else o = make_float4(v[u].w, nx0, nx1, nx2);
-        const long long e0 = i * 4;                      // first destination float
-        const int r0 = (int)(e0 / row);
-        const int c0 = (int)(e0 - (long long)r0 * row);
-        if (c0 + 3 < keep && i < total_vec) {            // whole vector inside the carried part of one row
-            if (reset_buf[r0]) o = make_float4(0.f, 0.f, 0.f, 0.f);
+        const uint32_t e0 = i * 4u;                      // first destination float
+        const uint32_t r0 = e0 / (uint32_t)ROW;
+        const uint32_t c0 = e0 - r0 * (uint32_t)ROW;
+        if (c0 + 3u < KEEP && i < total_vec) {           // whole vector inside the carried part of one row
             hb::st_stream4(n4 + i, o);
         } else {                                         // touches the newest-frame hole or a row boundary
             const float ov[4] = {o.x, o.y, o.z, o.w};
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                int r = r0, c = c0 + k;
-                if (c >= row) c -= row, r += 1;
-                if (c < keep && e0 + k < total) next[e0 + k] = reset_buf[r] ? 0.0f : ov[k];
+            for (uint32_t k = 0; k < 4u; ++k) {
+                uint32_t c = c0 + k;
+                if (c >= (uint32_t)ROW) c -= (uint32_t)ROW;
+                if (c < KEEP && e0 + k < total) next[e0 + k] = ov[k];
             }
         }
     }
 }
 
-template <int UNROLL>
-__global__ void __launch_bounds__(256)
-stack_shift_kernel(const float *__restrict__ prev, float *__restrict__ next, const uint8_t *__restrict__ reset_buf,
-                   long long total, int row, int frame, const uint8_t *__restrict__ latch_src,
-                   uint8_t *__restrict__ latch_dst, const int32_t *__restrict__ reset_count, int num_envs) {
-    stack_shift_body<UNROLL>(prev, next, reset_buf, total, row, frame, latch_src, latch_dst, reset_count, num_envs,
-                             blockIdx.x, gridDim.x);
-}
-
 // actor and critic histories in one launch: blocks [0, blocks_a) shift buffer a, the rest buffer b
-template <int UNROLL>
+template <int ROW_A, int FRAME_A, int ROW_B, int FRAME_B, int UNROLL>
 __global__ void __launch_bounds__(256)
-stack_shift_pair_kernel(const float *__restrict__ prev_a, float *__restrict__ next_a, long long total_a, int row_a,
-                        int frame_a, unsigned blocks_a, const float *__restrict__ prev_b, float *__restrict__ next_b,
-                        long long total_b, int row_b, int frame_b, const uint8_t *__restrict__ reset_buf,
-                        const uint8_t *__restrict__ latch_src, uint8_t *__restrict__ latch_dst,
-                        const int32_t *__restrict__ reset_count, int num_envs) {
+stack_shift_pair_kernel(const float *__restrict__ prev_a, float *__restrict__ next_a, uint32_t total_a, uint32_t blocks_a,
+                        const float *__restrict__ prev_b, float *__restrict__ next_b, uint32_t total_b) {
     if (blockIdx.x < blocks_a)
-        stack_shift_body<UNROLL>(prev_a, next_a, reset_buf, total_a, row_a, frame_a, latch_src, latch_dst, reset_count,
-                                 num_envs, blockIdx.x, blocks_a);
+        stack_shift_fixed<ROW_A, FRAME_A, UNROLL>(prev_a, next_a, total_a, blockIdx.x);
     else
-        stack_shift_body<UNROLL>(prev_b, next_b, reset_buf, total_b, row_b, frame_b, nullptr, nullptr, nullptr, num_envs,
-                                 blockIdx.x - blocks_a, gridDim.x - blocks_a);
+        stack_shift_fixed<ROW_B, FRAME_B, UNROLL>(prev_b, next_b, total_b, blockIdx.x - blocks_a);
 }
 
-// generic fallback (rows not a multiple of 4 floats in total, or unaligned buffers)
+template <int ROW, int FRAME, int UNROLL>
+__global__ void __launch_bounds__(256)
+stack_shift_fixed_kernel(const float *__restrict__ prev, float *__restrict__ next, uint32_t total) {
+    stack_shift_fixed<ROW, FRAME, UNROLL>(prev, next, total, blockIdx.x);
+}
+
+// generic shapes / unaligned buffers / optional per-env zeroing (reset_buf may be null)
 __global__ void __launch_bounds__(256)
 stack_shift_scalar_kernel(const float *__restrict__ prev, float *__restrict__ next,
-                          const uint8_t *__restrict__ reset_buf, long long total, int row, int frame,
-                          const uint8_t *__restrict__ latch_src, uint8_t *__restrict__ latch_dst,
-                          const int32_t *__restrict__ reset_count, int num_envs) {
+                          const uint8_t *__restrict__ reset_buf, long long total, int row, int frame) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (latch_dst && *reset_count > 0 && i < num_envs) latch_dst[i] = latch_src[i];
     if (i >= total) return;
     const int r = (int)(i / row), c = (int)(i - (long long)r * row);
-    if (c < row - frame) next[i] = reset_buf[r] ? 0.0f : prev[i + frame];
+    if (c < row - frame) next[i] = (reset_buf && reset_buf[r]) ? 0.0f : prev[i + frame];
+}
+
+// What reset_idx needs from the whole shard, after post_physics_kernel published one ballot per 32-env
+// tile and the shift wrote the carried frames:
+//   * env_ids = reset_buf.nonzero() (legged_robot.py:142): ascending ids + count (device and pinned host copy);
+//   * extras["episode"] means (:198-201) from the fp64 accumulators, only refreshed when >= 1 env was reset
+//     (quirk 4; otherwise the previous step's values are carried into this step's slot);
+//   * extras["time_outs"] (:208-209), also only then;
+//   * obs_history / critic_history zeroing of the reset envs (hector_env.py:256-261).
+// Every CTA owns a contiguous segment of tiles; it sums the popcounts before its segment (8 KB of ballots at
+// 65536 envs: cheaper to recount per CTA than to chain CTAs), scans its own, writes its ids in order and zeroes
+// the carried frames of its reset envs, one warp per (env, buffer).
+constexpr int FIN_THREADS = 256;
+
+__device__ __forceinline__ int block_sum(int v, int *scratch) {        // all threads get the total
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if (lane == 0) scratch[warp] = v;
+    __syncthreads();
+    int t = 0;
+#pragma unroll
+    for (int w = 0; w < FIN_THREADS / 32; ++w) t += scratch[w];
+    return t;
+}
+
+__global__ void __launch_bounds__(FIN_THREADS)
+reset_finalize_kernel(const __grid_constant__ hb_env_params p, const __grid_constant__ hb_env_buffers b,
+                      float *__restrict__ obs_new, float *__restrict__ priv_new, int tiles, int seg,
+                      int32_t *host_count) {
+    __shared__ int scratch[FIN_THREADS / 32];
+    __shared__ int wbase[FIN_THREADS / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int t_lo = blockIdx.x * seg, t_hi = min(t_lo + seg, tiles);
+    int before = 0, rest = 0;
+#pragma unroll 4
+    for (int t = threadIdx.x; t < tiles; t += FIN_THREADS) {
+        const int c = (t < t_lo || t >= t_hi) ? __popc(__ldg(b.scratch_ballots + t)) : 0;
+        before += (t < t_lo) ? c : 0;
+        rest += (t >= t_hi) ? c : 0;
+    }
+    const int prefix = block_sum(before, scratch);
+    const int after = block_sum(rest, scratch);
+    // this CTA's tiles: consecutive threads own consecutive tiles (segments longer than the CTA go in rounds)
+    int seg_count = 0;
+    for (int t0 = t_lo; t0 < t_hi; t0 += FIN_THREADS) {
+        const int t = t0 + threadIdx.x;
+        unsigned m = (t < t_hi) ? __ldg(b.scratch_ballots + t) : 0u;
+        const int cnt = __popc(m);
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int up = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += up;
+        }
+        __syncthreads();
+        if (lane == 31) wbase[warp] = incl;
+        __syncthreads();
+        int off = prefix + seg_count + incl - cnt, round_total = 0;
+#pragma unroll
+        for (int w = 0; w < FIN_THREADS / 32; ++w) {
+            off += (w < warp) ? wbase[w] : 0;
+            round_total += wbase[w];
+        }
+        while (m) {
+            const int bit = __ffs(m) - 1;
+            m &= m - 1;
+            b.reset_env_ids[off++] = t * TILE + bit;
+        }
+        seg_count += round_total;
+    }
+    const int total = prefix + seg_count + after;
+    if (blockIdx.x == 0) {
+        if (threadIdx.x == 0) {
+            *b.reset_count = total;
+            if (host_count) *host_count = total;
+        }
+        if (threadIdx.x < HB_NUM_REWARDS) {
+            const int k = threadIdx.x;
+            if (total > 0) {
+                b.episode_means[k] = (float)(b.scratch_sums[k] / (double)total) / p.max_episode_length_s;
+                b.scratch_sums[k] = 0.0;             // re-armed for the next step
+            } else if (b.episode_means_prev && b.episode_means_prev != b.episode_means) {
+                b.episode_means[k] = b.episode_means_prev[k];
+            }
+        }
+    }
+    if (total == 0) return;
+    if (b.time_outs_latched) {
+        for (int i = blockIdx.x * FIN_THREADS + threadIdx.x; i < p.num_envs; i += gridDim.x * FIN_THREADS)
+            b.time_outs_latched[i] = b.time_out_buf[i];
+    }
+    if (!obs_new || seg_count == 0) return;
+    __syncthreads();                                 // this CTA's ids are visible to all of its warps
+    const int row_a = p.frame_stack * p.num_single_obs, row_b = p.c_frame_stack * p.num_single_priv;
+    const int keep_a = row_a - p.num_single_obs, keep_b = row_b - p.num_single_priv;
+    for (int j = warp; j < 2 * seg_count; j += FIN_THREADS / 32) {
+        const int env = b.reset_env_ids[prefix + (j >> 1)];
+        float *dst = (j & 1) ? priv_new + (size_t)env * row_b : obs_new + (size_t)env * row_a;
+        const int keep = (j & 1) ? keep_b : keep_a;
+        for (int c = lane; c < keep; c += 32) dst[c] = 0.0f;
+    }
 }
 
 int g_use_bulk = 1;
+int g_stack_unroll = 4;
+
+// hector frame stacks (hector_config.py:8-20): obs 15 x 41, privileged obs 15 x 70
+constexpr int ROW_OBS = 15 * OBS, ROW_PRIV = 15 * PRIV;
+
+template <int ROW, int FRAME>
+void launch_stack_fixed(const float *prev, float *next, int n, cudaStream_t st) {
+    const uint32_t total = (uint32_t)n * ROW;
+    const uint32_t vecs = (total + 3u) / 4u;
+    if (g_stack_unroll == 8) {
+        const uint32_t blocks = (vecs + 8 * 256 - 1) / (8 * 256);
+        stack_shift_fixed_kernel<ROW, FRAME, 8><<<blocks, 256, 0, st>>>(prev, next, total);
+    } else {
+        const uint32_t blocks = (vecs + 4 * 256 - 1) / (4 * 256);
+        stack_shift_fixed_kernel<ROW, FRAME, 4><<<blocks, 256, 0, st>>>(prev, next, total);
+    }
+}
+
+bool fits_u32(int n, int row) { return (long long)n * row + 64 * 1024 < (1ll << 32); }
+
 
 }  // namespace
 
@@ -864,9 +985,25 @@ int g_use_bulk = 1;
 // ==============================================================================================
 extern "C" {
 
+#ifdef HB_POST_TIMING
+int hb_debug_post_stamps(long long *dst_host, int count) {
+    HB_CUDA(cudaMemcpyFromSymbol(dst_host, g_post_stamps, sizeof(long long) * count));
+    return HB_OK;
+}
+int hb_debug_post_globaltimes(unsigned long long *dst_host, int count) {
+    HB_CUDA(cudaMemcpyFromSymbol(dst_host, g_post_gt, sizeof(unsigned long long) * count));
+    return HB_OK;
+}
+#endif
+
 int hb_set_option(const char *name, int value) {
     if (name && !strcmp(name, "env_bulk_staging")) {
         g_use_bulk = value;
+        return HB_OK;
+    }
+    if (name && !strcmp(name, "stack_unroll")) {
+        HB_REQUIRE(value == 4 || value == 8, "hb_set_option: stack_unroll must be 4 or 8");
+        g_stack_unroll = value;
         return HB_OK;
     }
     hb::set_error("hb_set_option: unknown option '%s'", name ? name : "(null)");
@@ -920,7 +1057,7 @@ int hb_env_compute_torques(const hb_env_params *p, const hb_env_buffers *buf, vo
 }
 
 int hb_env_post_physics(const hb_env_params *p, const hb_env_buffers *buf, const hb_env_noise *noise,
-                        float *obs_new, float *priv_new, int32_t stages, int32_t *host_count, void *stream) {
+                        float *obs_new, float *priv_new, int32_t stages, void *stream) {
     if (int rc = check_params(p, buf, "hb_env_post_physics")) return rc;
     HB_REQUIRE(noise && obs_new && priv_new, "hb_env_post_physics: null noise/obs pointers");
     HB_REQUIRE(p->num_single_obs == OBS && p->num_single_priv == PRIV,
@@ -930,8 +1067,7 @@ int hb_env_post_physics(const hb_env_params *p, const hb_env_buffers *buf, const
     HB_REQUIRE(p->n_term >= 0 && p->n_term <= HB_MAX_CONTACT_BODIES && p->n_pen >= 0 &&
                    p->n_pen <= HB_MAX_CONTACT_BODIES, "hb_env_post_physics: too many contact bodies");
     HB_REQUIRE(noise->u_reset, "hb_env_post_physics: u_reset is required (any env may reset)");
-    HB_REQUIRE(buf->scratch_ballots && buf->scratch_partials && buf->scratch_ticket && buf->reset_env_ids &&
-                   buf->reset_count && buf->episode_means, "hb_env_post_physics: null scratch/result buffers");
+    HB_REQUIRE(buf->scratch_ballots && buf->scratch_sums, "hb_env_post_physics: null scratch buffers");
     const bool with_noise = p->add_noise && noise->z_obs;
     const TileLayout L = make_layout(p->num_bodies, with_noise);
     const size_t smem = (size_t)L.total * sizeof(float);
@@ -940,10 +1076,11 @@ int hb_env_post_physics(const hb_env_params *p, const hb_env_buffers *buf, const
     bool bulk = g_use_bulk != 0;
     const void *slabs[] = {buf->root_states, buf->dof_state, buf->contact_forces, buf->actions, buf->last_actions,
                            buf->last_last_actions, buf->last_dof_vel, buf->torques, buf->last_root_vel,
-                           buf->commands, with_noise ? noise->z_obs : buf->commands};
+                           buf->commands};
     bool all_aligned = true;
     for (const void *s : slabs) all_aligned = all_aligned && hb::aligned16(s);
     HB_REQUIRE(all_aligned, "hb_env_post_physics: state tensors must be 16-byte aligned");
+    if (with_noise && !hb::aligned16(noise->z_obs)) bulk = false;      // caller-supplied draws at an odd offset: plain loads
     static bool attr_set[2] = {false, false};
     if (bulk) {
         if (!attr_set[1]) {
@@ -951,41 +1088,33 @@ int hb_env_post_physics(const hb_env_params *p, const hb_env_buffers *buf, const
             attr_set[1] = true;
         }
         post_physics_kernel<true><<<tiles, 4 * TILE, smem, (cudaStream_t)stream>>>(*p, *buf, *noise, obs_new, priv_new,
-                                                                               stages, host_count);
+                                                                               stages);
     } else {
         if (!attr_set[0]) {
             HB_CUDA(cudaFuncSetAttribute(post_physics_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
             attr_set[0] = true;
         }
         post_physics_kernel<false><<<tiles, 4 * TILE, smem, (cudaStream_t)stream>>>(*p, *buf, *noise, obs_new, priv_new,
-                                                                                stages, host_count);
+                                                                                stages);
     }
     HB_CHECK_LAUNCH("post_physics_kernel");
     return HB_OK;
 }
 
-static int launch_stack(const float *prev, float *next, const uint8_t *reset_buf, int n, int row, int frame,
-                        const uint8_t *latch_src, uint8_t *latch_dst, const int32_t *reset_count, cudaStream_t st) {
-    const long long total = (long long)n * row;
-    if (hb::aligned16(prev) && hb::aligned16(next)) {
-        constexpr int UNROLL = 4;
-        const long long vecs = (total + 3) / 4;
-        const long long threads = (vecs + UNROLL - 1) / UNROLL;
-        const int blocks = (int)((threads + 255) / 256);
-        stack_shift_kernel<UNROLL><<<blocks, 256, 0, st>>>(prev, next, reset_buf, total, row, frame, latch_src,
-                                                            latch_dst, reset_count, n);
-    } else {
-        stack_shift_scalar_kernel<<<(int)((total + 255) / 256), 256, 0, st>>>(prev, next, reset_buf, total, row, frame,
-                                                                               latch_src, latch_dst, reset_count, n);
-    }
-    return 0;
-}
-
 int hb_stack_shift(const float *prev, float *next, const uint8_t *reset_buf, int32_t num_envs, int32_t row,
                    int32_t frame, void *stream) {
-    HB_REQUIRE(prev && next && reset_buf && prev != next, "hb_stack_shift: null or aliasing buffers");
+    HB_REQUIRE(prev && next && prev != next, "hb_stack_shift: null or aliasing buffers");
     HB_REQUIRE(num_envs > 0 && frame > 0 && row > frame, "hb_stack_shift: bad shape");
-    launch_stack(prev, next, reset_buf, num_envs, row, frame, nullptr, nullptr, nullptr, (cudaStream_t)stream);
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool fast = !reset_buf && hb::aligned16(prev) && hb::aligned16(next) && fits_u32(num_envs, row);
+    if (fast && row == ROW_OBS && frame == OBS) {
+        launch_stack_fixed<ROW_OBS, OBS>(prev, next, num_envs, st);
+    } else if (fast && row == ROW_PRIV && frame == PRIV) {
+        launch_stack_fixed<ROW_PRIV, PRIV>(prev, next, num_envs, st);
+    } else {
+        const long long total = (long long)num_envs * row;
+        stack_shift_scalar_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(prev, next, reset_buf, total, row, frame);
+    }
     HB_CHECK_LAUNCH("stack_shift_kernel");
     return HB_OK;
 }
@@ -993,28 +1122,46 @@ int hb_stack_shift(const float *prev, float *next, const uint8_t *reset_buf, int
 int hb_env_stack_observations(const hb_env_params *p, const hb_env_buffers *buf, const float *obs_prev,
                               const float *priv_prev, float *obs_new, float *priv_new, void *stream) {
     if (int rc = check_params(p, buf, "hb_env_stack_observations")) return rc;
-    HB_REQUIRE(obs_prev && priv_prev && obs_new && priv_new && buf->reset_buf, "hb_env_stack_observations: null buffer");
+    HB_REQUIRE(obs_prev && priv_prev && obs_new && priv_new, "hb_env_stack_observations: null buffer");
     HB_REQUIRE(obs_prev != obs_new && priv_prev != priv_new, "hb_env_stack_observations: prev and new must not alias");
     cudaStream_t st = (cudaStream_t)stream;
-    if (hb::aligned16(obs_prev) && hb::aligned16(obs_new) && hb::aligned16(priv_prev) && hb::aligned16(priv_new)) {
-        constexpr int UNROLL = 4;
-        const int row_a = p->frame_stack * p->num_single_obs, row_b = p->c_frame_stack * p->num_single_priv;
-        const long long total_a = (long long)p->num_envs * row_a, total_b = (long long)p->num_envs * row_b;
-        const unsigned blocks_a = (unsigned)(((total_a + 3) / 4 + UNROLL * 256 - 1) / (UNROLL * 256));
-        const unsigned blocks_b = (unsigned)(((total_b + 3) / 4 + UNROLL * 256 - 1) / (UNROLL * 256));
-        stack_shift_pair_kernel<UNROLL><<<blocks_a + blocks_b, 256, 0, st>>>(
-            obs_prev, obs_new, total_a, row_a, p->num_single_obs, blocks_a, priv_prev, priv_new, total_b, row_b,
-            p->num_single_priv, buf->reset_buf, buf->time_out_buf, buf->time_outs_latched, buf->reset_count,
-            p->num_envs);
+    const int row_a = p->frame_stack * p->num_single_obs, row_b = p->c_frame_stack * p->num_single_priv;
+    const bool fast = hb::aligned16(obs_prev) && hb::aligned16(obs_new) && hb::aligned16(priv_prev) &&
+                      hb::aligned16(priv_new) && row_a == ROW_OBS && p->num_single_obs == OBS && row_b == ROW_PRIV &&
+                      p->num_single_priv == PRIV && fits_u32(p->num_envs, row_b);
+    if (fast) {
+        const uint32_t total_a = (uint32_t)p->num_envs * ROW_OBS, total_b = (uint32_t)p->num_envs * ROW_PRIV;
+        if (g_stack_unroll == 8) {
+            constexpr uint32_t PER = 8 * 256;
+            const uint32_t blocks_a = ((total_a + 3u) / 4u + PER - 1) / PER, blocks_b = ((total_b + 3u) / 4u + PER - 1) / PER;
+            stack_shift_pair_kernel<ROW_OBS, OBS, ROW_PRIV, PRIV, 8><<<blocks_a + blocks_b, 256, 0, st>>>(
+                obs_prev, obs_new, total_a, blocks_a, priv_prev, priv_new, total_b);
+        } else {
+            constexpr uint32_t PER = 4 * 256;
+            const uint32_t blocks_a = ((total_a + 3u) / 4u + PER - 1) / PER, blocks_b = ((total_b + 3u) / 4u + PER - 1) / PER;
+            stack_shift_pair_kernel<ROW_OBS, OBS, ROW_PRIV, PRIV, 4><<<blocks_a + blocks_b, 256, 0, st>>>(
+                obs_prev, obs_new, total_a, blocks_a, priv_prev, priv_new, total_b);
+        }
         HB_CHECK_LAUNCH("stack_shift_pair_kernel");
         return HB_OK;
     }
-    launch_stack(obs_prev, obs_new, buf->reset_buf, p->num_envs, p->frame_stack * p->num_single_obs, p->num_single_obs,
-                 buf->time_out_buf, buf->time_outs_latched, buf->reset_count, st);
-    HB_CHECK_LAUNCH("stack_shift_kernel(obs)");
-    launch_stack(priv_prev, priv_new, buf->reset_buf, p->num_envs, p->c_frame_stack * p->num_single_priv,
-                 p->num_single_priv, nullptr, nullptr, nullptr, st);
-    HB_CHECK_LAUNCH("stack_shift_kernel(priv)");
+    if (int rc = hb_stack_shift(obs_prev, obs_new, nullptr, p->num_envs, row_a, p->num_single_obs, stream)) return rc;
+    return hb_stack_shift(priv_prev, priv_new, nullptr, p->num_envs, row_b, p->num_single_priv, stream);
+}
+
+int hb_env_reset_finalize(const hb_env_params *p, const hb_env_buffers *buf, float *obs_new, float *priv_new,
+                          int32_t *host_count, void *stream) {
+    if (int rc = check_params(p, buf, "hb_env_reset_finalize")) return rc;
+    HB_REQUIRE(buf->scratch_ballots && buf->scratch_sums && buf->reset_env_ids && buf->reset_count && buf->episode_means,
+               "hb_env_reset_finalize: null scratch/result buffers");
+    HB_REQUIRE((obs_new == nullptr) == (priv_new == nullptr), "hb_env_reset_finalize: pass both frame stacks or neither");
+    HB_REQUIRE(!buf->time_outs_latched || buf->time_out_buf, "hb_env_reset_finalize: latch without time_out_buf");
+    const int tiles = (p->num_envs + TILE - 1) / TILE;
+    int seg = (tiles + hb::sm_count() - 1) / hb::sm_count();
+    if (seg < 8) seg = 8;
+    const int grid = (tiles + seg - 1) / seg;
+    reset_finalize_kernel<<<grid, FIN_THREADS, 0, (cudaStream_t)stream>>>(*p, *buf, obs_new, priv_new, tiles, seg, host_count);
+    HB_CHECK_LAUNCH("reset_finalize_kernel");
     return HB_OK;
 }
 

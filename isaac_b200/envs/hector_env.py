@@ -8,12 +8,15 @@ envs/custom/hector_env.py:158-261):
 
 and the same attribute names the runner and `play.py` read (dof_pos, dof_vel, torques,
 commands, base_lin_vel, base_ang_vel, contact_forces, feet_indices, episode_sums, ...).
-The per-step work is four kinds of kernel launch through the C ABI (include/hector_b200.h):
+The per-step work is five kinds of kernel launch through the C ABI (include/hector_b200.h):
 
     hb_env_action_prologue      x1   hector_env.py:158-169
     hb_env_compute_torques      x decimation, around the opaque physics.simulate()
     hb_env_post_physics         x1   legged_robot.py:118-234,303-396 + newest obs frames
-    hb_env_stack_observations   x1   hector_env.py:246-261 (frame stacking, ping-pong buffers)
+    hb_env_stack_observations   x1   hector_env.py:246-254 (frame stacking, ping-pong buffers); independent of
+                                     this step's physics
+    hb_env_reset_finalize       x1   legged_robot.py:142,198-209 (ascending reset ids, count, episode means,
+                                     time_outs) + hector_env.py:256-261 (history zeroing of the envs just reset)
 
 There is no torch/eager fallback: without libhectorb200.so construction fails.
 `step()` never blocks on the GPU; the one host-visible value the reference needs (the reset
@@ -237,8 +240,7 @@ class HectorFreeEnvB200:
         self._time_outs_latched = torch.zeros(N, dtype=torch.bool, device=dev)
         tiles = (N + 31) // 32
         self._scratch_ballots = torch.zeros(tiles, dtype=torch.int32, device=dev)
-        self._scratch_partials = z(tiles, HB_NUM_REWARDS)
-        self._scratch_ticket = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._scratch_sums = torch.zeros(HB_NUM_REWARDS, dtype=torch.float64, device=dev)
         self._terrain_level_mean = torch.zeros((), **f32)
         # extras["episode"] dicts are prebuilt views into the ring (no per-step tensor indexing)
         self._extras_episode = []
@@ -283,7 +285,7 @@ class HectorFreeEnvB200:
                 episode_length_buf=self.episode_length_buf, reset_buf=self.reset_buf, time_out_buf=self.time_out_buf,
                 rew_buf=self.rew_buf, reset_env_ids=self.reset_env_ids, reset_count=self._reset_count,
                 time_outs_latched=self._time_outs_latched, scratch_ballots=self._scratch_ballots,
-                scratch_partials=self._scratch_partials, scratch_ticket=self._scratch_ticket).items():
+                scratch_sums=self._scratch_sums).items():
             if not t.is_contiguous():
                 raise ValueError(f"{name} must be contiguous")
             setattr(b, name, t.data_ptr())
@@ -352,7 +354,7 @@ class HectorFreeEnvB200:
         decimation sub-steps (`physics.capturable`, e.g. the synthetic stage used by tests and bench.py).
         Two graphs per ping-pong parity: A = noise draws, action prologue, first PD launch; then the host
         hands the previous step's reset ids to the physics stage (legged_robot.py:370-372,394-396) while A
-        runs; B = the remaining PD launches, post-physics and frame stacking.  Push steps (every
+        runs; B = the remaining PD launches, post-physics, the frame-stack shift and the reset finalisation.  Push steps (every
         `push_interval`) and steps with injected noise take the eager path."""
         if not getattr(self.physics, "capturable", False):
             raise ValueError("this physics stage needs host calls between sub-steps; CUDA-graph replay is not possible")
@@ -385,21 +387,16 @@ class HectorFreeEnvB200:
             pool = pool or ga.pool()
             with torch.cuda.graph(gb, pool=pool):
                 st = self._stream()
+                prev, cur = parity, parity ^ 1
                 for _ in range(dec - 1):
                     _lib.check(lib.hb_env_compute_torques(self._pp, self._pb, st), "hb_env_compute_torques")
-                prev, cur = parity, parity ^ 1
                 self._b.episode_means = self._g_means[cur].data_ptr()
                 self._b.episode_means_prev = self._g_means[prev].data_ptr()
-                _lib.check(lib.hb_env_post_physics(self._pp, self._pb, C.byref(nz), self._obs[cur].data_ptr(),
-                                                   self._priv[cur].data_ptr(), HB_STAGE_STEP,
-                                                   self._host_count.data_ptr(), st), "hb_env_post_physics")
-                _lib.check(lib.hb_env_stack_observations(self._pp, self._pb, self._obs[prev].data_ptr(),
-                                                         self._priv[prev].data_ptr(), self._obs[cur].data_ptr(),
-                                                         self._priv[cur].data_ptr(), st), "hb_env_stack_observations")
+                self._launch_post_kernels(HB_STAGE_STEP, C.byref(nz), prev, cur, True, st)
             graphs[parity] = (ga, gb, u, zn)
         self._cur, self._step_index, self._pending_event = saved
         self._graphs = graphs
-        self.graph_launches_per_step = 1 + dec + 2     # this library's kernels per replayed step (prologue, PD, post, stack)
+        self.graph_launches_per_step = 1 + dec + 3     # this library's kernels per replayed step (prologue, PD, post, stack, finalize)
 
     def _step_graph(self, actions):
         ga, gb, _, _ = self._graphs[self._cur]
@@ -445,13 +442,8 @@ class HectorFreeEnvB200:
         means0 = self._episode_means.data_ptr()
         self._b.episode_means = means0 + slot * HB_NUM_REWARDS * 4
         self._b.episode_means_prev = means0 + prev_slot * HB_NUM_REWARDS * 4 if self._step_index > 0 else None
-        host_count = self._host_count.data_ptr()
-        _lib.check(lib.hb_env_post_physics(self._pp, self._pb, self._pn, self._obs[cur].data_ptr(),
-                                           self._priv[cur].data_ptr(), stages, host_count, st), "hb_env_post_physics")
+        self._launch_post_kernels(stages, self._pn, prev, cur, emit, st)
         if emit:
-            _lib.check(lib.hb_env_stack_observations(self._pp, self._pb, self._obs[prev].data_ptr(),
-                                                     self._priv[prev].data_ptr(), self._obs[cur].data_ptr(),
-                                                     self._priv[cur].data_ptr(), st), "hb_env_stack_observations")
             self._cur = cur
         if self._events:
             self._pending_event = self._events[self._step_index & 1]
@@ -463,6 +455,20 @@ class HectorFreeEnvB200:
         self._step_index += 1
         self._injected = None
         self._nz.u_reset = None
+
+    def _launch_post_kernels(self, stages, noise_ref, prev, cur, emit, st):
+        """post-physics -> frame-stack shift -> reset finalisation, on one stream."""
+        lib = self._lib
+        obs_new, priv_new = self._obs[cur].data_ptr(), self._priv[cur].data_ptr()
+        _lib.check(lib.hb_env_post_physics(self._pp, self._pb, noise_ref, obs_new, priv_new, stages, st),
+                   "hb_env_post_physics")
+        if emit:
+            _lib.check(lib.hb_env_stack_observations(self._pp, self._pb, self._obs[prev].data_ptr(),
+                                                     self._priv[prev].data_ptr(), obs_new, priv_new, st),
+                       "hb_env_stack_observations")
+        _lib.check(lib.hb_env_reset_finalize(self._pp, self._pb, obs_new if emit else None,
+                                             priv_new if emit else None, self._host_count.data_ptr(), st),
+                   "hb_env_reset_finalize")
 
     def _apply_pending_resets(self):
         """The two opaque calls of _reset_dofs/_reset_root_states (legged_robot.py:370-372,394-396) need
