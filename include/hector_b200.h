@@ -290,6 +290,17 @@ int hb_ppo_loss_head(const float *mu, int32_t ld_mu, const float *value, int32_t
                      const float *records, int64_t mb, int64_t mb_global, const hb_ppo_loss_params *lp, float *d_mu,
                      float *d_value, float *d_std, double *stats, void *stream);
 
+/* Update path, output layers fused with the loss head: for hidden width 128 (hector_config.py:207-210) the last
+ * nn.Linear of both MLPs (actor_critic.py:62,74) is evaluated with fp32 FMAs inside the loss kernel, together with
+ * its data gradient (into dz3 = d loss / d pre-activation of the last hidden layer, ELU' applied) and its weight /
+ * bias gradients (accumulated into g4_actor [>=10 rows, ld_w] and g4_critic [>=1 row, ld_w], packed [W | b]).
+ * h3_* [mb, ld_h]: last hidden activations; w4_* packed [W | b] with leading dimension ld_w; records, std, lp,
+ * d_std, stats as in hb_ppo_loss_head. */
+int hb_ppo_head_fused(const float *h3_actor, int32_t ld_ha, const float *h3_critic, int32_t ld_hc, const float *w4_actor,
+                      const float *w4_critic, int32_t ld_w, const float *std, const float *records, int64_t mb,
+                      int64_t mb_global, const hb_ppo_loss_params *lp, float *dz3_actor, float *dz3_critic, int32_t ld_dz,
+                      float *g4_actor, float *g4_critic, float *d_std, double *stats, void *stream);
+
 /* PPO.act head (ppo.py:91-101, actor_critic.py:111-120): a = mu + sigma*eps, log-prob, copies of mu/sigma. */
 int hb_ppo_act_head(const float *mu, int32_t ld_mu, const float *std, const float *eps, int64_t n, float *actions,
                     float *log_prob, float *mu_out, float *sigma_out, void *stream);

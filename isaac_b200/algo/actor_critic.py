@@ -157,13 +157,22 @@ class ActorCritic:
         return ws
 
     # ------------------------------------------------------------------ forward
-    def _mlp_forward(self, net: str, x: torch.Tensor, ws: dict):
-        """x: [m, ld] with ld % 4 == 0 (only the first fan_in columns are read).  Returns out [m,16]."""
+    @property
+    def fused_head(self) -> bool:
+        """Both last hidden layers are 128 wide: the update path evaluates the output layers inside the loss
+        kernel (hb_ppo_head_fused) instead of as 128-row tensor-core tiles with 10 / 1 useful columns."""
+        return all(L.fan_in == 128 for L in self.layers if L.last)
+
+    def _mlp_forward(self, net: str, x: torch.Tensor, ws: dict, hidden_only: bool = False):
+        """x: [m, ld] with ld % 4 == 0 (only the first fan_in columns are read).  Returns out [m,16]
+        (or, with hidden_only, the last hidden activations [m, pad4(width + 1)])."""
         lib, st = self._lib, torch.cuda.current_stream(self.device).cuda_stream
         Ls = [L for L in self.layers if L.net == net]
         a, lda = x, x.stride(0)
         m = x.shape[0]
         for i, L in enumerate(Ls):
+            if L.last and hidden_only:
+                return ws[net]["h"][-1]
             P = self._matrix(self.flat, L)
             d = ws[net]["out"] if L.last else ws[net]["h"][i]
             gemm(lib, st, A=a.data_ptr(), B=P.data_ptr(), D=d.data_ptr(), M=m, N=L.rows if L.last else L.fan_out,
@@ -172,15 +181,18 @@ class ActorCritic:
             a, lda = d, d.stride(0)
         return ws[net]["out"]
 
-    def _mlp_backward(self, net: str, x: torch.Tensor, ws: dict):
+    def _mlp_backward(self, net: str, x: torch.Tensor, ws: dict, from_hidden: bool = False):
         """Gradients of every packed matrix of `net` from d_out (filled by the loss head); accumulates into
-        self.grad with split-K atomics (the buffer is zero on entry: Adam zeroes it)."""
+        self.grad with split-K atomics (the buffer is zero on entry: Adam zeroes it).  With from_hidden the
+        output layer has been handled by hb_ppo_head_fused, which left dz of the last hidden layer in ws."""
         lib, st = self._lib, torch.cuda.current_stream(self.device).cuda_stream
         Ls = [L for L in self.layers if L.net == net]
         m = x.shape[0]
         kb_total = (m + 31) // 32
         d_cur, ld_cur = ws[net]["d_out"], 16               # gradient w.r.t. the layer's pre-activation output
-        for i in reversed(range(4)):
+        if from_hidden:
+            d_cur, ld_cur = ws[net]["dz"][-1], ws[net]["dz"][-1].stride(0)
+        for i in reversed(range(3 if from_hidden else 4)):
             L = Ls[i]
             G = self._matrix(self.grad, L)
             act_in = x if i == 0 else ws[net]["h"][i - 1]      # [m, fan_in (+ ones column)]

@@ -3,10 +3,10 @@
     act / process_env_step / compute_returns / update       same signatures and semantics
     actor_critic, optimizer.state_dict(), learning_rate, storage, transition   same attributes
 
-Per minibatch step: 8 forward GEMMs (tcgen05, TF32 operands, fused bias+ELU), one loss-head kernel
-(log-prob, clipped surrogate, clipped value loss, entropy, KL and their analytic gradients), 6 data-gradient
-GEMMs (fused ELU'), 8 split-K weight-gradient GEMMs (bias gradients ride along as one more column), one
-gradient-norm reduction and one fused clip + Adam kernel that also applies the adaptive-KL learning-rate rule
+Per minibatch step: 6 forward GEMMs (tcgen05, TF32 operands, fused bias+ELU), one fused kernel for the two
+output layers + the loss head (log-prob, clipped surrogate, clipped value loss, entropy, KL, their analytic
+gradients, and the output layers' data / weight gradients), 4 data-gradient GEMMs (fused ELU'), 6 split-K
+weight-gradient GEMMs (bias gradients ride along as one more column), one gradient-norm reduction and one fused clip + Adam kernel that also applies the adaptive-KL learning-rate rule
 on the device (no `.item()` sync per minibatch; the reference needs ~22).  The minibatch
 permutation is drawn once per update and reused by every epoch (rollout_storage.py:149), so the index gathers
 of `mini_batch_generator` are done once per update into minibatch-ordered buffers.
@@ -162,15 +162,29 @@ class PPO:
         st = torch.cuda.current_stream(self.device).cuda_stream
         ws = ac.workspace(mb)
         xa, xc, rec = self._xa[i * mb:(i + 1) * mb], self._xc[i * mb:(i + 1) * mb], self._rec[i * mb:(i + 1) * mb]
-        mu16 = ac._mlp_forward("actor", xa, ws)
-        v16 = ac._mlp_forward("critic", xc, ws)
         self._stats.zero_()
-        _lib.check(lib.hb_ppo_loss_head(mu16.data_ptr(), 16, v16.data_ptr(), 16, ac.std.data_ptr(), rec.data_ptr(), mb,
-                                        mb * self.world_size, C.byref(self._lp), ws["actor"]["d_out"].data_ptr(),
-                                        ws["critic"]["d_out"].data_ptr(), ac.grad[ac._std_offset:].data_ptr(),
-                                        self._stats.data_ptr(), st), "hb_ppo_loss_head")
-        ac._mlp_backward("actor", xa, ws)
-        ac._mlp_backward("critic", xc, ws)
+        if ac.fused_head:
+            h3a = ac._mlp_forward("actor", xa, ws, hidden_only=True)
+            h3c = ac._mlp_forward("critic", xc, ws, hidden_only=True)
+            La, Lc = [L for L in ac.layers if L.last]
+            dza, dzc = ws["actor"]["dz"][-1], ws["critic"]["dz"][-1]
+            _lib.check(lib.hb_ppo_head_fused(
+                h3a.data_ptr(), h3a.stride(0), h3c.data_ptr(), h3c.stride(0),
+                ac._matrix(ac.flat, La).data_ptr(), ac._matrix(ac.flat, Lc).data_ptr(), La.ld, ac.std.data_ptr(),
+                rec.data_ptr(), mb, mb * self.world_size, C.byref(self._lp), dza.data_ptr(), dzc.data_ptr(), dza.stride(0),
+                ac._matrix(ac.grad, La).data_ptr(), ac._matrix(ac.grad, Lc).data_ptr(),
+                ac.grad[ac._std_offset:].data_ptr(), self._stats.data_ptr(), st), "hb_ppo_head_fused")
+            ac._mlp_backward("actor", xa, ws, from_hidden=True)
+            ac._mlp_backward("critic", xc, ws, from_hidden=True)
+        else:
+            mu16 = ac._mlp_forward("actor", xa, ws)
+            v16 = ac._mlp_forward("critic", xc, ws)
+            _lib.check(lib.hb_ppo_loss_head(mu16.data_ptr(), 16, v16.data_ptr(), 16, ac.std.data_ptr(), rec.data_ptr(), mb,
+                                            mb * self.world_size, C.byref(self._lp), ws["actor"]["d_out"].data_ptr(),
+                                            ws["critic"]["d_out"].data_ptr(), ac.grad[ac._std_offset:].data_ptr(),
+                                            self._stats.data_ptr(), st), "hb_ppo_loss_head")
+            ac._mlp_backward("actor", xa, ws)
+            ac._mlp_backward("critic", xc, ws)
         if self.grad_allreduce is not None:
             self.grad_allreduce(ac.grad, self._stats)        # sums over ranks (grads already carry 1/global_mb)
 

@@ -31,7 +31,8 @@ enum Epilogue { EPI_STORE = 0, EPI_BIAS = 1, EPI_BIAS_ELU = 2, EPI_ELU_BWD = 3, 
 
 struct GemmArgs {
     int M, N, K;                  // logical sizes (K = contraction length)
-    int kb_per_split;             // k-blocks handled by one CTA (gridDim.z splits)
+    int kb_per_split;             // k-blocks of one k split
+    int tiles_n, splits, total_tiles;   // tile list: (m tile, k split, n tile), n fastest
     float *D;                     // [M, ldd]
     int ldd;
     const float *bias;            // bias[n * bias_stride] (weights and bias share one packed matrix)
@@ -114,30 +115,41 @@ __host__ __device__ constexpr uint32_t make_idesc(int n, bool a_mn, bool b_mn) {
 template <int BN>
 __host__ __device__ constexpr int stages_for() { return BN >= 256 ? 4 : (BN >= 128 ? 6 : 8); }
 
+constexpr int EPI_TILE_FLOATS = 32 * 33;          // per epilogue warp: one padded 32 x 32 transpose tile
+template <int BN>
+__host__ __device__ constexpr size_t smem_bytes_for() {
+    return (size_t)stages_for<BN>() * (BM * BK * 4 + BN * BK * 4) + 4 * EPI_TILE_FLOATS * 4 + 4 * (BN < 32 ? 32 : BN) * 4 + 1024;
+}
+
+// Persistent, warp-specialised: one CTA per SM walks a static list of output tiles
+//   tile t = blockIdx.x + i * gridDim.x  ->  (m tile, n tile, k split), n fastest so that the CTAs running at the
+//   same time share the rows of A in L2 (the weights are small and always L2-resident).
+// Three pipelines: shared-memory stages (TMA <-> MMA), two TMEM accumulators (MMA <-> epilogue: the epilogue of tile
+// i overlaps the main loop of tile i + 1), and the tile list.
 template <int BN, bool A_MN, bool B_MN, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                  const __grid_constant__ GemmArgs g) {
     constexpr int NSTAGE = stages_for<BN>();
     constexpr int A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4;
-    constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+    constexpr uint32_t ACC_COLS = BN < 32 ? 32 : BN;          // TMEM columns of one accumulator
+    constexpr uint32_t TMEM_COLS = 2 * ACC_COLS;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t *sa = smem, *sb = smem + NSTAGE * A_BYTES;
-    __shared__ __align__(8) uint64_t full_bar[NSTAGE], empty_bar[NSTAGE], acc_bar;
+    float *epi_smem = reinterpret_cast<float *>(smem + NSTAGE * (A_BYTES + B_BYTES));
+    float *bias_smem = epi_smem + 4 * EPI_TILE_FLOATS;        // [4 warps][ACC_COLS]
+    __shared__ __align__(8) uint64_t full_bar[NSTAGE], empty_bar[NSTAGE], acc_full[2], acc_empty[2];
     __shared__ uint32_t tmem_base_smem;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
     const int kb_total = (g.K + BK - 1) / BK;
-    const int kb_begin = blockIdx.z * g.kb_per_split;
-    const int kb_end = min(kb_begin + g.kb_per_split, kb_total);
-    const int nkb = kb_end - kb_begin;
 
     if (threadIdx.x == 0) {
 #pragma unroll
         for (int s = 0; s < NSTAGE; ++s) hb::mbar_init(&full_bar[s], 1), hb::mbar_init(&empty_bar[s], 1);
-        hb::mbar_init(&acc_bar, 1);
+#pragma unroll
+        for (int a = 0; a < 2; ++a) hb::mbar_init(&acc_full[a], 1), hb::mbar_init(&acc_empty[a], 4);
         hb::fence_mbar_init();
     }
     if (warp == 4 && lane == 0) prefetch_tmap(&map_a), prefetch_tmap(&map_b);
@@ -145,148 +157,182 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_acc = tmem_base_smem;
+    const uint32_t tmem_base = tmem_base_smem;
+
+    auto tile_coords = [&](int t, int &m0, int &n0, int &kb_begin, int &nkb) {
+        const int nt = t % g.tiles_n;
+        const int rest = t / g.tiles_n;
+        const int z = rest % g.splits;
+        const int mt = rest / g.splits;
+        m0 = mt * BM, n0 = nt * BN;
+        kb_begin = z * g.kb_per_split;
+        nkb = min(kb_begin + g.kb_per_split, kb_total) - kb_begin;
+    };
 
     if (warp == 4) {
         // ===================== TMA producer =====================
         if (lane == 0) {
-            for (int i = 0; i < nkb; ++i) {
-                const int s = i % NSTAGE, ph = (i / NSTAGE) & 1;
-                hb::mbar_wait(&empty_bar[s], ph ^ 1);
-                hb::mbar_expect_tx(&full_bar[s], A_BYTES + B_BYTES);
-                const int k0 = (kb_begin + i) * BK;
-                if (A_MN) {      // tensor map dims (M, K): boxes of 32 m x 32 k, one 4 KB swizzle block each
+            uint32_t it = 0;
+            for (int t = blockIdx.x; t < g.total_tiles; t += gridDim.x) {
+                int m0, n0, kb_begin, nkb;
+                tile_coords(t, m0, n0, kb_begin, nkb);
+                for (int i = 0; i < nkb; ++i, ++it) {
+                    const uint32_t s = it % NSTAGE, ph = (it / NSTAGE) & 1;
+                    hb::mbar_wait(&empty_bar[s], ph ^ 1);
+                    hb::mbar_expect_tx(&full_bar[s], A_BYTES + B_BYTES);
+                    const int k0 = (kb_begin + i) * BK;
+                    if (A_MN) {      // tensor map dims (M, K): boxes of 32 m x 32 k, one 4 KB swizzle block each
 #pragma unroll
-                    for (int j = 0; j < BM / 32; ++j) tma_load_2d(sa + s * A_BYTES + j * 4096, &map_a, m0 + 32 * j, k0, &full_bar[s]);
-                } else {         // tensor map dims (K, M): one box of 32 k x 128 rows
-                    tma_load_2d(sa + s * A_BYTES, &map_a, k0, m0, &full_bar[s]);
-                }
-                if (B_MN) {
+                        for (int j = 0; j < BM / 32; ++j) tma_load_2d(sa + s * A_BYTES + j * 4096, &map_a, m0 + 32 * j, k0, &full_bar[s]);
+                    } else {         // tensor map dims (K, M): one box of 32 k x 128 rows
+                        tma_load_2d(sa + s * A_BYTES, &map_a, k0, m0, &full_bar[s]);
+                    }
+                    if (B_MN) {
 #pragma unroll
-                    for (int j = 0; j < BN / 32; ++j) tma_load_2d(sb + s * B_BYTES + j * 4096, &map_b, n0 + 32 * j, k0, &full_bar[s]);
-                } else {
-                    tma_load_2d(sb + s * B_BYTES, &map_b, k0, n0, &full_bar[s]);
+                        for (int j = 0; j < BN / 32; ++j) tma_load_2d(sb + s * B_BYTES + j * 4096, &map_b, n0 + 32 * j, k0, &full_bar[s]);
+                    } else {
+                        tma_load_2d(sb + s * B_BYTES, &map_b, k0, n0, &full_bar[s]);
+                    }
                 }
             }
         }
     } else if (warp == 5) {
         // ===================== MMA issuer =====================
         constexpr uint32_t idesc = make_idesc(BN < 16 ? 16 : BN, A_MN, B_MN);
-        for (int i = 0; i < nkb; ++i) {
-            const int s = i % NSTAGE, ph = (i / NSTAGE) & 1;
-            hb::mbar_wait(&full_bar[s], ph);
+        uint32_t it = 0, acc_it = 0;
+        for (int t = blockIdx.x; t < g.total_tiles; t += gridDim.x, ++acc_it) {
+            int m0, n0, kb_begin, nkb;
+            tile_coords(t, m0, n0, kb_begin, nkb);
+            const uint32_t a = acc_it & 1, aph = (acc_it >> 1) & 1;
+            hb::mbar_wait(&acc_empty[a], aph ^ 1);           // the epilogue has drained this accumulator
             tc_fence_after();
-            if (lane == 0) {
-                const uint32_t a_addr = hb::smem_u32(sa + s * A_BYTES), b_addr = hb::smem_u32(sb + s * B_BYTES);
+            const uint32_t tmem_acc = tmem_base + a * ACC_COLS;
+            for (int i = 0; i < nkb; ++i, ++it) {
+                const uint32_t s = it % NSTAGE, ph = (it / NSTAGE) & 1;
+                hb::mbar_wait(&full_bar[s], ph);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t a_addr = hb::smem_u32(sa + s * A_BYTES), b_addr = hb::smem_u32(sb + s * B_BYTES);
 #pragma unroll
-                for (int k = 0; k < BK / UMMA_K; ++k) {
-                    // K-major: 8 tf32 = 32 bytes further along the swizzled 128-byte row;
-                    // MN-major: 8 k-rows = one 1024-byte swizzle atom further
-                    const uint64_t ad = A_MN ? make_desc(a_addr + k * 1024, 4096, 512, LAYOUT_SW128_BASE32B)
-                                             : make_desc(a_addr + k * 32, 16, 1024, LAYOUT_SW128);
-                    const uint64_t bd = B_MN ? make_desc(b_addr + k * 1024, 4096, 512, LAYOUT_SW128_BASE32B)
-                                             : make_desc(b_addr + k * 32, 16, 1024, LAYOUT_SW128);
-                    umma_tf32(tmem_acc, ad, bd, idesc, (i > 0 || k > 0) ? 1u : 0u);
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        // K-major: 8 tf32 = 32 bytes further along the swizzled 128-byte row;
+                        // MN-major: 8 k-rows = one 1024-byte swizzle atom further
+                        const uint64_t ad = A_MN ? make_desc(a_addr + k * 1024, 4096, 512, LAYOUT_SW128_BASE32B)
+                                                 : make_desc(a_addr + k * 32, 16, 1024, LAYOUT_SW128);
+                        const uint64_t bd = B_MN ? make_desc(b_addr + k * 1024, 4096, 512, LAYOUT_SW128_BASE32B)
+                                                 : make_desc(b_addr + k * 32, 16, 1024, LAYOUT_SW128);
+                        umma_tf32(tmem_acc, ad, bd, idesc, (i > 0 || k > 0) ? 1u : 0u);
+                    }
+                    umma_commit(&empty_bar[s]);                  // frees the smem stage once the MMAs have read it
+                    if (i == nkb - 1) umma_commit(&acc_full[a]); // accumulator complete -> epilogue
                 }
-                umma_commit(&empty_bar[s]);                  // frees the smem stage once the MMAs have read it
-                if (i == nkb - 1) umma_commit(&acc_bar);     // accumulator complete -> epilogue
+                __syncwarp();
             }
-            __syncwarp();
         }
     } else {
         // ===================== epilogue (warps 0-3: TMEM lanes 32*warp .. 32*warp+31) =====================
         // The accumulator arrives with lane = row.  Global traffic wants lane = column (128-byte rows), so
-        // every 32 x 32 block goes through a padded shared-memory tile (the pipeline stages are idle once
-        // the accumulator barrier has fired): activations for ELU' come in coalesced, results leave coalesced.
-        if (nkb > 0) {
-            hb::mbar_wait(&acc_bar, 0);
-            tc_fence_after();
-        }
-        float *tile = reinterpret_cast<float *>(smem) + warp * (32 * 33);
-        const int mw = m0 + warp * 32;                     // first row of this warp
-#pragma unroll 1
-        for (int c = 0; c < BN; c += 32) {
-            const int n = n0 + c;
-            if (n >= g.N || mw >= g.M) break;
-            float v[32];
-            if (nkb > 0) {
-                tmem_ld16(tmem_acc + ((uint32_t)(warp * 32) << 16) + (uint32_t)c, v);
-                if (BN > 16) tmem_ld16(tmem_acc + ((uint32_t)(warp * 32) << 16) + (uint32_t)(c + 16), v + 16);
-            } else {
-#pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] = 0.0f;
+        // every 32 x 32 block goes through a padded shared-memory tile private to the warp: activations for
+        // ELU' come in coalesced, results leave coalesced.
+        float *tile = epi_smem + warp * EPI_TILE_FLOATS;
+        float *bias_w = bias_smem + warp * ACC_COLS;
+        uint32_t acc_it = 0;
+        for (int t = blockIdx.x; t < g.total_tiles; t += gridDim.x, ++acc_it) {
+            int m0, n0, kb_begin, nkb;
+            tile_coords(t, m0, n0, kb_begin, nkb);
+            const uint32_t a = acc_it & 1, aph = (acc_it >> 1) & 1;
+            const int mw = m0 + warp * 32;                     // first row of this warp
+            if (EPI == EPI_BIAS || EPI == EPI_BIAS_ELU) {      // the tile's biases, once, while the MMAs run
+                for (int c = lane; c < BN; c += 32)
+                    bias_w[c] = (n0 + c < g.N) ? __ldg(g.bias + (size_t)(n0 + c) * g.bias_stride) : 0.0f;
+                __syncwarp();
             }
-            const int ncols = min(32, g.N - n), nrows = min(32, g.M - mw);
-            const bool col_ok = lane < ncols;
-            if (EPI == EPI_BIAS || EPI == EPI_BIAS_ELU) {
-                const float bl = col_ok ? __ldg(g.bias + (size_t)(n + lane) * g.bias_stride) : 0.0f;
+            hb::mbar_wait(&acc_full[a], aph);
+            tc_fence_after();
+            const uint32_t tmem_acc = tmem_base + a * ACC_COLS + ((uint32_t)(warp * 32) << 16);
+#pragma unroll 1
+            for (int c = 0; c < BN; c += 32) {
+                const int n = n0 + c;
+                if (n >= g.N || mw >= g.M) break;
+                float v[32];
+                tmem_ld16(tmem_acc + (uint32_t)c, v);
+                if (BN > 16) tmem_ld16(tmem_acc + (uint32_t)(c + 16), v + 16);
+                const int ncols = min(32, g.N - n), nrows = min(32, g.M - mw);
+                const bool col_ok = lane < ncols;
+                if (EPI == EPI_BIAS || EPI == EPI_BIAS_ELU) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    float x = v[i] + __shfl_sync(0xffffffffu, bl, i);
-                    if (EPI == EPI_BIAS_ELU) x = x > 0.0f ? x : expf(x) - 1.0f;          // nn.ELU(alpha=1)
-                    v[i] = x;
+                    for (int i = 0; i < 32; ++i) {
+                        float x = v[i] + bias_w[c + i];
+                        if (EPI == EPI_BIAS_ELU) x = x > 0.0f ? x : __expf(x) - 1.0f;        // nn.ELU(alpha=1)
+                        v[i] = x;
+                    }
+                } else if (EPI == EPI_ELU_BWD) {
+                    // rows of H, coalesced: 8 lanes x float4 per row, 4 rows per instruction, all 8 loads in flight
+                    const int rr = lane >> 3, c4 = (lane & 7) * 4;
+                    const bool fast = (ncols == 32) && ((g.ldh & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.H) & 15u) == 0);
+                    if (fast) {
+                        float4 h4[8];
+#pragma unroll
+                        for (int it = 0; it < 8; ++it) {
+                            const int r = it * 4 + rr;
+                            h4[it] = (r < nrows) ? __ldg(reinterpret_cast<const float4 *>(g.H + (size_t)(mw + r) * g.ldh + n + c4))
+                                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+#pragma unroll
+                        for (int it = 0; it < 8; ++it) {
+                            float *tt = tile + (it * 4 + rr) * 33 + c4;
+                            tt[0] = h4[it].x, tt[1] = h4[it].y, tt[2] = h4[it].z, tt[3] = h4[it].w;
+                        }
+                    } else {
+                        for (int r = 0; r < nrows; ++r)
+                            tile[r * 33 + lane] = col_ok ? __ldg(g.H + (size_t)(mw + r) * g.ldh + n + lane) : 0.0f;
+                    }
+                    __syncwarp();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const float h = tile[lane * 33 + i];           // h = elu(z): elu'(z) = z > 0 ? 1 : h + 1
+                        v[i] = v[i] * (h > 0.0f ? 1.0f : h + 1.0f);
+                    }
+                    __syncwarp();
                 }
-            } else if (EPI == EPI_ELU_BWD) {
-                // rows of H, coalesced: 8 lanes x float4 per row, 4 rows per instruction, all 8 loads in flight
-                const int rr = lane >> 3, c4 = (lane & 7) * 4;
-                const bool fast = (ncols == 32) && ((g.ldh & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.H) & 15u) == 0);
-                if (fast) {
-                    float4 h4[8];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) tile[lane * 33 + i] = v[i];
+                __syncwarp();
+                const bool fast_out = (ncols == 32) && ((g.ldd & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.D) & 15u) == 0);
+                if (fast_out) {
+                    const int rr = lane >> 3, c4 = (lane & 7) * 4;
 #pragma unroll
                     for (int it = 0; it < 8; ++it) {
                         const int r = it * 4 + rr;
-                        h4[it] = (r < nrows) ? __ldg(reinterpret_cast<const float4 *>(g.H + (size_t)(mw + r) * g.ldh + n + c4))
-                                             : make_float4(0.f, 0.f, 0.f, 0.f);
-                    }
-#pragma unroll
-                    for (int it = 0; it < 8; ++it) {
-                        float *t = tile + (it * 4 + rr) * 33 + c4;
-                        t[0] = h4[it].x, t[1] = h4[it].y, t[2] = h4[it].z, t[3] = h4[it].w;
-                    }
-                } else {
-                    for (int r = 0; r < nrows; ++r)
-                        tile[r * 33 + lane] = col_ok ? __ldg(g.H + (size_t)(mw + r) * g.ldh + n + lane) : 0.0f;
-                }
-                __syncwarp();
-#pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const float h = tile[lane * 33 + i];           // h = elu(z): elu'(z) = z > 0 ? 1 : h + 1
-                    v[i] = v[i] * (h > 0.0f ? 1.0f : h + 1.0f);
-                }
-                __syncwarp();
-            }
-#pragma unroll
-            for (int i = 0; i < 32; ++i) tile[lane * 33 + i] = v[i];
-            __syncwarp();
-            const bool fast_out = (ncols == 32) && ((g.ldd & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.D) & 15u) == 0);
-            if (fast_out) {
-                const int rr = lane >> 3, c4 = (lane & 7) * 4;
-#pragma unroll
-                for (int it = 0; it < 8; ++it) {
-                    const int r = it * 4 + rr;
-                    if (r < nrows) {
-                        const float *t = tile + r * 33 + c4;
-                        float *dst = g.D + (size_t)(mw + r) * g.ldd + n + c4;
-                        if (EPI == EPI_ATOMIC) {
-                            atomicAdd(dst, t[0]), atomicAdd(dst + 1, t[1]), atomicAdd(dst + 2, t[2]), atomicAdd(dst + 3, t[3]);
-                        } else {
-                            *reinterpret_cast<float4 *>(dst) = make_float4(t[0], t[1], t[2], t[3]);
+                        if (r < nrows) {
+                            const float *tt = tile + r * 33 + c4;
+                            float *dst = g.D + (size_t)(mw + r) * g.ldd + n + c4;
+                            if (EPI == EPI_ATOMIC) {      // one 16-byte vector reduction per lane (sm_90+)
+                                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(tt[0]), "f"(tt[1]),
+                                             "f"(tt[2]), "f"(tt[3])
+                                             : "memory");
+                            } else {
+                                *reinterpret_cast<float4 *>(dst) = make_float4(tt[0], tt[1], tt[2], tt[3]);
+                            }
                         }
                     }
+                } else if (col_ok) {
+                    for (int r = 0; r < nrows; ++r) {
+                        float *dst = g.D + (size_t)(mw + r) * g.ldd + n + lane;
+                        if (EPI == EPI_ATOMIC) atomicAdd(dst, tile[r * 33 + lane]);
+                        else *dst = tile[r * 33 + lane];
+                    }
                 }
-            } else if (col_ok) {
-                for (int r = 0; r < nrows; ++r) {
-                    float *dst = g.D + (size_t)(mw + r) * g.ldd + n + lane;
-                    if (EPI == EPI_ATOMIC) atomicAdd(dst, tile[r * 33 + lane]);
-                    else *dst = tile[r * 33 + lane];
-                }
+                __syncwarp();
             }
-            __syncwarp();
+            // every tcgen05.ld of this warp has completed (tcgen05.wait::ld inside tmem_ld16): hand the accumulator back
+            tc_fence_before();
+            if (lane == 0) hb::mbar_arrive(&acc_empty[a]);
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 5) tmem_dealloc(tmem_acc, TMEM_COLS);
+    if (warp == 5) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
 // ---- host side --------------------------------------------------------------------------------------
@@ -340,8 +386,7 @@ int make_map(CUtensorMap *map, const float *base, int rows, int cols, int ld, in
 
 template <int BN, bool A_MN, bool B_MN, int EPI>
 int launch(const hb_gemm_desc *d, cudaStream_t st) {
-    constexpr int NSTAGE = stages_for<BN>();
-    constexpr size_t SMEM = (size_t)NSTAGE * (BM * BK * 4 + BN * BK * 4) + 1024;
+    constexpr size_t SMEM = smem_bytes_for<BN>();
     static bool attr = false;
     auto kern = gemm_tf32_kernel<BN, A_MN, B_MN, EPI>;
     if (!attr) {
@@ -363,7 +408,10 @@ int launch(const hb_gemm_desc *d, cudaStream_t st) {
     g.kb_per_split = (kb_total + splits - 1) / splits;
     splits = g.kb_per_split > 0 ? (kb_total + g.kb_per_split - 1) / g.kb_per_split : 1;
     g.D = d->D, g.ldd = d->ldd, g.bias = d->bias, g.bias_stride = d->bias_stride, g.H = d->H, g.ldh = d->ldh;
-    dim3 grid((d->M + BM - 1) / BM, (d->N + BN - 1) / BN, splits);
+    const int tiles_m = (d->M + BM - 1) / BM;
+    g.tiles_n = (d->N + BN - 1) / BN, g.splits = splits;
+    g.total_tiles = tiles_m * g.tiles_n * splits;
+    const int grid = g.total_tiles < hb::sm_count() ? g.total_tiles : hb::sm_count();
     kern<<<grid, GEMM_THREADS, SMEM, st>>>(ma, mb, g);
     HB_CHECK_LAUNCH("gemm_tf32_kernel");
     return HB_OK;

@@ -148,6 +148,177 @@ loss_head_kernel(const float *__restrict__ mu, int ld_mu, const float *__restric
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Fused output layers + loss head (update path).  The last nn.Linear of both MLPs is 128 -> 10 / 128 -> 1:
+// 1 290 + 129 MACs per sample, far too thin for a 128-row tensor-core tile, and it sits between the last hidden
+// activations and the loss.  One pass over the minibatch does, per sample (one warp per row, lane = 4 features):
+//   mu = H3a W4a^T + b, v = H3c W4c^T + b          actor_critic.py:62,74 (fp32 FMAs, not TF32)
+//   loss head and its gradient (ppo.py:130-168)     same arithmetic as loss_head_kernel
+//   dz3 = (d_out W4) * elu'(H3)                     data gradient into the last hidden layer
+//   G4 += d_out^T [H3 | 1]                          weight + bias gradients, reduced per CTA, then atomics
+// so H3 is read once and mu / value / d_out never touch HBM.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int HID = 128;                 // last hidden width of both networks (hector_config.py:207-210)
+constexpr int HEAD_THREADS = 256;
+
+struct HeadLoss {                        // per-sample results of the loss head (uniform across the warp)
+    float g_mu[NA], g_v, g_std[NA];
+    double st_s, st_v, st_k, st_e;
+};
+
+__device__ __forceinline__ void loss_head_sample(const float *__restrict__ r, const float *m, float v, const float *sig,
+                                                 double inv_b, const hb_ppo_loss_params &lp, HeadLoss &o) {
+    float lp_new = 0.0f, kl = 0.0f, ent = 0.0f, diff[NA];
+#pragma unroll
+    for (int j = 0; j < NA; ++j) {
+        const float var = sig[j] * sig[j];
+        diff[j] = r[j] - m[j];
+        lp_new += (-(diff[j] * diff[j]) / (2.0f * var) - logf(sig[j])) - HALF_LOG_2PI;      // Normal.log_prob
+        const float so = r[2 * NA + j], dm = r[NA + j] - m[j];
+        kl += (logf(sig[j] / so + 1.e-5f) + (so * so + dm * dm) / (2.0f * var)) - 0.5f;      // ppo.py:138-139
+        ent += (0.5f + HALF_LOG_2PI) + logf(sig[j]);                                          // Normal.entropy
+    }
+    const float v_old = r[3 * NA], adv = r[3 * NA + 1], ret = r[3 * NA + 2], lp_old = r[3 * NA + 3];
+    const float ratio = expf(lp_new - lp_old);                 // clipped surrogate (ppo.py:152-156)
+    const float lo = 1.0f - lp.clip_param, hi = 1.0f + lp.clip_param;
+    const float s1 = -adv * ratio, s2 = -adv * fminf(fmaxf(ratio, lo), hi);
+    const float inr = (ratio >= lo && ratio <= hi) ? 1.0f : 0.0f;
+    const float w1 = s1 > s2 ? 1.0f : (s1 == s2 ? 0.5f : 0.0f);       // torch.max splits the gradient evenly on ties
+    const float g_ratio = -adv * (w1 + (1.0f - w1) * inr);
+    const float g_lp = (float)((double)(g_ratio * ratio) * inv_b);
+    o.st_s = (double)fmaxf(s1, s2);
+    float g_v;
+    if (lp.use_clipped_value_loss) {                           // value loss (ppo.py:158-166)
+        const float dv = v - v_old;
+        const float vc = v_old + fminf(fmaxf(dv, -lp.clip_param), lp.clip_param);
+        const float l1 = (v - ret) * (v - ret), l2 = (vc - ret) * (vc - ret);
+        const float inv = (dv >= -lp.clip_param && dv <= lp.clip_param) ? 1.0f : 0.0f;
+        const float u1 = l1 > l2 ? 1.0f : (l1 == l2 ? 0.5f : 0.0f);
+        g_v = 2.0f * (v - ret) * u1 + 2.0f * (vc - ret) * inv * (1.0f - u1);
+        o.st_v = (double)fmaxf(l1, l2);
+    } else {
+        g_v = -2.0f * (ret - v);
+        o.st_v = (double)((ret - v) * (ret - v));
+    }
+    o.st_k = (double)kl, o.st_e = (double)ent;
+#pragma unroll
+    for (int j = 0; j < NA; ++j) {
+        const float var = sig[j] * sig[j];
+        o.g_mu[j] = g_lp * (diff[j] / var);
+        o.g_std[j] = g_lp * ((diff[j] * diff[j]) / (var * sig[j]) - 1.0f / sig[j]);
+    }
+    o.g_v = (float)((double)(lp.value_loss_coef * g_v) * inv_b);
+}
+
+__global__ void __launch_bounds__(HEAD_THREADS, 1)
+head_fused_kernel(const float *__restrict__ h3a, int ld_ha, const float *__restrict__ h3c, int ld_hc,
+                  const float *__restrict__ w4a, const float *__restrict__ w4c, int ld_w, const float *__restrict__ stdp,
+                  const float *__restrict__ rec, long long mb, double inv_b, float ent_scale, hb_ppo_loss_params lp,
+                  float *__restrict__ dz3a, float *__restrict__ dz3c, int ld_dz, float *__restrict__ g4a,
+                  float *__restrict__ g4c, float *__restrict__ d_std, double *__restrict__ stats) {
+    __shared__ float s_g[(NA + 1) * (HID + 1)];            // CTA-level weight/bias gradient accumulators
+    __shared__ float s_dstd[NA];
+    __shared__ double s_stat[4];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < (NA + 1) * (HID + 1); i += HEAD_THREADS) s_g[i] = 0.0f;
+    if (threadIdx.x < NA) s_dstd[threadIdx.x] = 0.0f;
+    if (threadIdx.x < 4) s_stat[threadIdx.x] = 0.0;
+    // this lane's 4 columns of the output-layer weights, biases (uniform) and sigma
+    float wa[NA][4], wc[4], ba[NA], sig[NA];
+#pragma unroll
+    for (int j = 0; j < NA; ++j) {
+        const float4 w = *reinterpret_cast<const float4 *>(w4a + (size_t)j * ld_w + lane * 4);
+        wa[j][0] = w.x, wa[j][1] = w.y, wa[j][2] = w.z, wa[j][3] = w.w;
+        ba[j] = w4a[(size_t)j * ld_w + HID];
+        sig[j] = stdp[j];
+    }
+    {
+        const float4 w = *reinterpret_cast<const float4 *>(w4c + lane * 4);
+        wc[0] = w.x, wc[1] = w.y, wc[2] = w.z, wc[3] = w.w;
+    }
+    const float bc = w4c[HID];
+    float ga[NA][4], gc[4], gba[NA], gbc = 0.0f, gstd[NA];
+#pragma unroll
+    for (int j = 0; j < NA; ++j) {
+        ga[j][0] = ga[j][1] = ga[j][2] = ga[j][3] = 0.0f;
+        gba[j] = 0.0f, gstd[j] = 0.0f;
+    }
+    gc[0] = gc[1] = gc[2] = gc[3] = 0.0f;
+    double st[4] = {0.0, 0.0, 0.0, 0.0};
+    __syncthreads();
+
+    const long long warps = (long long)gridDim.x * (HEAD_THREADS / 32);
+    for (long long row = (long long)blockIdx.x * (HEAD_THREADS / 32) + warp; row < mb; row += warps) {
+        const float4 ha4 = hb::ld_stream4(reinterpret_cast<const float4 *>(h3a + (size_t)row * ld_ha) + lane);
+        const float4 hc4 = hb::ld_stream4(reinterpret_cast<const float4 *>(h3c + (size_t)row * ld_hc) + lane);
+        const float ha[4] = {ha4.x, ha4.y, ha4.z, ha4.w}, hc[4] = {hc4.x, hc4.y, hc4.z, hc4.w};
+        float m[NA], v;
+#pragma unroll
+        for (int j = 0; j < NA; ++j) m[j] = ((ha[0] * wa[j][0] + ha[1] * wa[j][1]) + ha[2] * wa[j][2]) + ha[3] * wa[j][3];
+        v = ((hc[0] * wc[0] + hc[1] * wc[1]) + hc[2] * wc[2]) + hc[3] * wc[3];
+#pragma unroll
+        for (int j = 0; j < NA; ++j) m[j] = warp_sum(m[j]) + ba[j];
+        v = warp_sum(v) + bc;
+        HeadLoss o;
+        loss_head_sample(rec + row * HB_PPO_REC, m, v, sig, inv_b, lp, o);
+        // data gradient through the last ELU: elu'(z) = z > 0 ? 1 : elu(z) + 1
+        float da[4], dc[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float acc = 0.0f;
+#pragma unroll
+            for (int j = 0; j < NA; ++j) acc += o.g_mu[j] * wa[j][i];
+            da[i] = acc * (ha[i] > 0.0f ? 1.0f : ha[i] + 1.0f);
+            dc[i] = (o.g_v * wc[i]) * (hc[i] > 0.0f ? 1.0f : hc[i] + 1.0f);
+        }
+        hb::st_stream4(reinterpret_cast<float4 *>(dz3a + (size_t)row * ld_dz) + lane, make_float4(da[0], da[1], da[2], da[3]));
+        hb::st_stream4(reinterpret_cast<float4 *>(dz3c + (size_t)row * ld_dz) + lane, make_float4(dc[0], dc[1], dc[2], dc[3]));
+        // weight / bias gradients of the output layers
+#pragma unroll
+        for (int j = 0; j < NA; ++j) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) ga[j][i] += o.g_mu[j] * ha[i];
+            gba[j] += o.g_mu[j];
+            gstd[j] += o.g_std[j];
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) gc[i] += o.g_v * hc[i];
+        gbc += o.g_v;
+        st[0] += o.st_s, st[1] += o.st_v, st[2] += o.st_k, st[3] += o.st_e;
+    }
+    // CTA reduction in shared memory (8 warps), then one atomic per parameter and CTA
+#pragma unroll
+    for (int j = 0; j < NA; ++j)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) atomicAdd(&s_g[j * (HID + 1) + lane * 4 + i], ga[j][i]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) atomicAdd(&s_g[NA * (HID + 1) + lane * 4 + i], gc[i]);
+    if (lane == 0) {        // per-sample quantities are uniform across the warp: counted once
+#pragma unroll
+        for (int j = 0; j < NA; ++j) {
+            atomicAdd(&s_g[j * (HID + 1) + HID], gba[j]);
+            atomicAdd(&s_dstd[j], gstd[j]);
+        }
+        atomicAdd(&s_g[NA * (HID + 1) + HID], gbc);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) atomicAdd(&s_stat[k], st[k]);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < (NA + 1) * (HID + 1); i += HEAD_THREADS) {
+        const int j = i / (HID + 1), k = i - j * (HID + 1);
+        float *dst = (j < NA) ? g4a + (size_t)j * ld_w + k : g4c + k;
+        atomicAdd(dst, s_g[i]);
+    }
+    if (threadIdx.x < NA) {
+        float s = s_dstd[threadIdx.x];
+        // entropy bonus: -entropy_coef * mean(entropy) -> d/dsigma_j = -coef / sigma_j (added once, by block 0)
+        if (blockIdx.x == 0) s += ent_scale * (-lp.entropy_coef / sig[threadIdx.x]);
+        atomicAdd(d_std + threadIdx.x, s);
+    } else if (threadIdx.x >= 32 && threadIdx.x < 36) {
+        atomicAdd(stats + (threadIdx.x - 32), s_stat[threadIdx.x - 32]);
+    }
+}
+
 __global__ void __launch_bounds__(256)
 act_head_kernel(const float *__restrict__ mu, int ld_mu, const float *__restrict__ stdp, const float *__restrict__ eps,
                 long long n, float *__restrict__ actions, float *__restrict__ logp, float *__restrict__ mu_out,
@@ -266,6 +437,27 @@ int hb_ppo_loss_head(const float *mu, int32_t ld_mu, const float *value, int32_t
         mu, ld_mu, value, ld_v, std, records, mb, 1.0 / (double)mb_global, (float)((double)mb / (double)mb_global), *lp, d_mu,
         d_value, d_std, stats);
     HB_CHECK_LAUNCH("loss_head_kernel");
+    return HB_OK;
+}
+
+int hb_ppo_head_fused(const float *h3_actor, int32_t ld_ha, const float *h3_critic, int32_t ld_hc, const float *w4_actor,
+                      const float *w4_critic, int32_t ld_w, const float *std, const float *records, int64_t mb,
+                      int64_t mb_global, const hb_ppo_loss_params *lp, float *dz3_actor, float *dz3_critic, int32_t ld_dz,
+                      float *g4_actor, float *g4_critic, float *d_std, double *stats, void *stream) {
+    HB_REQUIRE(h3_actor && h3_critic && w4_actor && w4_critic && std && records && lp && dz3_actor && dz3_critic &&
+                   g4_actor && g4_critic && d_std && stats, "hb_ppo_head_fused: null buffer");
+    HB_REQUIRE(mb > 0 && mb_global >= mb, "hb_ppo_head_fused: bad sizes");
+    HB_REQUIRE(ld_ha >= HID + 1 && ld_hc >= HID + 1 && ld_w >= HID + 1 && ld_dz >= HID && ld_ha % 4 == 0 && ld_hc % 4 == 0 &&
+                   ld_w % 4 == 0 && ld_dz % 4 == 0,
+               "hb_ppo_head_fused: rows of %d features (+ ones column), leading dimensions multiples of 4", HID);
+    HB_REQUIRE(hb::aligned16(h3_actor) && hb::aligned16(h3_critic) && hb::aligned16(w4_actor) && hb::aligned16(w4_critic) &&
+                   hb::aligned16(dz3_actor) && hb::aligned16(dz3_critic), "hb_ppo_head_fused: 16-byte aligned buffers");
+    long long blocks = (mb + HEAD_THREADS / 32 - 1) / (HEAD_THREADS / 32);
+    const long long cap = 2ll * hb::sm_count();
+    head_fused_kernel<<<(unsigned)(blocks < cap ? blocks : cap), HEAD_THREADS, 0, (cudaStream_t)stream>>>(
+        h3_actor, ld_ha, h3_critic, ld_hc, w4_actor, w4_critic, ld_w, std, records, mb, 1.0 / (double)mb_global,
+        (float)((double)mb / (double)mb_global), *lp, dz3_actor, dz3_critic, ld_dz, g4_actor, g4_critic, d_std, stats);
+    HB_CHECK_LAUNCH("head_fused_kernel");
     return HB_OK;
 }
 
