@@ -2,13 +2,15 @@
 //
 //   D[M,N] (+)= A[M,K] * B[N,K]^T          fp32 storage, TF32 tensor-core math, fp32 accumulation in TMEM
 //
-// One CTA computes one 128 x BN output tile (optionally one K-split of it):
-//   warp 4      TMA producer: 2-D tiled tensor maps, 128-byte swizzle, NSTAGE-deep mbarrier ring
-//   warp 5      allocates TMEM and issues tcgen05.mma.cta_group::1.kind::tf32 (one elected lane);
-//               tcgen05.commit releases smem stages and finally signals the epilogue
-//   warps 0-3   epilogue: tcgen05.ld the accumulator quarter that belongs to the warp (lane = row) and
-//               apply the fused tail: bias + ELU (forward), ELU' (dgrad), plain store, or atomic
-//               accumulate (split-K wgrad)
+// One CTA computes a sequence of 128 x BN output tiles (optionally K-splits of them):
+//   warp 8      TMA producer: 2-D tiled tensor maps, 128-byte swizzle, NSTAGE-deep mbarrier ring
+//   warp 9      allocates TMEM (two accumulators) and issues tcgen05.mma.cta_group::1.kind::tf32 (one elected
+//               lane); tcgen05.commit releases smem stages and hands finished accumulators to the epilogue
+//   warps 0-7   epilogue: tcgen05.ld the accumulator quarter / column half that belongs to the warp
+//               (lane = row) and apply the fused tail: bias + ELU (forward), ELU' (dgrad), plain store, or
+//               vector red.add (split-K wgrad)
+// The kernel is persistent: one CTA per SM walks a static tile list, so barrier / TMEM setup is paid once and
+// the epilogue of one tile overlaps the main loop of the next.
 //
 // Operand layouts.  "K-major" = the contraction index is contiguous in memory (activations
 // [rows, features] as A, nn.Linear weights [out, in] as B: the forward pass).  "MN-major" = the
@@ -25,7 +27,9 @@ namespace {
 constexpr int BM = 128;           // UMMA M (cta_group::1)
 constexpr int BK = 32;            // floats per k-block = one 128-byte swizzle row
 constexpr int UMMA_K = 8;         // tf32: 32 bytes of K per instruction
-constexpr int GEMM_THREADS = 192;
+constexpr int EPI_WARPS = 8;          // two warps per TMEM lane quarter, each takes half of the tile's columns
+constexpr int PRODUCER_WARP = EPI_WARPS, MMA_WARP = EPI_WARPS + 1;
+constexpr int GEMM_THREADS = (EPI_WARPS + 2) * 32;
 
 enum Epilogue { EPI_STORE = 0, EPI_BIAS = 1, EPI_BIAS_ELU = 2, EPI_ELU_BWD = 3, EPI_ATOMIC = 4 };
 
@@ -118,7 +122,7 @@ __host__ __device__ constexpr int stages_for() { return BN >= 256 ? 4 : (BN >= 1
 constexpr int EPI_TILE_FLOATS = 32 * 33;          // per epilogue warp: one padded 32 x 32 transpose tile
 template <int BN>
 __host__ __device__ constexpr size_t smem_bytes_for() {
-    return (size_t)stages_for<BN>() * (BM * BK * 4 + BN * BK * 4) + 4 * EPI_TILE_FLOATS * 4 + 4 * (BN < 32 ? 32 : BN) * 4 + 1024;
+    return (size_t)stages_for<BN>() * (BM * BK * 4 + BN * BK * 4) + EPI_WARPS * EPI_TILE_FLOATS * 4 + 1024;
 }
 
 // Persistent, warp-specialised: one CTA per SM walks a static list of output tiles
@@ -138,7 +142,6 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t *sa = smem, *sb = smem + NSTAGE * A_BYTES;
     float *epi_smem = reinterpret_cast<float *>(smem + NSTAGE * (A_BYTES + B_BYTES));
-    float *bias_smem = epi_smem + 4 * EPI_TILE_FLOATS;        // [4 warps][ACC_COLS]
     __shared__ __align__(8) uint64_t full_bar[NSTAGE], empty_bar[NSTAGE], acc_full[2], acc_empty[2];
     __shared__ uint32_t tmem_base_smem;
 
@@ -149,11 +152,11 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 #pragma unroll
         for (int s = 0; s < NSTAGE; ++s) hb::mbar_init(&full_bar[s], 1), hb::mbar_init(&empty_bar[s], 1);
 #pragma unroll
-        for (int a = 0; a < 2; ++a) hb::mbar_init(&acc_full[a], 1), hb::mbar_init(&acc_empty[a], 4);
+        for (int a = 0; a < 2; ++a) hb::mbar_init(&acc_full[a], 1), hb::mbar_init(&acc_empty[a], EPI_WARPS);
         hb::fence_mbar_init();
     }
-    if (warp == 4 && lane == 0) prefetch_tmap(&map_a), prefetch_tmap(&map_b);
-    if (warp == 5) tmem_alloc(&tmem_base_smem, TMEM_COLS);
+    if (warp == PRODUCER_WARP && lane == 0) prefetch_tmap(&map_a), prefetch_tmap(&map_b);
+    if (warp == MMA_WARP) tmem_alloc(&tmem_base_smem, TMEM_COLS);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -169,7 +172,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         nkb = min(kb_begin + g.kb_per_split, kb_total) - kb_begin;
     };
 
-    if (warp == 4) {
+    if (warp == PRODUCER_WARP) {
         // ===================== TMA producer =====================
         if (lane == 0) {
             uint32_t it = 0;
@@ -196,7 +199,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 }
             }
         }
-    } else if (warp == 5) {
+    } else if (warp == MMA_WARP) {
         // ===================== MMA issuer =====================
         constexpr uint32_t idesc = make_idesc(BN < 16 ? 16 : BN, A_MN, B_MN);
         uint32_t it = 0, acc_it = 0;
@@ -230,97 +233,108 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             }
         }
     } else {
-        // ===================== epilogue (warps 0-3: TMEM lanes 32*warp .. 32*warp+31) =====================
+        // ===================== epilogue (warps 0-7) =====================
+        // Warp w reads TMEM lanes 32*(w%4) .. +31 (the hardware's lane-quarter rule) and the column half w/4.
         // The accumulator arrives with lane = row.  Global traffic wants lane = column (128-byte rows), so
         // every 32 x 32 block goes through a padded shared-memory tile private to the warp: activations for
         // ELU' come in coalesced, results leave coalesced.
+        const int quarter = warp & 3, half = warp >> 2;
+        constexpr int HALF_COLS = BN >= 64 ? BN / 2 : BN;          // narrow tiles: the second warp of a quarter idles
+        const int c_begin = BN >= 64 ? half * HALF_COLS : 0;
+        const int c_end = (BN >= 64 || half == 0) ? c_begin + HALF_COLS : 0;
         float *tile = epi_smem + warp * EPI_TILE_FLOATS;
-        float *bias_w = bias_smem + warp * ACC_COLS;
         uint32_t acc_it = 0;
         for (int t = blockIdx.x; t < g.total_tiles; t += gridDim.x, ++acc_it) {
             int m0, n0, kb_begin, nkb;
             tile_coords(t, m0, n0, kb_begin, nkb);
             const uint32_t a = acc_it & 1, aph = (acc_it >> 1) & 1;
-            const int mw = m0 + warp * 32;                     // first row of this warp
-            if (EPI == EPI_BIAS || EPI == EPI_BIAS_ELU) {      // the tile's biases, once, while the MMAs run
-                for (int c = lane; c < BN; c += 32)
-                    bias_w[c] = (n0 + c < g.N) ? __ldg(g.bias + (size_t)(n0 + c) * g.bias_stride) : 0.0f;
-                __syncwarp();
+            const int mw = m0 + quarter * 32;                  // first row of this warp
+            if (EPI == EPI_ELU_BWD) {                          // pull the warp's block of H towards L2 meanwhile
+                const int row = mw + lane, n_lo = n0 + c_begin;
+                if (row < g.M && n_lo < g.N) {
+                    const float *hrow = g.H + (size_t)row * g.ldh + n_lo;
+                    const int bytes = min(c_end - c_begin, g.N - n_lo) * 4;
+                    for (int o = 0; o < bytes; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(hrow) + o));
+                }
             }
             hb::mbar_wait(&acc_full[a], aph);
             tc_fence_after();
-            const uint32_t tmem_acc = tmem_base + a * ACC_COLS + ((uint32_t)(warp * 32) << 16);
+            const uint32_t tmem_acc = tmem_base + a * ACC_COLS + ((uint32_t)(quarter * 32) << 16);
 #pragma unroll 1
-            for (int c = 0; c < BN; c += 32) {
+            for (int c = c_begin; c < c_end; c += 32) {
                 const int n = n0 + c;
                 if (n >= g.N || mw >= g.M) break;
-                float v[32];
-                tmem_ld16(tmem_acc + (uint32_t)c, v);
-                if (BN > 16) tmem_ld16(tmem_acc + (uint32_t)(c + 16), v + 16);
                 const int ncols = min(32, g.N - n), nrows = min(32, g.M - mw);
                 const bool col_ok = lane < ncols;
-                if (EPI == EPI_BIAS || EPI == EPI_BIAS_ELU) {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        float x = v[i] + bias_w[c + i];
-                        if (EPI == EPI_BIAS_ELU) x = x > 0.0f ? x : __expf(x) - 1.0f;        // nn.ELU(alpha=1)
-                        v[i] = x;
-                    }
-                } else if (EPI == EPI_ELU_BWD) {
-                    // rows of H, coalesced: 8 lanes x float4 per row, 4 rows per instruction, all 8 loads in flight
-                    const int rr = lane >> 3, c4 = (lane & 7) * 4;
-                    const bool fast = (ncols == 32) && ((g.ldh & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.H) & 15u) == 0);
-                    if (fast) {
-                        float4 h4[8];
+                // readout mapping: 8 lanes x float4 per row, 4 rows per instruction (128-byte row segments)
+                const int rr = lane >> 3, c4 = (lane & 7) * 4;
+                const bool fast = (ncols == 32) && ((g.ldd & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.D) & 15u) == 0) &&
+                                  (EPI != EPI_ELU_BWD || (((g.ldh & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.H) & 15u) == 0)));
+                float4 h4[8];                                  // ELU': forward activations, all loads in flight early
+                float b4[4] = {0.f, 0.f, 0.f, 0.f};           // forward: this lane's four biases
+                if (fast) {
+                    if (EPI == EPI_ELU_BWD) {
 #pragma unroll
                         for (int it = 0; it < 8; ++it) {
                             const int r = it * 4 + rr;
                             h4[it] = (r < nrows) ? __ldg(reinterpret_cast<const float4 *>(g.H + (size_t)(mw + r) * g.ldh + n + c4))
                                                  : make_float4(0.f, 0.f, 0.f, 0.f);
                         }
-#pragma unroll
-                        for (int it = 0; it < 8; ++it) {
-                            float *tt = tile + (it * 4 + rr) * 33 + c4;
-                            tt[0] = h4[it].x, tt[1] = h4[it].y, tt[2] = h4[it].z, tt[3] = h4[it].w;
-                        }
-                    } else {
-                        for (int r = 0; r < nrows; ++r)
-                            tile[r * 33 + lane] = col_ok ? __ldg(g.H + (size_t)(mw + r) * g.ldh + n + lane) : 0.0f;
                     }
-                    __syncwarp();
+                    if (EPI == EPI_BIAS || EPI == EPI_BIAS_ELU) {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        const float h = tile[lane * 33 + i];           // h = elu(z): elu'(z) = z > 0 ? 1 : h + 1
-                        v[i] = v[i] * (h > 0.0f ? 1.0f : h + 1.0f);
+                        for (int k = 0; k < 4; ++k) b4[k] = __ldg(g.bias + (size_t)(n + c4 + k) * g.bias_stride);
                     }
-                    __syncwarp();
                 }
+                float v[32];
+                tmem_ld16(tmem_acc + (uint32_t)c, v);
+                if (BN > 16) tmem_ld16(tmem_acc + (uint32_t)(c + 16), v + 16);
+                // transpose through the warp's padded tile: written with lane = row, read with lane = column group
 #pragma unroll
                 for (int i = 0; i < 32; ++i) tile[lane * 33 + i] = v[i];
                 __syncwarp();
-                const bool fast_out = (ncols == 32) && ((g.ldd & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.D) & 15u) == 0);
-                if (fast_out) {
-                    const int rr = lane >> 3, c4 = (lane & 7) * 4;
+                if (fast) {
 #pragma unroll
                     for (int it = 0; it < 8; ++it) {
                         const int r = it * 4 + rr;
                         if (r < nrows) {
                             const float *tt = tile + r * 33 + c4;
+                            float x[4] = {tt[0], tt[1], tt[2], tt[3]};
+                            if (EPI == EPI_BIAS || EPI == EPI_BIAS_ELU) {
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) {
+                                    x[k] += b4[k];
+                                    if (EPI == EPI_BIAS_ELU) x[k] = x[k] > 0.0f ? x[k] : __expf(x[k]) - 1.0f;   // nn.ELU(alpha=1)
+                                }
+                            } else if (EPI == EPI_ELU_BWD) {    // h = elu(z): elu'(z) = z > 0 ? 1 : h + 1
+                                const float h[4] = {h4[it].x, h4[it].y, h4[it].z, h4[it].w};
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) x[k] *= (h[k] > 0.0f ? 1.0f : h[k] + 1.0f);
+                            }
                             float *dst = g.D + (size_t)(mw + r) * g.ldd + n + c4;
                             if (EPI == EPI_ATOMIC) {      // one 16-byte vector reduction per lane (sm_90+)
-                                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(tt[0]), "f"(tt[1]),
-                                             "f"(tt[2]), "f"(tt[3])
+                                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(x[0]), "f"(x[1]),
+                                             "f"(x[2]), "f"(x[3])
                                              : "memory");
                             } else {
-                                *reinterpret_cast<float4 *>(dst) = make_float4(tt[0], tt[1], tt[2], tt[3]);
+                                *reinterpret_cast<float4 *>(dst) = make_float4(x[0], x[1], x[2], x[3]);
                             }
                         }
                     }
-                } else if (col_ok) {
+                } else if (col_ok) {                           // ragged edge / unaligned: one column per lane
+                    const float bias = (EPI == EPI_BIAS || EPI == EPI_BIAS_ELU) ? __ldg(g.bias + (size_t)(n + lane) * g.bias_stride) : 0.0f;
                     for (int r = 0; r < nrows; ++r) {
+                        float x = tile[r * 33 + lane];
+                        if (EPI == EPI_BIAS || EPI == EPI_BIAS_ELU) {
+                            x += bias;
+                            if (EPI == EPI_BIAS_ELU) x = x > 0.0f ? x : __expf(x) - 1.0f;
+                        } else if (EPI == EPI_ELU_BWD) {
+                            const float h = __ldg(g.H + (size_t)(mw + r) * g.ldh + n + lane);
+                            x *= (h > 0.0f ? 1.0f : h + 1.0f);
+                        }
                         float *dst = g.D + (size_t)(mw + r) * g.ldd + n + lane;
-                        if (EPI == EPI_ATOMIC) atomicAdd(dst, tile[r * 33 + lane]);
-                        else *dst = tile[r * 33 + lane];
+                        if (EPI == EPI_ATOMIC) atomicAdd(dst, x);
+                        else *dst = x;
                     }
                 }
                 __syncwarp();
@@ -332,7 +346,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 5) tmem_dealloc(tmem_base, TMEM_COLS);
+    if (warp == MMA_WARP) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
 // ---- host side --------------------------------------------------------------------------------------
@@ -449,9 +463,18 @@ extern "C" int hb_gemm_tf32(const hb_gemm_desc *d, void *stream) {
     HB_REQUIRE(d->split_k <= 1 || d->epilogue == HB_EPI_ATOMIC_ADD, "hb_gemm_tf32: split-K needs the atomic epilogue");
     HB_REQUIRE(!d->b_mn_major || d->N > 64, "hb_gemm_tf32: MN-major B needs N > 64 (32-wide TMA boxes per 128-byte swizzle row)");
     cudaStream_t st = (cudaStream_t)stream;
-    // tile width: the widest UMMA N that does not waste more than half a tile
+    // tile width: the widest UMMA N that does not waste more than half a tile ...
     if (d->N <= 16) return dispatch_epi<16>(d, st);
     if (d->N <= 64) return dispatch_epi<64>(d, st);
     if (d->N <= 128 || d->tile_n == 128) return dispatch_epi<128>(d, st);
+    if (d->tile_n == 0 && d->split_k <= 1) {
+        // ... unless 128-wide tiles balance better over the SMs: rounds of the persistent tile loop x operand
+        // bytes per tile (proportional to 128 + BN); e.g. M = 24576, N = 256 is 192 tiles = 2 rounds of 148 SMs at
+        // BN = 256 but 3 rounds of half-size tiles at BN = 128
+        const long long sms = hb::sm_count(), tm = (d->M + BM - 1) / BM;
+        const long long t256 = tm * ((d->N + 255) / 256), t128 = tm * ((d->N + 127) / 128);
+        const long long c256 = ((t256 + sms - 1) / sms) * (128 + 256), c128 = ((t128 + sms - 1) / sms) * (128 + 128);
+        if (c128 <= c256) return dispatch_epi<128>(d, st);
+    }
     return dispatch_epi<256>(d, st);
 }
