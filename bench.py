@@ -345,12 +345,11 @@ def run_b200(args, rank, world):
     k_obs = time_launch(lambda st: lib.hb_stack_shift(env._obs[prev].data_ptr(), env._obs[cur].data_ptr(), rb, n,
                                                    STACK_OBS * FRAME_OBS, FRAME_OBS, st))
     k_pd = time_launch(lambda st: lib.hb_env_compute_torques(P, B, st))
-    env.inject_noise(noise_frames[0])
-    env._draw_noise(False)
+    env._draw_noise(False)              # device generator, like the replayed step
     k_post = time_launch(lambda st: lib.hb_env_post_physics(P, B, env._pn, env._obs[cur].data_ptr(), env._priv[cur].data_ptr(),
                                                          _lib.HB_STAGE_STEP, st))
     k_fin = time_launch(lambda st: lib.hb_env_reset_finalize(P, B, env._obs[cur].data_ptr(), env._priv[cur].data_ptr(),
-                                                          env._host_count.data_ptr(), st))
+                                                          env._host_count.data_ptr(), None, st))
     k_stack = time_launch(lambda st: lib.hb_env_stack_observations(P, B, env._obs[prev].data_ptr(), env._priv[prev].data_ptr(),
                                                                 env._obs[cur].data_ptr(), env._priv[cur].data_ptr(), st))
     # GAE
@@ -416,7 +415,7 @@ def run_b200(args, rank, world):
         "config": {"workload": f"hector task, {n} envs per GPU, env.step with stubbed physics (BASELINE configs[1])",
                    "envs_per_gpu": n, "decimation": 10, "frame_stack": 15,
                    "launch": "eager, noise tensors resident in HBM" if args.no_graph else
-                             "CUDA-graph replay (2 graphs/step around the reset-count hand-off), noise drawn on device inside the graph",
+                             "CUDA-graph replay (2 graphs/step around the reset-count hand-off), noise drawn in-kernel (Philox)",
                    "timing": "per-step CUDA events, L2 flushed between steps (256 MiB write then 256 MiB read, outside the events)",
                    "wall_ms_per_step_incl_flush": 1e3 * wall / args.steps},
         "clocks": clocks,

@@ -145,7 +145,10 @@ typedef struct hb_env_buffers {
     double *scratch_sums;
 } hb_env_buffers;
 
-/* Per-step random draws, indexed by env (NULL = that draw is not needed / treated as 0). */
+/* Per-step random draws, indexed by env.  A NULL pointer means: drawn on the device where it is consumed, if
+ * rng_counter is set (Philox4x32-10, key = rng_seed, counter = (env, slot, *rng_counter); the tensors the
+ * reference would have drawn with torch.rand / randn are never materialised); otherwise treated as 0 /
+ * "no such draw".  hb_env_reset_finalize advances *rng_counter once per call sequence. */
 typedef struct hb_env_noise {
     const float *u_delay;           /* [N]    torch.rand((N,1))            hector_env.py:166 */
     const float *z_action;          /* [N,ndof] torch.randn_like(actions)  hector_env.py:168 */
@@ -153,6 +156,8 @@ typedef struct hb_env_noise {
     const float *u_push;            /* [N,5]  push lin xy + ang xyz        hector_env.py:58-63 */
     const float *u_reset;           /* [N,15] dof(10) root xy(2) cmd(3)    legged_robot.py:366,384,327-330 */
     const float *z_obs;             /* [N,41] torch.randn_like(obs_buf)    hector_env.py:241 */
+    const uint64_t *rng_counter;    /* [1] device: step counter of the device generator, or NULL */
+    uint64_t rng_seed;
 } hb_env_noise;
 
 /* stage mask for hb_env_post_physics */
@@ -208,9 +213,10 @@ int hb_env_stack_observations(const hb_env_params *p, const hb_env_buffers *buf,
  *   episode_means (extras["episode"], :198-201) and time_outs_latched (extras["time_outs"], :208-209),
  *   both only refreshed on steps with >= 1 reset like the reference;
  *   slots 0..S-2 of obs_new/priv_new zeroed for the reset envs (pass NULL for both to skip: reset_idx
- *   called outside step()). */
+ *   called outside step());
+ *   *rng_counter += 1 if the device generator is in use (the same pointer as hb_env_noise.rng_counter), else NULL. */
 int hb_env_reset_finalize(const hb_env_params *p, const hb_env_buffers *buf, float *obs_new, float *priv_new,
-                          int32_t *host_count, void *stream);
+                          int32_t *host_count, uint64_t *rng_counter, void *stream);
 
 /* One frame-stack shift on its own: next[:, 0:row-frame] = prev[:, frame:row] (zeros for envs whose
  * reset_buf byte is set, if reset_buf is not NULL); next[:, row-frame:row] is left alone. */

@@ -77,7 +77,7 @@ _NOISE_FIELDS = ("u_delay", "z_action", "u_cmd", "u_push", "u_reset", "z_obs")
 
 
 class EnvNoise(C.Structure):
-    _fields_ = [(name, _fp) for name in _NOISE_FIELDS]
+    _fields_ = [(name, _fp) for name in _NOISE_FIELDS] + [("rng_counter", _fp), ("rng_seed", C.c_uint64)]
 
 
 HB_EPI_STORE, HB_EPI_BIAS, HB_EPI_BIAS_ELU, HB_EPI_ELU_BWD, HB_EPI_ATOMIC_ADD = range(5)
@@ -121,7 +121,7 @@ _SIGNATURES = {
     "hb_env_post_physics": (C.c_int, [C.POINTER(EnvParams), C.POINTER(EnvBuffers), C.POINTER(EnvNoise), _fp, _fp,
                                       C.c_int32, _fp]),
     "hb_env_stack_observations": (C.c_int, [C.POINTER(EnvParams), C.POINTER(EnvBuffers), _fp, _fp, _fp, _fp, _fp]),
-    "hb_env_reset_finalize": (C.c_int, [C.POINTER(EnvParams), C.POINTER(EnvBuffers), _fp, _fp, _fp, _fp]),
+    "hb_env_reset_finalize": (C.c_int, [C.POINTER(EnvParams), C.POINTER(EnvBuffers), _fp, _fp, _fp, _fp, _fp]),
     "hb_stack_shift": (C.c_int, [_fp, _fp, _fp, C.c_int32, C.c_int32, C.c_int32, _fp]),
     "hb_gemm_tf32": (C.c_int, [C.POINTER(GemmDesc), _fp]),
     "hb_ppo_gather_rows": (C.c_int, [_fp, C.c_int32, _fp, C.c_int32, _fp, C.c_int64, C.c_int32, C.c_int32, _fp]),

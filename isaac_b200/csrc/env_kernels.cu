@@ -65,18 +65,90 @@ __device__ __forceinline__ float py_mod(float a, float m) {
 __device__ __forceinline__ float clampf(float v, float lo, float hi) { return fminf(fmaxf(v, lo), hi); }
 
 // ------------------------------------------------------------------------------------------
+// Device-side draws.  When the caller supplies no tape for a draw, it is generated
+// where it is consumed with Philox4x32-10 (the generator behind torch.rand / curand): key = the env's seed,
+// counter = (env, slot, step), so a draw is a pure function of (seed, step, env, slot) - no state besides
+// the step counter, no tape written to or read from HBM, and rare draws (resets, command resampling,
+// pushes) cost nothing on the steps that do not need them.  Slots of one env and step:
+//   0-2 z_action[10] | 3-13 z_obs[41] | 14-17 u_reset[15] | 18 u_cmd[3] | 19-20 u_push[5] | 21 u_delay
+// ------------------------------------------------------------------------------------------
+struct Rng {
+    uint32_t k0, k1, s0, s1;
+    bool on;
+};
+__device__ __forceinline__ Rng make_rng(const hb_env_noise &nz) {
+    Rng r;
+    r.on = nz.rng_counter != nullptr;
+    const unsigned long long step = r.on ? *nz.rng_counter : 0ull;
+    r.k0 = (uint32_t)nz.rng_seed, r.k1 = (uint32_t)(nz.rng_seed >> 32);
+    r.s0 = (uint32_t)step, r.s1 = (uint32_t)(step >> 32);
+    return r;
+}
+constexpr int SLOT_Z_ACTION = 0, SLOT_Z_OBS = 3, SLOT_U_RESET = 14, SLOT_U_CMD = 18, SLOT_U_PUSH = 19, SLOT_U_DELAY = 21;
+
+__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+        const uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+        c0 = h1 ^ c1 ^ k0, c1 = l1, c2 = h0 ^ c3 ^ k1, c3 = l0;
+        k0 += 0x9E3779B9u, k1 += 0xBB67AE85u;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
+__device__ __forceinline__ void rng_uniform4(const Rng &g, int env, int slot, float u[4]) {      // [0, 1)
+    const uint4 x = philox4x32_10((uint32_t)env, (uint32_t)slot, g.s0, g.s1, g.k0, g.k1);
+    u[0] = (float)(x.x >> 8) * 5.9604644775390625e-8f, u[1] = (float)(x.y >> 8) * 5.9604644775390625e-8f;
+    u[2] = (float)(x.z >> 8) * 5.9604644775390625e-8f, u[3] = (float)(x.w >> 8) * 5.9604644775390625e-8f;
+}
+__device__ __forceinline__ void rng_normal4(const Rng &g, int env, int slot, float z[4]) {       // Box-Muller
+    const uint4 x = philox4x32_10((uint32_t)env, (uint32_t)slot, g.s0, g.s1, g.k0, g.k1);
+    const float u0 = (float)((x.x >> 8) + 1u) * 5.9604644775390625e-8f, u1 = (float)((x.z >> 8) + 1u) * 5.9604644775390625e-8f;
+    const float r0 = sqrtf(-2.0f * __logf(u0)), r1 = sqrtf(-2.0f * __logf(u1));
+    float s0, c0, s1, c1;
+    __sincosf(TWO_PI_F * ((float)(x.y >> 8) * 5.9604644775390625e-8f), &s0, &c0);
+    __sincosf(TWO_PI_F * ((float)(x.w >> 8) * 5.9604644775390625e-8f), &s1, &c1);
+    z[0] = r0 * c0, z[1] = r0 * s0, z[2] = r1 * c1, z[3] = r1 * s1;
+}
+// element `idx` of a per-env vector of uniforms that starts at `slot`
+__device__ __forceinline__ void rng_uniforms(const Rng &g, int env, int slot, int first, int count, float *out) {
+    for (int c = first / 4; c <= (first + count - 1) / 4; ++c) {
+        float u[4];
+        rng_uniform4(g, env, slot + c, u);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int idx = c * 4 + k - first;
+            if (idx >= 0 && idx < count) out[idx] = u[k];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // a2: HectorFreeEnv.step prologue (hector_env.py:158-169, legged_robot.py:90-91)
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-action_prologue_kernel(const float *__restrict__ a_in, float *__restrict__ actions, const float *__restrict__ u_delay,
-                       const float *__restrict__ z_action, int total, float clip, float action_delay,
-                       float action_noise) {
+action_prologue_kernel(const float *__restrict__ a_in, float *__restrict__ actions, const __grid_constant__ hb_env_noise nz,
+                       int total, float clip, float action_delay, float action_noise) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
+    const Rng rng = make_rng(nz);
+    const int env = i / NDOF, j = i - env * NDOF;
     float a = clampf(a_in[i], -clip, clip);
-    const float delay = (u_delay ? u_delay[i / NDOF] : 0.0f) * action_delay;
+    float ud = 0.0f;
+    if (action_delay != 0.0f) {
+        if (nz.u_delay) ud = nz.u_delay[env];
+        else if (rng.on) rng_uniforms(rng, env, SLOT_U_DELAY, 0, 1, &ud);
+    }
+    const float delay = ud * action_delay;
     a = (1.0f - delay) * a + delay * actions[i];
-    const float z = z_action ? z_action[i] : 0.0f;
+    float z = 0.0f;
+    if (nz.z_action) {
+        z = nz.z_action[i];
+    } else if (rng.on && action_noise != 0.0f) {
+        float z4[4];
+        rng_normal4(rng, env, SLOT_Z_ACTION + (j >> 2), z4);
+        z = z4[j & 3];
+    }
     a = a + (action_noise * z) * a;
     actions[i] = clampf(a, -clip, clip);
 }
@@ -240,7 +312,9 @@ post_physics_kernel(const __grid_constant__ hb_env_params p, const __grid_consta
     const bool do_step = stages & HB_STAGE_STEP;
     const bool derive = do_step || (stages & HB_STAGE_DERIVE);
     const bool emit_obs = do_step || (stages & HB_STAGE_OBS);
-    const bool with_noise = p.add_noise && nz.z_obs != nullptr;
+    const Rng rng = make_rng(nz);
+    const bool with_noise = p.add_noise && (nz.z_obs != nullptr || rng.on);
+    const bool tape_noise = p.add_noise && nz.z_obs != nullptr;
     HB_STAMP(0);
     HB_GT(0);
     const TileLayout L = make_layout(p.num_bodies, with_noise);
@@ -264,7 +338,7 @@ post_physics_kernel(const __grid_constant__ hb_env_params p, const __grid_consta
     if (bulk && threadIdx.x == 0) {
         hb::mbar_init(&bar, 1);
         hb::fence_mbar_init();
-        hb::mbar_expect_tx(&bar, TILE * 4u * (13 + 2 * NDOF + crow + 5 * NDOF + 6 + 4 + (with_noise ? OBS : 0)));
+        hb::mbar_expect_tx(&bar, TILE * 4u * (13 + 2 * NDOF + crow + 5 * NDOF + 6 + 4 + (tape_noise ? OBS : 0)));
     }
     auto stage = [&](const float *src, int dst, int row) {
         if (bulk) {
@@ -284,7 +358,7 @@ post_physics_kernel(const __grid_constant__ hb_env_params p, const __grid_consta
     stage(b.torques + e0 * NDOF, L.torques, NDOF);
     stage(b.last_root_vel + e0 * 6, L.last_root_vel, 6);
     stage(b.commands + e0 * 4, L.commands, 4);
-    if (with_noise) stage(nz.z_obs + e0 * OBS, L.z_obs, OBS);
+    if (tape_noise) stage(nz.z_obs + e0 * OBS, L.z_obs, OBS);
 
     __syncthreads();                             // mbarrier init / plain staging visible to every warp
     // Each role first issues its own global loads (they overlap the bulk copies), then waits for the tile.
@@ -321,8 +395,10 @@ post_physics_kernel(const __grid_constant__ hb_env_params p, const __grid_consta
         if (do_step) {
             ep_len += 1;
             // -------- _post_physics_step_callback, legged_robot.py:303-335 --------
-            if (valid && (ep_len % p.resample_interval) == 0 && nz.u_cmd) {
-                const float *u = nz.u_cmd + (size_t)env * 3;
+            if (valid && (ep_len % p.resample_interval) == 0 && (nz.u_cmd || rng.on)) {
+                float u[3];
+                if (nz.u_cmd) u[0] = nz.u_cmd[(size_t)env * 3], u[1] = nz.u_cmd[(size_t)env * 3 + 1], u[2] = nz.u_cmd[(size_t)env * 3 + 2];
+                else rng_uniforms(rng, env, SLOT_U_CMD, 0, 3, u);
                 cmd[0] = p.cmd_span[0] * u[0] + p.cmd_lo[0];
                 cmd[1] = p.cmd_span[1] * u[1] + p.cmd_lo[1];
                 cmd[3] = p.cmd_span[2] * u[2] + p.cmd_lo[2];
@@ -336,8 +412,14 @@ post_physics_kernel(const __grid_constant__ hb_env_params p, const __grid_consta
                 e = e - TWO_PI_F * ((e > PI_F) ? 1.0f : 0.0f);
                 cmd[2] = clampf(0.5f * e, -1.0f, 1.0f);
             }
-            if ((stages & HB_STAGE_PUSH) && valid && nz.u_push) {       // _push_robots, hector_env.py:53-68
-                const float *u = nz.u_push + (size_t)env * 5;
+            if ((stages & HB_STAGE_PUSH) && valid && (nz.u_push || rng.on)) {       // _push_robots, hector_env.py:53-68
+                float u[5];
+                if (nz.u_push) {
+#pragma unroll
+                    for (int k = 0; k < 5; ++k) u[k] = nz.u_push[(size_t)env * 5 + k];
+                } else {
+                    rng_uniforms(rng, env, SLOT_U_PUSH, 0, 5, u);
+                }
                 push_f[0] = p.push_lin_span * u[0] + p.push_lin_lo;
                 push_f[1] = p.push_lin_span * u[1] + p.push_lin_lo;
                 root[7] = push_f[0], root[8] = push_f[1];
@@ -377,7 +459,13 @@ post_physics_kernel(const __grid_constant__ hb_env_params p, const __grid_consta
         const bool reset = valid && (flags[lane] & 1);
         const float gs = reset ? 0.0f : sm[L.gait_s + lane], gc = reset ? 1.0f : sm[L.gait_c + lane];
         if (reset) {         // _reset_root_states + _resample_commands + the gravity/euler fix-up (:373-396,321-335,211-214)
-            const float *u = nz.u_reset + (size_t)env * 15;
+            float u[15];
+            if (nz.u_reset) {
+#pragma unroll
+                for (int k = 10; k < 15; ++k) u[k] = nz.u_reset[(size_t)env * 15 + k];
+            } else {
+                rng_uniforms(rng, env, SLOT_U_RESET, 10, 5, u + 10);
+            }
 #pragma unroll
             for (int k = 0; k < 13; ++k) root[k] = p.base_init_state[k];
 #pragma unroll
@@ -497,7 +585,13 @@ post_physics_kernel(const __grid_constant__ hb_env_params p, const __grid_consta
         HB_STAMP(3);
         const bool reset = valid && (flags[lane] & 1);
         if (reset) {         // _reset_dofs (legged_robot.py:358-372) + buffer zeroing (:186-191)
-            const float *u = nz.u_reset + (size_t)env * 15;
+            float u[NDOF];
+            if (nz.u_reset) {
+#pragma unroll
+                for (int j = 0; j < NDOF; ++j) u[j] = nz.u_reset[(size_t)env * 15 + j];
+            } else {
+                rng_uniforms(rng, env, SLOT_U_RESET, 0, NDOF, u);
+            }
 #pragma unroll
             for (int j = 0; j < NDOF; ++j) {
                 q[j] = p.default_dof_pos[j] + (p.reset_dof_span * u[j] + p.reset_dof_lo);
@@ -669,6 +763,23 @@ post_physics_kernel(const __grid_constant__ hb_env_params p, const __grid_consta
         float sums[HB_NUM_REWARDS];
 #pragma unroll
         for (int k = 0; k < HB_NUM_REWARDS; ++k) sums[k] = valid ? b.episode_sums[(size_t)k * N + env] : 0.0f;
+        if (with_noise && !tape_noise && emit_obs) {
+            // the tile's observation noise, drawn by this otherwise idle warp while the other roles are in phase A:
+            // 11 Philox calls of 4 normals per env; calls whose four columns all have zero noise scale are skipped
+            constexpr int CALLS = (OBS + 3) / 4;
+            float *z = sm + L.z_obs;
+            for (int c = lane; c < nv * CALLS; c += 32) {
+                const int e = c / CALLS, q = c - e * CALLS;
+                bool any = false;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) any = any || (q * 4 + k < OBS && p.noise_scale_vec[q * 4 + k] != 0.0f);
+                float z4[4] = {0.f, 0.f, 0.f, 0.f};
+                if (any) rng_normal4(rng, env0 + e, SLOT_Z_OBS + q, z4);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (q * 4 + k < OBS) z[e * OBS + q * 4 + k] = z4[k];
+            }
+        }
         HB_STAMP(2);
         tile_barrier();                                           // ---- barrier 1 ----
         HB_STAMP(3);
@@ -881,7 +992,7 @@ __device__ __forceinline__ int block_sum(int v, int *scratch) {        // all th
 __global__ void __launch_bounds__(FIN_THREADS)
 reset_finalize_kernel(const __grid_constant__ hb_env_params p, const __grid_constant__ hb_env_buffers b,
                       float *__restrict__ obs_new, float *__restrict__ priv_new, int tiles, int seg,
-                      int32_t *host_count) {
+                      int32_t *host_count, unsigned long long *rng_counter) {
     __shared__ int scratch[FIN_THREADS / 32];
     __shared__ int wbase[FIN_THREADS / 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -928,6 +1039,7 @@ reset_finalize_kernel(const __grid_constant__ hb_env_params p, const __grid_cons
         if (threadIdx.x == 0) {
             *b.reset_count = total;
             if (host_count) *host_count = total;
+            if (rng_counter) *rng_counter += 1ull;       // the next call draws from a fresh counter
         }
         if (threadIdx.x < HB_NUM_REWARDS) {
             const int k = threadIdx.x;
@@ -1024,9 +1136,9 @@ int hb_env_action_prologue(const hb_env_params *p, const hb_env_buffers *buf, co
     if (int rc = check_params(p, buf, "hb_env_action_prologue")) return rc;
     HB_REQUIRE(actions_in && buf->actions, "hb_env_action_prologue: null actions");
     const int total = p->num_envs * p->num_dof;
+    hb_env_noise none = {};
     action_prologue_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
-        actions_in, buf->actions, noise ? noise->u_delay : nullptr, noise ? noise->z_action : nullptr, total,
-        p->clip_actions, p->action_delay, p->action_noise);
+        actions_in, buf->actions, noise ? *noise : none, total, p->clip_actions, p->action_delay, p->action_noise);
     HB_CHECK_LAUNCH("action_prologue_kernel");
     return HB_OK;
 }
@@ -1066,9 +1178,9 @@ int hb_env_post_physics(const hb_env_params *p, const hb_env_buffers *buf, const
     HB_REQUIRE(p->num_bodies > 0 && p->num_bodies <= 32, "hb_env_post_physics: num_bodies out of range");
     HB_REQUIRE(p->n_term >= 0 && p->n_term <= HB_MAX_CONTACT_BODIES && p->n_pen >= 0 &&
                    p->n_pen <= HB_MAX_CONTACT_BODIES, "hb_env_post_physics: too many contact bodies");
-    HB_REQUIRE(noise->u_reset, "hb_env_post_physics: u_reset is required (any env may reset)");
+    HB_REQUIRE(noise->u_reset || noise->rng_counter, "hb_env_post_physics: u_reset or the device generator is required (any env may reset)");
     HB_REQUIRE(buf->scratch_ballots && buf->scratch_sums, "hb_env_post_physics: null scratch buffers");
-    const bool with_noise = p->add_noise && noise->z_obs;
+    const bool with_noise = p->add_noise && (noise->z_obs || noise->rng_counter);
     const TileLayout L = make_layout(p->num_bodies, with_noise);
     const size_t smem = (size_t)L.total * sizeof(float);
     const int tiles = (p->num_envs + TILE - 1) / TILE;
@@ -1080,7 +1192,7 @@ int hb_env_post_physics(const hb_env_params *p, const hb_env_buffers *buf, const
     bool all_aligned = true;
     for (const void *s : slabs) all_aligned = all_aligned && hb::aligned16(s);
     HB_REQUIRE(all_aligned, "hb_env_post_physics: state tensors must be 16-byte aligned");
-    if (with_noise && !hb::aligned16(noise->z_obs)) bulk = false;      // caller-supplied draws at an odd offset: plain loads
+    if (p->add_noise && noise->z_obs && !hb::aligned16(noise->z_obs)) bulk = false;      // caller-supplied draws at an odd offset: plain loads
     static bool attr_set[2] = {false, false};
     if (bulk) {
         if (!attr_set[1]) {
@@ -1150,7 +1262,7 @@ int hb_env_stack_observations(const hb_env_params *p, const hb_env_buffers *buf,
 }
 
 int hb_env_reset_finalize(const hb_env_params *p, const hb_env_buffers *buf, float *obs_new, float *priv_new,
-                          int32_t *host_count, void *stream) {
+                          int32_t *host_count, uint64_t *rng_counter, void *stream) {
     if (int rc = check_params(p, buf, "hb_env_reset_finalize")) return rc;
     HB_REQUIRE(buf->scratch_ballots && buf->scratch_sums && buf->reset_env_ids && buf->reset_count && buf->episode_means,
                "hb_env_reset_finalize: null scratch/result buffers");
@@ -1160,7 +1272,8 @@ int hb_env_reset_finalize(const hb_env_params *p, const hb_env_buffers *buf, flo
     int seg = (tiles + hb::sm_count() - 1) / hb::sm_count();
     if (seg < 8) seg = 8;
     const int grid = (tiles + seg - 1) / seg;
-    reset_finalize_kernel<<<grid, FIN_THREADS, 0, (cudaStream_t)stream>>>(*p, *buf, obs_new, priv_new, tiles, seg, host_count);
+    reset_finalize_kernel<<<grid, FIN_THREADS, 0, (cudaStream_t)stream>>>(
+        *p, *buf, obs_new, priv_new, tiles, seg, host_count, reinterpret_cast<unsigned long long *>(rng_counter));
     HB_CHECK_LAUNCH("reset_finalize_kernel");
     return HB_OK;
 }

@@ -257,8 +257,8 @@ class HectorFreeEnvB200:
         self._graphs = None
         self._last_means_slot = None
         self._injected = initial_noise      # draws consumed by the constructor's reset_idx(all)
-        self._rng = torch.Generator(device=dev)
-        self._rng.manual_seed(0)
+        self._rng_seed = int(getattr(cfg, "seed", 1)) & 0xFFFFFFFFFFFFFFFF
+        self._rng_counter = torch.zeros(1, dtype=torch.int64, device=dev)
         self._b = EnvBuffers()
         self._nz = EnvNoise()
         self._bind_buffers()
@@ -300,26 +300,30 @@ class HectorFreeEnvB200:
         self._injected = frame
 
     def _draw_noise(self, push: bool):
-        N, nz = self.num_envs, self._nz
+        """Bind the draws of the next launch sequence: the injected tape if there is one, otherwise the device
+        generator (Philox keyed by `self._rng_seed`, counter in `self._rng_counter`): the tensors the reference
+        draws with torch.rand / randn_like (hector_env.py:166,168,241; legged_robot.py:327-332,366,384) are never
+        materialised."""
+        nz = self._nz
         if self._injected is not None:
             f = self._injected
             self._noise_keepalive = f
             nz.u_delay, nz.z_action = f.u_delay.data_ptr(), f.z_action.data_ptr()
             nz.u_cmd, nz.u_push, nz.u_reset, nz.z_obs = (f.u_cmd.data_ptr(), f.u_push.data_ptr(),
                                                          f.u_reset.data_ptr(), f.z_obs.data_ptr())
+            nz.rng_counter = None
             return
-        dev = self.device
-        nu = 18 + (5 if push else 0) + (1 if self._p.action_delay != 0.0 else 0)
-        u = torch.rand(N * nu, device=dev, generator=self._rng)
-        zn = torch.randn(N * 51, device=dev, generator=self._rng)
-        self._noise_keepalive = (u, zn)
-        base = u.data_ptr()
-        nz.u_reset, nz.u_cmd = base, base + N * 15 * 4
-        off = N * 18
-        nz.u_push = base + off * 4 if push else None
-        off += N * 5 if push else 0
-        nz.u_delay = base + off * 4 if self._p.action_delay != 0.0 else None
-        nz.z_action, nz.z_obs = zn.data_ptr(), zn.data_ptr() + N * 10 * 4
+        self._bind_device_rng(nz)
+
+    def _bind_device_rng(self, nz):
+        nz.u_delay = nz.z_action = nz.u_cmd = nz.u_push = nz.u_reset = nz.z_obs = None
+        nz.rng_counter, nz.rng_seed = self._rng_counter.data_ptr(), self._rng_seed
+
+    def seed(self, seed: int) -> None:
+        """Seed of the device generator (the reference seeds torch globally, helpers.py:95-106)."""
+        self._rng_seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+        self._rng_counter.zero_()
+        self._nz.u_reset = self._nz.rng_counter = None
 
     # ------------------------------------------------------------------ the hot path
     def step(self, actions: torch.Tensor):
@@ -352,7 +356,7 @@ class HectorFreeEnvB200:
     def enable_cuda_graph(self):
         """Capture the step's launch sequence for physics stages that need no host work between the
         decimation sub-steps (`physics.capturable`, e.g. the synthetic stage used by tests and bench.py).
-        Two graphs per ping-pong parity: A = noise draws, action prologue, first PD launch; then the host
+        Two graphs per ping-pong parity: A = action prologue, first PD launch; then the host
         hands the previous step's reset ids to the physics stage (legged_robot.py:370-372,394-396) while A
         runs; B = the remaining PD launches, post-physics, the frame-stack shift and the reset finalisation.  Push steps (every
         `push_interval`) and steps with injected noise take the eager path."""
@@ -374,13 +378,8 @@ class HectorFreeEnvB200:
             ga, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
             with torch.cuda.graph(ga, pool=pool):
                 st = self._stream()
-                u = torch.rand(N * (19 if self._p.action_delay != 0.0 else 18), device=self.device)
-                zn = torch.randn(N * 51, device=self.device)
                 nz = EnvNoise()
-                base = u.data_ptr()
-                nz.u_reset, nz.u_cmd = base, base + N * 15 * 4
-                nz.u_delay = base + N * 18 * 4 if self._p.action_delay != 0.0 else None
-                nz.z_action, nz.z_obs = zn.data_ptr(), zn.data_ptr() + N * 10 * 4
+                self._bind_device_rng(nz)
                 _lib.check(lib.hb_env_action_prologue(self._pp, self._pb, self._g_actions.data_ptr(), C.byref(nz), st),
                            "hb_env_action_prologue")
                 _lib.check(lib.hb_env_compute_torques(self._pp, self._pb, st), "hb_env_compute_torques")
@@ -393,13 +392,13 @@ class HectorFreeEnvB200:
                 self._b.episode_means = self._g_means[cur].data_ptr()
                 self._b.episode_means_prev = self._g_means[prev].data_ptr()
                 self._launch_post_kernels(HB_STAGE_STEP, C.byref(nz), prev, cur, True, st)
-            graphs[parity] = (ga, gb, u, zn)
+            graphs[parity] = (ga, gb, nz)
         self._cur, self._step_index, self._pending_event = saved
         self._graphs = graphs
         self.graph_launches_per_step = 1 + dec + 3     # this library's kernels per replayed step (prologue, PD, post, stack, finalize)
 
     def _step_graph(self, actions):
-        ga, gb, _, _ = self._graphs[self._cur]
+        ga, gb, _ = self._graphs[self._cur]
         self._g_actions.copy_(actions, non_blocking=True)
         slot = self._step_index % _EXTRAS_RING
         if self._step_index > 0 and self._last_means_slot is not None:
@@ -433,7 +432,7 @@ class HectorFreeEnvB200:
 
     def _launch_post(self, stages: int):
         lib, st = self._lib, self._stream()
-        if self._nz.u_reset is None:
+        if self._nz.u_reset is None and self._nz.rng_counter is None:
             self._draw_noise(False)
         prev, cur = self._cur, self._cur ^ 1
         emit = bool(stages & (HB_STAGE_STEP | HB_STAGE_OBS))
@@ -454,7 +453,7 @@ class HectorFreeEnvB200:
         self._last_means_slot = slot
         self._step_index += 1
         self._injected = None
-        self._nz.u_reset = None
+        self._nz.u_reset = self._nz.rng_counter = None
 
     def _launch_post_kernels(self, stages, noise_ref, prev, cur, emit, st):
         """post-physics -> frame-stack shift -> reset finalisation, on one stream."""
@@ -466,9 +465,10 @@ class HectorFreeEnvB200:
             _lib.check(lib.hb_env_stack_observations(self._pp, self._pb, self._obs[prev].data_ptr(),
                                                      self._priv[prev].data_ptr(), obs_new, priv_new, st),
                        "hb_env_stack_observations")
+        noise = noise_ref._obj          # the EnvNoise behind the byref
         _lib.check(lib.hb_env_reset_finalize(self._pp, self._pb, obs_new if emit else None,
-                                             priv_new if emit else None, self._host_count.data_ptr(), st),
-                   "hb_env_reset_finalize")
+                                             priv_new if emit else None, self._host_count.data_ptr(),
+                                             noise.rng_counter, st), "hb_env_reset_finalize")
 
     def _apply_pending_resets(self):
         """The two opaque calls of _reset_dofs/_reset_root_states (legged_robot.py:370-372,394-396) need

@@ -202,26 +202,20 @@ def test_reset_then_step_matches_reference_reset(lib, cuda_device):
 
 def test_cuda_graph_replay_equals_eager(lib, cuda_device):
     """The captured step (2 graphs per ping-pong parity) must produce exactly what the eager launches
-    produce from the same state and the same draws."""
-    import copy
-    from isaac_b200.synthetic import NoiseFrame
+    produce from the same state and the same draws (both envs use the device generator: same seed, same
+    step counter -> same draws)."""
     dev = cuda_device
     n = 512
     tape = make_tape(n, 6, seed=21, fall_prob=0.02)
     env_g, phys_g = make_cuda_env(tape, dev)
     env_e, phys_e = make_cuda_env(tape, dev)
+    env_g.seed(9), env_e.seed(9)
     env_g.enable_cuda_graph()
     for t in range(1, 6):
         fr = tape.physics[t].to(dev)
         phys_g.load_frame(fr), phys_e.load_frame(fr)
         actions = tape.noise[t].actions.to(dev)
-        parity = env_g._cur
         out_g = env_g.step(actions)
-        _, _, u, zn = env_g._graphs[parity]
-        nz = NoiseFrame(actions=actions, u_delay=torch.zeros(n, 1, device=dev), z_action=zn[:n * 10].view(n, 10),
-                        u_cmd=u[n * 15:n * 18].view(n, 3), u_push=torch.zeros(n, 5, device=dev),
-                        u_reset=u[:n * 15].view(n, 15), z_obs=zn[n * 10:].view(n, 41))
-        env_e.inject_noise(nz)
         out_e = env_e.step(actions)
         torch.cuda.synchronize()
         for a, b, name in zip(out_g[:4], out_e[:4], ("obs", "priv", "rew", "reset")):
@@ -233,3 +227,45 @@ def test_cuda_graph_replay_equals_eager(lib, cuda_device):
         assert torch.equal(env_g._episode_sums, env_e._episode_sums)
     env_g._apply_pending_resets()
     assert phys_g.calls["set_dof_state_indexed"] >= 1
+
+
+def test_device_generator_draws(lib, cuda_device):
+    """The env's own draws (no injected tape): Philox in-kernel.  The observation noise must be N(0, 1) scaled by
+    noise_scale_vec * noise_level on the noisy columns and absent elsewhere, independent across envs and steps,
+    and a pure function of (seed, step): two envs with the same seed agree bit for bit, another seed does not."""
+    n, dev = 4096, cuda_device
+    tape = make_tape(n, 3, seed=77, fall_prob=0.0)
+    tape.statics.episode_length0.fill_(10)           # no time-outs, no resampling: the newest frame is a pure function of the state
+    cfg = HectorCfg()
+
+    def run(seed, noise):
+        c = HectorCfg()
+        c.noise.add_noise = noise
+        env, phys = make_cuda_env(tape, dev, cfg=c)
+        env.seed(seed)
+        frames = []
+        for t in (1, 2):
+            phys.load_frame(tape.physics[t].to(dev))
+            obs = env.step(tape.noise[t].actions.to(dev))[0]
+            frames.append(obs[:, -41:].clone())
+        return torch.stack(frames)
+
+    clean = run(1, False)
+    a, b, c = run(1, True), run(1, True), run(2, True)
+    assert torch.equal(a, b), "same seed, same step counter -> same draws"
+    assert not torch.equal(a, c)
+    scale = torch.tensor(list(make_cuda_env(tape, dev)[0]._p.noise_scale_vec[:41]), device=dev) * cfg.noise.noise_level
+    noisy = scale > 0
+    # action noise (domain_rand.action_noise) perturbs the action columns of both runs identically? no: the clean run has
+    # add_noise off but the same action noise, so the action columns (scale 0) must agree exactly
+    resid = a - clean
+    assert torch.equal(resid[:, :, ~noisy], torch.zeros_like(resid[:, :, ~noisy]))
+    z = resid[:, :, noisy] / scale[noisy]
+    assert abs(z.mean().item()) < 0.01 and abs(z.std().item() - 1.0) < 0.01
+    assert abs((z ** 4).mean().item() - 3.0) < 0.15                       # kurtosis of a normal
+    z0, z1 = z[0].flatten(), z[1].flatten()
+    assert abs(torch.corrcoef(torch.stack((z0, z1)))[0, 1].item()) < 0.01   # step to step
+    cols = z[0]
+    cc = torch.corrcoef(cols.T)
+    assert (cc - torch.eye(cc.shape[0], device=dev)).abs().max().item() < 0.08   # column to column (n = 4096)
+    assert abs(torch.corrcoef(torch.stack((cols[:-1, 0], cols[1:, 0])))[0, 1].item()) < 0.06   # env to env
