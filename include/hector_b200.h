@@ -267,6 +267,9 @@ typedef struct hb_gemm_desc {
     int32_t tile_n;              /* 0 = automatic; 128 forces 128-wide tiles */
 } hb_gemm_desc;
 int hb_gemm_tf32(const hb_gemm_desc *desc, void *stream);
+/* 256-wide tiles are computed by pairs of CTAs (tcgen05.mma.cta_group::2, 2-CTA clusters: each SM stages half of the
+ * B tile) unless switched off (on = 0: one CTA per tile everywhere; for A/B measurements). */
+int hb_gemm_set_pair_mode(int on);
 
 /* mini_batch_generator's index gathers (rollout_storage.py:165-180), done once per update because the
  * permutation is drawn once and reused by every epoch (:149): dst[i, 0:cols] = src[perm[i], 0:cols];

@@ -52,6 +52,55 @@ __device__ __forceinline__ void tma_load_2d(void *smem, const CUtensorMap *map, 
         ::"r"(hb::smem_u32(smem)), "l"(map), "r"(c0), "r"(c1), "r"(hb::smem_u32(bar))
         : "memory");
 }
+// pair mode (cta_group::2): both CTAs of a 2-CTA cluster load, the transaction bytes land on the leader's barrier
+__device__ __forceinline__ void tma_load_2d_pair(void *smem, const CUtensorMap *map, int c0, int c1, uint32_t leader_bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(hb::smem_u32(smem)), "l"(map), "r"(c0), "r"(c1), "r"(leader_bar)
+        : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {      // same variable in CTA `rank` of the cluster
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t *dst_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(hb::smem_u32(dst_smem)),
+                 "r"(cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_tf32_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint64_t *bar) {      // arrives on the same barrier of both CTAs
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                     hb::smem_u32(bar)),
+                 "h"((uint16_t)3)
+                 : "memory");
+}
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap *map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -111,18 +160,22 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_b
 }
 
 // Instruction descriptor (cute::UMMA::InstrDescriptor): F32 accumulate, TF32 x TF32.
-__host__ __device__ constexpr uint32_t make_idesc(int n, bool a_mn, bool b_mn) {
+__host__ __device__ constexpr uint32_t make_idesc(int n, bool a_mn, bool b_mn, int m = BM) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
-           ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+           ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
-template <int BN>
-__host__ __device__ constexpr int stages_for() { return BN >= 256 ? 4 : (BN >= 128 ? 6 : 8); }
+// PAIR = two CTAs of a cluster (two SMs) compute one 256 x BN tile with tcgen05.mma.cta_group::2: each CTA stages
+// its own 128 rows of A but only HALF of the B tile (the tensor core reads the other half from the peer's shared
+// memory).  These TF32 GEMMs are bound by operand delivery (L2 -> SMEM, ~12 TB/s chip-wide), not by the tensor
+// pipe: per CTA and k-block a pair moves 32 KB instead of 48 KB for the same 128 x 256 x 32 MACs.
+template <int BN, bool PAIR>
+__host__ __device__ constexpr int stages_for() { return PAIR ? 6 : (BN >= 256 ? 4 : (BN >= 128 ? 6 : 8)); }
 
 constexpr int EPI_TILE_FLOATS = 32 * 33;          // per epilogue warp: one padded 32 x 32 transpose tile
-template <int BN>
+template <int BN, bool PAIR>
 __host__ __device__ constexpr size_t smem_bytes_for() {
-    return (size_t)stages_for<BN>() * (BM * BK * 4 + BN * BK * 4) + EPI_WARPS * EPI_TILE_FLOATS * 4 + 1024;
+    return (size_t)stages_for<BN, PAIR>() * (BM * BK * 4 + (PAIR ? BN / 2 : BN) * BK * 4) + EPI_WARPS * EPI_TILE_FLOATS * 4 + 1024;
 }
 
 // Persistent, warp-specialised: one CTA per SM walks a static list of output tiles
@@ -130,12 +183,13 @@ __host__ __device__ constexpr size_t smem_bytes_for() {
 //   same time share the rows of A in L2 (the weights are small and always L2-resident).
 // Three pipelines: shared-memory stages (TMA <-> MMA), two TMEM accumulators (MMA <-> epilogue: the epilogue of tile
 // i overlaps the main loop of tile i + 1), and the tile list.
-template <int BN, bool A_MN, bool B_MN, int EPI>
+template <int BN, bool A_MN, bool B_MN, int EPI, bool PAIR>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                  const __grid_constant__ GemmArgs g) {
-    constexpr int NSTAGE = stages_for<BN>();
-    constexpr int A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4;
+    constexpr int NSTAGE = stages_for<BN, PAIR>();
+    constexpr int BN_CTA = PAIR ? BN / 2 : BN;               // B rows staged by this CTA
+    constexpr int A_BYTES = BM * BK * 4, B_BYTES = BN_CTA * BK * 4;
     constexpr uint32_t ACC_COLS = BN < 32 ? 32 : BN;          // TMEM columns of one accumulator
     constexpr uint32_t TMEM_COLS = 2 * ACC_COLS;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -147,18 +201,25 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int kb_total = (g.K + BK - 1) / BK;
+    const uint32_t rank = PAIR ? cluster_ctarank() : 0u;     // 0 = leader (issues the MMAs, owns full / acc_empty barriers)
+    const int first_tile = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int tile_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
     if (threadIdx.x == 0) {
 #pragma unroll
         for (int s = 0; s < NSTAGE; ++s) hb::mbar_init(&full_bar[s], 1), hb::mbar_init(&empty_bar[s], 1);
 #pragma unroll
-        for (int a = 0; a < 2; ++a) hb::mbar_init(&acc_full[a], 1), hb::mbar_init(&acc_empty[a], EPI_WARPS);
+        for (int a = 0; a < 2; ++a) hb::mbar_init(&acc_full[a], 1), hb::mbar_init(&acc_empty[a], PAIR ? 2 * EPI_WARPS : EPI_WARPS);
         hb::fence_mbar_init();
     }
     if (warp == PRODUCER_WARP && lane == 0) prefetch_tmap(&map_a), prefetch_tmap(&map_b);
-    if (warp == MMA_WARP) tmem_alloc(&tmem_base_smem, TMEM_COLS);
+    if (warp == MMA_WARP) {
+        if (PAIR) tmem_alloc_pair(&tmem_base_smem, TMEM_COLS);
+        else tmem_alloc(&tmem_base_smem, TMEM_COLS);
+    }
     tc_fence_before();
-    __syncthreads();
+    if (PAIR) cluster_sync();        // the peer's barriers are initialised before anything arrives on them
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_smem;
 
@@ -167,7 +228,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         const int rest = t / g.tiles_n;
         const int z = rest % g.splits;
         const int mt = rest / g.splits;
-        m0 = mt * BM, n0 = nt * BN;
+        m0 = PAIR ? (mt * 2 + (int)rank) * BM : mt * BM, n0 = nt * BN;
         kb_begin = z * g.kb_per_split;
         nkb = min(kb_begin + g.kb_per_split, kb_total) - kb_begin;
     };
@@ -176,34 +237,53 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         // ===================== TMA producer =====================
         if (lane == 0) {
             uint32_t it = 0;
-            for (int t = blockIdx.x; t < g.total_tiles; t += gridDim.x) {
+            for (int t = first_tile; t < g.total_tiles; t += tile_step) {
                 int m0, n0, kb_begin, nkb;
                 tile_coords(t, m0, n0, kb_begin, nkb);
+                const int nb0 = n0 + (PAIR ? (int)rank * BN_CTA : 0);      // this CTA's rows of the B tile
                 for (int i = 0; i < nkb; ++i, ++it) {
                     const uint32_t s = it % NSTAGE, ph = (it / NSTAGE) & 1;
                     hb::mbar_wait(&empty_bar[s], ph ^ 1);
-                    hb::mbar_expect_tx(&full_bar[s], A_BYTES + B_BYTES);
                     const int k0 = (kb_begin + i) * BK;
-                    if (A_MN) {      // tensor map dims (M, K): boxes of 32 m x 32 k, one 4 KB swizzle block each
+                    if (PAIR) {
+                        // both CTAs' bytes are counted on the leader's barrier
+                        if (rank == 0) hb::mbar_expect_tx(&full_bar[s], 2 * (A_BYTES + B_BYTES));
+                        const uint32_t bar = mapa_shared(hb::smem_u32(&full_bar[s]), 0);
+                        if (A_MN) {
 #pragma unroll
-                        for (int j = 0; j < BM / 32; ++j) tma_load_2d(sa + s * A_BYTES + j * 4096, &map_a, m0 + 32 * j, k0, &full_bar[s]);
-                    } else {         // tensor map dims (K, M): one box of 32 k x 128 rows
-                        tma_load_2d(sa + s * A_BYTES, &map_a, k0, m0, &full_bar[s]);
-                    }
-                    if (B_MN) {
+                            for (int j = 0; j < BM / 32; ++j) tma_load_2d_pair(sa + s * A_BYTES + j * 4096, &map_a, m0 + 32 * j, k0, bar);
+                        } else {
+                            tma_load_2d_pair(sa + s * A_BYTES, &map_a, k0, m0, bar);
+                        }
+                        if (B_MN) {
 #pragma unroll
-                        for (int j = 0; j < BN / 32; ++j) tma_load_2d(sb + s * B_BYTES + j * 4096, &map_b, n0 + 32 * j, k0, &full_bar[s]);
+                            for (int j = 0; j < BN_CTA / 32; ++j) tma_load_2d_pair(sb + s * B_BYTES + j * 4096, &map_b, nb0 + 32 * j, k0, bar);
+                        } else {
+                            tma_load_2d_pair(sb + s * B_BYTES, &map_b, k0, nb0, bar);
+                        }
                     } else {
-                        tma_load_2d(sb + s * B_BYTES, &map_b, k0, n0, &full_bar[s]);
+                        hb::mbar_expect_tx(&full_bar[s], A_BYTES + B_BYTES);
+                        if (A_MN) {      // tensor map dims (M, K): boxes of 32 m x 32 k, one 4 KB swizzle block each
+#pragma unroll
+                            for (int j = 0; j < BM / 32; ++j) tma_load_2d(sa + s * A_BYTES + j * 4096, &map_a, m0 + 32 * j, k0, &full_bar[s]);
+                        } else {         // tensor map dims (K, M): one box of 32 k x 128 rows
+                            tma_load_2d(sa + s * A_BYTES, &map_a, k0, m0, &full_bar[s]);
+                        }
+                        if (B_MN) {
+#pragma unroll
+                            for (int j = 0; j < BN / 32; ++j) tma_load_2d(sb + s * B_BYTES + j * 4096, &map_b, n0 + 32 * j, k0, &full_bar[s]);
+                        } else {
+                            tma_load_2d(sb + s * B_BYTES, &map_b, k0, n0, &full_bar[s]);
+                        }
                     }
                 }
             }
         }
     } else if (warp == MMA_WARP) {
         // ===================== MMA issuer =====================
-        constexpr uint32_t idesc = make_idesc(BN < 16 ? 16 : BN, A_MN, B_MN);
+        constexpr uint32_t idesc = make_idesc(BN < 16 ? 16 : BN, A_MN, B_MN, PAIR ? 2 * BM : BM);
         uint32_t it = 0, acc_it = 0;
-        for (int t = blockIdx.x; t < g.total_tiles; t += gridDim.x, ++acc_it) {
+        for (int t = first_tile; t < g.total_tiles && rank == 0; t += tile_step, ++acc_it) {
             int m0, n0, kb_begin, nkb;
             tile_coords(t, m0, n0, kb_begin, nkb);
             const uint32_t a = acc_it & 1, aph = (acc_it >> 1) & 1;
@@ -224,10 +304,16 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                                                  : make_desc(a_addr + k * 32, 16, 1024, LAYOUT_SW128);
                         const uint64_t bd = B_MN ? make_desc(b_addr + k * 1024, 4096, 512, LAYOUT_SW128_BASE32B)
                                                  : make_desc(b_addr + k * 32, 16, 1024, LAYOUT_SW128);
-                        umma_tf32(tmem_acc, ad, bd, idesc, (i > 0 || k > 0) ? 1u : 0u);
+                        if (PAIR) umma_tf32_pair(tmem_acc, ad, bd, idesc, (i > 0 || k > 0) ? 1u : 0u);
+                        else umma_tf32(tmem_acc, ad, bd, idesc, (i > 0 || k > 0) ? 1u : 0u);
                     }
-                    umma_commit(&empty_bar[s]);                  // frees the smem stage once the MMAs have read it
-                    if (i == nkb - 1) umma_commit(&acc_full[a]); // accumulator complete -> epilogue
+                    if (PAIR) {        // both CTAs' stages / epilogues are released
+                        umma_commit_pair(&empty_bar[s]);
+                        if (i == nkb - 1) umma_commit_pair(&acc_full[a]);
+                    } else {
+                        umma_commit(&empty_bar[s]);                  // frees the smem stage once the MMAs have read it
+                        if (i == nkb - 1) umma_commit(&acc_full[a]); // accumulator complete -> epilogue
+                    }
                 }
                 __syncwarp();
             }
@@ -244,7 +330,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         const int c_end = (BN >= 64 || half == 0) ? c_begin + HALF_COLS : 0;
         float *tile = epi_smem + warp * EPI_TILE_FLOATS;
         uint32_t acc_it = 0;
-        for (int t = blockIdx.x; t < g.total_tiles; t += gridDim.x, ++acc_it) {
+        for (int t = first_tile; t < g.total_tiles; t += tile_step, ++acc_it) {
             int m0, n0, kb_begin, nkb;
             tile_coords(t, m0, n0, kb_begin, nkb);
             const uint32_t a = acc_it & 1, aph = (acc_it >> 1) & 1;
@@ -341,12 +427,19 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             }
             // every tcgen05.ld of this warp has completed (tcgen05.wait::ld inside tmem_ld16): hand the accumulator back
             tc_fence_before();
-            if (lane == 0) hb::mbar_arrive(&acc_empty[a]);
+            if (lane == 0) {
+                if (PAIR) mbar_arrive_cluster(mapa_shared(hb::smem_u32(&acc_empty[a]), 0));   // the leader's barrier
+                else hb::mbar_arrive(&acc_empty[a]);
+            }
         }
     }
     tc_fence_before();
-    __syncthreads();
-    if (warp == MMA_WARP) tmem_dealloc(tmem_base, TMEM_COLS);
+    if (PAIR) cluster_sync();        // the leader's MMAs read the peer's shared memory: leave together
+    else __syncthreads();
+    if (warp == MMA_WARP) {
+        if (PAIR) tmem_dealloc_pair(tmem_base, TMEM_COLS);
+        else tmem_dealloc(tmem_base, TMEM_COLS);
+    }
 }
 
 // ---- host side --------------------------------------------------------------------------------------
@@ -398,11 +491,12 @@ int make_map(CUtensorMap *map, const float *base, int rows, int cols, int ld, in
     return HB_OK;
 }
 
-template <int BN, bool A_MN, bool B_MN, int EPI>
+template <int BN, bool A_MN, bool B_MN, int EPI, bool PAIR>
 int launch(const hb_gemm_desc *d, cudaStream_t st) {
-    constexpr size_t SMEM = smem_bytes_for<BN>();
+    constexpr size_t SMEM = smem_bytes_for<BN, PAIR>();
+    constexpr int BN_CTA = PAIR ? BN / 2 : BN;
     static bool attr = false;
-    auto kern = gemm_tf32_kernel<BN, A_MN, B_MN, EPI>;
+    auto kern = gemm_tf32_kernel<BN, A_MN, B_MN, EPI, PAIR>;
     if (!attr) {
         HB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
         attr = true;
@@ -412,7 +506,7 @@ int launch(const hb_gemm_desc *d, cudaStream_t st) {
     // A: K-major  -> memory [M, K] ;  MN-major -> memory [K, M]
     rc = A_MN ? make_map(&ma, d->A, d->K, d->M, d->lda, 32, 32, true) : make_map(&ma, d->A, d->M, d->K, d->lda, BK, BM, false);
     if (rc) return rc;
-    rc = B_MN ? make_map(&mb, d->B, d->K, d->N, d->ldb, 32, 32, true) : make_map(&mb, d->B, d->N, d->K, d->ldb, BK, BN, false);
+    rc = B_MN ? make_map(&mb, d->B, d->K, d->N, d->ldb, 32, 32, true) : make_map(&mb, d->B, d->N, d->K, d->ldb, BK, BN_CTA, false);
     if (rc) return rc;
     GemmArgs g;
     g.M = d->M, g.N = d->N, g.K = d->K;
@@ -422,20 +516,43 @@ int launch(const hb_gemm_desc *d, cudaStream_t st) {
     g.kb_per_split = (kb_total + splits - 1) / splits;
     splits = g.kb_per_split > 0 ? (kb_total + g.kb_per_split - 1) / g.kb_per_split : 1;
     g.D = d->D, g.ldd = d->ldd, g.bias = d->bias, g.bias_stride = d->bias_stride, g.H = d->H, g.ldh = d->ldh;
-    const int tiles_m = (d->M + BM - 1) / BM;
+    const int rows_per_tile = PAIR ? 2 * BM : BM;
+    const int tiles_m = (d->M + rows_per_tile - 1) / rows_per_tile;
     g.tiles_n = (d->N + BN - 1) / BN, g.splits = splits;
     g.total_tiles = tiles_m * g.tiles_n * splits;
-    const int grid = g.total_tiles < hb::sm_count() ? g.total_tiles : hb::sm_count();
-    kern<<<grid, GEMM_THREADS, SMEM, st>>>(ma, mb, g);
+    if (PAIR) {
+        const int pairs = hb::sm_count() / 2;
+        const int grid = 2 * (g.total_tiles < pairs ? g.total_tiles : pairs);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid), cfg.blockDim = dim3(GEMM_THREADS), cfg.dynamicSmemBytes = SMEM, cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2, at[0].val.clusterDim.y = 1, at[0].val.clusterDim.z = 1;
+        cfg.attrs = at, cfg.numAttrs = 1;
+        HB_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, mb, g));
+    } else {
+        const int grid = g.total_tiles < hb::sm_count() ? g.total_tiles : hb::sm_count();
+        kern<<<grid, GEMM_THREADS, SMEM, st>>>(ma, mb, g);
+    }
     HB_CHECK_LAUNCH("gemm_tf32_kernel");
     return HB_OK;
 }
 
+int g_gemm_pair = 1;          // "gemm_pair" option: 0 disables the 2-CTA kernels
+
+template <int BN, bool A_MN, bool B_MN, int EPI>
+int launch_auto(const hb_gemm_desc *d, cudaStream_t st) {
+    if constexpr (BN == 256) {
+        if (g_gemm_pair && d->M > BM) return launch<BN, A_MN, B_MN, EPI, true>(d, st);
+    }
+    return launch<BN, A_MN, B_MN, EPI, false>(d, st);
+}
+
 template <int BN, int EPI>
 int dispatch_major(const hb_gemm_desc *d, cudaStream_t st) {
-    if (!d->a_mn_major && !d->b_mn_major) return launch<BN, false, false, EPI>(d, st);
-    if (!d->a_mn_major && d->b_mn_major) return launch<BN, false, true, EPI>(d, st);
-    if (d->a_mn_major && d->b_mn_major) return launch<BN, true, true, EPI>(d, st);
+    if (!d->a_mn_major && !d->b_mn_major) return launch_auto<BN, false, false, EPI>(d, st);
+    if (!d->a_mn_major && d->b_mn_major) return launch_auto<BN, false, true, EPI>(d, st);
+    if (d->a_mn_major && d->b_mn_major) return launch_auto<BN, true, true, EPI>(d, st);
     hb::set_error("hb_gemm_tf32: A MN-major with B K-major is not instantiated");
     return HB_ERR_UNSUPPORTED;
 }
@@ -455,6 +572,11 @@ int dispatch_epi(const hb_gemm_desc *d, cudaStream_t st) {
 
 }  // namespace
 
+extern "C" int hb_gemm_set_pair_mode(int on) {
+    g_gemm_pair = on;
+    return HB_OK;
+}
+
 extern "C" int hb_gemm_tf32(const hb_gemm_desc *d, void *stream) {
     HB_REQUIRE(d && d->A && d->B && d->D, "hb_gemm_tf32: null descriptor/operand");
     HB_REQUIRE(d->M > 0 && d->N > 0 && d->K > 0, "hb_gemm_tf32: empty problem %dx%dx%d", d->M, d->N, d->K);
@@ -473,8 +595,13 @@ extern "C" int hb_gemm_tf32(const hb_gemm_desc *d, void *stream) {
         // BN = 256 but 3 rounds of half-size tiles at BN = 128
         const long long sms = hb::sm_count(), tm = (d->M + BM - 1) / BM;
         const long long t256 = tm * ((d->N + 255) / 256), t128 = tm * ((d->N + 127) / 128);
-        const long long c256 = ((t256 + sms - 1) / sms) * (128 + 256), c128 = ((t128 + sms - 1) / sms) * (128 + 128);
-        if (c128 <= c256) return dispatch_epi<128>(d, st);
+        long long c256 = ((t256 + sms - 1) / sms) * (128 + 256);
+        const long long c128 = ((t128 + sms - 1) / sms) * (128 + 128);
+        if (g_gemm_pair && d->M > BM) {      // 256-row pair tiles: half of B per CTA
+            const long long tp = ((d->M + 2 * BM - 1) / (2 * BM)) * ((d->N + 255) / 256), pairs = sms / 2;
+            c256 = ((tp + pairs - 1) / pairs) * (128 + 128);
+        }
+        if (c128 < c256) return dispatch_epi<128>(d, st);
     }
     return dispatch_epi<256>(d, st);
 }

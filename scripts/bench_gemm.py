@@ -26,6 +26,8 @@ for i, a in enumerate(sys.argv):
     if a == "--opt":
         k, v = sys.argv[i + 1].split("=")
         _lib.check(lib.hb_set_option(k.encode(), int(v)), a)
+if "--no-pair" in sys.argv:
+    lib.hb_gemm_set_pair_mode(0)
 torch.manual_seed(5)
 ac = ActorCritic(615, 1050, 10, actor_hidden_dims=[512, 256, 128], critic_hidden_dims=[768, 256, 128], device=dev)
 alg = PPO(ac, device=dev, **bench.PPO_CFG)
