@@ -263,7 +263,8 @@ typedef struct hb_gemm_desc {
     int32_t bias_stride;
     const float *H;              /* HB_EPI_ELU_BWD: forward activations [M, ldh] */
     int32_t ldh;
-    int32_t split_k;             /* >1: split the contraction over gridDim.z (HB_EPI_ATOMIC_ADD only) */
+    int32_t split_k;             /* HB_EPI_ATOMIC_ADD only: >1 = number of splits of the contraction; 0 = automatic
+                                    (about two rounds of tiles over the SMs) */
     int32_t tile_n;              /* 0 = automatic; 128 forces 128-wide tiles */
 } hb_gemm_desc;
 int hb_gemm_tf32(const hb_gemm_desc *desc, void *stream);

@@ -188,7 +188,6 @@ class ActorCritic:
         lib, st = self._lib, torch.cuda.current_stream(self.device).cuda_stream
         Ls = [L for L in self.layers if L.net == net]
         m = x.shape[0]
-        kb_total = (m + 31) // 32
         d_cur, ld_cur = ws[net]["d_out"], 16               # gradient w.r.t. the layer's pre-activation output
         if from_hidden:
             d_cur, ld_cur = ws[net]["dz"][-1], ws[net]["dz"][-1].stride(0)
@@ -197,11 +196,9 @@ class ActorCritic:
             G = self._matrix(self.grad, L)
             act_in = x if i == 0 else ws[net]["h"][i - 1]      # [m, fan_in (+ ones column)]
             n_w = L.fan_in + 1
-            tiles = ((L.rows + 127) // 128) * ((n_w + 255) // 256)
-            splits = max(1, min(kb_total, (2 * 148) // tiles))
             # weight gradient: G[rows, fan_in + 1] += d_cur^T [rows, m] * [act_in | 1] [m, fan_in + 1]
             gemm(lib, st, A=d_cur.data_ptr(), B=act_in.data_ptr(), D=G.data_ptr(), M=L.rows, N=n_w, K=m, lda=ld_cur,
-                 ldb=act_in.stride(0), ldd=L.ld, a_mn_major=1, b_mn_major=1, epilogue=HB_EPI_ATOMIC_ADD, split_k=splits)
+                 ldb=act_in.stride(0), ldd=L.ld, a_mn_major=1, b_mn_major=1, epilogue=HB_EPI_ATOMIC_ADD, split_k=0)
             if i == 0:
                 break
             # data gradient through the previous ELU: dz_prev = (d_cur * W) . elu'(h_prev)

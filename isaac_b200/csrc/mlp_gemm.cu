@@ -512,6 +512,14 @@ int launch(const hb_gemm_desc *d, cudaStream_t st) {
     g.M = d->M, g.N = d->N, g.K = d->K;
     const int kb_total = (d->K + BK - 1) / BK;
     int splits = d->split_k > 0 ? d->split_k : 1;
+    if (d->split_k == 0 && EPI == EPI_ATOMIC) {
+        // automatic split-K: about two rounds of tiles over the SMs (SM pairs in pair mode)
+        const int slots = PAIR ? hb::sm_count() / 2 : hb::sm_count();
+        const int rows = PAIR ? 2 * BM : BM;
+        const int tiles = ((d->M + rows - 1) / rows) * ((d->N + BN - 1) / BN);
+        splits = (2 * slots) / tiles;
+        if (splits < 1) splits = 1;
+    }
     if (splits > kb_total) splits = kb_total > 0 ? kb_total : 1;
     g.kb_per_split = (kb_total + splits - 1) / splits;
     splits = g.kb_per_split > 0 ? (kb_total + g.kb_per_split - 1) / g.kb_per_split : 1;
@@ -589,7 +597,7 @@ extern "C" int hb_gemm_tf32(const hb_gemm_desc *d, void *stream) {
     if (d->N <= 16) return dispatch_epi<16>(d, st);
     if (d->N <= 64) return dispatch_epi<64>(d, st);
     if (d->N <= 128 || d->tile_n == 128) return dispatch_epi<128>(d, st);
-    if (d->tile_n == 0 && d->split_k <= 1) {
+    if (d->tile_n == 0 && d->epilogue != HB_EPI_ATOMIC_ADD) {
         // ... unless 128-wide tiles balance better over the SMs: rounds of the persistent tile loop x operand
         // bytes per tile (proportional to 128 + BN); e.g. M = 24576, N = 256 is 192 tiles = 2 rounds of 148 SMs at
         // BN = 256 but 3 rounds of half-size tiles at BN = 128
