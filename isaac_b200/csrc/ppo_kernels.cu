@@ -159,161 +159,193 @@ loss_head_kernel(const float *__restrict__ mu, int ld_mu, const float *__restric
 // so H3 is read once and mu / value / d_out never touch HBM.
 // ------------------------------------------------------------------------------------------------------------
 constexpr int HID = 128;                 // last hidden width of both networks (hector_config.py:207-210)
-constexpr int HEAD_THREADS = 256;
+constexpr int HEAD_THREADS = 128;
+constexpr int HEAD_OUT = NA + 1;         // 10 action means + 1 value
 
-struct HeadLoss {                        // per-sample results of the loss head (uniform across the warp)
-    float g_mu[NA], g_v, g_std[NA];
-    double st_s, st_v, st_k, st_e;
-};
-
-__device__ __forceinline__ void loss_head_sample(const float *__restrict__ r, const float *m, float v, const float *sig,
-                                                 double inv_b, const hb_ppo_loss_params &lp, HeadLoss &o) {
-    float lp_new = 0.0f, kl = 0.0f, ent = 0.0f, diff[NA];
+// Sum 16 per-lane values over the warp with 16 shuffles instead of 80: every exchange halves the number of
+// values a lane carries (butterfly over lane bits 4..1), the last one adds lane bit 0.  Value i ends up, fully
+// summed, on lanes 2i and 2i + 1.
+__device__ __forceinline__ float warp_reduce16(float (&v)[16], int lane) {
 #pragma unroll
-    for (int j = 0; j < NA; ++j) {
-        const float var = sig[j] * sig[j];
-        diff[j] = r[j] - m[j];
-        lp_new += (-(diff[j] * diff[j]) / (2.0f * var) - logf(sig[j])) - HALF_LOG_2PI;      // Normal.log_prob
-        const float so = r[2 * NA + j], dm = r[NA + j] - m[j];
-        kl += (logf(sig[j] / so + 1.e-5f) + (so * so + dm * dm) / (2.0f * var)) - 0.5f;      // ppo.py:138-139
-        ent += (0.5f + HALF_LOG_2PI) + logf(sig[j]);                                          // Normal.entropy
-    }
-    const float v_old = r[3 * NA], adv = r[3 * NA + 1], ret = r[3 * NA + 2], lp_old = r[3 * NA + 3];
-    const float ratio = expf(lp_new - lp_old);                 // clipped surrogate (ppo.py:152-156)
-    const float lo = 1.0f - lp.clip_param, hi = 1.0f + lp.clip_param;
-    const float s1 = -adv * ratio, s2 = -adv * fminf(fmaxf(ratio, lo), hi);
-    const float inr = (ratio >= lo && ratio <= hi) ? 1.0f : 0.0f;
-    const float w1 = s1 > s2 ? 1.0f : (s1 == s2 ? 0.5f : 0.0f);       // torch.max splits the gradient evenly on ties
-    const float g_ratio = -adv * (w1 + (1.0f - w1) * inr);
-    const float g_lp = (float)((double)(g_ratio * ratio) * inv_b);
-    o.st_s = (double)fmaxf(s1, s2);
-    float g_v;
-    if (lp.use_clipped_value_loss) {                           // value loss (ppo.py:158-166)
-        const float dv = v - v_old;
-        const float vc = v_old + fminf(fmaxf(dv, -lp.clip_param), lp.clip_param);
-        const float l1 = (v - ret) * (v - ret), l2 = (vc - ret) * (vc - ret);
-        const float inv = (dv >= -lp.clip_param && dv <= lp.clip_param) ? 1.0f : 0.0f;
-        const float u1 = l1 > l2 ? 1.0f : (l1 == l2 ? 0.5f : 0.0f);
-        g_v = 2.0f * (v - ret) * u1 + 2.0f * (vc - ret) * inv * (1.0f - u1);
-        o.st_v = (double)fmaxf(l1, l2);
-    } else {
-        g_v = -2.0f * (ret - v);
-        o.st_v = (double)((ret - v) * (ret - v));
-    }
-    o.st_k = (double)kl, o.st_e = (double)ent;
+    for (int step = 0; step < 4; ++step) {
+        const int off = 16 >> step, half = 8 >> step;           // lane distance, values kept
+        const bool upper = (lane & off) != 0;
 #pragma unroll
-    for (int j = 0; j < NA; ++j) {
-        const float var = sig[j] * sig[j];
-        o.g_mu[j] = g_lp * (diff[j] / var);
-        o.g_std[j] = g_lp * ((diff[j] * diff[j]) / (var * sig[j]) - 1.0f / sig[j]);
+        for (int k = 0; k < 8; ++k) {
+            if (k < half) {
+                const float send = upper ? v[k] : v[k + half];   // the half this lane gives away
+                const float recv = __shfl_xor_sync(0xffffffffu, send, off);
+                v[k] = (upper ? v[k + half] : v[k]) + recv;
+            }
+        }
     }
-    o.g_v = (float)((double)(lp.value_loss_coef * g_v) * inv_b);
+    return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
 }
 
-__global__ void __launch_bounds__(HEAD_THREADS, 1)
+__global__ void __launch_bounds__(HEAD_THREADS, 3)
 head_fused_kernel(const float *__restrict__ h3a, int ld_ha, const float *__restrict__ h3c, int ld_hc,
                   const float *__restrict__ w4a, const float *__restrict__ w4c, int ld_w, const float *__restrict__ stdp,
                   const float *__restrict__ rec, long long mb, double inv_b, float ent_scale, hb_ppo_loss_params lp,
                   float *__restrict__ dz3a, float *__restrict__ dz3c, int ld_dz, float *__restrict__ g4a,
                   float *__restrict__ g4c, float *__restrict__ d_std, double *__restrict__ stats) {
-    __shared__ float s_g[(NA + 1) * (HID + 1)];            // CTA-level weight/bias gradient accumulators
+    __shared__ __align__(16) float s_w[HEAD_OUT * HID];    // output-layer weights, row j = action j, row 10 = value
+    __shared__ float s_g[HEAD_OUT * (HID + 1)];            // CTA-level weight/bias gradient accumulators
     __shared__ float s_dstd[NA];
     __shared__ double s_stat[4];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int i = threadIdx.x; i < (NA + 1) * (HID + 1); i += HEAD_THREADS) s_g[i] = 0.0f;
+    for (int i = threadIdx.x; i < HEAD_OUT * HID; i += HEAD_THREADS) {
+        const int j = i / HID, k = i - j * HID;
+        s_w[i] = (j < NA) ? w4a[(size_t)j * ld_w + k] : w4c[k];
+    }
+    for (int i = threadIdx.x; i < HEAD_OUT * (HID + 1); i += HEAD_THREADS) s_g[i] = 0.0f;
     if (threadIdx.x < NA) s_dstd[threadIdx.x] = 0.0f;
     if (threadIdx.x < 4) s_stat[threadIdx.x] = 0.0;
-    // this lane's 4 columns of the output-layer weights, biases (uniform) and sigma
-    float wa[NA][4], wc[4], ba[NA], sig[NA];
+    // After the butterfly, output `o` of a row lives on lanes 2o, 2o+1: lane pair o < 10 owns action o, pair 10 the value.
+    const int o = lane >> 1;
+    const bool own_action = o < NA, even = (lane & 1) == 0;
+    const float bias = (o < NA) ? w4a[(size_t)o * ld_w + HID] : (o == NA ? w4c[HID] : 0.0f);
+    // row-invariant pieces of the loss for this lane's action (ppo.py:130-168)
+    const float sg = own_action ? stdp[o] : 1.0f;
+    const float var = sg * sg, log_sg = logf(sg);
+    const float inv_2var = 1.0f / (2.0f * var), inv_var = 1.0f / var, inv_var_sg = 1.0f / (var * sg), inv_sg = 1.0f / sg;
+    const float inv_bf = (float)inv_b;
+    float ga[NA][4], gc[4], gb = 0.0f, gstd = 0.0f;        // weight grads of this lane's 4 columns; bias / std grad of output o
 #pragma unroll
-    for (int j = 0; j < NA; ++j) {
-        const float4 w = *reinterpret_cast<const float4 *>(w4a + (size_t)j * ld_w + lane * 4);
-        wa[j][0] = w.x, wa[j][1] = w.y, wa[j][2] = w.z, wa[j][3] = w.w;
-        ba[j] = w4a[(size_t)j * ld_w + HID];
-        sig[j] = stdp[j];
-    }
-    {
-        const float4 w = *reinterpret_cast<const float4 *>(w4c + lane * 4);
-        wc[0] = w.x, wc[1] = w.y, wc[2] = w.z, wc[3] = w.w;
-    }
-    const float bc = w4c[HID];
-    float ga[NA][4], gc[4], gba[NA], gbc = 0.0f, gstd[NA];
-#pragma unroll
-    for (int j = 0; j < NA; ++j) {
-        ga[j][0] = ga[j][1] = ga[j][2] = ga[j][3] = 0.0f;
-        gba[j] = 0.0f, gstd[j] = 0.0f;
-    }
+    for (int j = 0; j < NA; ++j) ga[j][0] = ga[j][1] = ga[j][2] = ga[j][3] = 0.0f;
     gc[0] = gc[1] = gc[2] = gc[3] = 0.0f;
-    double st[4] = {0.0, 0.0, 0.0, 0.0};
+    float stf[4] = {0.0f, 0.0f, 0.0f, 0.0f};
     __syncthreads();
+    const float4 *w4 = reinterpret_cast<const float4 *>(s_w);
 
     const long long warps = (long long)gridDim.x * (HEAD_THREADS / 32);
-    for (long long row = (long long)blockIdx.x * (HEAD_THREADS / 32) + warp; row < mb; row += warps) {
-        const float4 ha4 = hb::ld_stream4(reinterpret_cast<const float4 *>(h3a + (size_t)row * ld_ha) + lane);
-        const float4 hc4 = hb::ld_stream4(reinterpret_cast<const float4 *>(h3c + (size_t)row * ld_hc) + lane);
-        const float ha[4] = {ha4.x, ha4.y, ha4.z, ha4.w}, hc[4] = {hc4.x, hc4.y, hc4.z, hc4.w};
-        float m[NA], v;
+    long long row = (long long)blockIdx.x * (HEAD_THREADS / 32) + warp;
+    // software pipeline: the activations and the record of the NEXT row are in flight while this one is processed
+    struct RowIn {
+        float4 ha, hc;
+        float act, mu, sig, v_old, adv, ret, lp_old;
+    };
+    auto load_row = [&](long long rw) {
+        RowIn in;
+        in.ha = hb::ld_stream4(reinterpret_cast<const float4 *>(h3a + (size_t)rw * ld_ha) + lane);
+        in.hc = hb::ld_stream4(reinterpret_cast<const float4 *>(h3c + (size_t)rw * ld_hc) + lane);
+        const float *r = rec + rw * HB_PPO_REC;
+        in.act = own_action ? __ldg(r + o) : 0.0f, in.mu = own_action ? __ldg(r + NA + o) : 0.0f;
+        in.sig = own_action ? __ldg(r + 2 * NA + o) : 1.0f;
+        in.v_old = __ldg(r + 3 * NA), in.adv = __ldg(r + 3 * NA + 1), in.ret = __ldg(r + 3 * NA + 2), in.lp_old = __ldg(r + 3 * NA + 3);
+        return in;
+    };
+    RowIn nxt_in = {};
+    if (row < mb) nxt_in = load_row(row);
+    for (; row < mb; row += warps) {
+        const RowIn in = nxt_in;
+        if (row + warps < mb) nxt_in = load_row(row + warps);
+        const float ha[4] = {in.ha.x, in.ha.y, in.ha.z, in.ha.w}, hc[4] = {in.hc.x, in.hc.y, in.hc.z, in.hc.w};
+        const float r_act = in.act, r_mu = in.mu, r_sig = in.sig;
+        const float v_old = in.v_old, adv = in.adv, ret = in.ret, lp_old = in.lp_old;
+        // ---- output layers: partial dot products over this lane's 4 features, then the 16-shuffle reduction ----
+        float part[16];
 #pragma unroll
-        for (int j = 0; j < NA; ++j) m[j] = ((ha[0] * wa[j][0] + ha[1] * wa[j][1]) + ha[2] * wa[j][2]) + ha[3] * wa[j][3];
-        v = ((hc[0] * wc[0] + hc[1] * wc[1]) + hc[2] * wc[2]) + hc[3] * wc[3];
+        for (int j = 0; j < NA; ++j) {
+            const float4 w = w4[j * (HID / 4) + lane];
+            part[j] = ((ha[0] * w.x + ha[1] * w.y) + ha[2] * w.z) + ha[3] * w.w;
+        }
+        {
+            const float4 w = w4[NA * (HID / 4) + lane];
+            part[NA] = ((hc[0] * w.x + hc[1] * w.y) + hc[2] * w.z) + hc[3] * w.w;
+        }
 #pragma unroll
-        for (int j = 0; j < NA; ++j) m[j] = warp_sum(m[j]) + ba[j];
-        v = warp_sum(v) + bc;
-        HeadLoss o;
-        loss_head_sample(rec + row * HB_PPO_REC, m, v, sig, inv_b, lp, o);
-        // data gradient through the last ELU: elu'(z) = z > 0 ? 1 : elu(z) + 1
-        float da[4], dc[4];
+        for (int j = HEAD_OUT; j < 16; ++j) part[j] = 0.0f;
+        const float out = warp_reduce16(part, lane) + bias;               // mu_o on pair o < 10, value on pair 10
+        const float v = __shfl_sync(0xffffffffu, out, 2 * NA);
+        // ---- loss head (same arithmetic as loss_head_kernel), the per-action part on the lane pair of the action ----
+        const float diff = r_act - out, dm = r_mu - out;
+        float lp_j = 0.0f, kl_j = 0.0f, ent_j = 0.0f;
+        if (own_action && even) {
+            // divisions by the (row-invariant) variance are multiplications by its reciprocal here
+            lp_j = (-(diff * diff) * inv_2var - log_sg) - HALF_LOG_2PI;                                      // Normal.log_prob
+            kl_j = (logf(sg / r_sig + 1.e-5f) + (r_sig * r_sig + dm * dm) * inv_2var) - 0.5f;               // ppo.py:138-139
+            ent_j = (0.5f + HALF_LOG_2PI) + log_sg;                                                           // Normal.entropy
+        }
+        // sum over the actions in the reference's order (j = 0..9) so that the result matches loss_head_kernel
+        float lp_new = 0.0f, kl = 0.0f, ent = 0.0f;
+#pragma unroll
+        for (int j = 0; j < NA; ++j) {
+            lp_new += __shfl_sync(0xffffffffu, lp_j, 2 * j);
+            kl += __shfl_sync(0xffffffffu, kl_j, 2 * j);
+            ent += __shfl_sync(0xffffffffu, ent_j, 2 * j);
+        }
+        const float ratio = expf(lp_new - lp_old);                 // clipped surrogate (ppo.py:152-156)
+        const float lo = 1.0f - lp.clip_param, hi = 1.0f + lp.clip_param;
+        const float s1 = -adv * ratio, s2 = -adv * fminf(fmaxf(ratio, lo), hi);
+        const float inr = (ratio >= lo && ratio <= hi) ? 1.0f : 0.0f;
+        const float w1 = s1 > s2 ? 1.0f : (s1 == s2 ? 0.5f : 0.0f);       // torch.max splits the gradient evenly on ties
+        const float g_ratio = -adv * (w1 + (1.0f - w1) * inr);
+        const float g_lp = (g_ratio * ratio) * inv_bf;
+        float g_v, st_v;
+        if (lp.use_clipped_value_loss) {                           // value loss (ppo.py:158-166)
+            const float dv = v - v_old;
+            const float vc = v_old + fminf(fmaxf(dv, -lp.clip_param), lp.clip_param);
+            const float l1 = (v - ret) * (v - ret), l2 = (vc - ret) * (vc - ret);
+            const float inv = (dv >= -lp.clip_param && dv <= lp.clip_param) ? 1.0f : 0.0f;
+            const float u1 = l1 > l2 ? 1.0f : (l1 == l2 ? 0.5f : 0.0f);
+            g_v = 2.0f * (v - ret) * u1 + 2.0f * (vc - ret) * inv * (1.0f - u1);
+            st_v = fmaxf(l1, l2);
+        } else {
+            g_v = -2.0f * (ret - v);
+            st_v = (ret - v) * (ret - v);
+        }
+        g_v = (lp.value_loss_coef * g_v) * inv_bf;
+        // gradient w.r.t. this lane's output: d_mu_o on the action pairs, d_value on pair 10
+        const float g_out = own_action ? g_lp * (diff * inv_var) : (o == NA ? g_v : 0.0f);
+        if (own_action && even) gstd += g_lp * ((diff * diff) * inv_var_sg - inv_sg);
+        if (even) gb += g_out;
+        stf[0] += fmaxf(s1, s2), stf[1] += st_v, stf[2] += kl, stf[3] += ent;       // a warp sees a few dozen rows: fp32 is enough here
+        // ---- data gradient through the last ELU (elu'(z) = z > 0 ? 1 : elu(z) + 1) and weight gradients ----
+        float da[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int j = 0; j < NA; ++j) {
+            const float gm = __shfl_sync(0xffffffffu, g_out, 2 * j);
+            const float4 w = w4[j * (HID / 4) + lane];
+            da[0] += gm * w.x, da[1] += gm * w.y, da[2] += gm * w.z, da[3] += gm * w.w;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) ga[j][i] += gm * ha[i];
+        }
+        const float4 wc = w4[NA * (HID / 4) + lane];
+        const float wcv[4] = {wc.x, wc.y, wc.z, wc.w};
+        float dc[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            float acc = 0.0f;
-#pragma unroll
-            for (int j = 0; j < NA; ++j) acc += o.g_mu[j] * wa[j][i];
-            da[i] = acc * (ha[i] > 0.0f ? 1.0f : ha[i] + 1.0f);
-            dc[i] = (o.g_v * wc[i]) * (hc[i] > 0.0f ? 1.0f : hc[i] + 1.0f);
+            da[i] *= (ha[i] > 0.0f ? 1.0f : ha[i] + 1.0f);
+            dc[i] = (g_v * wcv[i]) * (hc[i] > 0.0f ? 1.0f : hc[i] + 1.0f);
+            gc[i] += g_v * hc[i];
         }
         hb::st_stream4(reinterpret_cast<float4 *>(dz3a + (size_t)row * ld_dz) + lane, make_float4(da[0], da[1], da[2], da[3]));
         hb::st_stream4(reinterpret_cast<float4 *>(dz3c + (size_t)row * ld_dz) + lane, make_float4(dc[0], dc[1], dc[2], dc[3]));
-        // weight / bias gradients of the output layers
-#pragma unroll
-        for (int j = 0; j < NA; ++j) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) ga[j][i] += o.g_mu[j] * ha[i];
-            gba[j] += o.g_mu[j];
-            gstd[j] += o.g_std[j];
-        }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) gc[i] += o.g_v * hc[i];
-        gbc += o.g_v;
-        st[0] += o.st_s, st[1] += o.st_v, st[2] += o.st_k, st[3] += o.st_e;
     }
-    // CTA reduction in shared memory (8 warps), then one atomic per parameter and CTA
+    // CTA reduction in shared memory, then one atomic per parameter and CTA
 #pragma unroll
     for (int j = 0; j < NA; ++j)
 #pragma unroll
         for (int i = 0; i < 4; ++i) atomicAdd(&s_g[j * (HID + 1) + lane * 4 + i], ga[j][i]);
 #pragma unroll
     for (int i = 0; i < 4; ++i) atomicAdd(&s_g[NA * (HID + 1) + lane * 4 + i], gc[i]);
-    if (lane == 0) {        // per-sample quantities are uniform across the warp: counted once
+    if (even && o <= NA) atomicAdd(&s_g[o * (HID + 1) + HID], gb);
+    if (even && own_action) atomicAdd(&s_dstd[o], gstd);
+    if (lane == 0) {
 #pragma unroll
-        for (int j = 0; j < NA; ++j) {
-            atomicAdd(&s_g[j * (HID + 1) + HID], gba[j]);
-            atomicAdd(&s_dstd[j], gstd[j]);
-        }
-        atomicAdd(&s_g[NA * (HID + 1) + HID], gbc);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) atomicAdd(&s_stat[k], st[k]);
+        for (int k = 0; k < 4; ++k) atomicAdd(&s_stat[k], (double)stf[k]);
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < (NA + 1) * (HID + 1); i += HEAD_THREADS) {
+    for (int i = threadIdx.x; i < HEAD_OUT * (HID + 1); i += HEAD_THREADS) {
         const int j = i / (HID + 1), k = i - j * (HID + 1);
         float *dst = (j < NA) ? g4a + (size_t)j * ld_w + k : g4c + k;
         atomicAdd(dst, s_g[i]);
     }
     if (threadIdx.x < NA) {
-        float s = s_dstd[threadIdx.x];
+        float sacc = s_dstd[threadIdx.x];
         // entropy bonus: -entropy_coef * mean(entropy) -> d/dsigma_j = -coef / sigma_j (added once, by block 0)
-        if (blockIdx.x == 0) s += ent_scale * (-lp.entropy_coef / sig[threadIdx.x]);
-        atomicAdd(d_std + threadIdx.x, s);
+        if (blockIdx.x == 0) sacc += ent_scale * (-lp.entropy_coef / stdp[threadIdx.x]);
+        atomicAdd(d_std + threadIdx.x, sacc);
     } else if (threadIdx.x >= 32 && threadIdx.x < 36) {
         atomicAdd(stats + (threadIdx.x - 32), s_stat[threadIdx.x - 32]);
     }
@@ -453,7 +485,7 @@ int hb_ppo_head_fused(const float *h3_actor, int32_t ld_ha, const float *h3_crit
     HB_REQUIRE(hb::aligned16(h3_actor) && hb::aligned16(h3_critic) && hb::aligned16(w4_actor) && hb::aligned16(w4_critic) &&
                    hb::aligned16(dz3_actor) && hb::aligned16(dz3_critic), "hb_ppo_head_fused: 16-byte aligned buffers");
     long long blocks = (mb + HEAD_THREADS / 32 - 1) / (HEAD_THREADS / 32);
-    const long long cap = 2ll * hb::sm_count();
+    const long long cap = 3ll * hb::sm_count();          // three resident CTAs per SM (__launch_bounds__)
     head_fused_kernel<<<(unsigned)(blocks < cap ? blocks : cap), HEAD_THREADS, 0, (cudaStream_t)stream>>>(
         h3_actor, ld_ha, h3_critic, ld_hc, w4_actor, w4_critic, ld_w, std, records, mb, 1.0 / (double)mb_global,
         (float)((double)mb / (double)mb_global), *lp, dz3_actor, dz3_critic, ld_dz, g4_actor, g4_critic, d_std, stats);

@@ -48,8 +48,12 @@ def rec(lib_, st, **kw):
 
 
 acm.gemm = rec
+head_args = []
+head_fn = lib.hb_ppo_head_fused
+lib.hb_ppo_head_fused = lambda *a: (head_args.append(a), head_fn(*a))[1]
 alg.minibatch_gradients(0)
 acm.gemm = orig
+lib.hb_ppo_head_fused = head_fn
 torch.cuda.synchronize()
 
 flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
@@ -83,6 +87,9 @@ for kw in calls:
     total_flop += flop
     kind = kinds[(kw.get("a_mn_major", 0), kw.get("b_mn_major", 0))]
     print(f"{kind} M={kw['M']:6d} N={kw['N']:5d} K={kw['K']:6d} split={kw.get('split_k', 1):3d}  {us:8.1f} us  {flop / us / 1e6:7.1f} TFLOP/s")
+if head_args:
+    us = time_graph(lambda st: head_fn(*head_args[0][:-1], st))
+    print(f"head_fused_kernel (output layers + loss head + their gradients): {us:.1f} us")
 print(f"sum of GEMMs: {total_us:.1f} us, {total_flop / 1e9:.1f} GFLOP, {total_flop / total_us / 1e6:.1f} TFLOP/s")
 us = time_graph(lambda st: alg.minibatch_gradients(0))
 print(f"minibatch_gradients (fwd + loss head + bwd) as one graph: {us:.1f} us -> {total_flop / us / 1e6:.1f} TFLOP/s")
