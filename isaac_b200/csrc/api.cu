@@ -17,6 +17,8 @@ void set_error(const char *fmt, ...) {
     va_end(ap);
 }
 
+int g_use_pdl = -1;
+
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 int sm_count() {

@@ -43,6 +43,24 @@ void count_launch(int n = 1);
 inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 int sm_count();   // cached cudaDevAttrMultiProcessorCount of the current device
+extern int g_use_pdl;   // "pdl" option: 1 / 0 = always / never launch the step's kernels with programmatic stream
+                        // serialization; -1 (default) = for shards of at most 8192 envs, where launch latency dominates
+inline bool use_pdl(int num_envs) { return g_use_pdl > 0 || (g_use_pdl < 0 && num_envs <= 8192); }
+
+#ifdef __CUDACC__
+// <<<grid, block, smem, stream>>> with the programmatic-dependent-launch attribute (kernels call hb::pdl_wait()).
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              Args &&...args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = smem, cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
+    cfg.attrs = at, cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
 
 // ---- device helpers -------------------------------------------------------------------------
 #ifdef __CUDACC__
@@ -103,6 +121,12 @@ template <int N>
 __device__ __forceinline__ void bulk_wait() {
     asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
 }
+
+// Programmatic dependent launch: a kernel launched with hb::launch_pdl may start while its predecessor in the stream
+// (or graph) is still running; it must not touch what the predecessor produces before pdl_wait() returns (= the
+// predecessor grid has completed and its writes are visible).  pdl_trigger() lets the NEXT kernel start early.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // streaming loads / stores (data touched once per step: keep it out of L1)
 __device__ __forceinline__ float4 ld_stream4(const float4 *p) {
