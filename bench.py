@@ -337,6 +337,26 @@ def run_b200(args, rank, world):
                 tot += a.elapsed_time(b)
         return tot / reps
 
+    def time_chain(fns, reps=10):
+        """Average duration of len(fns) back-to-back launches replayed from one CUDA graph, each launch on its own
+        (cold) buffers: the graph-launch latency in front of the first kernel is amortised over the chain."""
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            st_ = torch.cuda.current_stream(dev).cuda_stream
+            for fn in fns:
+                _lib.check(fn(st_), "time_chain")
+        tot = 0.0
+        for r in range(reps + 2):
+            flush_l2(r)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            g.replay()
+            b.record(stream)
+            b.synchronize()
+            if r >= 2:
+                tot += a.elapsed_time(b)
+        return tot / reps / len(fns)
+
     cur, prev = env._cur, env._cur ^ 1
     P, B = env._pp, env._pb
     rb = None            # unconditional shift (reset envs are zeroed by hb_env_reset_finalize)
@@ -350,8 +370,15 @@ def run_b200(args, rank, world):
                                                          _lib.HB_STAGE_STEP, st))
     k_fin = time_launch(lambda st: lib.hb_env_reset_finalize(P, B, env._obs[cur].data_ptr(), env._priv[cur].data_ptr(),
                                                           env._host_count.data_ptr(), None, st))
-    k_stack = time_launch(lambda st: lib.hb_env_stack_observations(P, B, env._obs[prev].data_ptr(), env._priv[prev].data_ptr(),
-                                                                env._obs[cur].data_ptr(), env._priv[cur].data_ptr(), st))
+    k_stack_single = time_launch(lambda st: lib.hb_env_stack_observations(P, B, env._obs[prev].data_ptr(), env._priv[prev].data_ptr(),
+                                                                       env._obs[cur].data_ptr(), env._priv[cur].data_ptr(), st))
+    # the roofline kernel: 4 launches per timed replay, each on its own cold set of history buffers
+    CHAIN = 4
+    sets = [(torch.randn(n, 615, device=dev), torch.randn(n, 1050, device=dev), torch.empty(n, 615, device=dev),
+             torch.empty(n, 1050, device=dev)) for _ in range(CHAIN)]
+    k_stack = time_chain([(lambda st, s_=s_: lib.hb_env_stack_observations(P, B, s_[0].data_ptr(), s_[1].data_ptr(),
+                                                                          s_[2].data_ptr(), s_[3].data_ptr(), st)) for s_ in sets])
+    del sets
     # GAE
     g = torch.Generator().manual_seed(rank)
     r_, v_ = torch.rand(T_GAE, n, 1, generator=g).to(dev), torch.randn(T_GAE, n, 1, generator=g).to(dev)
@@ -392,10 +419,11 @@ def run_b200(args, rank, world):
                                                       host_actions[0]))
     d2h = sum(t.numel() * t.element_size() for t in out_host)
 
-    t = torch.tensor([dev_ms, wall, e2e_wall, k_priv, k_obs, k_pd, k_gae, k_post, k_stack, k_fin], dtype=torch.float64, device=dev)
+    t = torch.tensor([dev_ms, wall, e2e_wall, k_priv, k_obs, k_pd, k_gae, k_post, k_stack, k_fin, k_stack_single],
+                     dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, wall, e2e_wall, k_priv, k_obs, k_pd, k_gae, k_post, k_stack, k_fin = t.tolist()
+    dev_ms, wall, e2e_wall, k_priv, k_obs, k_pd, k_gae, k_post, k_stack, k_fin, k_stack_single = t.tolist()
     if rank != 0:
         return
     peak, peak_src = peaks()
@@ -426,7 +454,9 @@ def run_b200(args, rank, world):
                      "kernel": "stack_shift_pair_kernel (frame stacking: 14 carried frames of 41 + 70 floats, read + write)",
                      "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": hist_priv + hist_obs,
-                     "launch_ms": k_stack},
+                     "launch_ms": k_stack,
+                     "timing": "CUDA events around a graph of 4 launches on 4 distinct cold buffer sets (L2 flushed before), / 4",
+                     "single_launch_ms_incl_graph_launch_latency": k_stack_single},
         "roofline_step": {"bytes_per_env_step": B_ENV_STEP, "achieved": value / world * B_ENV_STEP / 1e9,
                           "peak": peak, "unit": "GB/s", "frac": value / world * B_ENV_STEP / 1e9 / peak},
         "kernels": {"post_physics_ms": k_post, "reset_finalize_ms": k_fin, "stack_pair_ms": k_stack,
