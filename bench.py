@@ -210,6 +210,22 @@ def bench_ppo(args, dev, n, world, rank):
         attach_data_parallel(alg)
     last = torch.randn(n, 1050, device=dev)
     stream = torch.cuda.current_stream(dev)
+    # rollout side: PPO.act + process_env_step per env step, T steps, eager launches
+    obs_, priv_ = torch.randn(n, 615, device=dev), torch.randn(n, 1050, device=dev)
+    rew_, done_ = torch.rand(n, device=dev), torch.rand(n, device=dev) < 0.005
+    infos_ = {"time_outs": torch.rand(n, device=dev) < 0.0004}
+    roll_ms = None
+    for r in range(2):
+        alg.storage.clear()
+        torch.cuda.synchronize(dev)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        for _ in range(T_GAE):
+            alg.act(obs_, priv_)
+            alg.process_env_step(rew_, done_, infos_)
+        b.record(stream)
+        b.synchronize()
+        roll_ms = a.elapsed_time(b) / T_GAE
     times = []
     reps = max(2, args.ppo_updates)
     for r in range(reps + 1):
@@ -241,7 +257,8 @@ def bench_ppo(args, dev, n, world, rank):
             "tensor_tflops": tflops, "tensor_peak_tflops": bf16 * world / 2,
             "tensor_frac": tflops / (bf16 * world / 2),
             "tensor_peak_source": "half of measured sustained bf16 (MEASURED_PEAKS.json); TF32 rate = 1/2 bf16",
-            "mean_kl": alg.last_mean_kl, "learning_rate": alg.learning_rate}
+            "mean_kl": alg.last_mean_kl, "learning_rate": alg.learning_rate,
+            "rollout_act_and_record_ms_per_step": roll_ms}
 
 
 def run_b200(args, rank, world):

@@ -319,6 +319,18 @@ int hb_ppo_head_fused(const float *h3_actor, int32_t ld_ha, const float *h3_crit
 int hb_ppo_act_head(const float *mu, int32_t ld_mu, const float *std, const float *eps, int64_t n, float *actions,
                     float *log_prob, float *mu_out, float *sigma_out, void *stream);
 
+/* Rollout side.  hb_ppo_act_fused: the output layers of both MLPs (hidden width 128) + PPO.act's sampling head
+ * (ppo.py:91-101, actor_critic.py:111-120): a = mu + sigma * eps, log-prob, mu, sigma and the value, written to
+ * caller-chosen destinations - normally the rollout-storage slot of the step (rollout_storage.py:87-100), so
+ * add_transitions' copies of these tensors disappear.  actions/mu_out/sigma_out [n,10], log_prob/values [n].
+ * hb_ppo_record_step: PPO.process_env_step's record (ppo.py:103-113): rewards_out = rewards + gamma * values *
+ * time_outs (time_outs may be NULL), dones_out = dones as uint8. */
+int hb_ppo_act_fused(const float *h3_actor, int32_t ld_ha, const float *h3_critic, int32_t ld_hc, const float *w4_actor,
+                     const float *w4_critic, int32_t ld_w, const float *std, const float *eps, int64_t n, float *actions,
+                     float *log_prob, float *mu_out, float *sigma_out, float *values, void *stream);
+int hb_ppo_record_step(const float *rewards, const uint8_t *dones, const float *values, const uint8_t *time_outs, float gamma,
+                       int64_t n, float *rewards_out, uint8_t *dones_out, void *stream);
+
 typedef struct hb_adam_params {
     float beta1, beta2, eps;
     float max_grad_norm;          /* clip_grad_norm_ (ppo.py:173); <= 0 disables clipping */

@@ -93,6 +93,7 @@ class PPO:
         self.world_size = 1
         self.injected_eps = None            # parity: the Normal.sample() draw of the next act()
         self.injected_perm = None           # parity: the randperm of the next update()
+        self._recorded_slot = None          # rollout slot already filled by the fast path of act()
 
     # ------------------------------------------------------------------ learning rate (device-resident)
     @property
@@ -120,28 +121,75 @@ class PPO:
 
     # ------------------------------------------------------------------ rollout (ppo.py:91-117)
     def act(self, obs, critic_obs):
-        ac, lib = self.actor_critic, self._lib
+        """ppo.py:91-101.  Fast path (both last hidden layers 128 wide, rollout slot available): the observations
+        are copied into the slot's 16-byte-aligned rows first and feed the GEMMs from there (TMA cannot address
+        615- / 1050-float rows), three hidden-layer GEMMs per network, then ONE kernel for the two output layers,
+        the sample, its log-prob, mu, sigma and the value, written straight into the storage slot
+        (rollout_storage.py:87-100's copies of these tensors disappear)."""
+        ac, lib, s = self.actor_critic, self._lib, self.storage
         n = obs.shape[0]
         st = torch.cuda.current_stream(self.device).cuda_stream
         ws = ac.workspace(n)
-        mu16 = ac._mlp_forward("actor", ac._as_operand(obs, ac.num_actor_obs), ws)
-        v16 = ac._mlp_forward("critic", ac._as_operand(critic_obs, ac.num_critic_obs), ws)
         eps = self.injected_eps if self.injected_eps is not None else torch.randn(n, ac.num_actions, device=self.device)
         self.injected_eps = None
+        t = self.transition
+        fast = (ac.fused_head and s is not None and s.step < s.num_transitions_per_env and n == s.num_envs
+                and s.privileged_observations is not None and obs.is_cuda and critic_obs.is_cuda)
+        if fast:
+            k = s.step
+            s.observations[k].copy_(obs)
+            s.privileged_observations[k].copy_(critic_obs)
+            h3a = ac._mlp_forward("actor", s._observations[k], ws, hidden_only=True)
+            h3c = ac._mlp_forward("critic", s._privileged_observations[k], ws, hidden_only=True)
+            La, Lc = [L for L in ac.layers if L.last]
+            _lib.check(lib.hb_ppo_act_fused(h3a.data_ptr(), h3a.stride(0), h3c.data_ptr(), h3c.stride(0),
+                                            ac._matrix(ac.flat, La).data_ptr(), ac._matrix(ac.flat, Lc).data_ptr(), La.ld,
+                                            ac.std.data_ptr(), eps.contiguous().data_ptr(), n, s.actions[k].data_ptr(),
+                                            s.actions_log_prob[k].data_ptr(), s.mu[k].data_ptr(), s.sigma[k].data_ptr(),
+                                            s.values[k].data_ptr(), st), "hb_ppo_act_fused")
+            t.actions, t.values, t.actions_log_prob = s.actions[k], s.values[k], s.actions_log_prob[k].view(-1)
+            t.action_mean, t.action_sigma = s.mu[k], s.sigma[k]
+            t.observations, t.critic_observations = obs, critic_obs
+            self._recorded_slot = k
+            return t.actions
+        self._recorded_slot = None
+        mu16 = ac._mlp_forward("actor", ac._as_operand(obs, ac.num_actor_obs), ws)
+        v16 = ac._mlp_forward("critic", ac._as_operand(critic_obs, ac.num_critic_obs), ws)
         actions = torch.empty(n, ac.num_actions, device=self.device)
         logp = torch.empty(n, device=self.device)
         mu, sigma = torch.empty_like(actions), torch.empty_like(actions)
         _lib.check(lib.hb_ppo_act_head(mu16.data_ptr(), 16, ac.std.data_ptr(), eps.contiguous().data_ptr(), n,
                                        actions.data_ptr(), logp.data_ptr(), mu.data_ptr(), sigma.data_ptr(), st),
                    "hb_ppo_act_head")
-        t = self.transition
         t.actions, t.values, t.actions_log_prob = actions, v16[:, :1].clone(), logp
         t.action_mean, t.action_sigma = mu, sigma
         t.observations, t.critic_observations = obs, critic_obs          # recorded before env.step() (ppo.py:98-100)
         return t.actions
 
     def process_env_step(self, rewards, dones, infos):
-        t = self.transition
+        """ppo.py:103-113.  After the fast path of act() only rewards (with the time-out bootstrap) and dones are
+        left to record: one kernel."""
+        t, s = self.transition, self.storage
+        k = getattr(self, "_recorded_slot", None)
+        if k is not None and k == s.step and rewards.is_cuda and rewards.dtype == torch.float32:
+            rewards, dones = rewards.contiguous(), dones.contiguous()
+            if dones.dtype not in (torch.bool, torch.uint8):
+                dones = dones != 0
+            tos = infos.get("time_outs") if isinstance(infos, dict) else None
+            if tos is not None:
+                tos = tos.to(self.device).contiguous()
+                if tos.dtype not in (torch.bool, torch.uint8):
+                    tos = tos != 0
+            st = torch.cuda.current_stream(self.device).cuda_stream
+            _lib.check(self._lib.hb_ppo_record_step(rewards.data_ptr(), dones.data_ptr(), s.values[k].data_ptr(),
+                                                    tos.data_ptr() if tos is not None else None, float(self.gamma),
+                                                    rewards.numel(), s.rewards[k].data_ptr(), s.dones[k].data_ptr(), st),
+                       "hb_ppo_record_step")
+            s.step += 1
+            self._recorded_slot = None
+            t.clear()
+            self.actor_critic.reset(dones)
+            return
         t.rewards = rewards.clone()
         t.dones = dones
         if "time_outs" in infos:          # bootstrapping on time outs (ppo.py:106-108)

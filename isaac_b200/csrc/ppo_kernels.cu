@@ -351,6 +351,78 @@ head_fused_kernel(const float *__restrict__ h3a, int ld_ha, const float *__restr
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Rollout side: PPO.act's output layers + sampling head in one launch, writing straight into
+// the rollout-storage slot of this step (ppo.py:91-101, actor_critic.py:111-120, rollout_storage.py:87-100), and
+// PPO.process_env_step's reward bootstrap + record (ppo.py:103-113).  One warp per env, same lane mapping as
+// head_fused_kernel (lane = 4 hidden features; output o lands on lanes 2o, 2o+1).
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+act_fused_kernel(const float *__restrict__ h3a, int ld_ha, const float *__restrict__ h3c, int ld_hc,
+                 const float *__restrict__ w4a, const float *__restrict__ w4c, int ld_w, const float *__restrict__ stdp,
+                 const float *__restrict__ eps, long long n, float *__restrict__ actions, float *__restrict__ logp,
+                 float *__restrict__ mu_out, float *__restrict__ sigma_out, float *__restrict__ values) {
+    __shared__ __align__(16) float s_w[HEAD_OUT * HID];
+    const int lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < HEAD_OUT * HID; i += blockDim.x) {
+        const int j = i / HID, k = i - j * HID;
+        s_w[i] = (j < NA) ? w4a[(size_t)j * ld_w + k] : w4c[k];
+    }
+    const int o = lane >> 1;
+    const bool own_action = o < NA;
+    const float bias = (o < NA) ? w4a[(size_t)o * ld_w + HID] : (o == NA ? w4c[HID] : 0.0f);
+    const float sg = own_action ? stdp[o] : 1.0f;
+    __syncthreads();
+    const float4 *w4 = reinterpret_cast<const float4 *>(s_w);
+    const long long warps = (long long)gridDim.x * (blockDim.x >> 5);
+    for (long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < n; row += warps) {
+        const float4 ha = hb::ld_stream4(reinterpret_cast<const float4 *>(h3a + (size_t)row * ld_ha) + lane);
+        const float4 hc = hb::ld_stream4(reinterpret_cast<const float4 *>(h3c + (size_t)row * ld_hc) + lane);
+        const float e = own_action ? __ldg(eps + row * NA + o) : 0.0f;
+        float part[16];
+#pragma unroll
+        for (int j = 0; j < NA; ++j) {
+            const float4 w = w4[j * (HID / 4) + lane];
+            part[j] = ((ha.x * w.x + ha.y * w.y) + ha.z * w.z) + ha.w * w.w;
+        }
+        {
+            const float4 w = w4[NA * (HID / 4) + lane];
+            part[NA] = ((hc.x * w.x + hc.y * w.y) + hc.z * w.z) + hc.w * w.w;
+        }
+#pragma unroll
+        for (int j = HEAD_OUT; j < 16; ++j) part[j] = 0.0f;
+        const float out = warp_reduce16(part, lane) + bias;
+        const float sgm = out * 0.0f + sg;                              // actor_critic.py:113
+        const float act = out + sgm * e;                                // Normal.sample with the draw supplied
+        const float d = act - out;
+        const float lp_j = own_action ? (-(d * d) / (2.0f * (sgm * sgm)) - logf(sgm)) - HALF_LOG_2PI : 0.0f;
+        float lp = 0.0f;
+#pragma unroll
+        for (int j = 0; j < NA; ++j) lp += __shfl_sync(0xffffffffu, lp_j, 2 * j);
+        if ((lane & 1) == 0) {
+            if (own_action) {
+                actions[row * NA + o] = act, mu_out[row * NA + o] = out, sigma_out[row * NA + o] = sgm;
+            } else if (o == NA) {
+                values[row] = out;
+            }
+        }
+        if (lane == 0) logp[row] = lp;
+    }
+}
+
+// rewards_out = rewards + gamma * (values * time_outs)  (ppo.py:106-108; plain copy without time_outs); dones -> uint8
+__global__ void __launch_bounds__(256)
+record_step_kernel(const float *__restrict__ rewards, const uint8_t *__restrict__ dones, const float *__restrict__ values,
+                   const uint8_t *__restrict__ time_outs, float gamma, long long n, float *__restrict__ rewards_out,
+                   uint8_t *__restrict__ dones_out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float r = rewards[i];
+    if (time_outs) r += gamma * (values[i] * (time_outs[i] ? 1.0f : 0.0f));
+    rewards_out[i] = r;
+    dones_out[i] = dones[i] ? 1 : 0;
+}
+
 __global__ void __launch_bounds__(256)
 act_head_kernel(const float *__restrict__ mu, int ld_mu, const float *__restrict__ stdp, const float *__restrict__ eps,
                 long long n, float *__restrict__ actions, float *__restrict__ logp, float *__restrict__ mu_out,
@@ -500,6 +572,32 @@ int hb_ppo_act_head(const float *mu, int32_t ld_mu, const float *std, const floa
     act_head_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(mu, ld_mu, std, eps, n, actions,
                                                                                   log_prob, mu_out, sigma_out);
     HB_CHECK_LAUNCH("act_head_kernel");
+    return HB_OK;
+}
+
+int hb_ppo_act_fused(const float *h3_actor, int32_t ld_ha, const float *h3_critic, int32_t ld_hc, const float *w4_actor,
+                     const float *w4_critic, int32_t ld_w, const float *std, const float *eps, int64_t n, float *actions,
+                     float *log_prob, float *mu_out, float *sigma_out, float *values, void *stream) {
+    HB_REQUIRE(h3_actor && h3_critic && w4_actor && w4_critic && std && eps && actions && log_prob && mu_out && sigma_out &&
+                   values && n > 0, "hb_ppo_act_fused: bad arguments");
+    HB_REQUIRE(ld_ha >= HID && ld_hc >= HID && ld_w >= HID + 1 && ld_ha % 4 == 0 && ld_hc % 4 == 0 && ld_w % 4 == 0,
+               "hb_ppo_act_fused: rows of %d features, leading dimensions multiples of 4", HID);
+    HB_REQUIRE(hb::aligned16(h3_actor) && hb::aligned16(h3_critic) && hb::aligned16(w4_actor) && hb::aligned16(w4_critic),
+               "hb_ppo_act_fused: 16-byte aligned buffers");
+    long long blocks = (n + 7) / 8;
+    const long long cap = 8ll * hb::sm_count();
+    act_fused_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, (cudaStream_t)stream>>>(
+        h3_actor, ld_ha, h3_critic, ld_hc, w4_actor, w4_critic, ld_w, std, eps, n, actions, log_prob, mu_out, sigma_out, values);
+    HB_CHECK_LAUNCH("act_fused_kernel");
+    return HB_OK;
+}
+
+int hb_ppo_record_step(const float *rewards, const uint8_t *dones, const float *values, const uint8_t *time_outs, float gamma,
+                       int64_t n, float *rewards_out, uint8_t *dones_out, void *stream) {
+    HB_REQUIRE(rewards && dones && rewards_out && dones_out && n > 0 && (!time_outs || values), "hb_ppo_record_step: bad arguments");
+    record_step_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(rewards, dones, values, time_outs, gamma, n,
+                                                                                      rewards_out, dones_out);
+    HB_CHECK_LAUNCH("record_step_kernel");
     return HB_OK;
 }
 
