@@ -418,7 +418,8 @@ record_step_kernel(const float *__restrict__ rewards, const uint8_t *__restrict_
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float r = rewards[i];
-    if (time_outs) r += gamma * (values[i] * (time_outs[i] ? 1.0f : 0.0f));
+    // separate roundings, like the reference's three torch ops (this unit is compiled with FMA contraction on)
+    if (time_outs) r = __fadd_rn(r, __fmul_rn(gamma, __fmul_rn(values[i], time_outs[i] ? 1.0f : 0.0f)));
     rewards_out[i] = r;
     dones_out[i] = dones[i] ? 1 : 0;
 }

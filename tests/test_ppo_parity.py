@@ -212,3 +212,112 @@ def test_update_matches_reference_golden(lib, cuda_device, schedule):
         assert err < 0.25, f"{k}: update direction error {err:.3f} (moved {moved:.2e})"
         sample = torch.from_numpy(g[f"{schedule}/p/{k}/sample"]).double()
         assert float((got.flatten()[::97] - sample).abs().max()) <= 2.0 * lr_max * steps_taken * 1.01 + 1e-9
+
+
+def test_fused_head_matches_autograd_from_hidden(lib, cuda_device):
+    """hb_ppo_head_fused / hb_ppo_act_fused in isolation: from given last-hidden activations the output layers run in
+    fp32, so everything must agree with torch autograd (fp64 here) to fp32 accuracy - no TF32 in this kernel.
+    Reference expressions: actor_critic.py:62,74,111-120 and ppo.py:130-168."""
+    from isaac_b200 import _lib
+    dev = cuda_device
+    mb, HID, NA = 1000, 128, 10          # not a multiple of the warps per CTA
+    g = torch.Generator().manual_seed(17)
+    f64 = torch.float64
+    z3a, z3c = torch.randn(mb, HID, generator=g, dtype=f64), torch.randn(mb, HID, generator=g, dtype=f64)
+    w4a, b4a = 0.2 * torch.randn(NA, HID, generator=g, dtype=f64), 0.1 * torch.randn(NA, generator=g, dtype=f64)
+    w4c, b4c = 0.2 * torch.randn(1, HID, generator=g, dtype=f64), 0.1 * torch.randn(1, generator=g, dtype=f64)
+    std = 0.5 + torch.rand(NA, generator=g, dtype=f64)
+    actions = torch.randn(mb, NA, generator=g, dtype=f64)
+    mu_old = actions + 0.4 * torch.randn(mb, NA, generator=g, dtype=f64)
+    sig_old = 0.5 + torch.rand(mb, NA, generator=g, dtype=f64)
+    v_old, adv, ret = (torch.randn(mb, generator=g, dtype=f64) for _ in range(3))
+    lp_old = -0.5 * ((actions - mu_old) ** 2).sum(-1) - 9.0 + 0.3 * torch.randn(mb, generator=g, dtype=f64)
+    # the kernel sees fp32 inputs: round first, then do the reference computation in fp64 on the rounded values
+    r32 = lambda x: x.float().double()
+    z3a, z3c, w4a, b4a, w4c, b4c, std, actions, mu_old, sig_old, v_old, adv, ret, lp_old = map(
+        r32, (z3a, z3c, w4a, b4a, w4c, b4c, std, actions, mu_old, sig_old, v_old, adv, ret, lp_old))
+    h3a, h3c = r32(torch.nn.functional.elu(z3a)), r32(torch.nn.functional.elu(z3c))
+    ha, hc = h3a.clone().requires_grad_(True), h3c.clone().requires_grad_(True)
+    W4a, B4a, W4c, B4c, S = (x.clone().requires_grad_(True) for x in (w4a, b4a, w4c, b4c, std))
+    mu = ha @ W4a.T + B4a
+    v = (hc @ W4c.T + B4c).squeeze(-1)
+    sigma = mu * 0.0 + S
+    lp = (-((actions - mu) ** 2) / (2 * sigma ** 2) - sigma.log() - 0.5 * np.log(2 * np.pi)).sum(-1)
+    kl = (torch.log(sigma / sig_old + 1e-5) + (sig_old ** 2 + (mu_old - mu) ** 2) / (2 * sigma ** 2) - 0.5).sum(-1)
+    ent = (0.5 + 0.5 * np.log(2 * np.pi) + sigma.log()).sum(-1)
+    ratio = torch.exp(lp - lp_old)
+    sur = torch.max(-adv * ratio, -adv * ratio.clamp(0.8, 1.2))
+    vclip = v_old + (v - v_old).clamp(-0.2, 0.2)
+    vl = torch.max((v - ret) ** 2, (vclip - ret) ** 2)
+    (sur.mean() + 1.0 * vl.mean() - 0.001 * ent.mean()).backward()
+    dz3a = ha.grad * torch.where(h3a > 0, torch.ones_like(h3a), h3a + 1)
+    dz3c = hc.grad * torch.where(h3c > 0, torch.ones_like(h3c), h3c + 1)
+    assert ((ratio < 0.8) | (ratio > 1.2)).float().mean() > 0.05
+
+    ld = 132
+
+    def packed(rows, w, b):
+        P = torch.zeros(16, ld)
+        P[:rows, :HID], P[:rows, HID] = w.float(), b.float()
+        return P.to(dev)
+
+    def act_buf(h):
+        H = torch.zeros(mb, ld)
+        H[:, :HID], H[:, HID] = h.float(), 1.0
+        return H.to(dev)
+
+    Ha, Hc, Pa, Pc = act_buf(h3a), act_buf(h3c), packed(NA, w4a, b4a), packed(1, w4c, b4c)
+    rec = torch.zeros(mb, 36)
+    rec[:, 0:10], rec[:, 10:20], rec[:, 20:30] = actions.float(), mu_old.float(), sig_old.float()
+    rec[:, 30], rec[:, 31], rec[:, 32], rec[:, 33] = v_old.float(), adv.float(), ret.float(), lp_old.float()
+    rec = rec.to(dev)
+    std_d = std.float().to(dev)
+    dza, dzc = torch.empty(mb, HID, device=dev), torch.empty(mb, HID, device=dev)
+    Ga, Gc = torch.zeros(16, ld, device=dev), torch.zeros(16, ld, device=dev)
+    d_std, stats = torch.zeros(16, device=dev), torch.zeros(4, dtype=f64, device=dev)
+    lpp = _lib.PpoLossParams(0.2, 1.0, 0.001, 1)
+    st = torch.cuda.current_stream(dev).cuda_stream
+    _lib.check(lib.hb_ppo_head_fused(Ha.data_ptr(), ld, Hc.data_ptr(), ld, Pa.data_ptr(), Pc.data_ptr(), ld, std_d.data_ptr(),
+                                     rec.data_ptr(), mb, mb, C.byref(lpp), dza.data_ptr(), dzc.data_ptr(), HID, Ga.data_ptr(),
+                                     Gc.data_ptr(), d_std.data_ptr(), stats.data_ptr(), st), "hb_ppo_head_fused")
+    torch.cuda.synchronize()
+    tol = dict(rtol=2e-4, atol=2e-8)
+    assert_close("dz3_actor", dza.cpu().numpy(), dz3a.numpy(), **tol)
+    assert_close("dz3_critic", dzc.cpu().numpy(), dz3c.numpy(), **tol)
+    assert_close("dW4_actor", Ga[:NA, :HID].cpu().numpy(), W4a.grad.numpy(), rtol=2e-4, atol=1e-7)
+    assert_close("db4_actor", Ga[:NA, HID].cpu().numpy(), B4a.grad.numpy(), rtol=2e-4, atol=1e-7)
+    assert_close("dW4_critic", Gc[:1, :HID].cpu().numpy(), W4c.grad.numpy(), rtol=2e-4, atol=1e-7)
+    assert_close("db4_critic", Gc[:1, HID].cpu().numpy(), B4c.grad.numpy(), rtol=2e-4, atol=1e-7)
+    assert_close("d_std", d_std[:NA].cpu().numpy(), S.grad.numpy(), rtol=2e-4, atol=1e-7)
+    assert (Ga[NA:] == 0).all() and (Gc[1:] == 0).all() and (Ga[:, HID + 1:] == 0).all()
+    want = [sur.sum().item(), vl.sum().item(), kl.sum().item(), ent.sum().item()]
+    np.testing.assert_allclose(stats.cpu().numpy(), want, rtol=2e-5)
+
+    # rollout head: a = mu + sigma * eps, log-prob, value
+    eps = r32(torch.randn(mb, NA, generator=g, dtype=f64))
+    acts, logp = torch.empty(mb, NA, device=dev), torch.empty(mb, device=dev)
+    mu_o, sg_o, val = torch.empty(mb, NA, device=dev), torch.empty(mb, NA, device=dev), torch.empty(mb, device=dev)
+    eps_d = eps.float().to(dev)
+    _lib.check(lib.hb_ppo_act_fused(Ha.data_ptr(), ld, Hc.data_ptr(), ld, Pa.data_ptr(), Pc.data_ptr(), ld, std_d.data_ptr(),
+                                    eps_d.data_ptr(), mb, acts.data_ptr(), logp.data_ptr(), mu_o.data_ptr(),
+                                    sg_o.data_ptr(), val.data_ptr(), st), "hb_ppo_act_fused")
+    torch.cuda.synchronize()
+    mu_w, v_w = mu.detach(), v.detach()
+    a_w = mu_w + std * eps
+    lp_w = (-((a_w - mu_w) ** 2) / (2 * std ** 2) - std.log() - 0.5 * np.log(2 * np.pi)).sum(-1)
+    assert_close("mu", mu_o.cpu().numpy(), mu_w.numpy(), rtol=1e-5, atol=1e-6)
+    assert_close("value", val.cpu().numpy(), v_w.numpy(), rtol=1e-5, atol=1e-6)
+    assert_close("actions", acts.cpu().numpy(), a_w.numpy(), rtol=1e-5, atol=1e-6)
+    assert_close("log_prob", logp.cpu().numpy(), lp_w.numpy(), rtol=1e-5, atol=1e-5)
+    assert torch.equal(sg_o.cpu(), std.float().expand(mb, NA))
+
+    # record kernel: time-out bootstrap of ppo.py:106-108
+    rew, dn = torch.rand(mb, generator=g), torch.rand(mb, generator=g) < 0.1
+    tos = torch.rand(mb, generator=g) < 0.2
+    r_out, d_out = torch.empty(mb, device=dev), torch.empty(mb, dtype=torch.uint8, device=dev)
+    rew_d, dn_d, tos_d = rew.to(dev), dn.to(dev), tos.to(dev)          # kept alive across the asynchronous launch
+    _lib.check(lib.hb_ppo_record_step(rew_d.data_ptr(), dn_d.data_ptr(), val.data_ptr(), tos_d.data_ptr(),
+                                      0.994, mb, r_out.data_ptr(), d_out.data_ptr(), st), "hb_ppo_record_step")
+    torch.cuda.synchronize()
+    want_r = rew + 0.994 * (val.cpu() * tos.float())
+    assert torch.equal(r_out.cpu(), want_r) and torch.equal(d_out.cpu(), dn.to(torch.uint8))
