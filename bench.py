@@ -393,8 +393,9 @@ def run_b200(args, rank, world):
     CHAIN = 4
     sets = [(torch.randn(n, 615, device=dev), torch.randn(n, 1050, device=dev), torch.empty(n, 615, device=dev),
              torch.empty(n, 1050, device=dev)) for _ in range(CHAIN)]
-    k_stack = time_chain([(lambda st, s_=s_: lib.hb_env_stack_observations(P, B, s_[0].data_ptr(), s_[1].data_ptr(),
-                                                                          s_[2].data_ptr(), s_[3].data_ptr(), st)) for s_ in sets])
+    k_stack = time_chain([(lambda st, s_=s_: lib.hb_env_stack_finalize(P, B, s_[0].data_ptr(), s_[1].data_ptr(),
+                                                                      s_[2].data_ptr(), s_[3].data_ptr(),
+                                                                      env._host_count.data_ptr(), None, st)) for s_ in sets])
     del sets
     # GAE
     g = torch.Generator().manual_seed(rank)
@@ -468,7 +469,8 @@ def run_b200(args, rank, world):
                 "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_wall / args.steps},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm",
-                     "kernel": "stack_shift_pair_kernel (frame stacking: 14 carried frames of 41 + 70 floats, read + write)",
+                     "kernel": "stack_finalize_kernel (frame stacking: 14 carried frames of 41 + 70 floats, read + write; the "
+                               "shard-wide reset results ride in the last blocks of the same launch)",
                      "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": hist_priv + hist_obs,
                      "launch_ms": k_stack,

@@ -222,6 +222,12 @@ int hb_env_stack_observations(const hb_env_params *p, const hb_env_buffers *buf,
 int hb_env_reset_finalize(const hb_env_params *p, const hb_env_buffers *buf, float *obs_new, float *priv_new,
                           int32_t *host_count, uint64_t *rng_counter, void *stream);
 
+/* hb_env_stack_observations + hb_env_reset_finalize in ONE launch (what step() uses): the shift blocks zero the
+ * carried frames of the envs whose reset_buf byte hb_env_post_physics just set, extra blocks at the end of the grid
+ * produce the id list / count / episode means / time-out latch.  Same results as the two separate calls. */
+int hb_env_stack_finalize(const hb_env_params *p, const hb_env_buffers *buf, const float *obs_prev, const float *priv_prev,
+                          float *obs_new, float *priv_new, int32_t *host_count, uint64_t *rng_counter, void *stream);
+
 /* One frame-stack shift on its own: next[:, 0:row-frame] = prev[:, frame:row] (zeros for envs whose
  * reset_buf byte is set, if reset_buf is not NULL); next[:, row-frame:row] is left alone. */
 int hb_stack_shift(const float *prev, float *next, const uint8_t *reset_buf, int32_t num_envs, int32_t row,

@@ -891,9 +891,10 @@ __device__ __forceinline__ float4 ld_vec_guarded(const float *__restrict__ prev,
     return v;
 }
 
-template <int ROW, int FRAME, int UNROLL>
+template <int ROW, int FRAME, int UNROLL, bool CHECK_RESET = false>
 __device__ __forceinline__ void
-stack_shift_fixed(const float *__restrict__ prev, float *__restrict__ next, const uint32_t total, const uint32_t blk) {
+stack_shift_fixed(const float *__restrict__ prev, float *__restrict__ next, const uint32_t total, const uint32_t blk,
+                  const uint8_t *__restrict__ reset_buf = nullptr) {
     constexpr uint32_t KEEP = ROW - FRAME;              // floats of a row that are carried over
     constexpr int ROT = FRAME & 3;                      // source misalignment in floats
     constexpr uint32_t FVEC = FRAME >> 2;               // whole vectors of shift
@@ -904,10 +905,16 @@ stack_shift_fixed(const float *__restrict__ prev, float *__restrict__ next, cons
     const float4 *p4 = reinterpret_cast<const float4 *>(prev);
     float4 *n4 = reinterpret_cast<float4 *>(next);
     float4 v[UNROLL], w[UNROLL];
-    // all loads first (UNROLL independent 16-byte requests in flight per thread)
+    uint8_t rz[UNROLL];
+    // all loads first (UNROLL independent 16-byte requests in flight per thread, plus the row's reset flag)
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u) {
         const uint32_t s = warp_base + u * 32u + lane + FVEC;          // aligned source vector below the window
+        rz[u] = 0;
+        if (CHECK_RESET) {
+            const uint32_t e = (warp_base + u * 32u + lane) * 4u;
+            if (e < total) rz[u] = __ldg(reset_buf + e / (uint32_t)ROW);
+        }
         v[u] = (s < total_vec) ? hb::ld_stream4(p4 + s) : ld_vec_guarded(prev, s, total);
         if (ROT != 0 && lane == 31u)                                    // no neighbour lane: fetch the spill-over
             w[u] = (s + 1u < total_vec) ? hb::ld_stream4(p4 + s + 1u) : ld_vec_guarded(prev, s + 1u, total);
@@ -930,14 +937,15 @@ stack_shift_fixed(const float *__restrict__ prev, float *__restrict__ next, cons
         const uint32_t r0 = e0 / (uint32_t)ROW;
         const uint32_t c0 = e0 - r0 * (uint32_t)ROW;
         if (c0 + 3u < KEEP && i < total_vec) {           // whole vector inside the carried part of one row
+            if (CHECK_RESET && rz[u]) o = make_float4(0.f, 0.f, 0.f, 0.f);
             hb::st_stream4(n4 + i, o);
         } else {                                         // touches the newest-frame hole or a row boundary
             const float ov[4] = {o.x, o.y, o.z, o.w};
 #pragma unroll
             for (uint32_t k = 0; k < 4u; ++k) {
-                uint32_t c = c0 + k;
-                if (c >= (uint32_t)ROW) c -= (uint32_t)ROW;
-                if (c < KEEP && e0 + k < total) next[e0 + k] = ov[k];
+                uint32_t c = c0 + k, r = r0;
+                if (c >= (uint32_t)ROW) c -= (uint32_t)ROW, r += 1u;
+                if (c < KEEP && e0 + k < total) next[e0 + k] = (CHECK_RESET && reset_buf[r]) ? 0.0f : ov[k];
             }
         }
     }
@@ -1000,16 +1008,13 @@ __device__ __forceinline__ int block_sum(int v, int *scratch) {        // all th
     return t;
 }
 
-__global__ void __launch_bounds__(FIN_THREADS)
-reset_finalize_kernel(const __grid_constant__ hb_env_params p, const __grid_constant__ hb_env_buffers b,
-                      float *__restrict__ obs_new, float *__restrict__ priv_new, int tiles, int seg,
-                      int32_t *host_count, unsigned long long *rng_counter) {
+__device__ __forceinline__ void
+reset_finalize_body(const hb_env_params &p, const hb_env_buffers &b, float *__restrict__ obs_new, float *__restrict__ priv_new,
+                    int tiles, int seg, int32_t *host_count, unsigned long long *rng_counter, const int blk, const int nblk) {
     __shared__ int scratch[FIN_THREADS / 32];
     __shared__ int wbase[FIN_THREADS / 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int t_lo = blockIdx.x * seg, t_hi = min(t_lo + seg, tiles);
-    hb::pdl_trigger();
-    hb::pdl_wait();              // post-physics (ballots, sums) and the shift are complete
+    const int t_lo = blk * seg, t_hi = min(t_lo + seg, tiles);
     int before = 0, rest = 0;
 #pragma unroll 4
     for (int t = threadIdx.x; t < tiles; t += FIN_THREADS) {
@@ -1048,7 +1053,7 @@ reset_finalize_kernel(const __grid_constant__ hb_env_params p, const __grid_cons
         seg_count += round_total;
     }
     const int total = prefix + seg_count + after;
-    if (blockIdx.x == 0) {
+    if (blk == 0) {
         if (threadIdx.x == 0) {
             *b.reset_count = total;
             if (host_count) *host_count = total;
@@ -1066,7 +1071,7 @@ reset_finalize_kernel(const __grid_constant__ hb_env_params p, const __grid_cons
     }
     if (total == 0) return;
     if (b.time_outs_latched) {
-        for (int i = blockIdx.x * FIN_THREADS + threadIdx.x; i < p.num_envs; i += gridDim.x * FIN_THREADS)
+        for (int i = blk * FIN_THREADS + threadIdx.x; i < p.num_envs; i += nblk * FIN_THREADS)
             b.time_outs_latched[i] = b.time_out_buf[i];
     }
     if (!obs_new || seg_count == 0) return;
@@ -1078,6 +1083,40 @@ reset_finalize_kernel(const __grid_constant__ hb_env_params p, const __grid_cons
         float *dst = (j & 1) ? priv_new + (size_t)env * row_b : obs_new + (size_t)env * row_a;
         const int keep = (j & 1) ? keep_b : keep_a;
         for (int c = lane; c < keep; c += 32) dst[c] = 0.0f;
+    }
+}
+
+__global__ void __launch_bounds__(FIN_THREADS)
+reset_finalize_kernel(const __grid_constant__ hb_env_params p, const __grid_constant__ hb_env_buffers b,
+                      float *__restrict__ obs_new, float *__restrict__ priv_new, int tiles, int seg,
+                      int32_t *host_count, unsigned long long *rng_counter) {
+    hb::pdl_trigger();
+    hb::pdl_wait();              // post-physics (ballots, sums) and the shift are complete
+    reset_finalize_body(p, b, obs_new, priv_new, tiles, seg, host_count, rng_counter, blockIdx.x, gridDim.x);
+}
+
+// The step's last launch: frame-stack shift of both histories (zeroing the carried frames of the envs post-physics
+// just reset: hector_env.py:256-261) and the shard-wide half of reset_idx (ids, count, episode means, time-out
+// latch: reset_finalize_body without the zeroing) in a few extra blocks of the same grid - one
+// launch less on the step's dependency chain than shift + reset_finalize_kernel.
+template <int ROW_A, int FRAME_A, int ROW_B, int FRAME_B, int UNROLL>
+__global__ void __launch_bounds__(256, 6)
+stack_finalize_kernel(const float *__restrict__ prev_a, float *__restrict__ next_a, uint32_t total_a, uint32_t blocks_a,
+                      const float *__restrict__ prev_b, float *__restrict__ next_b, uint32_t total_b, uint32_t blocks_b,
+                      const __grid_constant__ hb_env_params p, const __grid_constant__ hb_env_buffers b, int tiles, int seg,
+                      int32_t *host_count, unsigned long long *rng_counter) {
+    static_assert(FIN_THREADS == 256, "shift and finalize blocks share one launch");
+    hb::pdl_trigger();
+    hb::pdl_wait();              // post-physics complete: reset flags, ballots, sums
+    // the finalize blocks come FIRST in the grid: their short latency chain (ballot scan, ids, means) then runs
+    // under the shift instead of behind its last block
+    const uint32_t fin_blocks = gridDim.x - blocks_a - blocks_b;
+    if (blockIdx.x < fin_blocks) {
+        reset_finalize_body(p, b, nullptr, nullptr, tiles, seg, host_count, rng_counter, blockIdx.x, fin_blocks);
+    } else {
+        const uint32_t blk = blockIdx.x - fin_blocks;
+        if (blk < blocks_a) stack_shift_fixed<ROW_A, FRAME_A, UNROLL, true>(prev_a, next_a, total_a, blk, b.reset_buf);
+        else stack_shift_fixed<ROW_B, FRAME_B, UNROLL, true>(prev_b, next_b, total_b, blk - blocks_a, b.reset_buf);
     }
 }
 
@@ -1276,6 +1315,36 @@ int hb_env_stack_observations(const hb_env_params *p, const hb_env_buffers *buf,
     }
     if (int rc = hb_stack_shift(obs_prev, obs_new, nullptr, p->num_envs, row_a, p->num_single_obs, stream)) return rc;
     return hb_stack_shift(priv_prev, priv_new, nullptr, p->num_envs, row_b, p->num_single_priv, stream);
+}
+
+int hb_env_stack_finalize(const hb_env_params *p, const hb_env_buffers *buf, const float *obs_prev, const float *priv_prev,
+                          float *obs_new, float *priv_new, int32_t *host_count, uint64_t *rng_counter, void *stream) {
+    if (int rc = check_params(p, buf, "hb_env_stack_finalize")) return rc;
+    HB_REQUIRE(obs_prev && priv_prev && obs_new && priv_new && buf->reset_buf, "hb_env_stack_finalize: null buffer");
+    HB_REQUIRE(obs_prev != obs_new && priv_prev != priv_new, "hb_env_stack_finalize: prev and new must not alias");
+    HB_REQUIRE(buf->scratch_ballots && buf->scratch_sums && buf->reset_env_ids && buf->reset_count && buf->episode_means,
+               "hb_env_stack_finalize: null scratch/result buffers");
+    const int row_a = p->frame_stack * p->num_single_obs, row_b = p->c_frame_stack * p->num_single_priv;
+    const bool fast = hb::aligned16(obs_prev) && hb::aligned16(obs_new) && hb::aligned16(priv_prev) &&
+                      hb::aligned16(priv_new) && row_a == ROW_OBS && p->num_single_obs == OBS && row_b == ROW_PRIV &&
+                      p->num_single_priv == PRIV && fits_u32(p->num_envs, row_b);
+    if (!fast) {        // other layouts: the two separate launches
+        if (int rc = hb_env_stack_observations(p, buf, obs_prev, priv_prev, obs_new, priv_new, stream)) return rc;
+        return hb_env_reset_finalize(p, buf, obs_new, priv_new, host_count, rng_counter, stream);
+    }
+    constexpr uint32_t PER = 4 * 256;
+    const uint32_t total_a = (uint32_t)p->num_envs * ROW_OBS, total_b = (uint32_t)p->num_envs * ROW_PRIV;
+    const uint32_t blocks_a = ((total_a + 3u) / 4u + PER - 1) / PER, blocks_b = ((total_b + 3u) / 4u + PER - 1) / PER;
+    const int tiles = (p->num_envs + TILE - 1) / TILE;
+    int seg = (tiles + hb::sm_count() - 1) / hb::sm_count();
+    if (seg < 8) seg = 8;
+    const uint32_t fin_blocks = (uint32_t)((tiles + seg - 1) / seg);
+    HB_CUDA(hb::launch_pdl(hb::use_pdl(p->num_envs), stack_finalize_kernel<ROW_OBS, OBS, ROW_PRIV, PRIV, 4>,
+                           dim3(blocks_a + blocks_b + fin_blocks), dim3(256), 0, (cudaStream_t)stream, obs_prev, obs_new, total_a,
+                           blocks_a, priv_prev, priv_new, total_b, blocks_b, *p, *buf, tiles, seg, host_count,
+                           reinterpret_cast<unsigned long long *>(rng_counter)));
+    HB_CHECK_LAUNCH("stack_finalize_kernel");
+    return HB_OK;
 }
 
 int hb_env_reset_finalize(const hb_env_params *p, const hb_env_buffers *buf, float *obs_new, float *priv_new,

@@ -13,10 +13,10 @@ The per-step work is five kinds of kernel launch through the C ABI (include/hect
     hb_env_action_prologue      x1   hector_env.py:158-169
     hb_env_compute_torques      x decimation, around the opaque physics.simulate()
     hb_env_post_physics         x1   legged_robot.py:118-234,303-396 + newest obs frames
-    hb_env_stack_observations   x1   hector_env.py:246-254 (frame stacking, ping-pong buffers); independent of
-                                     this step's physics
-    hb_env_reset_finalize       x1   legged_robot.py:142,198-209 (ascending reset ids, count, episode means,
-                                     time_outs) + hector_env.py:256-261 (history zeroing of the envs just reset)
+    hb_env_stack_finalize       x1   hector_env.py:246-261 (frame stacking into the ping-pong buffers, history zeroing
+                                     of the envs just reset) + legged_robot.py:142,198-209 (ascending reset ids,
+                                     count, episode means, time_outs) - the fused form of
+                                     hb_env_stack_observations + hb_env_reset_finalize
 
 There is no torch/eager fallback: without libhectorb200.so construction fails.
 `step()` never blocks on the GPU; the one host-visible value the reference needs (the reset
@@ -395,7 +395,7 @@ class HectorFreeEnvB200:
             graphs[parity] = (ga, gb, nz)
         self._cur, self._step_index, self._pending_event = saved
         self._graphs = graphs
-        self.graph_launches_per_step = 1 + dec + 3     # this library's kernels per replayed step (prologue, PD, post, stack, finalize)
+        self.graph_launches_per_step = 1 + dec + 2     # this library's kernels per replayed step (prologue, PD, post, stack+finalize)
 
     def _step_graph(self, actions):
         ga, gb, _ = self._graphs[self._cur]
@@ -456,19 +456,19 @@ class HectorFreeEnvB200:
         self._nz.u_reset = self._nz.rng_counter = None
 
     def _launch_post_kernels(self, stages, noise_ref, prev, cur, emit, st):
-        """post-physics -> frame-stack shift -> reset finalisation, on one stream."""
+        """post-physics -> frame-stack shift + reset finalisation, on one stream."""
         lib = self._lib
         obs_new, priv_new = self._obs[cur].data_ptr(), self._priv[cur].data_ptr()
         _lib.check(lib.hb_env_post_physics(self._pp, self._pb, noise_ref, obs_new, priv_new, stages, st),
                    "hb_env_post_physics")
-        if emit:
-            _lib.check(lib.hb_env_stack_observations(self._pp, self._pb, self._obs[prev].data_ptr(),
-                                                     self._priv[prev].data_ptr(), obs_new, priv_new, st),
-                       "hb_env_stack_observations")
         noise = noise_ref._obj          # the EnvNoise behind the byref
-        _lib.check(lib.hb_env_reset_finalize(self._pp, self._pb, obs_new if emit else None,
-                                             priv_new if emit else None, self._host_count.data_ptr(),
-                                             noise.rng_counter, st), "hb_env_reset_finalize")
+        if emit:        # shift + shard-wide reset results in one launch
+            _lib.check(lib.hb_env_stack_finalize(self._pp, self._pb, self._obs[prev].data_ptr(), self._priv[prev].data_ptr(),
+                                                 obs_new, priv_new, self._host_count.data_ptr(), noise.rng_counter, st),
+                       "hb_env_stack_finalize")
+        else:
+            _lib.check(lib.hb_env_reset_finalize(self._pp, self._pb, None, None, self._host_count.data_ptr(),
+                                                 noise.rng_counter, st), "hb_env_reset_finalize")
 
     def _apply_pending_resets(self):
         """The two opaque calls of _reset_dofs/_reset_root_states (legged_robot.py:370-372,394-396) need
