@@ -94,6 +94,7 @@ class PPO:
         self.injected_eps = None            # parity: the Normal.sample() draw of the next act()
         self.injected_perm = None           # parity: the randperm of the next update()
         self._recorded_slot = None          # rollout slot already filled by the fast path of act()
+        self._side_stream = torch.cuda.Stream(self.device) if self.device.type == "cuda" else None
 
     # ------------------------------------------------------------------ learning rate (device-resident)
     @property
@@ -212,8 +213,15 @@ class PPO:
         xa, xc, rec = self._xa[i * mb:(i + 1) * mb], self._xc[i * mb:(i + 1) * mb], self._rec[i * mb:(i + 1) * mb]
         self._stats.zero_()
         if ac.fused_head:
+            # The actor and critic chains are independent: the critic's GEMMs run on a second stream, so one network's
+            # persistent CTAs fill the SMs the other one leaves idle in its last round of tiles.
+            main = torch.cuda.current_stream(self.device)
+            side = self._side_stream
+            side.wait_stream(main)
             h3a = ac._mlp_forward("actor", xa, ws, hidden_only=True)
-            h3c = ac._mlp_forward("critic", xc, ws, hidden_only=True)
+            with torch.cuda.stream(side):
+                h3c = ac._mlp_forward("critic", xc, ws, hidden_only=True)
+            main.wait_stream(side)
             La, Lc = [L for L in ac.layers if L.last]
             dza, dzc = ws["actor"]["dz"][-1], ws["critic"]["dz"][-1]
             _lib.check(lib.hb_ppo_head_fused(
@@ -221,9 +229,12 @@ class PPO:
                 ac._matrix(ac.flat, La).data_ptr(), ac._matrix(ac.flat, Lc).data_ptr(), La.ld, ac.std.data_ptr(),
                 rec.data_ptr(), mb, mb * self.world_size, C.byref(self._lp), dza.data_ptr(), dzc.data_ptr(), dza.stride(0),
                 ac._matrix(ac.grad, La).data_ptr(), ac._matrix(ac.grad, Lc).data_ptr(),
-                ac.grad[ac._std_offset:].data_ptr(), self._stats.data_ptr(), st), "hb_ppo_head_fused")
+                ac.grad[ac._std_offset:].data_ptr(), self._stats.data_ptr(), main.cuda_stream), "hb_ppo_head_fused")
+            side.wait_stream(main)
             ac._mlp_backward("actor", xa, ws, from_hidden=True)
-            ac._mlp_backward("critic", xc, ws, from_hidden=True)
+            with torch.cuda.stream(side):
+                ac._mlp_backward("critic", xc, ws, from_hidden=True)
+            main.wait_stream(side)
         else:
             mu16 = ac._mlp_forward("actor", xa, ws)
             v16 = ac._mlp_forward("critic", xc, ws)
