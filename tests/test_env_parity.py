@@ -92,13 +92,14 @@ def test_env_matches_reference_golden(lib, cuda_device, bulk):
     lib.hb_set_option(b"env_bulk_staging", 1)
 
 
-@pytest.mark.parametrize("n,bulk", [(257, 1), (257, 0), (31, 1), (1024, 1)])
+@pytest.mark.parametrize("n,bulk", [(257, 1), (257, 0), (31, 1), (1024, 1), (1, 1), (33, 0), (1003, 1)])
 def test_env_matches_oracle_ragged(lib, cuda_device, n, bulk):
     from oracle.hector_oracle import OracleHectorEnv
     assert lib.hb_set_option(b"env_bulk_staging", bulk) == 0
     steps = 12
     tape = make_tape(n, steps, seed=1000 + n, fall_prob=0.03, randomize_gains=True)
-    tape.statics.episode_length0[:5] = torch.tensor([2399, 2400, 798, 799, 1599])
+    special = torch.tensor([2399, 2400, 798, 799, 1599])[:min(n, 5)]
+    tape.statics.episode_length0[:special.numel()] = special
     ora = OracleHectorEnv(HectorCfg(), tape.statics, tape.physics[0], tape.noise[0])
     ora.common_step_counter = 395
     want = {"obs_init": ora.obs_buf.numpy().copy(), "priv_init": ora.privileged_obs_buf.numpy().copy()}
@@ -113,7 +114,7 @@ def test_env_matches_oracle_ragged(lib, cuda_device, n, bulk):
     compare_records(rec, want)
     for t, (a, b) in enumerate(zip(ids, want_ids)):
         assert_equal(f"reset_env_ids@{t}", a, b)
-    assert sum(len(i) for i in want_ids) > 0
+    assert sum(len(i) for i in want_ids) > 0 or n < 8
     lib.hb_set_option(b"env_bulk_staging", 1)
 
 
@@ -269,3 +270,62 @@ def test_device_generator_draws(lib, cuda_device):
     cc = torch.corrcoef(cols.T)
     assert (cc - torch.eye(cc.shape[0], device=dev)).abs().max().item() < 0.08   # column to column (n = 4096)
     assert abs(torch.corrcoef(torch.stack((cols[:-1, 0], cols[1:, 0])))[0, 1].item()) < 0.06   # env to env
+
+
+@pytest.mark.parametrize("n", [1, 37, 1003, 4096])
+def test_fused_shift_finalize_equals_separate_calls(lib, cuda_device, n):
+    """hb_env_stack_finalize (what step() launches) against hb_env_stack_observations + hb_env_reset_finalize on the
+    same inputs: identical frame stacks, id lists, counts, episode means and time-out latch (ragged sizes included:
+    615 n is not a multiple of 4 for n = 1003, the last ballot word is partial for n = 37)."""
+    from isaac_b200 import _lib
+    dev = cuda_device
+    tape = make_tape(n, 2, seed=3 + n, fall_prob=0.2)
+    env, phys = make_cuda_env(tape, dev)
+    g = torch.Generator(device=dev).manual_seed(n)
+    prev_o, prev_p = torch.randn(n, 615, device=dev, generator=g), torch.randn(n, 1050, device=dev, generator=g)
+    reset = torch.rand(n, device=dev, generator=g) < 0.3
+    if n == 37:
+        reset[36] = True           # the last, partial tile
+    tiles = (n + 31) // 32
+    pad = torch.zeros(tiles * 32, dtype=torch.bool, device=dev)
+    pad[:n] = reset
+    weights = (2 ** torch.arange(32, device=dev, dtype=torch.int64))
+    ballots = (pad.view(tiles, 32).long() * weights).sum(1)
+    ballots = torch.where(ballots >= 2 ** 31, ballots - 2 ** 32, ballots).to(torch.int32)
+    sums = torch.rand(18, dtype=torch.float64, device=dev, generator=g)
+    st = torch.cuda.current_stream(dev).cuda_stream
+    results = []
+    for fused in (False, True):
+        env.reset_buf.copy_(reset)
+        env.time_out_buf.copy_(torch.rand(n, device=dev, generator=torch.Generator(device=dev).manual_seed(1)) < 0.5)
+        env._time_outs_latched.zero_()
+        env._scratch_ballots.copy_(ballots)
+        env._scratch_sums.copy_(sums)
+        env.reset_env_ids.fill_(-1)
+        new_o, new_p = torch.full((n, 615), 7.0, device=dev), torch.full((n, 1050), 7.0, device=dev)
+        means = torch.zeros(18, device=dev)
+        env._b.episode_means, env._b.episode_means_prev = means.data_ptr(), None
+        P, B, hc = env._pp, env._pb, env._host_count.data_ptr()
+        if fused:
+            _lib.check(lib.hb_env_stack_finalize(P, B, prev_o.data_ptr(), prev_p.data_ptr(), new_o.data_ptr(), new_p.data_ptr(),
+                                                 hc, None, st), "fused")
+        else:
+            _lib.check(lib.hb_env_stack_observations(P, B, prev_o.data_ptr(), prev_p.data_ptr(), new_o.data_ptr(),
+                                                     new_p.data_ptr(), st), "stack")
+            _lib.check(lib.hb_env_reset_finalize(P, B, new_o.data_ptr(), new_p.data_ptr(), hc, None, st), "finalize")
+        torch.cuda.synchronize()
+        cnt = int(env._reset_count.item())
+        results.append((new_o.clone(), new_p.clone(), cnt, env.reset_env_ids[:cnt].clone(), means.clone(),
+                        env._time_outs_latched.clone(), int(env._host_count[0]), env._scratch_sums.clone()))
+    a, b = results
+    for x, y in zip(a, b):
+        assert (x == y) if isinstance(x, int) else torch.equal(x, y)
+    new_o, new_p, cnt, ids, means, latch, host, sums_after = b
+    keep = ~reset
+    assert torch.equal(new_o[keep][:, :574], prev_o[keep][:, 41:]) and (new_o[reset][:, :574] == 0).all()
+    assert torch.equal(new_p[keep][:, :980], prev_p[keep][:, 70:]) and (new_p[reset][:, :980] == 0).all()
+    assert (new_o[:, 574:] == 7.0).all() and (new_p[:, 980:] == 7.0).all(), "the newest-frame slot belongs to post-physics"
+    assert cnt == int(reset.sum()) == host and torch.equal(ids.long(), reset.nonzero().flatten())
+    if cnt:
+        np.testing.assert_allclose(means.cpu().numpy(), (sums / cnt).float().cpu().numpy() / 24.0, rtol=1e-6)
+        assert torch.equal(latch, env.time_out_buf) and (sums_after == 0).all()

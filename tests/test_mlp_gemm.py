@@ -102,7 +102,7 @@ def test_dgrad_b_mn_major_with_elu_backward(lib, cuda_device, M, N, K):
 
 
 @pytest.mark.parametrize("M,N,K,split", [(512, 616, 4096, 8), (16, 129, 1024, 4), (768, 1051, 3000, 5), (128, 257, 160, 1),
-                                         (256, 513, 24576, 16)])
+                                         (256, 513, 24576, 16), (768, 1051, 24576, 0), (128, 257, 24576, 0), (300, 700, 999, 0)])
 def test_wgrad_both_mn_major_split_k(lib, cuda_device, M, N, K, split):
     """G[M,N] += dZ^T[M,K] @ X[K,N]: both operands are the row-major [K, *] tensors of the forward pass."""
     g = torch.Generator().manual_seed(11 + N)
