@@ -175,10 +175,10 @@ int64_t hb_launch_count(void);
 void hb_launch_count_reset(void);
 /* Tuning switches: "env_bulk_staging" 1 = 1-D bulk async copies (default), 0 = vector loads;
  * "stack_unroll" 4 (default) or 8 = 16-byte vectors in flight per thread of the frame-stack shift;
- * "pdl" 1 = the step's kernels are launched with programmatic stream serialization (each kernel's launch and
- * prologue overlap the tail of its predecessor; griddepcontrol.wait guards the dependent data), 0 = plain launches,
- * -1 (default) = only for shards of <= 8192 envs, where launch latency dominates (measured: +4 % at 4096 envs,
- * -13 % at 65536 envs, where the completion flush behind every wait costs more than the overlap gains). */
+ * "pdl" = programmatic stream serialization of the step's launches (each kernel's launch and prologue overlap the
+ * tail of its predecessor; griddepcontrol.wait guards the dependent data): 1 = all kernels, 0 = none, 2 = only the
+ * PD-torque launches, -1 (default) = PD launches always, the other kernels for shards of <= 8192 envs (measured:
+ * all kernels +4 % at 4096 envs but -13 % at 65536 envs; PD launches only +5.6 % at 16384, +2 % at 65536). */
 int hb_set_option(const char *name, int value);
 
 /* HectorFreeEnv.step prologue: clip, action delay, action noise, clip

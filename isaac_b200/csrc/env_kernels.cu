@@ -1211,12 +1211,12 @@ int hb_env_compute_torques(const hb_env_params *p, const hb_env_buffers *buf, vo
                        reinterpret_cast<uintptr_t>(buf->d_gains) | reinterpret_cast<uintptr_t>(buf->torques)) & 7u) == 0;
     if (vec) {
         const int pairs = total / 2;
-        HB_CUDA(hb::launch_pdl(hb::use_pdl(p->num_envs), pd_torque_kernel, dim3((pairs + 255) / 256), dim3(256), 0, (cudaStream_t)stream,
+        HB_CUDA(hb::launch_pdl(hb::use_pdl_small_kernel(p->num_envs), pd_torque_kernel, dim3((pairs + 255) / 256), dim3(256), 0, (cudaStream_t)stream,
                                reinterpret_cast<const float4 *>(buf->dof_state), reinterpret_cast<const float2 *>(buf->actions),
                                reinterpret_cast<const float2 *>(buf->p_gains), reinterpret_cast<const float2 *>(buf->d_gains),
                                reinterpret_cast<float2 *>(buf->torques), pairs, p->num_dof, p->action_scale, c));
     } else {
-        HB_CUDA(hb::launch_pdl(hb::use_pdl(p->num_envs), pd_torque_scalar_kernel, dim3((total + 255) / 256), dim3(256), 0, (cudaStream_t)stream,
+        HB_CUDA(hb::launch_pdl(hb::use_pdl_small_kernel(p->num_envs), pd_torque_scalar_kernel, dim3((total + 255) / 256), dim3(256), 0, (cudaStream_t)stream,
                                (const float *)buf->dof_state, (const float *)buf->actions, buf->p_gains, buf->d_gains,
                                buf->torques, total, p->num_dof, p->action_scale, c));
     }

@@ -43,9 +43,12 @@ void count_launch(int n = 1);
 inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 int sm_count();   // cached cudaDevAttrMultiProcessorCount of the current device
-extern int g_use_pdl;   // "pdl" option: 1 / 0 = always / never launch the step's kernels with programmatic stream
-                        // serialization; -1 (default) = for shards of at most 8192 envs, where launch latency dominates
-inline bool use_pdl(int num_envs) { return g_use_pdl > 0 || (g_use_pdl < 0 && num_envs <= 8192); }
+extern int g_use_pdl;   // "pdl" option: programmatic stream serialization of the step's kernels: 1 = all, 0 = none,
+                        // 2 = only the PD-torque launches, -1 (default) = PD launches always, the others for shards of
+                        // at most 8192 envs (the completion flush behind griddepcontrol.wait costs more than the
+                        // overlap gains on the large kernels of bigger shards)
+inline bool use_pdl(int num_envs) { return g_use_pdl == 1 || (g_use_pdl < 0 && num_envs <= 8192); }
+inline bool use_pdl_small_kernel(int num_envs) { return g_use_pdl == 2 || g_use_pdl < 0 || use_pdl(num_envs); }
 
 #ifdef __CUDACC__
 // <<<grid, block, smem, stream>>> with the programmatic-dependent-launch attribute (kernels call hb::pdl_wait()).
