@@ -174,7 +174,6 @@ int hb_abi_version(void);
 int64_t hb_launch_count(void);
 void hb_launch_count_reset(void);
 /* Tuning switches: "env_bulk_staging" 1 = 1-D bulk async copies (default), 0 = vector loads;
- * "stack_unroll" 4 (default) or 8 = 16-byte vectors in flight per thread of the frame-stack shift;
  * "pdl" = programmatic stream serialization of the step's launches (each kernel's launch and prologue overlap the
  * tail of its predecessor; griddepcontrol.wait guards the dependent data): 1 = all kernels, 0 = none, 2 = only the
  * PD-torque launches, -1 (default) = PD launches always, the other kernels for shards of <= 8192 envs (measured:

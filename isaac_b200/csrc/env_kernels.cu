@@ -1121,7 +1121,6 @@ stack_finalize_kernel(const float *__restrict__ prev_a, float *__restrict__ next
 }
 
 int g_use_bulk = 1;
-int g_stack_unroll = 4;
 
 // hector frame stacks (hector_config.py:8-20): obs 15 x 41, privileged obs 15 x 70
 constexpr int ROW_OBS = 15 * OBS, ROW_PRIV = 15 * PRIV;
@@ -1130,13 +1129,8 @@ template <int ROW, int FRAME>
 void launch_stack_fixed(const float *prev, float *next, int n, cudaStream_t st) {
     const uint32_t total = (uint32_t)n * ROW;
     const uint32_t vecs = (total + 3u) / 4u;
-    if (g_stack_unroll == 8) {
-        const uint32_t blocks = (vecs + 8 * 256 - 1) / (8 * 256);
-        stack_shift_fixed_kernel<ROW, FRAME, 8><<<blocks, 256, 0, st>>>(prev, next, total);
-    } else {
-        const uint32_t blocks = (vecs + 4 * 256 - 1) / (4 * 256);
-        stack_shift_fixed_kernel<ROW, FRAME, 4><<<blocks, 256, 0, st>>>(prev, next, total);
-    }
+    const uint32_t blocks = (vecs + 4 * 256 - 1) / (4 * 256);
+    stack_shift_fixed_kernel<ROW, FRAME, 4><<<blocks, 256, 0, st>>>(prev, next, total);
 }
 
 bool fits_u32(int n, int row) { return (long long)n * row + 64 * 1024 < (1ll << 32); }
@@ -1167,11 +1161,6 @@ int hb_set_option(const char *name, int value) {
     }
     if (name && !strcmp(name, "pdl")) {
         hb::g_use_pdl = value;
-        return HB_OK;
-    }
-    if (name && !strcmp(name, "stack_unroll")) {
-        HB_REQUIRE(value == 4 || value == 8, "hb_set_option: stack_unroll must be 4 or 8");
-        g_stack_unroll = value;
         return HB_OK;
     }
     hb::set_error("hb_set_option: unknown option '%s'", name ? name : "(null)");
@@ -1299,17 +1288,10 @@ int hb_env_stack_observations(const hb_env_params *p, const hb_env_buffers *buf,
                       p->num_single_priv == PRIV && fits_u32(p->num_envs, row_b);
     if (fast) {
         const uint32_t total_a = (uint32_t)p->num_envs * ROW_OBS, total_b = (uint32_t)p->num_envs * ROW_PRIV;
-        if (g_stack_unroll == 8) {
-            constexpr uint32_t PER = 8 * 256;
-            const uint32_t blocks_a = ((total_a + 3u) / 4u + PER - 1) / PER, blocks_b = ((total_b + 3u) / 4u + PER - 1) / PER;
-            HB_CUDA(hb::launch_pdl(hb::use_pdl(p->num_envs), stack_shift_pair_kernel<ROW_OBS, OBS, ROW_PRIV, PRIV, 8>, dim3(blocks_a + blocks_b), dim3(256), 0,
-                                   st, obs_prev, obs_new, total_a, blocks_a, priv_prev, priv_new, total_b));
-        } else {
-            constexpr uint32_t PER = 4 * 256;
-            const uint32_t blocks_a = ((total_a + 3u) / 4u + PER - 1) / PER, blocks_b = ((total_b + 3u) / 4u + PER - 1) / PER;
-            HB_CUDA(hb::launch_pdl(hb::use_pdl(p->num_envs), stack_shift_pair_kernel<ROW_OBS, OBS, ROW_PRIV, PRIV, 4>, dim3(blocks_a + blocks_b), dim3(256), 0,
-                                   st, obs_prev, obs_new, total_a, blocks_a, priv_prev, priv_new, total_b));
-        }
+        constexpr uint32_t PER = 4 * 256;
+        const uint32_t blocks_a = ((total_a + 3u) / 4u + PER - 1) / PER, blocks_b = ((total_b + 3u) / 4u + PER - 1) / PER;
+        HB_CUDA(hb::launch_pdl(hb::use_pdl(p->num_envs), stack_shift_pair_kernel<ROW_OBS, OBS, ROW_PRIV, PRIV, 4>, dim3(blocks_a + blocks_b), dim3(256), 0,
+                               st, obs_prev, obs_new, total_a, blocks_a, priv_prev, priv_new, total_b));
         HB_CHECK_LAUNCH("stack_shift_pair_kernel");
         return HB_OK;
     }
