@@ -347,11 +347,13 @@ typedef struct hb_adam_params {
     int64_t kl_count;             /* samples behind stats[2] */
 } hb_adam_params;
 /* clip_grad_norm_ + torch.optim.Adam.step (defaults, no weight decay) over one flat parameter buffer.
- * grad_sumsq: fp64 scalar (zeroed by the caller) that hb_grad_sumsq fills; lr_io: fp64 learning rate on
- * the device, updated in place by the adaptive schedule from kl_stats[2].  Gradients are zeroed. */
+ * grad_sumsq: fp64 scalar (zero on entry) that hb_grad_sumsq fills; lr_io: fp64 learning rate on the device,
+ * updated in place by the adaptive schedule from kl_stats[2].  Gradients are zeroed.  If loss_acc is not NULL
+ * (4 doubles), the minibatch's loss sums kl_stats[0..3] are added to it (update()'s running means, ppo.py:176-178)
+ * and kl_stats / grad_sumsq are zeroed for the next minibatch. */
 int hb_grad_sumsq(const float *grads, int64_t n, double *grad_sumsq, void *stream);
 int hb_adam_step(float *params, float *grads, float *exp_avg, float *exp_avg_sq, int64_t n, const hb_adam_params *ap,
-                 const double *grad_sumsq, const double *kl_stats, double *lr_io, void *stream);
+                 double *grad_sumsq, double *kl_stats, double *lr_io, double *loss_acc, void *stream);
 
 #ifdef __cplusplus
 }

@@ -211,7 +211,7 @@ class PPO:
         st = torch.cuda.current_stream(self.device).cuda_stream
         ws = ac.workspace(mb)
         xa, xc, rec = self._xa[i * mb:(i + 1) * mb], self._xc[i * mb:(i + 1) * mb], self._rec[i * mb:(i + 1) * mb]
-        self._stats.zero_()
+        # self._stats is zero here: update() zeroes it once, the optimizer step's epilogue kernel re-arms it
         if ac.fused_head:
             # The actor and critic chains are independent: the critic's GEMMs run on a second stream, so one network's
             # persistent CTAs fill the SMs the other one leaves idle in its last round of tiles.
@@ -248,18 +248,20 @@ class PPO:
             self.grad_allreduce(ac.grad, self._stats)        # sums over ranks (grads already carry 1/global_mb)
 
     def optimizer_step(self, adaptive: int):
-        """clip_grad_norm_ + Adam.step + zero_grad (ppo.py:171-174) with the adaptive-KL rule of :136-148."""
+        """clip_grad_norm_ + Adam.step + zero_grad (ppo.py:171-174) with the adaptive-KL rule of :136-148; the loss
+        sums of the minibatch are folded into self._loss_acc and the per-minibatch accumulators re-armed on the
+        device."""
         ac, lib = self.actor_critic, self._lib
         st = torch.cuda.current_stream(self.device).cuda_stream
         n_flat = ac.flat.numel()
-        self._sumsq.zero_()
         _lib.check(lib.hb_grad_sumsq(ac.grad.data_ptr(), n_flat, self._sumsq.data_ptr(), st), "hb_grad_sumsq")
         self._step += 1
         ap = AdamParams(0.9, 0.999, 1e-8, float(self.max_grad_norm or 0.0), 1.0 - 0.9 ** self._step,
                         1.0 - 0.999 ** self._step, adaptive, float(self.desired_kl or 0.0), self._mb * self.world_size)
         _lib.check(lib.hb_adam_step(ac.flat.data_ptr(), ac.grad.data_ptr(), self._exp_avg.data_ptr(),
                                     self._exp_avg_sq.data_ptr(), n_flat, C.byref(ap), self._sumsq.data_ptr(),
-                                    self._stats.data_ptr(), self._lr_dev.data_ptr(), st), "hb_adam_step")
+                                    self._stats.data_ptr(), self._lr_dev.data_ptr(), self._loss_acc.data_ptr(), st),
+                   "hb_adam_step")
 
     def prepare_minibatches(self, perm=None):
         """mini_batch_generator's gathers (rollout_storage.py:146-182), once per update (the permutation is
@@ -296,11 +298,10 @@ class PPO:
         self._mb, self._lp = mb, PpoLossParams(self.clip_param, self.value_loss_coef, self.entropy_coef,
                                                 int(self.use_clipped_value_loss))
         adaptive = int(self.desired_kl is not None and self.schedule == "adaptive")
-        self._loss_acc.zero_()
+        self._loss_acc.zero_(), self._stats.zero_(), self._sumsq.zero_()
         for _ in range(self.num_learning_epochs):
             for i in range(self.num_mini_batches):
                 self.minibatch_gradients(i)
-                self._loss_acc += self._stats
                 self.optimizer_step(adaptive)
         self._lr_dirty = bool(adaptive)
         num_updates = self.num_learning_epochs * self.num_mini_batches

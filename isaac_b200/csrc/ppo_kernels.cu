@@ -497,12 +497,23 @@ adam_kernel(float *__restrict__ p, float *__restrict__ g, float *__restrict__ m,
     }
 }
 
-__global__ void lr_update_kernel(hb_adam_params ap, const double *__restrict__ kl_stats, double *__restrict__ lr_io) {
-    double lr = *lr_io;
-    const double kl = kl_stats[2] / (double)ap.kl_count;
-    if (kl > ap.desired_kl * 2.0) lr = fmax(1e-5, lr / 1.5);
-    else if (kl < ap.desired_kl / 2.0 && kl > 0.0) lr = fmin(1e-2, lr * 1.5);
-    *lr_io = lr;
+// After every block of adam_kernel has read the old learning rate, the KL sum and the gradient norm: publish the new
+// rate (adaptive schedule), fold this minibatch's loss sums into the running totals of update() (ppo.py:176-178) and
+// re-arm the per-minibatch accumulators, so the host issues no tiny torch kernels between optimizer steps.
+__global__ void step_epilogue_kernel(hb_adam_params ap, double *__restrict__ kl_stats, double *__restrict__ lr_io,
+                                     double *__restrict__ grad_sumsq, double *__restrict__ loss_acc) {
+    if (ap.adaptive) {
+        double lr = *lr_io;
+        const double kl = kl_stats[2] / (double)ap.kl_count;
+        if (kl > ap.desired_kl * 2.0) lr = fmax(1e-5, lr / 1.5);
+        else if (kl < ap.desired_kl / 2.0 && kl > 0.0) lr = fmin(1e-2, lr * 1.5);
+        *lr_io = lr;
+    }
+    if (loss_acc) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) loss_acc[k] += kl_stats[k], kl_stats[k] = 0.0;
+        if (grad_sumsq) *grad_sumsq = 0.0;
+    }
 }
 
 }  // namespace
@@ -611,16 +622,17 @@ int hb_grad_sumsq(const float *grads, int64_t n, double *grad_sumsq, void *strea
 }
 
 int hb_adam_step(float *params, float *grads, float *exp_avg, float *exp_avg_sq, int64_t n, const hb_adam_params *ap,
-                 const double *grad_sumsq, const double *kl_stats, double *lr_io, void *stream) {
+                 double *grad_sumsq, double *kl_stats, double *lr_io, double *loss_acc, void *stream) {
     HB_REQUIRE(params && grads && exp_avg && exp_avg_sq && ap && lr_io && n > 0, "hb_adam_step: bad arguments");
     HB_REQUIRE(ap->max_grad_norm <= 0.0f || grad_sumsq, "hb_adam_step: clipping needs grad_sumsq");
     HB_REQUIRE(!ap->adaptive || (kl_stats && ap->kl_count > 0), "hb_adam_step: adaptive schedule needs kl_stats");
     adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, n, *ap,
                                                                              grad_sumsq, kl_stats, lr_io);
     HB_CHECK_LAUNCH("adam_kernel");
-    if (ap->adaptive) {
-        lr_update_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(*ap, kl_stats, lr_io);
-        HB_CHECK_LAUNCH("lr_update_kernel");
+    HB_REQUIRE(!loss_acc || kl_stats, "hb_adam_step: loss_acc needs the per-minibatch sums");
+    if (ap->adaptive || loss_acc) {
+        step_epilogue_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(*ap, kl_stats, lr_io, grad_sumsq, loss_acc);
+        HB_CHECK_LAUNCH("step_epilogue_kernel");
     }
     return HB_OK;
 }
