@@ -190,6 +190,11 @@ int hb_env_action_prologue(const hb_env_params *p, const hb_env_buffers *buf, co
  * Reads buf->actions, dof_state, p_gains, d_gains; writes buf->torques. */
 int hb_env_compute_torques(const hb_env_params *p, const hb_env_buffers *buf, void *stream);
 
+/* hb_env_action_prologue + the first hb_env_compute_torques of a step in one launch (what step() uses when no host
+ * work is needed between the two: same results as the two calls). */
+int hb_env_prologue_torques(const hb_env_params *p, const hb_env_buffers *buf, const float *actions_in,
+                            const hb_env_noise *noise, void *stream);
+
 /* LeggedRobot.post_physics_step without the observation stacking
  * (envs/base/legged_robot.py:118-153,155-234,303-335,358-396; hector_env.py:53-88,256-539):
  * derived base quantities, command resampling + heading command, push, termination, the 18

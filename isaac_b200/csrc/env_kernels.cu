@@ -126,12 +126,9 @@ __device__ __forceinline__ void rng_uniforms(const Rng &g, int env, int slot, in
 // ------------------------------------------------------------------------------------------
 // a2: HectorFreeEnv.step prologue (hector_env.py:158-169, legged_robot.py:90-91)
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-action_prologue_kernel(const float *__restrict__ a_in, float *__restrict__ actions, const __grid_constant__ hb_env_noise nz,
-                       int total, float clip, float action_delay, float action_noise) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= total) return;
-    const Rng rng = make_rng(nz);
+__device__ __forceinline__ float action_prologue(const float *__restrict__ a_in, const float *__restrict__ actions,
+                                                 const hb_env_noise &nz, const Rng &rng, int i, float clip, float action_delay,
+                                                 float action_noise) {
     const int env = i / NDOF, j = i - env * NDOF;
     float a = clampf(a_in[i], -clip, clip);
     float ud = 0.0f;
@@ -150,7 +147,16 @@ action_prologue_kernel(const float *__restrict__ a_in, float *__restrict__ actio
         z = z4[j & 3];
     }
     a = a + (action_noise * z) * a;
-    actions[i] = clampf(a, -clip, clip);
+    return clampf(a, -clip, clip);
+}
+
+__global__ void __launch_bounds__(256)
+action_prologue_kernel(const float *__restrict__ a_in, float *__restrict__ actions, const __grid_constant__ hb_env_noise nz,
+                       int total, float clip, float action_delay, float action_noise) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const Rng rng = make_rng(nz);
+    actions[i] = action_prologue(a_in, actions, nz, rng, i, clip, action_delay, action_noise);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -173,6 +179,33 @@ pd_torque_kernel(const float4 *__restrict__ dof_state2, const float2 *__restrict
     const float4 s = dof_state2[i];          // q0 qd0 q1 qd1
     const float2 a = actions2[i], kp = kp2[i], kd = kd2[i];
     const int j = (2 * i) % ndof;            // ndof even: a pair never straddles two envs
+    float2 t;
+    t.x = kp.x * ((a.x * action_scale + c.q0[j]) - s.x) - kd.x * s.y;
+    t.y = kp.y * ((a.y * action_scale + c.q0[j + 1]) - s.z) - kd.y * s.w;
+    t.x = clampf(t.x, -c.lim[j], c.lim[j]);
+    t.y = clampf(t.y, -c.lim[j + 1], c.lim[j + 1]);
+    torques2[i] = t;
+}
+
+// step()'s first launch: the action prologue (hector_env.py:158-169) and the first decimation sub-step's torques
+// (legged_robot.py:93-94) in one kernel - a thread owns a DOF pair of one env, so it can run the prologue of its two
+// actions and go straight on to the PD law.
+__global__ void __launch_bounds__(256)
+prologue_pd_kernel(const float *__restrict__ a_in, float *__restrict__ actions, const __grid_constant__ hb_env_noise nz,
+                   float clip, float action_delay, float action_noise, const float4 *__restrict__ dof_state2,
+                   const float2 *__restrict__ kp2, const float2 *__restrict__ kd2, float2 *__restrict__ torques2, int pairs,
+                   float action_scale, const __grid_constant__ PdConsts c) {
+    hb::pdl_trigger();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= pairs) return;
+    const Rng rng = make_rng(nz);
+    float2 a;
+    a.x = action_prologue(a_in, actions, nz, rng, 2 * i, clip, action_delay, action_noise);
+    a.y = action_prologue(a_in, actions, nz, rng, 2 * i + 1, clip, action_delay, action_noise);
+    reinterpret_cast<float2 *>(actions)[i] = a;
+    const float4 s = dof_state2[i];
+    const float2 kp = kp2[i], kd = kd2[i];
+    const int j = (2 * i) % NDOF;
     float2 t;
     t.x = kp.x * ((a.x * action_scale + c.q0[j]) - s.x) - kd.x * s.y;
     t.y = kp.y * ((a.y * action_scale + c.q0[j + 1]) - s.z) - kd.y * s.w;
@@ -1185,6 +1218,30 @@ int hb_env_action_prologue(const hb_env_params *p, const hb_env_buffers *buf, co
     action_prologue_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
         actions_in, buf->actions, noise ? *noise : none, total, p->clip_actions, p->action_delay, p->action_noise);
     HB_CHECK_LAUNCH("action_prologue_kernel");
+    return HB_OK;
+}
+
+int hb_env_prologue_torques(const hb_env_params *p, const hb_env_buffers *buf, const float *actions_in,
+                            const hb_env_noise *noise, void *stream) {
+    if (int rc = check_params(p, buf, "hb_env_prologue_torques")) return rc;
+    HB_REQUIRE(actions_in && buf->actions && buf->dof_state && buf->p_gains && buf->d_gains && buf->torques,
+               "hb_env_prologue_torques: null buffer");
+    const bool vec = hb::aligned16(buf->dof_state) &&
+                     ((reinterpret_cast<uintptr_t>(buf->actions) | reinterpret_cast<uintptr_t>(buf->p_gains) |
+                       reinterpret_cast<uintptr_t>(buf->d_gains) | reinterpret_cast<uintptr_t>(buf->torques)) & 7u) == 0;
+    if (!vec) {        // unaligned buffers: the two separate launches
+        if (int rc = hb_env_action_prologue(p, buf, actions_in, noise, stream)) return rc;
+        return hb_env_compute_torques(p, buf, stream);
+    }
+    PdConsts c;
+    for (int j = 0; j < HB_MAX_DOF; ++j) c.q0[j] = p->default_dof_pos[j], c.lim[j] = p->torque_limits[j];
+    const int pairs = p->num_envs * p->num_dof / 2;
+    hb_env_noise none = {};
+    prologue_pd_kernel<<<(pairs + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+        actions_in, buf->actions, noise ? *noise : none, p->clip_actions, p->action_delay, p->action_noise,
+        reinterpret_cast<const float4 *>(buf->dof_state), reinterpret_cast<const float2 *>(buf->p_gains),
+        reinterpret_cast<const float2 *>(buf->d_gains), reinterpret_cast<float2 *>(buf->torques), pairs, p->action_scale, c);
+    HB_CHECK_LAUNCH("prologue_pd_kernel");
     return HB_OK;
 }
 

@@ -12,6 +12,8 @@ The per-step work is five kinds of kernel launch through the C ABI (include/hect
 
     hb_env_action_prologue      x1   hector_env.py:158-169
     hb_env_compute_torques      x decimation, around the opaque physics.simulate()
+                                     (the CUDA-graph path fuses the prologue with the first sub-step:
+                                     hb_env_prologue_torques)
     hb_env_post_physics         x1   legged_robot.py:118-234,303-396 + newest obs frames
     hb_env_stack_finalize       x1   hector_env.py:246-261 (frame stacking into the ping-pong buffers, history zeroing
                                      of the envs just reset) + legged_robot.py:142,198-209 (ascending reset ids,
@@ -356,7 +358,7 @@ class HectorFreeEnvB200:
     def enable_cuda_graph(self):
         """Capture the step's launch sequence for physics stages that need no host work between the
         decimation sub-steps (`physics.capturable`, e.g. the synthetic stage used by tests and bench.py).
-        Two graphs per ping-pong parity: A = action prologue, first PD launch; then the host
+        Two graphs per ping-pong parity: A = action prologue + first PD sub-step (one kernel); then the host
         hands the previous step's reset ids to the physics stage (legged_robot.py:370-372,394-396) while A
         runs; B = the remaining PD launches, post-physics, the frame-stack shift and the reset finalisation.  Push steps (every
         `push_interval`) and steps with injected noise take the eager path."""
@@ -380,9 +382,8 @@ class HectorFreeEnvB200:
                 st = self._stream()
                 nz = EnvNoise()
                 self._bind_device_rng(nz)
-                _lib.check(lib.hb_env_action_prologue(self._pp, self._pb, self._g_actions.data_ptr(), C.byref(nz), st),
-                           "hb_env_action_prologue")
-                _lib.check(lib.hb_env_compute_torques(self._pp, self._pb, st), "hb_env_compute_torques")
+                _lib.check(lib.hb_env_prologue_torques(self._pp, self._pb, self._g_actions.data_ptr(), C.byref(nz), st),
+                           "hb_env_prologue_torques")
             pool = pool or ga.pool()
             with torch.cuda.graph(gb, pool=pool):
                 st = self._stream()
@@ -395,7 +396,7 @@ class HectorFreeEnvB200:
             graphs[parity] = (ga, gb, nz)
         self._cur, self._step_index, self._pending_event = saved
         self._graphs = graphs
-        self.graph_launches_per_step = 1 + dec + 2     # this library's kernels per replayed step (prologue, PD, post, stack+finalize)
+        self.graph_launches_per_step = dec + 2     # this library's kernels per replayed step (prologue+PD, PD x9, post, stack+finalize)
 
     def _step_graph(self, actions):
         ga, gb, _ = self._graphs[self._cur]
