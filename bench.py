@@ -196,7 +196,35 @@ def fill_storage(st, gen_seed, device):
     st.actions_log_prob.copy_(-0.5 * ((st.actions - st.mu) ** 2).sum(-1, keepdim=True) - 9.19)
 
 
-def bench_ppo(args, dev, n, world, rank):
+def bench_iteration(env, phys, phys_frames, alg, dev, n, iters=2):
+    """One learning iteration the way OnPolicyRunner.learn drives it (on_policy_runner.py:124-170): T x (act, env.step,
+    process_env_step), compute_returns, update - the reference's own `Perf/total_fps` = T * N / (collection + learning)
+    (on_policy_runner.py:199-213), wall clock, physics stubbed."""
+    frames = len(phys_frames)
+    obs, priv = env.get_observations(), env.get_privileged_observations()
+    out = None
+    for it in range(iters + 1):
+        alg.storage.clear()
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        for t in range(T_GAE):
+            actions = alg.act(obs, priv)
+            phys.load_frame(phys_frames[t % frames])
+            obs, priv, rew, dones, infos = env.step(actions)
+            alg.process_env_step(rew, dones, infos)
+        torch.cuda.synchronize(dev)
+        t1 = time.perf_counter()
+        alg.compute_returns(priv)
+        alg.update()
+        torch.cuda.synchronize(dev)
+        t2 = time.perf_counter()
+        out = {"total_fps": T_GAE * n / (t2 - t0), "collection_ms": 1e3 * (t1 - t0), "learning_ms": 1e3 * (t2 - t1),
+               "unit": "env-steps/s per GPU, wall clock, T=24 rollout + 5 epochs x 4 minibatches",
+               "definition": "Perf/total_fps of on_policy_runner.py:199-213 (physics stubbed)"}
+    return out
+
+
+def bench_ppo(args, dev, n, world, rank, env=None, phys=None, phys_frames=None):
     """compute_returns + update() on [T=24, n] rollouts: PPO samples/s (BASELINE configs[1]/[4])."""
     import torch.distributed as dist
     from isaac_b200.algo.actor_critic import ActorCritic
@@ -252,7 +280,9 @@ def bench_ppo(args, dev, n, world, rank):
     tflops = passes * PPO_FLOP_PER_SAMPLE_PASS / (ms * 1e-3) / 1e12
     peak_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     bf16 = json.load(open(peak_path))["bf16_tflops_sustained"] if os.path.exists(peak_path) else 1400.0
+    iteration = bench_iteration(env, phys, phys_frames, alg, dev, n) if env is not None else None
     return {"value": samples / (ms * 1e-3), "unit": "samples/s", "sample_passes_per_s": passes / (ms * 1e-3),
+            "iteration": iteration,
             "ms_per_update": ms, "T": T_GAE, "epochs": 5, "mini_batches": 4, "dtype": "tf32 operands, f32 accumulate",
             "tensor_tflops": tflops, "tensor_peak_tflops": bf16 * world / 2,
             "tensor_frac": tflops / (bf16 * world / 2),
@@ -404,7 +434,7 @@ def run_b200(args, rank, world):
     ret_, adv_ = torch.empty_like(r_), torch.empty_like(r_)
     gae_stats = torch.zeros(2, dtype=torch.float64, device=dev)
     k_gae = time_launch(lambda st: gae_compute_returns(r_, v_, d_, lv_, ret_, adv_, 0.994, 0.9, stats=gae_stats) and None)
-    ppo = None if args.skip_ppo else bench_ppo(args, dev, n, world, rank)
+    ppo = None if args.skip_ppo else bench_ppo(args, dev, n, world, rank, env, phys, phys_frames)
     clocks = sampler.summary()
 
     # ---- e2e: host buffers in, host buffers out, env's own noise ----

@@ -433,6 +433,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             }
         }
     }
+    __syncwarp();                    // single-lane roles (producer, MMA issuer) rejoin their warps before the aligned barrier
     tc_fence_before();
     if (PAIR) cluster_sync();        // the leader's MMAs read the peer's shared memory: leave together
     else __syncthreads();
