@@ -36,7 +36,7 @@ enum Epilogue { EPI_STORE = 0, EPI_BIAS = 1, EPI_BIAS_ELU = 2, EPI_ELU_BWD = 3, 
 struct GemmArgs {
     int M, N, K;                  // logical sizes (K = contraction length)
     int kb_per_split;             // k-blocks of one k split
-    int tiles_n, splits, total_tiles;   // tile list: (m tile, k split, n tile), n fastest
+    int tiles_m, tiles_n, splits, total_tiles;   // tile list: (k split, m tile, n tile), n fastest
     float *D;                     // [M, ldd]
     int ldd;
     const float *bias;            // bias[n * bias_stride] (weights and bias share one packed matrix)
@@ -179,7 +179,7 @@ __host__ __device__ constexpr size_t smem_bytes_for() {
 }
 
 // Persistent, warp-specialised: one CTA per SM walks a static list of output tiles
-//   tile t = blockIdx.x + i * gridDim.x  ->  (m tile, n tile, k split), n fastest so that the CTAs running at the
+//   tile t = blockIdx.x + i * gridDim.x  ->  (k split, m tile, n tile), n fastest so that the CTAs running at the
 //   same time share the rows of A in L2 (the weights are small and always L2-resident).
 // Three pipelines: shared-memory stages (TMA <-> MMA), two TMEM accumulators (MMA <-> epilogue: the epilogue of tile
 // i overlaps the main loop of tile i + 1), and the tile list.
@@ -224,10 +224,12 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     const uint32_t tmem_base = tmem_base_smem;
 
     auto tile_coords = [&](int t, int &m0, int &n0, int &kb_begin, int &nkb) {
+        // n fastest, then m, then the k split: the tiles in flight at any time share their k slices of A and B, so
+        // with split-K (weight gradients: both operands are minibatch-sized) every byte is fetched from HBM once
         const int nt = t % g.tiles_n;
         const int rest = t / g.tiles_n;
-        const int z = rest % g.splits;
-        const int mt = rest / g.splits;
+        const int mt = rest % g.tiles_m;
+        const int z = rest / g.tiles_m;
         m0 = PAIR ? (mt * 2 + (int)rank) * BM : mt * BM, n0 = nt * BN;
         kb_begin = z * g.kb_per_split;
         nkb = min(kb_begin + g.kb_per_split, kb_total) - kb_begin;
@@ -527,7 +529,7 @@ int launch(const hb_gemm_desc *d, cudaStream_t st) {
     g.D = d->D, g.ldd = d->ldd, g.bias = d->bias, g.bias_stride = d->bias_stride, g.H = d->H, g.ldh = d->ldh;
     const int rows_per_tile = PAIR ? 2 * BM : BM;
     const int tiles_m = (d->M + rows_per_tile - 1) / rows_per_tile;
-    g.tiles_n = (d->N + BN - 1) / BN, g.splits = splits;
+    g.tiles_m = tiles_m, g.tiles_n = (d->N + BN - 1) / BN, g.splits = splits;
     g.total_tiles = tiles_m * g.tiles_n * splits;
     if (PAIR) {
         const int pairs = hb::sm_count() / 2;
