@@ -904,10 +904,9 @@ post_physics_kernel(const __grid_constant__ hb_env_params p, const __grid_consta
 
 // ------------------------------------------------------------------------------------------
 // a8 (stacking): new[:, 0:(S-1)*F] = prev[:, F:S*F]  — a flat copy shifted by one frame with a
-// hole of F floats per row (the newest frame, written by post_physics_kernel).  The shift does
-// not depend on this step's physics, so it runs on a forked stream while the PD sub-steps, the
-// physics and post_physics_kernel run; the (rare) reset envs get their carried frames zeroed
-// afterwards by reset_fixup_kernel (reset_idx, hector_env.py:256-261).
+// hole of F floats per row (the newest frame, written by post_physics_kernel).  With CHECK_RESET the
+// carried frames of the envs post-physics just reset are written as zeros (reset_idx,
+// hector_env.py:256-261); without it that is left to reset_finalize_kernel.
 // Destination vectors are 16-byte aligned; the source is 4*F bytes further on, which is only
 // 4-byte aligned for F = 41, so each thread loads the aligned vector below its source window
 // and takes the missing floats from its neighbour lane (shuffle); F % 4 picks the rotation.

@@ -8,7 +8,7 @@ envs/custom/hector_env.py:158-261):
 
 and the same attribute names the runner and `play.py` read (dof_pos, dof_vel, torques,
 commands, base_lin_vel, base_ang_vel, contact_forces, feet_indices, episode_sums, ...).
-The per-step work is five kinds of kernel launch through the C ABI (include/hector_b200.h):
+The per-step work is four kinds of kernel launch through the C ABI (include/hector_b200.h), 12 launches in all:
 
     hb_env_action_prologue      x1   hector_env.py:158-169
     hb_env_compute_torques      x decimation, around the opaque physics.simulate()

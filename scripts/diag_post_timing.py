@@ -52,8 +52,7 @@ assert fn2(gt.ctypes.data, gt.size) == 0
 gt = gt.reshape(tiles, 3).astype(np.float64)
 t_first = gt[:, 0].min()
 start, done = (gt[:, 0] - t_first) / 1e3, (gt[:, 1] - t_first) / 1e3
-tail_done = (gt[:, 2].max() - t_first) / 1e3          # only the ticket-last CTA of this launch wrote a fresh stamp
-print(f"  global timeline (us): first CTA start 0.0, last CTA start {start.max():.1f}, last stores done {done.max():.1f}, "
-      f"tail done {tail_done:.1f} (tail = {tail_done - done.max():.1f}); CTA lifetime median {np.median(done - start):.1f}")
+print(f"  global timeline (us): first CTA start 0.0, last CTA start {start.max():.1f}, last stores done {done.max():.1f}; "
+      f"CTA lifetime median {np.median(done - start):.1f}")
 hist, edges = np.histogram(start, bins=8)
 print("  CTA start histogram:", " ".join(f"{e:.0f}us:{h}" for h, e in zip(hist, edges)))
