@@ -95,6 +95,9 @@ class PPO:
         self.injected_perm = None           # parity: the randperm of the next update()
         self._recorded_slot = None          # rollout slot already filled by the fast path of act()
         self._side_stream = torch.cuda.Stream(self.device) if self.device.type == "cuda" else None
+        self.graph_rollout = True           # PPO.act: replay the hidden-layer GEMMs from a CUDA graph for small shards
+        self.graph_rollout_max_envs = 16384
+        self._act_graphs, self._act_stage = {}, None
 
     # ------------------------------------------------------------------ learning rate (device-resident)
     @property
@@ -131,17 +134,28 @@ class PPO:
         n = obs.shape[0]
         st = torch.cuda.current_stream(self.device).cuda_stream
         ws = ac.workspace(n)
-        eps = self.injected_eps if self.injected_eps is not None else torch.randn(n, ac.num_actions, device=self.device)
-        self.injected_eps = None
         t = self.transition
         fast = (ac.fused_head and s is not None and s.step < s.num_transitions_per_env and n == s.num_envs
                 and s.privileged_observations is not None and obs.is_cuda and critic_obs.is_cuda)
+        graphed = (fast and self.graph_rollout and self.injected_eps is None and n <= self.graph_rollout_max_envs
+                   and obs.is_contiguous() and critic_obs.is_contiguous())
+        if graphed:
+            # small shards: the hidden layers of both networks are replayed from one CUDA graph (launch-bound at this
+            # size), the two chains on parallel branches; the graph reads the observations where the env left them
+            k = s.step
+            h3a, h3c, eps, xa, xc = self._replay_act_graph(obs, critic_obs, n, ws)
+            s._observations[k].copy_(xa)
+            s._privileged_observations[k].copy_(xc)
+        else:
+            eps = self.injected_eps if self.injected_eps is not None else torch.randn(n, ac.num_actions, device=self.device)
+        self.injected_eps = None
         if fast:
             k = s.step
-            s.observations[k].copy_(obs)
-            s.privileged_observations[k].copy_(critic_obs)
-            h3a = ac._mlp_forward("actor", s._observations[k], ws, hidden_only=True)
-            h3c = ac._mlp_forward("critic", s._privileged_observations[k], ws, hidden_only=True)
+            if not graphed:
+                s.observations[k].copy_(obs)
+                s.privileged_observations[k].copy_(critic_obs)
+                h3a = ac._mlp_forward("actor", s._observations[k], ws, hidden_only=True)
+                h3c = ac._mlp_forward("critic", s._privileged_observations[k], ws, hidden_only=True)
             La, Lc = [L for L in ac.layers if L.last]
             _lib.check(lib.hb_ppo_act_fused(h3a.data_ptr(), h3a.stride(0), h3c.data_ptr(), h3c.stride(0),
                                             ac._matrix(ac.flat, La).data_ptr(), ac._matrix(ac.flat, Lc).data_ptr(), La.ld,
@@ -166,6 +180,42 @@ class PPO:
         t.action_mean, t.action_sigma = mu, sigma
         t.observations, t.critic_observations = obs, critic_obs          # recorded before env.step() (ppo.py:98-100)
         return t.actions
+
+    def _replay_act_graph(self, obs, critic_obs, n, ws):
+        """Capture (once per pair of observation buffers: the env ping-pongs between two) and replay: padded staging
+        copies of both observation tensors, the three hidden-layer GEMMs of each network on two branches, the
+        N(0,1) draw of the sample.  Returns the last hidden activations, the draw and the staged observations."""
+        ac = self.actor_critic
+        key = (obs.data_ptr(), critic_obs.data_ptr(), n)
+        entry = self._act_graphs.get(key)
+        if entry is None:
+            dev = self.device
+            if self._act_stage is None or self._act_stage[0].shape[0] != n:
+                self._act_stage = (torch.zeros(n, pad4(ac.num_actor_obs + 1), device=dev),
+                                   torch.zeros(n, pad4(ac.num_critic_obs + 1), device=dev),
+                                   torch.zeros(n, ac.num_actions, device=dev))
+            xa, xc, eps = self._act_stage
+            torch.cuda.synchronize(dev)
+            g = torch.cuda.CUDAGraph()
+            side = self._side_stream
+            with torch.cuda.graph(g):
+                main = torch.cuda.current_stream(dev)
+                side.wait_stream(main)
+                xa[:, :ac.num_actor_obs].copy_(obs)
+                h3a = ac._mlp_forward("actor", xa, ws, hidden_only=True)
+                eps.normal_()
+                with torch.cuda.stream(side):
+                    xc[:, :ac.num_critic_obs].copy_(critic_obs)
+                    h3c = ac._mlp_forward("critic", xc, ws, hidden_only=True)
+                main.wait_stream(side)
+            entry = (g, h3a, h3c)
+            if len(self._act_graphs) >= 8:          # observation buffers changed (new env): drop the stale graphs
+                self._act_graphs.clear()
+            self._act_graphs[key] = entry
+        g, h3a, h3c = entry
+        g.replay()
+        xa, xc, eps = self._act_stage
+        return h3a, h3c, eps, xa, xc
 
     def process_env_step(self, rewards, dones, infos):
         """ppo.py:103-113.  After the fast path of act() only rewards (with the time-out bootstrap) and dones are

@@ -321,3 +321,35 @@ def test_fused_head_matches_autograd_from_hidden(lib, cuda_device):
     torch.cuda.synchronize()
     want_r = rew + 0.994 * (val.cpu() * tos.float())
     assert torch.equal(r_out.cpu(), want_r) and torch.equal(d_out.cpu(), dn.to(torch.uint8))
+
+
+def test_graphed_rollout_equals_eager(lib, cuda_device):
+    """PPO.act's CUDA-graph replay (small shards, own N(0,1) draw) must leave in the rollout slot exactly what the
+    eager path writes when it is handed the same draw; the two observation buffers of the env's ping-pong get one
+    graph each."""
+    dev = cuda_device
+    n, t = 256, 6
+    cfg = dict(mg.PPO_ALG, schedule="fixed")
+    alg_g, _, _ = make_pair(dev, n, t, cfg)
+    alg_e, _, _ = make_pair(dev, n, t, cfg)
+    alg_e.graph_rollout = False
+    alg_e.actor_critic.load_state_dict(alg_g.actor_critic.state_dict())
+    g = torch.Generator().manual_seed(3)
+    bufs = [(torch.randn(n, 615, generator=g).to(dev), torch.randn(n, 1050, generator=g).to(dev)) for _ in range(2)]
+    for k in range(t):
+        obs, cobs = bufs[k & 1]
+        obs.copy_(torch.randn(n, 615, generator=g)), cobs.copy_(torch.randn(n, 1050, generator=g))
+        a_g = alg_g.act(obs, cobs)
+        eps = alg_g._act_stage[2].clone()
+        alg_e.injected_eps = eps
+        a_e = alg_e.act(obs, cobs)
+        assert torch.equal(a_g, a_e), k
+        rew, dn = torch.rand(n, generator=g).to(dev), (torch.rand(n, generator=g) < 0.1).to(dev)
+        infos = {"time_outs": (torch.rand(n, generator=g) < 0.1).to(dev)}
+        alg_g.process_env_step(rew, dn, infos), alg_e.process_env_step(rew, dn, infos)
+    torch.cuda.synchronize()
+    assert len(alg_g._act_graphs) == 2
+    assert abs(eps.mean().item()) < 0.1 and abs(eps.std().item() - 1.0) < 0.1
+    for name in ("observations", "privileged_observations", "actions", "actions_log_prob", "mu", "sigma", "values", "rewards",
+                 "dones"):
+        assert torch.equal(getattr(alg_g.storage, name), getattr(alg_e.storage, name)), name
