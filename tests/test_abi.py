@@ -39,6 +39,24 @@ def test_bad_arguments_return_status_not_crash(lib):
     rc = lib.hb_gae_returns(None, None, None, None, None, None, None, 4, 4, 0.99, 0.95, None)
     assert rc == -1
     assert lib.hb_set_option(b"no_such_option", 1) == -1
+    # every entry point validates before it launches: null structs / pointers come back as HB_ERR_BAD_ARG (-1)
+    assert lib.hb_env_prologue_torques(None, None, None, None, None) == -1
+    assert lib.hb_env_post_physics(None, None, None, None, None, 1, None) == -1
+    assert lib.hb_env_stack_finalize(None, None, None, None, None, None, None, None, None) == -1
+    assert lib.hb_env_reset_finalize(None, None, None, None, None, None, None) == -1
+    assert lib.hb_stack_shift(None, None, None, 4, 615, 41, None) == -1
+    assert lib.hb_ppo_head_fused(None, 132, None, 132, None, None, 132, None, None, 8, 8, None, None, None, 128, None, None,
+                                 None, None, None) == -1
+    assert lib.hb_ppo_act_fused(None, 132, None, 132, None, None, 132, None, None, 8, None, None, None, None, None, None) == -1
+    assert lib.hb_ppo_record_step(None, None, None, None, 0.99, 8, None, None, None) == -1
+    assert lib.hb_adam_step(None, None, None, None, 8, None, None, None, None, None, None) == -1
+    d = _lib.GemmDesc()
+    assert lib.hb_gemm_tf32(ctypes.byref(d), None) == -1 and b"null" in lib.hb_last_error()
+    p, b = _lib.EnvParams(), _lib.EnvBuffers()
+    p.abi_version, p.num_envs, p.resample_interval, p.num_dof = _lib.HB_ABI_VERSION + 1, 4, 1, 10
+    assert lib.hb_env_compute_torques(ctypes.byref(p), ctypes.byref(b), None) == -1 and b"ABI version" in lib.hb_last_error()
+    p.abi_version, p.num_dof = _lib.HB_ABI_VERSION, 12
+    assert lib.hb_env_compute_torques(ctypes.byref(p), ctypes.byref(b), None) == -1 and b"10-DOF" in lib.hb_last_error()
 
 
 def test_only_sm100a_is_embedded(lib):
