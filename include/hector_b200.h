@@ -178,6 +178,8 @@ void hb_launch_count_reset(void);
  * tail of its predecessor; griddepcontrol.wait guards the dependent data): 1 = all kernels, 0 = none, 2 = only the
  * PD-torque launches, -1 (default) = PD launches always, the other kernels for shards of <= 8192 envs (measured:
  * all kernels +4 % at 4096 envs but -13 % at 65536 envs; PD launches only +5.6 % at 16384, +2 % at 65536). */
+/* "gemm_pdl" 1 (default) / 0: hb_gemm_tf32 launches with programmatic stream serialization (a GEMM's set-up - tensor-map
+ * prefetch, barriers, TMEM allocation, cluster rendezvous - overlaps the previous kernel's last tiles). */
 int hb_set_option(const char *name, int value);
 
 /* HectorFreeEnv.step prologue: clip, action delay, action noise, clip

@@ -1191,6 +1191,10 @@ int hb_set_option(const char *name, int value) {
         g_use_bulk = value;
         return HB_OK;
     }
+    if (name && !strcmp(name, "gemm_pdl")) {
+        hb::g_gemm_pdl = value != 0;
+        return HB_OK;
+    }
     if (name && !strcmp(name, "pdl")) {
         hb::g_use_pdl = value;
         return HB_OK;

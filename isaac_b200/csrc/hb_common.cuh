@@ -47,6 +47,7 @@ extern int g_use_pdl;   // "pdl" option: programmatic stream serialization of th
                         // 2 = only the PD-torque launches, -1 (default) = PD launches always, the others for shards of
                         // at most 8192 envs (the completion flush behind griddepcontrol.wait costs more than the
                         // overlap gains on the large kernels of bigger shards)
+extern int g_gemm_pdl;  // "gemm_pdl" option: 1 (default) = GEMM launches overlap their set-up with the previous kernel's tail
 inline bool use_pdl(int num_envs) { return g_use_pdl == 1 || (g_use_pdl < 0 && num_envs <= 8192); }
 inline bool use_pdl_small_kernel(int num_envs) { return g_use_pdl == 2 || g_use_pdl < 0 || use_pdl(num_envs); }
 

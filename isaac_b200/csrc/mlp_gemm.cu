@@ -222,6 +222,10 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_smem;
+    // Programmatic dependent launch: everything above (tensor-map prefetch, barriers, TMEM, cluster rendezvous) ran
+    // while the previous kernel of the stream was still draining its last tiles; its results are touched only from here.
+    hb::pdl_trigger();
+    hb::pdl_wait();
 
     auto tile_coords = [&](int t, int &m0, int &n0, int &kb_begin, int &nkb) {
         // n fastest, then m, then the k split: the tiles in flight at any time share their k slices of A and B, so
@@ -531,20 +535,25 @@ int launch(const hb_gemm_desc *d, cudaStream_t st) {
     const int tiles_m = (d->M + rows_per_tile - 1) / rows_per_tile;
     g.tiles_m = tiles_m, g.tiles_n = (d->N + BN - 1) / BN, g.splits = splits;
     g.total_tiles = tiles_m * g.tiles_n * splits;
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute at[2];
+    int nat = 0;
+    at[nat].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[nat].val.programmaticStreamSerializationAllowed = hb::g_gemm_pdl ? 1 : 0;
+    ++nat;
+    int grid;
     if (PAIR) {
         const int pairs = hb::sm_count() / 2;
-        const int grid = 2 * (g.total_tiles < pairs ? g.total_tiles : pairs);
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(grid), cfg.blockDim = dim3(GEMM_THREADS), cfg.dynamicSmemBytes = SMEM, cfg.stream = st;
-        cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeClusterDimension;
-        at[0].val.clusterDim.x = 2, at[0].val.clusterDim.y = 1, at[0].val.clusterDim.z = 1;
-        cfg.attrs = at, cfg.numAttrs = 1;
-        HB_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, mb, g));
+        grid = 2 * (g.total_tiles < pairs ? g.total_tiles : pairs);
+        at[nat].id = cudaLaunchAttributeClusterDimension;
+        at[nat].val.clusterDim.x = 2, at[nat].val.clusterDim.y = 1, at[nat].val.clusterDim.z = 1;
+        ++nat;
     } else {
-        const int grid = g.total_tiles < hb::sm_count() ? g.total_tiles : hb::sm_count();
-        kern<<<grid, GEMM_THREADS, SMEM, st>>>(ma, mb, g);
+        grid = g.total_tiles < hb::sm_count() ? g.total_tiles : hb::sm_count();
     }
+    cfg.gridDim = dim3(grid), cfg.blockDim = dim3(GEMM_THREADS), cfg.dynamicSmemBytes = SMEM, cfg.stream = st;
+    cfg.attrs = at, cfg.numAttrs = nat;
+    HB_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, mb, g));
     HB_CHECK_LAUNCH("gemm_tf32_kernel");
     return HB_OK;
 }

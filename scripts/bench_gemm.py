@@ -26,6 +26,8 @@ for i, a in enumerate(sys.argv):
     if a == "--opt":
         k, v = sys.argv[i + 1].split("=")
         _lib.check(lib.hb_set_option(k.encode(), int(v)), a)
+if "--no-gemm-pdl" in sys.argv:
+    lib.hb_set_option(b"gemm_pdl", 0)
 if "--no-pair" in sys.argv:
     lib.hb_gemm_set_pair_mode(0)
 torch.manual_seed(5)
