@@ -520,11 +520,12 @@ int launch(const hb_gemm_desc *d, cudaStream_t st) {
     const int kb_total = (d->K + BK - 1) / BK;
     int splits = d->split_k > 0 ? d->split_k : 1;
     if (d->split_k == 0 && EPI == EPI_ATOMIC) {
-        // automatic split-K: about two rounds of tiles over the SMs (SM pairs in pair mode)
+        // automatic split-K: about two rounds of tiles over the SMs (SM pairs in pair mode); one round when the output
+        // has only a few tiles, where the atomic accumulation of a second round costs more than the shorter k ranges save
         const int slots = PAIR ? hb::sm_count() / 2 : hb::sm_count();
         const int rows = PAIR ? 2 * BM : BM;
         const int tiles = ((d->M + rows - 1) / rows) * ((d->N + BN - 1) / BN);
-        splits = (2 * slots) / tiles;
+        splits = (tiles <= 2 ? slots : 2 * slots) / tiles;
         if (splits < 1) splits = 1;
     }
     if (splits > kb_total) splits = kb_total > 0 ? kb_total : 1;
