@@ -482,18 +482,25 @@ adam_kernel(float *__restrict__ p, float *__restrict__ g, float *__restrict__ m,
     }
     const float step_size = (float)(lr / ap.bias_correction1);
     const float bc2_sqrt = (float)sqrt(ap.bias_correction2);
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) {
-        const float gi = g[i] * scale;
-        float mi = m[i], vi = v[i];
+    auto update = [&](float &pi, float &gi_io, float &mi, float &vi) {
+        const float gi = gi_io * scale;
         mi = mi + (gi - mi) * (1.0f - ap.beta1);                    // exp_avg.lerp_(grad, 1 - beta1)
         vi = vi * ap.beta2 + (1.0f - ap.beta2) * gi * gi;           // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
         const float denom = sqrtf(vi) / bc2_sqrt + ap.eps;
-        p[i] = p[i] - step_size * (mi / denom);                     // param.addcdiv_(exp_avg, denom, value=-step_size)
-        m[i] = mi, v[i] = vi, g[i] = 0.0f;                          // optimizer.zero_grad() for the next minibatch
-    }
-    if (ap.adaptive) {
-        // the new rate is published by a second, tiny launch (hb_adam_step) once every block has read the old one
+        pi = pi - step_size * (mi / denom);                         // param.addcdiv_(exp_avg, denom, value=-step_size)
+        gi_io = 0.0f;                                               // optimizer.zero_grad() for the next minibatch
+    };
+    // four parameters per thread (the scalar preamble above is per thread); the flat buffers are 16-byte aligned
+    const long long i4 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i4 + 3 < n) {
+        float4 p4 = *reinterpret_cast<float4 *>(p + i4), g4 = *reinterpret_cast<float4 *>(g + i4);
+        float4 m4 = *reinterpret_cast<float4 *>(m + i4), v4 = *reinterpret_cast<float4 *>(v + i4);
+        update(p4.x, g4.x, m4.x, v4.x), update(p4.y, g4.y, m4.y, v4.y);
+        update(p4.z, g4.z, m4.z, v4.z), update(p4.w, g4.w, m4.w, v4.w);
+        *reinterpret_cast<float4 *>(p + i4) = p4, *reinterpret_cast<float4 *>(g + i4) = g4;
+        *reinterpret_cast<float4 *>(m + i4) = m4, *reinterpret_cast<float4 *>(v + i4) = v4;
+    } else {
+        for (long long i = i4; i < n; ++i) update(p[i], g[i], m[i], v[i]);
     }
 }
 
@@ -626,7 +633,9 @@ int hb_adam_step(float *params, float *grads, float *exp_avg, float *exp_avg_sq,
     HB_REQUIRE(params && grads && exp_avg && exp_avg_sq && ap && lr_io && n > 0, "hb_adam_step: bad arguments");
     HB_REQUIRE(ap->max_grad_norm <= 0.0f || grad_sumsq, "hb_adam_step: clipping needs grad_sumsq");
     HB_REQUIRE(!ap->adaptive || (kl_stats && ap->kl_count > 0), "hb_adam_step: adaptive schedule needs kl_stats");
-    adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, n, *ap,
+    HB_REQUIRE(hb::aligned16(params) && hb::aligned16(grads) && hb::aligned16(exp_avg) && hb::aligned16(exp_avg_sq),
+               "hb_adam_step: 16-byte aligned buffers");
+    adam_kernel<<<(unsigned)((n + 1023) / 1024), 256, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, n, *ap,
                                                                              grad_sumsq, kl_stats, lr_io);
     HB_CHECK_LAUNCH("adam_kernel");
     HB_REQUIRE(!loss_acc || kl_stats, "hb_adam_step: loss_acc needs the per-minibatch sums");
