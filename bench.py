@@ -4,18 +4,24 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--envs E] [--impl reference]
 
 A "step" is one `env.step(actions)` over E environments per GPU with the opaque physics stage
-stubbed: action prologue, `decimation`=10 PD-torque launches, the fused
-post-physics kernel (termination, 18 reward terms, resets, newest observation frames), the
-frame-stacking kernel and the reset finalisation (ids, count to pinned host memory, episode means).
+stubbed: action prologue + `decimation`=10 PD-torque sub-steps (10 launches), the fused
+post-physics kernel (termination, 18 reward terms, resets, newest observation frames) and the
+frame-stacking + reset-finalisation kernel (ids, count to pinned host memory, episode means): 12 launches,
+replayed from CUDA graphs.
 metric = env-steps/s summed over all GPUs (weak scaling: E envs per GPU, no data-path collective).
-The same run also times GAE over [T=24, E] and reports it under "gae".
+The same run also reports GAE over [T=24, E] ("gae"), the PPO update on [24, E] rollouts with 5 epochs x 4
+minibatches ("ppo": samples/s, TF32 TFLOP/s), the rollout side (PPO.act + process_env_step per step) and a whole
+learning iteration ("ppo.iteration", the reference's Perf/total_fps definition).
 
 value      device time: per-step CUDA events on the launching stream, all inputs resident in HBM,
-           L2 flushed between steps (a 256 MiB write outside the timed events), max over ranks.
+           L2 flushed between steps (a 256 MiB write, then a 256 MiB read so that no dirty flush lines are written
+           back inside the timed region; both outside the timed events), max over ranks.
 e2e        the public `HectorFreeEnvB200.step()` with HOST buffers: per step the physics state and the
            actions are copied from pinned host memory, the env draws its own noise, and obs /
            privileged obs / rewards / resets are copied back to pinned host memory; wall clock.
-roofline   the dominant kernel (frame stacking of both observation histories) against MEASURED_PEAKS.json.
+roofline   the dominant kernel (frame stacking of both observation histories, with the reset finalisation riding in
+           the same launch) against MEASURED_PEAKS.json: algorithmic bytes / average launch duration over a graph of
+           4 launches on 4 distinct cold buffer sets.
 cpu_baseline / --impl reference: the CPU oracle port of the reference's torch code
            (oracle/hector_oracle.py, torch CPU, all host threads) on the same workload.
 """
