@@ -163,7 +163,7 @@ def run_reference(args, rank):
 
 
 # ------------------------------------------------------------------------------------ B200 arm
-def cpu_baseline(n, budget_s=15.0):
+def cpu_baseline(n, budget_s=10.0):
     from isaac_b200.envs.hector_config import HectorCfg
     from oracle.hector_oracle import OracleHectorEnv
     cores = os.cpu_count() or 1
@@ -173,7 +173,7 @@ def cpu_baseline(n, budget_s=15.0):
     for i in range(2):
         env.step(tape.physics[i % 3], tape.noise[i % 3])
     steps, t0 = 0, time.perf_counter()
-    while time.perf_counter() - t0 < budget_s and steps < 200:
+    while time.perf_counter() - t0 < budget_s and steps < 5000:
         env.step(tape.physics[steps % 3], tape.noise[steps % 3])
         steps += 1
     dt = time.perf_counter() - t0
