@@ -135,11 +135,12 @@ def test_pd_torque_law(lib, cuda_device):
     assert (want.abs() == ora.torque_limits).any(), "case must hit the torque limits"
 
 
-@pytest.mark.parametrize("n", [4096, 65536])
+@pytest.mark.parametrize("n", [4096, 16384, 65536])
 def test_step_properties_at_baseline_sizes(lib, cuda_device, n):
-    """Size-independent properties at BASELINE.json sizes (the oracle would take minutes here)."""
+    """Size-independent properties at BASELINE.json sizes (the oracle would take minutes here); the 16384-env case
+    is BASELINE configs[2]: per-env kp / kd and friction / mass domain randomisation, injected noise."""
     dev = cuda_device
-    tape = make_tape(n, 3, seed=7, fall_prob=0.01)
+    tape = make_tape(n, 3, seed=7, fall_prob=0.01, randomize_gains=(n == 16384))
     env, phys = make_cuda_env(tape, dev)
     prev_obs, prev_priv = env.obs_buf.clone(), env.privileged_obs_buf.clone()
     for t in (1, 2):
@@ -163,6 +164,9 @@ def test_step_properties_at_baseline_sizes(lib, cuda_device, n):
         assert torch.equal(env.episode_length_buf[keep], ep_before[keep] + 1)
         assert (rew >= 0).all() and torch.isfinite(obs).all() and torch.isfinite(priv).all()
         assert obs.abs().max() <= 100 and priv.abs().max() <= 100
+        # domain randomisation reaches the newest privileged frame: friction, mass / 30 (hector_env.py:210-211)
+        assert torch.equal(priv[:, 980 + 64], tape.statics.env_frictions.to(dev).flatten())
+        assert torch.equal(priv[:, 980 + 65].cpu(), (tape.statics.body_mass / 30.0).flatten())    # IEEE division, as on the CPU
         prev_obs, prev_priv = obs.clone(), priv.clone()
     env._apply_pending_resets()
     assert env.last_reset_count == cnt and phys.calls["set_dof_state_indexed"] >= 1
