@@ -33,20 +33,33 @@ gae_scan_kernel(const float *__restrict__ rewards, const float *__restrict__ val
     const int e = env0 + lane;
     const bool ok = e < N;
 
-    // phase 1: coalesced loads; lane = env, warps stride over t
-    for (int t = warp; t < T; t += WARPS) {
-        float r = 0.f, v = 0.f, vn = 0.f, nnt = 0.f;
-        if (ok) {
-            const size_t i = (size_t)t * N + e;
-            r = rewards[i];
-            v = values[i];
-            vn = (t == T - 1) ? last_values[e] : values[i + N];
-            nnt = 1.0f - (float)dones[i];
+    // phase 1: coalesced loads; lane = env, warps stride over t.  All of a warp's loads are issued before the first
+    // shared-memory store (up to ITERS time steps per warp), so a tile pays one memory latency, not one per time step.
+    constexpr int ITERS = 4;
+    for (int tb = warp; tb < T; tb += WARPS * ITERS) {
+        float r[ITERS], v[ITERS], vn[ITERS], nnt[ITERS];
+#pragma unroll
+        for (int u = 0; u < ITERS; ++u) {
+            const int t = tb + u * WARPS;
+            r[u] = v[u] = vn[u] = nnt[u] = 0.f;
+            if (ok && t < T) {
+                const size_t i = (size_t)t * N + e;
+                r[u] = rewards[i];
+                v[u] = values[i];
+                vn[u] = (t == T - 1) ? last_values[e] : values[i + N];
+                nnt[u] = 1.0f - (float)dones[i];
+            }
         }
-        const float g = nnt * gamma;
-        sd[t * (ENVS + 1) + lane] = (r + g * vn) - v;
-        sc[t * (ENVS + 1) + lane] = g * lam;
-        sv[t * (ENVS + 1) + lane] = v;
+#pragma unroll
+        for (int u = 0; u < ITERS; ++u) {
+            const int t = tb + u * WARPS;
+            if (t < T) {
+                const float g = nnt[u] * gamma;
+                sd[t * (ENVS + 1) + lane] = (r[u] + g * vn[u]) - v[u];
+                sc[t * (ENVS + 1) + lane] = g * lam;
+                sv[t * (ENVS + 1) + lane] = v[u];
+            }
+        }
     }
     __syncthreads();
 
@@ -115,8 +128,15 @@ gae_normalize_kernel(float *__restrict__ adv, const double *__restrict__ stats, 
     if (var < 0.0) var = 0.0;
     const float m = (float)mean;
     const float denom = (float)sqrt(var) + 1e-8f;
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < count) adv[i] = (adv[i] - m) / denom;
+    // four advantages per thread where the buffer allows it (the fp64 preamble above is per thread)
+    const long long i4 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i4 + 3 < count && (reinterpret_cast<uintptr_t>(adv) & 15u) == 0) {
+        float4 a = *reinterpret_cast<float4 *>(adv + i4);
+        a.x = (a.x - m) / denom, a.y = (a.y - m) / denom, a.z = (a.z - m) / denom, a.w = (a.w - m) / denom;
+        *reinterpret_cast<float4 *>(adv + i4) = a;
+    } else {
+        for (long long i = i4; i < count && i < i4 + 4; ++i) adv[i] = (adv[i] - m) / denom;
+    }
 }
 
 }  // namespace
@@ -143,8 +163,8 @@ int hb_gae_returns(const float *rewards, const float *values, const uint8_t *don
 
 int hb_gae_normalize_n(float *advantages, const double *stats, int64_t stat_count, int64_t count, void *stream) {
     HB_REQUIRE(advantages && stats && stat_count > 1 && count > 0, "hb_gae_normalize: bad arguments");
-    gae_normalize_kernel<<<(int)((count + 255) / 256), 256, 0, (cudaStream_t)stream>>>(advantages, stats, stat_count,
-                                                                                     count);
+    gae_normalize_kernel<<<(int)((count + 1023) / 1024), 256, 0, (cudaStream_t)stream>>>(advantages, stats, stat_count,
+                                                                                       count);
     HB_CHECK_LAUNCH("gae_normalize_kernel");
     return HB_OK;
 }
