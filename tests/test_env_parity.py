@@ -215,6 +215,7 @@ def test_cuda_graph_replay_equals_eager(lib, cuda_device):
     env_g, phys_g = make_cuda_env(tape, dev)
     env_e, phys_e = make_cuda_env(tape, dev)
     env_g.seed(9), env_e.seed(9)
+    env_g.common_step_counter = env_e.common_step_counter = 397      # step 3 is a push step: the graph env takes the eager path there
     env_g.enable_cuda_graph()
     for t in range(1, 6):
         fr = tape.physics[t].to(dev)
@@ -232,6 +233,7 @@ def test_cuda_graph_replay_equals_eager(lib, cuda_device):
         assert torch.equal(env_g._episode_sums, env_e._episode_sums)
     env_g._apply_pending_resets()
     assert phys_g.calls["set_dof_state_indexed"] >= 1
+    assert phys_g.calls["set_root_state"] == 1 and phys_e.calls["set_root_state"] == 1, "one push step in the window"
 
 
 def test_device_generator_draws(lib, cuda_device):
