@@ -335,3 +335,62 @@ def test_fused_shift_finalize_equals_separate_calls(lib, cuda_device, n):
     if cnt:
         np.testing.assert_allclose(means.cpu().numpy(), (sums / cnt).float().cpu().numpy() / 24.0, rtol=1e-6)
         assert torch.equal(latch, env.time_out_buf) and (sums_after == 0).all()
+
+
+def test_soak_replayed_steps_and_learning_iterations(lib, cuda_device):
+    """A few thousand replayed steps (CUDA graphs, device generator, PDL launches) and several full learning
+    iterations: the invariants of a step must hold at every checkpoint and nothing may drift to NaN - guards the
+    asynchronous machinery (graphs, programmatic dependent launches, ping-pong buffers, two-stream update)."""
+    from isaac_b200.algo import ActorCritic, PPO
+    dev = cuda_device
+    n, frames = 2048, 4
+    tape = make_tape(n, frames + 1, seed=99, fall_prob=0.01, randomize_gains=True)
+    env, phys = make_cuda_env(tape, dev)
+    env.seed(123)
+    phys_frames = [f.to(dev) for f in tape.physics[1:]]
+    env.enable_cuda_graph()
+    actions = torch.zeros(n, 10, device=dev)
+    prev_obs = env.obs_buf.clone()
+    total_resets = 0
+    for t in range(3000):
+        phys.load_frame(phys_frames[t % frames])
+        actions.normal_()
+        check = t % 500 == 499
+        if check:
+            prev_obs = env.obs_buf.clone()
+            ep_before = env.episode_length_buf.clone()
+        obs, priv, rew, reset, extras = env.step(actions)
+        if check:
+            torch.cuda.synchronize()
+            keep = ~reset
+            assert torch.equal(obs[keep][:, :574], prev_obs[keep][:, 41:]), t
+            assert (obs[reset][:, :574] == 0).all() and (priv[reset][:, :980] == 0).all()
+            cnt = int(env._reset_count.item())
+            assert cnt == int(reset.sum()) == int(env._host_count[0])
+            assert torch.equal(env.reset_env_ids[:cnt].long(), reset.nonzero().flatten())
+            assert torch.equal(env.episode_length_buf[keep], ep_before[keep] + 1)
+            assert torch.isfinite(obs).all() and torch.isfinite(priv).all() and torch.isfinite(rew).all()
+            assert (rew >= 0).all() and obs.abs().max() <= 100
+            assert all(torch.isfinite(v) for v in extras["episode"].values())
+            total_resets += cnt
+    assert total_resets > 0 and int(env._rng_counter.item()) >= 3000
+    # learning iterations driven like OnPolicyRunner.learn (on_policy_runner.py:124-170)
+    torch.manual_seed(1)
+    ac = ActorCritic(615, 1050, 10, actor_hidden_dims=[512, 256, 128], critic_hidden_dims=[768, 256, 128], device=dev)
+    alg = PPO(ac, device=dev, num_learning_epochs=2, num_mini_batches=4, clip_param=0.2, gamma=0.994, lam=0.9,
+              value_loss_coef=1.0, entropy_coef=0.001, learning_rate=1e-4, max_grad_norm=1.0, schedule="adaptive", desired_kl=0.01)
+    T = 8
+    alg.init_storage(n, T, [615], [1050], [10])
+    obs, priv = env.get_observations(), env.get_privileged_observations()
+    w0 = ac.flat.clone()
+    for it in range(6):
+        for t in range(T):
+            a = alg.act(obs, priv)
+            phys.load_frame(phys_frames[t % frames])
+            obs, priv, rew, dones, infos = env.step(a)
+            alg.process_env_step(rew, dones, infos)
+        alg.compute_returns(priv)
+        v_loss, s_loss = alg.update()
+        assert np.isfinite(v_loss) and np.isfinite(s_loss) and np.isfinite(alg.last_mean_kl), (it, v_loss, s_loss)
+        assert torch.isfinite(ac.flat).all() and 1e-5 <= alg.learning_rate <= 1e-2
+    assert not torch.equal(w0, ac.flat) and (ac.grad == 0).all()
