@@ -308,7 +308,14 @@ def test_fused_shift_finalize_equals_separate_calls(lib, cuda_device, n):
         env._scratch_ballots.copy_(ballots)
         env._scratch_sums.copy_(sums)
         env.reset_env_ids.fill_(-1)
-        new_o, new_p = torch.full((n, 615), 7.0, device=dev), torch.full((n, 1050), 7.0, device=dev)
+        # the outputs live inside larger allocations with sentinel guards on both sides (compute-sanitizer is not
+        # available on this pool: an out-of-bounds store of the ragged tail paths would show up here)
+        GUARD = 1024
+        raw_o = torch.full((n * 615 + 2 * GUARD,), -3.0, device=dev)
+        raw_p = torch.full((n * 1050 + 2 * GUARD,), -3.0, device=dev)
+        new_o, new_p = raw_o[GUARD:GUARD + n * 615].view(n, 615), raw_p[GUARD:GUARD + n * 1050].view(n, 1050)
+        new_o.fill_(7.0), new_p.fill_(7.0)
+        assert new_o.data_ptr() % 16 == 0 and new_p.data_ptr() % 16 == 0
         means = torch.zeros(18, device=dev)
         env._b.episode_means, env._b.episode_means_prev = means.data_ptr(), None
         P, B, hc = env._pp, env._pb, env._host_count.data_ptr()
@@ -320,6 +327,8 @@ def test_fused_shift_finalize_equals_separate_calls(lib, cuda_device, n):
                                                      new_p.data_ptr(), st), "stack")
             _lib.check(lib.hb_env_reset_finalize(P, B, new_o.data_ptr(), new_p.data_ptr(), hc, None, st), "finalize")
         torch.cuda.synchronize()
+        for raw, size in ((raw_o, n * 615), (raw_p, n * 1050)):
+            assert (raw[:GUARD] == -3.0).all() and (raw[GUARD + size:] == -3.0).all(), "store outside the frame stack"
         cnt = int(env._reset_count.item())
         results.append((new_o.clone(), new_p.clone(), cnt, env.reset_env_ids[:cnt].clone(), means.clone(),
                         env._time_outs_latched.clone(), int(env._host_count[0]), env._scratch_sums.clone()))

@@ -28,7 +28,13 @@ def run_gemm(lib, dev, A, B, M, N, K, a_mn=False, b_mn=False, epilogue=0, bias=N
     from isaac_b200 import _lib
     d = _lib.GemmDesc()
     ldd = ldd or (N + 3) // 4 * 4
-    D = torch.zeros(M, ldd, device=dev) if D0 is None else D0
+    guard = None
+    if D0 is None:      # output inside a larger allocation: guard rows before / after catch out-of-bounds stores of ragged tiles
+        guard = torch.full((M + 16, ldd), -7.0, device=dev)
+        D = guard[8:8 + M]
+        D.zero_()
+    else:
+        D = D0
     d.A, d.B, d.D = A.data_ptr(), B.data_ptr(), D.data_ptr()
     d.M, d.N, d.K = M, N, K
     d.lda, d.ldb, d.ldd = A.stride(0), B.stride(0), D.stride(0)
@@ -39,6 +45,9 @@ def run_gemm(lib, dev, A, B, M, N, K, a_mn=False, b_mn=False, epilogue=0, bias=N
         d.H, d.ldh = H.data_ptr(), H.stride(0)
     _lib.check(lib.hb_gemm_tf32(C.byref(d), torch.cuda.current_stream(dev).cuda_stream), "hb_gemm_tf32")
     torch.cuda.synchronize()
+    if guard is not None:
+        assert (guard[:8] == -7.0).all() and (guard[8 + M:] == -7.0).all(), "store outside the output matrix"
+        assert (D[:, N:] == 0).all(), "store into the padding columns"
     return D[:, :N]
 
 
