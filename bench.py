@@ -207,6 +207,7 @@ def bench_iteration(env, phys, phys_frames, alg, dev, n, iters=2):
     process_env_step), compute_returns, update - the reference's own `Perf/total_fps` = T * N / (collection + learning)
     (on_policy_runner.py:199-213), wall clock, physics stubbed."""
     frames = len(phys_frames)
+    alg.attach_env(env)          # step() writes its observations straight into the rollout slots (SURVEY.md §8f rank 1)
     obs, priv = env.get_observations(), env.get_privileged_observations()
     out = None
     for it in range(iters + 1):
@@ -226,7 +227,9 @@ def bench_iteration(env, phys, phys_frames, alg, dev, n, iters=2):
         t2 = time.perf_counter()
         out = {"total_fps": T_GAE * n / (t2 - t0), "collection_ms": 1e3 * (t1 - t0), "learning_ms": 1e3 * (t2 - t1),
                "unit": "env-steps/s per GPU, wall clock, T=24 rollout + 5 epochs x 4 minibatches",
-               "definition": "Perf/total_fps of on_policy_runner.py:199-213 (physics stubbed)"}
+               "definition": "Perf/total_fps of on_policy_runner.py:199-213 (physics stubbed)",
+               "observations": "written by env.step() into the rollout slots (PPO.attach_env)"}
+    alg.attach_env(None)
     return out
 
 
@@ -244,8 +247,9 @@ def bench_ppo(args, dev, n, world, rank, env=None, phys=None, phys_frames=None):
         attach_data_parallel(alg)
     last = torch.randn(n, 1050, device=dev)
     stream = torch.cuda.current_stream(dev)
-    # rollout side: PPO.act + process_env_step per env step, T steps, eager launches
-    obs_, priv_ = torch.randn(n, 615, device=dev), torch.randn(n, 1050, device=dev)
+    # rollout side: PPO.act + process_env_step per env step, T steps; the observations are
+    # already in the slot, as after PPO.attach_env(env)
+    alg.storage.observations.normal_(), alg.storage.privileged_observations.normal_()
     rew_, done_ = torch.rand(n, device=dev), torch.rand(n, device=dev) < 0.005
     infos_ = {"time_outs": torch.rand(n, device=dev) < 0.0004}
     roll_ms = None
@@ -254,8 +258,8 @@ def bench_ppo(args, dev, n, world, rank, env=None, phys=None, phys_frames=None):
         torch.cuda.synchronize(dev)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(stream)
-        for _ in range(T_GAE):
-            alg.act(obs_, priv_)
+        for k in range(T_GAE):
+            alg.act(*alg.storage.observation_slot(k))
             alg.process_env_step(rew_, done_, infos_)
         b.record(stream)
         b.synchronize()
@@ -410,25 +414,29 @@ def run_b200(args, rank, world):
                 tot += a.elapsed_time(b)
         return tot / reps / len(fns)
 
-    cur, prev = env._cur, env._cur ^ 1
+    (o_prev, p_prev), (o_cur, p_cur) = env._own[0][:2], env._own[1][:2]      # the env's own pair; rows at the 616 / 1052-float pitch
     P, B = env._pp, env._pb
     rb = None            # unconditional shift (reset envs are zeroed by hb_env_reset_finalize)
-    k_priv = time_launch(lambda st: lib.hb_stack_shift(env._priv[prev].data_ptr(), env._priv[cur].data_ptr(), rb, n,
+    dense = [torch.randn(n, w, device=dev) for w in (STACK_PRIV * FRAME_PRIV, STACK_PRIV * FRAME_PRIV,
+                                                     STACK_OBS * FRAME_OBS, STACK_OBS * FRAME_OBS)]
+    k_priv = time_launch(lambda st: lib.hb_stack_shift(dense[0].data_ptr(), dense[1].data_ptr(), rb, n,
                                                     STACK_PRIV * FRAME_PRIV, FRAME_PRIV, st))
-    k_obs = time_launch(lambda st: lib.hb_stack_shift(env._obs[prev].data_ptr(), env._obs[cur].data_ptr(), rb, n,
+    k_obs = time_launch(lambda st: lib.hb_stack_shift(dense[2].data_ptr(), dense[3].data_ptr(), rb, n,
                                                    STACK_OBS * FRAME_OBS, FRAME_OBS, st))
+    del dense
     k_pd = time_launch(lambda st: lib.hb_env_compute_torques(P, B, st))
     env._draw_noise(False)              # device generator, like the replayed step
-    k_post = time_launch(lambda st: lib.hb_env_post_physics(P, B, env._pn, env._obs[cur].data_ptr(), env._priv[cur].data_ptr(),
+    k_post = time_launch(lambda st: lib.hb_env_post_physics(P, B, env._pn, o_cur.data_ptr(), p_cur.data_ptr(),
                                                          _lib.HB_STAGE_STEP, st))
-    k_fin = time_launch(lambda st: lib.hb_env_reset_finalize(P, B, env._obs[cur].data_ptr(), env._priv[cur].data_ptr(),
+    k_fin = time_launch(lambda st: lib.hb_env_reset_finalize(P, B, o_cur.data_ptr(), p_cur.data_ptr(),
                                                           env._host_count.data_ptr(), None, st))
-    k_stack_single = time_launch(lambda st: lib.hb_env_stack_observations(P, B, env._obs[prev].data_ptr(), env._priv[prev].data_ptr(),
-                                                                       env._obs[cur].data_ptr(), env._priv[cur].data_ptr(), st))
+    k_stack_single = time_launch(lambda st: lib.hb_env_stack_observations(P, B, o_prev.data_ptr(), p_prev.data_ptr(),
+                                                                       o_cur.data_ptr(), p_cur.data_ptr(), st))
     # the roofline kernel: 4 launches per timed replay, each on its own cold set of history buffers
     CHAIN = 4
-    sets = [(torch.randn(n, 615, device=dev), torch.randn(n, 1050, device=dev), torch.empty(n, 615, device=dev),
-             torch.empty(n, 1050, device=dev)) for _ in range(CHAIN)]
+    ld_o, ld_p = env._p.obs_ld, env._p.priv_ld
+    sets = [(torch.randn(n, ld_o, device=dev), torch.randn(n, ld_p, device=dev), torch.empty(n, ld_o, device=dev),
+             torch.empty(n, ld_p, device=dev)) for _ in range(CHAIN)]
     k_stack = time_chain([(lambda st, s_=s_: lib.hb_env_stack_finalize(P, B, s_[0].data_ptr(), s_[1].data_ptr(),
                                                                       s_[2].data_ptr(), s_[3].data_ptr(),
                                                                       env._host_count.data_ptr(), None, st)) for s_ in sets])
@@ -447,9 +455,13 @@ def run_b200(args, rank, world):
     host_frames = [type(f)(*(t.cpu().pin_memory() for t in (f.root_states, f.dof_state, f.contact_forces, f.rigid_state)))
                    for f in tape.physics]
     host_actions = [f.actions.pin_memory() for f in tape.noise]
-    out_host = [torch.empty(n, 615).pin_memory(), torch.empty(n, 1050).pin_memory(), torch.empty(n).pin_memory(),
-                torch.empty(n, dtype=torch.bool).pin_memory()]
+    # host images keep the device row pitch (616 / 1052 floats: one padding column), so each result is ONE copy
+    out_host = [torch.empty(n, env._p.obs_ld).pin_memory(), torch.empty(n, env._p.priv_ld).pin_memory(),
+                torch.empty(n).pin_memory(), torch.empty(n, dtype=torch.bool).pin_memory()]
     act_dev = torch.empty(n, 10, device=dev)
+
+    def whole_rows(t):          # [n, width] view at a pitch -> the [n, pitch] block it lives in
+        return t if t.dim() < 2 or t.is_contiguous() else torch.as_strided(t, (t.shape[0], t.stride(0)), (t.stride(0), 1))
 
     def e2e_step(i):
         f = i % frames
@@ -457,7 +469,7 @@ def run_b200(args, rank, world):
         act_dev.copy_(host_actions[f], non_blocking=True)
         out = env.step(act_dev)
         for h, d in zip(out_host, out[:4]):
-            h.copy_(d, non_blocking=True)
+            h.copy_(whole_rows(d), non_blocking=True)
         torch.cuda.synchronize(dev)      # the caller needs the results of this step
 
     for i in range(max(3, args.warmup)):

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define HB_ABI_VERSION 1
+#define HB_ABI_VERSION 2
 
 typedef enum hb_status {
     HB_OK = 0,
@@ -62,6 +62,10 @@ typedef struct hb_env_params {
     int32_t frame_stack;            /* 15 */
     int32_t num_single_priv;        /* 70 */
     int32_t c_frame_stack;          /* 15 */
+    int32_t obs_ld, priv_ld;        /* row pitch, in floats, of every obs / privileged-obs buffer handed to the calls
+                                       below; 0 = dense (frame_stack * num_single_obs).  A pitch that is a multiple of
+                                       4 (616 / 1052) makes the rows TMA-addressable: the buffers can be the rollout
+                                       storage's own slots (rollout_storage.py:60-61), SURVEY.md §8(f) rank 1 */
     int32_t feet[2];                /* rigid-body rows of the feet   (legged_robot.py:668-671) */
     int32_t knees[2];               /* rigid-body rows of the knees  (:672-674) */
     int32_t n_term;                 /* termination_contact_indices   (:680-682) */
@@ -234,7 +238,7 @@ int hb_env_reset_finalize(const hb_env_params *p, const hb_env_buffers *buf, flo
 int hb_env_stack_finalize(const hb_env_params *p, const hb_env_buffers *buf, const float *obs_prev, const float *priv_prev,
                           float *obs_new, float *priv_new, int32_t *host_count, uint64_t *rng_counter, void *stream);
 
-/* One frame-stack shift on its own: next[:, 0:row-frame] = prev[:, frame:row] (zeros for envs whose
+/* One frame-stack shift on its own, dense rows: next[:, 0:row-frame] = prev[:, frame:row] (zeros for envs whose
  * reset_buf byte is set, if reset_buf is not NULL); next[:, row-frame:row] is left alone. */
 int hb_stack_shift(const float *prev, float *next, const uint8_t *reset_buf, int32_t num_envs, int32_t row,
                    int32_t frame, void *stream);

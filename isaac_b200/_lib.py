@@ -10,7 +10,7 @@ import ctypes as C
 import os
 from typing import Optional
 
-HB_ABI_VERSION = 1
+HB_ABI_VERSION = 2
 HB_MAX_DOF = 16
 HB_MAX_OBS = 48
 HB_NUM_REWARDS = 18
@@ -38,6 +38,7 @@ class EnvParams(C.Structure):
     _fields_ = [
         ("abi_version", _i), ("num_envs", _i), ("num_dof", _i), ("num_bodies", _i),
         ("num_single_obs", _i), ("frame_stack", _i), ("num_single_priv", _i), ("c_frame_stack", _i),
+        ("obs_ld", _i), ("priv_ld", _i),
         ("feet", _i * 2), ("knees", _i * 2),
         ("n_term", _i), ("term_bodies", _i * HB_MAX_CONTACT_BODIES),
         ("n_pen", _i), ("pen_bodies", _i * HB_MAX_CONTACT_BODIES),

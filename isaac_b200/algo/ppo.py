@@ -124,12 +124,21 @@ class PPO:
         self.actor_critic.train()
 
     # ------------------------------------------------------------------ rollout (ppo.py:91-117)
+    def attach_env(self, env) -> None:
+        """from now on act() tells `env` (an isaac_b200 env) to write the observations of
+        its next step() straight into the rollout slot act() will record them in, so the two observation copies of
+        `add_transitions` (rollout_storage.py:90-92) disappear and the policy GEMMs read the slot in place.  Pass
+        None to detach.  Nothing else changes for the caller: step() still returns the tensors it wrote."""
+        if env is not None and not hasattr(env, "set_next_observation_buffers"):
+            raise TypeError("attach_env needs an env with set_next_observation_buffers()")
+        self._env = env
+
     def act(self, obs, critic_obs):
         """ppo.py:91-101.  Fast path (both last hidden layers 128 wide, rollout slot available): the observations
-        are copied into the slot's 16-byte-aligned rows first and feed the GEMMs from there (TMA cannot address
-        615- / 1050-float rows), three hidden-layer GEMMs per network, then ONE kernel for the two output layers,
-        the sample, its log-prob, mu, sigma and the value, written straight into the storage slot
-        (rollout_storage.py:87-100's copies of these tensors disappear)."""
+        are recorded in the slot first (16-byte row pitch: TMA cannot address 615- / 1050-float rows; no copy at all
+        when the env wrote them there, see attach_env) and feed the GEMMs from the slot, three hidden-layer GEMMs per
+        network, then ONE kernel for the two output layers, the sample, its log-prob, mu, sigma and the value, written
+        straight into the storage slot (rollout_storage.py:87-100's copies of these tensors disappear)."""
         ac, lib, s = self.actor_critic, self._lib, self.storage
         n = obs.shape[0]
         st = torch.cuda.current_stream(self.device).cuda_stream
@@ -137,25 +146,22 @@ class PPO:
         t = self.transition
         fast = (ac.fused_head and s is not None and s.step < s.num_transitions_per_env and n == s.num_envs
                 and s.privileged_observations is not None and obs.is_cuda and critic_obs.is_cuda)
-        graphed = (fast and self.graph_rollout and self.injected_eps is None and n <= self.graph_rollout_max_envs
-                   and obs.is_contiguous() and critic_obs.is_contiguous())
-        if graphed:
-            # small shards: the hidden layers of both networks are replayed from one CUDA graph (launch-bound at this
-            # size), the two chains on parallel branches; the graph reads the observations where the env left them
-            k = s.step
-            h3a, h3c, eps, xa, xc = self._replay_act_graph(obs, critic_obs, n, ws)
-            s._observations[k].copy_(xa)
-            s._privileged_observations[k].copy_(xc)
-        else:
-            eps = self.injected_eps if self.injected_eps is not None else torch.randn(n, ac.num_actions, device=self.device)
-        self.injected_eps = None
         if fast:
             k = s.step
-            if not graphed:
+            xa, xc = s._observations[k], s._privileged_observations[k]
+            if obs.data_ptr() != xa.data_ptr() or obs.stride(0) != s.obs_ld:
                 s.observations[k].copy_(obs)
+            if critic_obs.data_ptr() != xc.data_ptr() or critic_obs.stride(0) != s.priv_ld:
                 s.privileged_observations[k].copy_(critic_obs)
-                h3a = ac._mlp_forward("actor", s._observations[k], ws, hidden_only=True)
-                h3c = ac._mlp_forward("critic", s._privileged_observations[k], ws, hidden_only=True)
+            if self.graph_rollout and self.injected_eps is None and n <= self.graph_rollout_max_envs:
+                # small shards: the hidden layers of both networks are replayed from one CUDA graph per slot
+                # (launch-bound at this size), the two chains on parallel branches
+                h3a, h3c, eps = self._replay_act_graph(k, n, ws)
+            else:
+                eps = self.injected_eps if self.injected_eps is not None else torch.randn(n, ac.num_actions, device=self.device)
+                h3a = ac._mlp_forward("actor", xa, ws, hidden_only=True)
+                h3c = ac._mlp_forward("critic", xc, ws, hidden_only=True)
+            self.injected_eps = None
             La, Lc = [L for L in ac.layers if L.last]
             _lib.check(lib.hb_ppo_act_fused(h3a.data_ptr(), h3a.stride(0), h3c.data_ptr(), h3c.stride(0),
                                             ac._matrix(ac.flat, La).data_ptr(), ac._matrix(ac.flat, Lc).data_ptr(), La.ld,
@@ -166,7 +172,14 @@ class PPO:
             t.action_mean, t.action_sigma = s.mu[k], s.sigma[k]
             t.observations, t.critic_observations = obs, critic_obs
             self._recorded_slot = k
+            env = getattr(self, "_env", None)
+            if env is not None and env.num_envs == n:
+                nxt = s.observation_slot(k + 1)          # slot T exists: the observations after the last transition
+                if nxt[0].data_ptr() != obs.data_ptr() and nxt[1].data_ptr() != critic_obs.data_ptr():
+                    env.set_next_observation_buffers(*nxt)
             return t.actions
+        eps = self.injected_eps if self.injected_eps is not None else torch.randn(n, ac.num_actions, device=self.device)
+        self.injected_eps = None
         self._recorded_slot = None
         mu16 = ac._mlp_forward("actor", ac._as_operand(obs, ac.num_actor_obs), ws)
         v16 = ac._mlp_forward("critic", ac._as_operand(critic_obs, ac.num_critic_obs), ws)
@@ -181,41 +194,35 @@ class PPO:
         t.observations, t.critic_observations = obs, critic_obs          # recorded before env.step() (ppo.py:98-100)
         return t.actions
 
-    def _replay_act_graph(self, obs, critic_obs, n, ws):
-        """Capture (once per pair of observation buffers: the env ping-pongs between two) and replay: padded staging
-        copies of both observation tensors, the three hidden-layer GEMMs of each network on two branches, the
-        N(0,1) draw of the sample.  Returns the last hidden activations, the draw and the staged observations."""
-        ac = self.actor_critic
-        key = (obs.data_ptr(), critic_obs.data_ptr(), n)
+    def _replay_act_graph(self, k, n, ws):
+        """Capture (once per rollout slot) and replay: the three hidden-layer GEMMs of each network on two branches,
+        reading the slot's observations in place, and the N(0,1) draw of the sample.  Returns the last hidden
+        activations and the draw."""
+        ac, s = self.actor_critic, self.storage
+        key = (s._observations.data_ptr(), k, n)
         entry = self._act_graphs.get(key)
         if entry is None:
             dev = self.device
-            if self._act_stage is None or self._act_stage[0].shape[0] != n:
-                self._act_stage = (torch.zeros(n, pad4(ac.num_actor_obs + 1), device=dev),
-                                   torch.zeros(n, pad4(ac.num_critic_obs + 1), device=dev),
-                                   torch.zeros(n, ac.num_actions, device=dev))
-            xa, xc, eps = self._act_stage
+            if self._act_stage is None or self._act_stage.shape[0] != n:
+                self._act_stage = torch.zeros(n, ac.num_actions, device=dev)
+            eps = self._act_stage
+            if len(self._act_graphs) >= 4 * (s.num_transitions_per_env + 1):     # new storage: drop the stale graphs
+                self._act_graphs.clear()
             torch.cuda.synchronize(dev)
             g = torch.cuda.CUDAGraph()
             side = self._side_stream
             with torch.cuda.graph(g):
                 main = torch.cuda.current_stream(dev)
                 side.wait_stream(main)
-                xa[:, :ac.num_actor_obs].copy_(obs)
-                h3a = ac._mlp_forward("actor", xa, ws, hidden_only=True)
+                h3a = ac._mlp_forward("actor", s._observations[k], ws, hidden_only=True)
                 eps.normal_()
                 with torch.cuda.stream(side):
-                    xc[:, :ac.num_critic_obs].copy_(critic_obs)
-                    h3c = ac._mlp_forward("critic", xc, ws, hidden_only=True)
+                    h3c = ac._mlp_forward("critic", s._privileged_observations[k], ws, hidden_only=True)
                 main.wait_stream(side)
-            entry = (g, h3a, h3c)
-            if len(self._act_graphs) >= 8:          # observation buffers changed (new env): drop the stale graphs
-                self._act_graphs.clear()
-            self._act_graphs[key] = entry
+            entry = self._act_graphs[key] = (g, h3a, h3c)
         g, h3a, h3c = entry
         g.replay()
-        xa, xc, eps = self._act_stage
-        return h3a, h3c, eps, xa, xc
+        return h3a, h3c, self._act_stage
 
     def process_env_step(self, rewards, dones, infos):
         """ppo.py:103-113.  After the fast path of act() only rewards (with the time-out bootstrap) and dones are

@@ -63,19 +63,27 @@ class RolloutStorage:
         def clear(self):
             self.__init__()
 
+    def observation_slot(self, k: int):
+        """([N, num_obs], [N, num_privileged_obs]) views of slot k, 0 <= k <= T, at the storage's row pitch."""
+        return (self._observations[k][:, :self.obs_shape[0]],
+                self._privileged_observations[k][:, :self.privileged_obs_shape[0]])
+
     def __init__(self, num_envs, num_transitions_per_env, obs_shape, privileged_obs_shape, actions_shape,
                  device="cuda:0"):
         self.device = device
         self.obs_shape, self.privileged_obs_shape, self.actions_shape = obs_shape, privileged_obs_shape, actions_shape
         T, N = num_transitions_per_env, num_envs
         z = lambda *s, **kw: torch.zeros(*s, device=device, **kw)
+        # rows at a 16-byte pitch (TMA operands), and one slot more than the reference's [T, N, *]: slot T receives the
+        # observations that follow the last transition when the env writes straight into the storage
+        # (PPO.attach_env; they become slot 0 of the next rollout)
         self.obs_ld = _pad4(obs_shape[0])
-        self._observations = z(T, N, self.obs_ld)
-        self.observations = self._observations[..., :obs_shape[0]]
+        self._observations = z(T + 1, N, self.obs_ld)
+        self.observations = self._observations[:T, :, :obs_shape[0]]
         if privileged_obs_shape[0] is not None:
             self.priv_ld = _pad4(privileged_obs_shape[0])
-            self._privileged_observations = z(T, N, self.priv_ld)
-            self.privileged_observations = self._privileged_observations[..., :privileged_obs_shape[0]]
+            self._privileged_observations = z(T + 1, N, self.priv_ld)
+            self.privileged_observations = self._privileged_observations[:T, :, :privileged_obs_shape[0]]
         else:
             self.privileged_observations = None
         self.rewards = z(T, N, 1)

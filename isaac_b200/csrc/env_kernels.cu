@@ -869,11 +869,12 @@ post_physics_kernel(const __grid_constant__ hb_env_params p, const __grid_consta
             // 96 threads walk the tile's frames with (row, column) advanced incrementally: no per-element division.
             // Privileged frames leave as 8-byte pairs (row starts are 8-byte aligned: 4200 r + 3920 bytes).
             constexpr int NT = 3 * TILE, P2 = PRIV / 2;
-            const int ostride = p.frame_stack * OBS, pstride = p.c_frame_stack * PRIV;
+            const int orow = p.frame_stack * OBS, prow = p.c_frame_stack * PRIV;
+            const int ostride = p.obs_ld ? p.obs_ld : orow, pstride = p.priv_ld ? p.priv_ld : prow;   // row pitch
             const int t = threadIdx.x;
-            if ((pstride & 1) == 0 && (reinterpret_cast<uintptr_t>(priv_new) & 7u) == 0) {
+            if (((pstride | prow) & 1) == 0 && (reinterpret_cast<uintptr_t>(priv_new) & 7u) == 0) {
                 int r = t / P2, c2 = t - r * P2;
-                float2 *dst = reinterpret_cast<float2 *>(priv_new + (size_t)env0 * pstride + (pstride - PRIV));
+                float2 *dst = reinterpret_cast<float2 *>(priv_new + (size_t)env0 * pstride + (prow - PRIV));
                 const float2 *src = reinterpret_cast<const float2 *>(sp);
                 const int half = pstride / 2;
                 while (r < nv) {
@@ -884,13 +885,13 @@ post_physics_kernel(const __grid_constant__ hb_env_params p, const __grid_consta
             } else {
                 int r = t / PRIV, c = t - r * PRIV;
                 while (r < nv) {
-                    priv_new[(size_t)(env0 + r) * pstride + (pstride - PRIV) + c] = sp[r * PRIV + c];
+                    priv_new[(size_t)(env0 + r) * pstride + (prow - PRIV) + c] = sp[r * PRIV + c];
                     r += NT / PRIV, c += NT % PRIV;
                     if (c >= PRIV) c -= PRIV, r += 1;
                 }
             }
             int r = t / OBS, c = t - r * OBS;
-            float *dst = obs_new + (size_t)env0 * ostride + (ostride - OBS);
+            float *dst = obs_new + (size_t)env0 * ostride + (orow - OBS);
             while (r < nv) {
                 dst[(size_t)r * ostride + c] = so[r * OBS + c];
                 r += NT / OBS, c += NT % OBS;
@@ -923,7 +924,7 @@ __device__ __forceinline__ float4 ld_vec_guarded(const float *__restrict__ prev,
     return v;
 }
 
-template <int ROW, int FRAME, int UNROLL, bool CHECK_RESET = false>
+template <int ROW, int LD, int FRAME, int UNROLL, bool CHECK_RESET = false>
 __device__ __forceinline__ void
 stack_shift_fixed(const float *__restrict__ prev, float *__restrict__ next, const uint32_t total, const uint32_t blk,
                   const uint8_t *__restrict__ reset_buf = nullptr) {
@@ -942,14 +943,21 @@ stack_shift_fixed(const float *__restrict__ prev, float *__restrict__ next, cons
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u) {
         const uint32_t s = warp_base + u * 32u + lane + FVEC;          // aligned source vector below the window
+        const uint32_t e = (warp_base + u * 32u + lane) * 4u;
+        const uint32_t r = e / (uint32_t)LD;
         rz[u] = 0;
-        if (CHECK_RESET) {
-            const uint32_t e = (warp_base + u * 32u + lane) * 4u;
-            if (e < total) rz[u] = __ldg(reset_buf + e / (uint32_t)ROW);
+        if (CHECK_RESET && e < total) rz[u] = __ldg(reset_buf + r);
+        // vector-aligned rows: a destination vector that lies, like the one before it, wholly in the newest-frame
+        // hole or the padding needs no source (neither for itself nor for its left neighbour's spill-over)
+        if ((LD & 3) == 0) {                                            // the buffer is whole vectors: predicated loads
+            const bool need = e - r * (uint32_t)LD < KEEP + 4u;
+            v[u] = hb::ld_stream4_if(p4 + s, need && s < total_vec);
+            if (ROT != 0) w[u] = hb::ld_stream4_if(p4 + s + 1u, need && lane == 31u && s + 1u < total_vec);
+        } else {
+            v[u] = (s < total_vec) ? hb::ld_stream4(p4 + s) : ld_vec_guarded(prev, s, total);
+            if (ROT != 0 && lane == 31u)                                // no neighbour lane: fetch the spill-over
+                w[u] = (s + 1u < total_vec) ? hb::ld_stream4(p4 + s + 1u) : ld_vec_guarded(prev, s + 1u, total);
         }
-        v[u] = (s < total_vec) ? hb::ld_stream4(p4 + s) : ld_vec_guarded(prev, s, total);
-        if (ROT != 0 && lane == 31u)                                    // no neighbour lane: fetch the spill-over
-            w[u] = (s + 1u < total_vec) ? hb::ld_stream4(p4 + s + 1u) : ld_vec_guarded(prev, s + 1u, total);
     }
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u) {
@@ -966,8 +974,9 @@ stack_shift_fixed(const float *__restrict__ prev, float *__restrict__ next, cons
         }
         if (i >= tail_vec) continue;
         const uint32_t e0 = i * 4u;                      // first destination float
-        const uint32_t r0 = e0 / (uint32_t)ROW;
-        const uint32_t c0 = e0 - r0 * (uint32_t)ROW;
+        const uint32_t r0 = e0 / (uint32_t)LD;             // LD = row pitch (ROW, or ROW padded to whole vectors)
+        const uint32_t c0 = e0 - r0 * (uint32_t)LD;
+        if ((LD & 3) == 0 && c0 >= KEEP) continue;         // vector-aligned rows: newest-frame hole / padding
         if (c0 + 3u < KEEP && i < total_vec) {           // whole vector inside the carried part of one row
             if (CHECK_RESET && rz[u]) o = make_float4(0.f, 0.f, 0.f, 0.f);
             hb::st_stream4(n4 + i, o);
@@ -976,15 +985,16 @@ stack_shift_fixed(const float *__restrict__ prev, float *__restrict__ next, cons
 #pragma unroll
             for (uint32_t k = 0; k < 4u; ++k) {
                 uint32_t c = c0 + k, r = r0;
-                if (c >= (uint32_t)ROW) c -= (uint32_t)ROW, r += 1u;
-                if (c < KEEP && e0 + k < total) next[e0 + k] = (CHECK_RESET && reset_buf[r]) ? 0.0f : ov[k];
+                if (c >= (uint32_t)LD) c -= (uint32_t)LD, r += 1u;
+                const bool zero = CHECK_RESET && ((LD & 3) == 0 ? rz[u] != 0 : reset_buf[r] != 0);   // (a vector of a pitched row stays in its row)
+                if (c < KEEP && e0 + k < total) next[e0 + k] = zero ? 0.0f : ov[k];
             }
         }
     }
 }
 
 // actor and critic histories in one launch: blocks [0, blocks_a) shift buffer a, the rest buffer b
-template <int ROW_A, int FRAME_A, int ROW_B, int FRAME_B, int UNROLL>
+template <int ROW_A, int LD_A, int FRAME_A, int ROW_B, int LD_B, int FRAME_B, int UNROLL>
 __global__ void __launch_bounds__(256)
 stack_shift_pair_kernel(const float *__restrict__ prev_a, float *__restrict__ next_a, uint32_t total_a, uint32_t blocks_a,
                         const float *__restrict__ prev_b, float *__restrict__ next_b, uint32_t total_b) {
@@ -994,24 +1004,24 @@ stack_shift_pair_kernel(const float *__restrict__ prev_a, float *__restrict__ ne
     hb::pdl_trigger();
     hb::pdl_wait();
     if (blockIdx.x < blocks_a)
-        stack_shift_fixed<ROW_A, FRAME_A, UNROLL>(prev_a, next_a, total_a, blockIdx.x);
+        stack_shift_fixed<ROW_A, LD_A, FRAME_A, UNROLL>(prev_a, next_a, total_a, blockIdx.x);
     else
-        stack_shift_fixed<ROW_B, FRAME_B, UNROLL>(prev_b, next_b, total_b, blockIdx.x - blocks_a);
+        stack_shift_fixed<ROW_B, LD_B, FRAME_B, UNROLL>(prev_b, next_b, total_b, blockIdx.x - blocks_a);
 }
 
 template <int ROW, int FRAME, int UNROLL>
 __global__ void __launch_bounds__(256)
 stack_shift_fixed_kernel(const float *__restrict__ prev, float *__restrict__ next, uint32_t total) {
-    stack_shift_fixed<ROW, FRAME, UNROLL>(prev, next, total, blockIdx.x);
+    stack_shift_fixed<ROW, ROW, FRAME, UNROLL>(prev, next, total, blockIdx.x);
 }
 
 // generic shapes / unaligned buffers / optional per-env zeroing (reset_buf may be null)
 __global__ void __launch_bounds__(256)
 stack_shift_scalar_kernel(const float *__restrict__ prev, float *__restrict__ next,
-                          const uint8_t *__restrict__ reset_buf, long long total, int row, int frame) {
+                          const uint8_t *__restrict__ reset_buf, long long total, int row, int ld, int frame) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
-    const int r = (int)(i / row), c = (int)(i - (long long)r * row);
+    const int r = (int)(i / ld), c = (int)(i - (long long)r * ld);
     if (c < row - frame) next[i] = (reset_buf && reset_buf[r]) ? 0.0f : prev[i + frame];
 }
 
@@ -1112,7 +1122,8 @@ reset_finalize_body(const hb_env_params &p, const hb_env_buffers &b, float *__re
     const int keep_a = row_a - p.num_single_obs, keep_b = row_b - p.num_single_priv;
     for (int j = warp; j < 2 * seg_count; j += FIN_THREADS / 32) {
         const int env = b.reset_env_ids[prefix + (j >> 1)];
-        float *dst = (j & 1) ? priv_new + (size_t)env * row_b : obs_new + (size_t)env * row_a;
+        float *dst = (j & 1) ? priv_new + (size_t)env * (p.priv_ld ? p.priv_ld : row_b)
+                             : obs_new + (size_t)env * (p.obs_ld ? p.obs_ld : row_a);
         const int keep = (j & 1) ? keep_b : keep_a;
         for (int c = lane; c < keep; c += 32) dst[c] = 0.0f;
     }
@@ -1131,7 +1142,7 @@ reset_finalize_kernel(const __grid_constant__ hb_env_params p, const __grid_cons
 // just reset: hector_env.py:256-261) and the shard-wide half of reset_idx (ids, count, episode means, time-out
 // latch: reset_finalize_body without the zeroing) in a few extra blocks of the same grid - one
 // launch less on the step's dependency chain than shift + reset_finalize_kernel.
-template <int ROW_A, int FRAME_A, int ROW_B, int FRAME_B, int UNROLL>
+template <int ROW_A, int LD_A, int FRAME_A, int ROW_B, int LD_B, int FRAME_B, int UNROLL>
 __global__ void __launch_bounds__(256, 6)
 stack_finalize_kernel(const float *__restrict__ prev_a, float *__restrict__ next_a, uint32_t total_a, uint32_t blocks_a,
                       const float *__restrict__ prev_b, float *__restrict__ next_b, uint32_t total_b, uint32_t blocks_b,
@@ -1147,8 +1158,8 @@ stack_finalize_kernel(const float *__restrict__ prev_a, float *__restrict__ next
         reset_finalize_body(p, b, nullptr, nullptr, tiles, seg, host_count, rng_counter, blockIdx.x, fin_blocks);
     } else {
         const uint32_t blk = blockIdx.x - fin_blocks;
-        if (blk < blocks_a) stack_shift_fixed<ROW_A, FRAME_A, UNROLL, true>(prev_a, next_a, total_a, blk, b.reset_buf);
-        else stack_shift_fixed<ROW_B, FRAME_B, UNROLL, true>(prev_b, next_b, total_b, blk - blocks_a, b.reset_buf);
+        if (blk < blocks_a) stack_shift_fixed<ROW_A, LD_A, FRAME_A, UNROLL, true>(prev_a, next_a, total_a, blk, b.reset_buf);
+        else stack_shift_fixed<ROW_B, LD_B, FRAME_B, UNROLL, true>(prev_b, next_b, total_b, blk - blocks_a, b.reset_buf);
     }
 }
 
@@ -1156,6 +1167,21 @@ int g_use_bulk = 1;
 
 // hector frame stacks (hector_config.py:8-20): obs 15 x 41, privileged obs 15 x 70
 constexpr int ROW_OBS = 15 * OBS, ROW_PRIV = 15 * PRIV;
+// ... and the same rows at a 16-byte pitch (TMA-addressable: the rollout storage's slots)
+constexpr int LD_OBS = (ROW_OBS + 3) / 4 * 4, LD_PRIV = (ROW_PRIV + 3) / 4 * 4;
+
+// 0 = not a built layout, 1 = dense rows, 2 = 16-byte pitch
+int stack_layout(const hb_env_params *p) {
+    const int row_a = p->frame_stack * p->num_single_obs, row_b = p->c_frame_stack * p->num_single_priv;
+    if (row_a != ROW_OBS || p->num_single_obs != OBS || row_b != ROW_PRIV || p->num_single_priv != PRIV) return 0;
+    const int ld_a = p->obs_ld ? p->obs_ld : row_a, ld_b = p->priv_ld ? p->priv_ld : row_b;
+    if (ld_a == ROW_OBS && ld_b == ROW_PRIV) return 1;
+    if (ld_a == LD_OBS && ld_b == LD_PRIV) return 2;
+    return 0;
+}
+
+int shift_any(const float *prev, float *next, const uint8_t *reset_buf, int num_envs, int row, int ld, int frame,
+              cudaStream_t st);
 
 template <int ROW, int FRAME>
 void launch_stack_fixed(const float *prev, float *next, int n, cudaStream_t st) {
@@ -1167,6 +1193,22 @@ void launch_stack_fixed(const float *prev, float *next, int n, cudaStream_t st) 
 
 bool fits_u32(int n, int row) { return (long long)n * row + 64 * 1024 < (1ll << 32); }
 
+int shift_any(const float *prev, float *next, const uint8_t *reset_buf, int num_envs, int row, int ld, int frame,
+              cudaStream_t st) {
+    HB_REQUIRE(prev && next && prev != next, "hb_stack_shift: null or aliasing buffers");
+    HB_REQUIRE(num_envs > 0 && frame > 0 && row > frame && ld >= row, "hb_stack_shift: bad shape");
+    const bool fast = !reset_buf && ld == row && hb::aligned16(prev) && hb::aligned16(next) && fits_u32(num_envs, row);
+    if (fast && row == ROW_OBS && frame == OBS) {
+        launch_stack_fixed<ROW_OBS, OBS>(prev, next, num_envs, st);
+    } else if (fast && row == ROW_PRIV && frame == PRIV) {
+        launch_stack_fixed<ROW_PRIV, PRIV>(prev, next, num_envs, st);
+    } else {
+        const long long total = (long long)num_envs * ld;
+        stack_shift_scalar_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(prev, next, reset_buf, total, row, ld, frame);
+    }
+    HB_CHECK_LAUNCH("stack_shift_kernel");
+    return HB_OK;
+}
 
 }  // namespace
 
@@ -1209,6 +1251,9 @@ static int check_params(const hb_env_params *p, const hb_env_buffers *buf, const
     HB_REQUIRE(p->num_envs > 0, "%s: num_envs must be positive", who);
     HB_REQUIRE(p->resample_interval > 0, "%s: resample_interval must be positive", who);
     HB_REQUIRE(p->num_dof == NDOF, "%s: only the 10-DOF hector layout is built (num_dof=%d)", who, p->num_dof);
+    HB_REQUIRE((p->obs_ld == 0 || p->obs_ld >= p->frame_stack * p->num_single_obs) &&
+                   (p->priv_ld == 0 || p->priv_ld >= p->c_frame_stack * p->num_single_priv),
+               "%s: obs_ld / priv_ld (%d / %d) shorter than a row", who, p->obs_ld, p->priv_ld);
     return HB_OK;
 }
 
@@ -1320,20 +1365,7 @@ int hb_env_post_physics(const hb_env_params *p, const hb_env_buffers *buf, const
 
 int hb_stack_shift(const float *prev, float *next, const uint8_t *reset_buf, int32_t num_envs, int32_t row,
                    int32_t frame, void *stream) {
-    HB_REQUIRE(prev && next && prev != next, "hb_stack_shift: null or aliasing buffers");
-    HB_REQUIRE(num_envs > 0 && frame > 0 && row > frame, "hb_stack_shift: bad shape");
-    cudaStream_t st = (cudaStream_t)stream;
-    const bool fast = !reset_buf && hb::aligned16(prev) && hb::aligned16(next) && fits_u32(num_envs, row);
-    if (fast && row == ROW_OBS && frame == OBS) {
-        launch_stack_fixed<ROW_OBS, OBS>(prev, next, num_envs, st);
-    } else if (fast && row == ROW_PRIV && frame == PRIV) {
-        launch_stack_fixed<ROW_PRIV, PRIV>(prev, next, num_envs, st);
-    } else {
-        const long long total = (long long)num_envs * row;
-        stack_shift_scalar_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(prev, next, reset_buf, total, row, frame);
-    }
-    HB_CHECK_LAUNCH("stack_shift_kernel");
-    return HB_OK;
+    return shift_any(prev, next, reset_buf, num_envs, row, row, frame, (cudaStream_t)stream);
 }
 
 int hb_env_stack_observations(const hb_env_params *p, const hb_env_buffers *buf, const float *obs_prev,
@@ -1343,20 +1375,23 @@ int hb_env_stack_observations(const hb_env_params *p, const hb_env_buffers *buf,
     HB_REQUIRE(obs_prev != obs_new && priv_prev != priv_new, "hb_env_stack_observations: prev and new must not alias");
     cudaStream_t st = (cudaStream_t)stream;
     const int row_a = p->frame_stack * p->num_single_obs, row_b = p->c_frame_stack * p->num_single_priv;
+    const int ld_a = p->obs_ld ? p->obs_ld : row_a, ld_b = p->priv_ld ? p->priv_ld : row_b;
+    const int layout = stack_layout(p);
     const bool fast = hb::aligned16(obs_prev) && hb::aligned16(obs_new) && hb::aligned16(priv_prev) &&
-                      hb::aligned16(priv_new) && row_a == ROW_OBS && p->num_single_obs == OBS && row_b == ROW_PRIV &&
-                      p->num_single_priv == PRIV && fits_u32(p->num_envs, row_b);
+                      hb::aligned16(priv_new) && layout != 0 && fits_u32(p->num_envs, ld_b);
     if (fast) {
-        const uint32_t total_a = (uint32_t)p->num_envs * ROW_OBS, total_b = (uint32_t)p->num_envs * ROW_PRIV;
+        const uint32_t total_a = (uint32_t)p->num_envs * ld_a, total_b = (uint32_t)p->num_envs * ld_b;
         constexpr uint32_t PER = 4 * 256;
         const uint32_t blocks_a = ((total_a + 3u) / 4u + PER - 1) / PER, blocks_b = ((total_b + 3u) / 4u + PER - 1) / PER;
-        HB_CUDA(hb::launch_pdl(hb::use_pdl(p->num_envs), stack_shift_pair_kernel<ROW_OBS, OBS, ROW_PRIV, PRIV, 4>, dim3(blocks_a + blocks_b), dim3(256), 0,
+        auto kernel = layout == 1 ? stack_shift_pair_kernel<ROW_OBS, ROW_OBS, OBS, ROW_PRIV, ROW_PRIV, PRIV, 4>
+                                  : stack_shift_pair_kernel<ROW_OBS, LD_OBS, OBS, ROW_PRIV, LD_PRIV, PRIV, 4>;
+        HB_CUDA(hb::launch_pdl(hb::use_pdl(p->num_envs), kernel, dim3(blocks_a + blocks_b), dim3(256), 0,
                                st, obs_prev, obs_new, total_a, blocks_a, priv_prev, priv_new, total_b));
         HB_CHECK_LAUNCH("stack_shift_pair_kernel");
         return HB_OK;
     }
-    if (int rc = hb_stack_shift(obs_prev, obs_new, nullptr, p->num_envs, row_a, p->num_single_obs, stream)) return rc;
-    return hb_stack_shift(priv_prev, priv_new, nullptr, p->num_envs, row_b, p->num_single_priv, stream);
+    if (int rc = shift_any(obs_prev, obs_new, nullptr, p->num_envs, row_a, ld_a, p->num_single_obs, st)) return rc;
+    return shift_any(priv_prev, priv_new, nullptr, p->num_envs, row_b, ld_b, p->num_single_priv, st);
 }
 
 int hb_env_stack_finalize(const hb_env_params *p, const hb_env_buffers *buf, const float *obs_prev, const float *priv_prev,
@@ -1366,22 +1401,25 @@ int hb_env_stack_finalize(const hb_env_params *p, const hb_env_buffers *buf, con
     HB_REQUIRE(obs_prev != obs_new && priv_prev != priv_new, "hb_env_stack_finalize: prev and new must not alias");
     HB_REQUIRE(buf->scratch_ballots && buf->scratch_sums && buf->reset_env_ids && buf->reset_count && buf->episode_means,
                "hb_env_stack_finalize: null scratch/result buffers");
-    const int row_a = p->frame_stack * p->num_single_obs, row_b = p->c_frame_stack * p->num_single_priv;
+    const int row_b = p->c_frame_stack * p->num_single_priv;
+    const int ld_a = p->obs_ld ? p->obs_ld : p->frame_stack * p->num_single_obs, ld_b = p->priv_ld ? p->priv_ld : row_b;
+    const int layout = stack_layout(p);
     const bool fast = hb::aligned16(obs_prev) && hb::aligned16(obs_new) && hb::aligned16(priv_prev) &&
-                      hb::aligned16(priv_new) && row_a == ROW_OBS && p->num_single_obs == OBS && row_b == ROW_PRIV &&
-                      p->num_single_priv == PRIV && fits_u32(p->num_envs, row_b);
+                      hb::aligned16(priv_new) && layout != 0 && fits_u32(p->num_envs, ld_b);
     if (!fast) {        // other layouts: the two separate launches
         if (int rc = hb_env_stack_observations(p, buf, obs_prev, priv_prev, obs_new, priv_new, stream)) return rc;
         return hb_env_reset_finalize(p, buf, obs_new, priv_new, host_count, rng_counter, stream);
     }
     constexpr uint32_t PER = 4 * 256;
-    const uint32_t total_a = (uint32_t)p->num_envs * ROW_OBS, total_b = (uint32_t)p->num_envs * ROW_PRIV;
+    const uint32_t total_a = (uint32_t)p->num_envs * ld_a, total_b = (uint32_t)p->num_envs * ld_b;
     const uint32_t blocks_a = ((total_a + 3u) / 4u + PER - 1) / PER, blocks_b = ((total_b + 3u) / 4u + PER - 1) / PER;
     const int tiles = (p->num_envs + TILE - 1) / TILE;
     int seg = (tiles + hb::sm_count() - 1) / hb::sm_count();
     if (seg < 8) seg = 8;
     const uint32_t fin_blocks = (uint32_t)((tiles + seg - 1) / seg);
-    HB_CUDA(hb::launch_pdl(hb::use_pdl(p->num_envs), stack_finalize_kernel<ROW_OBS, OBS, ROW_PRIV, PRIV, 4>,
+    auto kernel = layout == 1 ? stack_finalize_kernel<ROW_OBS, ROW_OBS, OBS, ROW_PRIV, ROW_PRIV, PRIV, 4>
+                              : stack_finalize_kernel<ROW_OBS, LD_OBS, OBS, ROW_PRIV, LD_PRIV, PRIV, 4>;
+    HB_CUDA(hb::launch_pdl(hb::use_pdl(p->num_envs), kernel,
                            dim3(blocks_a + blocks_b + fin_blocks), dim3(256), 0, (cudaStream_t)stream, obs_prev, obs_new, total_a,
                            blocks_a, priv_prev, priv_new, total_b, blocks_b, *p, *buf, tiles, seg, host_count,
                            reinterpret_cast<unsigned long long *>(rng_counter)));

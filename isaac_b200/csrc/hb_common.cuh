@@ -140,6 +140,23 @@ __device__ __forceinline__ float4 ld_stream4(const float4 *p) {
                  : "l"(p));
     return v;
 }
+// predicated form: zeros, and no memory access, when `pred` is false (branch-free)
+__device__ __forceinline__ float4 ld_stream4_if(const float4 *p, bool pred) {
+    float4 v;
+    asm volatile(
+        "{\n"
+        ".reg .pred q;\n"
+        "setp.ne.u32 q, %5, 0;\n"
+        "mov.f32 %0, 0f00000000;\n"
+        "mov.f32 %1, 0f00000000;\n"
+        "mov.f32 %2, 0f00000000;\n"
+        "mov.f32 %3, 0f00000000;\n"
+        "@q ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];\n"
+        "}\n"
+        : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+        : "l"(p), "r"((uint32_t)pred));
+    return v;
+}
 __device__ __forceinline__ void st_stream4(float4 *p, const float4 &v) {
     asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
                  "f"(v.w)

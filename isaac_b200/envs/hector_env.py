@@ -76,6 +76,9 @@ def build_env_params(cfg, num_envs: int, num_bodies: int, body_names, dof_names,
     p.num_envs, p.num_dof, p.num_bodies = num_envs, cfg.env.num_actions, num_bodies
     p.num_single_obs, p.frame_stack = cfg.env.num_single_obs, cfg.env.frame_stack
     p.num_single_priv, p.c_frame_stack = cfg.env.single_num_privileged_obs, cfg.env.c_frame_stack
+    # rows at a 16-byte pitch: the observation buffers can then be rollout-storage slots and TMA operands
+    p.obs_ld = (p.num_single_obs * p.frame_stack + 3) // 4 * 4
+    p.priv_ld = (p.num_single_priv * p.c_frame_stack + 3) // 4 * 4
     feet = _find(body_names, [cfg.asset.foot_name])
     knees = _find(body_names, [cfg.asset.knee_name])
     term = _find(body_names, cfg.asset.terminate_after_contacts_on)
@@ -151,7 +154,7 @@ def build_env_params(cfg, num_envs: int, num_bodies: int, body_names, dof_names,
 class HectorFreeEnvB200:
     def __init__(self, cfg, sim_params=None, physics_engine=None, sim_device="cuda:0", headless=True, *,
                  physics, statics=None, body_names=None, dof_names=None, dof_effort=None,
-                 initial_noise=None):
+                 initial_noise=None, dense_rows=False):
         """`physics`: the opaque stage (isaac_b200.physics).  `statics`: per-env constants that the
         reference collects while creating actors (legged_robot.py:256-301,683-709); defaults are the
         config constants.  body/dof names default to what Isaac Gym reports for the hector URDF."""
@@ -171,6 +174,8 @@ class HectorFreeEnvB200:
         self.dof_names = dof_names or cfg.asset.dof_names
         dof_effort = dof_effort or cfg.asset.dof_effort
         self._p = build_env_params(cfg, N, self.num_bodies, body_names, self.dof_names, dof_effort)
+        if dense_rows:          # contiguous [N,615] / [N,1050] observation tensors like the reference's (no row padding)
+            self._p.obs_ld, self._p.priv_ld = self._p.num_single_obs * self._p.frame_stack, self._p.num_single_priv * self._p.c_frame_stack
         # _parse_cfg (legged_robot.py:711-722)
         self.dt = cfg.control.decimation * cfg.sim.dt
         self.obs_scales = cfg.normalization.obs_scales
@@ -230,10 +235,14 @@ class HectorFreeEnvB200:
         self.gravity_vec = torch.tensor([0.0, 0.0, -1.0], **f32).repeat(N, 1)
         self.forward_vec = torch.tensor([1.0, 0.0, 0.0], **f32).repeat(N, 1)
         # ping-pong observation buffers: the tensor returned by step() stays valid until the step
-        # after next (PPO.act keeps references until process_env_step, ppo.py:99-100,111)
-        self._obs = [z(N, self.num_obs), z(N, self.num_obs)]
-        self._priv = [z(N, self.num_privileged_obs), z(N, self.num_privileged_obs)]
-        self._cur = 0
+        # after next (PPO.act keeps references until process_env_step, ppo.py:99-100,111).  Rows sit at a
+        # 16-byte pitch (616 / 1052 floats); a caller may hand the env the buffers of the NEXT step
+        # (set_next_observation_buffers: the rollout storage's slots), else it alternates between its own two.
+        # Each buffer pair travels as (obs, priv, (obs address, priv address)): the addresses key the step graphs.
+        self._own = [self._buffer_pair(z(N, self._p.obs_ld)[:, :self.num_obs],
+                                       z(N, self._p.priv_ld)[:, :self.num_privileged_obs]) for _ in range(2)]
+        self._cur_buf = self._own[0]
+        self._next_out = None
         # reset compaction + extras
         self.reset_env_ids = torch.zeros(N, dtype=torch.int32, device=dev)
         self._reset_count = torch.zeros(1, dtype=torch.int32, device=dev)
@@ -296,6 +305,34 @@ class HectorFreeEnvB200:
     def _stream(self):
         return torch.cuda.current_stream(self.device).cuda_stream
 
+    def set_next_observation_buffers(self, obs: torch.Tensor, privileged_obs: torch.Tensor) -> None:
+        """The next step() writes its observations into these tensors instead of the env's own ping-pong pair
+        (one step only).  They are what step() then returns; rows must sit at the env's pitch
+        (`[N, num_obs]` views of `[N, 616]` / `[N, 1052]` fp32 buffers, 16-byte aligned) and must not be the
+        buffers the current observations live in.  PPO.act points this at the rollout storage's next slot, so
+        that `add_transitions`' observation copies (rollout_storage.py:90-92) never happen."""
+        for t, width, ld in ((obs, self.num_obs, self._p.obs_ld), (privileged_obs, self.num_privileged_obs, self._p.priv_ld)):
+            if (t.device != self.device or t.dtype != torch.float32 or tuple(t.shape) != (self.num_envs, width)
+                    or t.stride() != (ld, 1) or t.data_ptr() % 16):
+                raise ValueError(f"observation buffer must be a [{self.num_envs}, {width}] fp32 view with row pitch {ld} on {self.device}")
+        pair = self._buffer_pair(obs, privileged_obs)
+        if pair[2][0] == self._cur_buf[2][0] or pair[2][1] == self._cur_buf[2][1]:
+            raise ValueError("the next observation buffers must not alias the current ones")
+        self._next_out = pair
+
+    @staticmethod
+    def _buffer_pair(obs, priv):
+        return (obs, priv, (obs.data_ptr(), priv.data_ptr()))
+
+    def _take_output(self):
+        """Where this step's observations go: the caller's buffers if it supplied any, else the own pair not in use."""
+        out, cur = self._next_out, self._cur_buf
+        if out is not None:
+            self._next_out = None
+            if out[2][0] != cur[2][0] and out[2][1] != cur[2][1]:
+                return out
+        return self._own[1] if cur is self._own[0] else self._own[0]
+
     def inject_noise(self, frame) -> None:
         """Use the supplied draws (isaac_b200.synthetic.NoiseFrame on this device) for the next step
         instead of the env's own generator — "noise injected as a supplied tensor"."""
@@ -356,12 +393,14 @@ class HectorFreeEnvB200:
 
     # ------------------------------------------------------------------ CUDA-graph replay of the step
     def enable_cuda_graph(self):
-        """Capture the step's launch sequence for physics stages that need no host work between the
-        decimation sub-steps (`physics.capturable`, e.g. the synthetic stage used by tests and bench.py).
-        Two graphs per ping-pong parity: A = action prologue + first PD sub-step (one kernel); then the host
-        hands the previous step's reset ids to the physics stage (legged_robot.py:370-372,394-396) while A
-        runs; B = the remaining PD launches, post-physics, the frame-stack shift and the reset finalisation.  Push steps (every
-        `push_interval`) and steps with injected noise take the eager path."""
+        """Replay the step's launch sequence from CUDA graphs, for physics stages that need no host work between
+        the decimation sub-steps (`physics.capturable`, e.g. the synthetic stage used by tests and bench.py).
+        Two graphs per step: A = action prologue + first PD sub-step (one kernel); then the host hands the
+        previous step's reset ids to the physics stage (legged_robot.py:370-372,394-396) while A runs; B = the
+        remaining PD launches, post-physics, the frame-stack shift with the reset finalisation.  B is captured on
+        first use for each (previous buffers, next buffers) pair - two for the env's own ping-pong pair, one per
+        slot when the rollout storage supplies the buffers.  Push steps (every `push_interval`) and steps with
+        injected noise take the eager path."""
         if not getattr(self.physics, "capturable", False):
             raise ValueError("this physics stage needs host calls between sub-steps; CUDA-graph replay is not possible")
         if self.device.type != "cuda":
@@ -369,47 +408,52 @@ class HectorFreeEnvB200:
         N = self.num_envs
         self._g_actions = torch.zeros(N, self.num_actions, device=self.device)
         self._g_means = torch.zeros(2, HB_NUM_REWARDS, device=self.device)
+        self._g_par = 0                       # which half of _g_means holds the previous step's episode means
         self._apply_pending_resets()
         torch.cuda.synchronize(self.device)
-        saved = (self._cur, self._step_index, self._pending_event)
-        graphs, pool = {}, None
-        lib = self._lib
-        dec = self.cfg.control.decimation
-        for parity in (0, 1):
-            self._cur = parity
-            ga, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
-            with torch.cuda.graph(ga, pool=pool):
+        self._g_nz = EnvNoise()
+        self._bind_device_rng(self._g_nz)
+        ga = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(ga):
+            _lib.check(self._lib.hb_env_prologue_torques(self._pp, self._pb, self._g_actions.data_ptr(),
+                                                         C.byref(self._g_nz), self._stream()), "hb_env_prologue_torques")
+        self._graph_a, self._graph_pool = ga, ga.pool()
+        self._graphs = {}
+        self.graph_launches_per_step = self.cfg.control.decimation + 2     # this library's kernels per replayed step (prologue+PD, PD x9, post, stack+finalize)
+
+    def _graph_b(self, prev, out, par):
+        key = (prev[2], out[2], par)
+        entry = self._graphs.get(key)
+        if entry is None:
+            if len(self._graphs) >= 256:      # buffers keep changing (new storage): drop the stale graphs
+                self._graphs.clear()
+            saved = (self._b.episode_means, self._b.episode_means_prev)
+            gb = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gb, pool=self._graph_pool):
                 st = self._stream()
-                nz = EnvNoise()
-                self._bind_device_rng(nz)
-                _lib.check(lib.hb_env_prologue_torques(self._pp, self._pb, self._g_actions.data_ptr(), C.byref(nz), st),
-                           "hb_env_prologue_torques")
-            pool = pool or ga.pool()
-            with torch.cuda.graph(gb, pool=pool):
-                st = self._stream()
-                prev, cur = parity, parity ^ 1
-                for _ in range(dec - 1):
-                    _lib.check(lib.hb_env_compute_torques(self._pp, self._pb, st), "hb_env_compute_torques")
-                self._b.episode_means = self._g_means[cur].data_ptr()
-                self._b.episode_means_prev = self._g_means[prev].data_ptr()
-                self._launch_post_kernels(HB_STAGE_STEP, C.byref(nz), prev, cur, True, st)
-            graphs[parity] = (ga, gb, nz)
-        self._cur, self._step_index, self._pending_event = saved
-        self._graphs = graphs
-        self.graph_launches_per_step = dec + 2     # this library's kernels per replayed step (prologue+PD, PD x9, post, stack+finalize)
+                for _ in range(self.cfg.control.decimation - 1):
+                    _lib.check(self._lib.hb_env_compute_torques(self._pp, self._pb, st), "hb_env_compute_torques")
+                self._b.episode_means = self._g_means[par ^ 1].data_ptr()
+                self._b.episode_means_prev = self._g_means[par].data_ptr()
+                self._launch_post_kernels(HB_STAGE_STEP, C.byref(self._g_nz), prev, out, True, st)
+            self._b.episode_means, self._b.episode_means_prev = saved
+            entry = self._graphs[key] = (gb, prev, out)      # the graph keeps its buffers alive
+        return entry[0]
 
     def _step_graph(self, actions):
-        ga, gb, _ = self._graphs[self._cur]
         self._g_actions.copy_(actions, non_blocking=True)
         slot = self._step_index % _EXTRAS_RING
+        par = self._g_par
         if self._step_index > 0 and self._last_means_slot is not None:
             # the previous step ran eagerly: hand its episode means to the graph's carry-over slot
-            self._g_means[self._cur].copy_(self._episode_means[self._last_means_slot], non_blocking=True)
-        ga.replay()
+            self._g_means[par].copy_(self._episode_means[self._last_means_slot], non_blocking=True)
+        self._graph_a.replay()
         self._apply_pending_resets()          # gym.set_*_indexed of the previous step's resets
-        gb.replay()
-        self._cur ^= 1
-        self._episode_means[slot].copy_(self._g_means[self._cur], non_blocking=True)
+        out = self._take_output()
+        self._graph_b(self._cur_buf, out, par).replay()
+        self._cur_buf = out
+        self._g_par = par ^ 1
+        self._episode_means[slot].copy_(self._g_means[par ^ 1], non_blocking=True)
         self._last_means_slot = None
         self._pending_event = self._events[self._step_index & 1]
         self._pending_event.record(torch.cuda.current_stream(self.device))
@@ -417,7 +461,7 @@ class HectorFreeEnvB200:
         if self.cfg.env.send_timeouts:
             self.extras["time_outs"] = self._time_outs_latched
         self._step_index += 1
-        return self.obs_buf, self.privileged_obs_buf, self.rew_buf, self.reset_buf, self.extras
+        return out[0], out[1], self.rew_buf, self.reset_buf, self.extras
 
     def _compute_torques(self, actions=None):
         """legged_robot.py:339-355 on self.actions (one decimation sub-step)."""
@@ -435,16 +479,17 @@ class HectorFreeEnvB200:
         lib, st = self._lib, self._stream()
         if self._nz.u_reset is None and self._nz.rng_counter is None:
             self._draw_noise(False)
-        prev, cur = self._cur, self._cur ^ 1
         emit = bool(stages & (HB_STAGE_STEP | HB_STAGE_OBS))
+        prev = self._cur_buf
+        out = self._take_output() if emit else self._own[1 if prev is self._own[0] else 0]
         slot = self._step_index % _EXTRAS_RING
         prev_slot = (self._step_index - 1) % _EXTRAS_RING
         means0 = self._episode_means.data_ptr()
         self._b.episode_means = means0 + slot * HB_NUM_REWARDS * 4
         self._b.episode_means_prev = means0 + prev_slot * HB_NUM_REWARDS * 4 if self._step_index > 0 else None
-        self._launch_post_kernels(stages, self._pn, prev, cur, emit, st)
+        self._launch_post_kernels(stages, self._pn, prev, out, emit, st)
         if emit:
-            self._cur = cur
+            self._cur_buf = out
         if self._events:
             self._pending_event = self._events[self._step_index & 1]
             self._pending_event.record(torch.cuda.current_stream(self.device))
@@ -456,15 +501,15 @@ class HectorFreeEnvB200:
         self._injected = None
         self._nz.u_reset = self._nz.rng_counter = None
 
-    def _launch_post_kernels(self, stages, noise_ref, prev, cur, emit, st):
-        """post-physics -> frame-stack shift + reset finalisation, on one stream."""
+    def _launch_post_kernels(self, stages, noise_ref, prev, out, emit, st):
+        """post-physics -> frame-stack shift + reset finalisation, on one stream; prev / out = (obs, priv) tensors."""
         lib = self._lib
-        obs_new, priv_new = self._obs[cur].data_ptr(), self._priv[cur].data_ptr()
+        obs_new, priv_new = out[0].data_ptr(), out[1].data_ptr()
         _lib.check(lib.hb_env_post_physics(self._pp, self._pb, noise_ref, obs_new, priv_new, stages, st),
                    "hb_env_post_physics")
         noise = noise_ref._obj          # the EnvNoise behind the byref
         if emit:        # shift + shard-wide reset results in one launch
-            _lib.check(lib.hb_env_stack_finalize(self._pp, self._pb, self._obs[prev].data_ptr(), self._priv[prev].data_ptr(),
+            _lib.check(lib.hb_env_stack_finalize(self._pp, self._pb, prev[0].data_ptr(), prev[1].data_ptr(),
                                                  obs_new, priv_new, self._host_count.data_ptr(), noise.rng_counter, st),
                        "hb_env_stack_finalize")
         else:
@@ -487,11 +532,11 @@ class HectorFreeEnvB200:
     # ------------------------------------------------------------------ reference-named API
     @property
     def obs_buf(self):
-        return self._obs[self._cur]
+        return self._cur_buf[0]
 
     @property
     def privileged_obs_buf(self):
-        return self._priv[self._cur]
+        return self._cur_buf[1]
 
     def get_observations(self):
         return self.obs_buf
@@ -507,7 +552,7 @@ class HectorFreeEnvB200:
         self.reset_buf.zero_()
         self.reset_buf[env_ids] = True
         self._launch_post(HB_STAGE_RESET_MASK)
-        for hist in (*self._obs, *self._priv):
+        for hist in self._cur_buf[:2]:
             hist[env_ids] = 0.0
         self._apply_pending_resets()
 

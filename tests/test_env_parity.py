@@ -278,17 +278,21 @@ def test_device_generator_draws(lib, cuda_device):
     assert abs(torch.corrcoef(torch.stack((cols[:-1, 0], cols[1:, 0])))[0, 1].item()) < 0.06   # env to env
 
 
+@pytest.mark.parametrize("pitched", [False, True], ids=["dense", "pitched"])
 @pytest.mark.parametrize("n", [1, 37, 1003, 4096])
-def test_fused_shift_finalize_equals_separate_calls(lib, cuda_device, n):
+def test_fused_shift_finalize_equals_separate_calls(lib, cuda_device, n, pitched):
     """hb_env_stack_finalize (what step() launches) against hb_env_stack_observations + hb_env_reset_finalize on the
     same inputs: identical frame stacks, id lists, counts, episode means and time-out latch (ragged sizes included:
-    615 n is not a multiple of 4 for n = 1003, the last ballot word is partial for n = 37)."""
+    615 n is not a multiple of 4 for n = 1003, the last ballot word is partial for n = 37).  Both row layouts:
+    dense [n,615] / [n,1050] and the 16-byte pitch the env and the rollout storage use (616 / 1052)."""
     from isaac_b200 import _lib
     dev = cuda_device
     tape = make_tape(n, 2, seed=3 + n, fall_prob=0.2)
     env, phys = make_cuda_env(tape, dev)
+    ld_o, ld_p = (616, 1052) if pitched else (615, 1050)
+    env._p.obs_ld, env._p.priv_ld = (ld_o, ld_p) if pitched else (0, 0)
     g = torch.Generator(device=dev).manual_seed(n)
-    prev_o, prev_p = torch.randn(n, 615, device=dev, generator=g), torch.randn(n, 1050, device=dev, generator=g)
+    prev_o, prev_p = torch.randn(n, ld_o, device=dev, generator=g), torch.randn(n, ld_p, device=dev, generator=g)
     reset = torch.rand(n, device=dev, generator=g) < 0.3
     if n == 37:
         reset[36] = True           # the last, partial tile
@@ -311,9 +315,9 @@ def test_fused_shift_finalize_equals_separate_calls(lib, cuda_device, n):
         # the outputs live inside larger allocations with sentinel guards on both sides (compute-sanitizer is not
         # available on this pool: an out-of-bounds store of the ragged tail paths would show up here)
         GUARD = 1024
-        raw_o = torch.full((n * 615 + 2 * GUARD,), -3.0, device=dev)
-        raw_p = torch.full((n * 1050 + 2 * GUARD,), -3.0, device=dev)
-        new_o, new_p = raw_o[GUARD:GUARD + n * 615].view(n, 615), raw_p[GUARD:GUARD + n * 1050].view(n, 1050)
+        raw_o = torch.full((n * ld_o + 2 * GUARD,), -3.0, device=dev)
+        raw_p = torch.full((n * ld_p + 2 * GUARD,), -3.0, device=dev)
+        new_o, new_p = raw_o[GUARD:GUARD + n * ld_o].view(n, ld_o), raw_p[GUARD:GUARD + n * ld_p].view(n, ld_p)
         new_o.fill_(7.0), new_p.fill_(7.0)
         assert new_o.data_ptr() % 16 == 0 and new_p.data_ptr() % 16 == 0
         means = torch.zeros(18, device=dev)
@@ -327,7 +331,7 @@ def test_fused_shift_finalize_equals_separate_calls(lib, cuda_device, n):
                                                      new_p.data_ptr(), st), "stack")
             _lib.check(lib.hb_env_reset_finalize(P, B, new_o.data_ptr(), new_p.data_ptr(), hc, None, st), "finalize")
         torch.cuda.synchronize()
-        for raw, size in ((raw_o, n * 615), (raw_p, n * 1050)):
+        for raw, size in ((raw_o, n * ld_o), (raw_p, n * ld_p)):
             assert (raw[:GUARD] == -3.0).all() and (raw[GUARD + size:] == -3.0).all(), "store outside the frame stack"
         cnt = int(env._reset_count.item())
         results.append((new_o.clone(), new_p.clone(), cnt, env.reset_env_ids[:cnt].clone(), means.clone(),
@@ -337,9 +341,9 @@ def test_fused_shift_finalize_equals_separate_calls(lib, cuda_device, n):
         assert (x == y) if isinstance(x, int) else torch.equal(x, y)
     new_o, new_p, cnt, ids, means, latch, host, sums_after = b
     keep = ~reset
-    assert torch.equal(new_o[keep][:, :574], prev_o[keep][:, 41:]) and (new_o[reset][:, :574] == 0).all()
-    assert torch.equal(new_p[keep][:, :980], prev_p[keep][:, 70:]) and (new_p[reset][:, :980] == 0).all()
-    assert (new_o[:, 574:] == 7.0).all() and (new_p[:, 980:] == 7.0).all(), "the newest-frame slot belongs to post-physics"
+    assert torch.equal(new_o[keep][:, :574], prev_o[keep][:, 41:615]) and (new_o[reset][:, :574] == 0).all()
+    assert torch.equal(new_p[keep][:, :980], prev_p[keep][:, 70:1050]) and (new_p[reset][:, :980] == 0).all()
+    assert (new_o[:, 574:] == 7.0).all() and (new_p[:, 980:] == 7.0).all(), "the newest-frame slot (and the row padding) belongs to post-physics"
     assert cnt == int(reset.sum()) == host and torch.equal(ids.long(), reset.nonzero().flatten())
     if cnt:
         np.testing.assert_allclose(means.cpu().numpy(), (sums / cnt).float().cpu().numpy() / 24.0, rtol=1e-6)
@@ -403,3 +407,37 @@ def test_soak_replayed_steps_and_learning_iterations(lib, cuda_device):
         assert np.isfinite(v_loss) and np.isfinite(s_loss) and np.isfinite(alg.last_mean_kl), (it, v_loss, s_loss)
         assert torch.isfinite(ac.flat).all() and 1e-5 <= alg.learning_rate <= 1e-2
     assert not torch.equal(w0, ac.flat) and (ac.grad == 0).all()
+
+
+def test_caller_supplied_observation_buffers(lib, cuda_device):
+    """set_next_observation_buffers: the step writes into the caller's pitched buffers (one step only) exactly what
+    it would have written into its own pair; buffers of the wrong shape / pitch / aliasing the current ones are
+    refused."""
+    dev = cuda_device
+    n = 257
+    tape = make_tape(n, 4, seed=21, fall_prob=0.1)
+    env_a, phys_a = make_cuda_env(tape, dev)
+    env_b, phys_b = make_cuda_env(tape, dev)
+    env_a.seed(5), env_b.seed(5)
+    ext = [(torch.full((n, 616), 9.0, device=dev), torch.full((n, 1052), 9.0, device=dev)) for _ in range(2)]
+    actions = torch.zeros(n, 10, device=dev)
+    for k in range(3):
+        frame = tape.physics[k + 1].to(dev)
+        phys_a.load_frame(frame), phys_b.load_frame(frame)
+        want_o, want_p = env_a.step(actions)[:2]
+        if k < 2:
+            o, p = ext[k][0][:, :615], ext[k][1][:, :1050]
+            env_b.set_next_observation_buffers(o, p)
+        got_o, got_p = env_b.step(actions)[:2]
+        if k < 2:
+            assert got_o.data_ptr() == o.data_ptr() and got_p.data_ptr() == p.data_ptr()
+            assert (ext[k][0][:, 615:] == 9.0).all() and (ext[k][1][:, 1050:] == 9.0).all(), "row padding is never written"
+        else:
+            assert got_o.data_ptr() in (env_b._own[0][0].data_ptr(), env_b._own[1][0].data_ptr()), "one step only"
+        assert torch.equal(got_o, want_o) and torch.equal(got_p, want_p), k
+    with pytest.raises(ValueError):
+        env_b.set_next_observation_buffers(torch.zeros(n, 615, device=dev), ext[0][1][:, :1050])     # dense rows
+    with pytest.raises(ValueError):
+        env_b.set_next_observation_buffers(ext[0][0][:-1, :615], ext[0][1][:-1, :1050])             # wrong num_envs
+    with pytest.raises(ValueError):
+        env_b.set_next_observation_buffers(env_b.obs_buf, ext[0][1][:, :1050])                      # aliases the current

@@ -325,8 +325,8 @@ def test_fused_head_matches_autograd_from_hidden(lib, cuda_device):
 
 def test_graphed_rollout_equals_eager(lib, cuda_device):
     """PPO.act's CUDA-graph replay (small shards, own N(0,1) draw) must leave in the rollout slot exactly what the
-    eager path writes when it is handed the same draw; the two observation buffers of the env's ping-pong get one
-    graph each."""
+    eager path writes when it is handed the same draw; every rollout slot gets one graph (the GEMMs read the
+    observations from the slot)."""
     dev = cuda_device
     n, t = 256, 6
     cfg = dict(mg.PPO_ALG, schedule="fixed")
@@ -340,7 +340,7 @@ def test_graphed_rollout_equals_eager(lib, cuda_device):
         obs, cobs = bufs[k & 1]
         obs.copy_(torch.randn(n, 615, generator=g)), cobs.copy_(torch.randn(n, 1050, generator=g))
         a_g = alg_g.act(obs, cobs)
-        eps = alg_g._act_stage[2].clone()
+        eps = alg_g._act_stage.clone()
         alg_e.injected_eps = eps
         a_e = alg_e.act(obs, cobs)
         assert torch.equal(a_g, a_e), k
@@ -348,8 +348,71 @@ def test_graphed_rollout_equals_eager(lib, cuda_device):
         infos = {"time_outs": (torch.rand(n, generator=g) < 0.1).to(dev)}
         alg_g.process_env_step(rew, dn, infos), alg_e.process_env_step(rew, dn, infos)
     torch.cuda.synchronize()
-    assert len(alg_g._act_graphs) == 2
+    assert len(alg_g._act_graphs) == t
     assert abs(eps.mean().item()) < 0.1 and abs(eps.std().item() - 1.0) < 0.1
     for name in ("observations", "privileged_observations", "actions", "actions_log_prob", "mu", "sigma", "values", "rewards",
                  "dones"):
         assert torch.equal(getattr(alg_g.storage, name), getattr(alg_e.storage, name)), name
+
+
+@pytest.mark.parametrize("graphs", [False, True], ids=["eager", "graphs"])
+def test_attached_rollout_writes_observations_in_place(lib, cuda_device, graphs):
+    """with PPO.attach_env the env writes each step's observations straight into the rollout
+    slot act() records them in.  Two rollouts + updates of an attached pair against a detached pair from the same
+    seeds: identical storage, actions, returned observations and weights - and in the attached run the tensors
+    step() returns ARE the storage slots (no copy), slot T carrying the observations over to the next rollout."""
+    from isaac_b200.synthetic import make_tape
+    from test_env_parity import make_cuda_env
+    dev = cuda_device
+    n, t, frames = 512, 5, 3
+    cfg = dict(mg.PPO_ALG, schedule="adaptive", num_learning_epochs=2, num_mini_batches=2)
+    tape = make_tape(n, frames + 1, seed=11, fall_prob=0.05)
+    phys_frames = [f.to(dev) for f in tape.physics[1:]]
+    runs = []
+    for attached in (False, True):
+        env, phys = make_cuda_env(tape, dev)
+        env.seed(77)
+        if graphs:
+            env.enable_cuda_graph()
+        alg, _, _ = make_pair(dev, n, t, cfg)
+        alg.graph_rollout = graphs
+        if runs:
+            alg.actor_critic.load_state_dict(runs[0]["sd"])
+        sd0 = {k: v.clone() for k, v in alg.actor_critic.state_dict().items()}
+        if attached:
+            alg.attach_env(env)
+        g = torch.Generator().manual_seed(5)
+        obs, cobs = env.get_observations(), env.get_privileged_observations()
+        log = []
+        for it in range(2):
+            for k in range(t):
+                alg.injected_eps = torch.randn(n, 10, generator=g).to(dev) if not graphs else None
+                if graphs:          # the graph draws eps itself: fix torch's CUDA generator instead
+                    torch.cuda.manual_seed(1000 * it + k)
+                a = alg.act(obs, cobs)
+                if attached:
+                    so, sp = alg.storage.observation_slot(k)
+                    assert (so.data_ptr() == obs.data_ptr()) == (k > 0), "only the carried-over slot T is copied"
+                phys.load_frame(phys_frames[(it * t + k) % frames])
+                obs, cobs, rew, dn, infos = env.step(a)
+                if attached:
+                    so, sp = alg.storage.observation_slot(k + 1)
+                    assert obs.data_ptr() == so.data_ptr() and cobs.data_ptr() == sp.data_ptr(), "step() wrote into the next slot"
+                alg.process_env_step(rew, dn, infos)
+                log.append((a.clone(), obs.clone(), cobs.clone(), rew.clone(), dn.clone()))
+            alg.compute_returns(cobs)
+            snap = {name: getattr(alg.storage, name).clone() for name in
+                    ("observations", "privileged_observations", "actions", "values", "rewards", "dones", "returns",
+                     "advantages", "actions_log_prob")}
+            torch.manual_seed(50 + it)          # the minibatch permutation (rollout_storage.py:149)
+            alg.update()
+            log.append(tuple(snap[k] for k in sorted(snap)))
+        torch.cuda.synchronize()
+        runs.append(dict(sd=sd0, log=log, final=alg.actor_critic.flat.clone()))
+    for i, (x, y) in enumerate(zip(runs[0]["log"], runs[1]["log"])):
+        for j, (u, v) in enumerate(zip(x, y)):
+            if i <= t or u.dtype in (torch.bool, torch.uint8):       # everything up to the first update: bit for bit
+                assert torch.equal(u, v), (i, j)
+            else:       # the weight-gradient GEMMs accumulate split-K partials with float atomics: order-dependent bits
+                torch.testing.assert_close(u, v, rtol=1e-2, atol=5e-3, msg=lambda m: f"{(i, j)}: {m}")
+    torch.testing.assert_close(runs[0]["final"], runs[1]["final"], rtol=1e-2, atol=5e-3)       # Adam: sign flips of ~0 gradients
