@@ -14,6 +14,7 @@ of `mini_batch_generator` are done once per update into minibatch-ordered buffer
 from __future__ import annotations
 
 import ctypes as C
+from types import SimpleNamespace
 from typing import Optional
 
 import torch
@@ -116,6 +117,8 @@ class PPO:
     def init_storage(self, num_envs, num_transitions_per_env, actor_obs_shape, critic_obs_shape, action_shape):
         self.storage = RolloutStorage(num_envs, num_transitions_per_env, actor_obs_shape, critic_obs_shape,
                                       action_shape, self.device)
+        self._act_graphs.clear()            # they address the previous storage's slots
+        self._slots = None
 
     def test_mode(self):
         self.actor_critic.eval()
@@ -133,51 +136,72 @@ class PPO:
             raise TypeError("attach_env needs an env with set_next_observation_buffers()")
         self._env = env
 
+    def _slot(self, k):
+        """Views and addresses of rollout slot k, built once per storage (tensor indexing costs microseconds)."""
+        s = self.storage
+        cache = self.__dict__.get("_slots")
+        if cache is None or cache[0] is not s:
+            cache = self._slots = (s, {})
+        e = cache[1].get(k)
+        if e is None:
+            e = cache[1][k] = SimpleNamespace(
+                xa=s._observations[k], xc=s._privileged_observations[k], obs=s.observations[k],
+                priv=s.privileged_observations[k], actions=s.actions[k], values=s.values[k],
+                logp=s.actions_log_prob[k].view(-1), mu=s.mu[k], sigma=s.sigma[k], next=s.observation_slot(k + 1),
+                rewards_ptr=s.rewards[k].data_ptr(), dones_ptr=s.dones[k].data_ptr())
+            e.xa_ptr, e.xc_ptr, e.values_ptr = e.xa.data_ptr(), e.xc.data_ptr(), e.values.data_ptr()
+            e.next_ptrs = (e.next[0].data_ptr(), e.next[1].data_ptr())
+        return e
+
+    def _launch_act_head(self, e, h3a, h3c, eps, n, st):
+        ac = self.actor_critic
+        La, Lc = [L for L in ac.layers if L.last]
+        _lib.check(self._lib.hb_ppo_act_fused(h3a.data_ptr(), h3a.stride(0), h3c.data_ptr(), h3c.stride(0),
+                                              ac._matrix(ac.flat, La).data_ptr(), ac._matrix(ac.flat, Lc).data_ptr(), La.ld,
+                                              ac.std.data_ptr(), eps.data_ptr(), n, e.actions.data_ptr(),
+                                              e.logp.data_ptr(), e.mu.data_ptr(), e.sigma.data_ptr(), e.values_ptr, st),
+                   "hb_ppo_act_fused")
+
     def act(self, obs, critic_obs):
         """ppo.py:91-101.  Fast path (both last hidden layers 128 wide, rollout slot available): the observations
         are recorded in the slot first (16-byte row pitch: TMA cannot address 615- / 1050-float rows; no copy at all
         when the env wrote them there, see attach_env) and feed the GEMMs from the slot, three hidden-layer GEMMs per
         network, then ONE kernel for the two output layers, the sample, its log-prob, mu, sigma and the value, written
-        straight into the storage slot (rollout_storage.py:87-100's copies of these tensors disappear)."""
-        ac, lib, s = self.actor_critic, self._lib, self.storage
+        straight into the storage slot (rollout_storage.py:87-100's copies of these tensors disappear).  Small shards
+        replay all of it from one CUDA graph per slot."""
+        ac, s = self.actor_critic, self.storage
         n = obs.shape[0]
-        st = torch.cuda.current_stream(self.device).cuda_stream
-        ws = ac.workspace(n)
         t = self.transition
         fast = (ac.fused_head and s is not None and s.step < s.num_transitions_per_env and n == s.num_envs
                 and s.privileged_observations is not None and obs.is_cuda and critic_obs.is_cuda)
         if fast:
             k = s.step
-            xa, xc = s._observations[k], s._privileged_observations[k]
-            if obs.data_ptr() != xa.data_ptr() or obs.stride(0) != s.obs_ld:
-                s.observations[k].copy_(obs)
-            if critic_obs.data_ptr() != xc.data_ptr() or critic_obs.stride(0) != s.priv_ld:
-                s.privileged_observations[k].copy_(critic_obs)
+            e = self._slot(k)
+            if obs.data_ptr() != e.xa_ptr or obs.stride(0) != s.obs_ld:
+                e.obs.copy_(obs)
+            if critic_obs.data_ptr() != e.xc_ptr or critic_obs.stride(0) != s.priv_ld:
+                e.priv.copy_(critic_obs)
             if self.graph_rollout and self.injected_eps is None and n <= self.graph_rollout_max_envs:
-                # small shards: the hidden layers of both networks are replayed from one CUDA graph per slot
-                # (launch-bound at this size), the two chains on parallel branches
-                h3a, h3c, eps = self._replay_act_graph(k, n, ws)
+                self._replay_act_graph(k, e, n)
             else:
+                ws = ac.workspace(n)
                 eps = self.injected_eps if self.injected_eps is not None else torch.randn(n, ac.num_actions, device=self.device)
-                h3a = ac._mlp_forward("actor", xa, ws, hidden_only=True)
-                h3c = ac._mlp_forward("critic", xc, ws, hidden_only=True)
-            self.injected_eps = None
-            La, Lc = [L for L in ac.layers if L.last]
-            _lib.check(lib.hb_ppo_act_fused(h3a.data_ptr(), h3a.stride(0), h3c.data_ptr(), h3c.stride(0),
-                                            ac._matrix(ac.flat, La).data_ptr(), ac._matrix(ac.flat, Lc).data_ptr(), La.ld,
-                                            ac.std.data_ptr(), eps.contiguous().data_ptr(), n, s.actions[k].data_ptr(),
-                                            s.actions_log_prob[k].data_ptr(), s.mu[k].data_ptr(), s.sigma[k].data_ptr(),
-                                            s.values[k].data_ptr(), st), "hb_ppo_act_fused")
-            t.actions, t.values, t.actions_log_prob = s.actions[k], s.values[k], s.actions_log_prob[k].view(-1)
-            t.action_mean, t.action_sigma = s.mu[k], s.sigma[k]
+                h3a = ac._mlp_forward("actor", e.xa, ws, hidden_only=True)
+                h3c = ac._mlp_forward("critic", e.xc, ws, hidden_only=True)
+                self._launch_act_head(e, h3a, h3c, eps.contiguous(), n, torch.cuda.current_stream(self.device).cuda_stream)
+                self.injected_eps = None
+            t.actions, t.values, t.actions_log_prob = e.actions, e.values, e.logp
+            t.action_mean, t.action_sigma = e.mu, e.sigma
             t.observations, t.critic_observations = obs, critic_obs
             self._recorded_slot = k
-            env = getattr(self, "_env", None)
+            env = self.__dict__.get("_env")
             if env is not None and env.num_envs == n:
-                nxt = s.observation_slot(k + 1)          # slot T exists: the observations after the last transition
-                if nxt[0].data_ptr() != obs.data_ptr() and nxt[1].data_ptr() != critic_obs.data_ptr():
-                    env.set_next_observation_buffers(*nxt)
+                # slot T exists: it takes the observations after the last transition
+                if e.next_ptrs[0] != obs.data_ptr() and e.next_ptrs[1] != critic_obs.data_ptr():
+                    env.set_next_observation_buffers(*e.next)
             return t.actions
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        ws = ac.workspace(n)
         eps = self.injected_eps if self.injected_eps is not None else torch.randn(n, ac.num_actions, device=self.device)
         self.injected_eps = None
         self._recorded_slot = None
@@ -186,23 +210,22 @@ class PPO:
         actions = torch.empty(n, ac.num_actions, device=self.device)
         logp = torch.empty(n, device=self.device)
         mu, sigma = torch.empty_like(actions), torch.empty_like(actions)
-        _lib.check(lib.hb_ppo_act_head(mu16.data_ptr(), 16, ac.std.data_ptr(), eps.contiguous().data_ptr(), n,
-                                       actions.data_ptr(), logp.data_ptr(), mu.data_ptr(), sigma.data_ptr(), st),
+        _lib.check(self._lib.hb_ppo_act_head(mu16.data_ptr(), 16, ac.std.data_ptr(), eps.contiguous().data_ptr(), n,
+                                             actions.data_ptr(), logp.data_ptr(), mu.data_ptr(), sigma.data_ptr(), st),
                    "hb_ppo_act_head")
         t.actions, t.values, t.actions_log_prob = actions, v16[:, :1].clone(), logp
         t.action_mean, t.action_sigma = mu, sigma
         t.observations, t.critic_observations = obs, critic_obs          # recorded before env.step() (ppo.py:98-100)
         return t.actions
 
-    def _replay_act_graph(self, k, n, ws):
+    def _replay_act_graph(self, k, e, n):
         """Capture (once per rollout slot) and replay: the three hidden-layer GEMMs of each network on two branches,
-        reading the slot's observations in place, and the N(0,1) draw of the sample.  Returns the last hidden
-        activations and the draw."""
-        ac, s = self.actor_critic, self.storage
-        key = (s._observations.data_ptr(), k, n)
-        entry = self._act_graphs.get(key)
+        reading the slot's observations in place, the N(0,1) draw of the sample, and the fused output layers /
+        sample / log-prob / value kernel writing into the slot."""
+        entry = self._act_graphs.get(e.xa_ptr)
         if entry is None:
-            dev = self.device
+            ac, s, dev = self.actor_critic, self.storage, self.device
+            ws = ac.workspace(n)
             if self._act_stage is None or self._act_stage.shape[0] != n:
                 self._act_stage = torch.zeros(n, ac.num_actions, device=dev)
             eps = self._act_stage
@@ -214,15 +237,14 @@ class PPO:
             with torch.cuda.graph(g):
                 main = torch.cuda.current_stream(dev)
                 side.wait_stream(main)
-                h3a = ac._mlp_forward("actor", s._observations[k], ws, hidden_only=True)
+                h3a = ac._mlp_forward("actor", e.xa, ws, hidden_only=True)
                 eps.normal_()
                 with torch.cuda.stream(side):
-                    h3c = ac._mlp_forward("critic", s._privileged_observations[k], ws, hidden_only=True)
+                    h3c = ac._mlp_forward("critic", e.xc, ws, hidden_only=True)
                 main.wait_stream(side)
-            entry = self._act_graphs[key] = (g, h3a, h3c)
-        g, h3a, h3c = entry
-        g.replay()
-        return h3a, h3c, self._act_stage
+                self._launch_act_head(e, h3a, h3c, eps, n, main.cuda_stream)
+            entry = self._act_graphs[e.xa_ptr] = (g, e, ws)       # keeps the slot views and the workspace alive
+        entry[0].replay()
 
     def process_env_step(self, rewards, dones, infos):
         """ppo.py:103-113.  After the fast path of act() only rewards (with the time-out bootstrap) and dones are
@@ -239,9 +261,10 @@ class PPO:
                 if tos.dtype not in (torch.bool, torch.uint8):
                     tos = tos != 0
             st = torch.cuda.current_stream(self.device).cuda_stream
-            _lib.check(self._lib.hb_ppo_record_step(rewards.data_ptr(), dones.data_ptr(), s.values[k].data_ptr(),
+            e = self._slot(k)
+            _lib.check(self._lib.hb_ppo_record_step(rewards.data_ptr(), dones.data_ptr(), e.values_ptr,
                                                     tos.data_ptr() if tos is not None else None, float(self.gamma),
-                                                    rewards.numel(), s.rewards[k].data_ptr(), s.dones[k].data_ptr(), st),
+                                                    rewards.numel(), e.rewards_ptr, e.dones_ptr, st),
                        "hb_ppo_record_step")
             s.step += 1
             self._recorded_slot = None
