@@ -446,10 +446,8 @@ def run_b200(args, rank, world):
     r_, v_ = torch.rand(T_GAE, n, 1, generator=g).to(dev), torch.randn(T_GAE, n, 1, generator=g).to(dev)
     d_, lv_ = (torch.rand(T_GAE, n, 1, generator=g) < 0.005).byte().to(dev), torch.randn(n, 1, generator=g).to(dev)
     ret_, adv_ = torch.empty_like(r_), torch.empty_like(r_)
-    # one GPU: scan + grid barrier + normalisation in one cooperative launch; ranks of a multi-GPU job run the scan and
-    # the normalisation as two kernels around their all-reduce of the statistics (timed here without the all-reduce)
-    k_gae = time_launch(lambda st: gae_compute_returns(r_, v_, d_, lv_, ret_, adv_, 0.994, 0.9,
-                                                       reduce_stats=None if world == 1 else (lambda s_, c_: c_)) and None)
+    gae_stats = torch.zeros(2, dtype=torch.float64, device=dev)
+    k_gae = time_launch(lambda st: gae_compute_returns(r_, v_, d_, lv_, ret_, adv_, 0.994, 0.9, stats=gae_stats) and None)
     ppo = None if args.skip_ppo else bench_ppo(args, dev, n, world, rank, env, phys, phys_frames)
     clocks = sampler.summary()
 
@@ -533,8 +531,7 @@ def run_b200(args, rank, world):
                     "stack_priv_ms": k_priv, "stack_obs_ms": k_obs,
                     "stack_obs_gbs": hist_obs / (k_obs * 1e-3) / 1e9, "pd_ms": k_pd,
                     "pd_gbs": n * 240 / (k_pd * 1e-3) / 1e9, "gae_ms": k_gae,
-                    "gae_bytes_per_sample": 17 if world == 1 else 25,      # the normalise pass stays on chip in the one-launch kernel
-                    "gae_gbs": n * T_GAE * (17 if world == 1 else 25) / (k_gae * 1e-3) / 1e9},
+                    "gae_gbs": n * T_GAE * 25 / (k_gae * 1e-3) / 1e9},
         "gae": {"value": total_envs * T_GAE / (k_gae * 1e-3), "unit": "samples/s", "T": T_GAE},
         "ppo": ppo,
     }

@@ -255,16 +255,6 @@ int hb_gae_normalize(float *advantages, const double *stats, int64_t count, void
 /* Same, when `stats` were summed over `stat_count` samples (all ranks) and this rank holds `count`. */
 int hb_gae_normalize_n(float *advantages, const double *stats, int64_t stat_count, int64_t count, void *stream);
 
-/* The same compute_returns in ONE cooperative launch for a single-GPU caller (no all-reduce between the passes): scan,
- * grid-wide barrier, normalisation; the raw advantages stay in shared memory (17 B per sample instead of 25) and the
- * statistics are summed in a fixed order (bit-reproducible).  `work`: HB_GAE_WORK_DOUBLES doubles of device scratch,
- * no initialisation needed; on return work[0..1] = (sum, sum of squares) of the raw advantages.
- * HB_ERR_UNSUPPORTED if [T,N] does not fit one resident grid (use the two calls above). */
-#define HB_GAE_WORK_DOUBLES 8192
-int hb_gae_returns_normalized(const float *rewards, const float *values, const uint8_t *dones, const float *last_values,
-                              float *returns, float *advantages, double *work, int32_t T, int32_t N, float gamma,
-                              float lam, void *stream);
-
 /* ------------------------------------------------------------------------------------------------
  * PPO update (algo/ppo/ppo.py:119-184, actor_critic.py:36-128, rollout_storage.py:146-182)
  * ---------------------------------------------------------------------------------------------- */

@@ -14,7 +14,6 @@ HB_ABI_VERSION = 2
 HB_MAX_DOF = 16
 HB_MAX_OBS = 48
 HB_NUM_REWARDS = 18
-HB_GAE_WORK_DOUBLES = 8192
 HB_MAX_CONTACT_BODIES = 4
 
 HB_STAGE_STEP = 0x1
@@ -144,7 +143,6 @@ _SIGNATURES = {
     "hb_gae_returns": (C.c_int, [_fp, _fp, _fp, _fp, _fp, _fp, _fp, C.c_int32, C.c_int32, C.c_float, C.c_float, _fp]),
     "hb_gae_normalize": (C.c_int, [_fp, _fp, C.c_int64, _fp]),
     "hb_gae_normalize_n": (C.c_int, [_fp, _fp, C.c_int64, C.c_int64, _fp]),
-    "hb_gae_returns_normalized": (C.c_int, [_fp, _fp, _fp, _fp, _fp, _fp, _fp, C.c_int32, C.c_int32, C.c_float, C.c_float, _fp]),
 }
 
 

@@ -19,16 +19,6 @@ def _pad4(n: int) -> int:
     return (n + 3) // 4 * 4
 
 
-_GAE_WORK = {}
-
-
-def _gae_work(device):
-    w = _GAE_WORK.get(device)
-    if w is None:
-        w = _GAE_WORK[device] = torch.zeros(_lib.HB_GAE_WORK_DOUBLES, dtype=torch.float64, device=device)
-    return w
-
-
 def gae_compute_returns(rewards, values, dones, last_values, returns, advantages, gamma, lam,
                         stats: Optional[torch.Tensor] = None, reduce_stats=None):
     """rollout_storage.py:122-136 on `[T,N,1]` (or `[T,N]`) CUDA tensors, in place into returns/advantages.
@@ -41,19 +31,9 @@ def gae_compute_returns(rewards, values, dones, last_values, returns, advantages
             raise ValueError("gae_compute_returns needs contiguous CUDA tensors")
     if dones.dtype not in (torch.uint8, torch.bool):
         raise TypeError("dones must be uint8/bool")
-    st = torch.cuda.current_stream(rewards.device).cuda_stream
-    if reduce_stats is None and T * N > 1 and (stats is None or stats.numel() >= _lib.HB_GAE_WORK_DOUBLES):
-        # one GPU: scan, grid barrier and normalisation in ONE cooperative launch (stats[0:2] = sum, sum of squares)
-        work = stats if stats is not None else _gae_work(rewards.device)
-        rc = lib.hb_gae_returns_normalized(rewards.data_ptr(), values.data_ptr(), dones.data_ptr(), last_values.data_ptr(),
-                                           returns.data_ptr(), advantages.data_ptr(), work.data_ptr(), T, N,
-                                           float(gamma), float(lam), st)
-        if rc == 0:
-            return returns, advantages
-        if rc != -3:                    # HB_ERR_UNSUPPORTED: [T, N] too large for one resident grid -> two launches
-            _lib.check(rc, "hb_gae_returns_normalized")
     if stats is None:
         stats = torch.empty(2, dtype=torch.float64, device=rewards.device)
+    st = torch.cuda.current_stream(rewards.device).cuda_stream
     _lib.check(lib.hb_gae_returns(rewards.data_ptr(), values.data_ptr(), dones.data_ptr(), last_values.data_ptr(),
                                   returns.data_ptr(), advantages.data_ptr(), stats.data_ptr(), T, N,
                                   float(gamma), float(lam), st), "hb_gae_returns")

@@ -10,11 +10,7 @@
 // shared memory, every warp scans envs of the tile (lane = time step, chunks of 32 steps with a
 // carry for T > 32), results go back through shared memory and are written row by row.
 // Compiled with --fmad=false (same op sequence as the reference within one step).
-#include <cooperative_groups.h>
-
 #include "hb_common.cuh"
-
-namespace cg = cooperative_groups;
 
 namespace {
 
@@ -32,6 +28,7 @@ gae_scan_kernel(const float *__restrict__ rewards, const float *__restrict__ val
     float *sd = sm + (size_t)T * (ENVS + 1);
     float *sv = sd + (size_t)T * (ENVS + 1);
     __shared__ double red[2][WARPS];
+    hb::pdl_trigger();              // the normalise kernel may be scheduled behind this grid's tail (it waits before reading)
     const int env0 = blockIdx.x * ENVS;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int e = env0 + lane;
@@ -125,6 +122,7 @@ gae_scan_kernel(const float *__restrict__ rewards, const float *__restrict__ val
 __global__ void __launch_bounds__(256)
 gae_normalize_kernel(float *__restrict__ adv, const double *__restrict__ stats, long long stat_count,
                      long long count) {
+    hb::pdl_wait();                 // the scan (or the all-reduce of its statistics) is complete
     // mean and unbiased std from (sum, sum of squares), rollout_storage.py:136
     const double n = (double)stat_count;
     const double mean = stats[0] / n;
@@ -143,184 +141,9 @@ gae_normalize_kernel(float *__restrict__ adv, const double *__restrict__ stats, 
     }
 }
 
-// ------------------------------------------------------------------------------------------
-// One launch for the whole of compute_returns on one GPU: the scan above, then a grid-wide barrier (cooperative
-// launch: all CTAs are resident), then the normalisation - the raw advantages never leave shared memory, so
-// the normalise pass of the two-kernel path (read + write of every advantage, one more launch, the memset of the
-// accumulators) disappears: 17 B per sample instead of 25.  Every CTA owns tiles b, b + grid, ... (at most `tpc`);
-// the (sum, sum of squares) partials go through `work` per CTA and are re-summed by every CTA in the same order:
-// no atomics, bit-reproducible statistics.
-// ------------------------------------------------------------------------------------------
-constexpr int FWARPS = 4;      // 128-thread CTAs: 16 per SM, i.e. 2368 resident tiles on 148 SMs
-
-__global__ void __launch_bounds__(FWARPS * 32)
-gae_fused_kernel(const float *__restrict__ rewards, const float *__restrict__ values,
-                 const uint8_t *__restrict__ dones, const float *__restrict__ last_values,
-                 float *__restrict__ returns, float *__restrict__ advantages, double *__restrict__ work, int T, int N,
-                 int tiles, int tpc, float gamma, float lam) {
-    extern __shared__ float sm[];
-    const int plane = T * (ENVS + 1);
-    float *sc = sm, *sv = sm + plane, *sa = sm + 2 * plane;          // sa: [tpc][T][ENVS+1] raw advantages
-    __shared__ double red[2][FWARPS];
-    __shared__ float norm[2];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double s1 = 0.0, s2 = 0.0;
-    for (int j = 0; j < tpc; ++j) {
-        const int tile = blockIdx.x + j * gridDim.x;
-        if (tile >= tiles) break;
-        float *sd = sa + j * plane;
-        const int e = tile * ENVS + lane;
-        const bool ok = e < N;
-        // phase 1: coalesced loads, lane = env; all of a warp's loads are issued before the first shared-memory store
-        constexpr int ITERS = 6;
-        for (int tb = warp; tb < T; tb += FWARPS * ITERS) {
-            float r[ITERS], v[ITERS], vn[ITERS], nnt[ITERS];
-#pragma unroll
-            for (int u = 0; u < ITERS; ++u) {
-                const int t = tb + u * FWARPS;
-                r[u] = v[u] = vn[u] = nnt[u] = 0.f;
-                if (ok && t < T) {
-                    const size_t i = (size_t)t * N + e;
-                    r[u] = rewards[i];
-                    v[u] = values[i];
-                    vn[u] = (t == T - 1) ? last_values[e] : values[i + N];
-                    nnt[u] = 1.0f - (float)dones[i];
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < ITERS; ++u) {
-                const int t = tb + u * FWARPS;
-                if (t < T) {
-                    const float g = nnt[u] * gamma;
-                    sd[t * (ENVS + 1) + lane] = (r[u] + g * vn[u]) - v[u];
-                    sc[t * (ENVS + 1) + lane] = g * lam;
-                    sv[t * (ENVS + 1) + lane] = v[u];
-                }
-            }
-        }
-        __syncthreads();
-        // phase 2: lane = time step, reversed: inclusive scan of the affine maps x -> d + c x
-        for (int el = warp; el < ENVS; el += FWARPS) {
-            float carry = 0.0f;
-            for (int base = 0; base < T; base += 32) {
-                const int k = base + lane, t = T - 1 - k;
-                float C = 0.f, D = 0.f;
-                if (k < T) C = sc[t * (ENVS + 1) + el], D = sd[t * (ENVS + 1) + el];
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const float Cp = __shfl_up_sync(0xffffffffu, C, o);
-                    const float Dp = __shfl_up_sync(0xffffffffu, D, o);
-                    if (lane >= o) {
-                        D = D + C * Dp;
-                        C = C * Cp;
-                    }
-                }
-                const float A = D + C * carry;
-                if (k < T) sd[t * (ENVS + 1) + el] = A;
-                carry = __shfl_sync(0xffffffffu, A, 31);
-            }
-        }
-        __syncthreads();
-        // phase 3a: returns leave now; the raw advantage (returns - values, rollout_storage.py:135) stays in sd
-        for (int t = warp; t < T; t += FWARPS) {
-            if (ok) {
-                const float v = sv[t * (ENVS + 1) + lane];
-                const float ret = sd[t * (ENVS + 1) + lane] + v;
-                const float adv = ret - v;
-                returns[(size_t)t * N + e] = ret;
-                sd[t * (ENVS + 1) + lane] = adv;
-                s1 += (double)adv;
-                s2 += (double)adv * (double)adv;
-            }
-        }
-        __syncthreads();                // sc / sv are reused by the next tile
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-    }
-    if (lane == 0) red[0][warp] = s1, red[1][warp] = s2;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        double a = 0.0, q = 0.0;
-        for (int w = 0; w < FWARPS; ++w) a += red[0][w], q += red[1][w];
-        work[2 + 2 * blockIdx.x] = a;
-        work[3 + 2 * blockIdx.x] = q;
-    }
-    cg::this_grid().sync();
-    // every CTA sums the partials in the same order (warp 0: strided accumulate, then a fixed butterfly)
-    if (warp == 0) {
-        double a = 0.0, q = 0.0;
-        for (int b = lane; b < (int)gridDim.x; b += 32) a += __ldcg(work + 2 + 2 * b), q += __ldcg(work + 3 + 2 * b);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            a += __shfl_xor_sync(0xffffffffu, a, o);
-            q += __shfl_xor_sync(0xffffffffu, q, o);
-        }
-        if (lane == 0) {
-            const double n = (double)T * (double)N;
-            const double mean = a / n;
-            double var = (q - n * mean * mean) / (n - 1.0);      // unbiased, rollout_storage.py:136
-            if (var < 0.0) var = 0.0;
-            norm[0] = (float)mean;
-            norm[1] = (float)sqrt(var) + 1e-8f;
-            if (blockIdx.x == 0) work[0] = a, work[1] = q;
-        }
-    }
-    __syncthreads();
-    const float m = norm[0], denom = norm[1];
-    for (int j = 0; j < tpc; ++j) {
-        const int tile = blockIdx.x + j * gridDim.x;
-        if (tile >= tiles) break;
-        const float *sd = sa + j * plane;
-        const int e = tile * ENVS + lane;
-        if (e < N)
-            for (int t = warp; t < T; t += FWARPS) advantages[(size_t)t * N + e] = (sd[t * (ENVS + 1) + lane] - m) / denom;
-    }
-}
-
 }  // namespace
 
 extern "C" {
-
-int hb_gae_returns_normalized(const float *rewards, const float *values, const uint8_t *dones, const float *last_values,
-                              float *returns, float *advantages, double *work, int32_t T, int32_t N, float gamma,
-                              float lam, void *stream) {
-    HB_REQUIRE(rewards && values && dones && last_values && returns && advantages && work,
-               "hb_gae_returns_normalized: null buffer");
-    HB_REQUIRE(T > 0 && N > 0 && (long long)T * N > 1, "hb_gae_returns_normalized: needs at least two samples");
-    const int tiles = (N + ENVS - 1) / ENVS;
-    const size_t plane = (size_t)T * (ENVS + 1) * sizeof(float);
-    // grid and tiles per CTA: all CTAs must be resident (cooperative launch), the partials must fit `work`
-    int grid = 0, tpc = 1;
-    size_t smem = 0;
-    for (int iter = 0; iter < 8; ++iter) {
-        smem = (2 + (size_t)tpc) * plane;
-        if (smem > 200 * 1024) {
-            hb::set_error("hb_gae_returns_normalized: T=%d, N=%d do not fit one resident grid", T, N);
-            return HB_ERR_UNSUPPORTED;
-        }
-        if (smem > 48 * 1024)
-            HB_CUDA(cudaFuncSetAttribute(gae_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        int per_sm = 0;
-        HB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gae_fused_kernel, FWARPS * 32, smem));
-        HB_REQUIRE(per_sm > 0, "hb_gae_returns_normalized: kernel does not fit an SM");
-        int cap = per_sm * hb::sm_count();
-        if (cap > (HB_GAE_WORK_DOUBLES - 2) / 2) cap = (HB_GAE_WORK_DOUBLES - 2) / 2;
-        grid = tiles < cap ? tiles : cap;
-        const int need = (tiles + grid - 1) / grid;
-        if (need <= tpc) break;
-        tpc = need;
-    }
-    HB_REQUIRE((tiles + grid - 1) / grid <= tpc, "hb_gae_returns_normalized: no resident configuration for T=%d, N=%d", T, N);
-    void *args[] = {&rewards, &values, &dones, &last_values, &returns, &advantages, &work, &T, &N,
-                    const_cast<int *>(&tiles), &tpc, &gamma, &lam};
-    HB_CUDA(cudaLaunchCooperativeKernel((const void *)gae_fused_kernel, dim3(grid), dim3(FWARPS * 32), args, smem,
-                                        (cudaStream_t)stream));
-    HB_CHECK_LAUNCH("gae_fused_kernel");
-    return HB_OK;
-}
 
 int hb_gae_returns(const float *rewards, const float *values, const uint8_t *dones, const float *last_values,
                    float *returns, float *advantages, double *stats, int32_t T, int32_t N, float gamma, float lam,
@@ -342,8 +165,8 @@ int hb_gae_returns(const float *rewards, const float *values, const uint8_t *don
 
 int hb_gae_normalize_n(float *advantages, const double *stats, int64_t stat_count, int64_t count, void *stream) {
     HB_REQUIRE(advantages && stats && stat_count > 1 && count > 0, "hb_gae_normalize: bad arguments");
-    gae_normalize_kernel<<<(int)((count + 1023) / 1024), 256, 0, (cudaStream_t)stream>>>(advantages, stats, stat_count,
-                                                                                       count);
+    HB_CUDA(hb::launch_pdl(true, gae_normalize_kernel, dim3((unsigned)((count + 1023) / 1024)), dim3(256), 0,
+                           (cudaStream_t)stream, advantages, stats, (long long)stat_count, (long long)count));
     HB_CHECK_LAUNCH("gae_normalize_kernel");
     return HB_OK;
 }

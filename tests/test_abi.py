@@ -38,7 +38,6 @@ def test_bad_arguments_return_status_not_crash(lib):
     assert rc == -1 and b"null" in lib.hb_last_error()
     rc = lib.hb_gae_returns(None, None, None, None, None, None, None, 4, 4, 0.99, 0.95, None)
     assert rc == -1
-    assert lib.hb_gae_returns_normalized(None, None, None, None, None, None, None, 4, 4, 0.99, 0.95, None) == -1
     assert lib.hb_set_option(b"no_such_option", 1) == -1
     # every entry point validates before it launches: null structs / pointers come back as HB_ERR_BAD_ARG (-1)
     assert lib.hb_env_prologue_torques(None, None, None, None, None) == -1
