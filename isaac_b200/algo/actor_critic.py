@@ -70,7 +70,10 @@ class ActorCritic:
         self._std_offset = off
         off += 16
         self.flat = torch.zeros(off, device=self.device)
-        self.grad = torch.zeros(off, device=self.device)
+        # the gradient buffer carries 8 spare floats behind the parameters: a data-parallel replica parks its loss
+        # statistics there so that ONE all-reduce per optimizer step covers both (isaac_b200/parallel.py)
+        self._grad_wire = torch.zeros(off + 8, device=self.device)
+        self.grad = self._grad_wire[:off]
         # default nn.Linear initialisation, drawn in the reference's module construction order
         # (actor layers, critic layers, then std: actor_critic.py:54-83) so the same torch seed gives the same net
         for L in self.layers:

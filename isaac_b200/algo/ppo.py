@@ -325,7 +325,7 @@ class PPO:
             ac._mlp_backward("actor", xa, ws)
             ac._mlp_backward("critic", xc, ws)
         if self.grad_allreduce is not None:
-            self.grad_allreduce(ac.grad, self._stats)        # sums over ranks (grads already carry 1/global_mb)
+            self.grad_allreduce(ac.grad, self._stats, ac._grad_wire)     # sums over ranks (grads already carry 1/global_mb)
 
     def optimizer_step(self, adaptive: int):
         """clip_grad_norm_ + Adam.step + zero_grad (ppo.py:171-174) with the adaptive-KL rule of :136-148; the loss

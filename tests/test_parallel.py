@@ -33,6 +33,12 @@ def _worker(rank, world, port, out):
         GradReducer()(flat_grad, loss_stats)
         assert torch.allclose(flat_grad, contrib.mean(0), atol=1e-6)
         assert loss_stats[0] == T * N and loss_stats[2] == 2.0 * world
+        # --- the one-collective form: the statistics ride behind the gradient as fp32 ---
+        wire = torch.zeros(P + 8)
+        wire[:P] = contrib[rows].sum(0) / (T * N)
+        stats2 = torch.tensor([float(len(rows)), 1.0, 2.0, 3.0], dtype=torch.float64)
+        GradReducer()(wire[:P], stats2, wire)
+        assert torch.equal(wire[:P], flat_grad) and torch.equal(stats2, loss_stats)
         out[rank] = True
     finally:
         dist.destroy_process_group()
