@@ -324,6 +324,7 @@ def run_b200(args, rank, world):
     phys = SyntheticPhysics(n, device=dev)
     phys.load_frame(phys_frames[0])
     env = HectorFreeEnvB200(HectorCfg(), sim_device=str(dev), physics=phys, statics=tape.statics,
+                            dense_rows=bool(os.environ.get("HB_DENSE_ROWS")),
                             initial_noise=noise_frames[0])
     env.episode_length_buf.copy_(tape.statics.episode_length0)
     if not args.no_graph:

@@ -44,11 +44,12 @@ inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 
 
 int sm_count();   // cached cudaDevAttrMultiProcessorCount of the current device
 extern int g_use_pdl;   // "pdl" option: programmatic stream serialization of the step's kernels: 1 = all, 0 = none,
-                        // 2 = only the PD-torque launches, -1 (default) = PD launches always, the others for shards of
-                        // at most 8192 envs (the completion flush behind griddepcontrol.wait costs more than the
-                        // overlap gains on the large kernels of bigger shards)
+                        // 2 or -1 (default) = only the PD-torque launches.  On the large kernels (post-physics, frame
+                        // stack) the early-resident dependents and the completion flush behind griddepcontrol.wait
+                        // cost more than the overlap gains at every shard size measured (52.0 vs 60.4 us per step at
+                        // 4096 envs, -13 % at 65 536)
 extern int g_gemm_pdl;  // "gemm_pdl" option: 1 (default) = GEMM launches overlap their set-up with the previous kernel's tail
-inline bool use_pdl(int num_envs) { return g_use_pdl == 1 || (g_use_pdl < 0 && num_envs <= 8192); }
+inline bool use_pdl(int num_envs) { (void)num_envs; return g_use_pdl == 1; }
 inline bool use_pdl_small_kernel(int num_envs) { return g_use_pdl == 2 || g_use_pdl < 0 || use_pdl(num_envs); }
 
 #ifdef __CUDACC__
