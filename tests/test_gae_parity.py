@@ -20,8 +20,17 @@ def run_cuda_gae(lib, dev, rewards, values, dones, last_values, gamma, lam):
     return ret.cpu(), adv.cpu()
 
 
-@pytest.mark.parametrize("T,N", [(24, 64), (60, 257), (1, 33), (24, 4096), (100, 40)])
-def test_gae_matches_oracle(lib, cuda_device, T, N):
+@pytest.fixture
+def gae_kernel(lib, request):
+    """Force one of the two scan kernels (the library picks by shard width: serial-in-time from 8192 envs up)."""
+    lib.hb_set_option(b"gae_serial_min_envs", 1 if request.param == "serial" else 1 << 30)
+    yield request.param
+    lib.hb_set_option(b"gae_serial_min_envs", 8192)
+
+
+@pytest.mark.parametrize("gae_kernel", ["warp-scan", "serial"], indirect=True)
+@pytest.mark.parametrize("T,N", [(24, 64), (60, 257), (1, 33), (24, 4096), (100, 40), (24, 8192 + 5), (7, 9000)])
+def test_gae_matches_oracle(lib, cuda_device, T, N, gae_kernel):
     g = torch.Generator().manual_seed(T * 1000 + N)
     rewards = torch.rand(T, N, 1, generator=g)
     values = torch.randn(T, N, 1, generator=g)
@@ -30,6 +39,8 @@ def test_gae_matches_oracle(lib, cuda_device, T, N):
     want_ret, want_adv = gae_returns(rewards, values, dones, last, 0.994, 0.9)
     ret, adv = run_cuda_gae(lib, cuda_device, rewards, values, dones, last, 0.994, 0.9)
     assert_close("returns", ret.numpy(), want_ret.numpy(), rtol=1e-5, atol=1e-5)
+    if gae_kernel == "serial":      # the reference's own loop and operation order, no FMA contraction: the same bits
+        assert torch.equal(ret, want_ret)
     if T * N > 1:
         assert_close("advantages", adv.numpy(), want_adv.numpy(), rtol=1e-5, atol=1e-5)
 
