@@ -142,6 +142,12 @@ typedef struct hb_env_buffers {
     float *episode_means;           /* [HB_NUM_REWARDS] mean(episode_sums[k][ids]) / max_episode_length_s; on a step
                                        without resets the values of episode_means_prev are carried over */
     const float *episode_means_prev;/* [HB_NUM_REWARDS] or NULL */
+    int32_t *episode_ring;          /* NULL, or device int32[2] = {cursor, size}: episode_means is then the base of a ring
+                                       [size][HB_NUM_REWARDS]; hb_env_reset_finalize / hb_env_stack_finalize write slot
+                                       `cursor`, carry over from slot cursor-1 (episode_means_prev is ignored) and
+                                       advance the cursor - the launch sequence of a step can then be replayed from one
+                                       CUDA graph while every step's extras["episode"] keeps its own storage until the
+                                       runner logs it (on_policy_runner.py:140-154 reads them an iteration later) */
     uint8_t *time_outs_latched;     /* [N] copy of time_out_buf taken only on steps with >=1 reset (extras["time_outs"]) */
     /* scratch: ceil(N/32) ballot words (one per 32-env tile) and HB_NUM_REWARDS fp64 accumulators (zeroed
      * once by the caller; hb_env_reset_finalize re-arms them) */

@@ -67,7 +67,7 @@ _BUFFER_FIELDS = (
     "torques", "commands", "base_lin_vel", "base_ang_vel", "projected_gravity", "base_euler_xyz", "feet_air_time",
     "last_contacts", "feet_height", "last_feet_z", "rand_push_force", "rand_push_torque", "episode_sums",
     "episode_length_buf", "reset_buf", "time_out_buf", "rew_buf", "reset_env_ids", "reset_count", "episode_means",
-    "episode_means_prev", "time_outs_latched", "scratch_ballots", "scratch_sums")
+    "episode_means_prev", "episode_ring", "time_outs_latched", "scratch_ballots", "scratch_sums")
 
 
 class EnvBuffers(C.Structure):

@@ -1096,18 +1096,28 @@ reset_finalize_body(const hb_env_params &p, const hb_env_buffers &b, float *__re
     }
     const int total = prefix + seg_count + after;
     if (blk == 0) {
+        float *means = b.episode_means;
+        const float *means_prev = b.episode_means_prev;
+        int cursor = 0, ring = 0;
+        if (b.episode_ring) {                        // this step's slot of the extras ring, the previous step's behind it
+            cursor = b.episode_ring[0], ring = b.episode_ring[1];
+            means = b.episode_means + (size_t)cursor * HB_NUM_REWARDS;
+            means_prev = b.episode_means + (size_t)((cursor + ring - 1) % ring) * HB_NUM_REWARDS;
+        }
+        __syncthreads();                             // every thread has read the cursor before thread 0 advances it
         if (threadIdx.x == 0) {
             *b.reset_count = total;
             if (host_count) *host_count = total;
             if (rng_counter) *rng_counter += 1ull;       // the next call draws from a fresh counter
+            if (b.episode_ring) b.episode_ring[0] = (cursor + 1) % ring;
         }
         if (threadIdx.x < HB_NUM_REWARDS) {
             const int k = threadIdx.x;
             if (total > 0) {
-                b.episode_means[k] = (float)(b.scratch_sums[k] / (double)total) / p.max_episode_length_s;
+                means[k] = (float)(b.scratch_sums[k] / (double)total) / p.max_episode_length_s;
                 b.scratch_sums[k] = 0.0;             // re-armed for the next step
-            } else if (b.episode_means_prev && b.episode_means_prev != b.episode_means) {
-                b.episode_means[k] = b.episode_means_prev[k];
+            } else if (means_prev && means_prev != means) {
+                means[k] = means_prev[k];
             }
         }
     }

@@ -248,6 +248,9 @@ class HectorFreeEnvB200:
         self._reset_count = torch.zeros(1, dtype=torch.int32, device=dev)
         self._host_count = torch.zeros(1, dtype=torch.int32).pin_memory() if dev.type == "cuda" else torch.zeros(1, dtype=torch.int32)
         self._episode_means = z(_EXTRAS_RING, HB_NUM_REWARDS)
+        # device-side cursor of that ring: the finalize kernel writes slot `cursor` and advances it, so a captured
+        # launch sequence lands in a new slot on every replay; the host mirrors it with _step_index
+        self._episode_ring = torch.tensor([0, _EXTRAS_RING], dtype=torch.int32, device=dev)
         self._time_outs_latched = torch.zeros(N, dtype=torch.bool, device=dev)
         tiles = (N + 31) // 32
         self._scratch_ballots = torch.zeros(tiles, dtype=torch.int32, device=dev)
@@ -266,7 +269,6 @@ class HectorFreeEnvB200:
         self._step_index = 0
         self._pending_event: Optional[torch.cuda.Event] = None
         self._graphs = None
-        self._last_means_slot = None
         self._injected = initial_noise      # draws consumed by the constructor's reset_idx(all)
         self._rng_seed = int(getattr(cfg, "seed", 1)) & 0xFFFFFFFFFFFFFFFF
         self._rng_counter = torch.zeros(1, dtype=torch.int64, device=dev)
@@ -296,7 +298,8 @@ class HectorFreeEnvB200:
                 episode_length_buf=self.episode_length_buf, reset_buf=self.reset_buf, time_out_buf=self.time_out_buf,
                 rew_buf=self.rew_buf, reset_env_ids=self.reset_env_ids, reset_count=self._reset_count,
                 time_outs_latched=self._time_outs_latched, scratch_ballots=self._scratch_ballots,
-                scratch_sums=self._scratch_sums).items():
+                scratch_sums=self._scratch_sums, episode_means=self._episode_means,
+                episode_ring=self._episode_ring).items():
             if not t.is_contiguous():
                 raise ValueError(f"{name} must be contiguous")
             setattr(b, name, t.data_ptr())
@@ -369,12 +372,13 @@ class HectorFreeEnvB200:
         """hector_env.py:158-169 + legged_robot.py:84-108."""
         lib, st = self._lib, self._stream()
         self._st = st
-        if actions.device != self.device or actions.dtype != torch.float32 or not actions.is_contiguous():
+        staged = actions.device != self.device or actions.dtype != torch.float32 or not actions.is_contiguous()
+        if staged:
             actions = actions.to(self.device, dtype=torch.float32).contiguous()
         self.common_step_counter += 1
         push = bool(self.cfg.domain_rand.push_robots) and (self.common_step_counter % self.push_interval == 0)
         if self._graphs is not None and not push and self._injected is None:
-            return self._step_graph(actions)
+            return self._step_graph(actions, staged)
         self._draw_noise(push)
         _lib.check(lib.hb_env_action_prologue(self._pp, self._pb, actions.data_ptr(), self._pn, st),
                    "hb_env_action_prologue")
@@ -405,56 +409,59 @@ class HectorFreeEnvB200:
             raise ValueError("this physics stage needs host calls between sub-steps; CUDA-graph replay is not possible")
         if self.device.type != "cuda":
             raise ValueError("CUDA graphs need a CUDA device")
-        N = self.num_envs
-        self._g_actions = torch.zeros(N, self.num_actions, device=self.device)
-        self._g_means = torch.zeros(2, HB_NUM_REWARDS, device=self.device)
-        self._g_par = 0                       # which half of _g_means holds the previous step's episode means
+        self._g_actions = torch.zeros(self.num_envs, self.num_actions, device=self.device)   # staging for odd inputs
         self._apply_pending_resets()
         torch.cuda.synchronize(self.device)
         self._g_nz = EnvNoise()
         self._bind_device_rng(self._g_nz)
-        ga = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(ga):
-            _lib.check(self._lib.hb_env_prologue_torques(self._pp, self._pb, self._g_actions.data_ptr(),
-                                                         C.byref(self._g_nz), self._stream()), "hb_env_prologue_torques")
-        self._graph_a, self._graph_pool = ga, ga.pool()
-        self._graphs = {}
+        self._graph_pool = None
+        self._graphs_a, self._graphs = {}, {}
+        self._graph_a(self._g_actions)
         self.graph_launches_per_step = self.cfg.control.decimation + 2     # this library's kernels per replayed step (prologue+PD, PD x9, post, stack+finalize)
 
-    def _graph_b(self, prev, out, par):
-        key = (prev[2], out[2], par)
+    def _graph_a(self, actions):
+        """Graph A reads the actions where the caller left them (one graph per address: the rollout storage's
+        action slots, a policy's output buffer): no staging copy in front of the step."""
+        key = actions.data_ptr()
+        g = self._graphs_a.get(key)
+        if g is None:
+            if len(self._graphs_a) >= 256:
+                self._graphs_a.clear()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, pool=self._graph_pool):
+                _lib.check(self._lib.hb_env_prologue_torques(self._pp, self._pb, key, C.byref(self._g_nz), self._stream()),
+                           "hb_env_prologue_torques")
+            self._graph_pool = self._graph_pool or g.pool()
+            self._graphs_a[key] = g
+        return g
+
+    def _graph_b(self, prev, out):
+        key = (prev[2], out[2])
         entry = self._graphs.get(key)
         if entry is None:
             if len(self._graphs) >= 256:      # buffers keep changing (new storage): drop the stale graphs
                 self._graphs.clear()
-            saved = (self._b.episode_means, self._b.episode_means_prev)
             gb = torch.cuda.CUDAGraph()
             with torch.cuda.graph(gb, pool=self._graph_pool):
                 st = self._stream()
                 for _ in range(self.cfg.control.decimation - 1):
                     _lib.check(self._lib.hb_env_compute_torques(self._pp, self._pb, st), "hb_env_compute_torques")
-                self._b.episode_means = self._g_means[par ^ 1].data_ptr()
-                self._b.episode_means_prev = self._g_means[par].data_ptr()
                 self._launch_post_kernels(HB_STAGE_STEP, C.byref(self._g_nz), prev, out, True, st)
-            self._b.episode_means, self._b.episode_means_prev = saved
             entry = self._graphs[key] = (gb, prev, out)      # the graph keeps its buffers alive
         return entry[0]
 
-    def _step_graph(self, actions):
-        self._g_actions.copy_(actions, non_blocking=True)
+    def _step_graph(self, actions, staged=False):
+        if actions.shape != self._g_actions.shape:
+            raise ValueError(f"actions must be [{self.num_envs}, {self.num_actions}]")
+        if staged:          # a converted temporary: its address is not worth a graph of its own
+            self._g_actions.copy_(actions, non_blocking=True)
+            actions = self._g_actions
         slot = self._step_index % _EXTRAS_RING
-        par = self._g_par
-        if self._step_index > 0 and self._last_means_slot is not None:
-            # the previous step ran eagerly: hand its episode means to the graph's carry-over slot
-            self._g_means[par].copy_(self._episode_means[self._last_means_slot], non_blocking=True)
-        self._graph_a.replay()
+        self._graph_a(actions).replay()
         self._apply_pending_resets()          # gym.set_*_indexed of the previous step's resets
         out = self._take_output()
-        self._graph_b(self._cur_buf, out, par).replay()
+        self._graph_b(self._cur_buf, out).replay()
         self._cur_buf = out
-        self._g_par = par ^ 1
-        self._episode_means[slot].copy_(self._g_means[par ^ 1], non_blocking=True)
-        self._last_means_slot = None
         self._pending_event = self._events[self._step_index & 1]
         self._pending_event.record(torch.cuda.current_stream(self.device))
         self.extras["episode"] = self._extras_episode[slot]
@@ -482,11 +489,7 @@ class HectorFreeEnvB200:
         emit = bool(stages & (HB_STAGE_STEP | HB_STAGE_OBS))
         prev = self._cur_buf
         out = self._take_output() if emit else self._own[1 if prev is self._own[0] else 0]
-        slot = self._step_index % _EXTRAS_RING
-        prev_slot = (self._step_index - 1) % _EXTRAS_RING
-        means0 = self._episode_means.data_ptr()
-        self._b.episode_means = means0 + slot * HB_NUM_REWARDS * 4
-        self._b.episode_means_prev = means0 + prev_slot * HB_NUM_REWARDS * 4 if self._step_index > 0 else None
+        slot = self._step_index % _EXTRAS_RING          # = the ring cursor on the device: every finalize launch advances both
         self._launch_post_kernels(stages, self._pn, prev, out, emit, st)
         if emit:
             self._cur_buf = out
@@ -496,7 +499,6 @@ class HectorFreeEnvB200:
         self.extras["episode"] = self._extras_episode[slot]
         if self.cfg.env.send_timeouts:
             self.extras["time_outs"] = self._time_outs_latched
-        self._last_means_slot = slot
         self._step_index += 1
         self._injected = None
         self._nz.u_reset = self._nz.rng_counter = None

@@ -1,5 +1,5 @@
 """Where a replayed step spends its time: events around graph A (prologue + first PD) and graph B (the rest), with the
-bench.py protocol (L2 flushed between steps).  Works on any tree that keeps the step graphs in env._graphs."""
+bench.py protocol (L2 flushed between steps)."""
 import os
 import sys
 
@@ -44,11 +44,8 @@ def main():
         env.step(acts[i % 4])
     torch.cuda.synchronize()
     log = []
-    if hasattr(env, "_graph_a"):
-        env._graph_a = Probe(env._graph_a, log, "A", stream)
-        env._graphs = {k: (Probe(v[0], log, "B", stream),) + tuple(v[1:]) for k, v in env._graphs.items()}
-    else:
-        env._graphs = {k: (Probe(v[0], log, "A", stream), Probe(v[1], log, "B", stream)) + tuple(v[2:]) for k, v in env._graphs.items()}
+    env._graphs_a = {k: Probe(g, log, "A", stream) for k, g in env._graphs_a.items()}
+    env._graphs = {k: (Probe(v[0], log, "B", stream),) + tuple(v[1:]) for k, v in env._graphs.items()}
     steps = []
     for i in range(60):
         phys.load_frame(frames[i % 4])

@@ -321,7 +321,7 @@ def test_fused_shift_finalize_equals_separate_calls(lib, cuda_device, n, pitched
         new_o.fill_(7.0), new_p.fill_(7.0)
         assert new_o.data_ptr() % 16 == 0 and new_p.data_ptr() % 16 == 0
         means = torch.zeros(18, device=dev)
-        env._b.episode_means, env._b.episode_means_prev = means.data_ptr(), None
+        env._b.episode_means, env._b.episode_means_prev, env._b.episode_ring = means.data_ptr(), None, None
         P, B, hc = env._pp, env._pb, env._host_count.data_ptr()
         if fused:
             _lib.check(lib.hb_env_stack_finalize(P, B, prev_o.data_ptr(), prev_p.data_ptr(), new_o.data_ptr(), new_p.data_ptr(),
