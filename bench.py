@@ -378,17 +378,17 @@ def run_b200(args, rank, world):
     def time_launch(fn, reps=10):
         """One launch, replayed from a single-node CUDA graph so that the host-side launch path (ctypes,
         argument marshalling) stays out of the event interval; L2 flushed before every replay."""
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            rc = fn(torch.cuda.current_stream(dev).cuda_stream)
-        if rc not in (0, None):
-            _lib.check(rc, "time_launch")
+        def body(st_):
+            rc = fn(st_)
+            if rc not in (0, None):
+                _lib.check(rc, "time_launch")
+        g = _lib.LaunchGraph(dev).record(body)
         tot = 0.0
         for r in range(reps + 2):
             flush_l2(r)
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record(stream)
-            g.replay()
+            g.replay(stream.cuda_stream)
             b.record(stream)
             b.synchronize()
             if r >= 2:
@@ -398,17 +398,16 @@ def run_b200(args, rank, world):
     def time_chain(fns, reps=10):
         """Average duration of len(fns) back-to-back launches replayed from one CUDA graph, each launch on its own
         (cold) buffers: the graph-launch latency in front of the first kernel is amortised over the chain."""
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            st_ = torch.cuda.current_stream(dev).cuda_stream
+        def body(st_):
             for fn in fns:
                 _lib.check(fn(st_), "time_chain")
+        g = _lib.LaunchGraph(dev).record(body)
         tot = 0.0
         for r in range(reps + 2):
             flush_l2(r)
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record(stream)
-            g.replay()
+            g.replay(stream.cuda_stream)
             b.record(stream)
             b.synchronize()
             if r >= 2:

@@ -185,12 +185,21 @@ int64_t hb_launch_count(void);
 void hb_launch_count_reset(void);
 /* Tuning switches: "env_bulk_staging" 1 = 1-D bulk async copies (default), 0 = vector loads;
  * "pdl" = programmatic stream serialization of the step's launches (each kernel's launch and prologue overlap the
- * tail of its predecessor; griddepcontrol.wait guards the dependent data): 1 = all kernels, 0 = none, 2 = only the
- * PD-torque launches, -1 (default) = PD launches always, the other kernels for shards of <= 8192 envs (measured:
- * all kernels +4 % at 4096 envs but -13 % at 65536 envs; PD launches only +5.6 % at 16384, +2 % at 65536). */
+ * tail of its predecessor; griddepcontrol.wait guards the dependent data): 1 = all kernels, 0 = none, 2 or -1
+ * (default) = only the PD-torque launches (measured on one box, 4096 envs: 52.0 us per step with the default, 52.7
+ * with none, 60.4 with all; PD launches only: +5.6 % at 16384 envs, +2 % at 65536; all kernels: -13 % at 65536);
+ * "gae_serial_min_envs" (default 8192): shards at least this wide run GAE one thread per env. */
 /* "gemm_pdl" 1 (default) / 0: hb_gemm_tf32 launches with programmatic stream serialization (a GEMM's set-up - tensor-map
  * prefetch, barriers, TMEM allocation, cluster rendezvous - overlaps the previous kernel's last tiles). */
 int hb_set_option(const char *name, int value);
+
+/* CUDA graphs of hb_* launch sequences (one env step, one PPO.act) without the framework's graph object:
+ * begin capture on `stream` (not the legacy default stream), issue hb_* calls on it, end -> an executable graph;
+ * launch it on any stream.  Only hb_* calls may be captured (nothing that allocates). */
+int hb_graph_begin(void *stream);
+int hb_graph_end(void *stream, void **graph_exec);
+int hb_graph_launch(void *graph_exec, void *stream);
+int hb_graph_destroy(void *graph_exec);
 
 /* HectorFreeEnv.step prologue: clip, action delay, action noise, clip
  * (envs/custom/hector_env.py:158-169 + envs/base/legged_robot.py:90-91).

@@ -117,6 +117,10 @@ _SIGNATURES = {
     "hb_sizeof_env_buffers": (C.c_int, []),
     "hb_sizeof_env_noise": (C.c_int, []),
     "hb_check_device": (C.c_int, []),
+    "hb_graph_begin": (C.c_int, [_fp]),
+    "hb_graph_end": (C.c_int, [_fp, C.POINTER(C.c_void_p)]),
+    "hb_graph_launch": (C.c_int, [_fp, _fp]),
+    "hb_graph_destroy": (C.c_int, [_fp]),
     "hb_env_action_prologue": (C.c_int, [C.POINTER(EnvParams), C.POINTER(EnvBuffers), _fp, C.POINTER(EnvNoise), _fp]),
     "hb_env_prologue_torques": (C.c_int, [C.POINTER(EnvParams), C.POINTER(EnvBuffers), _fp, C.POINTER(EnvNoise), _fp]),
     "hb_env_compute_torques": (C.c_int, [C.POINTER(EnvParams), C.POINTER(EnvBuffers), _fp]),
@@ -174,6 +178,49 @@ def check(rc: int, what: str) -> None:
     if rc != 0:
         msg = _LIB.hb_last_error().decode() if _LIB is not None else ""
         raise HectorB200Error(f"{what} failed (status {rc}): {msg}")
+
+
+class LaunchGraph:
+    """A replayable sequence of hb_* launches (hb_graph_begin / end / launch): what `torch.cuda.CUDAGraph` does for
+    this library's kernels, without its allocator / generator bookkeeping around capture and replay.  `record(fn)` runs
+    `fn(stream_handle)` under capture on a private stream; only hb_* calls (no torch ops) may be issued inside."""
+
+    _capture_stream = {}
+
+    def __init__(self, device):
+        import torch
+        self._lib = load()
+        self._device = torch.device(device)
+        self._exec = C.c_void_p()
+        s = LaunchGraph._capture_stream.get(self._device)
+        if s is None:
+            s = LaunchGraph._capture_stream[self._device] = torch.cuda.Stream(self._device)
+        self._stream = s
+
+    def record(self, fn) -> "LaunchGraph":
+        import torch
+        torch.cuda.synchronize(self._device)
+        handle = self._stream.cuda_stream
+        with torch.cuda.stream(self._stream):       # code that asks torch for the current stream lands on the capture stream
+            check(self._lib.hb_graph_begin(handle), "hb_graph_begin")
+            try:
+                fn(handle)
+            finally:
+                rc = self._lib.hb_graph_end(handle, C.byref(self._exec))
+        check(rc, "hb_graph_end")
+        return self
+
+    def replay(self, stream_handle) -> None:
+        rc = self._lib.hb_graph_launch(self._exec, stream_handle)
+        if rc:
+            check(rc, "hb_graph_launch")
+
+    def __del__(self):
+        try:
+            if self._exec:
+                self._lib.hb_graph_destroy(self._exec)
+        except Exception:
+            pass
 
 
 def exported_symbols():

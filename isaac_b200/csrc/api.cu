@@ -63,4 +63,42 @@ int hb_check_device(void) {
     return HB_OK;
 }
 
+// ---- CUDA graphs of this library's launches ------------------------------------------------------------------
+// A host that replays a fixed sequence of hb_* calls (one env step) can capture it here instead of through its
+// framework's graph object: no allocator / generator bookkeeping around capture and replay (torch.cuda.graph
+// synchronises, collects garbage and empties its cache on every capture - the step graphs are captured lazily, one per
+// pair of observation buffers).  The capture must contain hb_* calls only (nothing that allocates); `stream` must not
+// be the legacy default stream.
+int hb_graph_begin(void *stream) {
+    HB_REQUIRE(stream != nullptr, "hb_graph_begin: capture needs a non-default stream");
+    HB_CUDA(cudaStreamBeginCapture((cudaStream_t)stream, cudaStreamCaptureModeThreadLocal));
+    return HB_OK;
+}
+
+int hb_graph_end(void *stream, void **graph_exec) {
+    HB_REQUIRE(stream != nullptr && graph_exec != nullptr, "hb_graph_end: null argument");
+    cudaGraph_t graph = nullptr;
+    HB_CUDA(cudaStreamEndCapture((cudaStream_t)stream, &graph));
+    cudaGraphExec_t exec = nullptr;
+    cudaError_t e = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) {
+        hb::set_error("cudaGraphInstantiate: %s", cudaGetErrorString(e));
+        return HB_ERR_CUDA;
+    }
+    *graph_exec = exec;
+    return HB_OK;
+}
+
+int hb_graph_launch(void *graph_exec, void *stream) {
+    HB_REQUIRE(graph_exec != nullptr, "hb_graph_launch: null graph");
+    HB_CUDA(cudaGraphLaunch((cudaGraphExec_t)graph_exec, (cudaStream_t)stream));
+    return HB_OK;
+}
+
+int hb_graph_destroy(void *graph_exec) {
+    if (graph_exec) HB_CUDA(cudaGraphExecDestroy((cudaGraphExec_t)graph_exec));
+    return HB_OK;
+}
+
 }  // extern "C"

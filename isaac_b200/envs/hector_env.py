@@ -414,7 +414,6 @@ class HectorFreeEnvB200:
         torch.cuda.synchronize(self.device)
         self._g_nz = EnvNoise()
         self._bind_device_rng(self._g_nz)
-        self._graph_pool = None
         self._graphs_a, self._graphs = {}, {}
         self._graph_a(self._g_actions)
         self.graph_launches_per_step = self.cfg.control.decimation + 2     # this library's kernels per replayed step (prologue+PD, PD x9, post, stack+finalize)
@@ -427,12 +426,8 @@ class HectorFreeEnvB200:
         if g is None:
             if len(self._graphs_a) >= 256:
                 self._graphs_a.clear()
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, pool=self._graph_pool):
-                _lib.check(self._lib.hb_env_prologue_torques(self._pp, self._pb, key, C.byref(self._g_nz), self._stream()),
-                           "hb_env_prologue_torques")
-            self._graph_pool = self._graph_pool or g.pool()
-            self._graphs_a[key] = g
+            g = self._graphs_a[key] = _lib.LaunchGraph(self.device).record(lambda st: _lib.check(
+                self._lib.hb_env_prologue_torques(self._pp, self._pb, key, C.byref(self._g_nz), st), "hb_env_prologue_torques"))
         return g
 
     def _graph_b(self, prev, out):
@@ -441,12 +436,11 @@ class HectorFreeEnvB200:
         if entry is None:
             if len(self._graphs) >= 256:      # buffers keep changing (new storage): drop the stale graphs
                 self._graphs.clear()
-            gb = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(gb, pool=self._graph_pool):
-                st = self._stream()
+            def launches(st):
                 for _ in range(self.cfg.control.decimation - 1):
                     _lib.check(self._lib.hb_env_compute_torques(self._pp, self._pb, st), "hb_env_compute_torques")
                 self._launch_post_kernels(HB_STAGE_STEP, C.byref(self._g_nz), prev, out, True, st)
+            gb = _lib.LaunchGraph(self.device).record(launches)
             entry = self._graphs[key] = (gb, prev, out)      # the graph keeps its buffers alive
         return entry[0]
 
@@ -457,10 +451,11 @@ class HectorFreeEnvB200:
             self._g_actions.copy_(actions, non_blocking=True)
             actions = self._g_actions
         slot = self._step_index % _EXTRAS_RING
-        self._graph_a(actions).replay()
+        st = self._st
+        self._graph_a(actions).replay(st)
         self._apply_pending_resets()          # gym.set_*_indexed of the previous step's resets
         out = self._take_output()
-        self._graph_b(self._cur_buf, out).replay()
+        self._graph_b(self._cur_buf, out).replay(st)
         self._cur_buf = out
         self._pending_event = self._events[self._step_index & 1]
         self._pending_event.record(torch.cuda.current_stream(self.device))

@@ -16,10 +16,10 @@ class Probe:
     def __init__(self, graph, log, tag, stream):
         self.graph, self.log, self.tag, self.stream = graph, log, tag, stream
 
-    def replay(self):
+    def replay(self, st):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(self.stream)
-        self.graph.replay()
+        self.graph.replay(st)
         b.record(self.stream)
         self.log.append((self.tag, a, b))
 
