@@ -331,6 +331,7 @@ def run_b200(args, rank, world):
         for i in range(3):          # eager warm-up (lazy module load, cudaFuncSetAttribute) before capture
             env.step(noise_frames[0].actions)
         env.enable_cuda_graph()
+        env.prepare_action_buffers(*[f.actions for f in noise_frames])      # no graph capture inside a timed step
     flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)     # > 126 MB L2
     flush_sink = torch.zeros(1, device=dev)
     stream = torch.cuda.current_stream(dev)

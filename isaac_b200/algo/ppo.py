@@ -135,6 +135,10 @@ class PPO:
         if env is not None and not hasattr(env, "set_next_observation_buffers"):
             raise TypeError("attach_env needs an env with set_next_observation_buffers()")
         self._env = env
+        s = self.storage
+        if env is not None and s is not None and getattr(env, "_graphs", None) is not None and env.num_envs == s.num_envs:
+            # act() returns the storage's action slots: their step graphs are captured now, not inside the first rollout
+            env.prepare_action_buffers(*[s.actions[k] for k in range(s.num_transitions_per_env)])
 
     def _slot(self, k):
         """Views and addresses of rollout slot k, built once per storage (tensor indexing costs microseconds)."""

@@ -416,7 +416,19 @@ class HectorFreeEnvB200:
         self._bind_device_rng(self._g_nz)
         self._graphs_a, self._graphs = {}, {}
         self._graph_a(self._g_actions)
+        self._graph_b(self._own[0], self._own[1]), self._graph_b(self._own[1], self._own[0])
         self.graph_launches_per_step = self.cfg.control.decimation + 2     # this library's kernels per replayed step (prologue+PD, PD x9, post, stack+finalize)
+
+    def prepare_action_buffers(self, *tensors) -> None:
+        """Capture the step's first graph for each of these action tensors now ([N, num_actions] fp32, contiguous, on
+        the device) instead of at their first step() - e.g. the rollout storage's action slots."""
+        if self._graphs is None:
+            raise ValueError("enable_cuda_graph() first")
+        for t in tensors:
+            if (t.device != self.device or t.dtype != torch.float32 or not t.is_contiguous()
+                    or t.shape != self._g_actions.shape):
+                raise ValueError(f"action buffers must be contiguous [{self.num_envs}, {self.num_actions}] fp32 tensors on {self.device}")
+            self._graph_a(t)
 
     def _graph_a(self, actions):
         """Graph A reads the actions where the caller left them (one graph per address: the rollout storage's
