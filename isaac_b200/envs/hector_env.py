@@ -20,6 +20,10 @@ The per-step work is four kinds of kernel launch through the C ABI (include/hect
                                      count, episode means, time_outs) - the fused form of
                                      hb_env_stack_observations + hb_env_reset_finalize
 
+Observation tensors are `[N, 615]` / `[N, 1050]` views of rows at a 16-byte pitch (616 / 1052 floats); the caller may
+supply the buffers of the next step (`set_next_observation_buffers`, what `PPO.attach_env` does with the rollout slots).
+`enable_cuda_graph()` replays the step from two graphs of these launches (hb_graph_*), with no staging copy around them.
+
 There is no torch/eager fallback: without libhectorb200.so construction fails.
 `step()` never blocks on the GPU; the one host-visible value the reference needs (the reset
 count for `gym.set_*_tensor_indexed`) is written to pinned memory by the kernel and consumed
