@@ -130,3 +130,18 @@ class RolloutStorage:
         done_indices = torch.cat((flat_dones.new_tensor([-1], dtype=torch.int64), flat_dones.nonzero(as_tuple=False)[:, 0]))
         trajectory_lengths = done_indices[1:] - done_indices[:-1]
         return trajectory_lengths.float().mean(), self.rewards.mean()
+
+    def mini_batch_generator(self, num_mini_batches, num_epochs=8):
+        """rollout_storage.py:146-182, for code that walks the storage itself (PPO.update() does not: it gathers the
+        minibatches once per update with hb_ppo_gather_rows / hb_ppo_pack_samples and feeds the GEMMs from there).
+        Same contract: ONE permutation of the first num_mini_batches * (T*N // num_mini_batches) samples, reused by
+        every epoch; yields (obs, critic_obs, actions, target_values, advantages, returns, old_log_prob, old_mu,
+        old_sigma, (None, None), None) per minibatch."""
+        per_batch = self.num_envs * self.num_transitions_per_env // num_mini_batches
+        order = torch.randperm(num_mini_batches * per_batch, device=self.device)
+        critic_src = self.privileged_observations if self.privileged_observations is not None else self.observations
+        fields = [t.flatten(0, 1) for t in (self.observations, critic_src, self.actions, self.values, self.advantages,
+                                            self.returns, self.actions_log_prob, self.mu, self.sigma)]
+        for _ in range(num_epochs):
+            for chunk in order.split(per_batch):
+                yield (*(f[chunk] for f in fields), (None, None), None)
