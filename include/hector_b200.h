@@ -346,6 +346,11 @@ int hb_ppo_head_fused(const float *h3_actor, int32_t ld_ha, const float *h3_crit
                       int64_t mb_global, const hb_ppo_loss_params *lp, float *dz3_actor, float *dz3_critic, int32_t ld_dz,
                       float *g4_actor, float *g4_critic, float *d_std, double *stats, void *stream);
 
+/* N(0,1) draws for the action sample (algo/ppo/ppo.py:93 -> actor_critic.py:116 `distribution.sample()`): count floats
+ * from the library's Philox4x32-10 generator keyed by `seed`; state = device uint64[2] {call counter, 0}, advanced by the
+ * launch itself, so the call can sit in a replayed CUDA graph and still draw fresh numbers every replay. */
+int hb_ppo_draw_normal(float *out, int64_t count, uint64_t seed, uint64_t *state, void *stream);
+
 /* PPO.act head (ppo.py:91-101, actor_critic.py:111-120): a = mu + sigma*eps, log-prob, copies of mu/sigma. */
 int hb_ppo_act_head(const float *mu, int32_t ld_mu, const float *std, const float *eps, int64_t n, float *actions,
                     float *log_prob, float *mu_out, float *sigma_out, void *stream);

@@ -141,6 +141,7 @@ _SIGNATURES = {
     "hb_ppo_act_fused": (C.c_int, [_fp, C.c_int32, _fp, C.c_int32, _fp, _fp, C.c_int32, _fp, _fp, C.c_int64, _fp, _fp, _fp, _fp,
                                    _fp, _fp]),
     "hb_ppo_record_step": (C.c_int, [_fp, _fp, _fp, _fp, C.c_float, C.c_int64, _fp, _fp, _fp]),
+    "hb_ppo_draw_normal": (C.c_int, [_fp, C.c_int64, C.c_uint64, _fp, _fp]),
     "hb_ppo_act_head": (C.c_int, [_fp, C.c_int32, _fp, _fp, C.c_int64, _fp, _fp, _fp, _fp, _fp]),
     "hb_grad_sumsq": (C.c_int, [_fp, C.c_int64, _fp, _fp]),
     "hb_adam_step": (C.c_int, [_fp, _fp, _fp, _fp, C.c_int64, C.POINTER(AdamParams), _fp, _fp, _fp, _fp, _fp]),

@@ -99,6 +99,10 @@ class PPO:
         self.graph_rollout = True           # PPO.act: replay the hidden-layer GEMMs from a CUDA graph for small shards
         self.graph_rollout_max_envs = 16384
         self._act_graphs, self._act_stage = {}, None
+        # the action sample's N(0,1) draws come from the library's Philox generator (hb_ppo_draw_normal): key = seed,
+        # counter on the device, so the draw can sit inside the replayed act graph
+        self._eps_seed = 0x9E3779B97F4A7C15
+        self._eps_state = torch.zeros(2, dtype=torch.int64, device=self.device) if self.device.type == "cuda" else None
 
     # ------------------------------------------------------------------ learning rate (device-resident)
     @property
@@ -139,6 +143,20 @@ class PPO:
         if env is not None and s is not None and getattr(env, "_graphs", None) is not None and env.num_envs == s.num_envs:
             # act() returns the storage's action slots: their step graphs are captured now, not inside the first rollout
             env.prepare_action_buffers(*[s.actions[k] for k in range(s.num_transitions_per_env)])
+
+    def seed(self, seed: int) -> None:
+        """Seed of the action-sample generator (the reference seeds torch globally, helpers.py:95-106)."""
+        self._eps_seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+        self._eps_state.zero_()
+
+    def _draw_eps(self, n, st):
+        """[n, num_actions] N(0,1) draws into the staging buffer (the eps of Normal.sample(), actor_critic.py:116)."""
+        na = self.actor_critic.num_actions
+        if self._act_stage is None or self._act_stage.shape[0] != n:
+            self._act_stage = torch.zeros(n, na, device=self.device)
+        _lib.check(self._lib.hb_ppo_draw_normal(self._act_stage.data_ptr(), n * na, self._eps_seed,
+                                                self._eps_state.data_ptr(), st), "hb_ppo_draw_normal")
+        return self._act_stage
 
     def _slot(self, k):
         """Views and addresses of rollout slot k, built once per storage (tensor indexing costs microseconds)."""
@@ -189,10 +207,11 @@ class PPO:
                 self._replay_act_graph(k, e, n)
             else:
                 ws = ac.workspace(n)
-                eps = self.injected_eps if self.injected_eps is not None else torch.randn(n, ac.num_actions, device=self.device)
+                st = torch.cuda.current_stream(self.device).cuda_stream
+                eps = self.injected_eps.contiguous() if self.injected_eps is not None else self._draw_eps(n, st)
                 h3a = ac._mlp_forward("actor", e.xa, ws, hidden_only=True)
                 h3c = ac._mlp_forward("critic", e.xc, ws, hidden_only=True)
-                self._launch_act_head(e, h3a, h3c, eps.contiguous(), n, torch.cuda.current_stream(self.device).cuda_stream)
+                self._launch_act_head(e, h3a, h3c, eps, n, st)
                 self.injected_eps = None
             t.actions, t.values, t.actions_log_prob = e.actions, e.values, e.logp
             t.action_mean, t.action_sigma = e.mu, e.sigma
@@ -206,7 +225,7 @@ class PPO:
             return t.actions
         st = torch.cuda.current_stream(self.device).cuda_stream
         ws = ac.workspace(n)
-        eps = self.injected_eps if self.injected_eps is not None else torch.randn(n, ac.num_actions, device=self.device)
+        eps = self.injected_eps if self.injected_eps is not None else self._draw_eps(n, st)
         self.injected_eps = None
         self._recorded_slot = None
         mu16 = ac._mlp_forward("actor", ac._as_operand(obs, ac.num_actor_obs), ws)
@@ -223,32 +242,31 @@ class PPO:
         return t.actions
 
     def _replay_act_graph(self, k, e, n):
-        """Capture (once per rollout slot) and replay: the three hidden-layer GEMMs of each network on two branches,
-        reading the slot's observations in place, the N(0,1) draw of the sample, and the fused output layers /
-        sample / log-prob / value kernel writing into the slot."""
+        """Capture (once per rollout slot, hb_graph_*) and replay: the three hidden-layer GEMMs of each network on two
+        branches, reading the slot's observations in place, the N(0,1) draw of the sample, and the fused output
+        layers / sample / log-prob / value kernel writing into the slot - library launches only."""
         entry = self._act_graphs.get(e.xa_ptr)
         if entry is None:
             ac, s, dev = self.actor_critic, self.storage, self.device
             ws = ac.workspace(n)
-            if self._act_stage is None or self._act_stage.shape[0] != n:
-                self._act_stage = torch.zeros(n, ac.num_actions, device=dev)
-            eps = self._act_stage
             if len(self._act_graphs) >= 4 * (s.num_transitions_per_env + 1):     # new storage: drop the stale graphs
                 self._act_graphs.clear()
-            torch.cuda.synchronize(dev)
-            g = torch.cuda.CUDAGraph()
             side = self._side_stream
-            with torch.cuda.graph(g):
-                main = torch.cuda.current_stream(dev)
+
+            def launches(st):
+                main = torch.cuda.current_stream(dev)       # the capture stream
                 side.wait_stream(main)
                 h3a = ac._mlp_forward("actor", e.xa, ws, hidden_only=True)
-                eps.normal_()
+                eps = self._draw_eps(n, st)
                 with torch.cuda.stream(side):
                     h3c = ac._mlp_forward("critic", e.xc, ws, hidden_only=True)
                 main.wait_stream(side)
-                self._launch_act_head(e, h3a, h3c, eps, n, main.cuda_stream)
+                self._launch_act_head(e, h3a, h3c, eps, n, st)
+
+            self._draw_eps(n, torch.cuda.current_stream(dev).cuda_stream)        # allocates the staging buffer before capture
+            g = _lib.LaunchGraph(dev).record(launches)
             entry = self._act_graphs[e.xa_ptr] = (g, e, ws)       # keeps the slot views and the workspace alive
-        entry[0].replay()
+        entry[0].replay(torch.cuda.current_stream(self.device).cuda_stream)
 
     def process_env_step(self, rewards, dones, infos):
         """ppo.py:103-113.  After the fast path of act() only rewards (with the time-out bootstrap) and dones are

@@ -86,16 +86,7 @@ __device__ __forceinline__ Rng make_rng(const hb_env_noise &nz) {
 }
 constexpr int SLOT_Z_ACTION = 0, SLOT_Z_OBS = 3, SLOT_U_RESET = 14, SLOT_U_CMD = 18, SLOT_U_PUSH = 19, SLOT_U_DELAY = 21;
 
-__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
-#pragma unroll
-    for (int r = 0; r < 10; ++r) {
-        const uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
-        const uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
-        c0 = h1 ^ c1 ^ k0, c1 = l1, c2 = h0 ^ c3 ^ k1, c3 = l0;
-        k0 += 0x9E3779B9u, k1 += 0xBB67AE85u;
-    }
-    return make_uint4(c0, c1, c2, c3);
-}
+using hb::philox4x32_10;
 __device__ __forceinline__ void rng_uniform4(const Rng &g, int env, int slot, float u[4]) {      // [0, 1)
     const uint4 x = philox4x32_10((uint32_t)env, (uint32_t)slot, g.s0, g.s1, g.k0, g.k1);
     u[0] = (float)(x.x >> 8) * 5.9604644775390625e-8f, u[1] = (float)(x.y >> 8) * 5.9604644775390625e-8f;

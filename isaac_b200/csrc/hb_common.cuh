@@ -165,5 +165,17 @@ __device__ __forceinline__ void st_stream4(float4 *p, const float4 &v) {
                  : "memory");
 }
 
+// Philox4x32-10 (counter c0..c3, key k0 k1): the library's device generator (env noise, PPO action sample)
+__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+        const uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+        c0 = h1 ^ c1 ^ k0, c1 = l1, c2 = h0 ^ c3 ^ k1, c3 = l0;
+        k0 += 0x9E3779B9u, k1 += 0xBB67AE85u;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
+
 #endif  // __CUDACC__
 }  // namespace hb

@@ -523,6 +523,39 @@ __global__ void step_epilogue_kernel(hb_adam_params ap, double *__restrict__ kl_
     }
 }
 
+// N(0,1) draws for the action sample of PPO.act (ppo.py:93, Normal.sample()): Philox4x32-10 keyed by the seed, counter =
+// (quad index, a domain tag, the call counter), Box-Muller on the four words.  state[0] = call counter, state[1] = ticket:
+// every block reads the counter first, the last block to finish advances it - the launch can sit in a replayed graph.
+__global__ void __launch_bounds__(256)
+draw_normal_kernel(float *__restrict__ out, long long count, uint32_t k0, uint32_t k1, unsigned long long *__restrict__ state) {
+    const unsigned long long call = *reinterpret_cast<volatile unsigned long long *>(state);
+    const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q * 4 < count) {
+        const uint4 x = hb::philox4x32_10((uint32_t)q, 0x50504F00u ^ (uint32_t)(q >> 32), (uint32_t)call, (uint32_t)(call >> 32), k0, k1);
+        const float scale = 5.9604644775390625e-8f;                 // 2^-24
+        const float u0 = (float)((x.x >> 8) + 1u) * scale, u1 = (float)((x.z >> 8) + 1u) * scale;      // (0, 1]
+        const float r0 = sqrtf(-2.0f * __logf(u0)), r1 = sqrtf(-2.0f * __logf(u1));
+        float s0, c0, s1, c1;
+        __sincosf(6.283185307179586f * ((float)(x.y >> 8) * scale), &s0, &c0);
+        __sincosf(6.283185307179586f * ((float)(x.w >> 8) * scale), &s1, &c1);
+        const float z[4] = {r0 * c0, r0 * s0, r1 * c1, r1 * s1};
+        if (q * 4 + 3 < count && (reinterpret_cast<uintptr_t>(out) & 15u) == 0) {
+            reinterpret_cast<float4 *>(out)[q] = make_float4(z[0], z[1], z[2], z[3]);
+        } else {
+            for (int k = 0; k < 4 && q * 4 + k < count; ++k) out[q * 4 + k] = z[k];
+        }
+    }
+    __syncthreads();                                                // the whole block has read the counter
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned long long ticket = atomicAdd(state + 1, 1ull);
+        if (ticket == (unsigned long long)gridDim.x - 1ull) {
+            state[1] = 0ull;
+            *reinterpret_cast<volatile unsigned long long *>(state) = call + 1ull;
+        }
+    }
+}
+
 }  // namespace
 
 extern "C" {
@@ -581,6 +614,15 @@ int hb_ppo_head_fused(const float *h3_actor, int32_t ld_ha, const float *h3_crit
         h3_actor, ld_ha, h3_critic, ld_hc, w4_actor, w4_critic, ld_w, std, records, mb, 1.0 / (double)mb_global,
         (float)((double)mb / (double)mb_global), *lp, dz3_actor, dz3_critic, ld_dz, g4_actor, g4_critic, d_std, stats);
     HB_CHECK_LAUNCH("head_fused_kernel");
+    return HB_OK;
+}
+
+int hb_ppo_draw_normal(float *out, int64_t count, uint64_t seed, uint64_t *state, void *stream) {
+    HB_REQUIRE(out && state && count > 0, "hb_ppo_draw_normal: bad arguments");
+    const long long quads = (count + 3) / 4;
+    draw_normal_kernel<<<(unsigned)((quads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        out, (long long)count, (uint32_t)seed, (uint32_t)(seed >> 32), reinterpret_cast<unsigned long long *>(state));
+    HB_CHECK_LAUNCH("draw_normal_kernel");
     return HB_OK;
 }
 

@@ -376,6 +376,7 @@ def test_attached_rollout_writes_observations_in_place(lib, cuda_device, graphs)
             env.enable_cuda_graph()
         alg, _, _ = make_pair(dev, n, t, cfg)
         alg.graph_rollout = graphs
+        alg.seed(31)                # the graph draws eps itself (library generator): same seed, same rollout
         if runs:
             alg.actor_critic.load_state_dict(runs[0]["sd"])
         sd0 = {k: v.clone() for k, v in alg.actor_critic.state_dict().items()}
@@ -387,8 +388,6 @@ def test_attached_rollout_writes_observations_in_place(lib, cuda_device, graphs)
         for it in range(2):
             for k in range(t):
                 alg.injected_eps = torch.randn(n, 10, generator=g).to(dev) if not graphs else None
-                if graphs:          # the graph draws eps itself: fix torch's CUDA generator instead
-                    torch.cuda.manual_seed(1000 * it + k)
                 a = alg.act(obs, cobs)
                 if attached:
                     so, sp = alg.storage.observation_slot(k)
@@ -416,3 +415,37 @@ def test_attached_rollout_writes_observations_in_place(lib, cuda_device, graphs)
             else:       # the weight-gradient GEMMs accumulate split-K partials with float atomics: order-dependent bits
                 torch.testing.assert_close(u, v, rtol=1e-2, atol=5e-3, msg=lambda m: f"{(i, j)}: {m}")
     torch.testing.assert_close(runs[0]["final"], runs[1]["final"], rtol=1e-2, atol=5e-3)       # Adam: sign flips of ~0 gradients
+
+
+def test_library_normal_draws(lib, cuda_device):
+    """hb_ppo_draw_normal (the eps of Normal.sample() in PPO.act): N(0,1) moments, fresh numbers on every launch from the
+    device-side call counter, bit-reproducible from (seed, counter), ragged counts and unaligned outputs in bounds."""
+    dev = cuda_device
+    n = 4096 * 10
+    state = torch.zeros(2, dtype=torch.int64, device=dev)
+    a, b, c = (torch.empty(n, device=dev) for _ in range(3))
+    for out in (a, b):
+        assert lib.hb_ppo_draw_normal(out.data_ptr(), n, 1234, state.data_ptr(), None) == 0
+    torch.cuda.synchronize()
+    assert state.tolist() == [2, 0], "two launches, ticket re-armed"
+    assert not torch.equal(a, b)
+    for z in (a, b):
+        assert abs(z.mean().item()) < 0.02 and abs(z.std().item() - 1.0) < 0.02
+        assert abs((z ** 3).mean().item()) < 0.06 and abs((z ** 4).mean().item() - 3.0) < 0.15
+        assert z.abs().max().item() < 6.5 and torch.isfinite(z).all()
+    assert abs(torch.corrcoef(torch.stack((a, b)))[0, 1].item()) < 0.02                       # call to call
+    assert abs(torch.corrcoef(torch.stack((a[:-1], a[1:])))[0, 1].item()) < 0.02               # neighbour to neighbour
+    state.zero_()
+    lib.hb_ppo_draw_normal(c.data_ptr(), n, 1234, state.data_ptr(), None)
+    torch.cuda.synchronize()
+    assert torch.equal(c, a), "same seed and counter, same numbers"
+    state.zero_()
+    lib.hb_ppo_draw_normal(c.data_ptr(), n, 99, state.data_ptr(), None)
+    torch.cuda.synchronize()
+    assert not torch.equal(c, a)
+    # ragged count at an address that is only 4-byte aligned, inside guard sentinels
+    raw = torch.full((64,), -7.0, device=dev)
+    state.zero_()
+    assert lib.hb_ppo_draw_normal(raw[9:].data_ptr(), 10, 1234, state.data_ptr(), None) == 0
+    torch.cuda.synchronize()
+    assert (raw[:9] == -7.0).all() and (raw[19:] == -7.0).all() and torch.equal(raw[9:19], a[:10])
