@@ -109,76 +109,152 @@ def fill_storage_cpu(st, seed):
     st["actions_log_prob"].copy_(-0.5 * ((st["actions"] - st["mu"]) ** 2).sum(-1, keepdim=True) - 9.19)
 
 
+def workload_name(n):
+    """config.workload, identical on both arms."""
+    return f"hector task, {n} envs per GPU, env.step with stubbed physics (BASELINE configs[1])"
+
+
 # ------------------------------------------------------------------------------------ reference arm
+def reference_env(n, frames, seed):
+    """The reference's CPU implementation of env.step on the workload's tape: the UNMODIFIED reference
+    (baseline/_ref, or /root/reference in the build container) through oracle/ref_harness.py when it is there
+    (kind "reference"), else the oracle port (kind "port").  Returns (step(i), kind, description)."""
+    from isaac_b200.envs.hector_config import HectorCfg
+    tape = make_workload(n, frames, seed)
+    from oracle import ref_harness
+    if ref_harness.reference_root() is not None:
+        ref = ref_harness.ReferenceEnv(tape.statics, tape.physics[0], tape.noise[0])
+        return (lambda i: ref.step(tape.physics[i % frames], tape.noise[i % frames]), "reference",
+                f"unmodified reference HectorFreeEnv.step ({ref_harness.reference_root()}), isaacgym stubbed")
+    from oracle.hector_oracle import OracleHectorEnv
+    env = OracleHectorEnv(HectorCfg(), tape.statics, tape.physics[0], tape.noise[0])
+    return (lambda i: env.step(tape.physics[i % frames], tape.noise[i % frames]), "port", "torch CPU oracle port")
+
+
 def run_reference(args, rank):
-    """The reference's own torch CPU implementation of the path, restated in oracle/ (the reference is
-    Python and cannot travel to the GPU box; oracle/hector_oracle.py is pinned bit-for-bit against it)."""
+    """--impl reference: the reference's own torch CPU code on the box's host cores, all threads (rank 0 only; at N > 1
+    it still steps ONE shard of args.envs envs - the CPU has no second socket per GPU - so per-N ratios compare a CPU
+    shard with N GPU shards)."""
     if rank != 0:
         return
-    from isaac_b200.envs.hector_config import HectorCfg
-    from oracle.hector_oracle import OracleHectorEnv
+    import contextlib
+    with contextlib.redirect_stdout(sys.stderr):      # the reference prints its networks on construction; stdout = one JSON line
+        line = _reference_line(args)
+    print(json.dumps(line), flush=True)
+
+
+def _reference_line(args):
     from oracle.ppo_oracle import gae_returns
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     n = args.envs
-    frames = 4
-    tape = make_workload(n, frames, 1234)
-    env = OracleHectorEnv(HectorCfg(), tape.statics, tape.physics[0], tape.noise[0])
+    step, kind, what = reference_env(n, 4, 1234)
     for i in range(args.warmup):
-        env.step(tape.physics[i % frames], tape.noise[i % frames])
+        step(i)
     t0 = time.perf_counter()
     for i in range(args.steps):
-        env.step(tape.physics[i % frames], tape.noise[i % frames])
+        step(args.warmup + i)
     dt = time.perf_counter() - t0
     value = n * args.steps / dt
     g = torch.Generator().manual_seed(0)
     r, v = torch.rand(T_GAE, n, 1, generator=g), torch.randn(T_GAE, n, 1, generator=g)
     d, lv = (torch.rand(T_GAE, n, 1, generator=g) < 0.005).byte(), torch.randn(n, 1, generator=g)
-    gae_returns(r, v, d, lv, 0.994, 0.9)
-    t0 = time.perf_counter()
-    for _ in range(5):
-        gae_returns(r, v, d, lv, 0.994, 0.9)
-    gae_s = (time.perf_counter() - t0) / 5
-    # PPO update on the CPU: a bounded sample (1 epoch x 4 minibatches of the same [24, n] rollout)
+    # PPO: GAE + update on the CPU, a bounded sample (1 epoch x 4 minibatches of the same [24, n] rollout)
+    from oracle import ref_harness
     from oracle.ppo_oracle import OraclePPO, init_actor_critic_params
-    ora = OraclePPO(init_actor_critic_params(seed=5), n, T_GAE, **dict(PPO_CFG, num_learning_epochs=1))
-    fill_storage_cpu(ora.st, 100)
-    ora.compute_returns(torch.randn(n, 1050, generator=g))
-    t0 = time.perf_counter()
-    ora.update(torch.randperm(n * T_GAE, generator=g))
-    ppo_s = time.perf_counter() - t0
+    cfg1 = dict(PPO_CFG, num_learning_epochs=1)
+    perm = torch.randperm(n * T_GAE, generator=g)
+    if kind == "reference":
+        policy = dict(init_noise_std=1.0, actor_hidden_dims=[512, 256, 128], critic_hidden_dims=[768, 256, 128])
+        ref = ref_harness.ReferencePPO(init_actor_critic_params(seed=5), n, T_GAE, cfg1, policy)
+        st = ref.alg.storage
+        fill_storage_cpu(dict(observations=st.observations, privileged_observations=st.privileged_observations,
+                              actions=st.actions, mu=st.mu, sigma=st.sigma, rewards=st.rewards, values=st.values,
+                              dones=st.dones, actions_log_prob=st.actions_log_prob), 100)
+        st.step = T_GAE
+        t0 = time.perf_counter()
+        ref.compute_returns(torch.randn(n, 1050, generator=g))
+        gae_s = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        ref.update(perm)
+        ppo_s = time.perf_counter() - t0
+    else:
+        gae_returns(r, v, d, lv, 0.994, 0.9)
+        t0 = time.perf_counter()
+        for _ in range(5):
+            gae_returns(r, v, d, lv, 0.994, 0.9)
+        gae_s = (time.perf_counter() - t0) / 5
+        ora = OraclePPO(init_actor_critic_params(seed=5), n, T_GAE, **cfg1)
+        fill_storage_cpu(ora.st, 100)
+        ora.compute_returns(torch.randn(n, 1050, generator=g))
+        t0 = time.perf_counter()
+        ora.update(perm)
+        ppo_s = time.perf_counter() - t0
+    sample = f"{args.steps} steps of {n} envs after {args.warmup} warm-up, {what}, torch CPU {torch.__version__}, {cores} threads"
     line = {"impl": "reference", "metric": "env-steps/s", "value": value, "unit": "env-steps/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"hector task, {n} envs, env.step with stubbed physics (BASELINE configs[1])",
-                       "envs_per_gpu": n, "decimation": 10},
-            "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port",
-                             "sample": f"{args.steps} steps of {n} envs after {args.warmup} warm-up, torch CPU {torch.__version__}"},
-            "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gae": {"value": T_GAE * n / gae_s, "unit": "samples/s", "T": T_GAE},
+            "config": {"workload": workload_name(n), "envs_per_gpu": n, "decimation": 10,
+                       "note": "the CPU arm steps one shard of envs_per_gpu envs at every --gpus N"},
+            "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": kind, "sample": sample},
+            "gae": {"value": T_GAE * n / gae_s, "unit": "samples/s", "T": T_GAE,
+                    "what": "PPO.compute_returns (critic forward + GAE)" if kind == "reference" else "GAE scan"},
+            "gpu_launches": 0,
             "ppo": {"value": T_GAE * n / (ppo_s * 5), "unit": "samples/s", "sample_passes_per_s": T_GAE * n / ppo_s,
                     "sample": f"1 epoch x 4 minibatches of [{T_GAE},{n}] timed ({ppo_s:.1f} s), x5 epochs extrapolated"},
-            "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+            "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    return line
 
 
 # ------------------------------------------------------------------------------------ B200 arm
 def cpu_baseline(n, budget_s=10.0):
-    from isaac_b200.envs.hector_config import HectorCfg
-    from oracle.hector_oracle import OracleHectorEnv
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    tape = make_workload(n, 3, 1234)
-    env = OracleHectorEnv(HectorCfg(), tape.statics, tape.physics[0], tape.noise[0])
+    step, kind, what = reference_env(n, 3, 1234)
     for i in range(2):
-        env.step(tape.physics[i % 3], tape.noise[i % 3])
+        step(i)
     steps, t0 = 0, time.perf_counter()
     while time.perf_counter() - t0 < budget_s and steps < 5000:
-        env.step(tape.physics[steps % 3], tape.noise[steps % 3])
+        step(steps)
         steps += 1
     dt = time.perf_counter() - t0
-    return {"value": n * steps / dt, "unit": "env-steps/s", "cores": cores, "kind": "port",
-            "sample": f"{steps} steps of {n} envs ({dt:.1f} s), torch CPU oracle port, {cores} threads"}
+    return {"value": n * steps / dt, "unit": "env-steps/s", "cores": cores, "kind": kind,
+            "sample": f"{steps} steps of {n} envs ({dt:.1f} s), {what}, {cores} threads"}
+
+
+def measure_tf32_peak(dev, seconds=1.5):
+    """Dense TF32 tensor-core peak of this GPU, the way MEASURED_PEAKS.json measures bf16: torch.matmul (cuBLAS) on
+    8192^3 fp32 operands with TF32 math allowed - best of 10 (burst) and back to back for `seconds` (sustained)."""
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        n = 8192
+        a, b = torch.randn(n, n, device=dev), torch.randn(n, n, device=dev)
+        c = torch.empty(n, n, device=dev)
+        for _ in range(3):
+            torch.matmul(a, b, out=c)
+        torch.cuda.synchronize(dev)
+        flop = 2.0 * n ** 3
+        best = 0.0
+        for _ in range(10):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            torch.matmul(a, b, out=c)
+            e1.record()
+            e1.synchronize()
+            best = max(best, flop / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+        reps = max(10, int(seconds / (flop / (best * 1e12))))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            torch.matmul(a, b, out=c)
+        e1.record()
+        e1.synchronize()
+        sustained = reps * flop / (e0.elapsed_time(e1) * 1e-3) / 1e12
+        return {"burst_tflops": best, "sustained_tflops": sustained,
+                "how": f"torch.matmul fp32 {n}^3 with allow_tf32 (cuBLAS): best of 10; {reps} back to back"}
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
 
 
 PPO_FLOP_PER_SAMPLE_PASS = 6.853e6        # fwd 3.032 + bwd 3.821 MFLOP (SURVEY.md §8d)
@@ -233,9 +309,35 @@ def bench_iteration(env, phys, phys_frames, alg, dev, n, iters=2):
     return out
 
 
+def time_updates(alg, args, dev, n, world, rank, last, reps):
+    """Mean device time (ms, max over ranks) of compute_returns + update() over `reps` timed updates after one warm-up
+    (the second update also captures the per-minibatch graphs: two warm-ups on a single GPU)."""
+    import torch.distributed as dist
+    stream = torch.cuda.current_stream(dev)
+    times = []
+    warm = 2 if world == 1 else 1
+    for r in range(reps + warm):
+        fill_storage(alg.storage, 100 + rank, dev)
+        alg.storage.step = T_GAE
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        alg.compute_returns(last)
+        alg.update()
+        b.record(stream)
+        b.synchronize()
+        if r >= warm:
+            times.append(a.elapsed_time(b))
+    t = torch.tensor([sum(times) / len(times)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
 def bench_ppo(args, dev, n, world, rank, env=None, phys=None, phys_frames=None):
     """compute_returns + update() on [T=24, n] rollouts: PPO samples/s (BASELINE configs[1]/[4])."""
-    import torch.distributed as dist
     from isaac_b200.algo.actor_critic import ActorCritic
     from isaac_b200.algo.ppo import PPO
     torch.manual_seed(5)
@@ -244,7 +346,7 @@ def bench_ppo(args, dev, n, world, rank, env=None, phys=None, phys_frames=None):
     alg.init_storage(n, T_GAE, [615], [1050], [10])
     if world > 1:
         from isaac_b200.parallel import attach_data_parallel
-        attach_data_parallel(alg)
+        attach_data_parallel(alg, env=env)
     last = torch.randn(n, 1050, device=dev)
     stream = torch.cuda.current_stream(dev)
     # rollout side: PPO.act + process_env_step per env step, T steps; the observations are
@@ -264,41 +366,38 @@ def bench_ppo(args, dev, n, world, rank, env=None, phys=None, phys_frames=None):
         b.record(stream)
         b.synchronize()
         roll_ms = a.elapsed_time(b) / T_GAE
-    times = []
     reps = max(2, args.ppo_updates)
-    for r in range(reps + 1):
-        fill_storage(alg.storage, 100 + rank, dev)
-        alg.storage.step = T_GAE
-        torch.cuda.synchronize(dev)
-        if world > 1:
-            dist.barrier()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record(stream)
-        alg.compute_returns(last)
-        alg.update()
-        b.record(stream)
-        b.synchronize()
-        if r > 0:
-            times.append(a.elapsed_time(b))
-    ms = sum(times) / len(times)
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
+    ms = time_updates(alg, args, dev, n, world, rank, last, reps)
     samples = n * T_GAE * world
     passes = samples * PPO_CFG["num_learning_epochs"]
     tflops = passes * PPO_FLOP_PER_SAMPLE_PASS / (ms * 1e-3) / 1e12
-    peak_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    bf16 = json.load(open(peak_path))["bf16_tflops_sustained"] if os.path.exists(peak_path) else 1400.0
+    mean_kl, lr_after = alg.last_mean_kl, alg.learning_rate
     iteration = bench_iteration(env, phys, phys_frames, alg, dev, n) if env is not None else None
-    return {"value": samples / (ms * 1e-3), "unit": "samples/s", "sample_passes_per_s": passes / (ms * 1e-3),
-            "iteration": iteration,
-            "ms_per_update": ms, "T": T_GAE, "epochs": 5, "mini_batches": 4, "dtype": "tf32 operands, f32 accumulate",
-            "tensor_tflops": tflops, "tensor_peak_tflops": bf16 * world / 2,
-            "tensor_frac": tflops / (bf16 * world / 2),
-            "tensor_peak_source": "half of measured sustained bf16 (MEASURED_PEAKS.json); TF32 rate = 1/2 bf16",
-            "mean_kl": alg.last_mean_kl, "learning_rate": alg.learning_rate,
-            "rollout_act_and_record_ms_per_step": roll_ms}
+    # the fp32-grade mode (3xTF32: hi/lo split operands, three partial products per GEMM), same update
+    fp32_grade = None
+    if world == 1 and not args.skip_3xtf32:
+        torch.manual_seed(5)
+        ac3 = ActorCritic(615, 1050, 10, actor_hidden_dims=[512, 256, 128], critic_hidden_dims=[768, 256, 128], device=dev,
+                          precision="3xtf32")
+        alg3 = PPO(ac3, device=dev, **PPO_CFG)
+        alg3.init_storage(n, T_GAE, [615], [1050], [10])
+        ms3 = time_updates(alg3, args, dev, n, world, rank, last, 2)
+        fp32_grade = {"value": samples / (ms3 * 1e-3), "unit": "samples/s", "ms_per_update": ms3,
+                      "dtype": "3xTF32 (hi/lo split operands, f32 accumulate): fp32-grade results"}
+        del alg3, ac3
+    peak = measure_tf32_peak(dev) if rank == 0 or world == 1 else None
+    out = {"value": samples / (ms * 1e-3), "unit": "samples/s", "sample_passes_per_s": passes / (ms * 1e-3),
+           "iteration": iteration,
+           "ms_per_update": ms, "T": T_GAE, "epochs": 5, "mini_batches": 4, "dtype": "tf32 operands, f32 accumulate",
+           "tensor_tflops": tflops, "fp32_grade": fp32_grade,
+           "mean_kl": mean_kl, "learning_rate": lr_after,
+           "rollout_act_and_record_ms_per_step": roll_ms}
+    if peak is not None:
+        # a whole update is a seconds-scale loop under the power cap: the sustained figure is the denominator
+        out.update({"tensor_peak_tflops": peak["sustained_tflops"] * world, "tensor_frac": tflops / (peak["sustained_tflops"] * world),
+                    "tensor_peak_burst_tflops": peak["burst_tflops"] * world,
+                    "tensor_peak_source": "measured in this run: " + peak["how"] + " (sustained)"})
+    return out
 
 
 def run_b200(args, rank, world):
@@ -501,21 +600,19 @@ def run_b200(args, rank, world):
     ach = (hist_priv + hist_obs) / (k_stack * 1e-3) / 1e9
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-    if os.path.exists(tpath):           # dram bytes of one launch from the committed ncu --set full capture, scaled to n envs
-        traffic = json.load(open(tpath))["bytes_per_env"] * n
+    if os.path.exists(tpath):           # dram bytes of one launch from the committed ncu --set full captures, per shard size
+        traffic = json.load(open(tpath)).get("bytes_per_launch", {}).get(str(n))      # null when this size was not captured
     line = {
         "metric": "env-steps/s", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"hector task, {n} envs per GPU, env.step with stubbed physics (BASELINE configs[1])",
+        "config": {"workload": workload_name(n),
                    "envs_per_gpu": n, "decimation": 10, "frame_stack": 15,
                    "launch": "eager, noise tensors resident in HBM" if args.no_graph else
                              "CUDA-graph replay (2 graphs/step around the reset-count hand-off), noise drawn in-kernel (Philox)",
                    "timing": "per-step CUDA events, L2 flushed between steps (256 MiB write then 256 MiB read, outside the events)",
                    "wall_ms_per_step_incl_flush": 1e3 * wall / args.steps},
         "clocks": clocks,
-        "e2e": {"value": total_envs * args.steps / e2e_wall, "unit": "env-steps/s", "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_wall / args.steps},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm",
                      "kernel": "stack_finalize_kernel (frame stacking: 14 carried frames of 41 + 70 floats, read + write; the "
@@ -534,10 +631,13 @@ def run_b200(args, rank, world):
                     "pd_gbs": n * 240 / (k_pd * 1e-3) / 1e9, "gae_ms": k_gae,
                     "gae_gbs": n * T_GAE * 25 / (k_gae * 1e-3) / 1e9},
         "gae": {"value": total_envs * T_GAE / (k_gae * 1e-3), "unit": "samples/s", "T": T_GAE},
-        "ppo": ppo,
     }
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(n)
+    # the last keys of the line (a truncated tail still carries them): PPO samples/s and the end-to-end number
+    line["ppo"] = ppo
+    line["e2e"] = {"value": total_envs * args.steps / e2e_wall, "unit": "env-steps/s", "h2d_bytes_per_step": h2d,
+                   "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_wall / args.steps}
     print(json.dumps(line), flush=True)
 
 
@@ -553,6 +653,7 @@ def main():
     ap.add_argument("--opt", action="append", default=[], help="library tuning switch name=value (hb_set_option)")
     ap.add_argument("--skip-ppo", action="store_true", help="env stage only (tuning sweeps)")
     ap.add_argument("--ppo-updates", type=int, default=3, help="timed PPO updates (after one warm-up)")
+    ap.add_argument("--skip-3xtf32", action="store_true", help="do not time the fp32-grade (3xTF32) update as well")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define HB_ABI_VERSION 2
+#define HB_ABI_VERSION 3
 
 typedef enum hb_status {
     HB_OK = 0,
@@ -156,9 +156,10 @@ typedef struct hb_env_buffers {
 } hb_env_buffers;
 
 /* Per-step random draws, indexed by env.  A NULL pointer means: drawn on the device where it is consumed, if
- * rng_counter is set (Philox4x32-10, key = rng_seed, counter = (env, slot, *rng_counter); the tensors the
+ * rng_counter is set (Philox4x32-10, key = rng_counter[1], counter = (env, slot, rng_counter[0]); the tensors the
  * reference would have drawn with torch.rand / randn are never materialised); otherwise treated as 0 /
- * "no such draw".  hb_env_reset_finalize advances *rng_counter once per call sequence. */
+ * "no such draw".  hb_env_reset_finalize advances rng_counter[0] once per call sequence.  Counter AND key live in
+ * device memory, so launches captured in a CUDA graph follow a re-seed (write rng_counter[1], zero rng_counter[0]). */
 typedef struct hb_env_noise {
     const float *u_delay;           /* [N]    torch.rand((N,1))            hector_env.py:166 */
     const float *z_action;          /* [N,ndof] torch.randn_like(actions)  hector_env.py:168 */
@@ -166,8 +167,7 @@ typedef struct hb_env_noise {
     const float *u_push;            /* [N,5]  push lin xy + ang xyz        hector_env.py:58-63 */
     const float *u_reset;           /* [N,15] dof(10) root xy(2) cmd(3)    legged_robot.py:366,384,327-330 */
     const float *z_obs;             /* [N,41] torch.randn_like(obs_buf)    hector_env.py:241 */
-    const uint64_t *rng_counter;    /* [1] device: step counter of the device generator, or NULL */
-    uint64_t rng_seed;
+    const uint64_t *rng_counter;    /* [2] device: {step counter, key} of the device generator, or NULL */
 } hb_env_noise;
 
 /* stage mask for hb_env_post_physics */
@@ -301,8 +301,18 @@ typedef struct hb_gemm_desc {
     int32_t split_k;             /* HB_EPI_ATOMIC_ADD only: >1 = number of splits of the contraction; 0 = automatic
                                     (about two rounds of tiles over the SMs) */
     int32_t tile_n;              /* 0 = automatic; 128 forces 128-wide tiles */
+    int32_t precision;           /* hb_gemm_precision */
+    float *workspace;            /* HB_GEMM_3XTF32: scratch for the split operands, 16-byte aligned, */
+    int64_t workspace_floats;    /*   at least hb_gemm_workspace_floats(desc) floats */
 } hb_gemm_desc;
+/* Arithmetic of the products.  HB_GEMM_TF32: operands truncated to TF32 by the tensor core (10-bit mantissa), fp32
+ * accumulation - the fast path.  HB_GEMM_3XTF32: every operand is split x = hi + lo (hi = x rounded to TF32, lo = x - hi)
+ * and the tensor core sums a_hi*b_hi + a_lo*b_hi + a_hi*b_lo in the same fp32 accumulator (one contraction of 3 K): the
+ * dropped a_lo*b_lo term is 2^-22 relative, i.e. the result is fp32-grade like the reference's nn.Linear
+ * (algo/ppo/actor_critic.py:54-83) at about a third of the TF32 throughput. */
+enum hb_gemm_precision { HB_GEMM_TF32 = 0, HB_GEMM_3XTF32 = 1 };
 int hb_gemm_tf32(const hb_gemm_desc *desc, void *stream);
+int64_t hb_gemm_workspace_floats(const hb_gemm_desc *desc);
 /* 256-wide tiles are computed by pairs of CTAs (tcgen05.mma.cta_group::2, 2-CTA clusters: each SM stages half of the
  * B tile) unless switched off (on = 0: one CTA per tile everywhere; for A/B measurements). */
 int hb_gemm_set_pair_mode(int on);
@@ -347,9 +357,10 @@ int hb_ppo_head_fused(const float *h3_actor, int32_t ld_ha, const float *h3_crit
                       float *g4_actor, float *g4_critic, float *d_std, double *stats, void *stream);
 
 /* N(0,1) draws for the action sample (algo/ppo/ppo.py:93 -> actor_critic.py:116 `distribution.sample()`): count floats
- * from the library's Philox4x32-10 generator keyed by `seed`; state = device uint64[2] {call counter, 0}, advanced by the
- * launch itself, so the call can sit in a replayed CUDA graph and still draw fresh numbers every replay. */
-int hb_ppo_draw_normal(float *out, int64_t count, uint64_t seed, uint64_t *state, void *stream);
+ * from the library's Philox4x32-10 generator; state = device uint64[3] {call counter, 0, key}: the counter is advanced by
+ * the launch itself, so the call can sit in a replayed CUDA graph, draw fresh numbers every replay and follow a re-seed
+ * (write the key, zero the counter). */
+int hb_ppo_draw_normal(float *out, int64_t count, uint64_t *state, void *stream);
 
 /* PPO.act head (ppo.py:91-101, actor_critic.py:111-120): a = mu + sigma*eps, log-prob, copies of mu/sigma. */
 int hb_ppo_act_head(const float *mu, int32_t ld_mu, const float *std, const float *eps, int64_t n, float *actions,
@@ -368,23 +379,35 @@ int hb_ppo_record_step(const float *rewards, const uint8_t *dones, const float *
                        int64_t n, float *rewards_out, uint8_t *dones_out, void *stream);
 
 typedef struct hb_adam_params {
-    float beta1, beta2, eps;
+    double beta1, beta2, eps;     /* torch.optim.Adam defaults 0.9, 0.999, 1e-8 (ppo.py:68); doubles like the Python floats */
     float max_grad_norm;          /* clip_grad_norm_ (ppo.py:173); <= 0 disables clipping */
-    double bias_correction1;      /* 1 - beta1^t */
-    double bias_correction2;      /* 1 - beta2^t */
-    /* adaptive learning rate (ppo.py:136-148), evaluated on the device from the KL sum of the loss head */
-    int32_t adaptive;             /* 1: schedule == 'adaptive' and desired_kl is set */
+    int32_t adaptive;             /* 1: schedule == 'adaptive' and desired_kl is set (ppo.py:136-148) */
     double desired_kl;
-    int64_t kl_count;             /* samples behind stats[2] */
+    int64_t kl_count;             /* samples behind state->stats[2] (the global minibatch) */
 } hb_adam_params;
-/* clip_grad_norm_ + torch.optim.Adam.step (defaults, no weight decay) over one flat parameter buffer.
- * grad_sumsq: fp64 scalar (zero on entry) that hb_grad_sumsq fills; lr_io: fp64 learning rate on the device,
- * updated in place by the adaptive schedule from kl_stats[2].  Gradients are zeroed.  If loss_acc is not NULL
- * (4 doubles), the minibatch's loss sums kl_stats[0..3] are added to it (update()'s running means, ppo.py:176-178)
- * and kl_stats / grad_sumsq are zeroed for the next minibatch. */
-int hb_grad_sumsq(const float *grads, int64_t n, double *grad_sumsq, void *stream);
-int hb_adam_step(float *params, float *grads, float *exp_avg, float *exp_avg_sq, int64_t n, const hb_adam_params *ap,
-                 double *grad_sumsq, double *kl_stats, double *lr_io, double *loss_acc, void *stream);
+
+/* Optimizer scalars, resident in device memory (8-byte aligned): nothing about a step travels by value, so the launch
+ * sequence of one minibatch step can be captured once and replayed for every step of every update. */
+#define HB_OPT_TRACE_MAX 64
+typedef struct hb_optim_state {
+    double lr;                    /* learning rate; the adaptive-KL rule updates it in place */
+    double grad_sumsq;            /* scratch, zero between steps */
+    double stats[4];              /* this minibatch's loss sums {surrogate, value loss, kl, entropy}: accumulated by
+                                     hb_ppo_head_fused / hb_ppo_loss_head (all-reduced over ranks), zero between steps */
+    double loss_acc[4];           /* running sums over the update (ppo.py:176-178); the host zeroes them per update() */
+    int64_t step;                 /* Adam's step count t (bias corrections 1 - beta^t) */
+    int64_t steps_in_update;      /* optimizer steps since the host last zeroed it: index into trace */
+    uint64_t ticket;              /* grid barrier of hb_optimizer_step; zero between steps */
+    uint64_t reserved;
+    double trace[2 * HB_OPT_TRACE_MAX];   /* {mean KL, learning rate after the rule} of step i < HB_OPT_TRACE_MAX of the update */
+} hb_optim_state;
+
+/* clip_grad_norm_ + torch.optim.Adam.step (defaults, no weight decay) + optimizer.zero_grad over one flat parameter
+ * buffer, with the adaptive learning-rate rule evaluated on the device from state->stats[2] - ONE cooperative launch
+ * (gradient norm, grid barrier, update; ppo.py:136-148,171-174).  On return (stream order): gradients zeroed,
+ * state->stats folded into state->loss_acc and zeroed, state->step and state->steps_in_update advanced. */
+int hb_optimizer_step(float *params, float *grads, float *exp_avg, float *exp_avg_sq, int64_t n, const hb_adam_params *ap,
+                      hb_optim_state *state, void *stream);
 
 #ifdef __cplusplus
 }

@@ -10,7 +10,7 @@ import ctypes as C
 import os
 from typing import Optional
 
-HB_ABI_VERSION = 2
+HB_ABI_VERSION = 3
 HB_MAX_DOF = 16
 HB_MAX_OBS = 48
 HB_NUM_REWARDS = 18
@@ -78,7 +78,7 @@ _NOISE_FIELDS = ("u_delay", "z_action", "u_cmd", "u_push", "u_reset", "z_obs")
 
 
 class EnvNoise(C.Structure):
-    _fields_ = [(name, _fp) for name in _NOISE_FIELDS] + [("rng_counter", _fp), ("rng_seed", C.c_uint64)]
+    _fields_ = [(name, _fp) for name in _NOISE_FIELDS] + [("rng_counter", _fp)]
 
 
 HB_EPI_STORE, HB_EPI_BIAS, HB_EPI_BIAS_ELU, HB_EPI_ELU_BWD, HB_EPI_ATOMIC_ADD = range(5)
@@ -88,7 +88,11 @@ HB_PPO_ACT, HB_PPO_REC = 10, 36
 class GemmDesc(C.Structure):
     _fields_ = [("A", _fp), ("B", _fp), ("D", _fp), ("M", _i), ("N", _i), ("K", _i), ("lda", _i), ("ldb", _i),
                 ("ldd", _i), ("a_mn_major", _i), ("b_mn_major", _i), ("epilogue", _i), ("bias", _fp),
-                ("bias_stride", _i), ("H", _fp), ("ldh", _i), ("split_k", _i), ("tile_n", _i)]
+                ("bias_stride", _i), ("H", _fp), ("ldh", _i), ("split_k", _i), ("tile_n", _i), ("precision", _i),
+                ("workspace", _fp), ("workspace_floats", C.c_int64)]
+
+
+HB_GEMM_TF32, HB_GEMM_3XTF32 = 0, 1
 
 
 class PpoLossParams(C.Structure):
@@ -96,8 +100,23 @@ class PpoLossParams(C.Structure):
 
 
 class AdamParams(C.Structure):
-    _fields_ = [("beta1", _f), ("beta2", _f), ("eps", _f), ("max_grad_norm", _f), ("bias_correction1", C.c_double),
-                ("bias_correction2", C.c_double), ("adaptive", _i), ("desired_kl", C.c_double), ("kl_count", C.c_int64)]
+    _fields_ = [("beta1", C.c_double), ("beta2", C.c_double), ("eps", C.c_double), ("max_grad_norm", _f), ("adaptive", _i),
+                ("desired_kl", C.c_double), ("kl_count", C.c_int64)]
+
+
+HB_OPT_TRACE_MAX = 64
+
+
+class OptimState(C.Structure):
+    """Layout of hb_optim_state; on the Python side it is a float64 device tensor of OPTIM_STATE_DOUBLES elements whose
+    integer fields are read through an int64 view (indices below are in 8-byte words)."""
+    _fields_ = [("lr", C.c_double), ("grad_sumsq", C.c_double), ("stats", C.c_double * 4), ("loss_acc", C.c_double * 4),
+                ("step", C.c_int64), ("steps_in_update", C.c_int64), ("ticket", C.c_uint64), ("reserved", C.c_uint64),
+                ("trace", C.c_double * (2 * HB_OPT_TRACE_MAX))]
+
+
+OPTIM_STATE_DOUBLES = C.sizeof(OptimState) // 8
+OPT_LR, OPT_SUMSQ, OPT_STATS, OPT_LOSS_ACC, OPT_STEP, OPT_STEPS_IN_UPDATE, OPT_TICKET, OPT_TRACE = 0, 1, 2, 6, 10, 11, 12, 14
 
 
 class HectorB200Error(RuntimeError):
@@ -116,6 +135,9 @@ _SIGNATURES = {
     "hb_sizeof_env_params": (C.c_int, []),
     "hb_sizeof_env_buffers": (C.c_int, []),
     "hb_sizeof_env_noise": (C.c_int, []),
+    "hb_sizeof_gemm_desc": (C.c_int, []),
+    "hb_sizeof_adam_params": (C.c_int, []),
+    "hb_sizeof_optim_state": (C.c_int, []),
     "hb_check_device": (C.c_int, []),
     "hb_graph_begin": (C.c_int, [_fp]),
     "hb_graph_end": (C.c_int, [_fp, C.POINTER(C.c_void_p)]),
@@ -131,6 +153,7 @@ _SIGNATURES = {
     "hb_env_stack_finalize": (C.c_int, [C.POINTER(EnvParams), C.POINTER(EnvBuffers), _fp, _fp, _fp, _fp, _fp, _fp, _fp]),
     "hb_stack_shift": (C.c_int, [_fp, _fp, _fp, C.c_int32, C.c_int32, C.c_int32, _fp]),
     "hb_gemm_tf32": (C.c_int, [C.POINTER(GemmDesc), _fp]),
+    "hb_gemm_workspace_floats": (C.c_int64, [C.POINTER(GemmDesc)]),
     "hb_gemm_set_pair_mode": (C.c_int, [C.c_int]),
     "hb_ppo_gather_rows": (C.c_int, [_fp, C.c_int32, _fp, C.c_int32, _fp, C.c_int64, C.c_int32, C.c_int32, _fp]),
     "hb_ppo_pack_samples": (C.c_int, [_fp, C.c_int64, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp]),
@@ -141,10 +164,9 @@ _SIGNATURES = {
     "hb_ppo_act_fused": (C.c_int, [_fp, C.c_int32, _fp, C.c_int32, _fp, _fp, C.c_int32, _fp, _fp, C.c_int64, _fp, _fp, _fp, _fp,
                                    _fp, _fp]),
     "hb_ppo_record_step": (C.c_int, [_fp, _fp, _fp, _fp, C.c_float, C.c_int64, _fp, _fp, _fp]),
-    "hb_ppo_draw_normal": (C.c_int, [_fp, C.c_int64, C.c_uint64, _fp, _fp]),
+    "hb_ppo_draw_normal": (C.c_int, [_fp, C.c_int64, _fp, _fp]),
     "hb_ppo_act_head": (C.c_int, [_fp, C.c_int32, _fp, _fp, C.c_int64, _fp, _fp, _fp, _fp, _fp]),
-    "hb_grad_sumsq": (C.c_int, [_fp, C.c_int64, _fp, _fp]),
-    "hb_adam_step": (C.c_int, [_fp, _fp, _fp, _fp, C.c_int64, C.POINTER(AdamParams), _fp, _fp, _fp, _fp, _fp]),
+    "hb_optimizer_step": (C.c_int, [_fp, _fp, _fp, _fp, C.c_int64, C.POINTER(AdamParams), _fp, _fp]),
     "hb_gae_returns": (C.c_int, [_fp, _fp, _fp, _fp, _fp, _fp, _fp, C.c_int32, C.c_int32, C.c_float, C.c_float, _fp]),
     "hb_gae_normalize": (C.c_int, [_fp, _fp, C.c_int64, _fp]),
     "hb_gae_normalize_n": (C.c_int, [_fp, _fp, C.c_int64, C.c_int64, _fp]),
@@ -166,7 +188,9 @@ def load(check_device: bool = False) -> C.CDLL:
         if lib.hb_abi_version() != HB_ABI_VERSION:
             raise HectorB200Error("ABI version mismatch between libhectorb200.so and isaac_b200/_lib.py")
         for fn, cls in ((lib.hb_sizeof_env_params, EnvParams), (lib.hb_sizeof_env_buffers, EnvBuffers),
-                        (lib.hb_sizeof_env_noise, EnvNoise)):
+                        (lib.hb_sizeof_env_noise, EnvNoise), (lib.hb_sizeof_adam_params, AdamParams),
+                        (lib.hb_sizeof_gemm_desc, GemmDesc),
+                        (lib.hb_sizeof_optim_state, OptimState)):
             if fn() != C.sizeof(cls):
                 raise HectorB200Error(f"struct {cls.__name__}: header says {fn()} bytes, ctypes mirror {C.sizeof(cls)}")
         _LIB = lib

@@ -18,7 +18,8 @@ from typing import Dict, List, Optional
 import torch
 
 from .. import _lib
-from .._lib import (GemmDesc, HB_EPI_ATOMIC_ADD, HB_EPI_BIAS, HB_EPI_BIAS_ELU, HB_EPI_ELU_BWD, HB_PPO_ACT)
+from .._lib import (GemmDesc, HB_EPI_ATOMIC_ADD, HB_EPI_BIAS, HB_EPI_BIAS_ELU, HB_EPI_ELU_BWD, HB_GEMM_3XTF32, HB_GEMM_TF32,
+                    HB_PPO_ACT)
 
 
 def pad4(n: int) -> int:
@@ -38,10 +39,18 @@ class _Layer:
         return self.rows * self.ld
 
 
-def gemm(lib, st, **kw):
+def gemm(lib, st, scratch=None, **kw):
+    """One hb_gemm_tf32 call.  `scratch` (a one-element list holding a float tensor or None) switches the call to
+    HB_GEMM_3XTF32 and supplies / grows the workspace of the split operands."""
     d = GemmDesc()
     for k, v in kw.items():
         setattr(d, k, v)
+    if scratch is not None:
+        d.precision = HB_GEMM_3XTF32
+        need = int(lib.hb_gemm_workspace_floats(C.byref(d)))
+        if scratch[0] is None or scratch[0].numel() < need:
+            scratch[0] = torch.empty(need, device=scratch[1])
+        d.workspace, d.workspace_floats = scratch[0].data_ptr(), scratch[0].numel()
     _lib.check(lib.hb_gemm_tf32(C.byref(d), st), "hb_gemm_tf32")
 
 
@@ -50,6 +59,9 @@ class ActorCritic:
 
     def __init__(self, num_actor_obs, num_critic_obs, num_actions, actor_hidden_dims=(256, 256, 256),
                  critic_hidden_dims=(256, 256, 256), init_noise_std=1.0, activation=None, device="cuda:0", **kwargs):
+        precision = kwargs.pop("precision", "tf32")
+        if precision not in ("tf32", "3xtf32"):
+            raise ValueError("precision must be 'tf32' or '3xtf32'")
         if kwargs:
             print("ActorCritic.__init__ got unexpected arguments, which will be ignored: " + str(list(kwargs)))
         if num_actions != HB_PPO_ACT:
@@ -84,6 +96,10 @@ class ActorCritic:
         self.distribution = None
         self._ws: Dict[int, dict] = {}
         self._last: Optional[dict] = None
+        # "tf32": operands truncated to TF32 by the tensor core (fast path).  "3xtf32": hi/lo split operands, three
+        # partial products in one fp32 accumulator - fp32-grade results like the reference's nn.Linear (parity mode)
+        self.precision = precision
+        self._scratch = {"actor": [None, self.device], "critic": [None, self.device]}     # one per stream / network
 
     # ------------------------------------------------------------------ parameter views
     def _matrix(self, flat, L):
@@ -159,6 +175,9 @@ class ActorCritic:
             self._ws[m] = ws
         return ws
 
+    def _scratch_for(self, net: str):
+        return self._scratch[net] if self.precision == "3xtf32" else None
+
     # ------------------------------------------------------------------ forward
     @property
     def fused_head(self) -> bool:
@@ -178,7 +197,7 @@ class ActorCritic:
                 return ws[net]["h"][-1]
             P = self._matrix(self.flat, L)
             d = ws[net]["out"] if L.last else ws[net]["h"][i]
-            gemm(lib, st, A=a.data_ptr(), B=P.data_ptr(), D=d.data_ptr(), M=m, N=L.rows if L.last else L.fan_out,
+            gemm(lib, st, self._scratch_for(net), A=a.data_ptr(), B=P.data_ptr(), D=d.data_ptr(), M=m, N=L.rows if L.last else L.fan_out,
                  K=L.fan_in, lda=lda, ldb=L.ld, ldd=d.stride(0), epilogue=HB_EPI_BIAS if L.last else HB_EPI_BIAS_ELU,
                  bias=P.data_ptr() + L.fan_in * 4, bias_stride=L.ld)
             a, lda = d, d.stride(0)
@@ -200,14 +219,14 @@ class ActorCritic:
             act_in = x if i == 0 else ws[net]["h"][i - 1]      # [m, fan_in (+ ones column)]
             n_w = L.fan_in + 1
             # weight gradient: G[rows, fan_in + 1] += d_cur^T [rows, m] * [act_in | 1] [m, fan_in + 1]
-            gemm(lib, st, A=d_cur.data_ptr(), B=act_in.data_ptr(), D=G.data_ptr(), M=L.rows, N=n_w, K=m, lda=ld_cur,
+            gemm(lib, st, self._scratch_for(net), A=d_cur.data_ptr(), B=act_in.data_ptr(), D=G.data_ptr(), M=L.rows, N=n_w, K=m, lda=ld_cur,
                  ldb=act_in.stride(0), ldd=L.ld, a_mn_major=1, b_mn_major=1, epilogue=HB_EPI_ATOMIC_ADD, split_k=0)
             if i == 0:
                 break
             # data gradient through the previous ELU: dz_prev = (d_cur * W) . elu'(h_prev)
             P = self._matrix(self.flat, L)
             h_prev, dz = ws[net]["h"][i - 1], ws[net]["dz"][i - 1]
-            gemm(lib, st, A=d_cur.data_ptr(), B=P.data_ptr(), D=dz.data_ptr(), M=m, N=L.fan_in, K=L.rows, lda=ld_cur,
+            gemm(lib, st, self._scratch_for(net), A=d_cur.data_ptr(), B=P.data_ptr(), D=dz.data_ptr(), M=m, N=L.fan_in, K=L.rows, lda=ld_cur,
                  ldb=L.ld, ldd=dz.stride(0), b_mn_major=1, epilogue=HB_EPI_ELU_BWD, H=h_prev.data_ptr(),
                  ldh=h_prev.stride(0))
             d_cur, ld_cur = dz, dz.stride(0)

@@ -20,7 +20,8 @@ from typing import Optional
 import torch
 
 from .. import _lib
-from .._lib import AdamParams, HB_PPO_REC, PpoLossParams
+from .._lib import (AdamParams, HB_OPT_TRACE_MAX, HB_PPO_REC, OPT_LOSS_ACC, OPT_LR, OPT_STATS, OPT_STEP,
+                    OPT_STEPS_IN_UPDATE, OPT_SUMSQ, OPT_TRACE, OPTIM_STATE_DOUBLES, PpoLossParams)
 from .actor_critic import ActorCritic, pad4
 from .rollout_storage import RolloutStorage
 
@@ -58,7 +59,7 @@ class _AdamState:
             if i in sd["state"]:
                 m.copy_(sd["state"][i]["exp_avg"].to(m.device))
                 v.copy_(sd["state"][i]["exp_avg_sq"].to(v.device))
-                p._step = int(sd["state"][i]["step"])
+                p._set_step(int(sd["state"][i]["step"]))
         p.learning_rate = sd["param_groups"][0]["lr"]
 
 
@@ -82,13 +83,18 @@ class PPO:
         n = actor_critic.flat.numel()
         self._exp_avg = torch.zeros(n, device=self.device)
         self._exp_avg_sq = torch.zeros(n, device=self.device)
+        # hb_optim_state (include/hector_b200.h): learning rate, Adam step count, gradient norm, loss sums and the
+        # per-step {KL, learning rate} trace of the current update, all device-resident
+        self._opt = torch.zeros(OPTIM_STATE_DOUBLES, dtype=torch.float64, device=self.device)
+        self._opt_i64 = self._opt.view(torch.int64)
+        self._lr_dev = self._opt[OPT_LR:OPT_LR + 1]
+        self._stats = self._opt[OPT_STATS:OPT_STATS + 4]
+        self._loss_acc = self._opt[OPT_LOSS_ACC:OPT_LOSS_ACC + 4]
+        self._per_update = self._opt[OPT_SUMSQ:OPT_STEP]             # grad_sumsq, stats, loss_acc: zeroed per update()
         self._step = 0
         self._lr_host = float(learning_rate)
-        self._lr_dev = torch.tensor([learning_rate], dtype=torch.float64, device=self.device)
+        self._lr_dev.fill_(float(learning_rate))
         self._lr_dirty = False
-        self._sumsq = torch.zeros(1, dtype=torch.float64, device=self.device)
-        self._stats = torch.zeros(4, dtype=torch.float64, device=self.device)
-        self._loss_acc = torch.zeros(4, dtype=torch.float64, device=self.device)
         self.optimizer = _AdamState(self)
         self.grad_allreduce = None          # multi-GPU hook: fn(flat_grad) sums gradients over ranks
         self.world_size = 1
@@ -98,11 +104,18 @@ class PPO:
         self._side_stream = torch.cuda.Stream(self.device) if self.device.type == "cuda" else None
         self.graph_rollout = True           # PPO.act: replay the hidden-layer GEMMs from a CUDA graph for small shards
         self.graph_rollout_max_envs = 16384
-        self._act_graphs, self._act_stage = {}, None
-        # the action sample's N(0,1) draws come from the library's Philox generator (hb_ppo_draw_normal): key = seed,
-        # counter on the device, so the draw can sit inside the replayed act graph
-        self._eps_seed = 0x9E3779B97F4A7C15
-        self._eps_state = torch.zeros(2, dtype=torch.int64, device=self.device) if self.device.type == "cuda" else None
+        self._act_graphs, self._act_stages = {}, {}
+        # the action sample's N(0,1) draws come from the library's Philox generator (hb_ppo_draw_normal): call counter
+        # AND key live on the device ({counter, ticket, key}), so the draw can sit inside the replayed act graph and
+        # still follow seed()
+        self._eps_state = torch.zeros(3, dtype=torch.int64, device=self.device)
+        self.seed(0x9E3779B97F4A7C15)
+        # update(): one CUDA graph per minibatch index (forward, loss head, backward, optimizer step), captured on the
+        # second update and replayed for every epoch of every later update (single-GPU; data-parallel replicas launch
+        # eagerly around their gradient all-reduce)
+        self.graph_update = True
+        self._update_graphs = {}
+        self._updates_done = 0
 
     # ------------------------------------------------------------------ learning rate (device-resident)
     @property
@@ -145,18 +158,33 @@ class PPO:
             env.prepare_action_buffers(*[s.actions[k] for k in range(s.num_transitions_per_env)])
 
     def seed(self, seed: int) -> None:
-        """Seed of the action-sample generator (the reference seeds torch globally, helpers.py:95-106)."""
+        """Seed of the action-sample generator (the reference seeds torch globally, helpers.py:95-106).  The key is
+        device-resident: act graphs captured earlier draw from it on their next replay.  Data-parallel replicas need
+        distinct seeds (isaac_b200.parallel.attach_data_parallel derives one per rank)."""
         self._eps_seed = int(seed) & 0xFFFFFFFFFFFFFFFF
-        self._eps_state.zero_()
+        signed = self._eps_seed - (1 << 64) if self._eps_seed >= (1 << 63) else self._eps_seed
+        self._eps_state.copy_(torch.tensor([0, 0, signed], dtype=torch.int64))
+
+    def _set_step(self, step: int) -> None:
+        """Adam's step count (host mirror + hb_optim_state.step)."""
+        self._step = int(step)
+        self._opt_i64[OPT_STEP] = int(step)
+
+    @property
+    def _act_stage(self):
+        """The eps staging buffer of the storage's shard width (tests read the draw of the last act())."""
+        return self._act_stages.get(self.storage.num_envs if self.storage is not None else None)
 
     def _draw_eps(self, n, st):
-        """[n, num_actions] N(0,1) draws into the staging buffer (the eps of Normal.sample(), actor_critic.py:116)."""
+        """[n, num_actions] N(0,1) draws into the staging buffer of this batch size (one per size, never freed: captured
+        act graphs address it) - the eps of Normal.sample(), actor_critic.py:116."""
         na = self.actor_critic.num_actions
-        if self._act_stage is None or self._act_stage.shape[0] != n:
-            self._act_stage = torch.zeros(n, na, device=self.device)
-        _lib.check(self._lib.hb_ppo_draw_normal(self._act_stage.data_ptr(), n * na, self._eps_seed,
-                                                self._eps_state.data_ptr(), st), "hb_ppo_draw_normal")
-        return self._act_stage
+        stage = self._act_stages.get(n)
+        if stage is None:
+            stage = self._act_stages[n] = torch.zeros(n, na, device=self.device)
+        _lib.check(self._lib.hb_ppo_draw_normal(stage.data_ptr(), n * na, self._eps_state.data_ptr(), st),
+                   "hb_ppo_draw_normal")
+        return stage
 
     def _slot(self, k):
         """Views and addresses of rollout slot k, built once per storage (tensor indexing costs microseconds)."""
@@ -203,7 +231,7 @@ class PPO:
                 e.obs.copy_(obs)
             if critic_obs.data_ptr() != e.xc_ptr or critic_obs.stride(0) != s.priv_ld:
                 e.priv.copy_(critic_obs)
-            if self.graph_rollout and self.injected_eps is None and n <= self.graph_rollout_max_envs:
+            if self.graph_rollout and self.injected_eps is None and n <= self.graph_rollout_max_envs and ac.precision == "tf32":
                 self._replay_act_graph(k, e, n)
             else:
                 ws = ac.workspace(n)
@@ -350,20 +378,39 @@ class PPO:
             self.grad_allreduce(ac.grad, self._stats, ac._grad_wire)     # sums over ranks (grads already carry 1/global_mb)
 
     def optimizer_step(self, adaptive: int):
-        """clip_grad_norm_ + Adam.step + zero_grad (ppo.py:171-174) with the adaptive-KL rule of :136-148; the loss
-        sums of the minibatch are folded into self._loss_acc and the per-minibatch accumulators re-armed on the
-        device."""
+        """clip_grad_norm_ + Adam.step + zero_grad (ppo.py:171-174) with the adaptive-KL rule of :136-148 in one
+        cooperative launch; learning rate, Adam's step count, the minibatch's loss sums and update()'s running sums
+        all stay in hb_optim_state on the device, so nothing in the call changes from step to step."""
         ac, lib = self.actor_critic, self._lib
         st = torch.cuda.current_stream(self.device).cuda_stream
-        n_flat = ac.flat.numel()
-        _lib.check(lib.hb_grad_sumsq(ac.grad.data_ptr(), n_flat, self._sumsq.data_ptr(), st), "hb_grad_sumsq")
+        ap = AdamParams(0.9, 0.999, 1e-8, float(self.max_grad_norm or 0.0), adaptive, float(self.desired_kl or 0.0),
+                        self._mb * self.world_size)
+        _lib.check(lib.hb_optimizer_step(ac.flat.data_ptr(), ac.grad.data_ptr(), self._exp_avg.data_ptr(),
+                                         self._exp_avg_sq.data_ptr(), ac.flat.numel(), C.byref(ap), self._opt.data_ptr(), st),
+                   "hb_optimizer_step")
         self._step += 1
-        ap = AdamParams(0.9, 0.999, 1e-8, float(self.max_grad_norm or 0.0), 1.0 - 0.9 ** self._step,
-                        1.0 - 0.999 ** self._step, adaptive, float(self.desired_kl or 0.0), self._mb * self.world_size)
-        _lib.check(lib.hb_adam_step(ac.flat.data_ptr(), ac.grad.data_ptr(), self._exp_avg.data_ptr(),
-                                    self._exp_avg_sq.data_ptr(), n_flat, C.byref(ap), self._sumsq.data_ptr(),
-                                    self._stats.data_ptr(), self._lr_dev.data_ptr(), self._loss_acc.data_ptr(), st),
-                   "hb_adam_step")
+
+    def _update_graph(self, i: int, adaptive: int):
+        """The launches of minibatch i's step as one CUDA graph (hb_graph_*): 6 forward GEMMs on two branches, the fused
+        head, 10 backward GEMMs on two branches, the optimizer step.  Every buffer address and every by-value argument
+        is the same for all epochs and updates (the step's scalars live in hb_optim_state), so it is captured once."""
+        key = (i, self._mb, self._xa.data_ptr(), self._xc.data_ptr(), self._rec.data_ptr(), adaptive, self.clip_param,
+               self.value_loss_coef, self.entropy_coef, self.use_clipped_value_loss, self.max_grad_norm, self.desired_kl,
+               self.actor_critic.precision)
+        g = self._update_graphs.get(key)
+        if g is None:
+            if len(self._update_graphs) >= 4 * self.num_mini_batches:
+                self._update_graphs.clear()
+            self.actor_critic.workspace(self._mb)                   # allocated before capture
+            step0 = self._step
+
+            def launches(st):
+                self.minibatch_gradients(i)
+                self.optimizer_step(adaptive)
+
+            g = self._update_graphs[key] = _lib.LaunchGraph(self.device).record(launches)
+            self._step = step0                                       # capture executed nothing
+        return g
 
     def prepare_minibatches(self, perm=None):
         """mini_batch_generator's gathers (rollout_storage.py:146-182), once per update (the permutation is
@@ -400,16 +447,32 @@ class PPO:
         self._mb, self._lp = mb, PpoLossParams(self.clip_param, self.value_loss_coef, self.entropy_coef,
                                                 int(self.use_clipped_value_loss))
         adaptive = int(self.desired_kl is not None and self.schedule == "adaptive")
-        self._loss_acc.zero_(), self._stats.zero_(), self._sumsq.zero_()
+        self._per_update.zero_()                 # gradient norm scratch, minibatch loss sums, running sums
+        self._opt_i64[OPT_STEPS_IN_UPDATE:OPT_STEPS_IN_UPDATE + 2].zero_()     # trace cursor, barrier ticket
+        # the first update launches eagerly (lazy module load, cudaFuncSetAttribute); later ones replay graphs
+        graphs = (self.graph_update and self.grad_allreduce is None and self._updates_done > 0
+                  and self.actor_critic.fused_head and self.actor_critic.precision == "tf32")
+        stream = torch.cuda.current_stream(self.device).cuda_stream
         for _ in range(self.num_learning_epochs):
             for i in range(self.num_mini_batches):
-                self.minibatch_gradients(i)
-                self.optimizer_step(adaptive)
+                if graphs:
+                    self._update_graph(i, adaptive).replay(stream)
+                    self._step += 1
+                else:
+                    self.minibatch_gradients(i)
+                    self.optimizer_step(adaptive)
+        self._updates_done += 1
         self._lr_dirty = bool(adaptive)
         num_updates = self.num_learning_epochs * self.num_mini_batches
-        acc = self._loss_acc.cpu()              # the single host sync of the update (the reference's .item() calls)
+        host = self._opt.cpu()                   # the single host sync of the update (the reference's .item() calls)
+        acc = host[OPT_LOSS_ACC:OPT_LOSS_ACC + 4]
         denom = num_updates * mb * self.world_size
         mean_surrogate_loss, mean_value_loss = float(acc[0]) / denom, float(acc[1]) / denom
         self.last_mean_kl = float(acc[2]) / denom
+        k = min(num_updates, HB_OPT_TRACE_MAX)
+        trace = host[OPT_TRACE:OPT_TRACE + 2 * k].view(k, 2)
+        self.kl_trace, self.lr_trace = trace[:, 0].tolist(), trace[:, 1].tolist()     # per optimizer step of this update
+        if adaptive:
+            self._lr_host, self._lr_dirty = float(host[OPT_LR]), False
         self.storage.clear()
         return mean_value_loss, mean_surrogate_loss

@@ -77,15 +77,20 @@ class RolloutStorage:
         # rows at a 16-byte pitch (TMA operands), and one slot more than the reference's [T, N, *]: slot T receives the
         # observations that follow the last transition when the env writes straight into the storage
         # (PPO.attach_env; they become slot 0 of the next rollout)
-        self.obs_ld = _pad4(obs_shape[0])
+        # (pitch = pad4(width + 1): there is always room for the constant ones column the weight-gradient GEMM reads)
+        self.obs_ld = _pad4(obs_shape[0] + 1)
         self._observations = z(T + 1, N, self.obs_ld)
         self.observations = self._observations[:T, :, :obs_shape[0]]
         if privileged_obs_shape[0] is not None:
-            self.priv_ld = _pad4(privileged_obs_shape[0])
+            self.priv_ld = _pad4(privileged_obs_shape[0] + 1)
             self._privileged_observations = z(T + 1, N, self.priv_ld)
             self.privileged_observations = self._privileged_observations[:T, :, :privileged_obs_shape[0]]
         else:
+            # no privileged observations: the critic reads the actor's (rollout_storage.py:157-160); the padded
+            # buffer is shared so that the update's gathers work unchanged
             self.privileged_observations = None
+            self.privileged_obs_shape = [obs_shape[0]]
+            self.priv_ld, self._privileged_observations = self.obs_ld, self._observations
         self.rewards = z(T, N, 1)
         self.actions = z(T, N, *actions_shape)
         self.dones = z(T, N, 1, dtype=torch.uint8)

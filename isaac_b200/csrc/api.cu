@@ -49,6 +49,9 @@ void hb_launch_count_reset(void) { hb::g_launches.store(0, std::memory_order_rel
 int hb_sizeof_env_params(void) { return (int)sizeof(hb_env_params); }
 int hb_sizeof_env_buffers(void) { return (int)sizeof(hb_env_buffers); }
 int hb_sizeof_env_noise(void) { return (int)sizeof(hb_env_noise); }
+int hb_sizeof_gemm_desc(void) { return (int)sizeof(hb_gemm_desc); }
+int hb_sizeof_adam_params(void) { return (int)sizeof(hb_adam_params); }
+int hb_sizeof_optim_state(void) { return (int)sizeof(hb_optim_state); }
 
 // The kernels are sm_100a-only (no other cubin or PTX is embedded): refuse anything else loudly.
 int hb_check_device(void) {

@@ -66,7 +66,7 @@ __device__ __forceinline__ float clampf(float v, float lo, float hi) { return fm
 
 // ------------------------------------------------------------------------------------------
 // Device-side draws.  When the caller supplies no tape for a draw, it is generated
-// where it is consumed with Philox4x32-10 (the generator behind torch.rand / curand): key = the env's seed,
+// where it is consumed with Philox4x32-10 (the generator behind torch.rand / curand): key = the env's seed (device memory),
 // counter = (env, slot, step), so a draw is a pure function of (seed, step, env, slot) - no state besides
 // the step counter, no tape written to or read from HBM, and rare draws (resets, command resampling,
 // pushes) cost nothing on the steps that do not need them.  Slots of one env and step:
@@ -79,8 +79,9 @@ struct Rng {
 __device__ __forceinline__ Rng make_rng(const hb_env_noise &nz) {
     Rng r;
     r.on = nz.rng_counter != nullptr;
-    const unsigned long long step = r.on ? *nz.rng_counter : 0ull;
-    r.k0 = (uint32_t)nz.rng_seed, r.k1 = (uint32_t)(nz.rng_seed >> 32);
+    // {step counter, key} both live in device memory: a captured launch picks up a re-seed on its next replay
+    const unsigned long long step = r.on ? nz.rng_counter[0] : 0ull, key = r.on ? nz.rng_counter[1] : 0ull;
+    r.k0 = (uint32_t)key, r.k1 = (uint32_t)(key >> 32);
     r.s0 = (uint32_t)step, r.s1 = (uint32_t)(step >> 32);
     return r;
 }

@@ -591,6 +591,86 @@ int dispatch_epi(const hb_gemm_desc *d, cudaStream_t st) {
     return HB_ERR_BAD_ARG;
 }
 
+// ---- 3xTF32: fp32-grade products on the TF32 tensor cores ---------------------------------------------
+// x = hi + lo with hi = x rounded to TF32 (10 explicit mantissa bits) and lo = x - hi (exact in fp32, |lo| <= 2^-11 |x|):
+//   a * b  =  a_hi b_hi + a_lo b_hi + a_hi b_lo  (+ a_lo b_lo, dropped: 2^-22 relative)
+// The three partial products are ONE longer contraction: A' = [A_hi | A_lo | A_hi], B' = [B_hi | B_hi | B_lo] along K,
+// so the tcgen05 kernel above runs unchanged (fused epilogues, split-K, pair mode) on K' = 3 K with the fp32
+// accumulator in TMEM summing all three.  The split is a pre-pass into a caller-supplied workspace.
+__device__ __forceinline__ float tf32_round(float x) {
+    return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
+}
+// K-major operand [rows, K] (leading dimension ld) -> [rows, 3 * kp], kp = K rounded up to 4, zero padded
+__global__ void __launch_bounds__(256)
+split3_kmajor_kernel(const float *__restrict__ src, int ld, long long rows, int K, int kp, float *__restrict__ dst, int second_is_lo) {
+    const long long quads = (long long)(kp >> 2);
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * quads) return;
+    const long long r = i / quads;
+    const int c = (int)(i - r * quads) * 4;
+    float x[4], hi[4], lo[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        x[k] = (c + k < K) ? __ldg(src + (size_t)r * ld + c + k) : 0.0f;
+        hi[k] = tf32_round(x[k]), lo[k] = x[k] - hi[k];
+    }
+    float *row = dst + (size_t)r * 3 * kp + c;
+    const float4 h4 = make_float4(hi[0], hi[1], hi[2], hi[3]), l4 = make_float4(lo[0], lo[1], lo[2], lo[3]);
+    *reinterpret_cast<float4 *>(row) = h4;
+    *reinterpret_cast<float4 *>(row + kp) = second_is_lo ? l4 : h4;
+    *reinterpret_cast<float4 *>(row + 2 * kp) = second_is_lo ? h4 : l4;
+}
+// MN-major operand [K, cols] (leading dimension ld) -> [3 * kp, ldd]: the three parts stacked along K at the same
+// pitch kp as a K-major partner (rows K..kp-1 of each part are zero)
+__global__ void __launch_bounds__(256)
+split3_mnmajor_kernel(const float *__restrict__ src, int ld, long long K, long long kp, int cols, float *__restrict__ dst, int ldd,
+                      int second_is_lo) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= kp * ldd) return;
+    const long long k = i / ldd;
+    const int c = (int)(i - k * ldd);
+    const float x = (c < cols && k < K) ? __ldg(src + (size_t)k * ld + c) : 0.0f;
+    const float hi = tf32_round(x), lo = x - hi;
+    dst[(size_t)k * ldd + c] = hi;
+    dst[(size_t)(kp + k) * ldd + c] = second_is_lo ? lo : hi;
+    dst[(size_t)(2 * kp + k) * ldd + c] = second_is_lo ? hi : lo;
+}
+
+inline long long pad4ll(long long v) { return (v + 3) / 4 * 4; }
+long long split3_floats(long long rows, long long K, bool mn_major) {
+    return mn_major ? 3 * pad4ll(K) * pad4ll(rows) : rows * 3 * pad4ll(K);
+}
+
+int gemm_tf32_dispatch(const hb_gemm_desc *d, cudaStream_t st);
+
+int gemm_3xtf32(const hb_gemm_desc *d, cudaStream_t st) {
+    const long long fa = split3_floats(d->M, d->K, d->a_mn_major != 0), fb = split3_floats(d->N, d->K, d->b_mn_major != 0);
+    HB_REQUIRE(d->workspace && hb::aligned16(d->workspace) && d->workspace_floats >= fa + fb,
+               "hb_gemm_tf32: HB_GEMM_3XTF32 needs a 16-byte aligned workspace of %lld floats (hb_gemm_workspace_floats), got %lld",
+               fa + fb, (long long)d->workspace_floats);
+    const long long kp = pad4ll(d->K);
+    HB_REQUIRE(3 * kp < (1ll << 31), "hb_gemm_tf32: contraction too long for the 3xTF32 form");
+    float *wa = d->workspace, *wb = d->workspace + fa;
+    hb_gemm_desc e = *d;
+    e.precision = HB_GEMM_TF32, e.A = wa, e.B = wb, e.K = (int)(3 * kp);
+    auto split = [&](const float *src, int ld, int rows, bool mn, float *dst, int second_is_lo, int &ld_out) {
+        if (mn) {
+            ld_out = (int)pad4ll(rows);
+            const long long total = kp * ld_out;
+            split3_mnmajor_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(src, ld, d->K, kp, rows, dst, ld_out, second_is_lo);
+        } else {
+            ld_out = (int)(3 * kp);
+            const long long total = (long long)rows * (kp >> 2);
+            split3_kmajor_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(src, ld, rows, d->K, (int)kp, dst, second_is_lo);
+        }
+    };
+    split(d->A, d->lda, d->M, d->a_mn_major != 0, wa, 1, e.lda);       // A' = [hi | lo | hi]
+    HB_CHECK_LAUNCH("split3 (A)");
+    split(d->B, d->ldb, d->N, d->b_mn_major != 0, wb, 0, e.ldb);       // B' = [hi | hi | lo]
+    HB_CHECK_LAUNCH("split3 (B)");
+    return gemm_tf32_dispatch(&e, st);
+}
+
 }  // namespace
 
 extern "C" int hb_gemm_set_pair_mode(int on) {
@@ -598,14 +678,14 @@ extern "C" int hb_gemm_set_pair_mode(int on) {
     return HB_OK;
 }
 
-extern "C" int hb_gemm_tf32(const hb_gemm_desc *d, void *stream) {
+namespace {
+int gemm_tf32_dispatch(const hb_gemm_desc *d, cudaStream_t st) {
     HB_REQUIRE(d && d->A && d->B && d->D, "hb_gemm_tf32: null descriptor/operand");
     HB_REQUIRE(d->M > 0 && d->N > 0 && d->K > 0, "hb_gemm_tf32: empty problem %dx%dx%d", d->M, d->N, d->K);
     HB_REQUIRE((d->epilogue != HB_EPI_BIAS && d->epilogue != HB_EPI_BIAS_ELU) || d->bias, "hb_gemm_tf32: bias epilogue without bias");
     HB_REQUIRE(d->epilogue != HB_EPI_ELU_BWD || d->H, "hb_gemm_tf32: ELU backward epilogue without activations");
     HB_REQUIRE(d->split_k <= 1 || d->epilogue == HB_EPI_ATOMIC_ADD, "hb_gemm_tf32: split-K needs the atomic epilogue");
     HB_REQUIRE(!d->b_mn_major || d->N > 64, "hb_gemm_tf32: MN-major B needs N > 64 (32-wide TMA boxes per 128-byte swizzle row)");
-    cudaStream_t st = (cudaStream_t)stream;
     // tile width: the widest UMMA N that does not waste more than half a tile ...
     if (d->N <= 16) return dispatch_epi<16>(d, st);
     if (d->N <= 64) return dispatch_epi<64>(d, st);
@@ -625,4 +705,20 @@ extern "C" int hb_gemm_tf32(const hb_gemm_desc *d, void *stream) {
         if (c128 < c256) return dispatch_epi<128>(d, st);
     }
     return dispatch_epi<256>(d, st);
+}
+}  // namespace
+
+extern "C" int64_t hb_gemm_workspace_floats(const hb_gemm_desc *d) {
+    if (!d || d->precision != HB_GEMM_3XTF32) return 0;
+    return split3_floats(d->M, d->K, d->a_mn_major != 0) + split3_floats(d->N, d->K, d->b_mn_major != 0);
+}
+
+extern "C" int hb_gemm_tf32(const hb_gemm_desc *d, void *stream) {
+    HB_REQUIRE(d, "hb_gemm_tf32: null descriptor");
+    HB_REQUIRE(d->precision == HB_GEMM_TF32 || d->precision == HB_GEMM_3XTF32, "hb_gemm_tf32: unknown precision %d", d->precision);
+    if (d->precision == HB_GEMM_3XTF32) {
+        HB_REQUIRE(d->A && d->B && d->D && d->M > 0 && d->N > 0 && d->K > 0, "hb_gemm_tf32: null operand / empty problem");
+        return gemm_3xtf32(d, (cudaStream_t)stream);
+    }
+    return gemm_tf32_dispatch(d, (cudaStream_t)stream);
 }

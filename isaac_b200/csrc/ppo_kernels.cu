@@ -443,92 +443,133 @@ act_head_kernel(const float *__restrict__ mu, int ld_mu, const float *__restrict
     logp[i] = lp;
 }
 
-__global__ void __launch_bounds__(256)
-grad_sumsq_kernel(const float *__restrict__ g, long long n, double *__restrict__ out) {
-    __shared__ double s[8];
+// ------------------------------------------------------------------------------------------------------------
+// clip_grad_norm_ + torch.optim.Adam.step (single-tensor semantics, no amsgrad / weight decay) + optimizer.zero_grad +
+// the adaptive-KL learning-rate rule (ppo.py:136-148,171-174) + update()'s running loss sums (:176-178) in ONE launch.
+// Every scalar of the optimizer (learning rate, Adam's step count, gradient norm, the minibatch's loss sums) lives in
+// hb_optim_state in device memory, so the launch takes no per-step host values and a captured minibatch step can be
+// replayed for every step of every update.
+//   phase 1  each thread loads its gradient vectors ONCE (kept in registers) and the grid reduces their sum of squares;
+//   barrier  ticket in hb_optim_state (cooperative launch: all blocks are co-resident);
+//   phase 2  every block derives clip coefficient / bias corrections / new learning rate from the same device values,
+//            checks in a second time, and applies Adam; the LAST block to check in (everyone has read the old values by
+//            then) publishes the new learning rate, folds the loss sums, bumps the step count and re-arms the state.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int OPT_THREADS = 256;
+constexpr int OPT_REGV = 8;          // float4 gradient vectors a thread carries from phase 1 to phase 2
+
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__global__ void __launch_bounds__(OPT_THREADS)
+optimizer_step_kernel(float *__restrict__ p, float *__restrict__ g, float *__restrict__ m, float *__restrict__ v, long long n,
+                      const hb_adam_params ap, hb_optim_state *__restrict__ st) {
+    __shared__ double s_red[OPT_THREADS / 32];
+    __shared__ float s_scal[3];                                    // clip scale, step size, sqrt(bias_correction2)
+    const long long nvec = n >> 2;
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, stride = (long long)gridDim.x * blockDim.x;
+    const float4 *g4 = reinterpret_cast<const float4 *>(g);
+    float4 gv[OPT_REGV];
     double acc = 0.0;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        const double v = (double)g[i];
-        acc += v * v;
+#pragma unroll
+    for (int k = 0; k < OPT_REGV; ++k) {
+        const long long i = tid + k * stride;
+        gv[k] = (i < nvec) ? g4[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+        acc += ((double)gv[k].x * gv[k].x + (double)gv[k].y * gv[k].y) + ((double)gv[k].z * gv[k].z + (double)gv[k].w * gv[k].w);
     }
+    for (long long i = tid + OPT_REGV * stride; i < nvec; i += stride) {           // larger buffers: re-read in phase 2
+        const float4 x = g4[i];
+        acc += ((double)x.x * x.x + (double)x.y * x.y) + ((double)x.z * x.z + (double)x.w * x.w);
+    }
+    if (tid == 0)
+        for (long long i = nvec << 2; i < n; ++i) acc += (double)g[i] * g[i];
     acc = warp_sum(acc);
-    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = acc;
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = acc;
     __syncthreads();
+    unsigned long long *ticket = reinterpret_cast<unsigned long long *>(&st->ticket);
     if (threadIdx.x == 0) {
         double t = 0.0;
-        for (int w = 0; w < 8; ++w) t += s[w];
-        atomicAdd(out, t);
-    }
-}
-
-// torch.optim.Adam (single-tensor semantics, no amsgrad / weight decay) after clip_grad_norm_.
-__global__ void __launch_bounds__(256)
-adam_kernel(float *__restrict__ p, float *__restrict__ g, float *__restrict__ m, float *__restrict__ v, long long n,
-            hb_adam_params ap, const double *__restrict__ sumsq, const double *__restrict__ kl_stats,
-            double *__restrict__ lr_io) {
-    // adaptive learning rate from the KL mean of this minibatch (ppo.py:140-148); every thread derives the
-    // same value from the same inputs, thread 0 of block 0 stores it after everyone has read the old one
-    double lr = *lr_io;
-    if (ap.adaptive) {
-        const double kl = kl_stats[2] / (double)ap.kl_count;
-        if (kl > ap.desired_kl * 2.0) lr = fmax(1e-5, lr / 1.5);
-        else if (kl < ap.desired_kl / 2.0 && kl > 0.0) lr = fmin(1e-2, lr * 1.5);
-    }
-    float scale = 1.0f;
-    if (ap.max_grad_norm > 0.0f) {            // clip_grad_norm_: coef = max_norm / (total_norm + 1e-6), clamped to 1
-        const float total = (float)sqrt(*sumsq);
-        const float coef = ap.max_grad_norm / (total + 1e-6f);
-        scale = coef < 1.0f ? coef : 1.0f;
-    }
-    const float step_size = (float)(lr / ap.bias_correction1);
-    const float bc2_sqrt = (float)sqrt(ap.bias_correction2);
-    auto update = [&](float &pi, float &gi_io, float &mi, float &vi) {
-        const float gi = gi_io * scale;
-        mi = mi + (gi - mi) * (1.0f - ap.beta1);                    // exp_avg.lerp_(grad, 1 - beta1)
-        vi = vi * ap.beta2 + (1.0f - ap.beta2) * gi * gi;           // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
-        const float denom = sqrtf(vi) / bc2_sqrt + ap.eps;
-        pi = pi - step_size * (mi / denom);                         // param.addcdiv_(exp_avg, denom, value=-step_size)
-        gi_io = 0.0f;                                               // optimizer.zero_grad() for the next minibatch
-    };
-    // four parameters per thread (the scalar preamble above is per thread); the flat buffers are 16-byte aligned
-    const long long i4 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    if (i4 + 3 < n) {
-        float4 p4 = *reinterpret_cast<float4 *>(p + i4), g4 = *reinterpret_cast<float4 *>(g + i4);
-        float4 m4 = *reinterpret_cast<float4 *>(m + i4), v4 = *reinterpret_cast<float4 *>(v + i4);
-        update(p4.x, g4.x, m4.x, v4.x), update(p4.y, g4.y, m4.y, v4.y);
-        update(p4.z, g4.z, m4.z, v4.z), update(p4.w, g4.w, m4.w, v4.w);
-        *reinterpret_cast<float4 *>(p + i4) = p4, *reinterpret_cast<float4 *>(g + i4) = g4;
-        *reinterpret_cast<float4 *>(m + i4) = m4, *reinterpret_cast<float4 *>(v + i4) = v4;
-    } else {
-        for (long long i = i4; i < n; ++i) update(p[i], g[i], m[i], v[i]);
-    }
-}
-
-// After every block of adam_kernel has read the old learning rate, the KL sum and the gradient norm: publish the new
-// rate (adaptive schedule), fold this minibatch's loss sums into the running totals of update() (ppo.py:176-178) and
-// re-arm the per-minibatch accumulators, so the host issues no tiny torch kernels between optimizer steps.
-__global__ void step_epilogue_kernel(hb_adam_params ap, double *__restrict__ kl_stats, double *__restrict__ lr_io,
-                                     double *__restrict__ grad_sumsq, double *__restrict__ loss_acc) {
-    if (ap.adaptive) {
-        double lr = *lr_io;
-        const double kl = kl_stats[2] / (double)ap.kl_count;
-        if (kl > ap.desired_kl * 2.0) lr = fmax(1e-5, lr / 1.5);
-        else if (kl < ap.desired_kl / 2.0 && kl > 0.0) lr = fmin(1e-2, lr * 1.5);
-        *lr_io = lr;
-    }
-    if (loss_acc) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) loss_acc[k] += kl_stats[k], kl_stats[k] = 0.0;
-        if (grad_sumsq) *grad_sumsq = 0.0;
+        for (int w = 0; w < OPT_THREADS / 32; ++w) t += s_red[w];
+        atomicAdd(&st->grad_sumsq, t);
+        __threadfence();
+        atomicAdd(ticket, 1ull);
+        while (ld_acquire_u64(ticket) < (unsigned long long)gridDim.x) { }      // ---- grid barrier ----
+        const volatile hb_optim_state *sv = st;
+        double lr = sv->lr;
+        const double kl = sv->stats[2] / (double)ap.kl_count;
+        if (ap.adaptive) {                                          // ppo.py:140-148
+            if (kl > ap.desired_kl * 2.0) lr = fmax(1e-5, lr / 1.5);
+            else if (kl < ap.desired_kl / 2.0 && kl > 0.0) lr = fmin(1e-2, lr * 1.5);
+        }
+        float scale = 1.0f;
+        if (ap.max_grad_norm > 0.0f) {          // clip_grad_norm_: coef = max_norm / (total_norm + 1e-6), clamped to 1
+            const float total = (float)sqrt(sv->grad_sumsq);
+            const float coef = ap.max_grad_norm / (total + 1e-6f);
+            scale = coef < 1.0f ? coef : 1.0f;
+        }
+        const long long t_adam = sv->step + 1;
+        const double bc1 = 1.0 - pow(ap.beta1, (double)t_adam), bc2 = 1.0 - pow(ap.beta2, (double)t_adam);
+        s_scal[0] = scale, s_scal[1] = (float)(lr / bc1), s_scal[2] = (float)sqrt(bc2);
+        __threadfence();
+        const unsigned long long arrived = atomicAdd(ticket, 1ull);
+        if (arrived == 2ull * gridDim.x - 1ull) {                   // every block has read the old state: publish the new one
+            const long long idx = st->steps_in_update;
+            if (idx >= 0 && idx < HB_OPT_TRACE_MAX) st->trace[2 * idx] = kl, st->trace[2 * idx + 1] = lr;
+            st->steps_in_update = idx + 1;
+            st->lr = lr;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) st->loss_acc[k] += st->stats[k], st->stats[k] = 0.0;
+            st->grad_sumsq = 0.0;
+            st->step = t_adam;
+            __threadfence();
+            *ticket = 0ull;
+        }
     }
+    __syncthreads();
+    const float scale = s_scal[0], step_size = s_scal[1], bc2_sqrt = s_scal[2];
+    const float w1 = (float)(1.0 - ap.beta1), b2 = (float)ap.beta2, w2 = (float)(1.0 - ap.beta2), eps = (float)ap.eps;
+    auto update = [&](float &pi, float gi, float &mi, float &vi) {
+        gi = gi * scale;
+        mi = mi + (gi - mi) * w1;                                   // exp_avg.lerp_(grad, 1 - beta1)
+        vi = vi * b2 + w2 * (gi * gi);                              // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
+        const float denom = sqrtf(vi) / bc2_sqrt + eps;
+        pi = pi - step_size * (mi / denom);                         // param.addcdiv_(exp_avg, denom, value=-step_size)
+    };
+    auto update4 = [&](long long i, const float4 &gq) {
+        float4 p4 = *reinterpret_cast<float4 *>(p + 4 * i), m4 = *reinterpret_cast<float4 *>(m + 4 * i);
+        float4 v4 = *reinterpret_cast<float4 *>(v + 4 * i);
+        update(p4.x, gq.x, m4.x, v4.x), update(p4.y, gq.y, m4.y, v4.y);
+        update(p4.z, gq.z, m4.z, v4.z), update(p4.w, gq.w, m4.w, v4.w);
+        *reinterpret_cast<float4 *>(p + 4 * i) = p4, *reinterpret_cast<float4 *>(m + 4 * i) = m4;
+        *reinterpret_cast<float4 *>(v + 4 * i) = v4;
+        *reinterpret_cast<float4 *>(g + 4 * i) = make_float4(0.f, 0.f, 0.f, 0.f);      // optimizer.zero_grad()
+    };
+#pragma unroll
+    for (int k = 0; k < OPT_REGV; ++k) {
+        const long long i = tid + k * stride;
+        if (i < nvec) update4(i, gv[k]);
+    }
+    for (long long i = tid + OPT_REGV * stride; i < nvec; i += stride) update4(i, g4[i]);
+    if (tid == 0)
+        for (long long i = nvec << 2; i < n; ++i) {
+            update(p[i], g[i], m[i], v[i]);
+            g[i] = 0.0f;
+        }
 }
 
-// N(0,1) draws for the action sample of PPO.act (ppo.py:93, Normal.sample()): Philox4x32-10 keyed by the seed, counter =
-// (quad index, a domain tag, the call counter), Box-Muller on the four words.  state[0] = call counter, state[1] = ticket:
-// every block reads the counter first, the last block to finish advances it - the launch can sit in a replayed graph.
+// N(0,1) draws for the action sample of PPO.act (ppo.py:93, Normal.sample()): Philox4x32-10 keyed by state[2], counter =
+// (quad index, a domain tag, the call counter), Box-Muller on the four words.  state[0] = call counter, state[1] = ticket,
+// state[2] = key - all in device memory: every block reads counter and key first, the last block to finish advances the
+// counter, so the launch can sit in a replayed graph, draw fresh numbers every replay and follow a re-seed.
 __global__ void __launch_bounds__(256)
-draw_normal_kernel(float *__restrict__ out, long long count, uint32_t k0, uint32_t k1, unsigned long long *__restrict__ state) {
+draw_normal_kernel(float *__restrict__ out, long long count, unsigned long long *__restrict__ state) {
     const unsigned long long call = *reinterpret_cast<volatile unsigned long long *>(state);
+    const unsigned long long key = *reinterpret_cast<volatile unsigned long long *>(state + 2);
+    const uint32_t k0 = (uint32_t)key, k1 = (uint32_t)(key >> 32);
     const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (q * 4 < count) {
         const uint4 x = hb::philox4x32_10((uint32_t)q, 0x50504F00u ^ (uint32_t)(q >> 32), (uint32_t)call, (uint32_t)(call >> 32), k0, k1);
@@ -617,11 +658,11 @@ int hb_ppo_head_fused(const float *h3_actor, int32_t ld_ha, const float *h3_crit
     return HB_OK;
 }
 
-int hb_ppo_draw_normal(float *out, int64_t count, uint64_t seed, uint64_t *state, void *stream) {
+int hb_ppo_draw_normal(float *out, int64_t count, uint64_t *state, void *stream) {
     HB_REQUIRE(out && state && count > 0, "hb_ppo_draw_normal: bad arguments");
     const long long quads = (count + 3) / 4;
     draw_normal_kernel<<<(unsigned)((quads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-        out, (long long)count, (uint32_t)seed, (uint32_t)(seed >> 32), reinterpret_cast<unsigned long long *>(state));
+        out, (long long)count, reinterpret_cast<unsigned long long *>(state));
     HB_CHECK_LAUNCH("draw_normal_kernel");
     return HB_OK;
 }
@@ -662,29 +703,24 @@ int hb_ppo_record_step(const float *rewards, const uint8_t *dones, const float *
     return HB_OK;
 }
 
-int hb_grad_sumsq(const float *grads, int64_t n, double *grad_sumsq, void *stream) {
-    HB_REQUIRE(grads && grad_sumsq && n > 0, "hb_grad_sumsq: bad arguments");
-    const int blocks = (int)((n + 256 * 8 - 1) / (256 * 8));
-    grad_sumsq_kernel<<<blocks < 1184 ? blocks : 1184, 256, 0, (cudaStream_t)stream>>>(grads, n, grad_sumsq);
-    HB_CHECK_LAUNCH("grad_sumsq_kernel");
-    return HB_OK;
-}
-
-int hb_adam_step(float *params, float *grads, float *exp_avg, float *exp_avg_sq, int64_t n, const hb_adam_params *ap,
-                 double *grad_sumsq, double *kl_stats, double *lr_io, double *loss_acc, void *stream) {
-    HB_REQUIRE(params && grads && exp_avg && exp_avg_sq && ap && lr_io && n > 0, "hb_adam_step: bad arguments");
-    HB_REQUIRE(ap->max_grad_norm <= 0.0f || grad_sumsq, "hb_adam_step: clipping needs grad_sumsq");
-    HB_REQUIRE(!ap->adaptive || (kl_stats && ap->kl_count > 0), "hb_adam_step: adaptive schedule needs kl_stats");
-    HB_REQUIRE(hb::aligned16(params) && hb::aligned16(grads) && hb::aligned16(exp_avg) && hb::aligned16(exp_avg_sq),
-               "hb_adam_step: 16-byte aligned buffers");
-    adam_kernel<<<(unsigned)((n + 1023) / 1024), 256, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, n, *ap,
-                                                                             grad_sumsq, kl_stats, lr_io);
-    HB_CHECK_LAUNCH("adam_kernel");
-    HB_REQUIRE(!loss_acc || kl_stats, "hb_adam_step: loss_acc needs the per-minibatch sums");
-    if (ap->adaptive || loss_acc) {
-        step_epilogue_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(*ap, kl_stats, lr_io, grad_sumsq, loss_acc);
-        HB_CHECK_LAUNCH("step_epilogue_kernel");
-    }
+int hb_optimizer_step(float *params, float *grads, float *exp_avg, float *exp_avg_sq, int64_t n, const hb_adam_params *ap,
+                      hb_optim_state *state, void *stream) {
+    HB_REQUIRE(params && grads && exp_avg && exp_avg_sq && ap && state && n > 0, "hb_optimizer_step: bad arguments");
+    HB_REQUIRE(!ap->adaptive || ap->kl_count > 0, "hb_optimizer_step: adaptive schedule needs kl_count");
+    HB_REQUIRE(hb::aligned16(params) && hb::aligned16(grads) && hb::aligned16(exp_avg) && hb::aligned16(exp_avg_sq) &&
+                   (reinterpret_cast<uintptr_t>(state) & 7u) == 0, "hb_optimizer_step: 16-byte aligned buffers");
+    // all blocks wait on one another: the grid must be co-resident (cooperative launch), two blocks per SM at most
+    const long long want = ((n >> 2) + OPT_THREADS - 1) / OPT_THREADS;
+    const long long cap = 2ll * hb::sm_count();
+    const unsigned grid = (unsigned)(want < 1 ? 1 : (want < cap ? want : cap));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid), cfg.blockDim = dim3(OPT_THREADS), cfg.dynamicSmemBytes = 0, cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeCooperative;
+    at[0].val.cooperative = 1;
+    cfg.attrs = at, cfg.numAttrs = 1;
+    HB_CUDA(cudaLaunchKernelEx(&cfg, optimizer_step_kernel, params, grads, exp_avg, exp_avg_sq, (long long)n, *ap, state));
+    HB_CHECK_LAUNCH("optimizer_step_kernel");
     return HB_OK;
 }
 

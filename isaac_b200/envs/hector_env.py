@@ -81,8 +81,8 @@ def build_env_params(cfg, num_envs: int, num_bodies: int, body_names, dof_names,
     p.num_single_obs, p.frame_stack = cfg.env.num_single_obs, cfg.env.frame_stack
     p.num_single_priv, p.c_frame_stack = cfg.env.single_num_privileged_obs, cfg.env.c_frame_stack
     # rows at a 16-byte pitch: the observation buffers can then be rollout-storage slots and TMA operands
-    p.obs_ld = (p.num_single_obs * p.frame_stack + 3) // 4 * 4
-    p.priv_ld = (p.num_single_priv * p.c_frame_stack + 3) // 4 * 4
+    p.obs_ld = (p.num_single_obs * p.frame_stack + 1 + 3) // 4 * 4          # pad4(width + 1), like RolloutStorage
+    p.priv_ld = (p.num_single_priv * p.c_frame_stack + 1 + 3) // 4 * 4
     feet = _find(body_names, [cfg.asset.foot_name])
     knees = _find(body_names, [cfg.asset.knee_name])
     term = _find(body_names, cfg.asset.terminate_after_contacts_on)
@@ -274,8 +274,10 @@ class HectorFreeEnvB200:
         self._pending_event: Optional[torch.cuda.Event] = None
         self._graphs = None
         self._injected = initial_noise      # draws consumed by the constructor's reset_idx(all)
-        self._rng_seed = int(getattr(cfg, "seed", 1)) & 0xFFFFFFFFFFFFFFFF
-        self._rng_counter = torch.zeros(1, dtype=torch.int64, device=dev)
+        # device generator state {step counter, key}: both in device memory, so captured step graphs follow seed()
+        self._rng_state = torch.zeros(2, dtype=torch.int64, device=dev)
+        self._rng_counter = self._rng_state[:1]
+        self.seed(int(getattr(cfg, "seed", 1)))
         self._b = EnvBuffers()
         self._nz = EnvNoise()
         self._bind_buffers()
@@ -347,7 +349,7 @@ class HectorFreeEnvB200:
 
     def _draw_noise(self, push: bool):
         """Bind the draws of the next launch sequence: the injected tape if there is one, otherwise the device
-        generator (Philox keyed by `self._rng_seed`, counter in `self._rng_counter`): the tensors the reference
+        generator (Philox; key and step counter in `self._rng_state`): the tensors the reference
         draws with torch.rand / randn_like (hector_env.py:166,168,241; legged_robot.py:327-332,366,384) are never
         materialised."""
         nz = self._nz
@@ -363,13 +365,17 @@ class HectorFreeEnvB200:
 
     def _bind_device_rng(self, nz):
         nz.u_delay = nz.z_action = nz.u_cmd = nz.u_push = nz.u_reset = nz.z_obs = None
-        nz.rng_counter, nz.rng_seed = self._rng_counter.data_ptr(), self._rng_seed
+        nz.rng_counter = self._rng_state.data_ptr()
 
     def seed(self, seed: int) -> None:
-        """Seed of the device generator (the reference seeds torch globally, helpers.py:95-106)."""
+        """Seed of the device generator (the reference seeds torch globally, helpers.py:95-106).  Key and counter are
+        device-resident: step graphs captured earlier draw from the new key on their next replay.  Data-parallel
+        shards must differ: seed each rank with `cfg.seed + rank` (isaac_b200.parallel.rank_seed)."""
         self._rng_seed = int(seed) & 0xFFFFFFFFFFFFFFFF
-        self._rng_counter.zero_()
-        self._nz.u_reset = self._nz.rng_counter = None
+        signed = self._rng_seed - (1 << 64) if self._rng_seed >= (1 << 63) else self._rng_seed
+        self._rng_state.copy_(torch.tensor([0, signed], dtype=torch.int64), non_blocking=False)
+        if hasattr(self, "_nz"):
+            self._nz.u_reset = self._nz.rng_counter = None
 
     # ------------------------------------------------------------------ the hot path
     def step(self, actions: torch.Tensor):

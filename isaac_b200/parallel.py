@@ -64,15 +64,32 @@ def broadcast_parameters(actor_critic, src: int = 0, group=None) -> None:
     dist.broadcast(actor_critic.flat, src=src, group=group)
 
 
-def attach_data_parallel(alg, group=None):
-    """Turn a single-GPU `PPO` into one data-parallel replica (call after init_storage)."""
+_GOLDEN = 0x9E3779B97F4A7C15
+
+
+def rank_seed(base: int, rank: int) -> int:
+    """A distinct 64-bit generator key per rank (rank 0 keeps `base`): replicas that drew from the same key would
+    sample identical action noise, observation noise, command resamples and reset poses for env i of every shard, and
+    the all-reduced gradient would carry 1/G of the intended information."""
+    return (int(base) ^ ((int(rank) * _GOLDEN) & 0xFFFFFFFFFFFFFFFF)) & 0xFFFFFFFFFFFFFFFF
+
+
+def attach_data_parallel(alg, group=None, env=None):
+    """Turn a single-GPU `PPO` into one data-parallel replica (call after init_storage).  The action-sample generator
+    of the replica is re-keyed with `rank_seed`; pass the replica's env as well (or call `env.seed(rank_seed(cfg.seed,
+    rank))` yourself) so that its in-kernel draws differ between shards too."""
     if not dist.is_initialized():
         raise RuntimeError("torch.distributed is not initialised (launch with torchrun)")
     alg.world_size = dist.get_world_size(group)
+    rank = dist.get_rank(group)
     alg.grad_allreduce = GradReducer(group)
     if alg.storage is not None:
         alg.storage.reduce_stats = AdvantageStatsReducer(group)
     broadcast_parameters(alg.actor_critic, 0, group)
+    if hasattr(alg, "seed") and hasattr(alg, "_eps_seed"):
+        alg.seed(rank_seed(alg._eps_seed, rank))
+    if env is not None:
+        env.seed(rank_seed(env._rng_seed, rank))
     return alg
 
 

@@ -29,9 +29,16 @@ GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
 
 ENV_CASE = dict(n=32, steps=40, seed=20261018, fall_prob=0.01, step_counter0=393)
 ENV_EP0 = [2395, 2399, 2400, 795, 798, 799, 1599, 0]       # forces time-outs and command resampling
-PPO_CASE = dict(n=16, t=8, seed=11, param_seed=3)
+# the action-delay branch of HectorFreeEnv.step (hector_env.py:166-167) is dead at the shipped action_delay = 0.0: a
+# second, small case runs the reference with a non-zero delay
+DELAY_CASE = dict(n=24, steps=8, seed=424242, fall_prob=0.05, action_delay=0.3)
+# BASELINE configs[0]: 64 envs, num_steps_per_env = 24, 5 epochs x 4 minibatches.  Seed and learning rate are chosen
+# so that every mean KL of the adaptive run stays >= 4.9e-3 away from the schedule's thresholds (0.005 / 0.02): the rule
+# is a discontinuous function of that scalar, and the case exercises all of it - one x1.5 step, fourteen /1.5 steps and
+# the 1e-5 floor (ppo.py:136-148).
+PPO_CASE = dict(n=64, t=24, seed=11, param_seed=3)
 PPO_ALG = dict(value_loss_coef=1.0, use_clipped_value_loss=True, clip_param=0.2, entropy_coef=0.001,
-               num_learning_epochs=2, num_mini_batches=4, learning_rate=1e-3, schedule="adaptive",
+               num_learning_epochs=5, num_mini_batches=4, learning_rate=2e-3, schedule="adaptive",
                gamma=0.994, lam=0.9, desired_kl=0.01, max_grad_norm=1.0)
 PPO_POLICY = dict(init_noise_std=1.0, actor_hidden_dims=[512, 256, 128], critic_hidden_dims=[768, 256, 128])
 
@@ -79,13 +86,23 @@ def record_env_step(rec, env_like, out, root_states, dof_state):
         rec.setdefault(k, []).append(v.numpy().astype(np.uint8 if v.dtype == torch.bool else v.numpy().dtype).copy())
 
 
-def make_env_golden():
+def delay_golden_tape():
+    c = DELAY_CASE
+    return make_tape(c["n"], c["steps"], seed=c["seed"], fall_prob=c["fall_prob"], randomize_gains=True)
+
+
+def delay_cfg(cfg):
+    """The config edit of the action-delay case, for the reference's and for this repo's HectorCfg alike."""
+    cfg.domain_rand.action_delay = DELAY_CASE["action_delay"]
+    return cfg
+
+
+def _run_reference_env(tape, steps, step_counter0, configure=None):
     from oracle.ref_harness import ReferenceEnv
-    tape = env_golden_tape()
-    ref = ReferenceEnv(tape.statics, tape.physics[0], tape.noise[0])
-    ref.env.common_step_counter = ENV_CASE["step_counter0"]
+    ref = ReferenceEnv(tape.statics, tape.physics[0], tape.noise[0], configure=configure)
+    ref.env.common_step_counter = step_counter0
     rec = {"obs_init": ref.env.obs_buf.numpy().copy(), "priv_init": ref.env.privileged_obs_buf.numpy().copy()}
-    for t in range(1, ENV_CASE["steps"]):
+    for t in range(1, steps):
         out = ref.step(tape.physics[t], tape.noise[t])
         record_env_step(rec, ref.env, out, ref.root_states, ref.dof_state)
     final = {"obs_final": out[0].numpy().copy(), "priv_final": out[1].numpy().copy()}
@@ -93,11 +110,22 @@ def make_env_golden():
     arrays.update(final)
     arrays["input_checksum"] = tape_checksum(tape)
     arrays["reward_names"] = np.array(sorted(ref.env.episode_sums))
+    return arrays
+
+
+def make_env_golden():
+    arrays = _run_reference_env(env_golden_tape(), ENV_CASE["steps"], ENV_CASE["step_counter0"])
     path = os.path.join(GOLDEN_DIR, "env_rollout_ref.npz")
     np.savez_compressed(path, **arrays)
     n_reset = int(arrays["reset"].sum())
     print(f"wrote {path}: {os.path.getsize(path) / 1e6:.2f} MB, resets={n_reset}, "
           f"time_outs={int(arrays['time_outs'].sum())}")
+    arrays = _run_reference_env(delay_golden_tape(), DELAY_CASE["steps"], 0, configure=delay_cfg)
+    keep = ("actions", "torques", "obs_frame", "priv_frame", "rew", "reset", "last_actions", "last_last_actions",
+            "input_checksum")
+    path = os.path.join(GOLDEN_DIR, "env_action_delay_ref.npz")
+    np.savez_compressed(path, **{k: arrays[k] for k in keep})
+    print(f"wrote {path}: {os.path.getsize(path) / 1e6:.2f} MB (action_delay = {DELAY_CASE['action_delay']})")
 
 
 def golden_ppo_inputs():
@@ -155,6 +183,7 @@ def make_ppo_golden():
         losses = r.update(perm)
         arrays[f"{tag}/losses"] = np.array(losses, dtype=np.float64)
         arrays[f"{tag}/lr"] = np.array([r.alg.learning_rate], dtype=np.float64)
+        arrays[f"{tag}/lr_trace"] = np.array(r.lr_trace, dtype=np.float64)      # the rate each Adam step ran with
         for k, v in param_digest(dict(r.alg.actor_critic.state_dict())).items():
             arrays[f"{tag}/{k}"] = v
     path = os.path.join(GOLDEN_DIR, "ppo_update_ref.npz")

@@ -1,12 +1,14 @@
-"""TEST INFRASTRUCTURE — build-container only.
+"""TEST INFRASTRUCTURE.
 
-Runs the UNMODIFIED reference (`/root/reference/humanoid/...`) on the CPU so that
-(a) the oracle restatement in `oracle/hector_oracle.py` can be pinned against it and
-(b) golden vectors can be generated for `tests/golden/` (see `oracle/make_golden.py`).
+Runs the UNMODIFIED reference (`humanoid/...`) on the CPU so that
+(a) the oracle restatement in `oracle/hector_oracle.py` can be pinned against it,
+(b) golden vectors can be generated for `tests/golden/` (see `oracle/make_golden.py`) and
+(c) `bench.py --impl reference` can time the reference's own code on the GPU box's host cores.
 
-`/root/reference` does not exist on the GPU box, so nothing under `tests/ -m gpu`,
-`bench.py` or `__graft_entry__.smoke()` imports this module.  No reference source is
-copied into this repository: the reference is imported from where it lies.
+The reference is imported from where it lies: `/root/reference` in the build container,
+else the installed copy under `baseline/_ref` (written by `baseline/install_ref.sh`;
+git-ignored, it travels to the GPU box with the snapshot).  No reference source is part
+of this repository's history.  `reference_root()` is None when neither exists.
 
 How: the reference needs the closed third-party `isaacgym` package.
 We register stub modules for it — `isaacgym.torch_utils` is a restatement of the
@@ -30,7 +32,19 @@ from unittest.mock import MagicMock
 import numpy as np
 import torch
 
-REFERENCE_ROOT = "/root/reference"
+import os
+
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def reference_root():
+    for root in ("/root/reference", os.path.join(_REPO, "baseline", "_ref")):
+        if os.path.isfile(os.path.join(root, "humanoid", "envs", "custom", "hector_env.py")):
+            return root
+    return None
+
+
+REFERENCE_ROOT = reference_root()
 
 
 # --------------------------------------------------------------------------------------
@@ -96,6 +110,9 @@ def _normalize(x, eps: float = 1e-9):
 
 
 def install_isaacgym_stub():
+    if REFERENCE_ROOT is None:
+        raise ImportError("the reference is neither at /root/reference nor installed under baseline/_ref "
+                          "(run baseline/install_ref.sh in the build container)")
     if "isaacgym" in sys.modules:
         return
     tu = types.ModuleType("isaacgym.torch_utils")
@@ -140,7 +157,9 @@ EFFORT = [33.5, 33.5, 33.5, 67.0, 33.5] * 2     # robot.urdf:124,166,217,291,320
 class ReferenceEnv:
     """The reference HectorFreeEnv, stepping on supplied physics frames and noise tapes."""
 
-    def __init__(self, statics, first_frame, first_noise):
+    def __init__(self, statics, first_frame, first_noise, configure=None):
+        """`configure(cfg)`: optional edits of the reference's HectorCfg before the env parses it (e.g. a non-zero
+        `domain_rand.action_delay`)."""
         install_isaacgym_stub()
         from humanoid.envs.custom.hector_env import HectorFreeEnv
         from humanoid.envs.custom.hector_config import HectorCfg
@@ -152,6 +171,8 @@ class ReferenceEnv:
         e = HectorFreeEnv.__new__(HectorFreeEnv)
         cfg = HectorCfg()
         cfg.env.num_envs = n
+        if configure is not None:
+            configure(cfg)
         e.cfg = cfg
         e.sim_params = types.SimpleNamespace(dt=cfg.sim.dt)
         e.height_samples = None
@@ -356,6 +377,20 @@ class ReferencePPO:
             self.alg.compute_returns(last_critic_obs)
 
     def update(self, perm):
+        """Also records `lr_trace`: the learning rate of every optimizer step (read from the param group at the moment
+        the reference calls `optimizer.step()`), which pins the adaptive-KL schedule step by step."""
         self._perm, self._eps = perm, None
-        with self._patched():
-            return self.alg.update()
+        self.lr_trace = []
+        opt = self.alg.optimizer
+        real_step = opt.step
+
+        def step(*a, **kw):
+            self.lr_trace.append(float(opt.param_groups[0]["lr"]))
+            return real_step(*a, **kw)
+
+        opt.step = step
+        try:
+            with self._patched():
+                return self.alg.update()
+        finally:
+            opt.step = real_step

@@ -54,6 +54,7 @@ def main():
     nl = hi - lo
     alg = make_alg(dev, nl)
     attach_data_parallel(alg)
+    assert rank == 0 or alg._eps_seed != 0x9E3779B97F4A7C15, "replicas must draw from distinct keys"
     load(alg, R, lo, hi, dev)
     g = torch.Generator().manual_seed(100 + rank)
     local_perm = torch.randperm(T * nl, generator=g)
@@ -103,7 +104,7 @@ def main():
         print(f"worst relative update difference DP vs single: {worst:.3e}")
         # Adam divides by sqrt(v): elements with near-zero gradient amplify the (1e-5-level) summation-order
         # differences, so the updates agree to a few percent of the distance moved, not to 1e-5
-        ok = ok and worst < 0.1
+        ok = ok and worst < 0.07          # 2 x the 3.5e-2 measured on 2 B200s (profiles/r02_dp2_test.log)
     # replicas must stay bit-identical
     flat = alg.actor_critic.flat.clone()
     dist.broadcast(flat, 0)

@@ -30,6 +30,9 @@ def test_struct_mirrors_match(lib):
     assert lib.hb_sizeof_env_params() == ctypes.sizeof(_lib.EnvParams)
     assert lib.hb_sizeof_env_buffers() == ctypes.sizeof(_lib.EnvBuffers)
     assert lib.hb_sizeof_env_noise() == ctypes.sizeof(_lib.EnvNoise)
+    assert lib.hb_sizeof_gemm_desc() == ctypes.sizeof(_lib.GemmDesc)
+    assert lib.hb_sizeof_adam_params() == ctypes.sizeof(_lib.AdamParams)
+    assert lib.hb_sizeof_optim_state() == ctypes.sizeof(_lib.OptimState)
     assert lib.hb_abi_version() == _lib.HB_ABI_VERSION
 
 
@@ -49,7 +52,7 @@ def test_bad_arguments_return_status_not_crash(lib):
                                  None, None, None) == -1
     assert lib.hb_ppo_act_fused(None, 132, None, 132, None, None, 132, None, None, 8, None, None, None, None, None, None) == -1
     assert lib.hb_ppo_record_step(None, None, None, None, 0.99, 8, None, None, None) == -1
-    assert lib.hb_adam_step(None, None, None, None, 8, None, None, None, None, None, None) == -1
+    assert lib.hb_optimizer_step(None, None, None, None, 8, None, None, None) == -1
     d = _lib.GemmDesc()
     assert lib.hb_gemm_tf32(ctypes.byref(d), None) == -1 and b"null" in lib.hb_last_error()
     p, b = _lib.EnvParams(), _lib.EnvBuffers()

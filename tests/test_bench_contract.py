@@ -1,5 +1,6 @@
-"""bench.py contract on the CPU: the reference arm (the oracle port on the host cores) prints exactly one JSON line
-with the keys the driver reads.  The B200 arm needs a GPU and is exercised by the driver / gpurun."""
+"""bench.py contract on the CPU: the reference arm (the unmodified reference from baseline/_ref or /root/reference on the
+host cores; the oracle port only when neither is there) prints exactly one JSON line with the keys the driver reads.  The
+B200 arm needs a GPU and is exercised by the driver / gpurun."""
 import json
 import os
 import subprocess
@@ -18,9 +19,15 @@ def test_reference_arm_prints_one_json_line():
     assert d["impl"] == "reference" and d["metric"] == "env-steps/s" and d["unit"] == "env-steps/s"
     assert d["higher_is_better"] is True and d["scaling"] == "weak" and d["n_gpus"] == 1 and d["steps"] == 2 and d["warmup"] == 1
     assert d["value"] > 0 and d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
-    assert "workload" in d["config"] and d["gpu_launches"] == 0 and d["vs_baseline"] is None
+    from oracle.ref_harness import reference_root
+    assert d["cpu_baseline"]["kind"] == ("reference" if reference_root() else "port")
+    assert d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    sys.path.insert(0, ROOT)
+    import bench
+    assert d["config"]["workload"] == bench.workload_name(64), "both arms must name the workload identically"
+    assert d["gpu_launches"] == 0 and d["vs_baseline"] is None
     assert d["gae"]["value"] > 0 and d["ppo"]["value"] > 0
+    assert list(d)[-2:] == ["ppo", "e2e"], "PPO samples/s and e2e close the line"
 
 
 def test_reference_arm_other_ranks_exit_quietly():

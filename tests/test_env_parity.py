@@ -49,8 +49,8 @@ class _View:
         return getattr(self._env, k).cpu()
 
 
-def run_cuda_case(tape, dev, step_counter0=0):
-    env, phys = make_cuda_env(tape, dev)
+def run_cuda_case(tape, dev, step_counter0=0, cfg=None):
+    env, phys = make_cuda_env(tape, dev, cfg=cfg)
     env.common_step_counter = step_counter0
     rec = {"obs_init": to_np(env.obs_buf), "priv_init": to_np(env.privileged_obs_buf)}
     ids_per_step, out = [], None
@@ -116,6 +116,49 @@ def test_env_matches_oracle_ragged(lib, cuda_device, n, bulk):
         assert_equal(f"reset_env_ids@{t}", a, b)
     assert sum(len(i) for i in want_ids) > 0 or n < 8
     lib.hb_set_option(b"env_bulk_staging", 1)
+
+
+def test_env_action_delay_matches_reference_golden(lib, cuda_device):
+    """The action-delay branch of the step prologue (hector_env.py:166-167; action_delay = 0.3 instead of the shipped
+    0.0) against what the unmodified reference produced."""
+    g = dict(np.load(f"{GOLDEN}/env_action_delay_ref.npz"))
+    tape = mg.delay_golden_tape()
+    np.testing.assert_array_equal(mg.tape_checksum(tape), g["input_checksum"])
+    rec, _, env, _ = run_cuda_case(tape, cuda_device, 0, cfg=mg.delay_cfg(HectorCfg()))
+    assert abs(env._p.action_delay - 0.3) < 1e-7
+    assert_equal("reset", rec["reset"], g["reset"])
+    for k in ("actions", "torques", "obs_frame", "priv_frame", "rew", "last_actions", "last_last_actions"):
+        assert_close(k, rec[k], g[k])
+
+
+@pytest.mark.parametrize("n,steps,dr", [(4096, 4, False), (16384, 4, True), (65536, 3, False)],
+                         ids=["configs1-4096", "configs2-16384-dr-noise", "configs3-65536"])
+def test_env_matches_oracle_at_baseline_sizes(lib, cuda_device, n, steps, dr):
+    """BASELINE.json's shard sizes against the CPU oracle itself, every recorded tensor (same comparison as the ragged
+    cases): 4096 envs with the shipped constants (configs[1]); 16384 envs with per-env kp / kd, friction and mass
+    domain randomisation and injected observation / action noise (configs[2]); 65536 envs (configs[3]'s total)."""
+    from oracle.hector_oracle import OracleHectorEnv
+    tape = make_tape(n, steps, seed=5000 + n, fall_prob=0.01, randomize_gains=dr)
+    assert dr or tape.statics.p_gains.std(dim=0).max() == 0, "configs[1] / [3]: the shipped kp / kd constants"
+    special = torch.tensor([2399, 2400, 798, 799, 1599])
+    tape.statics.episode_length0[:5] = special
+    ora = OracleHectorEnv(HectorCfg(), tape.statics, tape.physics[0], tape.noise[0])
+    ora.common_step_counter = 398                      # the second step is a push step
+    want = {"obs_init": ora.obs_buf.numpy().copy(), "priv_init": ora.privileged_obs_buf.numpy().copy()}
+    want_ids, out = [], None
+    for t in range(1, steps):
+        out = ora.step(tape.physics[t], tape.noise[t])
+        mg.record_env_step(want, ora, out, ora.root_states, ora.dof_state)
+        want_ids.append(ora.last_reset_ids.numpy().astype(np.int32))
+    want = {k: (np.stack(v) if isinstance(v, list) else v) for k, v in want.items()}
+    want["obs_final"], want["priv_final"] = out[0].numpy(), out[1].numpy()
+    rec, ids, _, phys = run_cuda_case(tape, cuda_device, 398)
+    compare_records(rec, want)
+    for t, (a, b) in enumerate(zip(ids, want_ids)):
+        assert_equal(f"reset_env_ids@{t}", a, b)
+    assert sum(len(i) for i in want_ids) > n // 200 and phys.calls["set_root_state"] >= 1
+    if dr:
+        assert tape.statics.p_gains.std() > 1 and tape.statics.env_frictions.unique().numel() > 100
 
 
 def test_pd_torque_law(lib, cuda_device):

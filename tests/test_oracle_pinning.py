@@ -55,6 +55,26 @@ def test_env_oracle_matches_reference_golden():
     assert g["reset"].sum() > 20 and g["time_outs"].sum() > 0, "golden case must exercise resets and time-outs"
 
 
+def test_env_oracle_action_delay_matches_reference_golden():
+    """hector_env.py:166-167 with action_delay = 0.3 (dead code at the shipped 0.0): the reference's own outputs."""
+    g = np.load(f"{GOLDEN}/env_action_delay_ref.npz")
+    tape = mg.delay_golden_tape()
+    np.testing.assert_array_equal(mg.tape_checksum(tape), g["input_checksum"])
+    env = OracleHectorEnv(mg.delay_cfg(HectorCfg()), tape.statics, tape.physics[0], tape.noise[0])
+    rec = {}
+    for t in range(1, mg.DELAY_CASE["steps"]):
+        out = env.step(tape.physics[t], tape.noise[t])
+        mg.record_env_step(rec, env, out, env.root_states, env.dof_state)
+    assert_equal("reset", np.stack(rec["reset"]), g["reset"])
+    for k in ("actions", "torques", "obs_frame", "priv_frame", "rew", "last_actions", "last_last_actions"):
+        assert_close(k, np.stack(rec[k]), g[k], **TIGHT)
+    # the delay really mixes in the previous action: without it the recorded actions differ
+    plain = OracleHectorEnv(HectorCfg(), tape.statics, tape.physics[0], tape.noise[0])
+    for t in range(1, 3):          # step 1 blends with the zero actions of the constructor's reset, step 2 with step 1's
+        plain.step(tape.physics[t], tape.noise[t])
+    assert np.abs(plain.actions.numpy() - g["actions"][1]).max() > 1e-3
+
+
 def rec_names():
     env_scales = {k: v for k, v in vars(type(HectorCfg().rewards.scales)).items() if not k.startswith("_") and v != 0}
     return list(env_scales)

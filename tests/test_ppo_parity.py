@@ -1,16 +1,21 @@
 """PPO stage (act / process_env_step / compute_returns / update) on the B200 kernels against the CPU oracle
 (which is pinned bit-for-bit to the reference's rsl_rl fork).
 
-Tolerances.  The MLP GEMMs run on the tensor cores with TF32 operands (fp32 storage, fp32 accumulate): every
-product carries <= 2^-10 relative operand rounding, so
+Tolerances.  Two arithmetic modes (ActorCritic(precision=...), hb_gemm_desc.precision):
+"3xtf32" - hi/lo split operands, three partial products per GEMM in one fp32 accumulator: fp32-grade, compared with
+the oracle at the 1e-5 the north star quotes (forward rel-L2 < 1e-5, post-update weights rtol 1e-5 / atol lr * 1e-2).
+"tf32" (the fast path) - TF32 operands (fp32 storage, fp32 accumulate): every product carries <= 2^-10 relative
+operand rounding, so
   * forward quantities (mu, values, log-prob) agree to 4e-3 relative L2 (the tensor core truncates operands
     to TF32 and the bias compounds over four layers),
   * gradients agree to 8e-3 relative L2 per tensor for identical output gradients (the clipped surrogate is
     discontinuous in mu, so branch decisions are compared on the oracle's own mu),
   * post-update weights: Adam normalises the step to ~lr per element, so |w_cuda - w_ref| <= 2*lr*steps
     element-wise by construction; the test demands 0.25 of that bound in relative-L2 form per tensor.
-The adaptive-KL learning-rate rule is a discontinuous function of a reduced scalar (SURVEY.md §7 hard part 3):
-the fixed schedule is compared exactly, the adaptive one only when the KL is away from the thresholds."""
+The adaptive-KL learning-rate rule is a discontinuous function of a reduced scalar (SURVEY.md §7 hard part 3): the
+golden case (BASELINE configs[0]: 64 envs x 24 steps, 5 epochs x 4 minibatches) keeps every KL >= 4.9e-3 away from
+the thresholds, and the schedule is compared step by step - the learning rate of each of the 20 Adam steps must equal
+the unmodified reference's (golden `lr_trace`), the per-step KL the oracle's."""
 import ctypes as C
 
 import numpy as np
@@ -24,11 +29,12 @@ from oracle.ppo_oracle import OraclePPO, PARAM_ORDER, init_actor_critic_params, 
 pytestmark = pytest.mark.gpu
 
 
-def make_pair(dev, n, t, alg_cfg, seed=3):
+def make_pair(dev, n, t, alg_cfg, seed=3, precision="tf32"):
     from isaac_b200.algo.actor_critic import ActorCritic
     from isaac_b200.algo.ppo import PPO
     params = init_actor_critic_params(seed=seed)
-    ac = ActorCritic(615, 1050, 10, actor_hidden_dims=[512, 256, 128], critic_hidden_dims=[768, 256, 128], device=dev)
+    ac = ActorCritic(615, 1050, 10, actor_hidden_dims=[512, 256, 128], critic_hidden_dims=[768, 256, 128], device=dev,
+                     precision=precision)
     ac.load_state_dict(params)
     alg = PPO(ac, device=dev, **alg_cfg)
     alg.init_storage(n, t, [615], [1050], [10])
@@ -41,8 +47,9 @@ def rel_l2(a, b):
     return float((a - b).norm() / b.norm().clamp_min(1e-30))
 
 
-def test_state_dict_round_trip_and_forward(lib, cuda_device):
-    alg, ora, params = make_pair(cuda_device, 64, 4, dict(mg.PPO_ALG, schedule="fixed"))
+@pytest.mark.parametrize("precision,tol", [("tf32", 4e-3), ("3xtf32", 1e-5)])
+def test_state_dict_round_trip_and_forward(lib, cuda_device, precision, tol):
+    alg, ora, params = make_pair(cuda_device, 64, 4, dict(mg.PPO_ALG, schedule="fixed"), precision=precision)
     sd = alg.actor_critic.state_dict()
     assert list(sd) == PARAM_ORDER
     for k in PARAM_ORDER:
@@ -53,7 +60,10 @@ def test_state_dict_round_trip_and_forward(lib, cuda_device):
     v = alg.actor_critic.evaluate(cobs.to(cuda_device)).cpu()
     with torch.no_grad():
         w_mu, w_v = mlp(ora.params, "actor", obs), mlp(ora.params, "critic", cobs)
-    assert rel_l2(mu, w_mu) < 4e-3 and rel_l2(v, w_v) < 4e-3
+    assert rel_l2(mu, w_mu) < tol and rel_l2(v, w_v) < tol, (rel_l2(mu, w_mu), rel_l2(v, w_v))
+    if precision == "3xtf32":          # element-wise, at the north star's 1e-5 (atol = 1e-5 of the output scale)
+        assert_close("mu", mu.numpy(), w_mu.numpy(), rtol=1e-5, atol=1e-5 * float(w_mu.abs().max()))
+        assert_close("value", v.numpy(), w_v.numpy(), rtol=1e-5, atol=1e-5 * float(w_v.abs().max()))
 
 
 def run_rollout(alg, ora, dev, steps_inputs, last):
@@ -178,12 +188,15 @@ def test_minibatch_gradients_match_autograd(lib, cuda_device):
         assert (G[:, L.fan_in + 1:] == 0).all() and (G[L.fan_out:, :] == 0).all()
 
 
+@pytest.mark.parametrize("precision", ["tf32", "3xtf32"])
 @pytest.mark.parametrize("schedule", ["fixed", "adaptive"])
-def test_update_matches_reference_golden(lib, cuda_device, schedule):
-    """Full update() on the golden case: the reference's own post-update weights (digests) and losses."""
+def test_update_matches_reference_golden(lib, cuda_device, schedule, precision):
+    """Full update() on the golden case (BASELINE configs[0]): the reference's own post-update weights (digests), losses
+    and - for the adaptive schedule - the learning rate of every one of the 20 optimizer steps."""
     dev = cuda_device
     c = mg.PPO_CASE
-    alg, ora, params = make_pair(dev, c["n"], c["t"], dict(mg.PPO_ALG, schedule=schedule), seed=c["param_seed"])
+    alg, ora, params = make_pair(dev, c["n"], c["t"], dict(mg.PPO_ALG, schedule=schedule), seed=c["param_seed"],
+                                 precision=precision)
     steps, last, perm = mg.golden_ppo_inputs()
     run_rollout(alg, ora, dev, steps, last)
     for k in ("actions", "values", "returns", "advantages", "actions_log_prob", "mu", "sigma", "rewards"):
@@ -193,25 +206,108 @@ def test_update_matches_reference_golden(lib, cuda_device, schedule):
     w_v, w_s = ora.update(perm)
     g = np.load(f"{mg.GOLDEN_DIR}/ppo_update_ref.npz")
     np.testing.assert_allclose([w_v, w_s], g[f"{schedule}/losses"], rtol=1e-5)       # oracle == reference
-    assert abs(v_loss - w_v) < 5e-3 * max(1.0, abs(w_v)) and abs(s_loss - w_s) < 5e-3
+    np.testing.assert_allclose(ora.lr_trace, g[f"{schedule}/lr_trace"], rtol=1e-12)
+    loss_tol = 5e-3 if precision == "tf32" else 2e-5
+    assert abs(v_loss - w_v) < loss_tol * max(1.0, abs(w_v)) and abs(s_loss - w_s) < loss_tol, (v_loss, w_v, s_loss, w_s)
     sd = alg.actor_critic.state_dict()
     steps_taken = mg.PPO_ALG["num_learning_epochs"] * mg.PPO_ALG["num_mini_batches"]
+    assert len(alg.lr_trace) == steps_taken
     if schedule == "adaptive":
         kls = np.array(ora.kl_trace)
         margin = np.minimum(np.abs(kls - 0.02), np.abs(kls - 0.005)).min()
-        if margin < 2e-3:
-            pytest.skip(f"KL {kls} too close to a schedule threshold for a discontinuous comparison")
+        assert margin >= 3e-3, f"golden case drifted: KL {kls} within {margin:.1e} of a schedule threshold"
+        # the schedule, step by step: the rate each Adam step ran with == the unmodified reference's
+        np.testing.assert_allclose(alg.lr_trace, g["adaptive/lr_trace"], rtol=1e-12, atol=0)
+        np.testing.assert_allclose(alg.kl_trace, kls, rtol=5e-2 if precision == "tf32" else 1e-4, atol=1e-6)
         assert abs(alg.learning_rate - ora.learning_rate) < 1e-12 * max(1, ora.learning_rate) + 1e-15
         assert abs(alg.learning_rate - float(g["adaptive/lr"][0])) < 1e-12
+    else:
+        np.testing.assert_allclose(alg.lr_trace, [mg.PPO_ALG["learning_rate"]] * steps_taken, rtol=0, atol=0)
     lr_max = max(ora.lr_trace)
     for k in PARAM_ORDER:
         got, want, init = sd[k].cpu().double(), ora.params[k].detach().double(), params[k].double()
+        sample = torch.from_numpy(g[f"{schedule}/p/{k}/sample"]).double()
+        if precision == "3xtf32" and schedule == "fixed":
+            # fp32-grade arithmetic: the north star's tolerance on post-update weights
+            assert_close(k, got.numpy(), want.numpy(), rtol=1e-5, atol=lr_max * 1e-2)
+            assert_close(k + " (reference digest)", got.flatten()[::97].numpy(), sample.numpy(), rtol=1e-5, atol=lr_max * 1e-2)
+            continue
         moved = (want - init).abs().max().item()
         assert (got - want).abs().max().item() <= 2.0 * lr_max * steps_taken * 1.01 + 1e-9, k     # Adam bound
         err = float((got - want).norm() / (want - init).norm().clamp_min(1e-30))
-        assert err < 0.25, f"{k}: update direction error {err:.3f} (moved {moved:.2e})"
-        sample = torch.from_numpy(g[f"{schedule}/p/{k}/sample"]).double()
+        bound = 0.25 if precision == "tf32" else 0.02
+        assert err < bound, f"{k}: update direction error {err:.3f} (moved {moved:.2e})"
         assert float((got.flatten()[::97] - sample).abs().max()) <= 2.0 * lr_max * steps_taken * 1.01 + 1e-9
+
+
+def test_update_graph_replay_equals_eager(lib, cuda_device):
+    """update() replays one captured graph per minibatch index from the second update on (single GPU).  Two PPO
+    instances from the same weights and rollouts, one with graphs and one eager: same schedule trace, weights equal up to
+    the order of the split-K float atomics."""
+    dev = cuda_device
+    c = mg.PPO_CASE
+    cfg = dict(mg.PPO_ALG, schedule="adaptive", learning_rate=1e-4)
+    pair = [make_pair(dev, c["n"], c["t"], cfg, seed=c["param_seed"])[0] for _ in range(2)]
+    pair[1].graph_update = False
+    steps, last, perm = mg.golden_ppo_inputs()
+    g = torch.Generator().manual_seed(9)
+    for it in range(3):
+        perm_it = torch.randperm(c["n"] * c["t"], generator=g)
+        for alg in pair:
+            for obs, cobs, eps, rew, dones, tos in steps:
+                alg.injected_eps = eps.to(dev)
+                alg.act(obs.to(dev), cobs.to(dev))
+                alg.process_env_step(rew.to(dev), dones.to(dev), {"time_outs": tos.to(dev)})
+            alg.compute_returns(last.to(dev))
+            alg.injected_perm = perm_it
+            alg.update()
+        assert len(pair[0]._update_graphs) == (0 if it == 0 else cfg["num_mini_batches"])
+        np.testing.assert_allclose(pair[0].lr_trace, pair[1].lr_trace, rtol=1e-12)
+        np.testing.assert_allclose(pair[0].kl_trace, pair[1].kl_trace, rtol=1e-3, atol=1e-7)
+        assert pair[0]._step == pair[1]._step == 20 * (it + 1)
+        assert int(pair[0]._opt_i64[10].item()) == pair[0]._step, "device-side Adam step count"
+        torch.testing.assert_close(pair[0].actor_critic.flat, pair[1].actor_critic.flat, rtol=1e-3, atol=2e-5)
+
+
+def test_optimizer_step_matches_torch_adam(lib, cuda_device):
+    """hb_optimizer_step alone (clip_grad_norm_ + Adam + zero_grad + adaptive-KL rule, one cooperative launch) against
+    torch.nn.utils.clip_grad_norm_ + torch.optim.Adam on the same gradients, several steps, ragged length."""
+    from isaac_b200 import _lib
+    dev = cuda_device
+    n = 148 * 2 * 256 * 4 * 9 + 4 * 37 + 3      # more vectors than a thread keeps in registers, plus a ragged tail
+    g = torch.Generator().manual_seed(2)
+    p0 = torch.randn(n, generator=g)
+    ref_p = p0.clone().requires_grad_(True)
+    opt = torch.optim.Adam([ref_p], lr=1e-3)
+    p, m, v = p0.to(dev), torch.zeros(n, device=dev), torch.zeros(n, device=dev)
+    state = torch.zeros(_lib.OPTIM_STATE_DOUBLES, dtype=torch.float64, device=dev)
+    state[_lib.OPT_LR] = 1e-3
+    lr = 1e-3
+    for step in range(4):
+        grad = torch.randn(n, generator=g) * (0.01 if step % 2 else 1e-4)      # clipped and unclipped steps
+        kl_sum, count = (0.05 if step == 1 else 0.001) * 100, 100               # -> lr / 1.5 at step 1, * 1.5 otherwise
+        ref_p.grad = grad.clone()
+        kl = kl_sum / count
+        lr = max(1e-5, lr / 1.5) if kl > 0.02 else (min(1e-2, lr * 1.5) if 0 < kl < 0.005 else lr)
+        for grp in opt.param_groups:
+            grp["lr"] = lr
+        torch.nn.utils.clip_grad_norm_([ref_p], 1.0)
+        opt.step()
+        gd = grad.to(dev)
+        state[_lib.OPT_STATS + 2] = kl_sum
+        state[_lib.OPT_STATS] = 3.0
+        ap = _lib.AdamParams(0.9, 0.999, 1e-8, 1.0, 1, 0.01, count)
+        _lib.check(lib.hb_optimizer_step(p.data_ptr(), gd.data_ptr(), m.data_ptr(), v.data_ptr(), n, C.byref(ap),
+                                         state.data_ptr(), torch.cuda.current_stream(dev).cuda_stream), "hb_optimizer_step")
+        torch.cuda.synchronize()
+        assert (gd == 0).all(), "zero_grad"
+        h = state.cpu()
+        assert abs(h[_lib.OPT_LR].item() - lr) < 1e-15 and h[_lib.OPT_SUMSQ].item() == 0 and (h[_lib.OPT_STATS:_lib.OPT_STATS + 4] == 0).all()
+        assert h[_lib.OPT_LOSS_ACC].item() == 3.0 * (step + 1)
+        hi = state.view(torch.int64).cpu()
+        assert hi[_lib.OPT_STEP].item() == step + 1 and hi[_lib.OPT_STEPS_IN_UPDATE].item() == step + 1 and hi[_lib.OPT_TICKET].item() == 0
+        assert abs(h[_lib.OPT_TRACE + 2 * step].item() - kl) < 1e-12 and abs(h[_lib.OPT_TRACE + 2 * step + 1].item() - lr) < 1e-15
+        assert_close(f"params after step {step}", p.cpu().numpy(), ref_p.detach().numpy(), rtol=2e-6, atol=2e-7)
 
 
 def test_fused_head_matches_autograd_from_hidden(lib, cuda_device):
@@ -422,12 +518,12 @@ def test_library_normal_draws(lib, cuda_device):
     device-side call counter, bit-reproducible from (seed, counter), ragged counts and unaligned outputs in bounds."""
     dev = cuda_device
     n = 4096 * 10
-    state = torch.zeros(2, dtype=torch.int64, device=dev)
+    state = torch.tensor([0, 0, 1234], dtype=torch.int64, device=dev)      # {call counter, ticket, key}
     a, b, c = (torch.empty(n, device=dev) for _ in range(3))
     for out in (a, b):
-        assert lib.hb_ppo_draw_normal(out.data_ptr(), n, 1234, state.data_ptr(), None) == 0
+        assert lib.hb_ppo_draw_normal(out.data_ptr(), n, state.data_ptr(), None) == 0
     torch.cuda.synchronize()
-    assert state.tolist() == [2, 0], "two launches, ticket re-armed"
+    assert state.tolist() == [2, 0, 1234], "two launches, ticket re-armed"
     assert not torch.equal(a, b)
     for z in (a, b):
         assert abs(z.mean().item()) < 0.02 and abs(z.std().item() - 1.0) < 0.02
@@ -435,17 +531,17 @@ def test_library_normal_draws(lib, cuda_device):
         assert z.abs().max().item() < 6.5 and torch.isfinite(z).all()
     assert abs(torch.corrcoef(torch.stack((a, b)))[0, 1].item()) < 0.02                       # call to call
     assert abs(torch.corrcoef(torch.stack((a[:-1], a[1:])))[0, 1].item()) < 0.02               # neighbour to neighbour
-    state.zero_()
-    lib.hb_ppo_draw_normal(c.data_ptr(), n, 1234, state.data_ptr(), None)
+    state[:2] = 0
+    lib.hb_ppo_draw_normal(c.data_ptr(), n, state.data_ptr(), None)
     torch.cuda.synchronize()
     assert torch.equal(c, a), "same seed and counter, same numbers"
-    state.zero_()
-    lib.hb_ppo_draw_normal(c.data_ptr(), n, 99, state.data_ptr(), None)
+    state.copy_(torch.tensor([0, 0, 99]))
+    lib.hb_ppo_draw_normal(c.data_ptr(), n, state.data_ptr(), None)
     torch.cuda.synchronize()
     assert not torch.equal(c, a)
     # ragged count at an address that is only 4-byte aligned, inside guard sentinels
     raw = torch.full((64,), -7.0, device=dev)
-    state.zero_()
-    assert lib.hb_ppo_draw_normal(raw[9:].data_ptr(), 10, 1234, state.data_ptr(), None) == 0
+    state.copy_(torch.tensor([0, 0, 1234]))
+    assert lib.hb_ppo_draw_normal(raw[9:].data_ptr(), 10, state.data_ptr(), None) == 0
     torch.cuda.synchronize()
     assert (raw[:9] == -7.0).all() and (raw[19:] == -7.0).all() and torch.equal(raw[9:19], a[:10])
