@@ -546,8 +546,8 @@ def run_b200(args, rank, world):
     r_, v_ = torch.rand(T_GAE, n, 1, generator=g).to(dev), torch.randn(T_GAE, n, 1, generator=g).to(dev)
     d_, lv_ = (torch.rand(T_GAE, n, 1, generator=g) < 0.005).byte().to(dev), torch.randn(n, 1, generator=g).to(dev)
     ret_, adv_ = torch.empty_like(r_), torch.empty_like(r_)
-    gae_stats = torch.zeros(2, dtype=torch.float64, device=dev)
-    k_gae = time_launch(lambda st: gae_compute_returns(r_, v_, d_, lv_, ret_, adv_, 0.994, 0.9, stats=gae_stats) and None)
+    gae_compute_returns(r_, v_, d_, lv_, ret_, adv_, 0.994, 0.9)          # allocates the launch's scratch before capture
+    k_gae = time_launch(lambda st: gae_compute_returns(r_, v_, d_, lv_, ret_, adv_, 0.994, 0.9) and None)      # hb_gae_fused: one launch
     ppo = None if args.skip_ppo else bench_ppo(args, dev, n, world, rank, env, phys, phys_frames)
     clocks = sampler.summary()
 

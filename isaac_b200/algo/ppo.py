@@ -178,12 +178,15 @@ class PPO:
     def _draw_eps(self, n, st):
         """[n, num_actions] N(0,1) draws into the staging buffer of this batch size (one per size, never freed: captured
         act graphs address it) - the eps of Normal.sample(), actor_critic.py:116."""
-        na = self.actor_critic.num_actions
+        stage = self._eps_stage(n)
+        _lib.check(self._lib.hb_ppo_draw_normal(stage.data_ptr(), stage.numel(), self._eps_state.data_ptr(), st),
+                   "hb_ppo_draw_normal")
+        return stage
+
+    def _eps_stage(self, n):
         stage = self._act_stages.get(n)
         if stage is None:
-            stage = self._act_stages[n] = torch.zeros(n, na, device=self.device)
-        _lib.check(self._lib.hb_ppo_draw_normal(stage.data_ptr(), n * na, self._eps_state.data_ptr(), st),
-                   "hb_ppo_draw_normal")
+            stage = self._act_stages[n] = torch.zeros(n, self.actor_critic.num_actions, device=self.device)
         return stage
 
     def _slot(self, k):
@@ -291,7 +294,7 @@ class PPO:
                 main.wait_stream(side)
                 self._launch_act_head(e, h3a, h3c, eps, n, st)
 
-            self._draw_eps(n, torch.cuda.current_stream(dev).cuda_stream)        # allocates the staging buffer before capture
+            self._eps_stage(n)          # allocated before capture (and without consuming a draw)
             g = _lib.LaunchGraph(dev).record(launches)
             entry = self._act_graphs[e.xa_ptr] = (g, e, ws)       # keeps the slot views and the workspace alive
         entry[0].replay(torch.cuda.current_stream(self.device).cuda_stream)

@@ -19,11 +19,15 @@ def _pad4(n: int) -> int:
     return (n + 3) // 4 * 4
 
 
+_FUSED_SCRATCH = {}
+
+
 def gae_compute_returns(rewards, values, dones, last_values, returns, advantages, gamma, lam,
-                        stats: Optional[torch.Tensor] = None, reduce_stats=None):
+                        stats: Optional[torch.Tensor] = None, reduce_stats=None, fused: bool = True):
     """rollout_storage.py:122-136 on `[T,N,1]` (or `[T,N]`) CUDA tensors, in place into returns/advantages.
-    `reduce_stats(stats, count) -> count` lets a multi-GPU caller all-reduce (sum, sum sq) and the
-    sample count across ranks before the normalisation pass."""
+    Single GPU (no `reduce_stats`): ONE launch, `hb_gae_fused` (raw advantages stay in registers across a grid barrier on
+    their statistics).  `reduce_stats(stats, count) -> count` lets a multi-GPU caller all-reduce (sum, sum sq) and the
+    sample count across ranks between the two passes of the two-kernel form."""
     lib = _lib.load()
     T, N = rewards.shape[0], rewards.shape[1]
     for t in (rewards, values, dones, last_values, returns, advantages):
@@ -31,9 +35,17 @@ def gae_compute_returns(rewards, values, dones, last_values, returns, advantages
             raise ValueError("gae_compute_returns needs contiguous CUDA tensors")
     if dones.dtype not in (torch.uint8, torch.bool):
         raise TypeError("dones must be uint8/bool")
+    st = torch.cuda.current_stream(rewards.device).cuda_stream
+    if fused and reduce_stats is None and stats is None and T * N > 1:
+        scratch = _FUSED_SCRATCH.get(rewards.device)
+        if scratch is None:          # {sum, sum sq, ticket, -}: zeroed once, re-armed by every launch
+            scratch = _FUSED_SCRATCH[rewards.device] = torch.zeros(4, dtype=torch.float64, device=rewards.device)
+        _lib.check(lib.hb_gae_fused(rewards.data_ptr(), values.data_ptr(), dones.data_ptr(), last_values.data_ptr(),
+                                    returns.data_ptr(), advantages.data_ptr(), scratch.data_ptr(), T, N,
+                                    float(gamma), float(lam), st), "hb_gae_fused")
+        return returns, advantages
     if stats is None:
         stats = torch.empty(2, dtype=torch.float64, device=rewards.device)
-    st = torch.cuda.current_stream(rewards.device).cuda_stream
     _lib.check(lib.hb_gae_returns(rewards.data_ptr(), values.data_ptr(), dones.data_ptr(), last_values.data_ptr(),
                                   returns.data_ptr(), advantages.data_ptr(), stats.data_ptr(), T, N,
                                   float(gamma), float(lam), st), "hb_gae_returns")

@@ -193,6 +193,111 @@ gae_serial_kernel(const float *__restrict__ rewards, const float *__restrict__ v
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Single-GPU form: the whole of compute_returns in ONE launch.  One thread per env as above, but the T raw advantages
+// of the env stay in registers while the grid agrees on (sum, sum of squares): block reduction -> fp64 atomics -> ticket
+// barrier (cooperative launch: every block is resident) -> mean / unbiased std -> the normalised advantages are written
+// once.  Against memset + scan + normalise this drops two launches and the write + re-read of the raw advantages
+// (17 instead of 25 bytes per sample).  scratch = {sum, sum sq, ticket, -}: zero on entry, re-armed by the last block.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+template <int TMAX, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+gae_fused_kernel(const float *__restrict__ rewards, const float *__restrict__ values, const uint8_t *__restrict__ dones,
+                 const float *__restrict__ last_values, float *__restrict__ returns, float *__restrict__ advantages,
+                 double *__restrict__ scratch, int T, int N, float gamma, float lam) {
+    constexpr int CHUNK = 8;
+    static_assert(TMAX % CHUNK == 0, "whole chunks");
+    __shared__ double red[2][THREADS / 32 > 0 ? THREADS / 32 : 1];
+    __shared__ float s_norm[2];
+    const int e = blockIdx.x * THREADS + threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool ok = e < N;
+    float raw[TMAX];                         // advantages = returns - values of this env, t = 0 .. T-1
+    double s1 = 0.0, s2 = 0.0;
+    {
+        float r[CHUNK], v[CHUNK], nr[CHUNK], nv[CHUNK];
+        uint8_t d[CHUNK], nd[CHUNK];
+        auto load = [&](int c, float *rr, float *vv, uint8_t *dd) {          // steps c*CHUNK .. c*CHUNK + CHUNK - 1
+#pragma unroll
+            for (int u = 0; u < CHUNK; ++u) {
+                const int t = c * CHUNK + u;
+                rr[u] = vv[u] = 0.f, dd[u] = 0;
+                if (ok && t < T) {
+                    const size_t i = (size_t)t * N + e;
+                    rr[u] = rewards[i], vv[u] = values[i], dd[u] = dones[i];
+                }
+            }
+        };
+        float next_v = ok ? last_values[e] : 0.0f, adv = 0.0f;
+        load(TMAX / CHUNK - 1, r, v, d);
+#pragma unroll
+        for (int c = TMAX / CHUNK - 1; c >= 0; --c) {
+            if (c > 0) load(c - 1, nr, nv, nd);                                  // next chunk in flight
+#pragma unroll
+            for (int u = CHUNK - 1; u >= 0; --u) {
+                const int t = c * CHUNK + u;
+                raw[t] = 0.0f;
+                if (ok && t < T) {
+                    const float g = (1.0f - (float)d[u]) * gamma;
+                    const float delta = (r[u] + g * next_v) - v[u];
+                    adv = delta + (g * lam) * adv;
+                    const float ret = adv + v[u];
+                    raw[t] = ret - v[u];                                         // advantages = returns - values (:135)
+                    returns[(size_t)t * N + e] = ret;
+                    s1 += (double)raw[t];
+                    s2 += (double)raw[t] * (double)raw[t];
+                    next_v = v[u];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < CHUNK; ++u) r[u] = nr[u], v[u] = nv[u], d[u] = nd[u];
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    if (lane == 0) red[0][warp] = s1, red[1][warp] = s2;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0.0, q = 0.0;
+#pragma unroll
+        for (int w = 0; w < (THREADS / 32 > 0 ? THREADS / 32 : 1); ++w) a += red[0][w], q += red[1][w];
+        unsigned long long *ticket = reinterpret_cast<unsigned long long *>(scratch + 2);
+        atomicAdd(scratch, a);
+        atomicAdd(scratch + 1, q);
+        __threadfence();
+        atomicAdd(ticket, 1ull);
+        while (ld_acquire_u64(ticket) < (unsigned long long)gridDim.x) { }       // ---- grid barrier ----
+        const volatile double *sv = scratch;
+        const double n = (double)T * (double)N;
+        const double mean = sv[0] / n;
+        double var = (sv[1] - n * mean * mean) / (n - 1.0);                      // unbiased (rollout_storage.py:136)
+        if (var < 0.0) var = 0.0;
+        s_norm[0] = (float)mean, s_norm[1] = (float)sqrt(var) + 1e-8f;
+        __threadfence();
+        if (atomicAdd(ticket, 1ull) == 2ull * gridDim.x - 1ull) {                // every block has read: re-arm
+            scratch[0] = 0.0, scratch[1] = 0.0;
+            __threadfence();
+            *ticket = 0ull;
+        }
+    }
+    __syncthreads();
+    const float m = s_norm[0], denom = s_norm[1];
+    if (ok) {
+#pragma unroll
+        for (int t = 0; t < TMAX; ++t)
+            if (t < T) advantages[(size_t)t * N + e] = (raw[t] - m) / denom;
+    }
+}
+
 __global__ void __launch_bounds__(256)
 gae_normalize_kernel(float *__restrict__ adv, const double *__restrict__ stats, long long stat_count,
                      long long count) {
@@ -213,6 +318,27 @@ gae_normalize_kernel(float *__restrict__ adv, const double *__restrict__ stats, 
     } else {
         for (long long i = i4; i < count && i < i4 + 4; ++i) adv[i] = (adv[i] - m) / denom;
     }
+}
+
+template <int TMAX, int THREADS>
+int launch_gae_fused(const float *rewards, const float *values, const uint8_t *dones, const float *last_values,
+                            float *returns, float *advantages, double *scratch, int T, int N, float gamma, float lam,
+                            cudaStream_t st, bool *fits) {
+    auto kern = gae_fused_kernel<TMAX, THREADS>;
+    static int per_sm = -1;
+    if (per_sm < 0) HB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, 0));
+    const int grid = (N + THREADS - 1) / THREADS;
+    *fits = grid <= per_sm * hb::sm_count();
+    if (!*fits) return HB_OK;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid), cfg.blockDim = dim3(THREADS), cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeCooperative;
+    at[0].val.cooperative = 1;
+    cfg.attrs = at, cfg.numAttrs = 1;
+    HB_CUDA(cudaLaunchKernelEx(&cfg, kern, rewards, values, dones, last_values, returns, advantages, scratch, T, N, gamma, lam));
+    HB_CHECK_LAUNCH("gae_fused_kernel");
+    return HB_OK;
 }
 
 }  // namespace
@@ -240,6 +366,32 @@ int hb_gae_returns(const float *rewards, const float *values, const uint8_t *don
     gae_scan_kernel<<<(N + ENVS - 1) / ENVS, WARPS * 32, smem, st>>>(rewards, values, dones, last_values, returns,
                                                                      advantages, stats, T, N, gamma, lam);
     HB_CHECK_LAUNCH("gae_scan_kernel");
+    return HB_OK;
+}
+
+int hb_gae_fused(const float *rewards, const float *values, const uint8_t *dones, const float *last_values, float *returns,
+                 float *advantages, double *scratch, int32_t T, int32_t N, float gamma, float lam, void *stream) {
+    HB_REQUIRE(rewards && values && dones && last_values && returns && advantages && scratch, "hb_gae_fused: null buffer");
+    HB_REQUIRE(T > 0 && N > 0 && (long long)T * N > 1, "hb_gae_fused: T and N must be positive, T * N > 1");
+    HB_REQUIRE((reinterpret_cast<uintptr_t>(scratch) & 7u) == 0, "hb_gae_fused: scratch must be 8-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    bool fits = false;
+    int rc = HB_OK;
+    // narrow shards get narrow blocks so that the grid still covers the SMs
+    if (T <= 32) {
+        if (N <= 8192) rc = launch_gae_fused<32, 32>(rewards, values, dones, last_values, returns, advantages, scratch, T, N, gamma, lam, st, &fits);
+        else if (N <= 16384) rc = launch_gae_fused<32, 64>(rewards, values, dones, last_values, returns, advantages, scratch, T, N, gamma, lam, st, &fits);
+        else rc = launch_gae_fused<32, 128>(rewards, values, dones, last_values, returns, advantages, scratch, T, N, gamma, lam, st, &fits);
+    } else if (T <= 64) {
+        if (N <= 8192) rc = launch_gae_fused<64, 32>(rewards, values, dones, last_values, returns, advantages, scratch, T, N, gamma, lam, st, &fits);
+        else rc = launch_gae_fused<64, 128>(rewards, values, dones, last_values, returns, advantages, scratch, T, N, gamma, lam, st, &fits);
+    }
+    if (rc) return rc;
+    if (fits) return HB_OK;
+    // long rollouts / shards too wide for one co-resident grid: the two-kernel form (scratch doubles as the statistics)
+    if (int rc2 = hb_gae_returns(rewards, values, dones, last_values, returns, advantages, scratch, T, N, gamma, lam, stream)) return rc2;
+    if (int rc2 = hb_gae_normalize_n(advantages, scratch, (int64_t)T * N, (int64_t)T * N, stream)) return rc2;
+    HB_CUDA(cudaMemsetAsync(scratch, 0, 4 * sizeof(double), st));
     return HB_OK;
 }
 

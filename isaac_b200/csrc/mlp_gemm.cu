@@ -643,6 +643,31 @@ long long split3_floats(long long rows, long long K, bool mn_major) {
 
 int gemm_tf32_dispatch(const hb_gemm_desc *d, cudaStream_t st);
 
+// The tensor core adds each instruction's products (8 along K) into the TMEM accumulator with truncation, about
+// 3e-8 relative per step (measured: 1.2e-5 over the ~400 steps of a K' = 3 * 1052 contraction, where exact accumulation of
+// the same split operands gives 5e-7).  The fp32-grade mode therefore keeps accumulation chains SHORT: the contraction
+// is cut into splits of CHAIN_KB k-blocks (16 accumulation steps), every split adds its partial tile to D with
+// round-to-nearest fp32 reductions (red.global.add), and bias / ELU / ELU' run as a separate pass over D.
+constexpr int CHAIN_KB = 4;
+
+__global__ void __launch_bounds__(256)
+epilogue_inplace_kernel(float *__restrict__ D, int ldd, long long M, int N, int epi, const float *__restrict__ bias, int bias_stride,
+                        const float *__restrict__ H, int ldh) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M * N) return;
+    const long long m = i / N;
+    const int n = (int)(i - m * N);
+    float x = D[(size_t)m * ldd + n];
+    if (epi == EPI_BIAS || epi == EPI_BIAS_ELU) {
+        x += __ldg(bias + (size_t)n * bias_stride);
+        if (epi == EPI_BIAS_ELU) x = x > 0.0f ? x : expm1f(x);                   // nn.ELU(alpha=1)
+    } else if (epi == EPI_ELU_BWD) {
+        const float h = __ldg(H + (size_t)m * ldh + n);
+        x *= (h > 0.0f ? 1.0f : h + 1.0f);
+    }
+    D[(size_t)m * ldd + n] = x;
+}
+
 int gemm_3xtf32(const hb_gemm_desc *d, cudaStream_t st) {
     const long long fa = split3_floats(d->M, d->K, d->a_mn_major != 0), fb = split3_floats(d->N, d->K, d->b_mn_major != 0);
     HB_REQUIRE(d->workspace && hb::aligned16(d->workspace) && d->workspace_floats >= fa + fb,
@@ -668,7 +693,21 @@ int gemm_3xtf32(const hb_gemm_desc *d, cudaStream_t st) {
     HB_CHECK_LAUNCH("split3 (A)");
     split(d->B, d->ldb, d->N, d->b_mn_major != 0, wb, 0, e.ldb);       // B' = [hi | hi | lo]
     HB_CHECK_LAUNCH("split3 (B)");
-    return gemm_tf32_dispatch(&e, st);
+    // short accumulation chains: split-K with fp32 reductions into D, fused tails moved to a second pass
+    const int kb_total = (e.K + BK - 1) / BK;
+    e.split_k = (kb_total + CHAIN_KB - 1) / CHAIN_KB;
+    e.epilogue = HB_EPI_ATOMIC_ADD;
+    e.bias = nullptr, e.H = nullptr;
+    if (d->epilogue != HB_EPI_ATOMIC_ADD)                               // D = ..., not D += ...: start from zero
+        HB_CUDA(cudaMemset2DAsync(d->D, (size_t)d->ldd * 4, 0, (size_t)d->N * 4, (size_t)d->M, st));
+    if (int rc = gemm_tf32_dispatch(&e, st)) return rc;
+    if (d->epilogue == HB_EPI_BIAS || d->epilogue == HB_EPI_BIAS_ELU || d->epilogue == HB_EPI_ELU_BWD) {
+        const long long total = (long long)d->M * d->N;
+        epilogue_inplace_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d->D, d->ldd, d->M, d->N, d->epilogue, d->bias,
+                                                                              d->bias_stride, d->H, d->ldh);
+        HB_CHECK_LAUNCH("epilogue_inplace_kernel");
+    }
+    return HB_OK;
 }
 
 }  // namespace
