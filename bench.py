@@ -548,6 +548,11 @@ def run_b200(args, rank, world):
     ret_, adv_ = torch.empty_like(r_), torch.empty_like(r_)
     gae_compute_returns(r_, v_, d_, lv_, ret_, adv_, 0.994, 0.9)          # allocates the launch's scratch before capture
     k_gae = time_launch(lambda st: gae_compute_returns(r_, v_, d_, lv_, ret_, adv_, 0.994, 0.9) and None)      # hb_gae_fused: one launch
+    lib.hb_set_option(b"coop_launch", 1)
+    k_gae_coop = time_launch(lambda st: gae_compute_returns(r_, v_, d_, lv_, ret_, adv_, 0.994, 0.9) and None)
+    lib.hb_set_option(b"coop_launch", 0)
+    gae_stats = torch.zeros(2, dtype=torch.float64, device=dev)
+    k_gae_two = time_launch(lambda st: gae_compute_returns(r_, v_, d_, lv_, ret_, adv_, 0.994, 0.9, stats=gae_stats) and None)
     ppo = None if args.skip_ppo else bench_ppo(args, dev, n, world, rank, env, phys, phys_frames)
     clocks = sampler.summary()
 
@@ -628,7 +633,7 @@ def run_b200(args, rank, world):
                     "stack_pair_gbs": (hist_obs + hist_priv) / (k_stack * 1e-3) / 1e9,
                     "stack_priv_ms": k_priv, "stack_obs_ms": k_obs,
                     "stack_obs_gbs": hist_obs / (k_obs * 1e-3) / 1e9, "pd_ms": k_pd,
-                    "pd_gbs": n * 240 / (k_pd * 1e-3) / 1e9, "gae_ms": k_gae,
+                    "pd_gbs": n * 240 / (k_pd * 1e-3) / 1e9, "gae_ms": k_gae, "gae_cooperative_launch_ms": k_gae_coop, "gae_two_kernel_form_ms": k_gae_two,
                     "gae_gbs": n * T_GAE * 25 / (k_gae * 1e-3) / 1e9},
         "gae": {"value": total_envs * T_GAE / (k_gae * 1e-3), "unit": "samples/s", "T": T_GAE},
     }

@@ -189,6 +189,11 @@ void hb_launch_count_reset(void);
  * (default) = only the PD-torque launches (measured on one box, 4096 envs: 52.0 us per step with the default, 52.7
  * with none, 60.4 with all; PD launches only: +5.6 % at 16384 envs, +2 % at 65536; all kernels: -13 % at 65536);
  * "gae_serial_min_envs" (default 8192): shards at least this wide run GAE one thread per env. */
+/* "coop_launch" 0 (default) / 1: the two kernels that contain a grid barrier (hb_optimizer_step, hb_gae_fused) size their
+ * grid to what the device holds at once; with 1 they are also launched with the cooperative attribute (the driver then
+ * guarantees co-residency but serialises the launch against everything else on the device: measured 24.8 us against
+ * the plain launch for GAE at 4096 x 24).  Plain launches are safe as long as nothing that occupies the SMs waits for
+ * these kernels - true for stream-ordered use in one process per GPU. */
 /* "gemm_pdl" 1 (default) / 0: hb_gemm_tf32 launches with programmatic stream serialization (a GEMM's set-up - tensor-map
  * prefetch, barriers, TMEM allocation, cluster rendezvous - overlaps the previous kernel's last tiles). */
 int hb_set_option(const char *name, int value);

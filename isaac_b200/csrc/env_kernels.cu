@@ -1247,6 +1247,10 @@ int hb_set_option(const char *name, int value) {
         hb::g_use_pdl = value;
         return HB_OK;
     }
+    if (name && !strcmp(name, "coop_launch")) {
+        hb::g_coop_launch = value != 0;
+        return HB_OK;
+    }
     hb::set_error("hb_set_option: unknown option '%s'", name ? name : "(null)");
     return HB_ERR_BAD_ARG;
 }

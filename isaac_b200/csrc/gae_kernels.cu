@@ -334,7 +334,7 @@ int launch_gae_fused(const float *rewards, const float *values, const uint8_t *d
     cfg.gridDim = dim3(grid), cfg.blockDim = dim3(THREADS), cfg.stream = st;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeCooperative;
-    at[0].val.cooperative = 1;
+    at[0].val.cooperative = hb::g_coop_launch ? 1 : 0;
     cfg.attrs = at, cfg.numAttrs = 1;
     HB_CUDA(cudaLaunchKernelEx(&cfg, kern, rewards, values, dones, last_values, returns, advantages, scratch, T, N, gamma, lam));
     HB_CHECK_LAUNCH("gae_fused_kernel");

@@ -717,7 +717,7 @@ int hb_optimizer_step(float *params, float *grads, float *exp_avg, float *exp_av
     cfg.gridDim = dim3(grid), cfg.blockDim = dim3(OPT_THREADS), cfg.dynamicSmemBytes = 0, cfg.stream = (cudaStream_t)stream;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeCooperative;
-    at[0].val.cooperative = 1;
+    at[0].val.cooperative = hb::g_coop_launch ? 1 : 0;
     cfg.attrs = at, cfg.numAttrs = 1;
     HB_CUDA(cudaLaunchKernelEx(&cfg, optimizer_step_kernel, params, grads, exp_avg, exp_avg_sq, (long long)n, *ap, state));
     HB_CHECK_LAUNCH("optimizer_step_kernel");

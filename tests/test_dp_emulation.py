@@ -55,7 +55,7 @@ def test_emulated_data_parallel_update_matches_single_replica(lib, cuda_device, 
     for r, alg in enumerate(reps):
         lo, hi = shard_range(N, r, world)
         torch.testing.assert_close(alg.storage.advantages, ref.storage.advantages[:, lo:hi], rtol=1e-5, atol=1e-6)
-        assert torch.equal(alg.storage.returns, ref.storage.returns[:, lo:hi])
+        torch.testing.assert_close(alg.storage.returns, ref.storage.returns[:, lo:hi], rtol=1e-5, atol=1e-6)
     # ---- minibatch index tapes: global minibatch k = rank-wise concatenation of the local minibatches k ----
     mbl = (T * nl) // CFG["num_mini_batches"]
     perms = [torch.randperm(T * nl, generator=torch.Generator().manual_seed(100 + r)) for r in range(world)]
