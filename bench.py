@@ -90,6 +90,23 @@ class ClockSampler(threading.Thread):
         return out
 
 
+def bind_to_gpu_cpus(index: int):
+    """Pin this process to the CPUs NVML reports as local to GPU `index` (its NUMA node): pinned host buffers and the
+    copy engines' DMA then stay on that socket (e2e leg at N > 1)."""
+    try:
+        import pynvml as nv
+        nv.nvmlInit()
+        h = nv.nvmlDeviceGetHandleByIndex(index)
+        words = nv.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return sorted(cpus)
+    except Exception:
+        return None
+
+
 def make_workload(n, frames, seed):
     from isaac_b200.synthetic import make_tape
     return make_tape(n, frames, seed=seed, fall_prob=0.005, randomize_gains=True)
@@ -411,6 +428,8 @@ def run_b200(args, rank, world):
     local = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    if world > 1:                    # (the single-GPU run keeps every core: it also times the CPU baseline)
+        bind_to_gpu_cpus(local)      # before any pinned allocation: first touch lands on the GPU's NUMA node
     lib = _lib.load(check_device=True)
     for kv in args.opt:
         k, v = kv.split("=")
@@ -557,38 +576,64 @@ def run_b200(args, rank, world):
     clocks = sampler.summary()
 
     # ---- e2e: host buffers in, host buffers out, env's own noise ----
+    # Pipelined like a host consumer would run it: the two big results of step k (obs, privileged obs: 27 MB at 4096
+    # envs) leave on a copy stream into one of two pinned buffer sets while step k+1 already runs; the host only waits
+    # for the buffer set it is about to read (step k-1's), and a step may not start overwriting an observation buffer
+    # whose copy is still in flight.  Rewards and resets are single device buffers that the next step overwrites: they
+    # are copied in stream order behind the step (20 KB).  Every step's inputs come from pinned host memory.
     host_frames = [type(f)(*(t.cpu().pin_memory() for t in (f.root_states, f.dof_state, f.contact_forces, f.rigid_state)))
                    for f in tape.physics]
     host_actions = [f.actions.pin_memory() for f in tape.noise]
     # host images keep the device row pitch (616 / 1052 floats: one padding column), so each result is ONE copy
-    out_host = [torch.empty(n, env._p.obs_ld).pin_memory(), torch.empty(n, env._p.priv_ld).pin_memory(),
-                torch.empty(n).pin_memory(), torch.empty(n, dtype=torch.bool).pin_memory()]
+    out_host = [[torch.empty(n, env._p.obs_ld).pin_memory(), torch.empty(n, env._p.priv_ld).pin_memory(),
+                 torch.empty(n).pin_memory(), torch.empty(n, dtype=torch.bool).pin_memory()] for _ in range(2)]
     act_dev = torch.empty(n, 10, device=dev)
+    copy_stream = torch.cuda.Stream(dev)
+    ev_step = [torch.cuda.Event() for _ in range(2)]
+    ev_copied = [torch.cuda.Event() for _ in range(2)]
+    checksum = [0.0]
 
     def whole_rows(t):          # [n, width] view at a pitch -> the [n, pitch] block it lives in
         return t if t.dim() < 2 or t.is_contiguous() else torch.as_strided(t, (t.shape[0], t.stride(0)), (t.stride(0), 1))
 
+    def consume(slot):          # the caller's read of a finished step: waits for that buffer set only
+        ev_copied[slot].synchronize()
+        checksum[0] += float(out_host[slot][2][0])
+
     def e2e_step(i):
-        f = i % frames
+        f, slot = i % frames, i & 1
+        if i >= 2:
+            stream.wait_event(ev_copied[slot])       # step i reuses the observation buffers step i-2's copies read
         phys.load_frame(host_frames[f])
         act_dev.copy_(host_actions[f], non_blocking=True)
         out = env.step(act_dev)
-        for h, d in zip(out_host, out[:4]):
-            h.copy_(whole_rows(d), non_blocking=True)
-        torch.cuda.synchronize(dev)      # the caller needs the results of this step
+        out_host[slot][2].copy_(out[2], non_blocking=True)
+        out_host[slot][3].copy_(out[3], non_blocking=True)
+        ev_step[slot].record(stream)
+        copy_stream.wait_event(ev_step[slot])
+        with torch.cuda.stream(copy_stream):
+            out_host[slot][0].copy_(whole_rows(out[0]), non_blocking=True)
+            out_host[slot][1].copy_(whole_rows(out[1]), non_blocking=True)
+            ev_copied[slot].record(copy_stream)
+        if i >= 1:
+            consume(slot ^ 1)                        # hand step i-1's results to the caller
 
-    for i in range(max(3, args.warmup)):
-        e2e_step(i)
+    def e2e_run(k):
+        for i in range(k):
+            e2e_step(i)
+        consume((k - 1) & 1)                         # the last step's results
+        torch.cuda.synchronize(dev)
+
+    e2e_run(max(4, args.warmup))
     barrier()
     t0 = time.perf_counter()
-    for i in range(args.steps):
-        e2e_step(i)
+    e2e_run(args.steps)
     barrier()
     e2e_wall = time.perf_counter() - t0
     h2d = sum(t.numel() * t.element_size() for t in (host_frames[0].root_states, host_frames[0].dof_state,
                                                       host_frames[0].contact_forces, host_frames[0].rigid_state,
                                                       host_actions[0]))
-    d2h = sum(t.numel() * t.element_size() for t in out_host)
+    d2h = sum(t.numel() * t.element_size() for t in out_host[0])
 
     t = torch.tensor([dev_ms, wall, e2e_wall, k_priv, k_obs, k_pd, k_gae, k_post, k_stack, k_fin, k_stack_single],
                      dtype=torch.float64, device=dev)
@@ -642,7 +687,10 @@ def run_b200(args, rank, world):
     # the last keys of the line (a truncated tail still carries them): PPO samples/s and the end-to-end number
     line["ppo"] = ppo
     line["e2e"] = {"value": total_envs * args.steps / e2e_wall, "unit": "env-steps/s", "h2d_bytes_per_step": h2d,
-                   "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_wall / args.steps}
+                   "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_wall / args.steps,
+                   "d2h_gbs_per_gpu": d2h * args.steps / e2e_wall / 1e9,
+                   "pipeline": "obs / privileged obs of step k leave on a copy stream into double-buffered pinned memory "
+                               "while step k+1 runs; the host waits per buffer set; CPU affinity = the GPU's NUMA node"}
     print(json.dumps(line), flush=True)
 
 

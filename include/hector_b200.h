@@ -177,6 +177,15 @@ typedef struct hb_env_noise {
 #define HB_STAGE_OBS       0x8   /* emit the newest frames even without HB_STAGE_STEP */
 #define HB_STAGE_RESET_MASK 0x20 /* reset_idx(env_ids): reset the envs whose reset_buf was set by the caller */
 #define HB_STAGE_DERIVE    0x10  /* _init_buffers: base_lin_vel / base_ang_vel / gravity of the initial state (:477-479) */
+/* The reference's overridable hooks one by one: each bit runs that span of post_physics_step on the
+ * current buffers, exactly as HB_STAGE_STEP does inside the fused launch.  The reference's order is PREPARE,
+ * TERMINATION, REWARD, [reset_idx(reset_buf.nonzero()) = HB_STAGE_RESET_MASK + hb_env_reset_finalize], OBS
+ * (+ hb_env_stack_finalize), LAST.  Launches with only PREPARE / TERMINATION / REWARD / LAST bits reset nothing and
+ * need no hb_env_reset_finalize behind them. */
+#define HB_STAGE_PREPARE     0x40  /* legged_robot.py:127-137: episode_length_buf += 1, base quantities, _post_physics_step_callback */
+#define HB_STAGE_TERMINATION 0x80  /* check_termination (:155-160): reset_buf, time_out_buf */
+#define HB_STAGE_REWARD      0x100 /* compute_reward (:216-234): rew_buf, episode_sums, feet_air_time / last_contacts / feet_height / last_feet_z */
+#define HB_STAGE_LAST        0x200 /* legged_robot.py:146-150: last_last_actions, last_actions, last_dof_vel, last_root_vel */
 
 const char *hb_last_error(void);
 int hb_abi_version(void);
@@ -274,8 +283,8 @@ int hb_gae_returns(const float *rewards, const float *values, const uint8_t *don
 int hb_gae_normalize(float *advantages, const double *stats, int64_t count, void *stream);
 /* Same, when `stats` were summed over `stat_count` samples (all ranks) and this rank holds `count`. */
 int hb_gae_normalize_n(float *advantages, const double *stats, int64_t stat_count, int64_t count, void *stream);
-/* Single-GPU form of the whole of compute_returns in ONE launch (T <= 64): one thread per env, the raw advantages stay in
- * registers across a grid barrier on (sum, sum sq) and are written once, normalised - 17 instead of 25 bytes per sample
+/* Single-GPU form of the whole of compute_returns in ONE launch: one thread per env, the raw advantages stay in
+ * shared memory across a grid barrier on (sum, sum sq) and are written once, normalised - 17 instead of 25 bytes per sample
  * and one launch instead of memset + two kernels.  scratch: 4 doubles of device memory, zero before the first call (the
  * launch re-arms them).  Falls back to hb_gae_returns + hb_gae_normalize for longer rollouts or shards too wide for one
  * co-resident grid.  Multi-GPU callers use the two-call form (the statistics are all-reduced between the passes). */

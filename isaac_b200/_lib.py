@@ -22,6 +22,7 @@ HB_STAGE_PUSH = 0x4
 HB_STAGE_OBS = 0x8
 HB_STAGE_DERIVE = 0x10
 HB_STAGE_RESET_MASK = 0x20
+HB_STAGE_PREPARE, HB_STAGE_TERMINATION, HB_STAGE_REWARD, HB_STAGE_LAST = 0x40, 0x80, 0x100, 0x200
 
 # alphabetical = the reference's accumulation order (utils/helpers.py:47)
 REWARD_NAMES = ("action_smoothness", "base_acc", "base_height", "collision", "default_joint_pos", "dof_acc",

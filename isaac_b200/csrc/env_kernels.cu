@@ -338,9 +338,17 @@ post_physics_kernel(const __grid_constant__ hb_env_params p, const __grid_consta
     const int env = env0 + lane;
     const bool valid = lane < nv;
     const int ln = valid ? lane : 0;
+    // HB_STAGE_STEP is the whole of post_physics_step in one launch; the finer bits run one of the reference's hooks on
+    // its own (check_termination, compute_reward, compute_observations, and the head / tail of post_physics_step), so that
+    // a host that calls - or overrides - them one by one gets the same buffers as the fused launch
     const bool do_step = stages & HB_STAGE_STEP;
-    const bool derive = do_step || (stages & HB_STAGE_DERIVE);
+    const bool do_prepare = do_step || (stages & HB_STAGE_PREPARE);
+    const bool do_term = do_step || (stages & HB_STAGE_TERMINATION);
+    const bool do_rew = do_step || (stages & HB_STAGE_REWARD);
+    const bool do_last = do_step || (stages & HB_STAGE_LAST);
+    const bool derive = do_prepare || (stages & HB_STAGE_DERIVE);
     const bool emit_obs = do_step || (stages & HB_STAGE_OBS);
+    const bool any_reset = do_step || (stages & (HB_STAGE_RESET_ALL | HB_STAGE_RESET_MASK));
     const Rng rng = make_rng(nz);
     const bool with_noise = p.add_noise && (nz.z_obs != nullptr || rng.on);
     const bool tape_noise = p.add_noise && nz.z_obs != nullptr;
@@ -423,7 +431,7 @@ post_physics_kernel(const __grid_constant__ hb_env_params p, const __grid_consta
             grav = {b.projected_gravity[env * 3], b.projected_gravity[env * 3 + 1], b.projected_gravity[env * 3 + 2]};
         }
         eul = euler_xyz_wrapped_nl(quat[0], quat[1], quat[2], quat[3]);
-        if (do_step) {
+        if (do_prepare) {
             ep_len += 1;
             // -------- _post_physics_step_callback, legged_robot.py:303-335 --------
             if (valid && (ep_len % p.resample_interval) == 0 && (nz.u_cmd || rng.on)) {
@@ -463,6 +471,8 @@ post_physics_kernel(const __grid_constant__ hb_env_params p, const __grid_consta
 #pragma unroll
                 for (int k = 0; k < 3; ++k) b.rand_push_torque[env * 3 + k] = push_t[k];
             }
+        }
+        if (do_rew) {
             {   // base_acc, hector_env.py:385-392 (root velocity after the push)
                 float ss = 0.f;
 #pragma unroll
@@ -526,7 +536,7 @@ post_physics_kernel(const __grid_constant__ hb_env_params p, const __grid_consta
                 b.base_lin_vel[env * 3] = lin.x, b.base_lin_vel[env * 3 + 1] = lin.y, b.base_lin_vel[env * 3 + 2] = lin.z;
                 b.base_ang_vel[env * 3] = ang.x, b.base_ang_vel[env * 3 + 1] = ang.y, b.base_ang_vel[env * 3 + 2] = ang.z;
             }
-            if (do_step) {
+            if (do_last) {
 #pragma unroll
                 for (int k = 0; k < 6; ++k) b.last_root_vel[(size_t)env * 6 + k] = root[7 + k];
             }
@@ -575,7 +585,7 @@ post_physics_kernel(const __grid_constant__ hb_env_params p, const __grid_consta
             qd[j] = sm[L.dof + ln * NDOF * 2 + 2 * j + 1];
             act[j] = sm[L.actions + ln * NDOF + j];
         }
-        if (do_step) {
+        if (do_rew || do_last) {
             float t1 = 0.f, t2 = 0.f, t3 = 0.f, ss = 0.f, acc = 0.f, vel = 0.f, tq = 0.f;
             float dy[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -597,19 +607,21 @@ post_physics_kernel(const __grid_constant__ hb_env_params p, const __grid_consta
                 vel += qd[j] * qd[j];                                  // dof_vel :508-513
                 const float tau = sm[L.torques + ln * NDOF + j];       // torques :501-506
                 tq += tau * tau;
-                if (valid) {                                           // legged_robot.py:146-148 (reset envs: zeroed below)
+                if (valid && do_last) {                                // legged_robot.py:146-148 (reset envs: zeroed below)
                     b.last_last_actions[(size_t)env * NDOF + j] = lact;
                     b.last_actions[(size_t)env * NDOF + j] = act[j];
                     b.last_dof_vel[(size_t)env * NDOF + j] = qd[j];
                 }
             }
-            terms[HB_R_ACTION_SMOOTHNESS * TILE + lane] = (t1 + t2) + 0.05f * t3;
-            float yr = sqrtf(dy[0] * dy[0] + dy[1] * dy[1]) + sqrtf(dy[2] * dy[2] + dy[3] * dy[3]);
-            yr = clampf(yr - 0.1f, 0.0f, 50.0f);
-            terms[HB_R_DEFAULT_JOINT_POS * TILE + lane] = expf(-yr * 100.0f) - 0.01f * sqrtf(ss);
-            terms[HB_R_DOF_ACC * TILE + lane] = acc;
-            terms[HB_R_DOF_VEL * TILE + lane] = vel;
-            terms[HB_R_TORQUES * TILE + lane] = tq;
+            if (do_rew) {
+                terms[HB_R_ACTION_SMOOTHNESS * TILE + lane] = (t1 + t2) + 0.05f * t3;
+                float yr = sqrtf(dy[0] * dy[0] + dy[1] * dy[1]) + sqrtf(dy[2] * dy[2] + dy[3] * dy[3]);
+                yr = clampf(yr - 0.1f, 0.0f, 50.0f);
+                terms[HB_R_DEFAULT_JOINT_POS * TILE + lane] = expf(-yr * 100.0f) - 0.01f * sqrtf(ss);
+                terms[HB_R_DOF_ACC * TILE + lane] = acc;
+                terms[HB_R_DOF_VEL * TILE + lane] = vel;
+                terms[HB_R_TORQUES * TILE + lane] = tq;
+            }
         }
         HB_STAMP(2);
         tile_barrier();                                           // ---- barrier 1 ----
@@ -681,28 +693,30 @@ post_physics_kernel(const __grid_constant__ hb_env_params p, const __grid_consta
 #pragma unroll
             for (int k = 0; k < 3; ++k) foot_f[f][k] = cf[p.feet[f] * 3 + k];
         const float root_z = sm[L.root + ln * 13 + 2];
-        bool reset = false, time_out = false;
+        bool term = false, time_out = false;
         float gs = 0.0f, gc = 1.0f, st[2] = {1.0f, 1.0f};
         const bool ct[2] = {foot_f[0][2] > 5.0f, foot_f[1][2] > 5.0f};
-        if (do_step) {
-            ep_len += 1;
-            // -------- check_termination, legged_robot.py:155-160 --------
+        if (do_prepare) ep_len += 1;
+        if (do_term) {   // -------- check_termination, legged_robot.py:155-160 --------
+#pragma unroll 1
+            for (int i = 0; i < p.n_term; ++i) term |= norm3(cf + p.term_bodies[i] * 3) > 1.0f;
+            time_out = ep_len > (long long)p.max_episode_length;
+            term |= time_out;
+        }
+        if (do_rew) {    // collision, hector_env.py:522-527
             float coll = 0.f;
 #pragma unroll 1
-            for (int i = 0; i < p.n_term; ++i) reset |= norm3(cf + p.term_bodies[i] * 3) > 1.0f;
-#pragma unroll 1
             for (int i = 0; i < p.n_pen; ++i) coll += (norm3(cf + p.pen_bodies[i] * 3) > 0.1f) ? 1.0f : 0.0f;
-            time_out = ep_len > (long long)p.max_episode_length;
-            reset |= time_out;
-            terms[HB_R_COLLISION * TILE + lane] = coll;                 // :522-527
+            terms[HB_R_COLLISION * TILE + lane] = coll;
         }
+        bool reset = do_step && term;        // the fused step resets what it has just found terminated
         {   // -------- gait phase, hector_env.py:70-88 --------
             const float arg = TWO_PI_F * (((float)ep_len * dt) / p.cycle_time);
             sincosf(arg, &gs, &gc);
             st[0] = (gs >= 0.0f) ? 1.0f : 0.0f, st[1] = (gs < 0.0f) ? 1.0f : 0.0f;
             if (fabsf(gs) < 0.1f) st[0] = st[1] = 1.0f;
         }
-        if (do_step) {
+        if (do_rew) {
             {   // base_height, :369-383
                 const float ground = (foot_pos[0][2] * st[0] + foot_pos[1][2] * st[1]) / (st[0] + st[1]);
                 const float h = root_z - (ground - 0.05f);
@@ -764,9 +778,10 @@ post_physics_kernel(const __grid_constant__ hb_env_params p, const __grid_consta
         if (valid) {
             b.feet_air_time[env * 2] = air[0], b.feet_air_time[env * 2 + 1] = air[1];
             b.episode_length_buf[env] = ep_len;
-            b.reset_buf[env] = reset ? 1 : 0;
-            if (do_step) {
-                b.time_out_buf[env] = time_out ? 1 : 0;
+            if (any_reset) b.reset_buf[env] = reset ? 1 : 0;
+            else if (do_term) b.reset_buf[env] = term ? 1 : 0;           // check_termination on its own: the mask only
+            if (do_term) b.time_out_buf[env] = time_out ? 1 : 0;
+            if (do_rew) {
 #pragma unroll
                 for (int f = 0; f < 2; ++f) {
                     b.last_contacts[env * 2 + f] = last_ct[f] ? 1 : 0;
@@ -815,7 +830,7 @@ post_physics_kernel(const __grid_constant__ hb_env_params p, const __grid_consta
         tile_barrier();                                           // ---- barrier 1 ----
         HB_STAMP(3);
         const bool reset = valid && (flags[lane] & 1);
-        if (do_step) {       // compute_reward, legged_robot.py:216-234: alphabetical accumulation
+        if (do_rew) {        // compute_reward, legged_robot.py:216-234: alphabetical accumulation
             float rew = 0.0f;
 #pragma unroll
             for (int k = 0; k < HB_NUM_REWARDS; ++k) {

@@ -195,7 +195,7 @@ gae_serial_kernel(const float *__restrict__ rewards, const float *__restrict__ v
 
 // ------------------------------------------------------------------------------------------
 // Single-GPU form: the whole of compute_returns in ONE launch.  One thread per env as above, but the T raw advantages
-// of the env stay in registers while the grid agrees on (sum, sum of squares): block reduction -> fp64 atomics -> ticket
+// of the env stay on chip (shared memory) while the grid agrees on (sum, sum of squares): block reduction -> fp64 atomics -> ticket
 // barrier (cooperative launch: every block is resident) -> mean / unbiased std -> the normalised advantages are written
 // once.  Against memset + scan + normalise this drops two launches and the write + re-read of the raw advantages
 // (17 instead of 25 bytes per sample).  scratch = {sum, sum sq, ticket, -}: zero on entry, re-armed by the last block.
@@ -206,52 +206,51 @@ __device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long
     return v;
 }
 
-template <int TMAX, int THREADS>
+template <int THREADS>
 __global__ void __launch_bounds__(THREADS)
 gae_fused_kernel(const float *__restrict__ rewards, const float *__restrict__ values, const uint8_t *__restrict__ dones,
                  const float *__restrict__ last_values, float *__restrict__ returns, float *__restrict__ advantages,
                  double *__restrict__ scratch, int T, int N, float gamma, float lam) {
     constexpr int CHUNK = 8;
-    static_assert(TMAX % CHUNK == 0, "whole chunks");
-    __shared__ double red[2][THREADS / 32 > 0 ? THREADS / 32 : 1];
+    extern __shared__ float s_raw[];          // [T][THREADS]: this block's raw advantages, parked across the grid barrier
+    __shared__ double red[2][THREADS / 32];
     __shared__ float s_norm[2];
     const int e = blockIdx.x * THREADS + threadIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const bool ok = e < N;
-    float raw[TMAX];                         // advantages = returns - values of this env, t = 0 .. T-1
     double s1 = 0.0, s2 = 0.0;
-    {
+    if (ok) {
         float r[CHUNK], v[CHUNK], nr[CHUNK], nv[CHUNK];
         uint8_t d[CHUNK], nd[CHUNK];
-        auto load = [&](int c, float *rr, float *vv, uint8_t *dd) {          // steps c*CHUNK .. c*CHUNK + CHUNK - 1
+        auto load = [&](int t_hi, float *rr, float *vv, uint8_t *dd) {          // steps t_hi, t_hi - 1, ...
 #pragma unroll
             for (int u = 0; u < CHUNK; ++u) {
-                const int t = c * CHUNK + u;
+                const int t = t_hi - u;
                 rr[u] = vv[u] = 0.f, dd[u] = 0;
-                if (ok && t < T) {
+                if (t >= 0) {
                     const size_t i = (size_t)t * N + e;
                     rr[u] = rewards[i], vv[u] = values[i], dd[u] = dones[i];
                 }
             }
         };
-        float next_v = ok ? last_values[e] : 0.0f, adv = 0.0f;
-        load(TMAX / CHUNK - 1, r, v, d);
+        float next_v = last_values[e], adv = 0.0f;
+        load(T - 1, r, v, d);
+#pragma unroll 1
+        for (int t_hi = T - 1; t_hi >= 0; t_hi -= CHUNK) {
+            load(t_hi - CHUNK, nr, nv, nd);                                       // next chunk in flight
 #pragma unroll
-        for (int c = TMAX / CHUNK - 1; c >= 0; --c) {
-            if (c > 0) load(c - 1, nr, nv, nd);                                  // next chunk in flight
-#pragma unroll
-            for (int u = CHUNK - 1; u >= 0; --u) {
-                const int t = c * CHUNK + u;
-                raw[t] = 0.0f;
-                if (ok && t < T) {
+            for (int u = 0; u < CHUNK; ++u) {
+                const int t = t_hi - u;
+                if (t >= 0) {
                     const float g = (1.0f - (float)d[u]) * gamma;
                     const float delta = (r[u] + g * next_v) - v[u];
                     adv = delta + (g * lam) * adv;
                     const float ret = adv + v[u];
-                    raw[t] = ret - v[u];                                         // advantages = returns - values (:135)
+                    const float raw = ret - v[u];                                 // advantages = returns - values (:135)
                     returns[(size_t)t * N + e] = ret;
-                    s1 += (double)raw[t];
-                    s2 += (double)raw[t] * (double)raw[t];
+                    s_raw[t * THREADS + threadIdx.x] = raw;
+                    s1 += (double)raw;
+                    s2 += (double)raw * (double)raw;
                     next_v = v[u];
                 }
             }
@@ -269,7 +268,7 @@ gae_fused_kernel(const float *__restrict__ rewards, const float *__restrict__ va
     if (threadIdx.x == 0) {
         double a = 0.0, q = 0.0;
 #pragma unroll
-        for (int w = 0; w < (THREADS / 32 > 0 ? THREADS / 32 : 1); ++w) a += red[0][w], q += red[1][w];
+        for (int w = 0; w < THREADS / 32; ++w) a += red[0][w], q += red[1][w];
         unsigned long long *ticket = reinterpret_cast<unsigned long long *>(scratch + 2);
         atomicAdd(scratch, a);
         atomicAdd(scratch + 1, q);
@@ -292,9 +291,8 @@ gae_fused_kernel(const float *__restrict__ rewards, const float *__restrict__ va
     __syncthreads();
     const float m = s_norm[0], denom = s_norm[1];
     if (ok) {
-#pragma unroll
-        for (int t = 0; t < TMAX; ++t)
-            if (t < T) advantages[(size_t)t * N + e] = (raw[t] - m) / denom;
+#pragma unroll 4
+        for (int t = 0; t < T; ++t) advantages[(size_t)t * N + e] = (s_raw[t * THREADS + threadIdx.x] - m) / denom;
     }
 }
 
@@ -320,18 +318,26 @@ gae_normalize_kernel(float *__restrict__ adv, const double *__restrict__ stats, 
     }
 }
 
-template <int TMAX, int THREADS>
+template <int THREADS>
 int launch_gae_fused(const float *rewards, const float *values, const uint8_t *dones, const float *last_values,
-                            float *returns, float *advantages, double *scratch, int T, int N, float gamma, float lam,
-                            cudaStream_t st, bool *fits) {
-    auto kern = gae_fused_kernel<TMAX, THREADS>;
-    static int per_sm = -1;
-    if (per_sm < 0) HB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, 0));
+                     float *returns, float *advantages, double *scratch, int T, int N, float gamma, float lam,
+                     cudaStream_t st, bool *fits) {
+    auto kern = gae_fused_kernel<THREADS>;
+    const size_t smem = (size_t)T * THREADS * sizeof(float);
+    *fits = false;
+    if (smem > 64 * 1024) return HB_OK;
+    static bool attr = false;
+    if (!attr) {
+        HB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        attr = true;
+    }
+    int per_sm = 0;
+    HB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, smem));
     const int grid = (N + THREADS - 1) / THREADS;
-    *fits = grid <= per_sm * hb::sm_count();
+    *fits = grid <= per_sm * hb::sm_count();                 // the blocks wait for one another: all must be resident
     if (!*fits) return HB_OK;
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid), cfg.blockDim = dim3(THREADS), cfg.stream = st;
+    cfg.gridDim = dim3(grid), cfg.blockDim = dim3(THREADS), cfg.dynamicSmemBytes = smem, cfg.stream = st;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeCooperative;
     at[0].val.cooperative = hb::g_coop_launch ? 1 : 0;
@@ -378,14 +384,9 @@ int hb_gae_fused(const float *rewards, const float *values, const uint8_t *dones
     bool fits = false;
     int rc = HB_OK;
     // narrow shards get narrow blocks so that the grid still covers the SMs
-    if (T <= 32) {
-        if (N <= 8192) rc = launch_gae_fused<32, 32>(rewards, values, dones, last_values, returns, advantages, scratch, T, N, gamma, lam, st, &fits);
-        else if (N <= 16384) rc = launch_gae_fused<32, 64>(rewards, values, dones, last_values, returns, advantages, scratch, T, N, gamma, lam, st, &fits);
-        else rc = launch_gae_fused<32, 128>(rewards, values, dones, last_values, returns, advantages, scratch, T, N, gamma, lam, st, &fits);
-    } else if (T <= 64) {
-        if (N <= 8192) rc = launch_gae_fused<64, 32>(rewards, values, dones, last_values, returns, advantages, scratch, T, N, gamma, lam, st, &fits);
-        else rc = launch_gae_fused<64, 128>(rewards, values, dones, last_values, returns, advantages, scratch, T, N, gamma, lam, st, &fits);
-    }
+    if (N <= 8192) rc = launch_gae_fused<32>(rewards, values, dones, last_values, returns, advantages, scratch, T, N, gamma, lam, st, &fits);
+    else if (N <= 16384) rc = launch_gae_fused<64>(rewards, values, dones, last_values, returns, advantages, scratch, T, N, gamma, lam, st, &fits);
+    else rc = launch_gae_fused<128>(rewards, values, dones, last_values, returns, advantages, scratch, T, N, gamma, lam, st, &fits);
     if (rc) return rc;
     if (fits) return HB_OK;
     // long rollouts / shards too wide for one co-resident grid: the two-kernel form (scratch doubles as the statistics)

@@ -38,8 +38,9 @@ import numpy as np
 import torch
 
 from .. import _lib
-from .._lib import (EnvBuffers, EnvNoise, EnvParams, HB_NUM_REWARDS, HB_STAGE_DERIVE, HB_STAGE_OBS, HB_STAGE_PUSH,
-                    HB_STAGE_RESET_ALL, HB_STAGE_RESET_MASK, HB_STAGE_STEP, REWARD_NAMES)
+from .._lib import (EnvBuffers, EnvNoise, EnvParams, HB_NUM_REWARDS, HB_STAGE_DERIVE, HB_STAGE_LAST, HB_STAGE_OBS,
+                    HB_STAGE_PREPARE, HB_STAGE_PUSH, HB_STAGE_RESET_ALL, HB_STAGE_RESET_MASK, HB_STAGE_REWARD, HB_STAGE_STEP,
+                    HB_STAGE_TERMINATION, REWARD_NAMES)
 from .hector_config import class_to_dict
 
 _EXTRAS_RING = 256       # >= num_steps_per_env: episode-mean slots handed out through extras["episode"]
@@ -387,7 +388,7 @@ class HectorFreeEnvB200:
             actions = actions.to(self.device, dtype=torch.float32).contiguous()
         self.common_step_counter += 1
         push = bool(self.cfg.domain_rand.push_robots) and (self.common_step_counter % self.push_interval == 0)
-        if self._graphs is not None and not push and self._injected is None:
+        if self._graphs is not None and not push and self._injected is None and not self._hooks_overridden():
             return self._step_graph(actions, staged)
         self._draw_noise(push)
         _lib.check(lib.hb_env_action_prologue(self._pp, self._pb, actions.data_ptr(), self._pn, st),
@@ -493,11 +494,67 @@ class HectorFreeEnvB200:
         return self.torques
 
     def post_physics_step(self, push: bool = False):
-        """legged_robot.py:118-153 (termination, rewards, resets, observations, last_* copies)."""
+        """legged_robot.py:118-153 (termination, rewards, resets, observations, last_* copies): ONE fused launch plus the
+        frame-stack / finalisation launch.  If a subclass overrides one of the reference's hooks (check_termination,
+        compute_reward, reset_idx, compute_observations), the step instead calls the hooks one after the other in the
+        reference's order, each a launch of the same kernel restricted to that span - same results, six launches."""
         self.physics.refresh_post_physics()
-        self._launch_post(HB_STAGE_STEP | (HB_STAGE_PUSH if push else 0))
+        if not self._hooks_overridden():
+            self._launch_post(HB_STAGE_STEP | (HB_STAGE_PUSH if push else 0))
+        else:
+            self._post_physics_step_staged(push)
         if push:
             self.physics.set_root_state()
+
+    # ------------------------------------------------------------------ the reference's hooks, one by one
+    _HOOKS = ("check_termination", "compute_reward", "reset_idx", "compute_observations")
+
+    def _hooks_overridden(self) -> bool:
+        cls = type(self)
+        flag = cls.__dict__.get("_hooks_overridden_cache")
+        if flag is None:
+            flag = any(getattr(cls, h) is not getattr(HectorFreeEnvB200, h) for h in self._HOOKS)
+            cls._hooks_overridden_cache = flag
+        return flag
+
+    def _launch_stage(self, stages: int) -> None:
+        """One launch of the post-physics kernel restricted to `stages` (PREPARE / TERMINATION / REWARD / LAST bits): it
+        resets nothing, so no finalisation launch follows and the extras ring does not advance."""
+        if self._nz.u_reset is None and self._nz.rng_counter is None:
+            self._draw_noise(False)
+        out = self._cur_buf          # not written: no HB_STAGE_OBS bit
+        _lib.check(self._lib.hb_env_post_physics(self._pp, self._pb, self._pn, out[0].data_ptr(), out[1].data_ptr(), stages,
+                                                 self._stream()), "hb_env_post_physics")
+
+    def _post_physics_step_staged(self, push: bool) -> None:
+        """post_physics_step as the reference spells it (legged_robot.py:118-153), through the overridable hooks."""
+        keep = self._injected         # the step's tape (if any) serves every stage
+        self._launch_stage(HB_STAGE_PREPARE | (HB_STAGE_PUSH if push else 0))      # :127-137
+        self.check_termination()                                                   # :139
+        self.compute_reward()                                                      # :140
+        env_ids = self.reset_buf.nonzero(as_tuple=False).flatten()                 # :142
+        self._injected = keep
+        self.reset_idx(env_ids)                                                    # :143
+        self._injected = keep
+        self.compute_observations()                                                # :144
+        self._injected = keep
+        self._launch_stage(HB_STAGE_LAST)                                          # :146-150
+        self._injected = None
+        self._nz.u_reset = self._nz.rng_counter = None
+
+    def check_termination(self):
+        """legged_robot.py:155-160: reset_buf = contact on a termination body | time-out; time_out_buf."""
+        self._launch_stage(HB_STAGE_TERMINATION)
+
+    def compute_reward(self):
+        """legged_robot.py:216-234: rew_buf, episode_sums (alphabetical accumulation over the 18 active terms) and the
+        stateful reward buffers (feet_air_time, last_contacts, feet_height, last_feet_z)."""
+        self._launch_stage(HB_STAGE_REWARD)
+
+    def compute_observations(self):
+        """hector_env.py:172-254: the newest obs / privileged frames from the current state, pushed onto the 15-frame
+        histories (the frame-stack launch)."""
+        self._launch_post(HB_STAGE_OBS)
 
     def _launch_post(self, stages: int):
         lib, st = self._lib, self._stream()

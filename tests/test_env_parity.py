@@ -19,14 +19,14 @@ pytestmark = pytest.mark.gpu
 EXACT = ("reset", "time_outs", "episode_length_buf", "last_contacts")
 
 
-def make_cuda_env(tape, dev, cfg=None):
+def make_cuda_env(tape, dev, cfg=None, cls=None):
     from isaac_b200.envs.hector_env import HectorFreeEnvB200
     from isaac_b200.physics import SyntheticPhysics
     n = tape.statics.p_gains.shape[0]
     phys = SyntheticPhysics(n, device=dev)
     phys.load_frame(tape.physics[0].to(dev))
-    env = HectorFreeEnvB200(cfg or HectorCfg(), sim_device=str(dev), physics=phys, statics=tape.statics,
-                            initial_noise=tape.noise[0].to(dev))
+    env = (cls or HectorFreeEnvB200)(cfg or HectorCfg(), sim_device=str(dev), physics=phys, statics=tape.statics,
+                                     initial_noise=tape.noise[0].to(dev))
     env.episode_length_buf.copy_(tape.statics.episode_length0)
     return env, phys
 
@@ -49,8 +49,8 @@ class _View:
         return getattr(self._env, k).cpu()
 
 
-def run_cuda_case(tape, dev, step_counter0=0, cfg=None):
-    env, phys = make_cuda_env(tape, dev, cfg=cfg)
+def run_cuda_case(tape, dev, step_counter0=0, cfg=None, cls=None):
+    env, phys = make_cuda_env(tape, dev, cfg=cfg, cls=cls)
     env.common_step_counter = step_counter0
     rec = {"obs_init": to_np(env.obs_buf), "priv_init": to_np(env.privileged_obs_buf)}
     ids_per_step, out = [], None
@@ -159,6 +159,64 @@ def test_env_matches_oracle_at_baseline_sizes(lib, cuda_device, n, steps, dr):
     assert sum(len(i) for i in want_ids) > n // 200 and phys.calls["set_root_state"] >= 1
     if dr:
         assert tape.statics.p_gains.std() > 1 and tape.statics.env_frictions.unique().numel() > 100
+
+
+def test_overridden_hooks_run_the_staged_step(lib, cuda_device):
+    """check_termination / compute_reward / reset_idx / compute_observations are overridable hooks with the
+    reference's names.  A subclass that overrides them (here: pass-through overrides that count their calls) makes
+    post_physics_step call them one by one in the reference's order (legged_robot.py:118-153), each a launch of the same
+    kernel restricted to that span - and the golden rollout of the unmodified reference must come out all the same,
+    resets, time-outs, push step and extras included.  A second subclass changes the reward through its hook."""
+    from isaac_b200.envs.hector_env import HectorFreeEnvB200
+    calls = {"check_termination": 0, "compute_reward": 0, "reset_idx": 0, "compute_observations": 0}
+
+    class Staged(HectorFreeEnvB200):
+        def check_termination(self):
+            calls["check_termination"] += 1
+            super().check_termination()
+
+        def compute_reward(self):
+            calls["compute_reward"] += 1
+            super().compute_reward()
+
+        def reset_idx(self, env_ids):
+            calls["reset_idx"] += 1
+            super().reset_idx(env_ids)
+
+        def compute_observations(self):
+            calls["compute_observations"] += 1
+            super().compute_observations()
+
+    g = dict(np.load(f"{GOLDEN}/env_rollout_ref.npz"))
+    tape = mg.env_golden_tape()
+    rec, ids, env, phys = run_cuda_case(tape, cuda_device, mg.ENV_CASE["step_counter0"], cls=Staged)
+    steps = mg.ENV_CASE["steps"] - 1
+    assert calls["check_termination"] == calls["compute_reward"] == calls["compute_observations"] == steps
+    assert calls["reset_idx"] == steps, "reset_idx is called every step (with an empty id list on most)"
+    compare_records(rec, g)
+    for t, got in enumerate(ids):
+        want = np.nonzero(g["reset"][t])[0].astype(np.int32)
+        if len(want):            # on steps without resets the staged path launches no finalisation: the list is stale
+            assert_equal(f"reset_env_ids@{t}", got[:len(want)], want)
+
+    class Bonus(HectorFreeEnvB200):
+        def compute_reward(self):
+            super().compute_reward()
+            self.rew_buf += 1.0
+
+    tape2 = make_tape(64, 3, seed=5)
+    plain, p1 = make_cuda_env(tape2, cuda_device)
+    bonus, p2 = make_cuda_env(tape2, cuda_device, cls=Bonus)
+    for t in (1, 2):
+        a = cuda_step(plain, p1, tape2.physics[t], tape2.noise[t], cuda_device)
+        b = cuda_step(bonus, p2, tape2.physics[t], tape2.noise[t], cuda_device)
+        assert torch.equal(b[2], a[2] + 1.0) and torch.equal(a[0], b[0]) and torch.equal(a[3], b[3])
+    # the hooks also work on their own, on the current buffers (what play.py-style code does)
+    before = plain.rew_buf.clone()
+    plain.check_termination()
+    f = tape2.physics[2].contact_forces.to(cuda_device)
+    want_reset = (f[:, [0, 3, 8]].norm(dim=-1) > 1.0).any(dim=1) | (plain.episode_length_buf > 2400)
+    assert torch.equal(plain.reset_buf, want_reset) and torch.equal(plain.rew_buf, before)
 
 
 def test_pd_torque_law(lib, cuda_device):

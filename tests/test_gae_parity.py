@@ -41,7 +41,7 @@ def test_gae_single_launch_matches_oracle(lib, cuda_device, T, N):
     want_ret, want_adv = gae_returns(rewards, values, dones, last, 0.994, 0.9)
     for rep in range(2):
         ret, adv = run_cuda_gae(lib, cuda_device, rewards, values, dones, last, 0.994, 0.9, fused=True)
-        if T <= 64:
+        if T <= 100:
             assert torch.equal(ret, want_ret), "the reference's own loop and operation order, no FMA contraction: the same bits"
         assert_close("returns", ret.numpy(), want_ret.numpy(), rtol=1e-5, atol=1e-5)
         assert_close("advantages", adv.numpy(), want_adv.numpy(), rtol=1e-5, atol=1e-5)

@@ -273,7 +273,7 @@ def test_update_graph_replay_equals_eager(lib, cuda_device):
             alg.update()
         assert len(pair[0]._update_graphs) == (0 if it == 0 else cfg["num_mini_batches"])
         np.testing.assert_allclose(pair[0].lr_trace, pair[1].lr_trace, rtol=1e-12)
-        np.testing.assert_allclose(pair[0].kl_trace, pair[1].kl_trace, rtol=1e-3, atol=1e-7)
+        np.testing.assert_allclose(pair[0].kl_trace, pair[1].kl_trace, rtol=2e-2, atol=1e-7)
         assert pair[0]._step == pair[1]._step == 20 * (it + 1)
         assert int(pair[0]._opt_i64[10].item()) == pair[0]._step, "device-side Adam step count"
         # Same arithmetic, different order of the split-K float atomics: Adam divides by sqrt(v), so weights whose
