@@ -519,7 +519,9 @@ def run_b200(args, rank, world):
         (cold) buffers: the graph-launch latency in front of the first kernel is amortised over the chain."""
         def body(st_):
             for fn in fns:
-                _lib.check(fn(st_), "time_chain")
+                rc = fn(st_)
+                if rc not in (0, None):
+                    _lib.check(rc, "time_chain")
         g = _lib.LaunchGraph(dev).record(body)
         tot = 0.0
         for r in range(reps + 2):
@@ -543,12 +545,13 @@ def run_b200(args, rank, world):
     k_obs = time_launch(lambda st: lib.hb_stack_shift(dense[2].data_ptr(), dense[3].data_ptr(), rb, n,
                                                    STACK_OBS * FRAME_OBS, FRAME_OBS, st))
     del dense
-    k_pd = time_launch(lambda st: lib.hb_env_compute_torques(P, B, st))
+    # short kernels: chains (CUDA events tick in ~2 us steps), per-launch time = chain / length
+    k_pd = time_chain([lambda st: lib.hb_env_compute_torques(P, B, st)] * 8)
     env._draw_noise(False)              # device generator, like the replayed step
-    k_post = time_launch(lambda st: lib.hb_env_post_physics(P, B, env._pn, o_cur.data_ptr(), p_cur.data_ptr(),
-                                                         _lib.HB_STAGE_STEP, st))
-    k_fin = time_launch(lambda st: lib.hb_env_reset_finalize(P, B, o_cur.data_ptr(), p_cur.data_ptr(),
-                                                          env._host_count.data_ptr(), None, st))
+    k_post = time_chain([lambda st: lib.hb_env_post_physics(P, B, env._pn, o_cur.data_ptr(), p_cur.data_ptr(),
+                                                         _lib.HB_STAGE_STEP, st)] * 4)
+    k_fin = time_chain([lambda st: lib.hb_env_reset_finalize(P, B, o_cur.data_ptr(), p_cur.data_ptr(),
+                                                          env._host_count.data_ptr(), None, st)] * 4)
     k_stack_single = time_launch(lambda st: lib.hb_env_stack_observations(P, B, o_prev.data_ptr(), p_prev.data_ptr(),
                                                                        o_cur.data_ptr(), p_cur.data_ptr(), st))
     # the roofline kernel: 4 launches per timed replay, each on its own cold set of history buffers
@@ -560,18 +563,26 @@ def run_b200(args, rank, world):
                                                                       s_[2].data_ptr(), s_[3].data_ptr(),
                                                                       env._host_count.data_ptr(), None, st)) for s_ in sets])
     del sets
-    # GAE
+    # GAE: CUDA events tick in ~2 us steps on this driver, so one short launch cannot be timed alone - a graph of 8
+    # launches on 8 distinct (cold) buffer sets, / 8
     g = torch.Generator().manual_seed(rank)
-    r_, v_ = torch.rand(T_GAE, n, 1, generator=g).to(dev), torch.randn(T_GAE, n, 1, generator=g).to(dev)
-    d_, lv_ = (torch.rand(T_GAE, n, 1, generator=g) < 0.005).byte().to(dev), torch.randn(n, 1, generator=g).to(dev)
-    ret_, adv_ = torch.empty_like(r_), torch.empty_like(r_)
-    gae_compute_returns(r_, v_, d_, lv_, ret_, adv_, 0.994, 0.9)          # allocates the launch's scratch before capture
-    k_gae = time_launch(lambda st: gae_compute_returns(r_, v_, d_, lv_, ret_, adv_, 0.994, 0.9) and None)      # hb_gae_fused: one launch
-    lib.hb_set_option(b"coop_launch", 1)
-    k_gae_coop = time_launch(lambda st: gae_compute_returns(r_, v_, d_, lv_, ret_, adv_, 0.994, 0.9) and None)
-    lib.hb_set_option(b"coop_launch", 0)
+    gsets = []
+    for _ in range(8):
+        r_, v_ = torch.rand(T_GAE, n, 1, generator=g).to(dev), torch.randn(T_GAE, n, 1, generator=g).to(dev)
+        d_, lv_ = (torch.rand(T_GAE, n, 1, generator=g) < 0.005).byte().to(dev), torch.randn(n, 1, generator=g).to(dev)
+        gsets.append((r_, v_, d_, lv_, torch.empty_like(r_), torch.empty_like(r_)))
+    gae_compute_returns(*gsets[0], 0.994, 0.9)          # allocates the launch's scratch before capture
     gae_stats = torch.zeros(2, dtype=torch.float64, device=dev)
-    k_gae_two = time_launch(lambda st: gae_compute_returns(r_, v_, d_, lv_, ret_, adv_, 0.994, 0.9, stats=gae_stats) and None)
+
+    def gae_chain(**kw):
+        return time_chain([(lambda st, s_=s_: gae_compute_returns(*s_, 0.994, 0.9, **kw) and 0) for s_ in gsets])
+
+    k_gae = gae_chain()                                  # hb_gae_fused: one launch
+    lib.hb_set_option(b"coop_launch", 1)
+    k_gae_coop = gae_chain()
+    lib.hb_set_option(b"coop_launch", 0)
+    k_gae_two = gae_chain(stats=gae_stats)               # memset + scan + normalise
+    del gsets
     ppo = None if args.skip_ppo else bench_ppo(args, dev, n, world, rank, env, phys, phys_frames)
     clocks = sampler.summary()
 

@@ -207,7 +207,9 @@ def test_update_matches_reference_golden(lib, cuda_device, schedule, precision):
     g = np.load(f"{mg.GOLDEN_DIR}/ppo_update_ref.npz")
     np.testing.assert_allclose([w_v, w_s], g[f"{schedule}/losses"], rtol=1e-5)       # oracle == reference
     np.testing.assert_allclose(ora.lr_trace, g[f"{schedule}/lr_trace"], rtol=1e-12)
-    loss_tol = 5e-3 if precision == "tf32" else 2e-5
+    # (adaptive golden case: KL up to 0.23 at rates up to 3e-3 - one sample changing its clipping branch moves the mean
+    # losses by ~4e-4, and which way it falls depends on the order of the split-K float atomics)
+    loss_tol = 5e-3 if precision == "tf32" else (2e-5 if schedule == "fixed" else 1e-3)
     assert abs(v_loss - w_v) < loss_tol * max(1.0, abs(w_v)) and abs(s_loss - w_s) < loss_tol, (v_loss, w_v, s_loss, w_s)
     sd = alg.actor_critic.state_dict()
     steps_taken = mg.PPO_ALG["num_learning_epochs"] * mg.PPO_ALG["num_mini_batches"]
