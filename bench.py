@@ -363,7 +363,9 @@ def bench_ppo(args, dev, n, world, rank, env=None, phys=None, phys_frames=None):
     alg.init_storage(n, T_GAE, [615], [1050], [10])
     if world > 1:
         from isaac_b200.parallel import attach_data_parallel
-        attach_data_parallel(alg, env=env)
+        # default: ONE kernel per rank over NVLink peer memory (reduce + clip + Adam + broadcast); HB_DP_FUSED=0 = NCCL
+        attach_data_parallel(alg, env=env, fused=os.environ.get("HB_DP_FUSED", "1") != "0",
+                             use_multicast=os.environ.get("HB_DP_MULTICAST", "1") != "0")
     last = torch.randn(n, 1050, device=dev)
     stream = torch.cuda.current_stream(dev)
     # rollout side: PPO.act + process_env_step per env step, T steps; the observations are
@@ -407,6 +409,9 @@ def bench_ppo(args, dev, n, world, rank, env=None, phys=None, phys_frames=None):
            "iteration": iteration,
            "ms_per_update": ms, "T": T_GAE, "epochs": 5, "mini_batches": 4, "dtype": "tf32 operands, f32 accumulate",
            "tensor_tflops": tflops, "fp32_grade": fp32_grade,
+           "gradient_exchange": ("single GPU" if world == 1 else
+                                 ("hb_dp_optimizer_step over peer memory" + (" (NVLS multimem)" if alg._peer.multicast else " (peer loads / stores)")
+                                  if alg._peer is not None else "NCCL all-reduce of the flat gradient + local optimizer step")),
            "mean_kl": mean_kl, "learning_rate": lr_after,
            "rollout_act_and_record_ms_per_step": roll_ms}
     if peak is not None:

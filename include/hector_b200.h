@@ -419,7 +419,9 @@ typedef struct hb_optim_state {
     int64_t step;                 /* Adam's step count t (bias corrections 1 - beta^t) */
     int64_t steps_in_update;      /* optimizer steps since the host last zeroed it: index into trace */
     uint64_t ticket;              /* grid barrier of hb_optimizer_step; zero between steps */
-    uint64_t reserved;
+    uint64_t reserved;            /* hb_dp_optimizer_step: 0, or the phase in which a peer failed to arrive (time-out) */
+    uint64_t go;                  /* hb_dp_optimizer_step: local gate, monotonic */
+    float bcast[4];               /* hb_dp_optimizer_step: clip scale, step size, sqrt(bias_correction2) of the step */
     double trace[2 * HB_OPT_TRACE_MAX];   /* {mean KL, learning rate after the rule} of step i < HB_OPT_TRACE_MAX of the update */
 } hb_optim_state;
 
@@ -429,6 +431,27 @@ typedef struct hb_optim_state {
  * state->stats folded into state->loss_acc and zeroed, state->step and state->steps_in_update advanced. */
 int hb_optimizer_step(float *params, float *grads, float *exp_avg, float *exp_avg_sq, int64_t n, const hb_adam_params *ap,
                       hb_optim_state *state, void *stream);
+
+/* Data-parallel replicas (the reference is single-device).  Every rank's flat gradient / parameter
+ * buffers, a mailbox and a flag array are mapped into every rank's address space (symmetric memory over NVLink /
+ * NVSwitch; the host passes the peer pointers).  hb_dp_optimizer_step is ONE kernel per rank that replaces the gradient
+ * all-reduce, clip_grad_norm_, Adam, zero_grad and the parameter broadcast: each rank sums ITS 1/world slice of the
+ * gradient over all ranks (peer loads, or multimem.ld_reduce through the switch when grad_mc is set), exchanges slice
+ * norms and loss sums through the mailboxes, applies clip + Adam to its slice (optimizer state is sharded: a rank only
+ * touches its slice of exp_avg / exp_avg_sq) and stores the new parameters into all ranks' buffers (peer stores or
+ * multimem.st).  state as in hb_optimizer_step; state->reserved != 0 afterwards means a peer did not arrive in time.
+ * All ranks must call it the same number of times with the same state->step. */
+#define HB_DP_MAX_RANKS 8
+typedef struct hb_dp_comm {
+    int32_t world, rank;
+    float *grad[HB_DP_MAX_RANKS];      /* flat gradient buffers (n floats), [rank] = this rank's own */
+    float *param[HB_DP_MAX_RANKS];     /* flat parameter buffers (n floats) */
+    double *mail[HB_DP_MAX_RANKS];     /* mailboxes: HB_DP_MAX_RANKS x 8 doubles each */
+    uint32_t *flag[HB_DP_MAX_RANKS];   /* flag arrays: 3 x HB_DP_MAX_RANKS words each, zero before the first step */
+    float *grad_mc, *param_mc;         /* multicast (NVLS) addresses of the gradient / parameter buffers, or NULL */
+} hb_dp_comm;
+int hb_dp_optimizer_step(const hb_dp_comm *comm, float *exp_avg, float *exp_avg_sq, int64_t n, const hb_adam_params *ap,
+                         hb_optim_state *state, void *stream);
 
 #ifdef __cplusplus
 }

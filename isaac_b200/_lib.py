@@ -113,11 +113,19 @@ class OptimState(C.Structure):
     integer fields are read through an int64 view (indices below are in 8-byte words)."""
     _fields_ = [("lr", C.c_double), ("grad_sumsq", C.c_double), ("stats", C.c_double * 4), ("loss_acc", C.c_double * 4),
                 ("step", C.c_int64), ("steps_in_update", C.c_int64), ("ticket", C.c_uint64), ("reserved", C.c_uint64),
-                ("trace", C.c_double * (2 * HB_OPT_TRACE_MAX))]
+                ("go", C.c_uint64), ("bcast", _f * 4), ("trace", C.c_double * (2 * HB_OPT_TRACE_MAX))]
 
 
 OPTIM_STATE_DOUBLES = C.sizeof(OptimState) // 8
-OPT_LR, OPT_SUMSQ, OPT_STATS, OPT_LOSS_ACC, OPT_STEP, OPT_STEPS_IN_UPDATE, OPT_TICKET, OPT_TRACE = 0, 1, 2, 6, 10, 11, 12, 14
+OPT_LR, OPT_SUMSQ, OPT_STATS, OPT_LOSS_ACC, OPT_STEP, OPT_STEPS_IN_UPDATE, OPT_TICKET, OPT_ERROR, OPT_TRACE = 0, 1, 2, 6, 10, 11, 12, 13, 17
+assert OptimState.trace.offset == 8 * OPT_TRACE and OptimState.reserved.offset == 8 * OPT_ERROR
+
+HB_DP_MAX_RANKS = 8
+
+
+class DpComm(C.Structure):
+    _fields_ = [("world", _i), ("rank", _i), ("grad", _fp * HB_DP_MAX_RANKS), ("param", _fp * HB_DP_MAX_RANKS),
+                ("mail", _fp * HB_DP_MAX_RANKS), ("flag", _fp * HB_DP_MAX_RANKS), ("grad_mc", _fp), ("param_mc", _fp)]
 
 
 class HectorB200Error(RuntimeError):
@@ -168,6 +176,8 @@ _SIGNATURES = {
     "hb_ppo_draw_normal": (C.c_int, [_fp, C.c_int64, _fp, _fp]),
     "hb_ppo_act_head": (C.c_int, [_fp, C.c_int32, _fp, _fp, C.c_int64, _fp, _fp, _fp, _fp, _fp]),
     "hb_optimizer_step": (C.c_int, [_fp, _fp, _fp, _fp, C.c_int64, C.POINTER(AdamParams), _fp, _fp]),
+    "hb_dp_optimizer_step": (C.c_int, [C.POINTER(DpComm), _fp, _fp, C.c_int64, C.POINTER(AdamParams), _fp, _fp]),
+    "hb_sizeof_dp_comm": (C.c_int, []),
     "hb_gae_returns": (C.c_int, [_fp, _fp, _fp, _fp, _fp, _fp, _fp, C.c_int32, C.c_int32, C.c_float, C.c_float, _fp]),
     "hb_gae_fused": (C.c_int, [_fp, _fp, _fp, _fp, _fp, _fp, _fp, C.c_int32, C.c_int32, C.c_float, C.c_float, _fp]),
     "hb_gae_normalize": (C.c_int, [_fp, _fp, C.c_int64, _fp]),
@@ -191,7 +201,7 @@ def load(check_device: bool = False) -> C.CDLL:
             raise HectorB200Error("ABI version mismatch between libhectorb200.so and isaac_b200/_lib.py")
         for fn, cls in ((lib.hb_sizeof_env_params, EnvParams), (lib.hb_sizeof_env_buffers, EnvBuffers),
                         (lib.hb_sizeof_env_noise, EnvNoise), (lib.hb_sizeof_adam_params, AdamParams),
-                        (lib.hb_sizeof_gemm_desc, GemmDesc),
+                        (lib.hb_sizeof_gemm_desc, GemmDesc), (lib.hb_sizeof_dp_comm, DpComm),
                         (lib.hb_sizeof_optim_state, OptimState)):
             if fn() != C.sizeof(cls):
                 raise HectorB200Error(f"struct {cls.__name__}: header says {fn()} bytes, ctypes mirror {C.sizeof(cls)}")

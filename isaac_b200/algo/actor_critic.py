@@ -101,6 +101,14 @@ class ActorCritic:
         self.precision = precision
         self._scratch = {"actor": [None, self.device], "critic": [None, self.device]}     # one per stream / network
 
+    def rebind(self, flat: torch.Tensor, grad_wire: torch.Tensor) -> None:
+        """Move the flat parameter / gradient buffers to caller-provided storage of the same size (symmetric memory for
+        data-parallel replicas); contents are the caller's responsibility."""
+        if flat.numel() != self.flat.numel() or grad_wire.numel() != self._grad_wire.numel():
+            raise ValueError("rebind needs buffers of the same size")
+        self.flat, self._grad_wire = flat, grad_wire
+        self.grad = grad_wire[:flat.numel()]
+
     # ------------------------------------------------------------------ parameter views
     def _matrix(self, flat, L):
         return flat[L.offset:L.offset + L.numel].view(L.rows, L.ld)

@@ -20,7 +20,7 @@ from typing import Optional
 import torch
 
 from .. import _lib
-from .._lib import (AdamParams, HB_OPT_TRACE_MAX, HB_PPO_REC, OPT_LOSS_ACC, OPT_LR, OPT_STATS, OPT_STEP,
+from .._lib import (AdamParams, HB_OPT_TRACE_MAX, HB_PPO_REC, OPT_ERROR, OPT_LOSS_ACC, OPT_LR, OPT_STATS, OPT_STEP,
                     OPT_STEPS_IN_UPDATE, OPT_SUMSQ, OPT_TRACE, OPTIM_STATE_DOUBLES, PpoLossParams)
 from .actor_critic import ActorCritic, pad4
 from .rollout_storage import RolloutStorage
@@ -47,7 +47,10 @@ class _AdamState:
         p = self._ppo
         state = {}
         if p._step > 0:
-            for i, (m, v) in enumerate(zip(self._views(p._exp_avg), self._views(p._exp_avg_sq))):
+            exp_avg, exp_avg_sq = p._exp_avg, p._exp_avg_sq
+            if p._peer is not None:          # sharded optimizer state: every rank owns a slice
+                exp_avg, exp_avg_sq = p._peer.gather_sharded(exp_avg), p._peer.gather_sharded(exp_avg_sq)
+            for i, (m, v) in enumerate(zip(self._views(exp_avg), self._views(exp_avg_sq))):
                 state[i] = {"step": torch.tensor(float(p._step)), "exp_avg": m.clone().contiguous(),
                             "exp_avg_sq": v.clone().contiguous()}
         groups = [dict(self.param_groups[0], lr=p.learning_rate)]
@@ -96,7 +99,8 @@ class PPO:
         self._lr_dev.fill_(float(learning_rate))
         self._lr_dirty = False
         self.optimizer = _AdamState(self)
-        self.grad_allreduce = None          # multi-GPU hook: fn(flat_grad) sums gradients over ranks
+        self.grad_allreduce = None          # multi-GPU hook: fn(flat_grad) sums gradients over ranks (NCCL path)
+        self._peer = None                   # multi-GPU: isaac_b200.parallel.PeerOptimizer (fused reduce + Adam + broadcast)
         self.world_size = 1
         self.injected_eps = None            # parity: the Normal.sample() draw of the next act()
         self.injected_perm = None           # parity: the randperm of the next update()
@@ -164,6 +168,12 @@ class PPO:
         self._eps_seed = int(seed) & 0xFFFFFFFFFFFFFFFF
         signed = self._eps_seed - (1 << 64) if self._eps_seed >= (1 << 63) else self._eps_seed
         self._eps_state.copy_(torch.tensor([0, 0, signed], dtype=torch.int64))
+
+    def attach_peer_optimizer(self, peer) -> None:
+        """Data-parallel replica: the optimizer step becomes hb_dp_optimizer_step over `peer`'s symmetric buffers (the
+        ActorCritic has been re-bound to them); graphs that baked the old buffer addresses are dropped."""
+        self._peer = peer
+        self._act_graphs.clear(), self._update_graphs.clear()
 
     def _set_step(self, step: int) -> None:
         """Adam's step count (host mirror + hb_optim_state.step)."""
@@ -388,9 +398,13 @@ class PPO:
         st = torch.cuda.current_stream(self.device).cuda_stream
         ap = AdamParams(0.9, 0.999, 1e-8, float(self.max_grad_norm or 0.0), adaptive, float(self.desired_kl or 0.0),
                         self._mb * self.world_size)
-        _lib.check(lib.hb_optimizer_step(ac.flat.data_ptr(), ac.grad.data_ptr(), self._exp_avg.data_ptr(),
-                                         self._exp_avg_sq.data_ptr(), ac.flat.numel(), C.byref(ap), self._opt.data_ptr(), st),
-                   "hb_optimizer_step")
+        if self._peer is not None:          # all ranks: reduce + clip + Adam + broadcast over peer memory, one kernel
+            _lib.check(lib.hb_dp_optimizer_step(self._peer.comm_ref, self._exp_avg.data_ptr(), self._exp_avg_sq.data_ptr(),
+                                                ac.flat.numel(), C.byref(ap), self._opt.data_ptr(), st), "hb_dp_optimizer_step")
+        else:
+            _lib.check(lib.hb_optimizer_step(ac.flat.data_ptr(), ac.grad.data_ptr(), self._exp_avg.data_ptr(),
+                                             self._exp_avg_sq.data_ptr(), ac.flat.numel(), C.byref(ap), self._opt.data_ptr(), st),
+                       "hb_optimizer_step")
         self._step += 1
 
     def _update_graph(self, i: int, adaptive: int):
@@ -472,6 +486,9 @@ class PPO:
         denom = num_updates * mb * self.world_size
         mean_surrogate_loss, mean_value_loss = float(acc[0]) / denom, float(acc[1]) / denom
         self.last_mean_kl = float(acc[2]) / denom
+        err = int(host.view(torch.int64)[OPT_ERROR])
+        if self._peer is not None and err != 0:
+            raise _lib.HectorB200Error(f"hb_dp_optimizer_step: a peer rank did not arrive (phase {err})")
         k = min(num_updates, HB_OPT_TRACE_MAX)
         trace = host[OPT_TRACE:OPT_TRACE + 2 * k].view(k, 2)
         self.kl_trace, self.lr_trace = trace[:, 0].tolist(), trace[:, 1].tolist()     # per optimizer step of this update

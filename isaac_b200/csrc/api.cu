@@ -53,6 +53,7 @@ int hb_sizeof_env_noise(void) { return (int)sizeof(hb_env_noise); }
 int hb_sizeof_gemm_desc(void) { return (int)sizeof(hb_gemm_desc); }
 int hb_sizeof_adam_params(void) { return (int)sizeof(hb_adam_params); }
 int hb_sizeof_optim_state(void) { return (int)sizeof(hb_optim_state); }
+int hb_sizeof_dp_comm(void) { return (int)sizeof(hb_dp_comm); }
 
 // The kernels are sm_100a-only (no other cubin or PTX is embedded): refuse anything else loudly.
 int hb_check_device(void) {

@@ -561,6 +561,255 @@ optimizer_step_kernel(float *__restrict__ p, float *__restrict__ g, float *__res
         }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Data-parallel optimizer step over peer memory: ONE kernel per rank replaces the gradient all-reduce
+// (NCCL), clip_grad_norm_, Adam and the parameter broadcast.  Every rank's flat gradient and parameter buffers are
+// mapped into every other rank's address space (NVLink / NVSwitch peer access; the host passes the pointers):
+//   start barrier (flags)    every rank's backward has finished
+//   phase A                  rank r reads ITS 1/G slice of the flat gradient from all G ranks (peer loads, or one
+//                            multimem.ld_reduce per vector when the NVSwitch multicast address is given), sums them in
+//                            registers and reduces the slice's sum of squares over the grid
+//   mailbox exchange         slice norms and the minibatch's loss sums go to every peer (5 doubles), flag barrier: every
+//                            rank now derives the same clip coefficient, KL mean and learning rate
+//   phase B                  Adam on the slice (optimizer state is sharded: a rank only ever touches its slice of m, v),
+//                            the new parameters are stored into ALL ranks' parameter buffers (peer stores / multimem.st);
+//                            the rank's own gradient buffer is zeroed
+//   end barrier              all slices have landed in this rank's parameters before the next forward pass reads them
+// NVLink traffic per rank and step: (G-1)/G of the gradient in, (G-1)/G of the parameters out (2 x 5.3 MB at G = 8)
+// instead of NCCL's ring / tree passes over the whole buffer, and no SM hand-over between NCCL and the GEMMs.
+// Spin loops give up after ~2 s and set state->reserved (a rank that never arrives must not hang the GPU).
+// ------------------------------------------------------------------------------------------------------------
+constexpr int DP_THREADS = 256;
+constexpr int DP_REGV = 8;
+constexpr int DP_MAIL = 8;           // doubles per sender in a mailbox
+
+__device__ __forceinline__ void st_release_sys_u32(uint32_t *p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ float4 multimem_ld_reduce4(const float *mc) {
+    float4 v;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(mc)
+                 : "memory");
+    return v;
+}
+__device__ __forceinline__ void multimem_st4(float *mc, const float4 &v) {
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(mc), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                 : "memory");
+}
+// bounded spin: false on time-out
+template <typename Pred>
+__device__ __forceinline__ bool spin_until(Pred done) {
+    const long long t0 = clock64();
+    while (!done()) {
+        if (clock64() - t0 > 4000000000ll) return false;       // ~2 s at 2 GHz
+    }
+    return true;
+}
+
+// cross-rank barrier by the first `world` threads of one block: tell every peer, wait for every peer
+__device__ __forceinline__ bool rank_barrier(const hb_dp_comm &c, int phase, uint32_t epoch) {
+    bool ok = true;
+    if ((int)threadIdx.x < c.world) {
+        const int peer = threadIdx.x;
+        st_release_sys_u32(c.flag[peer] + phase * HB_DP_MAX_RANKS + c.rank, epoch);
+        const uint32_t *mine = c.flag[c.rank] + phase * HB_DP_MAX_RANKS + peer;
+        ok = spin_until([&] { return ld_acquire_sys_u32(mine) >= epoch; });
+    }
+    return __syncthreads_and(ok);
+}
+
+__global__ void __launch_bounds__(DP_THREADS)
+dp_optimizer_step_kernel(const __grid_constant__ hb_dp_comm c, float *__restrict__ m, float *__restrict__ v, long long n,
+                         const hb_adam_params ap, hb_optim_state *__restrict__ st) {
+    __shared__ double s_red[DP_THREADS / 32];
+    __shared__ float s_scal[3];
+    __shared__ int s_flag;
+    const int W = c.world, R = c.rank;
+    const long long nvec = n >> 2;
+    const long long per = (nvec + W - 1) / W, lo = (long long)R * per, hi = lo + per < nvec ? lo + per : nvec;
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, stride = (long long)gridDim.x * blockDim.x;
+    unsigned long long *ticket = reinterpret_cast<unsigned long long *>(&st->ticket);
+    unsigned long long *go = reinterpret_cast<unsigned long long *>(&st->go);
+    const uint32_t epoch = (uint32_t)(st->step + 1);                // identical on every rank, advances every step
+    float *g_own = c.grad[R], *p_own = c.param[R];
+
+    // ---- start barrier: block 0 meets the peers, then opens the local gate ----
+    if (blockIdx.x == 0) {
+        const bool ok = rank_barrier(c, 0, epoch);
+        if (threadIdx.x == 0) {
+            if (!ok) st->reserved = 1;
+            __threadfence();
+            atomicExch(go, 3ull * epoch + 1ull);
+        }
+    }
+    if (threadIdx.x == 0) {
+        const bool ok = spin_until([&] { return ld_acquire_u64(go) >= 3ull * epoch + 1ull; });
+        if (!ok) st->reserved = 2;
+    }
+    __syncthreads();
+
+    // ---- phase A: reduce this rank's slice of the gradient over all ranks ----
+    float4 gv[DP_REGV];
+    double acc = 0.0;
+    auto reduce_vec = [&](long long i) {
+        if (c.grad_mc) return multimem_ld_reduce4(c.grad_mc + 4 * i);
+        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+        for (int p = 0; p < W; ++p) {
+            const float4 x = *reinterpret_cast<const float4 *>(c.grad[p] + 4 * i);
+            s.x += x.x, s.y += x.y, s.z += x.z, s.w += x.w;
+        }
+        return s;
+    };
+#pragma unroll
+    for (int k = 0; k < DP_REGV; ++k) {
+        const long long i = lo + tid + k * stride;
+        gv[k] = (i < hi) ? reduce_vec(i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        acc += ((double)gv[k].x * gv[k].x + (double)gv[k].y * gv[k].y) + ((double)gv[k].z * gv[k].z + (double)gv[k].w * gv[k].w);
+    }
+    // longer slices: the sums are parked in this rank's OWN gradient buffer - no other rank reads that range (every rank
+    // reads only its own slice of everybody's buffer), and each element is read before it is overwritten by the same thread
+    for (long long i = lo + tid + DP_REGV * stride; i < hi; i += stride) {
+        const float4 x = reduce_vec(i);
+        acc += ((double)x.x * x.x + (double)x.y * x.y) + ((double)x.z * x.z + (double)x.w * x.w);
+        *reinterpret_cast<float4 *>(g_own + 4 * i) = x;
+    }
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < DP_THREADS / 32; ++w) t += s_red[w];
+        atomicAdd(&st->grad_sumsq, t);
+        __threadfence();
+        s_flag = (atomicAdd(ticket, 1ull) == (unsigned long long)gridDim.x - 1ull);
+    }
+    __syncthreads();
+    // ---- mailbox exchange by the last block of this rank ----
+    if (s_flag) {
+        if ((int)threadIdx.x < W) {
+            double *box = c.mail[threadIdx.x] + (size_t)R * DP_MAIL;           // my row in the peer's mailbox
+            const volatile hb_optim_state *sv = st;
+            box[0] = sv->grad_sumsq;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) box[1 + k] = sv->stats[k];
+            __threadfence_system();
+        }
+        __syncthreads();
+        const bool ok = rank_barrier(c, 1, epoch);
+        if (threadIdx.x == 0) {
+            if (!ok) st->reserved = 3;
+            double sumsq = 0.0, tot[4] = {0.0, 0.0, 0.0, 0.0};
+            const volatile double *mine = c.mail[R];
+            for (int p = 0; p < W; ++p) {
+                sumsq += mine[p * DP_MAIL];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) tot[k] += mine[p * DP_MAIL + 1 + k];
+            }
+            double lr = st->lr;
+            const double kl = tot[2] / (double)ap.kl_count;
+            if (ap.adaptive) {
+                if (kl > ap.desired_kl * 2.0) lr = fmax(1e-5, lr / 1.5);
+                else if (kl < ap.desired_kl / 2.0 && kl > 0.0) lr = fmin(1e-2, lr * 1.5);
+            }
+            float scale = 1.0f;
+            if (ap.max_grad_norm > 0.0f) {
+                const float total = (float)sqrt(sumsq);
+                const float coef = ap.max_grad_norm / (total + 1e-6f);
+                scale = coef < 1.0f ? coef : 1.0f;
+            }
+            const long long t_adam = st->step + 1;
+            const double bc1 = 1.0 - pow(ap.beta1, (double)t_adam), bc2 = 1.0 - pow(ap.beta2, (double)t_adam);
+            st->bcast[0] = scale, st->bcast[1] = (float)(lr / bc1), st->bcast[2] = (float)sqrt(bc2);
+            // the step's bookkeeping (same totals on every rank)
+            const long long idx = st->steps_in_update;
+            if (idx >= 0 && idx < HB_OPT_TRACE_MAX) st->trace[2 * idx] = kl, st->trace[2 * idx + 1] = lr;
+            st->steps_in_update = idx + 1;
+            st->lr = lr;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) st->loss_acc[k] += tot[k], st->stats[k] = 0.0;
+            st->grad_sumsq = 0.0;
+            *ticket = 0ull;
+            __threadfence();
+            atomicExch(go, 3ull * epoch + 2ull);
+        }
+    }
+    if (threadIdx.x == 0) {
+        const bool ok = spin_until([&] { return ld_acquire_u64(go) >= 3ull * epoch + 2ull; });
+        if (!ok) st->reserved = 4;
+        const volatile float *bc = st->bcast;
+        s_scal[0] = bc[0], s_scal[1] = bc[1], s_scal[2] = bc[2];
+    }
+    __syncthreads();
+
+    // ---- phase B: Adam on the slice, parameters out to every rank, own gradients zeroed ----
+    const float scale = s_scal[0], step_size = s_scal[1], bc2_sqrt = s_scal[2];
+    const float w1 = (float)(1.0 - ap.beta1), b2 = (float)ap.beta2, w2 = (float)(1.0 - ap.beta2), eps = (float)ap.eps;
+    auto update = [&](float &pi, float gi, float &mi, float &vi) {
+        gi = gi * scale;
+        mi = mi + (gi - mi) * w1;
+        vi = vi * b2 + w2 * (gi * gi);
+        const float denom = sqrtf(vi) / bc2_sqrt + eps;
+        pi = pi - step_size * (mi / denom);
+    };
+    auto update4 = [&](long long i, const float4 &gq) {
+        float4 p4 = *reinterpret_cast<float4 *>(p_own + 4 * i), m4 = *reinterpret_cast<float4 *>(m + 4 * i);
+        float4 v4 = *reinterpret_cast<float4 *>(v + 4 * i);
+        update(p4.x, gq.x, m4.x, v4.x), update(p4.y, gq.y, m4.y, v4.y);
+        update(p4.z, gq.z, m4.z, v4.z), update(p4.w, gq.w, m4.w, v4.w);
+        *reinterpret_cast<float4 *>(m + 4 * i) = m4, *reinterpret_cast<float4 *>(v + 4 * i) = v4;
+        if (c.param_mc) {
+            multimem_st4(c.param_mc + 4 * i, p4);
+        } else {
+#pragma unroll 4
+            for (int p = 0; p < W; ++p) *reinterpret_cast<float4 *>(c.param[p] + 4 * i) = p4;
+        }
+    };
+#pragma unroll
+    for (int k = 0; k < DP_REGV; ++k) {
+        const long long i = lo + tid + k * stride;
+        if (i < hi) update4(i, gv[k]);
+    }
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (long long i = lo + tid + DP_REGV * stride; i < hi; i += stride) {
+        update4(i, *reinterpret_cast<const float4 *>(g_own + 4 * i));
+        *reinterpret_cast<float4 *>(g_own + 4 * i) = zero4;
+    }
+#pragma unroll
+    for (int k = 0; k < DP_REGV; ++k) {
+        const long long i = lo + tid + k * stride;
+        if (i < hi) *reinterpret_cast<float4 *>(g_own + 4 * i) = zero4;
+    }
+    // every peer has finished reading this rank's gradients (it passed the mailbox barrier): zero the rest of the buffer
+    // for the next backward pass (optimizer.zero_grad)
+    for (long long i = tid; i < nvec - (hi - lo); i += stride) {
+        const long long j = i < lo ? i : i + (hi - lo);
+        *reinterpret_cast<float4 *>(g_own + 4 * j) = zero4;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) s_flag = (atomicAdd(ticket, 1ull) == (unsigned long long)gridDim.x - 1ull);
+    __syncthreads();
+    // ---- end barrier: all ranks' slices have landed here before anything reads the parameters ----
+    if (s_flag) {
+        const bool ok = rank_barrier(c, 2, epoch);
+        if (threadIdx.x == 0) {
+            if (!ok) st->reserved = 5;
+            st->step = st->step + 1;
+            __threadfence();
+            *ticket = 0ull;
+        }
+    }
+}
+
 // N(0,1) draws for the action sample of PPO.act (ppo.py:93, Normal.sample()): Philox4x32-10 keyed by state[2], counter =
 // (quad index, a domain tag, the call counter), Box-Muller on the four words.  state[0] = call counter, state[1] = ticket,
 // state[2] = key - all in device memory: every block reads counter and key first, the last block to finish advances the
@@ -721,6 +970,31 @@ int hb_optimizer_step(float *params, float *grads, float *exp_avg, float *exp_av
     cfg.attrs = at, cfg.numAttrs = 1;
     HB_CUDA(cudaLaunchKernelEx(&cfg, optimizer_step_kernel, params, grads, exp_avg, exp_avg_sq, (long long)n, *ap, state));
     HB_CHECK_LAUNCH("optimizer_step_kernel");
+    return HB_OK;
+}
+
+int hb_dp_optimizer_step(const hb_dp_comm *comm, float *exp_avg, float *exp_avg_sq, int64_t n, const hb_adam_params *ap,
+                         hb_optim_state *state, void *stream) {
+    HB_REQUIRE(comm && exp_avg && exp_avg_sq && ap && state && n > 0 && n % 4 == 0, "hb_dp_optimizer_step: bad arguments (n must be a multiple of 4)");
+    HB_REQUIRE(comm->world >= 1 && comm->world <= HB_DP_MAX_RANKS && comm->rank >= 0 && comm->rank < comm->world,
+               "hb_dp_optimizer_step: world %d / rank %d out of range", comm->world, comm->rank);
+    for (int p = 0; p < comm->world; ++p)
+        HB_REQUIRE(comm->grad[p] && comm->param[p] && comm->mail[p] && comm->flag[p] && hb::aligned16(comm->grad[p]) &&
+                       hb::aligned16(comm->param[p]), "hb_dp_optimizer_step: peer %d buffers missing or misaligned", p);
+    HB_REQUIRE(!ap->adaptive || ap->kl_count > 0, "hb_dp_optimizer_step: adaptive schedule needs kl_count");
+    HB_REQUIRE(hb::aligned16(exp_avg) && hb::aligned16(exp_avg_sq), "hb_dp_optimizer_step: 16-byte aligned optimizer state");
+    const long long per = ((n >> 2) + comm->world - 1) / comm->world;
+    const long long want = (per + DP_THREADS - 1) / DP_THREADS;
+    const long long cap = hb::sm_count();                  // blocks wait on one another and on the peers: one per SM, all resident
+    const unsigned grid = (unsigned)(want < 1 ? 1 : (want < cap ? want : cap));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid), cfg.blockDim = dim3(DP_THREADS), cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeCooperative;
+    at[0].val.cooperative = hb::g_coop_launch ? 1 : 0;
+    cfg.attrs = at, cfg.numAttrs = 1;
+    HB_CUDA(cudaLaunchKernelEx(&cfg, dp_optimizer_step_kernel, *comm, exp_avg, exp_avg_sq, (long long)n, *ap, state));
+    HB_CHECK_LAUNCH("dp_optimizer_step_kernel");
     return HB_OK;
 }
 

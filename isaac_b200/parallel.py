@@ -74,18 +74,80 @@ def rank_seed(base: int, rank: int) -> int:
     return (int(base) ^ ((int(rank) * _GOLDEN) & 0xFFFFFFFFFFFFFFFF)) & 0xFFFFFFFFFFFFFFFF
 
 
-def attach_data_parallel(alg, group=None, env=None):
-    """Turn a single-GPU `PPO` into one data-parallel replica (call after init_storage).  The action-sample generator
-    of the replica is re-keyed with `rank_seed`; pass the replica's env as well (or call `env.seed(rank_seed(cfg.seed,
-    rank))` yourself) so that its in-kernel draws differ between shards too."""
+class PeerOptimizer:
+    """The plumbing of `hb_dp_optimizer_step` (include/hector_b200.h): the replica's flat parameter and gradient buffers
+    move into symmetric memory (torch.distributed._symmetric_memory: every rank's allocation mapped into every rank's
+    address space over NVLink / NVSwitch, plus the switch's multicast address where NVLS exists), and the peer pointers are
+    handed to the kernel that replaces all-reduce + clip + Adam + broadcast.  No NCCL call on the update path."""
+
+    def __init__(self, alg, group=None, use_multicast=True):
+        import ctypes as C
+        import torch.distributed._symmetric_memory as symm_mem
+        from . import _lib
+        group = group or dist.group.WORLD
+        ac = alg.actor_critic
+        dev = ac.device
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        if world > _lib.HB_DP_MAX_RANKS:
+            raise ValueError(f"at most {_lib.HB_DP_MAX_RANKS} ranks")
+        n = ac.flat.numel()
+        self.params = symm_mem.empty(n, dtype=torch.float32, device=dev)
+        self.grads = symm_mem.empty(ac._grad_wire.numel(), dtype=torch.float32, device=dev)
+        self.mail = symm_mem.empty(_lib.HB_DP_MAX_RANKS * 8, dtype=torch.float64, device=dev)
+        self.flags = symm_mem.empty(3 * _lib.HB_DP_MAX_RANKS, dtype=torch.int32, device=dev)
+        self.params.copy_(ac.flat)
+        self.grads.zero_(), self.mail.zero_(), self.flags.zero_()
+        self.handles = [symm_mem.rendezvous(t, group) for t in (self.params, self.grads, self.mail, self.flags)]
+        hp, hg, hm, hf = self.handles
+        comm = _lib.DpComm()
+        comm.world, comm.rank = world, rank
+        for p in range(world):
+            comm.param[p], comm.grad[p] = hp.buffer_ptrs[p], hg.buffer_ptrs[p]
+            comm.mail[p], comm.flag[p] = hm.buffer_ptrs[p], hf.buffer_ptrs[p]
+        self.multicast = bool(use_multicast and hp.multicast_ptr and hg.multicast_ptr)
+        comm.param_mc = hp.multicast_ptr if self.multicast else None
+        comm.grad_mc = hg.multicast_ptr if self.multicast else None
+        self.comm, self.comm_ref = comm, C.byref(comm)
+        self.world, self.rank, self.group = world, rank, group
+        ac.rebind(self.params, self.grads)           # the GEMMs, the loss head and Adam now work in the shared buffers
+        torch.cuda.synchronize(dev)
+        dist.barrier(group)                          # every rank's flags / mailboxes are zero before the first step
+
+    def slice_range(self, n):
+        per = ((n // 4 + self.world - 1) // self.world) * 4
+        return self.rank * per, min(n, (self.rank + 1) * per), per
+
+    def gather_sharded(self, t: torch.Tensor) -> torch.Tensor:
+        """Full copy of an optimizer-state buffer whose slices live on their owner ranks (checkpoints)."""
+        n = t.numel()
+        lo, hi, per = self.slice_range(n)
+        mine = torch.zeros(per, device=t.device)
+        mine[:hi - lo] = t[lo:hi]
+        full = torch.empty(per * self.world, device=t.device)
+        dist.all_gather_into_tensor(full, mine, group=self.group)
+        return full[:n]
+
+
+def attach_data_parallel(alg, group=None, env=None, fused=None, use_multicast=True):
+    """Turn a single-GPU `PPO` into one data-parallel replica (call after init_storage).  `fused` (default: on CUDA):
+    gradients are reduced, clipped, applied and the parameters re-broadcast by ONE kernel over peer memory
+    (`PeerOptimizer` / hb_dp_optimizer_step); fused=False keeps the NCCL all-reduce + local optimizer step.  The
+    action-sample generator of the replica is re-keyed with `rank_seed`; pass the replica's env as well (or call
+    `env.seed(rank_seed(cfg.seed, rank))` yourself) so that its in-kernel draws differ between shards too."""
     if not dist.is_initialized():
         raise RuntimeError("torch.distributed is not initialised (launch with torchrun)")
     alg.world_size = dist.get_world_size(group)
     rank = dist.get_rank(group)
-    alg.grad_allreduce = GradReducer(group)
     if alg.storage is not None:
         alg.storage.reduce_stats = AdvantageStatsReducer(group)
     broadcast_parameters(alg.actor_critic, 0, group)
+    if fused is None:
+        fused = alg.actor_critic.flat.is_cuda and alg.world_size > 1
+    if fused:
+        alg.grad_allreduce = None
+        alg.attach_peer_optimizer(PeerOptimizer(alg, group, use_multicast))
+    else:
+        alg.grad_allreduce = GradReducer(group)
     if hasattr(alg, "seed") and hasattr(alg, "_eps_seed"):
         alg.seed(rank_seed(alg._eps_seed, rank))
     if env is not None:
