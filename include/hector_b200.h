@@ -267,6 +267,15 @@ int hb_env_reset_finalize(const hb_env_params *p, const hb_env_buffers *buf, flo
 int hb_env_stack_finalize(const hb_env_params *p, const hb_env_buffers *buf, const float *obs_prev, const float *priv_prev,
                           float *obs_new, float *priv_new, int32_t *host_count, uint64_t *rng_counter, void *stream);
 
+/* LeggedRobot._get_heights (envs/base/legged_robot.py:759-795) for terrains with a height field (mesh_type 'heightfield'
+ * / 'trimesh', measure_heights = True): heights[slot, j] = vertical_scale * min over the cell under point j (base frame
+ * points_xy[j] = (x, y), rotated by the base yaw, utils/math.py:39-43, plus base position and border_size, divided by
+ * horizontal_scale, truncated) and its +x and +y neighbours of the int16 field height_samples[rows, cols].
+ * env_ids: `count` env indices (the reference's env_ids argument), or NULL for envs 0..count-1.  heights [count, num_points]. */
+int hb_env_get_heights(const float *root_states, const float *points_xy, int32_t num_points, const int16_t *height_samples,
+                       int32_t rows, int32_t cols, float border_size, float horizontal_scale, float vertical_scale,
+                       const int32_t *env_ids, int64_t count, float *heights, void *stream);
+
 /* One frame-stack shift on its own, dense rows: next[:, 0:row-frame] = prev[:, frame:row] (zeros for envs whose
  * reset_buf byte is set, if reset_buf is not NULL); next[:, row-frame:row] is left alone. */
 int hb_stack_shift(const float *prev, float *next, const uint8_t *reset_buf, int32_t num_envs, int32_t row,

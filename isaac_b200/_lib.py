@@ -160,6 +160,8 @@ _SIGNATURES = {
     "hb_env_stack_observations": (C.c_int, [C.POINTER(EnvParams), C.POINTER(EnvBuffers), _fp, _fp, _fp, _fp, _fp]),
     "hb_env_reset_finalize": (C.c_int, [C.POINTER(EnvParams), C.POINTER(EnvBuffers), _fp, _fp, _fp, _fp, _fp]),
     "hb_env_stack_finalize": (C.c_int, [C.POINTER(EnvParams), C.POINTER(EnvBuffers), _fp, _fp, _fp, _fp, _fp, _fp, _fp]),
+    "hb_env_get_heights": (C.c_int, [_fp, _fp, C.c_int32, _fp, C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_float, _fp,
+                                     C.c_int64, _fp, _fp]),
     "hb_stack_shift": (C.c_int, [_fp, _fp, _fp, C.c_int32, C.c_int32, C.c_int32, _fp]),
     "hb_gemm_tf32": (C.c_int, [C.POINTER(GemmDesc), _fp]),
     "hb_gemm_workspace_floats": (C.c_int64, [C.POINTER(GemmDesc)]),

@@ -1180,6 +1180,45 @@ stack_finalize_kernel(const float *__restrict__ prev_a, float *__restrict__ next
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// LeggedRobot._get_heights (legged_robot.py:759-795): terrain height under a grid of points around
+// each robot.  The points (base frame, z = 0) are rotated by the base's yaw - quat_apply_yaw (utils/math.py:39-43):
+// x, y of the quaternion zeroed, normalised, quat_apply - shifted by the base position and the terrain border, divided by
+// the horizontal scale and truncated to a cell; the height is the minimum of the cell and its +x / +y neighbours in the
+// int16 height field, times the vertical scale.  One thread per (env, point); the field (a few MB) lives in L2, the
+// [N, P] output is written coalesced.  Same fp32 operation order as the reference (this unit is built without FMA
+// contraction), so the cell indices - and with them the heights - are bit-exact.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+get_heights_kernel(const float *__restrict__ root_states, const float *__restrict__ points_xy, const int16_t *__restrict__ field,
+                   int rows, int cols, float border, float hscale, float vscale, long long total, int npoints,
+                   const int32_t *__restrict__ env_ids, float *__restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const long long slot = i / npoints;
+    const int j = (int)(i - slot * npoints);
+    const long long env = env_ids ? env_ids[slot] : slot;
+    const float *root = root_states + env * 13;
+    // quat_apply_yaw: q = normalize((0, 0, qz, qw)); the norm sums the four squares in order (two exact zeros first)
+    const float z0 = root[5], w0 = root[6];
+    float nrm = sqrtf(((0.0f + 0.0f) + z0 * z0) + w0 * w0);
+    nrm = fmaxf(nrm, 1e-9f);
+    const float qz = z0 / nrm, qw = w0 / nrm;
+    const float px = points_xy[2 * j], py = points_xy[2 * j + 1];
+    // t = 2 * cross((0,0,qz), (px,py,0)) = 2 * (-(qz*py), qz*px, 0);  v + w*t + cross((0,0,qz), t)
+    const float tx = (0.0f - qz * py) * 2.0f, ty = (qz * px - 0.0f) * 2.0f;
+    const float rx = (px + qw * tx) + (0.0f - qz * ty);
+    const float ry = (py + qw * ty) + (qz * tx - 0.0f);
+    const float wx = ((rx + root[0]) + border) / hscale, wy = ((ry + root[1]) + border) / hscale;
+    long long cx = (long long)wx, cy = (long long)wy;              // .long(): truncation toward zero
+    cx = cx < 0 ? 0 : (cx > rows - 2 ? rows - 2 : cx);
+    cy = cy < 0 ? 0 : (cy > cols - 2 ? cols - 2 : cy);
+    const int16_t h1 = __ldg(field + cx * cols + cy), h2 = __ldg(field + (cx + 1) * cols + cy), h3 = __ldg(field + cx * cols + cy + 1);
+    int16_t h = h1 < h2 ? h1 : h2;
+    h = h < h3 ? h : h3;
+    out[i] = (float)h * vscale;
+}
+
 int g_use_bulk = 1;
 
 // hector frame stacks (hector_config.py:8-20): obs 15 x 41, privileged obs 15 x 70
@@ -1385,6 +1424,19 @@ int hb_env_post_physics(const hb_env_params *p, const hb_env_buffers *buf, const
                                *noise, obs_new, priv_new, (int)stages));
     }
     HB_CHECK_LAUNCH("post_physics_kernel");
+    return HB_OK;
+}
+
+int hb_env_get_heights(const float *root_states, const float *points_xy, int32_t num_points, const int16_t *height_samples,
+                       int32_t rows, int32_t cols, float border_size, float horizontal_scale, float vertical_scale,
+                       const int32_t *env_ids, int64_t count, float *heights, void *stream) {
+    HB_REQUIRE(root_states && points_xy && height_samples && heights, "hb_env_get_heights: null buffer");
+    HB_REQUIRE(num_points > 0 && rows >= 2 && cols >= 2 && count > 0 && horizontal_scale > 0.0f, "hb_env_get_heights: bad sizes");
+    const long long total = (long long)count * num_points;
+    get_heights_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        root_states, points_xy, height_samples, rows, cols, border_size, horizontal_scale, vertical_scale, total, num_points,
+        env_ids, heights);
+    HB_CHECK_LAUNCH("get_heights_kernel");
     return HB_OK;
 }
 

@@ -70,6 +70,12 @@ class HectorCfg(_Cfg):
         mesh_type = "trimesh"
         curriculum = False
         measure_heights = False
+        # height sampling (legged_robot_config.py:46-48,55-56; used when measure_heights is switched on)
+        horizontal_scale = 0.1
+        vertical_scale = 0.005
+        border_size = 25
+        measured_points_x = [-0.8, -0.7, -0.6, -0.5, -0.4, -0.3, -0.2, -0.1, 0., 0.1, 0.2, 0.3, 0.4, 0.5, 0.6, 0.7, 0.8]
+        measured_points_y = [-0.5, -0.4, -0.3, -0.2, -0.1, 0., 0.1, 0.2, 0.3, 0.4, 0.5]
 
     class noise:
         add_noise = True

@@ -529,6 +529,7 @@ class HectorFreeEnvB200:
     def _post_physics_step_staged(self, push: bool) -> None:
         """post_physics_step as the reference spells it (legged_robot.py:118-153), through the overridable hooks."""
         keep = self._injected         # the step's tape (if any) serves every stage
+        self._measure_heights(self._stream())
         self._launch_stage(HB_STAGE_PREPARE | (HB_STAGE_PUSH if push else 0))      # :127-137
         self.check_termination()                                                   # :139
         self.compute_reward()                                                      # :140
@@ -581,6 +582,8 @@ class HectorFreeEnvB200:
         """post-physics -> frame-stack shift + reset finalisation, on one stream; prev / out = (obs, priv) tensors."""
         lib = self._lib
         obs_new, priv_new = out[0].data_ptr(), out[1].data_ptr()
+        if stages & HB_STAGE_STEP:
+            self._measure_heights(st)        # _post_physics_step_callback, before anything is reset (legged_robot.py:315-316)
         _lib.check(lib.hb_env_post_physics(self._pp, self._pb, noise_ref, obs_new, priv_new, stages, st),
                    "hb_env_post_physics")
         noise = noise_ref._obj          # the EnvNoise behind the byref
@@ -637,6 +640,61 @@ class HectorFreeEnvB200:
         self.reset_idx(torch.arange(self.num_envs, device=self.device))
         obs, priv, _, _, _ = self.step(torch.zeros(self.num_envs, self.num_actions, device=self.device))
         return obs, priv
+
+    # ------------------------------------------------------------------ terrain heights (legged_robot.py:744-795)
+    def set_height_field(self, height_samples, measured_points_x=None, measured_points_y=None) -> None:
+        """Install the terrain's int16 height field (`Terrain.heightsamples` viewed [tot_rows, tot_cols],
+        legged_robot.py:569,585) and the sampling grid of `_init_height_points` (:744-757; defaults:
+        cfg.terrain.measured_points_x / _y).  From then on `_get_heights()` works and, when cfg.terrain.measure_heights is
+        set, `measured_heights` is refreshed every step like `_post_physics_step_callback` does (:315-316)."""
+        t = self.cfg.terrain
+        xs = list(measured_points_x if measured_points_x is not None else t.measured_points_x)
+        ys = list(measured_points_y if measured_points_y is not None else t.measured_points_y)
+        self.height_samples = torch.as_tensor(height_samples).to(device=self.device, dtype=torch.int16).contiguous()
+        if self.height_samples.dim() != 2:
+            raise ValueError("height_samples must be [tot_rows, tot_cols]")
+        gx, gy = torch.meshgrid(torch.tensor(xs, dtype=torch.float32), torch.tensor(ys, dtype=torch.float32), indexing="ij")
+        self.num_height_points = gx.numel()
+        self.height_points = torch.zeros(self.num_envs, self.num_height_points, 3, device=self.device)
+        self.height_points[:, :, 0] = gx.flatten().to(self.device)
+        self.height_points[:, :, 1] = gy.flatten().to(self.device)
+        self._height_points_xy = self.height_points[0, :, :2].contiguous()        # the grid is the same for every env
+        self.measured_heights = torch.zeros(self.num_envs, self.num_height_points, device=self.device)
+
+    def _measure_heights(self, st) -> None:
+        """measured_heights = _get_heights() of the callback (legged_robot.py:315-316), when the config asks for it; a
+        plain launch on `st`, so it also sits in the captured step graph."""
+        if getattr(self.cfg.terrain, "measure_heights", False) and getattr(self, "height_samples", None) is not None:
+            t = self.cfg.terrain
+            _lib.check(self._lib.hb_env_get_heights(self.root_states.data_ptr(), self._height_points_xy.data_ptr(),
+                                                    self.num_height_points, self.height_samples.data_ptr(),
+                                                    self.height_samples.shape[0], self.height_samples.shape[1],
+                                                    float(t.border_size), float(t.horizontal_scale), float(t.vertical_scale),
+                                                    None, self.num_envs, self.measured_heights.data_ptr(), st),
+                       "hb_env_get_heights")
+
+    def _get_heights(self, env_ids=None):
+        """legged_robot.py:759-795: terrain height under the grid of points around each robot -> [N, P] (or [len(env_ids),
+        P]; the reference's own env_ids branch cannot run, it ends in `.view(self.num_envs, -1)`)."""
+        t = self.cfg.terrain
+        if t.mesh_type == "plane":
+            return torch.zeros(self.num_envs, getattr(self, "num_height_points", 0), device=self.device)
+        if t.mesh_type == "none":
+            raise NameError("Can't measure height with terrain mesh type 'none'")
+        if getattr(self, "height_samples", None) is None:
+            raise RuntimeError("no height field installed: call set_height_field(terrain.heightsamples ...) first")
+        ids, count = None, self.num_envs
+        if env_ids is not None:
+            ids = torch.as_tensor(env_ids, device=self.device, dtype=torch.int32).contiguous()
+            count = ids.numel()
+        out = self.measured_heights if ids is None else torch.empty(count, self.num_height_points, device=self.device)
+        _lib.check(self._lib.hb_env_get_heights(self.root_states.data_ptr(), self._height_points_xy.data_ptr(),
+                                                self.num_height_points, self.height_samples.data_ptr(),
+                                                self.height_samples.shape[0], self.height_samples.shape[1],
+                                                float(t.border_size), float(t.horizontal_scale), float(t.vertical_scale),
+                                                ids.data_ptr() if ids is not None else None, count, out.data_ptr(),
+                                                self._stream()), "hb_env_get_heights")
+        return out
 
     @property
     def last_rigid_state(self):

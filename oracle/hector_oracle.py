@@ -76,6 +76,35 @@ def wrap_to_pi(a: torch.Tensor) -> torch.Tensor:
     return a - 2 * np.pi * (a > np.pi)
 
 
+def height_points(measured_points_x, measured_points_y, num_envs: int) -> torch.Tensor:
+    """LeggedRobot._init_height_points (legged_robot.py:744-757): the sampling grid in the base frame, [N, P, 3]."""
+    y = torch.tensor(measured_points_y)
+    x = torch.tensor(measured_points_x)
+    grid_x, grid_y = torch.meshgrid(x, y, indexing="ij")
+    points = torch.zeros(num_envs, grid_x.numel(), 3)
+    points[:, :, 0] = grid_x.flatten()
+    points[:, :, 1] = grid_y.flatten()
+    return points
+
+
+def get_heights(root_states, points, height_samples, border_size, horizontal_scale, vertical_scale, env_ids=None):
+    """LeggedRobot._get_heights (legged_robot.py:759-795) with quat_apply_yaw (utils/math.py:39-43): terrain height under
+    each point, min over the cell and its +x / +y neighbours of the int16 field."""
+    if env_ids is not None:
+        root_states, points = root_states[env_ids], points[env_ids]
+    n, p = points.shape[:2]
+    quat = root_states[:, 3:7].repeat(1, p).clone().view(-1, 4)
+    quat[:, :2] = 0.0
+    quat = quat / quat.norm(p=2, dim=-1).clamp(min=1e-9).unsqueeze(-1)          # isaacgym.torch_utils.normalize
+    pts = quat_apply(quat, points.reshape(-1, 3)).view(n, p, 3) + root_states[:, :3].unsqueeze(1)
+    pts = pts + border_size
+    pts = (pts / horizontal_scale).long()
+    px = torch.clip(pts[:, :, 0].reshape(-1), 0, height_samples.shape[0] - 2)
+    py = torch.clip(pts[:, :, 1].reshape(-1), 0, height_samples.shape[1] - 2)
+    h = torch.min(torch.min(height_samples[px, py], height_samples[px + 1, py]), height_samples[px, py + 1])
+    return h.view(n, -1) * vertical_scale
+
+
 def scaled_uniform(lo: float, hi: float, u: torch.Tensor) -> torch.Tensor:
     """isaacgym.torch_utils.torch_rand_float with the uniform draw supplied."""
     return (hi - lo) * u + lo

@@ -128,6 +128,41 @@ def make_env_golden():
     print(f"wrote {path}: {os.path.getsize(path) / 1e6:.2f} MB (action_delay = {DELAY_CASE['action_delay']})")
 
 
+HEIGHT_CASE = dict(n=48, seed=77, rows=420, cols=380, border_size=25.0, horizontal_scale=0.1, vertical_scale=0.005)
+MEASURED_X = [-0.8, -0.7, -0.6, -0.5, -0.4, -0.3, -0.2, -0.1, 0., 0.1, 0.2, 0.3, 0.4, 0.5, 0.6, 0.7, 0.8]     # legged_robot_config.py:55-56
+MEASURED_Y = [-0.5, -0.4, -0.3, -0.2, -0.1, 0., 0.1, 0.2, 0.3, 0.4, 0.5]
+
+
+def height_golden_inputs(n=None, seed=None):
+    """Root states scattered over (and a little beyond) an int16 height field, arbitrary yaw and tilt."""
+    c = HEIGHT_CASE
+    n = n or c["n"]
+    g = torch.Generator().manual_seed(seed or c["seed"])
+    field = (torch.randn(c["rows"], c["cols"], generator=g) * 40).round().to(torch.int16)       # terrain.heightsamples
+    root = torch.zeros(n, 13)
+    extent_x, extent_y = c["rows"] * c["horizontal_scale"], c["cols"] * c["horizontal_scale"]
+    root[:, 0] = torch.rand(n, generator=g) * (extent_x + 4.0) - c["border_size"] - 2.0            # some robots off the map: clipped
+    root[:, 1] = torch.rand(n, generator=g) * (extent_y + 4.0) - c["border_size"] - 2.0
+    root[:, 2] = 0.55
+    q = torch.randn(n, 4, generator=g)
+    q[: n // 4, :2] *= 0.05                                                                      # mostly upright, some tumbling
+    root[:, 3:7] = q / q.norm(dim=-1, keepdim=True)
+    return root, field
+
+
+def make_height_golden():
+    from oracle.ref_harness import reference_get_heights
+    c = HEIGHT_CASE
+    root, field = height_golden_inputs()
+    h = reference_get_heights(root, field, MEASURED_X, MEASURED_Y, c["border_size"], c["horizontal_scale"], c["vertical_scale"])
+    # (the reference's env_ids branch cannot run: it ends in .view(self.num_envs, -1), legged_robot.py:795 - every call
+    # site passes no ids)
+    path = os.path.join(GOLDEN_DIR, "heights_ref.npz")
+    np.savez_compressed(path, heights=h.numpy(),
+                        input_checksum=np.array([float(root.double().sum()), float(field.double().sum())]))
+    print(f"wrote {path}: {os.path.getsize(path) / 1e6:.3f} MB, {tuple(h.shape)}")
+
+
 def golden_ppo_inputs():
     """Seeded rollout inputs for the PPO golden case (regenerated on both sides)."""
     c = PPO_CASE
@@ -195,3 +230,4 @@ if __name__ == "__main__":
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     make_env_golden()
     make_ppo_golden()
+    make_height_golden()

@@ -394,3 +394,20 @@ class ReferencePPO:
                 return self.alg.update()
         finally:
             opt.step = real_step
+
+
+# --------------------------------------------------------------------------------------
+# Reference terrain height sampling (legged_robot.py:744-795), called unbound on a stub
+# --------------------------------------------------------------------------------------
+def reference_get_heights(root_states, height_samples, measured_points_x, measured_points_y, border_size, horizontal_scale,
+                          vertical_scale, env_ids=None):
+    """The reference's own `LeggedRobot._init_height_points` + `_get_heights` on the given state and int16 height field."""
+    install_isaacgym_stub()
+    from humanoid.envs.base.legged_robot import LeggedRobot
+    tcfg = types.SimpleNamespace(mesh_type="trimesh", measured_points_x=measured_points_x, measured_points_y=measured_points_y,
+                                 border_size=border_size, horizontal_scale=horizontal_scale, vertical_scale=vertical_scale)
+    stub = types.SimpleNamespace(cfg=types.SimpleNamespace(terrain=tcfg), terrain=types.SimpleNamespace(cfg=tcfg), device="cpu",
+                                 num_envs=root_states.shape[0], root_states=root_states, base_quat=root_states[:, 3:7],
+                                 height_samples=height_samples)
+    stub.height_points = LeggedRobot._init_height_points(stub)
+    return LeggedRobot._get_heights(stub, env_ids)

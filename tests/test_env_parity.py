@@ -221,6 +221,41 @@ def test_overridden_hooks_run_the_staged_step(lib, cuda_device):
     assert torch.equal(plain.reset_buf, want_reset) and torch.equal(plain.rew_buf, before)
 
 
+def test_get_heights_matches_reference_golden_and_oracle(lib, cuda_device):
+    """LeggedRobot._get_heights (legged_robot.py:759-795) as a kernel: bit-exact against the reference's own output on the
+    golden case and against the oracle at 4096 envs (every value is an int16 sample x vertical_scale: a cell index off by
+    one would show), including an env_ids subset and the measure_heights refresh inside step()."""
+    from oracle.hector_oracle import get_heights, height_points
+    dev = cuda_device
+    g = np.load(f"{GOLDEN}/heights_ref.npz")
+    c = mg.HEIGHT_CASE
+    for n, seed, golden in ((c["n"], None, g["heights"]), (4096, 9, None)):
+        root, field = mg.height_golden_inputs(n=n, seed=seed)
+        cfg = HectorCfg()
+        cfg.terrain.measure_heights = True
+        tape = make_tape(n, 2, seed=4)
+        env, phys = make_cuda_env(tape, dev, cfg=cfg)
+        env.set_height_field(field, mg.MEASURED_X, mg.MEASURED_Y)
+        env.root_states.copy_(root)
+        got = env._get_heights().cpu()
+        want = get_heights(root, height_points(mg.MEASURED_X, mg.MEASURED_Y, n), field, c["border_size"],
+                           c["horizontal_scale"], c["vertical_scale"])
+        assert_equal("heights vs oracle", got.numpy(), want.numpy())
+        if golden is not None:
+            assert_equal("heights vs reference golden", got.numpy(), golden)
+        ids = [3, n - 1, 7]
+        assert_equal("env_ids subset", env._get_heights(ids).cpu().numpy(), want[ids].numpy())
+        # step() refreshes measured_heights in the callback, i.e. from the state the physics produced, before any env is
+        # reset (legged_robot.py:315-316)
+        fr = tape.physics[1]
+        fr.root_states[:, :2] = root[:, :2]
+        cuda_step(env, phys, fr, tape.noise[1], dev)
+        want2 = get_heights(fr.root_states, height_points(mg.MEASURED_X, mg.MEASURED_Y, n), field, c["border_size"],
+                            c["horizontal_scale"], c["vertical_scale"])
+        assert_equal("measured_heights after step", env.measured_heights.cpu().numpy(), want2.numpy())
+        assert int(env.reset_buf.sum()) > 0 or n < 100
+
+
 def test_pd_torque_law(lib, cuda_device):
     """legged_robot.py:339-355 alone, including clipping at the URDF effort limits."""
     from oracle.hector_oracle import OracleHectorEnv

@@ -75,6 +75,33 @@ def test_env_oracle_action_delay_matches_reference_golden():
     assert np.abs(plain.actions.numpy() - g["actions"][1]).max() > 1e-3
 
 
+def test_height_oracle_matches_reference_golden():
+    """LeggedRobot._get_heights (legged_robot.py:759-795): the restatement against what the reference's own function
+    returned for the golden case (robots on, at the edge of and off the height field; arbitrary orientation) - every
+    height is an int16 sample times vertical_scale, so equality is exact."""
+    from oracle.hector_oracle import get_heights, height_points
+    g = np.load(f"{GOLDEN}/heights_ref.npz")
+    root, field = mg.height_golden_inputs()
+    np.testing.assert_array_equal(g["input_checksum"], [float(root.double().sum()), float(field.double().sum())])
+    c = mg.HEIGHT_CASE
+    pts = height_points(mg.MEASURED_X, mg.MEASURED_Y, c["n"])
+    h = get_heights(root, pts, field, c["border_size"], c["horizontal_scale"], c["vertical_scale"])
+    assert_equal("heights", h.numpy(), g["heights"])
+    assert np.unique(g["heights"]).size > 100 and g["heights"].shape == (c["n"], 187)
+
+
+@pytest.mark.skipif(not HAVE_REFERENCE, reason="/root/reference only exists in the build container")
+def test_height_oracle_equal_to_live_reference():
+    from oracle.hector_oracle import get_heights, height_points
+    from oracle.ref_harness import reference_get_heights
+    c = mg.HEIGHT_CASE
+    root, field = mg.height_golden_inputs(n=300, seed=5)
+    want = reference_get_heights(root, field, mg.MEASURED_X, mg.MEASURED_Y, c["border_size"], c["horizontal_scale"], c["vertical_scale"])
+    pts = height_points(mg.MEASURED_X, mg.MEASURED_Y, 300)
+    got = get_heights(root, pts, field, c["border_size"], c["horizontal_scale"], c["vertical_scale"])
+    assert torch.equal(got, want)
+
+
 def rec_names():
     env_scales = {k: v for k, v in vars(type(HectorCfg().rewards.scales)).items() if not k.startswith("_") and v != 0}
     return list(env_scales)
