@@ -343,6 +343,11 @@ typedef struct hb_gemm_desc {
 enum hb_gemm_precision { HB_GEMM_TF32 = 0, HB_GEMM_3XTF32 = 1 };
 int hb_gemm_tf32(const hb_gemm_desc *desc, void *stream);
 int64_t hb_gemm_workspace_floats(const hb_gemm_desc *desc);
+/* Two GEMMs of the same kind (same epilogue and operand layouts: the actor's and the critic's GEMM of one layer,
+ * actor_critic.py:54-77) in ONE launch: the persistent CTAs walk the concatenated tile list, so both networks share every
+ * wave of tiles and a launch's pipeline set-up / drain is paid once per layer.  Results are those of two hb_gemm_tf32
+ * calls; problems whose tile shapes cannot share a kernel (or HB_GEMM_3XTF32) fall back to exactly that. */
+int hb_gemm_tf32_grouped(const hb_gemm_desc *desc0, const hb_gemm_desc *desc1, void *stream);
 /* 256-wide tiles are computed by pairs of CTAs (tcgen05.mma.cta_group::2, 2-CTA clusters: each SM stages half of the
  * B tile) unless switched off (on = 0: one CTA per tile everywhere; for A/B measurements). */
 int hb_gemm_set_pair_mode(int on);

@@ -39,9 +39,7 @@ class _Layer:
         return self.rows * self.ld
 
 
-def gemm(lib, st, scratch=None, **kw):
-    """One hb_gemm_tf32 call.  `scratch` (a one-element list holding a float tensor or None) switches the call to
-    HB_GEMM_3XTF32 and supplies / grows the workspace of the split operands."""
+def _desc(lib, scratch, kw):
     d = GemmDesc()
     for k, v in kw.items():
         setattr(d, k, v)
@@ -51,7 +49,19 @@ def gemm(lib, st, scratch=None, **kw):
         if scratch[0] is None or scratch[0].numel() < need:
             scratch[0] = torch.empty(need, device=scratch[1])
         d.workspace, d.workspace_floats = scratch[0].data_ptr(), scratch[0].numel()
-    _lib.check(lib.hb_gemm_tf32(C.byref(d), st), "hb_gemm_tf32")
+    return d
+
+
+def gemm(lib, st, scratch=None, **kw):
+    """One hb_gemm_tf32 call.  `scratch` (a one-element list holding a float tensor or None) switches the call to
+    HB_GEMM_3XTF32 and supplies / grows the workspace of the split operands."""
+    _lib.check(lib.hb_gemm_tf32(C.byref(_desc(lib, scratch, kw)), st), "hb_gemm_tf32")
+
+
+def gemm2(lib, st, scratch0, kw0, scratch1, kw1):
+    """The same GEMM of both networks in one launch (hb_gemm_tf32_grouped)."""
+    _lib.check(lib.hb_gemm_tf32_grouped(C.byref(_desc(lib, scratch0, kw0)), C.byref(_desc(lib, scratch1, kw1)), st),
+               "hb_gemm_tf32_grouped")
 
 
 class ActorCritic:
@@ -99,6 +109,7 @@ class ActorCritic:
         # "tf32": operands truncated to TF32 by the tensor core (fast path).  "3xtf32": hi/lo split operands, three
         # partial products in one fp32 accumulator - fp32-grade results like the reference's nn.Linear (parity mode)
         self.precision = precision
+        self.grouped = True          # the actor's and the critic's GEMM of a layer share one launch (hb_gemm_tf32_grouped)
         self._scratch = {"actor": [None, self.device], "critic": [None, self.device]}     # one per stream / network
 
     def rebind(self, flat: torch.Tensor, grad_wire: torch.Tensor) -> None:
@@ -210,6 +221,56 @@ class ActorCritic:
                  bias=P.data_ptr() + L.fan_in * 4, bias_stride=L.ld)
             a, lda = d, d.stride(0)
         return ws[net]["out"]
+
+    # ------------------------------------------------------------------ both networks, layer by layer, grouped launches
+    def _fwd_kw(self, net, i, a, lda, m, ws):
+        L = [L for L in self.layers if L.net == net][i]
+        P = self._matrix(self.flat, L)
+        d = ws[net]["out"] if L.last else ws[net]["h"][i]
+        return dict(A=a.data_ptr(), B=P.data_ptr(), D=d.data_ptr(), M=m, N=L.rows if L.last else L.fan_out, K=L.fan_in,
+                    lda=lda, ldb=L.ld, ldd=d.stride(0), epilogue=HB_EPI_BIAS if L.last else HB_EPI_BIAS_ELU,
+                    bias=P.data_ptr() + L.fan_in * 4, bias_stride=L.ld), d
+
+    def forward_both(self, xa: torch.Tensor, xc: torch.Tensor, ws: dict):
+        """The three hidden layers of the actor (on xa) and the critic (on xc): three grouped launches instead of six.
+        Returns the last hidden activations (h3_actor, h3_critic)."""
+        lib, st = self._lib, torch.cuda.current_stream(self.device).cuda_stream
+        m = xa.shape[0]
+        a, c = (xa, xa.stride(0)), (xc, xc.stride(0))
+        for i in range(3):
+            kwa, da = self._fwd_kw("actor", i, a[0], a[1], m, ws)
+            kwc, dc = self._fwd_kw("critic", i, c[0], c[1], m, ws)
+            gemm2(lib, st, self._scratch_for("critic"), kwc, self._scratch_for("actor"), kwa)      # the larger problem first
+            a, c = (da, da.stride(0)), (dc, dc.stride(0))
+        return ws["actor"]["h"][-1], ws["critic"]["h"][-1]
+
+    def backward_both(self, xa: torch.Tensor, xc: torch.Tensor, ws: dict):
+        """Gradients of the three hidden layers of both networks from dz3 (left in ws by hb_ppo_head_fused): per layer one
+        grouped data-gradient launch (critical path first) and one grouped weight-gradient launch - five launches for ten
+        GEMMs."""
+        lib, st = self._lib, torch.cuda.current_stream(self.device).cuda_stream
+        m = xa.shape[0]
+        nets = {"actor": xa, "critic": xc}
+        cur = {net: (ws[net]["dz"][-1], ws[net]["dz"][-1].stride(0)) for net in nets}
+        for i in (2, 1, 0):
+            kw_w, kw_d, nxt = {}, {}, {}
+            for net, x in nets.items():
+                L = [L for L in self.layers if L.net == net][i]
+                G, P = self._matrix(self.grad, L), self._matrix(self.flat, L)
+                d_cur, ld_cur = cur[net]
+                act_in = x if i == 0 else ws[net]["h"][i - 1]
+                kw_w[net] = dict(A=d_cur.data_ptr(), B=act_in.data_ptr(), D=G.data_ptr(), M=L.rows, N=L.fan_in + 1, K=m, lda=ld_cur,
+                                 ldb=act_in.stride(0), ldd=L.ld, a_mn_major=1, b_mn_major=1, epilogue=HB_EPI_ATOMIC_ADD, split_k=0)
+                if i > 0:
+                    h_prev, dz = ws[net]["h"][i - 1], ws[net]["dz"][i - 1]
+                    kw_d[net] = dict(A=d_cur.data_ptr(), B=P.data_ptr(), D=dz.data_ptr(), M=m, N=L.fan_in, K=L.rows, lda=ld_cur,
+                                     ldb=L.ld, ldd=dz.stride(0), b_mn_major=1, epilogue=HB_EPI_ELU_BWD, H=h_prev.data_ptr(),
+                                     ldh=h_prev.stride(0))
+                    nxt[net] = (dz, dz.stride(0))
+            if i > 0:
+                gemm2(lib, st, self._scratch_for("critic"), kw_d["critic"], self._scratch_for("actor"), kw_d["actor"])
+            gemm2(lib, st, self._scratch_for("critic"), kw_w["critic"], self._scratch_for("actor"), kw_w["actor"])
+            cur = nxt
 
     def _mlp_backward(self, net: str, x: torch.Tensor, ws: dict, from_hidden: bool = False):
         """Gradients of every packed matrix of `net` from d_out (filled by the loss head); accumulates into

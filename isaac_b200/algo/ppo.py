@@ -250,8 +250,11 @@ class PPO:
                 ws = ac.workspace(n)
                 st = torch.cuda.current_stream(self.device).cuda_stream
                 eps = self.injected_eps.contiguous() if self.injected_eps is not None else self._draw_eps(n, st)
-                h3a = ac._mlp_forward("actor", e.xa, ws, hidden_only=True)
-                h3c = ac._mlp_forward("critic", e.xc, ws, hidden_only=True)
+                if ac.grouped:
+                    h3a, h3c = ac.forward_both(e.xa, e.xc, ws)
+                else:
+                    h3a = ac._mlp_forward("actor", e.xa, ws, hidden_only=True)
+                    h3c = ac._mlp_forward("critic", e.xc, ws, hidden_only=True)
                 self._launch_act_head(e, h3a, h3c, eps, n, st)
                 self.injected_eps = None
             t.actions, t.values, t.actions_log_prob = e.actions, e.values, e.logp
@@ -296,12 +299,16 @@ class PPO:
 
             def launches(st):
                 main = torch.cuda.current_stream(dev)       # the capture stream
-                side.wait_stream(main)
-                h3a = ac._mlp_forward("actor", e.xa, ws, hidden_only=True)
-                eps = self._draw_eps(n, st)
-                with torch.cuda.stream(side):
-                    h3c = ac._mlp_forward("critic", e.xc, ws, hidden_only=True)
-                main.wait_stream(side)
+                if ac.grouped:
+                    eps = self._draw_eps(n, st)
+                    h3a, h3c = ac.forward_both(e.xa, e.xc, ws)
+                else:
+                    side.wait_stream(main)
+                    h3a = ac._mlp_forward("actor", e.xa, ws, hidden_only=True)
+                    eps = self._draw_eps(n, st)
+                    with torch.cuda.stream(side):
+                        h3c = ac._mlp_forward("critic", e.xc, ws, hidden_only=True)
+                    main.wait_stream(side)
                 self._launch_act_head(e, h3a, h3c, eps, n, st)
 
             self._eps_stage(n)          # allocated before capture (and without consuming a draw)
@@ -360,11 +367,14 @@ class PPO:
             # persistent CTAs fill the SMs the other one leaves idle in its last round of tiles.
             main = torch.cuda.current_stream(self.device)
             side = self._side_stream
-            side.wait_stream(main)
-            h3a = ac._mlp_forward("actor", xa, ws, hidden_only=True)
-            with torch.cuda.stream(side):
-                h3c = ac._mlp_forward("critic", xc, ws, hidden_only=True)
-            main.wait_stream(side)
+            if ac.grouped:          # both networks layer by layer, one launch per layer
+                h3a, h3c = ac.forward_both(xa, xc, ws)
+            else:
+                side.wait_stream(main)
+                h3a = ac._mlp_forward("actor", xa, ws, hidden_only=True)
+                with torch.cuda.stream(side):
+                    h3c = ac._mlp_forward("critic", xc, ws, hidden_only=True)
+                main.wait_stream(side)
             La, Lc = [L for L in ac.layers if L.last]
             dza, dzc = ws["actor"]["dz"][-1], ws["critic"]["dz"][-1]
             _lib.check(lib.hb_ppo_head_fused(
@@ -373,11 +383,14 @@ class PPO:
                 rec.data_ptr(), mb, mb * self.world_size, C.byref(self._lp), dza.data_ptr(), dzc.data_ptr(), dza.stride(0),
                 ac._matrix(ac.grad, La).data_ptr(), ac._matrix(ac.grad, Lc).data_ptr(),
                 ac.grad[ac._std_offset:].data_ptr(), self._stats.data_ptr(), main.cuda_stream), "hb_ppo_head_fused")
-            side.wait_stream(main)
-            ac._mlp_backward("actor", xa, ws, from_hidden=True)
-            with torch.cuda.stream(side):
-                ac._mlp_backward("critic", xc, ws, from_hidden=True)
-            main.wait_stream(side)
+            if ac.grouped:
+                ac.backward_both(xa, xc, ws)
+            else:
+                side.wait_stream(main)
+                ac._mlp_backward("actor", xa, ws, from_hidden=True)
+                with torch.cuda.stream(side):
+                    ac._mlp_backward("critic", xc, ws, from_hidden=True)
+                main.wait_stream(side)
         else:
             mu16 = ac._mlp_forward("actor", xa, ws)
             v16 = ac._mlp_forward("critic", xc, ws)
@@ -413,7 +426,7 @@ class PPO:
         is the same for all epochs and updates (the step's scalars live in hb_optim_state), so it is captured once."""
         key = (i, self._mb, self._xa.data_ptr(), self._xc.data_ptr(), self._rec.data_ptr(), adaptive, self.clip_param,
                self.value_loss_coef, self.entropy_coef, self.use_clipped_value_loss, self.max_grad_norm, self.desired_kl,
-               self.actor_critic.precision)
+               self.actor_critic.precision, self.actor_critic.grouped)
         g = self._update_graphs.get(key)
         if g is None:
             if len(self._update_graphs) >= 4 * self.num_mini_batches:

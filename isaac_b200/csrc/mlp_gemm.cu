@@ -183,10 +183,14 @@ __host__ __device__ constexpr size_t smem_bytes_for() {
 //   same time share the rows of A in L2 (the weights are small and always L2-resident).
 // Three pipelines: shared-memory stages (TMA <-> MMA), two TMEM accumulators (MMA <-> epilogue: the epilogue of tile
 // i overlaps the main loop of tile i + 1), and the tile list.
+// GROUPED: one launch may carry TWO problems of the same kind (the actor's and the critic's GEMM of one layer): the tile
+// list is problem 0's tiles followed by problem 1's, dealt round-robin to the persistent CTAs, so both networks share
+// every wave of tiles and the pipeline set-up / drain of a launch is paid once per layer instead of once per network.
 template <int BN, bool A_MN, bool B_MN, int EPI, bool PAIR>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                 const __grid_constant__ GemmArgs g) {
+gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_b0,
+                 const __grid_constant__ GemmArgs g0, const __grid_constant__ CUtensorMap map_a1,
+                 const __grid_constant__ CUtensorMap map_b1, const __grid_constant__ GemmArgs g1) {
     constexpr int NSTAGE = stages_for<BN, PAIR>();
     constexpr int BN_CTA = PAIR ? BN / 2 : BN;               // B rows staged by this CTA
     constexpr int A_BYTES = BM * BK * 4, B_BYTES = BN_CTA * BK * 4;
@@ -200,7 +204,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     __shared__ uint32_t tmem_base_smem;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int kb_total = (g.K + BK - 1) / BK;
+    const int all_tiles = g0.total_tiles + g1.total_tiles;
     const uint32_t rank = PAIR ? cluster_ctarank() : 0u;     // 0 = leader (issues the MMAs, owns full / acc_empty barriers)
     const int first_tile = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
     const int tile_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
@@ -212,7 +216,10 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         for (int a = 0; a < 2; ++a) hb::mbar_init(&acc_full[a], 1), hb::mbar_init(&acc_empty[a], PAIR ? 2 * EPI_WARPS : EPI_WARPS);
         hb::fence_mbar_init();
     }
-    if (warp == PRODUCER_WARP && lane == 0) prefetch_tmap(&map_a), prefetch_tmap(&map_b);
+    if (warp == PRODUCER_WARP && lane == 0) {
+        prefetch_tmap(&map_a0), prefetch_tmap(&map_b0);
+        if (g1.total_tiles > 0) prefetch_tmap(&map_a1), prefetch_tmap(&map_b1);
+    }
     if (warp == MMA_WARP) {
         if (PAIR) tmem_alloc_pair(&tmem_base_smem, TMEM_COLS);
         else tmem_alloc(&tmem_base_smem, TMEM_COLS);
@@ -227,9 +234,10 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     hb::pdl_trigger();
     hb::pdl_wait();
 
-    auto tile_coords = [&](int t, int &m0, int &n0, int &kb_begin, int &nkb) {
+    auto tile_coords = [&](int t, const GemmArgs &g, int &m0, int &n0, int &kb_begin, int &nkb) {
         // n fastest, then m, then the k split: the tiles in flight at any time share their k slices of A and B, so
         // with split-K (weight gradients: both operands are minibatch-sized) every byte is fetched from HBM once
+        const int kb_total = (g.K + BK - 1) / BK;
         const int nt = t % g.tiles_n;
         const int rest = t / g.tiles_n;
         const int mt = rest % g.tiles_m;
@@ -243,9 +251,12 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         // ===================== TMA producer =====================
         if (lane == 0) {
             uint32_t it = 0;
-            for (int t = first_tile; t < g.total_tiles; t += tile_step) {
+            for (int t = first_tile; t < all_tiles; t += tile_step) {
+                const bool second = t >= g0.total_tiles;
+                const GemmArgs &g = second ? g1 : g0;
+                const CUtensorMap *pmap_a = second ? &map_a1 : &map_a0, *pmap_b = second ? &map_b1 : &map_b0;
                 int m0, n0, kb_begin, nkb;
-                tile_coords(t, m0, n0, kb_begin, nkb);
+                tile_coords(second ? t - g0.total_tiles : t, g, m0, n0, kb_begin, nkb);
                 const int nb0 = n0 + (PAIR ? (int)rank * BN_CTA : 0);      // this CTA's rows of the B tile
                 for (int i = 0; i < nkb; ++i, ++it) {
                     const uint32_t s = it % NSTAGE, ph = (it / NSTAGE) & 1;
@@ -257,29 +268,29 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                         const uint32_t bar = mapa_shared(hb::smem_u32(&full_bar[s]), 0);
                         if (A_MN) {
 #pragma unroll
-                            for (int j = 0; j < BM / 32; ++j) tma_load_2d_pair(sa + s * A_BYTES + j * 4096, &map_a, m0 + 32 * j, k0, bar);
+                            for (int j = 0; j < BM / 32; ++j) tma_load_2d_pair(sa + s * A_BYTES + j * 4096, pmap_a, m0 + 32 * j, k0, bar);
                         } else {
-                            tma_load_2d_pair(sa + s * A_BYTES, &map_a, k0, m0, bar);
+                            tma_load_2d_pair(sa + s * A_BYTES, pmap_a, k0, m0, bar);
                         }
                         if (B_MN) {
 #pragma unroll
-                            for (int j = 0; j < BN_CTA / 32; ++j) tma_load_2d_pair(sb + s * B_BYTES + j * 4096, &map_b, nb0 + 32 * j, k0, bar);
+                            for (int j = 0; j < BN_CTA / 32; ++j) tma_load_2d_pair(sb + s * B_BYTES + j * 4096, pmap_b, nb0 + 32 * j, k0, bar);
                         } else {
-                            tma_load_2d_pair(sb + s * B_BYTES, &map_b, k0, nb0, bar);
+                            tma_load_2d_pair(sb + s * B_BYTES, pmap_b, k0, nb0, bar);
                         }
                     } else {
                         hb::mbar_expect_tx(&full_bar[s], A_BYTES + B_BYTES);
                         if (A_MN) {      // tensor map dims (M, K): boxes of 32 m x 32 k, one 4 KB swizzle block each
 #pragma unroll
-                            for (int j = 0; j < BM / 32; ++j) tma_load_2d(sa + s * A_BYTES + j * 4096, &map_a, m0 + 32 * j, k0, &full_bar[s]);
+                            for (int j = 0; j < BM / 32; ++j) tma_load_2d(sa + s * A_BYTES + j * 4096, pmap_a, m0 + 32 * j, k0, &full_bar[s]);
                         } else {         // tensor map dims (K, M): one box of 32 k x 128 rows
-                            tma_load_2d(sa + s * A_BYTES, &map_a, k0, m0, &full_bar[s]);
+                            tma_load_2d(sa + s * A_BYTES, pmap_a, k0, m0, &full_bar[s]);
                         }
                         if (B_MN) {
 #pragma unroll
-                            for (int j = 0; j < BN / 32; ++j) tma_load_2d(sb + s * B_BYTES + j * 4096, &map_b, n0 + 32 * j, k0, &full_bar[s]);
+                            for (int j = 0; j < BN / 32; ++j) tma_load_2d(sb + s * B_BYTES + j * 4096, pmap_b, n0 + 32 * j, k0, &full_bar[s]);
                         } else {
-                            tma_load_2d(sb + s * B_BYTES, &map_b, k0, n0, &full_bar[s]);
+                            tma_load_2d(sb + s * B_BYTES, pmap_b, k0, n0, &full_bar[s]);
                         }
                     }
                 }
@@ -289,9 +300,10 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         // ===================== MMA issuer =====================
         constexpr uint32_t idesc = make_idesc(BN < 16 ? 16 : BN, A_MN, B_MN, PAIR ? 2 * BM : BM);
         uint32_t it = 0, acc_it = 0;
-        for (int t = first_tile; t < g.total_tiles && rank == 0; t += tile_step, ++acc_it) {
+        for (int t = first_tile; t < all_tiles && rank == 0; t += tile_step, ++acc_it) {
+            const bool second = t >= g0.total_tiles;
             int m0, n0, kb_begin, nkb;
-            tile_coords(t, m0, n0, kb_begin, nkb);
+            tile_coords(second ? t - g0.total_tiles : t, second ? g1 : g0, m0, n0, kb_begin, nkb);
             const uint32_t a = acc_it & 1, aph = (acc_it >> 1) & 1;
             hb::mbar_wait(&acc_empty[a], aph ^ 1);           // the epilogue has drained this accumulator
             tc_fence_after();
@@ -336,9 +348,11 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         const int c_end = (BN >= 64 || half == 0) ? c_begin + HALF_COLS : 0;
         float *tile = epi_smem + warp * EPI_TILE_FLOATS;
         uint32_t acc_it = 0;
-        for (int t = first_tile; t < g.total_tiles; t += tile_step, ++acc_it) {
+        for (int t = first_tile; t < all_tiles; t += tile_step, ++acc_it) {
+            const bool second = t >= g0.total_tiles;
+            const GemmArgs &g = second ? g1 : g0;
             int m0, n0, kb_begin, nkb;
-            tile_coords(t, m0, n0, kb_begin, nkb);
+            tile_coords(second ? t - g0.total_tiles : t, g, m0, n0, kb_begin, nkb);
             const uint32_t a = acc_it & 1, aph = (acc_it >> 1) & 1;
             const int mw = m0 + quarter * 32;                  // first row of this warp
             if (EPI == EPI_ELU_BWD) {                          // pull the warp's block of H towards L2 meanwhile
@@ -498,31 +512,25 @@ int make_map(CUtensorMap *map, const float *base, int rows, int cols, int ld, in
     return HB_OK;
 }
 
+// tensor maps + tile list of one problem
 template <int BN, bool A_MN, bool B_MN, int EPI, bool PAIR>
-int launch(const hb_gemm_desc *d, cudaStream_t st) {
-    constexpr size_t SMEM = smem_bytes_for<BN, PAIR>();
+int setup_problem(const hb_gemm_desc *d, CUtensorMap *ma, CUtensorMap *mb, GemmArgs *gp, int sharing) {
     constexpr int BN_CTA = PAIR ? BN / 2 : BN;
-    static bool attr = false;
-    auto kern = gemm_tf32_kernel<BN, A_MN, B_MN, EPI, PAIR>;
-    if (!attr) {
-        HB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
-        attr = true;
-    }
-    alignas(64) CUtensorMap ma, mb;
     int rc;
     // A: K-major  -> memory [M, K] ;  MN-major -> memory [K, M]
-    rc = A_MN ? make_map(&ma, d->A, d->K, d->M, d->lda, 32, 32, true) : make_map(&ma, d->A, d->M, d->K, d->lda, BK, BM, false);
+    rc = A_MN ? make_map(ma, d->A, d->K, d->M, d->lda, 32, 32, true) : make_map(ma, d->A, d->M, d->K, d->lda, BK, BM, false);
     if (rc) return rc;
-    rc = B_MN ? make_map(&mb, d->B, d->K, d->N, d->ldb, 32, 32, true) : make_map(&mb, d->B, d->N, d->K, d->ldb, BK, BN_CTA, false);
+    rc = B_MN ? make_map(mb, d->B, d->K, d->N, d->ldb, 32, 32, true) : make_map(mb, d->B, d->N, d->K, d->ldb, BK, BN_CTA, false);
     if (rc) return rc;
-    GemmArgs g;
+    GemmArgs &g = *gp;
     g.M = d->M, g.N = d->N, g.K = d->K;
     const int kb_total = (d->K + BK - 1) / BK;
     int splits = d->split_k > 0 ? d->split_k : 1;
     if (d->split_k == 0 && EPI == EPI_ATOMIC) {
         // automatic split-K: about two rounds of tiles over the SMs (SM pairs in pair mode); one round when the output
         // has only a few tiles, where the atomic accumulation of a second round costs more than the shorter k ranges save
-        const int slots = PAIR ? hb::sm_count() / 2 : hb::sm_count();
+        // (`sharing` problems ride in the launch: each aims at its share of the SMs)
+        const int slots = (PAIR ? hb::sm_count() / 2 : hb::sm_count()) / sharing;
         const int rows = PAIR ? 2 * BM : BM;
         const int tiles = ((d->M + rows - 1) / rows) * ((d->N + BN - 1) / BN);
         splits = (tiles <= 2 ? slots : 2 * slots) / tiles;
@@ -536,6 +544,29 @@ int launch(const hb_gemm_desc *d, cudaStream_t st) {
     const int tiles_m = (d->M + rows_per_tile - 1) / rows_per_tile;
     g.tiles_m = tiles_m, g.tiles_n = (d->N + BN - 1) / BN, g.splits = splits;
     g.total_tiles = tiles_m * g.tiles_n * splits;
+    return HB_OK;
+}
+
+// d1 may be null (one problem)
+template <int BN, bool A_MN, bool B_MN, int EPI, bool PAIR>
+int launch(const hb_gemm_desc *d, const hb_gemm_desc *d1, cudaStream_t st) {
+    constexpr size_t SMEM = smem_bytes_for<BN, PAIR>();
+    static bool attr = false;
+    auto kern = gemm_tf32_kernel<BN, A_MN, B_MN, EPI, PAIR>;
+    if (!attr) {
+        HB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+        attr = true;
+    }
+    alignas(64) CUtensorMap ma, mb, ma1, mb1;
+    GemmArgs g, g1;
+    if (int rc = setup_problem<BN, A_MN, B_MN, EPI, PAIR>(d, &ma, &mb, &g, d1 ? 2 : 1)) return rc;
+    if (d1) {
+        if (int rc = setup_problem<BN, A_MN, B_MN, EPI, PAIR>(d1, &ma1, &mb1, &g1, 2)) return rc;
+    } else {
+        ma1 = ma, mb1 = mb, g1 = g;
+        g1.total_tiles = 0;
+    }
+    const int total_tiles = g.total_tiles + g1.total_tiles;
     cudaLaunchConfig_t cfg = {};
     cudaLaunchAttribute at[2];
     int nat = 0;
@@ -545,16 +576,16 @@ int launch(const hb_gemm_desc *d, cudaStream_t st) {
     int grid;
     if (PAIR) {
         const int pairs = hb::sm_count() / 2;
-        grid = 2 * (g.total_tiles < pairs ? g.total_tiles : pairs);
+        grid = 2 * (total_tiles < pairs ? total_tiles : pairs);
         at[nat].id = cudaLaunchAttributeClusterDimension;
         at[nat].val.clusterDim.x = 2, at[nat].val.clusterDim.y = 1, at[nat].val.clusterDim.z = 1;
         ++nat;
     } else {
-        grid = g.total_tiles < hb::sm_count() ? g.total_tiles : hb::sm_count();
+        grid = total_tiles < hb::sm_count() ? total_tiles : hb::sm_count();
     }
     cfg.gridDim = dim3(grid), cfg.blockDim = dim3(GEMM_THREADS), cfg.dynamicSmemBytes = SMEM, cfg.stream = st;
     cfg.attrs = at, cfg.numAttrs = nat;
-    HB_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, mb, g));
+    HB_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, mb, g, ma1, mb1, g1));
     HB_CHECK_LAUNCH("gemm_tf32_kernel");
     return HB_OK;
 }
@@ -562,30 +593,30 @@ int launch(const hb_gemm_desc *d, cudaStream_t st) {
 int g_gemm_pair = 1;          // "gemm_pair" option: 0 disables the 2-CTA kernels
 
 template <int BN, bool A_MN, bool B_MN, int EPI>
-int launch_auto(const hb_gemm_desc *d, cudaStream_t st) {
+int launch_auto(const hb_gemm_desc *d, const hb_gemm_desc *d1, cudaStream_t st) {
     if constexpr (BN == 256) {
-        if (g_gemm_pair && d->M > BM) return launch<BN, A_MN, B_MN, EPI, true>(d, st);
+        if (g_gemm_pair && d->M > BM && (!d1 || d1->M > BM)) return launch<BN, A_MN, B_MN, EPI, true>(d, d1, st);
     }
-    return launch<BN, A_MN, B_MN, EPI, false>(d, st);
+    return launch<BN, A_MN, B_MN, EPI, false>(d, d1, st);
 }
 
 template <int BN, int EPI>
-int dispatch_major(const hb_gemm_desc *d, cudaStream_t st) {
-    if (!d->a_mn_major && !d->b_mn_major) return launch_auto<BN, false, false, EPI>(d, st);
-    if (!d->a_mn_major && d->b_mn_major) return launch_auto<BN, false, true, EPI>(d, st);
-    if (d->a_mn_major && d->b_mn_major) return launch_auto<BN, true, true, EPI>(d, st);
+int dispatch_major(const hb_gemm_desc *d, const hb_gemm_desc *d1, cudaStream_t st) {
+    if (!d->a_mn_major && !d->b_mn_major) return launch_auto<BN, false, false, EPI>(d, d1, st);
+    if (!d->a_mn_major && d->b_mn_major) return launch_auto<BN, false, true, EPI>(d, d1, st);
+    if (d->a_mn_major && d->b_mn_major) return launch_auto<BN, true, true, EPI>(d, d1, st);
     hb::set_error("hb_gemm_tf32: A MN-major with B K-major is not instantiated");
     return HB_ERR_UNSUPPORTED;
 }
 
 template <int BN>
-int dispatch_epi(const hb_gemm_desc *d, cudaStream_t st) {
+int dispatch_epi(const hb_gemm_desc *d, const hb_gemm_desc *d1, cudaStream_t st) {
     switch (d->epilogue) {
-        case HB_EPI_STORE: return dispatch_major<BN, EPI_STORE>(d, st);
-        case HB_EPI_BIAS: return dispatch_major<BN, EPI_BIAS>(d, st);
-        case HB_EPI_BIAS_ELU: return dispatch_major<BN, EPI_BIAS_ELU>(d, st);
-        case HB_EPI_ELU_BWD: return dispatch_major<BN, EPI_ELU_BWD>(d, st);
-        case HB_EPI_ATOMIC_ADD: return dispatch_major<BN, EPI_ATOMIC>(d, st);
+        case HB_EPI_STORE: return dispatch_major<BN, EPI_STORE>(d, d1, st);
+        case HB_EPI_BIAS: return dispatch_major<BN, EPI_BIAS>(d, d1, st);
+        case HB_EPI_BIAS_ELU: return dispatch_major<BN, EPI_BIAS_ELU>(d, d1, st);
+        case HB_EPI_ELU_BWD: return dispatch_major<BN, EPI_ELU_BWD>(d, d1, st);
+        case HB_EPI_ATOMIC_ADD: return dispatch_major<BN, EPI_ATOMIC>(d, d1, st);
     }
     hb::set_error("hb_gemm_tf32: unknown epilogue %d", d->epilogue);
     return HB_ERR_BAD_ARG;
@@ -718,17 +749,22 @@ extern "C" int hb_gemm_set_pair_mode(int on) {
 }
 
 namespace {
-int gemm_tf32_dispatch(const hb_gemm_desc *d, cudaStream_t st) {
+static int check_desc(const hb_gemm_desc *d) {
     HB_REQUIRE(d && d->A && d->B && d->D, "hb_gemm_tf32: null descriptor/operand");
     HB_REQUIRE(d->M > 0 && d->N > 0 && d->K > 0, "hb_gemm_tf32: empty problem %dx%dx%d", d->M, d->N, d->K);
     HB_REQUIRE((d->epilogue != HB_EPI_BIAS && d->epilogue != HB_EPI_BIAS_ELU) || d->bias, "hb_gemm_tf32: bias epilogue without bias");
     HB_REQUIRE(d->epilogue != HB_EPI_ELU_BWD || d->H, "hb_gemm_tf32: ELU backward epilogue without activations");
     HB_REQUIRE(d->split_k <= 1 || d->epilogue == HB_EPI_ATOMIC_ADD, "hb_gemm_tf32: split-K needs the atomic epilogue");
     HB_REQUIRE(!d->b_mn_major || d->N > 64, "hb_gemm_tf32: MN-major B needs N > 64 (32-wide TMA boxes per 128-byte swizzle row)");
-    // tile width: the widest UMMA N that does not waste more than half a tile ...
-    if (d->N <= 16) return dispatch_epi<16>(d, st);
-    if (d->N <= 64) return dispatch_epi<64>(d, st);
-    if (d->N <= 128 || d->tile_n == 128) return dispatch_epi<128>(d, st);
+    return HB_OK;
+}
+
+// tile width of a problem: 16 / 64 / 128 / 256
+static int pick_tile_n(const hb_gemm_desc *d) {
+    // the widest UMMA N that does not waste more than half a tile ...
+    if (d->N <= 16) return 16;
+    if (d->N <= 64) return 64;
+    if (d->N <= 128 || d->tile_n == 128) return 128;
     if (d->tile_n == 0 && d->epilogue != HB_EPI_ATOMIC_ADD) {
         // ... unless 128-wide tiles balance better over the SMs: rounds of the persistent tile loop x operand
         // bytes per tile (proportional to 128 + BN); e.g. M = 24576, N = 256 is 192 tiles = 2 rounds of 148 SMs at
@@ -741,15 +777,54 @@ int gemm_tf32_dispatch(const hb_gemm_desc *d, cudaStream_t st) {
             const long long tp = ((d->M + 2 * BM - 1) / (2 * BM)) * ((d->N + 255) / 256), pairs = sms / 2;
             c256 = ((tp + pairs - 1) / pairs) * (128 + 128);
         }
-        if (c128 < c256) return dispatch_epi<128>(d, st);
+        if (c128 < c256) return 128;
     }
-    return dispatch_epi<256>(d, st);
+    return 256;
+}
+
+static int dispatch_tile(int bn, const hb_gemm_desc *d, const hb_gemm_desc *d1, cudaStream_t st) {
+    switch (bn) {
+        case 16: return dispatch_epi<16>(d, d1, st);
+        case 64: return dispatch_epi<64>(d, d1, st);
+        case 128: return dispatch_epi<128>(d, d1, st);
+        default: return dispatch_epi<256>(d, d1, st);
+    }
+}
+
+int gemm_tf32_dispatch(const hb_gemm_desc *d, cudaStream_t st) {
+    if (int rc = check_desc(d)) return rc;
+    return dispatch_tile(pick_tile_n(d), d, nullptr, st);
+}
+
+int gemm_tf32_dispatch_grouped(const hb_gemm_desc *d0, const hb_gemm_desc *d1, cudaStream_t st) {
+    if (int rc = check_desc(d0)) return rc;
+    if (int rc = check_desc(d1)) return rc;
+    HB_REQUIRE(d0->epilogue == d1->epilogue && d0->a_mn_major == d1->a_mn_major && d0->b_mn_major == d1->b_mn_major,
+               "hb_gemm_tf32_grouped: both problems must share epilogue and operand layouts");
+    // one tile width for both: with two problems in flight there are enough tiles for the wide one whenever both are wide
+    int bn0 = pick_tile_n(d0), bn1 = pick_tile_n(d1);
+    if ((bn0 >= 128) != (bn1 >= 128) || (bn0 < 128 && bn0 != bn1)) {       // too different to share a kernel: two launches
+        if (int rc = dispatch_tile(bn0, d0, nullptr, st)) return rc;
+        return dispatch_tile(bn1, d1, nullptr, st);
+    }
+    const int bn = bn0 > bn1 ? bn0 : bn1;
+    if (bn == 256 && (d0->N <= 128 || d1->N <= 128)) return dispatch_tile(128, d0, d1, st);
+    return dispatch_tile(bn, d0, d1, st);
 }
 }  // namespace
 
 extern "C" int64_t hb_gemm_workspace_floats(const hb_gemm_desc *d) {
     if (!d || d->precision != HB_GEMM_3XTF32) return 0;
     return split3_floats(d->M, d->K, d->a_mn_major != 0) + split3_floats(d->N, d->K, d->b_mn_major != 0);
+}
+
+extern "C" int hb_gemm_tf32_grouped(const hb_gemm_desc *d0, const hb_gemm_desc *d1, void *stream) {
+    HB_REQUIRE(d0 && d1, "hb_gemm_tf32_grouped: null descriptor");
+    if (d0->precision != HB_GEMM_TF32 || d1->precision != HB_GEMM_TF32) {      // the fp32-grade mode has its own passes
+        if (int rc = hb_gemm_tf32(d0, stream)) return rc;
+        return hb_gemm_tf32(d1, stream);
+    }
+    return gemm_tf32_dispatch_grouped(d0, d1, (cudaStream_t)stream);
 }
 
 extern "C" int hb_gemm_tf32(const hb_gemm_desc *d, void *stream) {
