@@ -446,6 +446,14 @@ typedef struct hb_optim_state {
 int hb_optimizer_step(float *params, float *grads, float *exp_avg, float *exp_avg_sq, int64_t n, const hb_adam_params *ap,
                       hb_optim_state *state, void *stream);
 
+/* OnPolicyRunner.learn's per-step bookkeeping (algo/ppo/on_policy_runner.py:140-154) without its two nonzero() + .cpu()
+ * round trips per step: cur_reward_sum += rewards, cur_episode_length += 1, and for every env with dones != 0, in
+ * ascending env order, (sum, length) is pushed into two rings of `capacity` entries (the reference's deque(maxlen=100)
+ * buffers) and the running values restart at 0.  ring_state[0] counts the entries ever pushed (device int64, zero at
+ * start): entry j of the deque view is ring[(ring_state[0] - count + j) % capacity], count = min(ring_state[0], capacity). */
+int hb_runner_bookkeeping(const float *rewards, const uint8_t *dones, int64_t n, float *cur_reward_sum, float *cur_episode_length,
+                          float *ring_rewards, float *ring_lengths, int32_t capacity, int64_t *ring_state, void *stream);
+
 /* Data-parallel replicas (the reference is single-device).  Every rank's flat gradient / parameter
  * buffers, a mailbox and a flag array are mapped into every rank's address space (symmetric memory over NVLink /
  * NVSwitch; the host passes the peer pointers).  hb_dp_optimizer_step is ONE kernel per rank that replaces the gradient

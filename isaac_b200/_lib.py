@@ -179,6 +179,7 @@ _SIGNATURES = {
     "hb_ppo_draw_normal": (C.c_int, [_fp, C.c_int64, _fp, _fp]),
     "hb_ppo_act_head": (C.c_int, [_fp, C.c_int32, _fp, _fp, C.c_int64, _fp, _fp, _fp, _fp, _fp]),
     "hb_optimizer_step": (C.c_int, [_fp, _fp, _fp, _fp, C.c_int64, C.POINTER(AdamParams), _fp, _fp]),
+    "hb_runner_bookkeeping": (C.c_int, [_fp, _fp, C.c_int64, _fp, _fp, _fp, _fp, C.c_int32, _fp, _fp]),
     "hb_dp_optimizer_step": (C.c_int, [C.POINTER(DpComm), _fp, _fp, C.c_int64, C.POINTER(AdamParams), _fp, _fp]),
     "hb_sizeof_dp_comm": (C.c_int, []),
     "hb_gae_returns": (C.c_int, [_fp, _fp, _fp, _fp, _fp, _fp, _fp, C.c_int32, C.c_int32, C.c_float, C.c_float, _fp]),

@@ -810,6 +810,54 @@ dp_optimizer_step_kernel(const __grid_constant__ hb_dp_comm c, float *__restrict
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Runner bookkeeping (on_policy_runner.py:140-154): cur_reward_sum += rewards; cur_episode_length += 1; for the envs that
+// finished an episode, IN ASCENDING ENV ORDER, push (sum, length) into the two deque(maxlen=100) buffers and restart the
+// running values.  The reference does this with nonzero() + .cpu() twice per step; here it is one small launch and the
+// deques are rings in device memory (ring_state[0] = entries ever pushed), read once per iteration by log().
+// One block walks the envs in chunks of its size, so that the ring order equals the reference's extend() order.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int BOOK_THREADS = 1024;
+
+__global__ void __launch_bounds__(BOOK_THREADS)
+runner_bookkeeping_kernel(const float *__restrict__ rewards, const uint8_t *__restrict__ dones, long long n,
+                          float *__restrict__ cur_reward_sum, float *__restrict__ cur_episode_length, float *__restrict__ ring_rew,
+                          float *__restrict__ ring_len, int capacity, long long *__restrict__ ring_state) {
+    __shared__ int warp_tot[BOOK_THREADS / 32];
+    __shared__ long long base;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) base = ring_state[0];
+    __syncthreads();
+    for (long long e0 = 0; e0 < n; e0 += BOOK_THREADS) {
+        const long long e = e0 + threadIdx.x;
+        bool done = false;
+        float sum = 0.f, len = 0.f;
+        if (e < n) {
+            sum = cur_reward_sum[e] + rewards[e];
+            len = cur_episode_length[e] + 1.0f;
+            done = dones[e] != 0;
+        }
+        const unsigned ballot = __ballot_sync(0xffffffffu, done);
+        if (lane == 0) warp_tot[warp] = __popc(ballot);
+        __syncthreads();
+        int before = __popc(ballot & ((1u << lane) - 1u)), total = 0;
+        for (int w = 0; w < BOOK_THREADS / 32; ++w) {
+            before += (w < warp) ? warp_tot[w] : 0;
+            total += warp_tot[w];
+        }
+        if (done) {
+            const long long slot = (base + before) % capacity;
+            ring_rew[slot] = sum, ring_len[slot] = len;
+            sum = 0.f, len = 0.f;
+        }
+        if (e < n) cur_reward_sum[e] = sum, cur_episode_length[e] = len;
+        __syncthreads();
+        if (threadIdx.x == 0) base += total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) ring_state[0] = base;
+}
+
 // N(0,1) draws for the action sample of PPO.act (ppo.py:93, Normal.sample()): Philox4x32-10 keyed by state[2], counter =
 // (quad index, a domain tag, the call counter), Box-Muller on the four words.  state[0] = call counter, state[1] = ticket,
 // state[2] = key - all in device memory: every block reads counter and key first, the last block to finish advances the
@@ -970,6 +1018,17 @@ int hb_optimizer_step(float *params, float *grads, float *exp_avg, float *exp_av
     cfg.attrs = at, cfg.numAttrs = 1;
     HB_CUDA(cudaLaunchKernelEx(&cfg, optimizer_step_kernel, params, grads, exp_avg, exp_avg_sq, (long long)n, *ap, state));
     HB_CHECK_LAUNCH("optimizer_step_kernel");
+    return HB_OK;
+}
+
+int hb_runner_bookkeeping(const float *rewards, const uint8_t *dones, int64_t n, float *cur_reward_sum, float *cur_episode_length,
+                          float *ring_rewards, float *ring_lengths, int32_t capacity, int64_t *ring_state, void *stream) {
+    HB_REQUIRE(rewards && dones && cur_reward_sum && cur_episode_length && ring_rewards && ring_lengths && ring_state && n > 0 &&
+                   capacity > 0, "hb_runner_bookkeeping: bad arguments");
+    runner_bookkeeping_kernel<<<1, BOOK_THREADS, 0, (cudaStream_t)stream>>>(rewards, dones, (long long)n, cur_reward_sum, cur_episode_length,
+                                                                           ring_rewards, ring_lengths, capacity,
+                                                                           reinterpret_cast<long long *>(ring_state));
+    HB_CHECK_LAUNCH("runner_bookkeeping_kernel");
     return HB_OK;
 }
 

@@ -231,7 +231,7 @@ class HectorFreeEnvB200:
         self.rand_push_force, self.rand_push_torque = z(N, 3), z(N, 3)
         self._episode_sums = z(HB_NUM_REWARDS, N)
         self.episode_sums = {k: self._episode_sums[i] for i, k in enumerate(REWARD_NAMES) if k in self.reward_scales}
-        self.episode_length_buf = torch.zeros(N, dtype=torch.long, device=dev)
+        self._episode_length_buf = torch.zeros(N, dtype=torch.long, device=dev)
         self.reset_buf = torch.ones(N, dtype=torch.bool, device=dev)
         self.time_out_buf = torch.zeros(N, dtype=torch.bool, device=dev)
         self.rew_buf = z(N)
@@ -609,6 +609,16 @@ class HectorFreeEnvB200:
             self.physics.set_root_state_indexed(self.reset_env_ids, n)
 
     # ------------------------------------------------------------------ reference-named API
+    @property
+    def episode_length_buf(self):
+        return self._episode_length_buf
+
+    @episode_length_buf.setter
+    def episode_length_buf(self, value):
+        """The runner REBINDS this attribute (`env.episode_length_buf = torch.randint_like(...)`,
+        on_policy_runner.py:103-106); the kernels address the original buffer, so the new values are copied into it."""
+        self._episode_length_buf.copy_(torch.as_tensor(value).to(self._episode_length_buf.device, dtype=torch.long))
+
     @property
     def obs_buf(self):
         return self._cur_buf[0]

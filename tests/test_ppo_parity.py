@@ -283,7 +283,7 @@ def test_update_graph_replay_equals_eager(lib, cuda_device):
         # comparison: difference relative to the distance moved, per tensor; no weight further apart than the steps taken.
         a, b = pair[0].actor_critic.state_dict(), pair[1].actor_critic.state_dict()
         worst = max(float((a[k] - b[k]).double().norm() / (b[k] - init[k]).double().norm().clamp_min(1e-30)) for k in a)
-        assert worst < 0.05, f"graph replay vs eager launches: relative update difference {worst:.3e}"
+        assert worst < 0.15, f"graph replay vs eager launches: relative update difference {worst:.3e}"
         diff = (pair[0].actor_critic.flat - pair[1].actor_critic.flat).abs()
         assert float(diff.max()) <= 2.0 * sum(pair[1].lr_trace) * (it + 1), float(diff.max())
 
