@@ -824,10 +824,23 @@ runner_bookkeeping_kernel(const float *__restrict__ rewards, const uint8_t *__re
                           float *__restrict__ cur_reward_sum, float *__restrict__ cur_episode_length, float *__restrict__ ring_rew,
                           float *__restrict__ ring_len, int capacity, long long *__restrict__ ring_state) {
     __shared__ int warp_tot[BOOK_THREADS / 32];
-    __shared__ long long base;
+    __shared__ long long base, step_total;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) base = ring_state[0];
+    // pass 1: how many episodes end in this step (a deque keeps only the last `capacity` of them: earlier ones must not
+    // be written at all, or they would race with the later entry that lands in the same ring slot)
+    int mine = 0;
+    for (long long e = threadIdx.x; e < n; e += BOOK_THREADS) mine += dones[e] != 0;
+    mine = __reduce_add_sync(0xffffffffu, mine);
+    if (lane == 0) warp_tot[warp] = mine;
     __syncthreads();
+    if (threadIdx.x == 0) {
+        long long t = 0;
+        for (int w = 0; w < BOOK_THREADS / 32; ++w) t += warp_tot[w];
+        step_total = t;
+        base = ring_state[0];
+    }
+    __syncthreads();
+    const long long keep_from = base + step_total - capacity;       // global index of the oldest entry that survives
     for (long long e0 = 0; e0 < n; e0 += BOOK_THREADS) {
         const long long e = e0 + threadIdx.x;
         bool done = false;
@@ -838,6 +851,7 @@ runner_bookkeeping_kernel(const float *__restrict__ rewards, const uint8_t *__re
             done = dones[e] != 0;
         }
         const unsigned ballot = __ballot_sync(0xffffffffu, done);
+        __syncthreads();
         if (lane == 0) warp_tot[warp] = __popc(ballot);
         __syncthreads();
         int before = __popc(ballot & ((1u << lane) - 1u)), total = 0;
@@ -846,8 +860,8 @@ runner_bookkeeping_kernel(const float *__restrict__ rewards, const uint8_t *__re
             total += warp_tot[w];
         }
         if (done) {
-            const long long slot = (base + before) % capacity;
-            ring_rew[slot] = sum, ring_len[slot] = len;
+            const long long idx = base + before;
+            if (idx >= keep_from) ring_rew[idx % capacity] = sum, ring_len[idx % capacity] = len;
             sum = 0.f, len = 0.f;
         }
         if (e < n) cur_reward_sum[e] = sum, cur_episode_length[e] = len;

@@ -41,7 +41,9 @@ def test_reference_runner_learn_runs_over_dropin_classes(lib, cuda_device, tmp_p
         pytest.skip("the reference is neither at /root/reference nor installed under baseline/_ref (baseline/install_ref.sh)")
     monkeypatch.setenv("WANDB_MODE", "disabled")
     ref_harness.install_isaacgym_stub()
-    import humanoid.algo.ppo.on_policy_runner as ref_runner          # the reference's file, unmodified
+    import importlib
+    # (humanoid/algo/__init__.py rebinds `humanoid.algo.ppo` to the module ppo.py: attribute-style import would miss the file)
+    ref_runner = importlib.import_module("humanoid.algo.ppo.on_policy_runner")          # the reference's file, unmodified
     from isaac_b200.algo import ActorCritic, PPO
     # the binding a maintainer adds: the two names the runner resolves with eval() (on_policy_runner.py:68,72)
     monkeypatch.setattr(ref_runner, "ActorCritic", ActorCritic)
