@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define HB_ABI_VERSION 3
+#define HB_ABI_VERSION 4
 
 typedef enum hb_status {
     HB_OK = 0,
@@ -36,10 +36,20 @@ typedef enum hb_status {
     HB_ERR_UNSUPPORTED = -3  /* device is not sm_100 / feature not built */
 } hb_status;
 
-#define HB_MAX_DOF 16
-#define HB_MAX_OBS 48
-#define HB_NUM_REWARDS 18
-#define HB_MAX_CONTACT_BODIES 4
+#define HB_MAX_DOF 24
+#define HB_MAX_OBS 80
+#define HB_NUM_REWARDS 22
+#define HB_MAX_CONTACT_BODIES 16
+
+/* The tasks the reference registers (envs/__init__.py:46-48) share the env step; they differ in the number of joints,
+ * the frame sizes and the layout of the privileged frame:
+ *   HB_TASK_HECTOR  hector (10 DOF, frames 41 / 70, stacks 15 / 15; envs/custom/hector_env.py) and hector_full (18 DOF,
+ *                   frames 65 / 94; envs/custom/hector_w_arm_env.py): feet positions / velocities and the root position
+ *                   in the privileged frame
+ *   HB_TASK_XBOT    humanoid_ppo / XBot-L (12 DOF, frames 47 / 73, stacks 15 / 3; envs/custom/humanoid_env.py): the
+ *                   reference-trajectory error q - ref_dof_pos instead */
+#define HB_TASK_HECTOR 0
+#define HB_TASK_XBOT 1
 
 /* Reward terms in the reference's accumulation order: alphabetical, because
  * utils/helpers.py:47 walks dir() (envs/base/legged_robot.py:517-540). */
@@ -47,8 +57,8 @@ enum hb_reward_id {
     HB_R_ACTION_SMOOTHNESS = 0, HB_R_BASE_ACC, HB_R_BASE_HEIGHT, HB_R_COLLISION,
     HB_R_DEFAULT_JOINT_POS, HB_R_DOF_ACC, HB_R_DOF_VEL, HB_R_FEET_AIR_TIME,
     HB_R_FEET_CLEARANCE, HB_R_FEET_CONTACT_FORCES, HB_R_FEET_CONTACT_NUMBER,
-    HB_R_FEET_DISTANCE, HB_R_FOOT_SLIP, HB_R_KNEE_DISTANCE, HB_R_ORIENTATION,
-    HB_R_TORQUES, HB_R_TRACKING_ANG_VEL, HB_R_TRACKING_LIN_VEL
+    HB_R_FEET_DISTANCE, HB_R_FOOT_SLIP, HB_R_JOINT_POS, HB_R_KNEE_DISTANCE, HB_R_LOW_SPEED, HB_R_ORIENTATION,
+    HB_R_TORQUES, HB_R_TRACK_VEL_HARD, HB_R_TRACKING_ANG_VEL, HB_R_TRACKING_LIN_VEL, HB_R_VEL_MISMATCH_EXP
 };
 
 /* Task constants (envs/custom/hector_config.py:4-200, resolved the way
@@ -56,12 +66,13 @@ enum hb_reward_id {
 typedef struct hb_env_params {
     int32_t abi_version;            /* = HB_ABI_VERSION */
     int32_t num_envs;
-    int32_t num_dof;                /* 10 */
-    int32_t num_bodies;             /* 11 after collapse_fixed_joints */
-    int32_t num_single_obs;         /* 41 */
+    int32_t task_kind;              /* HB_TASK_HECTOR / HB_TASK_XBOT */
+    int32_t num_dof;                /* 10 (hector), 18 (hector_full), 12 (XBot-L) */
+    int32_t num_bodies;             /* 11 / 19 / 13 after collapse_fixed_joints */
+    int32_t num_single_obs;         /* 41 / 65 / 47 */
     int32_t frame_stack;            /* 15 */
-    int32_t num_single_priv;        /* 70 */
-    int32_t c_frame_stack;          /* 15 */
+    int32_t num_single_priv;        /* 70 / 94 / 73 */
+    int32_t c_frame_stack;          /* 15 / 15 / 3 */
     int32_t obs_ld, priv_ld;        /* row pitch, in floats, of every obs / privileged-obs buffer handed to the calls
                                        below; 0 = dense (frame_stack * num_single_obs).  A pitch that is a multiple of
                                        4 (616 / 1052) makes the rows TMA-addressable: the buffers can be the rollout
@@ -78,6 +89,12 @@ typedef struct hb_env_params {
     int32_t add_noise;              /* noise.add_noise */
     int32_t only_positive_rewards;
     int32_t custom_origins;         /* root xy jitter at reset (:381-384) */
+    /* joint index constants of the reward terms, as the task's env file spells them */
+    int32_t yaw_roll[2];            /* first joint of the (yaw, roll) pair of the left / right leg: default_joint_pos
+                                       (hector_env.py:363-364 -> 0, 5; hector_w_arm_env.py:370-373 -> 0, 9; humanoid_env.py -> 0, 6) */
+    int32_t arm_pair[2];            /* hector_full: first joint of the left / right arm pair (5, 14; :371-378); else -1 */
+    int32_t ref_left[3], ref_right[3];   /* compute_ref_state: joints driven by the left / right half of the gait sine
+                                       (hector_env.py:100-107 -> 2,3,4 / 7,8,9; humanoid_env.py:131-138 -> 2,3,4 / 8,9,10) */
     /* control (legged_robot.py:339-355) */
     float action_scale;
     float clip_actions;
@@ -87,6 +104,7 @@ typedef struct hb_env_params {
     float default_dof_pos[HB_MAX_DOF];
     float torque_limits[HB_MAX_DOF];
     /* time */
+    float ref_scale[2];             /* target_joint_pos_scale and twice it (compute_ref_state) */
     float dt;                       /* decimation * sim.dt */
     float cycle_time;
     float max_episode_length_s;
@@ -130,6 +148,8 @@ typedef struct hb_env_buffers {
     float *feet_air_time;           /* [N,2] */
     uint8_t *last_contacts;         /* [N,2] bool */
     float *feet_height, *last_feet_z;   /* [N,2] */
+    float *ref_dof_pos;             /* [N,ndof] reference trajectory left by the last compute_observations (compute_ref_state);
+                                       needed for the joint_pos reward and the XBot-L privileged frame, else may be NULL */
     float *rand_push_force, *rand_push_torque;   /* [N,3] */
     float *episode_sums;            /* [HB_NUM_REWARDS, N] */
     int64_t *episode_length_buf;    /* [N] */
@@ -165,8 +185,8 @@ typedef struct hb_env_noise {
     const float *z_action;          /* [N,ndof] torch.randn_like(actions)  hector_env.py:168 */
     const float *u_cmd;             /* [N,3]  command resampling           legged_robot.py:327-330 */
     const float *u_push;            /* [N,5]  push lin xy + ang xyz        hector_env.py:58-63 */
-    const float *u_reset;           /* [N,15] dof(10) root xy(2) cmd(3)    legged_robot.py:366,384,327-330 */
-    const float *z_obs;             /* [N,41] torch.randn_like(obs_buf)    hector_env.py:241 */
+    const float *u_reset;           /* [N,ndof+5] dof(ndof) root xy(2) cmd(3)  legged_robot.py:366,384,327-330 */
+    const float *z_obs;             /* [N,num_single_obs] torch.randn_like(obs_buf)    hector_env.py:241 */
     const uint64_t *rng_counter;    /* [2] device: {step counter, key} of the device generator, or NULL */
 } hb_env_noise;
 

@@ -10,11 +10,12 @@ import ctypes as C
 import os
 from typing import Optional
 
-HB_ABI_VERSION = 3
-HB_MAX_DOF = 16
-HB_MAX_OBS = 48
-HB_NUM_REWARDS = 18
-HB_MAX_CONTACT_BODIES = 4
+HB_ABI_VERSION = 4
+HB_MAX_DOF = 24
+HB_MAX_OBS = 80
+HB_NUM_REWARDS = 22
+HB_MAX_CONTACT_BODIES = 16
+HB_TASK_HECTOR, HB_TASK_XBOT = 0, 1
 
 HB_STAGE_STEP = 0x1
 HB_STAGE_RESET_ALL = 0x2
@@ -27,8 +28,8 @@ HB_STAGE_PREPARE, HB_STAGE_TERMINATION, HB_STAGE_REWARD, HB_STAGE_LAST = 0x40, 0
 # alphabetical = the reference's accumulation order (utils/helpers.py:47)
 REWARD_NAMES = ("action_smoothness", "base_acc", "base_height", "collision", "default_joint_pos", "dof_acc",
                 "dof_vel", "feet_air_time", "feet_clearance", "feet_contact_forces", "feet_contact_number",
-                "feet_distance", "foot_slip", "knee_distance", "orientation", "torques", "tracking_ang_vel",
-                "tracking_lin_vel")
+                "feet_distance", "foot_slip", "joint_pos", "knee_distance", "low_speed", "orientation", "torques",
+                "track_vel_hard", "tracking_ang_vel", "tracking_lin_vel", "vel_mismatch_exp")
 assert len(REWARD_NAMES) == HB_NUM_REWARDS and list(REWARD_NAMES) == sorted(REWARD_NAMES)
 
 _f, _i = C.c_float, C.c_int32
@@ -37,7 +38,7 @@ _fp = C.c_void_p   # device pointers travel as integers
 
 class EnvParams(C.Structure):
     _fields_ = [
-        ("abi_version", _i), ("num_envs", _i), ("num_dof", _i), ("num_bodies", _i),
+        ("abi_version", _i), ("num_envs", _i), ("task_kind", _i), ("num_dof", _i), ("num_bodies", _i),
         ("num_single_obs", _i), ("frame_stack", _i), ("num_single_priv", _i), ("c_frame_stack", _i),
         ("obs_ld", _i), ("priv_ld", _i),
         ("feet", _i * 2), ("knees", _i * 2),
@@ -45,10 +46,11 @@ class EnvParams(C.Structure):
         ("n_pen", _i), ("pen_bodies", _i * HB_MAX_CONTACT_BODIES),
         ("max_episode_length", _i), ("resample_interval", _i), ("heading_command", _i), ("add_noise", _i),
         ("only_positive_rewards", _i), ("custom_origins", _i),
+        ("yaw_roll", _i * 2), ("arm_pair", _i * 2), ("ref_left", _i * 3), ("ref_right", _i * 3),
         ("action_scale", _f), ("clip_actions", _f), ("clip_observations", _f), ("action_delay", _f),
         ("action_noise", _f),
         ("default_dof_pos", _f * HB_MAX_DOF), ("torque_limits", _f * HB_MAX_DOF),
-        ("dt", _f), ("cycle_time", _f), ("max_episode_length_s", _f),
+        ("ref_scale", _f * 2), ("dt", _f), ("cycle_time", _f), ("max_episode_length_s", _f),
         ("cmd_lo", _f * 3), ("cmd_span", _f * 3),
         ("push_lin_lo", _f), ("push_lin_span", _f), ("push_ang_lo", _f), ("push_ang_span", _f),
         ("reset_dof_lo", _f), ("reset_dof_span", _f), ("reset_xy_lo", _f), ("reset_xy_span", _f),
@@ -66,7 +68,7 @@ _BUFFER_FIELDS = (
     "root_states", "dof_state", "contact_forces", "rigid_state", "p_gains", "d_gains", "env_frictions",
     "body_mass", "env_origins", "actions", "last_actions", "last_last_actions", "last_dof_vel", "last_root_vel",
     "torques", "commands", "base_lin_vel", "base_ang_vel", "projected_gravity", "base_euler_xyz", "feet_air_time",
-    "last_contacts", "feet_height", "last_feet_z", "rand_push_force", "rand_push_torque", "episode_sums",
+    "last_contacts", "feet_height", "last_feet_z", "ref_dof_pos", "rand_push_force", "rand_push_torque", "episode_sums",
     "episode_length_buf", "reset_buf", "time_out_buf", "rew_buf", "reset_env_ids", "reset_count", "episode_means",
     "episode_means_prev", "episode_ring", "time_outs_latched", "scratch_ballots", "scratch_sums")
 

@@ -15,9 +15,34 @@
 
 namespace {
 
-constexpr int NDOF = 10;                          // hector (hector_config.py:16)
-constexpr int OBS = 5 + 3 * NDOF + 6;             // 41  (hector_env.py:219-226)
-constexpr int PRIV = 5 + 3 * NDOF + 9 + 12 + 3 + 5 + 2 + 4;   // 70  (hector_env.py:195-216)
+// The three tasks the reference registers (envs/__init__.py:46-48) share one env step; they differ in the number of
+// joints and in the privileged frame:
+//   KIND_HECTOR  hector (10 DOF, hector_env.py:195-226) and hector_full (18 DOF, hector_w_arm_env.py:202-233):
+//                [cmd 5 | q-q0 N | dq N | a N | lin 3 | ang 3 | euler 3 | feet pos 6 | feet vel 6 | root pos 3 | push 2+3 |
+//                 friction | mass/30 | stance 2 | contact 2]                                        = 3 N + 40
+//   KIND_XBOT    humanoid_ppo / XBot-L (12 DOF, humanoid_env.py:217-234): the reference-trajectory error instead of the
+//                feet / root entries: [cmd 5 | q-q0 N | dq N | a N | q-ref N | lin 3 | ang 3 | euler 3 | push 2+3 |
+//                 friction | mass/30 | stance 2 | contact 2]                                        = 4 N + 25
+// The observation frame is [cmd 5 | q-q0 N | dq N | a N | ang 3 | euler 3] = 3 N + 11 for all of them.
+constexpr int KIND_HECTOR = 0, KIND_XBOT = 1;
+template <int NDOF_, int KIND_>
+struct Task {
+    static constexpr int NDOF = NDOF_, KIND = KIND_;
+    static constexpr int OBS = 5 + 3 * NDOF + 6;
+    static constexpr int B0 = 5 + 3 * NDOF;                         // end of the joint columns
+    static constexpr int B1 = KIND == KIND_XBOT ? B0 + NDOF : B0;   // start of the base-velocity columns
+    static constexpr int P_DIFF = B0;                               // KIND_XBOT only
+    static constexpr int P_LIN = B1, P_ANG = B1 + 3, P_EUL = B1 + 6;
+    static constexpr int P_FEET_POS = B1 + 9, P_FEET_VEL = B1 + 15, P_ROOT = B1 + 21;       // KIND_HECTOR only
+    static constexpr int P_PUSH_F = KIND == KIND_XBOT ? B1 + 9 : B1 + 24;
+    static constexpr int P_PUSH_T = P_PUSH_F + 2, P_FRICTION = P_PUSH_F + 5, P_MASS = P_PUSH_F + 6, P_STANCE = P_PUSH_F + 7,
+                         P_CONTACT = P_PUSH_F + 9;
+    static constexpr int PRIV = P_CONTACT + 2;
+    static constexpr int U_RESET = NDOF + 5;                        // dof offsets, root xy, command draws (legged_robot.py:366,384,327-330)
+};
+static_assert(Task<10, KIND_HECTOR>::OBS == 41 && Task<10, KIND_HECTOR>::PRIV == 70, "hector (hector_config.py:12-14)");
+static_assert(Task<18, KIND_HECTOR>::OBS == 65 && Task<18, KIND_HECTOR>::PRIV == 94, "hector_full (hector_w_arm_config.py:12-14)");
+static_assert(Task<12, KIND_XBOT>::OBS == 47 && Task<12, KIND_XBOT>::PRIV == 73, "XBot-L (humanoid_config.py:46-48)");
 constexpr int TILE = 32;
 
 constexpr float TWO_PI_F = 6.283185307179586f;    // float32(2*np.pi)
@@ -70,7 +95,7 @@ __device__ __forceinline__ float clampf(float v, float lo, float hi) { return fm
 // counter = (env, slot, step), so a draw is a pure function of (seed, step, env, slot) - no state besides
 // the step counter, no tape written to or read from HBM, and rare draws (resets, command resampling,
 // pushes) cost nothing on the steps that do not need them.  Slots of one env and step:
-//   0-2 z_action[10] | 3-13 z_obs[41] | 14-17 u_reset[15] | 18 u_cmd[3] | 19-20 u_push[5] | 21 u_delay
+//   0-5 z_action[<=24] | 6-25 z_obs[<=80] | 26-33 u_reset[<=29] | 34 u_cmd[3] | 35-36 u_push[5] | 37 u_delay
 // ------------------------------------------------------------------------------------------
 struct Rng {
     uint32_t k0, k1, s0, s1;
@@ -85,7 +110,7 @@ __device__ __forceinline__ Rng make_rng(const hb_env_noise &nz) {
     r.s0 = (uint32_t)step, r.s1 = (uint32_t)(step >> 32);
     return r;
 }
-constexpr int SLOT_Z_ACTION = 0, SLOT_Z_OBS = 3, SLOT_U_RESET = 14, SLOT_U_CMD = 18, SLOT_U_PUSH = 19, SLOT_U_DELAY = 21;
+constexpr int SLOT_Z_ACTION = 0, SLOT_Z_OBS = 6, SLOT_U_RESET = 26, SLOT_U_CMD = 34, SLOT_U_PUSH = 35, SLOT_U_DELAY = 37;
 
 using hb::philox4x32_10;
 __device__ __forceinline__ void rng_uniform4(const Rng &g, int env, int slot, float u[4]) {      // [0, 1)
@@ -119,9 +144,9 @@ __device__ __forceinline__ void rng_uniforms(const Rng &g, int env, int slot, in
 // a2: HectorFreeEnv.step prologue (hector_env.py:158-169, legged_robot.py:90-91)
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ float action_prologue(const float *__restrict__ a_in, const float *__restrict__ actions,
-                                                 const hb_env_noise &nz, const Rng &rng, int i, float clip, float action_delay,
-                                                 float action_noise) {
-    const int env = i / NDOF, j = i - env * NDOF;
+                                                 const hb_env_noise &nz, const Rng &rng, int i, int ndof, float clip,
+                                                 float action_delay, float action_noise) {
+    const int env = i / ndof, j = i - env * ndof;
     float a = clampf(a_in[i], -clip, clip);
     float ud = 0.0f;
     if (action_delay != 0.0f) {
@@ -144,11 +169,11 @@ __device__ __forceinline__ float action_prologue(const float *__restrict__ a_in,
 
 __global__ void __launch_bounds__(256)
 action_prologue_kernel(const float *__restrict__ a_in, float *__restrict__ actions, const __grid_constant__ hb_env_noise nz,
-                       int total, float clip, float action_delay, float action_noise) {
+                       int total, int ndof, float clip, float action_delay, float action_noise) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
     const Rng rng = make_rng(nz);
-    actions[i] = action_prologue(a_in, actions, nz, rng, i, clip, action_delay, action_noise);
+    actions[i] = action_prologue(a_in, actions, nz, rng, i, ndof, clip, action_delay, action_noise);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -186,18 +211,18 @@ __global__ void __launch_bounds__(256)
 prologue_pd_kernel(const float *__restrict__ a_in, float *__restrict__ actions, const __grid_constant__ hb_env_noise nz,
                    float clip, float action_delay, float action_noise, const float4 *__restrict__ dof_state2,
                    const float2 *__restrict__ kp2, const float2 *__restrict__ kd2, float2 *__restrict__ torques2, int pairs,
-                   float action_scale, const __grid_constant__ PdConsts c) {
+                   int ndof, float action_scale, const __grid_constant__ PdConsts c) {
     hb::pdl_trigger();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= pairs) return;
     const Rng rng = make_rng(nz);
     float2 a;
-    a.x = action_prologue(a_in, actions, nz, rng, 2 * i, clip, action_delay, action_noise);
-    a.y = action_prologue(a_in, actions, nz, rng, 2 * i + 1, clip, action_delay, action_noise);
+    a.x = action_prologue(a_in, actions, nz, rng, 2 * i, ndof, clip, action_delay, action_noise);
+    a.y = action_prologue(a_in, actions, nz, rng, 2 * i + 1, ndof, clip, action_delay, action_noise);
     reinterpret_cast<float2 *>(actions)[i] = a;
     const float4 s = dof_state2[i];
     const float2 kp = kp2[i], kd = kd2[i];
-    const int j = (2 * i) % NDOF;
+    const int j = (2 * i) % ndof;
     float2 t;
     t.x = kp.x * ((a.x * action_scale + c.q0[j]) - s.x) - kd.x * s.y;
     t.y = kp.y * ((a.y * action_scale + c.q0[j + 1]) - s.z) - kd.y * s.w;
@@ -241,12 +266,11 @@ struct TileLayout {          // float offsets into the CTA's shared-memory tile
     int root, dof, contact, actions, last_actions, last_last_actions, last_dof_vel, torques, last_root_vel,
         commands, z_obs, terms, gait_s, gait_c, flags, so, sp, total;
 };
-constexpr int PRIV_PAD = PRIV;         // even row stride: the store loop reads 8-byte pairs (2-way conflicts on the role writes)
 
 // The staged inputs are dead once every role has passed barrier 1 (each lane keeps its env's values in
 // registers), so the newest-frame staging tiles so/sp reuse the same bytes: ~19 KB per CTA instead of
 // ~38 KB, which is what bounds the number of resident tiles per SM.
-__host__ __device__ inline TileLayout make_layout(int nbody, bool with_noise) {
+__host__ __device__ inline TileLayout make_layout(int nbody, bool with_noise, int NDOF, int OBS, int PRIV) {
     TileLayout L;
     int o = 0;
     L.root = o, o += TILE * 13;
@@ -261,7 +285,7 @@ __host__ __device__ inline TileLayout make_layout(int nbody, bool with_noise) {
     L.commands = o, o += TILE * 4;
     L.so = 0;
     L.sp = TILE * OBS;
-    const int out_end = TILE * (OBS + PRIV_PAD);
+    const int out_end = TILE * (OBS + PRIV);
     o = o > out_end ? o : out_end;
     L.z_obs = o, o += with_noise ? TILE * OBS : 0;      // read by the store loop: must outlive the inputs
     L.terms = o, o += HB_NUM_REWARDS * TILE;
@@ -324,11 +348,12 @@ __device__ __forceinline__ unsigned long long gtime() {
 #define HB_GT(slot) do { } while (0)
 #endif
 
-template <bool kBulk>
-__global__ void __launch_bounds__(4 * TILE, 8)
+template <bool kBulk, typename T>
+__global__ void __launch_bounds__(4 * TILE, T::NDOF <= 12 ? 8 : 5)
 post_physics_kernel(const __grid_constant__ hb_env_params p, const __grid_constant__ hb_env_buffers b,
                     const __grid_constant__ hb_env_noise nz, float *__restrict__ obs_new,
                     float *__restrict__ priv_new, int stages) {
+    constexpr int NDOF = T::NDOF, OBS = T::OBS, PRIV = T::PRIV, PRIV_PAD = T::PRIV, KIND = T::KIND, U_RESET = T::U_RESET;
     extern __shared__ __align__(128) float sm[];
     __shared__ __align__(8) uint64_t bar;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -354,7 +379,7 @@ post_physics_kernel(const __grid_constant__ hb_env_params p, const __grid_consta
     const bool tape_noise = p.add_noise && nz.z_obs != nullptr;
     HB_STAMP(0);
     HB_GT(0);
-    const TileLayout L = make_layout(p.num_bodies, with_noise);
+    const TileLayout L = make_layout(p.num_bodies, with_noise, NDOF, OBS, PRIV);
     const int crow = p.num_bodies * 3;
     const float dt = p.dt;
     const float clip = p.clip_observations;
@@ -493,6 +518,29 @@ post_physics_kernel(const __grid_constant__ hb_env_params p, const __grid_consta
                 const float ex = cmd[0] - lin.x, ey = cmd[1] - lin.y;
                 terms[HB_R_TRACKING_LIN_VEL * TILE + lane] = expf(-(ex * ex + ey * ey) * p.tracking_sigma);
             }
+            if (p.reward_scale[HB_R_VEL_MISMATCH_EXP] != 0.0f) {      // hector_env.py:395-405
+                const float lm = expf(-(lin.z * lin.z) * 10.0f);
+                const float am = expf(-sqrtf(ang.x * ang.x + ang.y * ang.y) * 5.0f);
+                terms[HB_R_VEL_MISMATCH_EXP * TILE + lane] = (lm + am) / 2.0f;
+            }
+            if (p.reward_scale[HB_R_TRACK_VEL_HARD] != 0.0f) {        // :407-424
+                const float ex = cmd[0] - lin.x, ey = cmd[1] - lin.y;
+                const float le = sqrtf(ex * ex + ey * ey), ae = fabsf(cmd[2] - ang.z);
+                terms[HB_R_TRACK_VEL_HARD * TILE + lane] = (expf(-le * 10.0f) + expf(-ae * 10.0f)) / 2.0f - 0.2f * (le + ae);
+            }
+            if (p.reward_scale[HB_R_LOW_SPEED] != 0.0f) {             // :468-499
+                const float sp_abs = fabsf(lin.x), cm_abs = fabsf(cmd[0]);
+                const bool too_low = sp_abs < 0.5f * cm_abs, too_high = sp_abs > 1.2f * cm_abs;
+                const float sgn_v = (lin.x > 0.0f) ? 1.0f : ((lin.x < 0.0f) ? -1.0f : 0.0f);
+                const float sgn_c = (cmd[0] > 0.0f) ? 1.0f : ((cmd[0] < 0.0f) ? -1.0f : 0.0f);
+                float r = 0.0f;
+                if (too_low) r = -1.0f;
+                if (too_high) r = 0.0f;
+                if (!(too_low || too_high)) r = 1.2f;
+                if (sgn_v != sgn_c) r = -2.0f;
+                r = r * ((cm_abs > 0.1f) ? 1.0f : 0.0f);
+                terms[HB_R_LOW_SPEED * TILE + lane] = r;
+            }
         }
         HB_STAMP(2);
         tile_barrier();                                           // ---- barrier 1 ----
@@ -500,24 +548,24 @@ post_physics_kernel(const __grid_constant__ hb_env_params p, const __grid_consta
         const bool reset = valid && (flags[lane] & 1);
         const float gs = reset ? 0.0f : sm[L.gait_s + lane], gc = reset ? 1.0f : sm[L.gait_c + lane];
         if (reset) {         // _reset_root_states + _resample_commands + the gravity/euler fix-up (:373-396,321-335,211-214)
-            float u[15];
+            float u5[5];        // root xy jitter (2) and the command draws (3): columns NDOF .. NDOF+4 of the reset draws
             if (nz.u_reset) {
 #pragma unroll
-                for (int k = 10; k < 15; ++k) u[k] = nz.u_reset[(size_t)env * 15 + k];
+                for (int k = 0; k < 5; ++k) u5[k] = nz.u_reset[(size_t)env * U_RESET + NDOF + k];
             } else {
-                rng_uniforms(rng, env, SLOT_U_RESET, 10, 5, u + 10);
+                rng_uniforms(rng, env, SLOT_U_RESET, NDOF, 5, u5);
             }
 #pragma unroll
             for (int k = 0; k < 13; ++k) root[k] = p.base_init_state[k];
 #pragma unroll
             for (int k = 0; k < 3; ++k) root[k] += b.env_origins[env * 3 + k];
             if (p.custom_origins) {
-                root[0] += p.reset_xy_span * u[10] + p.reset_xy_lo;
-                root[1] += p.reset_xy_span * u[11] + p.reset_xy_lo;
+                root[0] += p.reset_xy_span * u5[0] + p.reset_xy_lo;
+                root[1] += p.reset_xy_span * u5[1] + p.reset_xy_lo;
             }
-            cmd[0] = p.cmd_span[0] * u[12] + p.cmd_lo[0];
-            cmd[1] = p.cmd_span[1] * u[13] + p.cmd_lo[1];
-            cmd[3] = p.cmd_span[2] * u[14] + p.cmd_lo[2];
+            cmd[0] = p.cmd_span[0] * u5[2] + p.cmd_lo[0];
+            cmd[1] = p.cmd_span[1] * u5[3] + p.cmd_lo[1];
+            cmd[3] = p.cmd_span[2] * u5[4] + p.cmd_lo[2];
             const float keep = (sqrtf(cmd[0] * cmd[0] + cmd[1] * cmd[1]) > 0.2f) ? 1.0f : 0.0f;
             cmd[0] *= keep, cmd[1] *= keep;
             grav = {p.reset_gravity[0], p.reset_gravity[1], p.reset_gravity[2]};
@@ -546,7 +594,7 @@ post_physics_kernel(const __grid_constant__ hb_env_params p, const __grid_consta
             for (int k = 0; k < 4; ++k) b.commands[(size_t)env * 4 + k] = cmd[k];
         }
         if (emit_obs) {      // command input, base velocities, euler, root position, push (hector_env.py:186-226)
-            constexpr int B0 = 5 + 3 * NDOF;
+            constexpr int B0 = T::B0;
             float o[11];
             o[0] = gs, o[1] = gc;
             o[2] = cmd[0] * p.obs_lin_vel, o[3] = cmd[1] * p.obs_lin_vel, o[4] = cmd[2] * p.obs_ang_vel;
@@ -559,18 +607,20 @@ post_physics_kernel(const __grid_constant__ hb_env_params p, const __grid_consta
             }
 #pragma unroll
             for (int k = 0; k < 6; ++k) {
-                sp[lane * PRIV_PAD + B0 + 3 + k] = clampf(o[5 + k], -clip, clip);
+                sp[lane * PRIV_PAD + T::P_ANG + k] = clampf(o[5 + k], -clip, clip);
                 so[lane * OBS + B0 + k] = noisy_clip(o[5 + k], B0 + k);
             }
-            sp[lane * PRIV_PAD + B0] = clampf(lin.x * p.obs_lin_vel, -clip, clip);
-            sp[lane * PRIV_PAD + B0 + 1] = clampf(lin.y * p.obs_lin_vel, -clip, clip);
-            sp[lane * PRIV_PAD + B0 + 2] = clampf(lin.z * p.obs_lin_vel, -clip, clip);
+            sp[lane * PRIV_PAD + T::P_LIN] = clampf(lin.x * p.obs_lin_vel, -clip, clip);
+            sp[lane * PRIV_PAD + T::P_LIN + 1] = clampf(lin.y * p.obs_lin_vel, -clip, clip);
+            sp[lane * PRIV_PAD + T::P_LIN + 2] = clampf(lin.z * p.obs_lin_vel, -clip, clip);
+            if (KIND == KIND_HECTOR) {
 #pragma unroll
-            for (int k = 0; k < 3; ++k) sp[lane * PRIV_PAD + B0 + 21 + k] = clampf(root[k], -clip, clip);
-            sp[lane * PRIV_PAD + B0 + 24] = clampf(push_f[0], -clip, clip);
-            sp[lane * PRIV_PAD + B0 + 25] = clampf(push_f[1], -clip, clip);
+                for (int k = 0; k < 3; ++k) sp[lane * PRIV_PAD + T::P_ROOT + k] = clampf(root[k], -clip, clip);
+            }
+            sp[lane * PRIV_PAD + T::P_PUSH_F] = clampf(push_f[0], -clip, clip);
+            sp[lane * PRIV_PAD + T::P_PUSH_F + 1] = clampf(push_f[1], -clip, clip);
 #pragma unroll
-            for (int k = 0; k < 3; ++k) sp[lane * PRIV_PAD + B0 + 26 + k] = clampf(push_t[k], -clip, clip);
+            for (int k = 0; k < 3; ++k) sp[lane * PRIV_PAD + T::P_PUSH_T + k] = clampf(push_t[k], -clip, clip);
         }
     } else if (warp == 1) {
         // ================================ joints ================================
@@ -578,6 +628,12 @@ post_physics_kernel(const __grid_constant__ hb_env_params p, const __grid_consta
         HB_STAMP(1);
         // Only q, qd and the actions stay live across the barrier; the previous-step buffers are consumed
         // (and, on a step, rolled forward: legged_robot.py:146-148) joint by joint before it.
+        // The reference trajectory (compute_ref_state, hector_env.py:90-111 / humanoid_env.py:120-142) is STATE: it is
+        // refreshed inside compute_observations, so the joint_pos reward of a step sees the one the previous step left.
+        const bool joint_pos_on = p.reward_scale[HB_R_JOINT_POS] != 0.0f;
+        const bool use_ref = (KIND == KIND_XBOT || joint_pos_on) && b.ref_dof_pos != nullptr;
+        long long ep_len = 0;
+        if (use_ref && valid) ep_len = b.episode_length_buf[env] + (do_prepare ? 1 : 0);
         float q[NDOF], qd[NDOF], act[NDOF];
 #pragma unroll
         for (int j = 0; j < NDOF; ++j) {
@@ -586,8 +642,8 @@ post_physics_kernel(const __grid_constant__ hb_env_params p, const __grid_consta
             act[j] = sm[L.actions + ln * NDOF + j];
         }
         if (do_rew || do_last) {
-            float t1 = 0.f, t2 = 0.f, t3 = 0.f, ss = 0.f, acc = 0.f, vel = 0.f, tq = 0.f;
-            float dy[4] = {0.f, 0.f, 0.f, 0.f};
+            float t1 = 0.f, t2 = 0.f, t3 = 0.f, ss = 0.f, acc = 0.f, vel = 0.f, tq = 0.f, rr = 0.f;
+            float dy[4] = {0.f, 0.f, 0.f, 0.f}, da[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
             for (int j = 0; j < NDOF; ++j) {
                 const float lact = sm[L.last_actions + ln * NDOF + j];
@@ -600,8 +656,18 @@ post_physics_kernel(const __grid_constant__ hb_env_params p, const __grid_consta
                 t3 += fabsf(act[j]);
                 const float d = q[j] - p.default_dof_pos[j];           // default_joint_pos, :357-367
                 ss += d * d;
-                if (j == 0 || j == 1) dy[j] = d;
-                if (j == 5 || j == 6) dy[j - 3] = d;
+                // hip yaw / roll of both legs (and, hector_full, the first two arm joints of both arms:
+                // hector_w_arm_env.py:371-378); the index pairs are task constants
+                if (j == p.yaw_roll[0] || j == p.yaw_roll[0] + 1) dy[j - p.yaw_roll[0]] = d;
+                if (j == p.yaw_roll[1] || j == p.yaw_roll[1] + 1) dy[2 + j - p.yaw_roll[1]] = d;
+                if (p.arm_pair[0] >= 0) {
+                    if (j == p.arm_pair[0] || j == p.arm_pair[0] + 1) da[j - p.arm_pair[0]] = d;
+                    if (j == p.arm_pair[1] || j == p.arm_pair[1] + 1) da[2 + j - p.arm_pair[1]] = d;
+                }
+                if (joint_pos_on && use_ref && do_rew) {               // joint_pos, hector_env.py:264-275
+                    const float e = q[j] - (valid ? b.ref_dof_pos[(size_t)env * NDOF + j] : 0.0f);
+                    rr += e * e;
+                }
                 const float a = (ldv - qd[j]) / dt;                    // dof_acc :515-520
                 acc += a * a;
                 vel += qd[j] * qd[j];                                  // dof_vel :508-513
@@ -617,7 +683,17 @@ post_physics_kernel(const __grid_constant__ hb_env_params p, const __grid_consta
                 terms[HB_R_ACTION_SMOOTHNESS * TILE + lane] = (t1 + t2) + 0.05f * t3;
                 float yr = sqrtf(dy[0] * dy[0] + dy[1] * dy[1]) + sqrtf(dy[2] * dy[2] + dy[3] * dy[3]);
                 yr = clampf(yr - 0.1f, 0.0f, 50.0f);
-                terms[HB_R_DEFAULT_JOINT_POS * TILE + lane] = expf(-yr * 100.0f) - 0.01f * sqrtf(ss);
+                float djp = expf(-yr * 100.0f);
+                if (p.arm_pair[0] >= 0) {
+                    float ar = sqrtf(da[0] * da[0] + da[1] * da[1]) + sqrtf(da[2] * da[2] + da[3] * da[3]);
+                    ar = clampf(ar - 0.1f, 0.0f, 25.0f);
+                    djp = djp + expf(-ar * 2.0f);
+                }
+                terms[HB_R_DEFAULT_JOINT_POS * TILE + lane] = djp - 0.01f * sqrtf(ss);
+                if (joint_pos_on) {
+                    const float nrm = sqrtf(rr);
+                    terms[HB_R_JOINT_POS * TILE + lane] = expf(-2.0f * nrm) - 0.2f * clampf(nrm, 0.0f, 0.5f);
+                }
                 terms[HB_R_DOF_ACC * TILE + lane] = acc;
                 terms[HB_R_DOF_VEL * TILE + lane] = vel;
                 terms[HB_R_TORQUES * TILE + lane] = tq;
@@ -631,7 +707,7 @@ post_physics_kernel(const __grid_constant__ hb_env_params p, const __grid_consta
             float u[NDOF];
             if (nz.u_reset) {
 #pragma unroll
-                for (int j = 0; j < NDOF; ++j) u[j] = nz.u_reset[(size_t)env * 15 + j];
+                for (int j = 0; j < NDOF; ++j) u[j] = nz.u_reset[(size_t)env * U_RESET + j];
             } else {
                 rng_uniforms(rng, env, SLOT_U_RESET, 0, NDOF, u);
             }
@@ -649,8 +725,26 @@ post_physics_kernel(const __grid_constant__ hb_env_params p, const __grid_consta
             }
         }
         if (emit_obs) {
+            float sl = 0.0f, sr = 0.0f;
+            if (use_ref) {       // compute_ref_state of this compute_observations call
+                if (reset) ep_len = 0;
+                const float sn = sinf(TWO_PI_F * (((float)ep_len * dt) / p.cycle_time));
+                sl = fminf(sn, 0.0f), sr = fmaxf(sn, 0.0f);
+                if (fabsf(sn) < 0.1f) sl = sr = 0.0f;               // double support
+            }
 #pragma unroll
             for (int j = 0; j < NDOF; ++j) {
+                if (use_ref) {
+                    float ref = 0.0f;
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        const float sc = (k == 1) ? p.ref_scale[1] : p.ref_scale[0];
+                        if (j == p.ref_left[k]) ref = sl * sc;
+                        if (j == p.ref_right[k]) ref = sr * sc;
+                    }
+                    if (valid) b.ref_dof_pos[(size_t)env * NDOF + j] = ref;
+                    if (KIND == KIND_XBOT) sp[lane * PRIV_PAD + T::P_DIFF + j] = clampf(q[j] - ref, -clip, clip);
+                }
                 float v0 = (q[j] - p.default_dof_pos[j]) * p.obs_dof_pos, v1 = qd[j] * p.obs_dof_vel;
                 sp[lane * PRIV_PAD + 5 + j] = clampf(v0, -clip, clip);
                 sp[lane * PRIV_PAD + 5 + NDOF + j] = clampf(v1, -clip, clip);
@@ -791,18 +885,19 @@ post_physics_kernel(const __grid_constant__ hb_env_params p, const __grid_consta
             }
         }
         if (emit_obs) {
-            constexpr int B0 = 5 + 3 * NDOF;
+            if (KIND == KIND_HECTOR) {
 #pragma unroll
-            for (int f = 0; f < 2; ++f)
+                for (int f = 0; f < 2; ++f)
 #pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    sp[lane * PRIV_PAD + B0 + 9 + f * 3 + k] = clampf(foot_pos[f][k], -clip, clip);
-                    sp[lane * PRIV_PAD + B0 + 15 + f * 3 + k] = clampf(foot_vel[f][k], -clip, clip);
-                }
-            sp[lane * PRIV_PAD + B0 + 29] = clampf(friction, -clip, clip);
-            sp[lane * PRIV_PAD + B0 + 30] = clampf(mass / 30.0f, -clip, clip);
-            sp[lane * PRIV_PAD + B0 + 31] = st[0], sp[lane * PRIV_PAD + B0 + 32] = st[1];
-            sp[lane * PRIV_PAD + B0 + 33] = ct[0] ? 1.0f : 0.0f, sp[lane * PRIV_PAD + B0 + 34] = ct[1] ? 1.0f : 0.0f;
+                    for (int k = 0; k < 3; ++k) {
+                        sp[lane * PRIV_PAD + T::P_FEET_POS + f * 3 + k] = clampf(foot_pos[f][k], -clip, clip);
+                        sp[lane * PRIV_PAD + T::P_FEET_VEL + f * 3 + k] = clampf(foot_vel[f][k], -clip, clip);
+                    }
+            }
+            sp[lane * PRIV_PAD + T::P_FRICTION] = clampf(friction, -clip, clip);
+            sp[lane * PRIV_PAD + T::P_MASS] = clampf(mass / 30.0f, -clip, clip);
+            sp[lane * PRIV_PAD + T::P_STANCE] = st[0], sp[lane * PRIV_PAD + T::P_STANCE + 1] = st[1];
+            sp[lane * PRIV_PAD + T::P_CONTACT] = ct[0] ? 1.0f : 0.0f, sp[lane * PRIV_PAD + T::P_CONTACT + 1] = ct[1] ? 1.0f : 0.0f;
         }
     } else {
         // ================================ ledger ================================
@@ -879,7 +974,7 @@ post_physics_kernel(const __grid_constant__ hb_env_params p, const __grid_consta
             const int orow = p.frame_stack * OBS, prow = p.c_frame_stack * PRIV;
             const int ostride = p.obs_ld ? p.obs_ld : orow, pstride = p.priv_ld ? p.priv_ld : prow;   // row pitch
             const int t = threadIdx.x;
-            if (((pstride | prow) & 1) == 0 && (reinterpret_cast<uintptr_t>(priv_new) & 7u) == 0) {
+            if ((PRIV & 1) == 0 && ((pstride | prow) & 1) == 0 && (reinterpret_cast<uintptr_t>(priv_new) & 7u) == 0) {
                 int r = t / P2, c2 = t - r * P2;
                 float2 *dst = reinterpret_cast<float2 *>(priv_new + (size_t)env0 * pstride + (prow - PRIV));
                 const float2 *src = reinterpret_cast<const float2 *>(sp);
@@ -1221,19 +1316,36 @@ get_heights_kernel(const float *__restrict__ root_states, const float *__restric
 
 int g_use_bulk = 1;
 
-// hector frame stacks (hector_config.py:8-20): obs 15 x 41, privileged obs 15 x 70
-constexpr int ROW_OBS = 15 * OBS, ROW_PRIV = 15 * PRIV;
-// ... and the same rows at a 16-byte pitch (TMA-addressable: the rollout storage's slots)
-constexpr int LD_OBS = (ROW_OBS + 3) / 4 * 4, LD_PRIV = (ROW_PRIV + 3) / 4 * 4;
+// Frame stacks of the three tasks (hector_config.py:8-20, hector_w_arm_config.py:8-20, humanoid_config.py:42-52): rows
+// either dense or at the 16-byte pitch pad4(row + 1) (TMA-addressable: the rollout storage's slots)
+constexpr int pad4c(int v) { return (v + 3) / 4 * 4; }
+template <int OBS_, int S_, int PRIV_, int CS_>
+struct StackShape {
+    static constexpr int FRAME_A = OBS_, ROW_A = S_ * OBS_, LD_A = pad4c(ROW_A + 1);
+    static constexpr int FRAME_B = PRIV_, ROW_B = CS_ * PRIV_, LD_B = pad4c(ROW_B + 1);
+};
+using ShapeHector = StackShape<41, 15, 70, 15>;
+using ShapeHectorFull = StackShape<65, 15, 94, 15>;
+using ShapeXBot = StackShape<47, 15, 73, 3>;
+constexpr int ROW_OBS = ShapeHector::ROW_A, ROW_PRIV = ShapeHector::ROW_B, OBS = 41, PRIV = 70;      // hb_stack_shift's fast paths
 
-// 0 = not a built layout, 1 = dense rows, 2 = 16-byte pitch
-int stack_layout(const hb_env_params *p) {
+template <typename S>
+int shape_layout(const hb_env_params *p) {      // 0 = other shape, 1 = dense rows, 2 = 16-byte pitch
     const int row_a = p->frame_stack * p->num_single_obs, row_b = p->c_frame_stack * p->num_single_priv;
-    if (row_a != ROW_OBS || p->num_single_obs != OBS || row_b != ROW_PRIV || p->num_single_priv != PRIV) return 0;
+    if (row_a != S::ROW_A || p->num_single_obs != S::FRAME_A || row_b != S::ROW_B || p->num_single_priv != S::FRAME_B) return 0;
     const int ld_a = p->obs_ld ? p->obs_ld : row_a, ld_b = p->priv_ld ? p->priv_ld : row_b;
-    if (ld_a == ROW_OBS && ld_b == ROW_PRIV) return 1;
-    if (ld_a == LD_OBS && ld_b == LD_PRIV) return 2;
+    if (ld_a == S::ROW_A && ld_b == S::ROW_B) return 1;
+    if (ld_a == S::LD_A && ld_b == S::LD_B) return 2;
     return 0;
+}
+
+// shape id (0 hector, 1 hector_full, 2 XBot-L) and layout of the buffers described by p; layout 0 = not a built shape
+int stack_layout(const hb_env_params *p, int *shape) {
+    int l;
+    if ((l = shape_layout<ShapeHector>(p))) return *shape = 0, l;
+    if ((l = shape_layout<ShapeHectorFull>(p))) return *shape = 1, l;
+    if ((l = shape_layout<ShapeXBot>(p))) return *shape = 2, l;
+    return *shape = -1, 0;
 }
 
 int shift_any(const float *prev, float *next, const uint8_t *reset_buf, int num_envs, int row, int ld, int frame,
@@ -1263,6 +1375,33 @@ int shift_any(const float *prev, float *next, const uint8_t *reset_buf, int num_
         stack_shift_scalar_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(prev, next, reset_buf, total, row, ld, frame);
     }
     HB_CHECK_LAUNCH("stack_shift_kernel");
+    return HB_OK;
+}
+
+template <typename T>
+int launch_post_physics(const hb_env_params *p, const hb_env_buffers *buf, const hb_env_noise *noise, float *obs_new,
+                               float *priv_new, int32_t stages, bool bulk, cudaStream_t st) {
+    const bool with_noise = p->add_noise && (noise->z_obs || noise->rng_counter);
+    const TileLayout L = make_layout(p->num_bodies, with_noise, T::NDOF, T::OBS, T::PRIV);
+    const size_t smem = (size_t)L.total * sizeof(float);
+    const int tiles = (p->num_envs + TILE - 1) / TILE;
+    static bool attr_set[2] = {false, false};
+    if (bulk) {
+        if (!attr_set[1]) {
+            HB_CUDA(cudaFuncSetAttribute(post_physics_kernel<true, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+            attr_set[1] = true;
+        }
+        HB_CUDA(hb::launch_pdl(hb::use_pdl(p->num_envs), post_physics_kernel<true, T>, dim3(tiles), dim3(4 * TILE), smem, st, *p, *buf,
+                               *noise, obs_new, priv_new, (int)stages));
+    } else {
+        if (!attr_set[0]) {
+            HB_CUDA(cudaFuncSetAttribute(post_physics_kernel<false, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+            attr_set[0] = true;
+        }
+        HB_CUDA(hb::launch_pdl(hb::use_pdl(p->num_envs), post_physics_kernel<false, T>, dim3(tiles), dim3(4 * TILE), smem, st, *p, *buf,
+                               *noise, obs_new, priv_new, (int)stages));
+    }
+    HB_CHECK_LAUNCH("post_physics_kernel");
     return HB_OK;
 }
 
@@ -1314,7 +1453,7 @@ static int check_params(const hb_env_params *p, const hb_env_buffers *buf, const
     HB_REQUIRE(p->abi_version == HB_ABI_VERSION, "%s: ABI version %d != %d", who, p->abi_version, HB_ABI_VERSION);
     HB_REQUIRE(p->num_envs > 0, "%s: num_envs must be positive", who);
     HB_REQUIRE(p->resample_interval > 0, "%s: resample_interval must be positive", who);
-    HB_REQUIRE(p->num_dof == NDOF, "%s: only the 10-DOF hector layout is built (num_dof=%d)", who, p->num_dof);
+    HB_REQUIRE(p->num_dof > 0 && p->num_dof <= HB_MAX_DOF, "%s: num_dof=%d out of range", who, p->num_dof);
     HB_REQUIRE((p->obs_ld == 0 || p->obs_ld >= p->frame_stack * p->num_single_obs) &&
                    (p->priv_ld == 0 || p->priv_ld >= p->c_frame_stack * p->num_single_priv),
                "%s: obs_ld / priv_ld (%d / %d) shorter than a row", who, p->obs_ld, p->priv_ld);
@@ -1328,7 +1467,7 @@ int hb_env_action_prologue(const hb_env_params *p, const hb_env_buffers *buf, co
     const int total = p->num_envs * p->num_dof;
     hb_env_noise none = {};
     action_prologue_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
-        actions_in, buf->actions, noise ? *noise : none, total, p->clip_actions, p->action_delay, p->action_noise);
+        actions_in, buf->actions, noise ? *noise : none, total, p->num_dof, p->clip_actions, p->action_delay, p->action_noise);
     HB_CHECK_LAUNCH("action_prologue_kernel");
     return HB_OK;
 }
@@ -1338,10 +1477,10 @@ int hb_env_prologue_torques(const hb_env_params *p, const hb_env_buffers *buf, c
     if (int rc = check_params(p, buf, "hb_env_prologue_torques")) return rc;
     HB_REQUIRE(actions_in && buf->actions && buf->dof_state && buf->p_gains && buf->d_gains && buf->torques,
                "hb_env_prologue_torques: null buffer");
-    const bool vec = hb::aligned16(buf->dof_state) &&
+    const bool vec = (p->num_dof % 2 == 0) && hb::aligned16(buf->dof_state) &&
                      ((reinterpret_cast<uintptr_t>(buf->actions) | reinterpret_cast<uintptr_t>(buf->p_gains) |
                        reinterpret_cast<uintptr_t>(buf->d_gains) | reinterpret_cast<uintptr_t>(buf->torques)) & 7u) == 0;
-    if (!vec) {        // unaligned buffers: the two separate launches
+    if (!vec) {        // unaligned buffers / odd joint count: the two separate launches
         if (int rc = hb_env_action_prologue(p, buf, actions_in, noise, stream)) return rc;
         return hb_env_compute_torques(p, buf, stream);
     }
@@ -1352,7 +1491,8 @@ int hb_env_prologue_torques(const hb_env_params *p, const hb_env_buffers *buf, c
     prologue_pd_kernel<<<(pairs + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
         actions_in, buf->actions, noise ? *noise : none, p->clip_actions, p->action_delay, p->action_noise,
         reinterpret_cast<const float4 *>(buf->dof_state), reinterpret_cast<const float2 *>(buf->p_gains),
-        reinterpret_cast<const float2 *>(buf->d_gains), reinterpret_cast<float2 *>(buf->torques), pairs, p->action_scale, c);
+        reinterpret_cast<const float2 *>(buf->d_gains), reinterpret_cast<float2 *>(buf->torques), pairs, p->num_dof,
+        p->action_scale, c);
     HB_CHECK_LAUNCH("prologue_pd_kernel");
     return HB_OK;
 }
@@ -1386,18 +1526,15 @@ int hb_env_post_physics(const hb_env_params *p, const hb_env_buffers *buf, const
                         float *obs_new, float *priv_new, int32_t stages, void *stream) {
     if (int rc = check_params(p, buf, "hb_env_post_physics")) return rc;
     HB_REQUIRE(noise && obs_new && priv_new, "hb_env_post_physics: null noise/obs pointers");
-    HB_REQUIRE(p->num_single_obs == OBS && p->num_single_priv == PRIV,
-               "hb_env_post_physics: frame sizes %d/%d do not match the hector layout %d/%d", p->num_single_obs,
-               p->num_single_priv, OBS, PRIV);
     HB_REQUIRE(p->num_bodies > 0 && p->num_bodies <= 32, "hb_env_post_physics: num_bodies out of range");
     HB_REQUIRE(p->n_term >= 0 && p->n_term <= HB_MAX_CONTACT_BODIES && p->n_pen >= 0 &&
                    p->n_pen <= HB_MAX_CONTACT_BODIES, "hb_env_post_physics: too many contact bodies");
     HB_REQUIRE(noise->u_reset || noise->rng_counter, "hb_env_post_physics: u_reset or the device generator is required (any env may reset)");
     HB_REQUIRE(buf->scratch_ballots && buf->scratch_sums, "hb_env_post_physics: null scratch buffers");
-    const bool with_noise = p->add_noise && (noise->z_obs || noise->rng_counter);
-    const TileLayout L = make_layout(p->num_bodies, with_noise);
-    const size_t smem = (size_t)L.total * sizeof(float);
-    const int tiles = (p->num_envs + TILE - 1) / TILE;
+    HB_REQUIRE(p->yaw_roll[0] >= 0 && p->yaw_roll[0] + 1 < p->num_dof && p->yaw_roll[1] >= 0 && p->yaw_roll[1] + 1 < p->num_dof,
+               "hb_env_post_physics: yaw_roll joint pairs out of range");
+    HB_REQUIRE((p->reward_scale[HB_R_JOINT_POS] == 0.0f && p->task_kind != HB_TASK_XBOT) || buf->ref_dof_pos,
+               "hb_env_post_physics: ref_dof_pos is required (joint_pos reward / XBot-L privileged frame)");
     // bulk staging needs 16-byte aligned slabs: base pointers aligned and 32-env tiles (128-byte multiples)
     bool bulk = g_use_bulk != 0;
     const void *slabs[] = {buf->root_states, buf->dof_state, buf->contact_forces, buf->actions, buf->last_actions,
@@ -1407,24 +1544,20 @@ int hb_env_post_physics(const hb_env_params *p, const hb_env_buffers *buf, const
     for (const void *s : slabs) all_aligned = all_aligned && hb::aligned16(s);
     HB_REQUIRE(all_aligned, "hb_env_post_physics: state tensors must be 16-byte aligned");
     if (p->add_noise && noise->z_obs && !hb::aligned16(noise->z_obs)) bulk = false;      // caller-supplied draws at an odd offset: plain loads
-    static bool attr_set[2] = {false, false};
-    if (bulk) {
-        if (!attr_set[1]) {
-            HB_CUDA(cudaFuncSetAttribute(post_physics_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-            attr_set[1] = true;
-        }
-        HB_CUDA(hb::launch_pdl(hb::use_pdl(p->num_envs), post_physics_kernel<true>, dim3(tiles), dim3(4 * TILE), smem, (cudaStream_t)stream, *p, *buf,
-                               *noise, obs_new, priv_new, (int)stages));
-    } else {
-        if (!attr_set[0]) {
-            HB_CUDA(cudaFuncSetAttribute(post_physics_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-            attr_set[0] = true;
-        }
-        HB_CUDA(hb::launch_pdl(hb::use_pdl(p->num_envs), post_physics_kernel<false>, dim3(tiles), dim3(4 * TILE), smem, (cudaStream_t)stream, *p, *buf,
-                               *noise, obs_new, priv_new, (int)stages));
-    }
-    HB_CHECK_LAUNCH("post_physics_kernel");
-    return HB_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    // the three registered tasks (envs/__init__.py:46-48)
+    using Hector = Task<10, KIND_HECTOR>;
+    using HectorFull = Task<18, KIND_HECTOR>;
+    using XBot = Task<12, KIND_XBOT>;
+    auto matches = [&](int ndof, int kind, int obs, int priv) {
+        return p->num_dof == ndof && p->task_kind == kind && p->num_single_obs == obs && p->num_single_priv == priv;
+    };
+    if (matches(10, HB_TASK_HECTOR, Hector::OBS, Hector::PRIV)) return launch_post_physics<Hector>(p, buf, noise, obs_new, priv_new, stages, bulk, st);
+    if (matches(18, HB_TASK_HECTOR, HectorFull::OBS, HectorFull::PRIV)) return launch_post_physics<HectorFull>(p, buf, noise, obs_new, priv_new, stages, bulk, st);
+    if (matches(12, HB_TASK_XBOT, XBot::OBS, XBot::PRIV)) return launch_post_physics<XBot>(p, buf, noise, obs_new, priv_new, stages, bulk, st);
+    hb::set_error("hb_env_post_physics: no kernel for num_dof=%d task_kind=%d frames %d/%d (built: hector 10/41/70, hector_full "
+                  "18/65/94, XBot-L 12/47/73)", p->num_dof, p->task_kind, p->num_single_obs, p->num_single_priv);
+    return HB_ERR_UNSUPPORTED;
 }
 
 int hb_env_get_heights(const float *root_states, const float *points_xy, int32_t num_points, const int16_t *height_samples,
@@ -1453,15 +1586,20 @@ int hb_env_stack_observations(const hb_env_params *p, const hb_env_buffers *buf,
     cudaStream_t st = (cudaStream_t)stream;
     const int row_a = p->frame_stack * p->num_single_obs, row_b = p->c_frame_stack * p->num_single_priv;
     const int ld_a = p->obs_ld ? p->obs_ld : row_a, ld_b = p->priv_ld ? p->priv_ld : row_b;
-    const int layout = stack_layout(p);
+    int shape = -1;
+    const int layout = stack_layout(p, &shape);
     const bool fast = hb::aligned16(obs_prev) && hb::aligned16(obs_new) && hb::aligned16(priv_prev) &&
-                      hb::aligned16(priv_new) && layout != 0 && fits_u32(p->num_envs, ld_b);
+                      hb::aligned16(priv_new) && layout != 0 && fits_u32(p->num_envs, ld_a > ld_b ? ld_a : ld_b);
     if (fast) {
         const uint32_t total_a = (uint32_t)p->num_envs * ld_a, total_b = (uint32_t)p->num_envs * ld_b;
         constexpr uint32_t PER = 4 * 256;
         const uint32_t blocks_a = ((total_a + 3u) / 4u + PER - 1) / PER, blocks_b = ((total_b + 3u) / 4u + PER - 1) / PER;
-        auto kernel = layout == 1 ? stack_shift_pair_kernel<ROW_OBS, ROW_OBS, OBS, ROW_PRIV, ROW_PRIV, PRIV, 4>
-                                  : stack_shift_pair_kernel<ROW_OBS, LD_OBS, OBS, ROW_PRIV, LD_PRIV, PRIV, 4>;
+        using PairKernel = void (*)(const float *, float *, uint32_t, uint32_t, const float *, float *, uint32_t);
+#define HB_PAIR(S, PITCH) (PITCH ? (PairKernel)stack_shift_pair_kernel<S::ROW_A, S::LD_A, S::FRAME_A, S::ROW_B, S::LD_B, S::FRAME_B, 4> \
+                                 : (PairKernel)stack_shift_pair_kernel<S::ROW_A, S::ROW_A, S::FRAME_A, S::ROW_B, S::ROW_B, S::FRAME_B, 4>)
+        const bool pitch = layout == 2;
+        PairKernel kernel = shape == 0 ? HB_PAIR(ShapeHector, pitch) : (shape == 1 ? HB_PAIR(ShapeHectorFull, pitch) : HB_PAIR(ShapeXBot, pitch));
+#undef HB_PAIR
         HB_CUDA(hb::launch_pdl(hb::use_pdl(p->num_envs), kernel, dim3(blocks_a + blocks_b), dim3(256), 0,
                                st, obs_prev, obs_new, total_a, blocks_a, priv_prev, priv_new, total_b));
         HB_CHECK_LAUNCH("stack_shift_pair_kernel");
@@ -1480,9 +1618,10 @@ int hb_env_stack_finalize(const hb_env_params *p, const hb_env_buffers *buf, con
                "hb_env_stack_finalize: null scratch/result buffers");
     const int row_b = p->c_frame_stack * p->num_single_priv;
     const int ld_a = p->obs_ld ? p->obs_ld : p->frame_stack * p->num_single_obs, ld_b = p->priv_ld ? p->priv_ld : row_b;
-    const int layout = stack_layout(p);
+    int shape = -1;
+    const int layout = stack_layout(p, &shape);
     const bool fast = hb::aligned16(obs_prev) && hb::aligned16(obs_new) && hb::aligned16(priv_prev) &&
-                      hb::aligned16(priv_new) && layout != 0 && fits_u32(p->num_envs, ld_b);
+                      hb::aligned16(priv_new) && layout != 0 && fits_u32(p->num_envs, ld_a > ld_b ? ld_a : ld_b);
     if (!fast) {        // other layouts: the two separate launches
         if (int rc = hb_env_stack_observations(p, buf, obs_prev, priv_prev, obs_new, priv_new, stream)) return rc;
         return hb_env_reset_finalize(p, buf, obs_new, priv_new, host_count, rng_counter, stream);
@@ -1494,8 +1633,13 @@ int hb_env_stack_finalize(const hb_env_params *p, const hb_env_buffers *buf, con
     int seg = (tiles + hb::sm_count() - 1) / hb::sm_count();
     if (seg < 8) seg = 8;
     const uint32_t fin_blocks = (uint32_t)((tiles + seg - 1) / seg);
-    auto kernel = layout == 1 ? stack_finalize_kernel<ROW_OBS, ROW_OBS, OBS, ROW_PRIV, ROW_PRIV, PRIV, 4>
-                              : stack_finalize_kernel<ROW_OBS, LD_OBS, OBS, ROW_PRIV, LD_PRIV, PRIV, 4>;
+    using FinKernel = void (*)(const float *, float *, uint32_t, uint32_t, const float *, float *, uint32_t, uint32_t, hb_env_params,
+                               hb_env_buffers, int, int, int32_t *, unsigned long long *);
+#define HB_FIN(S, PITCH) (PITCH ? (FinKernel)stack_finalize_kernel<S::ROW_A, S::LD_A, S::FRAME_A, S::ROW_B, S::LD_B, S::FRAME_B, 4> \
+                                : (FinKernel)stack_finalize_kernel<S::ROW_A, S::ROW_A, S::FRAME_A, S::ROW_B, S::ROW_B, S::FRAME_B, 4>)
+    const bool pitch = layout == 2;
+    FinKernel kernel = shape == 0 ? HB_FIN(ShapeHector, pitch) : (shape == 1 ? HB_FIN(ShapeHectorFull, pitch) : HB_FIN(ShapeXBot, pitch));
+#undef HB_FIN
     HB_CUDA(hb::launch_pdl(hb::use_pdl(p->num_envs), kernel,
                            dim3(blocks_a + blocks_b + fin_blocks), dim3(256), 0, (cudaStream_t)stream, obs_prev, obs_new, total_a,
                            blocks_a, priv_prev, priv_new, total_b, blocks_b, *p, *buf, tiles, seg, host_count,

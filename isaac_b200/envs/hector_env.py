@@ -42,6 +42,7 @@ from .._lib import (EnvBuffers, EnvNoise, EnvParams, HB_NUM_REWARDS, HB_STAGE_DE
                     HB_STAGE_PREPARE, HB_STAGE_PUSH, HB_STAGE_RESET_ALL, HB_STAGE_RESET_MASK, HB_STAGE_REWARD, HB_STAGE_STEP,
                     HB_STAGE_TERMINATION, REWARD_NAMES)
 from .hector_config import class_to_dict
+from .tasks import layout_for
 
 _EXTRAS_RING = 256       # >= num_steps_per_env: episode-mean slots handed out through extras["episode"]
 
@@ -78,7 +79,11 @@ def build_env_params(cfg, num_envs: int, num_bodies: int, body_names, dof_names,
     arithmetic first, fp32 at the end, exactly like scalars reach torch kernels in the reference."""
     p = EnvParams()
     p.abi_version = _lib.HB_ABI_VERSION
-    p.num_envs, p.num_dof, p.num_bodies = num_envs, cfg.env.num_actions, num_bodies
+    lay = layout_for(cfg)
+    p.num_envs, p.num_dof, p.num_bodies, p.task_kind = num_envs, cfg.env.num_actions, num_bodies, lay.kind
+    p.yaw_roll[:], p.arm_pair[:], p.ref_left[:], p.ref_right[:] = lay.yaw_roll, lay.arm_pair, lay.ref_left, lay.ref_right
+    scale_1 = cfg.rewards.target_joint_pos_scale          # compute_ref_state: scale_1, scale_2 = 2 * scale_1 (Python doubles)
+    p.ref_scale[0], p.ref_scale[1] = scale_1, 2 * scale_1
     p.num_single_obs, p.frame_stack = cfg.env.num_single_obs, cfg.env.frame_stack
     p.num_single_priv, p.c_frame_stack = cfg.env.single_num_privileged_obs, cfg.env.c_frame_stack
     # rows at a 16-byte pitch: the observation buffers can then be rollout-storage slots and TMA operands
@@ -89,7 +94,7 @@ def build_env_params(cfg, num_envs: int, num_bodies: int, body_names, dof_names,
     term = _find(body_names, cfg.asset.terminate_after_contacts_on)
     pen = _find(body_names, cfg.asset.penalize_contacts_on)
     if len(feet) != 2 or len(knees) != 2:
-        raise ValueError(f"hector layout expects 2 feet and 2 knees, found {feet} / {knees}")
+        raise ValueError(f"the env step expects 2 feet and 2 knees, found {feet} / {knees}")
     if len(term) > _lib.HB_MAX_CONTACT_BODIES or len(pen) > _lib.HB_MAX_CONTACT_BODIES:
         raise ValueError("too many termination / penalised contact bodies")
     p.feet[:], p.knees[:] = feet, knees
@@ -135,12 +140,13 @@ def build_env_params(cfg, num_envs: int, num_bodies: int, body_names, dof_names,
         os_.lin_vel, os_.ang_vel, os_.dof_pos, os_.dof_vel, os_.quat)
     p.noise_level = cfg.noise.noise_level
     ns = cfg.noise.noise_scales
-    nd = p.num_dof
-    vec = np.zeros(p.num_single_obs, dtype=np.float32)          # hector_env.py:145-155 builds it in fp32
-    vec[5:5 + nd] = ns.dof_pos * os_.dof_pos
-    vec[5 + nd:5 + 2 * nd] = ns.dof_vel * os_.dof_vel
-    vec[5 + 3 * nd:5 + 3 * nd + 3] = ns.ang_vel * os_.ang_vel
-    vec[5 + 3 * nd + 3:] = ns.quat * os_.quat
+    vec = np.zeros(p.num_single_obs, dtype=np.float32)          # _get_noise_scale_vec builds it in fp32, with the slices
+    sl = [slice(a, b) for a, b in lay.noise_slices]             # each env file spells out (hector_env.py:145-155, ...)
+    vec[sl[0]] = ns.dof_pos * os_.dof_pos
+    vec[sl[1]] = ns.dof_vel * os_.dof_vel
+    vec[sl[2]] = 0.0
+    vec[sl[3]] = ns.ang_vel * os_.ang_vel
+    vec[sl[4]] = ns.quat * os_.quat
     for k in range(p.num_single_obs):
         p.noise_scale_vec[k] = float(vec[k])
     scales = class_to_dict(cfg.rewards.scales)
@@ -219,8 +225,10 @@ class HectorFreeEnvB200:
             self.env_frictions.copy_(statics.env_frictions), self.body_mass.copy_(statics.body_mass)
             self.env_origins.copy_(statics.env_origins)
         # env state (legged_robot.py:458-515, base_task.py:72-92)
-        self.actions, self.last_actions, self.last_last_actions = z(N, 10), z(N, 10), z(N, 10)
-        self.last_dof_vel, self.last_root_vel, self.torques = z(N, 10), z(N, 6), z(N, 10)
+        nd = self.num_dof
+        self.actions, self.last_actions, self.last_last_actions = z(N, nd), z(N, nd), z(N, nd)
+        self.last_dof_vel, self.last_root_vel, self.torques = z(N, nd), z(N, 6), z(N, nd)
+        self.ref_dof_pos = z(N, nd)                                        # compute_ref_state (hector_env.py:90-111)
         self.commands = z(N, cfg.commands.num_commands)
         self.commands_scale = torch.tensor([self.obs_scales.lin_vel, self.obs_scales.lin_vel, self.obs_scales.ang_vel], **f32)
         self.base_lin_vel, self.base_ang_vel = z(N, 3), z(N, 3)
@@ -300,7 +308,7 @@ class HectorFreeEnvB200:
                 commands=self.commands, base_lin_vel=self.base_lin_vel, base_ang_vel=self.base_ang_vel,
                 projected_gravity=self.projected_gravity, base_euler_xyz=self.base_euler_xyz,
                 feet_air_time=self.feet_air_time, last_contacts=self.last_contacts, feet_height=self.feet_height,
-                last_feet_z=self.last_feet_z, rand_push_force=self.rand_push_force,
+                last_feet_z=self.last_feet_z, ref_dof_pos=self.ref_dof_pos, rand_push_force=self.rand_push_force,
                 rand_push_torque=self.rand_push_torque, episode_sums=self._episode_sums,
                 episode_length_buf=self.episode_length_buf, reset_buf=self.reset_buf, time_out_buf=self.time_out_buf,
                 rew_buf=self.rew_buf, reset_env_ids=self.reset_env_ids, reset_count=self._reset_count,
@@ -710,3 +718,12 @@ class HectorFreeEnvB200:
     def last_rigid_state(self):
         """Never read by the hector task: materialised on demand only."""
         return self.rigid_state.clone()
+
+
+class HectorFullFreeEnvB200(HectorFreeEnvB200):
+    """`hector_full` (envs/custom/hector_w_arm_env.py): the 18-DOF robot with arms; same step, `HectorFullCfg`."""
+
+
+class XBotLFreeEnvB200(HectorFreeEnvB200):
+    """`humanoid_ppo` / XBot-L (envs/custom/humanoid_env.py): 12 DOF, reference-trajectory error in the privileged frame,
+    critic history of 3 frames; same step, `XBotLCfg`."""

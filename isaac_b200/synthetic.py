@@ -31,6 +31,37 @@ TERM_BODIES = (0, 3, 8)
 DEFAULT_DOF_POS = (0.0, 0.0, 0.785, -1.578, 0.785, 0.0, 0.0, 0.785, -1.578, 0.785)
 
 
+@dataclass(frozen=True)
+class TaskDims:
+    """What the generators need to know about a task's robot (default: hector)."""
+    ndof: int = NDOF
+    nbody: int = NBODY
+    feet: tuple = FEET
+    knees: tuple = KNEES
+    term_bodies: tuple = TERM_BODIES
+    default_dof_pos: tuple = DEFAULT_DOF_POS
+    kp: tuple = (40.0, 40.0, 60.0, 120.0, 20.0) * 2
+    kd: tuple = (3.0, 3.0, 5.0, 4.0, 1.0) * 2
+    base_height: float = 0.55
+    nobs: int = 41
+
+
+def task_dims(cfg) -> TaskDims:
+    """Dimensions, body indices and nominal gains of a task config (the way LeggedRobot._create_envs / _init_buffers
+    resolve them by name: legged_robot.py:485-500,627-634,668-681)."""
+    a = cfg.asset
+    find = lambda pats: tuple(i for p in pats for i, nm in enumerate(a.body_names) if p in nm)
+    kp, kd = [0.0] * len(a.dof_names), [0.0] * len(a.dof_names)
+    for i, name in enumerate(a.dof_names):
+        for key in cfg.control.stiffness:
+            if key in name:
+                kp[i], kd[i] = float(cfg.control.stiffness[key]), float(cfg.control.damping[key])
+    return TaskDims(ndof=len(a.dof_names), nbody=len(a.body_names), feet=find([a.foot_name]), knees=find([a.knee_name]),
+                    term_bodies=find(a.terminate_after_contacts_on),
+                    default_dof_pos=tuple(cfg.init_state.default_joint_angles[k] for k in a.dof_names), kp=tuple(kp), kd=tuple(kd),
+                    base_height=float(cfg.init_state.pos[2]), nobs=cfg.env.num_single_obs)
+
+
 @dataclass
 class PhysicsFrame:
     """One refresh of the gym tensors (what PhysX would hand back)."""
@@ -71,12 +102,12 @@ def _quat_mul(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
                         aw * bw - ax * bx - ay * by - az * bz), dim=-1)
 
 
-def make_physics_frame(n: int, gen: torch.Generator, fall_prob: float = 0.005,
-                       ndof: int = NDOF, nbody: int = NBODY) -> PhysicsFrame:
+def make_physics_frame(n: int, gen: torch.Generator, fall_prob: float = 0.005, dims: TaskDims = TaskDims()) -> PhysicsFrame:
+    ndof, nbody, FEET, KNEES, TERM_BODIES = dims.ndof, dims.nbody, tuple(dims.feet), tuple(dims.knees), tuple(dims.term_bodies)
     f32 = dict(dtype=torch.float32, generator=gen)
     root = torch.zeros(n, 13)
     root[:, 0:2] = torch.rand(n, 2, **f32) * 2 - 1
-    root[:, 2] = 0.55 + 0.02 * torch.randn(n, **f32)
+    root[:, 2] = dims.base_height + 0.02 * torch.randn(n, **f32)
     tilt = torch.stack((0.1 * torch.randn(n, **f32), 0.1 * torch.randn(n, **f32),
                         0.3 * torch.randn(n, **f32), torch.ones(n)), dim=-1)
     tilt = tilt / tilt.norm(dim=-1, keepdim=True)
@@ -89,7 +120,7 @@ def make_physics_frame(n: int, gen: torch.Generator, fall_prob: float = 0.005,
     root[:, 7:10] = 0.3 * torch.randn(n, 3, **f32)
     root[:, 10:13] = 0.5 * torch.randn(n, 3, **f32)
 
-    q0 = torch.tensor(DEFAULT_DOF_POS)
+    q0 = torch.tensor(dims.default_dof_pos)
     dof = torch.zeros(n, ndof, 2)
     dof[..., 0] = q0 + 0.2 * torch.randn(n, ndof, **f32)
     dof[..., 1] = 1.5 * torch.randn(n, ndof, **f32)
@@ -121,14 +152,15 @@ def make_physics_frame(n: int, gen: torch.Generator, fall_prob: float = 0.005,
     return PhysicsFrame(root, dof.reshape(n * ndof, 2).contiguous(), contact, rigid)
 
 
-def make_noise_frame(n: int, gen: torch.Generator, ndof: int = NDOF, nobs: int = 41) -> NoiseFrame:
+def make_noise_frame(n: int, gen: torch.Generator, dims: TaskDims = TaskDims()) -> NoiseFrame:
+    ndof, nobs = dims.ndof, dims.nobs
     f32 = dict(dtype=torch.float32, generator=gen)
     return NoiseFrame(actions=torch.randn(n, ndof, **f32),
                       u_delay=torch.rand(n, 1, **f32),
                       z_action=torch.randn(n, ndof, **f32),
                       u_cmd=torch.rand(n, 3, **f32),
                       u_push=torch.rand(n, 5, **f32),
-                      u_reset=torch.rand(n, 15, **f32),
+                      u_reset=torch.rand(n, ndof + 5, **f32),
                       z_obs=torch.randn(n, nobs, **f32))
 
 
@@ -148,13 +180,13 @@ KD_NOMINAL = (3.0, 3.0, 5.0, 4.0, 1.0) * 2            # hector_config.py:95-96
 
 
 def make_env_statics(n: int, gen: torch.Generator, randomize_gains: bool = False,
-                     max_episode_length: int = 2400) -> EnvStatics:
+                     max_episode_length: int = 2400, dims: TaskDims = TaskDims()) -> EnvStatics:
     f32 = dict(dtype=torch.float32, generator=gen)
-    kp = torch.tensor(KP_NOMINAL).repeat(n, 1)
-    kd = torch.tensor(KD_NOMINAL).repeat(n, 1)
+    kp = torch.tensor(dims.kp).repeat(n, 1)
+    kd = torch.tensor(dims.kd).repeat(n, 1)
     if randomize_gains:   # BASELINE.json config 3: kp/kd domain randomisation
-        kp = kp * (0.8 + 0.4 * torch.rand(n, NDOF, **f32))
-        kd = kd * (0.8 + 0.4 * torch.rand(n, NDOF, **f32))
+        kp = kp * (0.8 + 0.4 * torch.rand(n, dims.ndof, **f32))
+        kd = kd * (0.8 + 0.4 * torch.rand(n, dims.ndof, **f32))
     buckets = 0.1 + 0.9 * torch.rand(256, 1, **f32)               # legged_robot.py:256-268
     fric = buckets[torch.randint(0, 256, (n,), generator=gen)]
     mass = 13.0 + (torch.rand(n, 1, **f32) * 6 - 2)               # legged_robot.py:295-301
@@ -174,10 +206,12 @@ class Tape:
 
 
 def make_tape(n: int, steps: int, seed: int = 1234, randomize_gains: bool = False,
-              fall_prob: float = 0.005) -> Tape:
+              fall_prob: float = 0.005, cfg=None) -> Tape:
+    """`cfg`: a task config (isaac_b200.envs: HectorCfg / HectorFullCfg / XBotLCfg); default = hector."""
+    dims = task_dims(cfg) if cfg is not None else TaskDims()
     gen = torch.Generator().manual_seed(seed)
-    tape = Tape(make_env_statics(n, gen, randomize_gains))
+    tape = Tape(make_env_statics(n, gen, randomize_gains, dims=dims))
     for _ in range(steps):
-        tape.physics.append(make_physics_frame(n, gen, fall_prob))
-        tape.noise.append(make_noise_frame(n, gen))
+        tape.physics.append(make_physics_frame(n, gen, fall_prob, dims))
+        tape.noise.append(make_noise_frame(n, gen, dims))
     return tape

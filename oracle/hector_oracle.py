@@ -111,10 +111,14 @@ def scaled_uniform(lo: float, hi: float, u: torch.Tensor) -> torch.Tensor:
 
 
 class OracleHectorEnv:
-    """State + step of the hector env stage, on CPU, for N envs."""
+    """State + step of the env stage, on CPU, for N envs: `hector` (hector_env.py) and, through the task layout of the
+    config (isaac_b200.envs.tasks), `hector_full` (hector_w_arm_env.py) and `humanoid_ppo` / XBot-L (humanoid_env.py) -
+    the three env files differ in joint indices, the arm term of default_joint_pos and the privileged frame."""
 
     def __init__(self, cfg, statics, frame, noise):
+        from isaac_b200.envs.tasks import layout_for
         self.cfg = cfg
+        self.layout = layout_for(cfg)
         n = statics.p_gains.shape[0]
         self.num_envs = n
         self.num_dof = self.num_actions = cfg.env.num_actions
@@ -150,9 +154,11 @@ class OracleHectorEnv:
         self.default_dof_pos = torch.tensor(
             [cfg.init_state.default_joint_angles[k] for k in cfg.asset.dof_names]).unsqueeze(0)
         z = lambda *s: torch.zeros(*s)
-        self.torques, self.actions = z(n, 10), z(n, 10)
-        self.last_actions, self.last_last_actions = z(n, 10), z(n, 10)
-        self.last_dof_vel, self.last_root_vel = z(n, 10), z(n, 6)
+        nd = self.num_dof
+        self.torques, self.actions = z(n, nd), z(n, nd)
+        self.last_actions, self.last_last_actions = z(n, nd), z(n, nd)
+        self.last_dof_vel, self.last_root_vel = z(n, nd), z(n, 6)
+        self.ref_dof_pos = z(n, nd)
         self.commands = z(n, cfg.commands.num_commands)
         self.commands_scale = torch.tensor([os_.lin_vel, os_.lin_vel, os_.ang_vel])
         self.feet_air_time = z(n, 2)
@@ -191,10 +197,12 @@ class OracleHectorEnv:
     def _noise_scale_vec(self):
         ns, os_ = self.cfg.noise.noise_scales, self.obs_scales
         v = torch.zeros(self.cfg.env.num_single_obs)
-        v[5:15] = ns.dof_pos * os_.dof_pos
-        v[15:25] = ns.dof_vel * os_.dof_vel
-        v[35:38] = ns.ang_vel * os_.ang_vel
-        v[38:42] = ns.quat * os_.quat          # slice silently clamps to 38:41 (quirk 6)
+        sl = [slice(a, b) for a, b in self.layout.noise_slices]          # the literal slices of each env file
+        v[sl[0]] = ns.dof_pos * os_.dof_pos
+        v[sl[1]] = ns.dof_vel * os_.dof_vel
+        v[sl[2]] = 0.0                         # previous actions
+        v[sl[3]] = ns.ang_vel * os_.ang_vel
+        v[sl[4]] = ns.quat * os_.quat          # hector: 38:42 silently clamps to 38:41 (quirk 6)
         return v
 
     # ------------------------------------------------------------------ legged_robot.py:339-355
@@ -290,12 +298,14 @@ class OracleHectorEnv:
         if len(ids) == 0:
             return                                            # extras untouched (quirk 4)
         u = noise.u_reset[ids]
-        self.dof_pos[ids] = self.default_dof_pos + scaled_uniform(-0.15, 0.15, u[:, 0:10])
+        nd = self.num_dof
+        self.dof_pos[ids] = self.default_dof_pos + scaled_uniform(-0.15, 0.15, u[:, 0:nd])
         self.dof_vel[ids] = 0.0
         self.root_states[ids] = self.base_init_state
         self.root_states[ids, :3] += self.env_origins[ids]
-        self.root_states[ids, :2] += scaled_uniform(-1.0, 1.0, u[:, 10:12])
-        self.resample_commands(ids, u[:, 12:15])
+        if self.cfg.terrain.mesh_type in ("heightfield", "trimesh"):      # custom_origins (legged_robot.py:381-384,687-688)
+            self.root_states[ids, :2] += scaled_uniform(-1.0, 1.0, u[:, nd:nd + 2])
+        self.resample_commands(ids, u[:, nd + 2:nd + 5])
         for buf in (self.last_last_actions, self.actions, self.last_actions, self.last_dof_vel, self.feet_air_time):
             buf[ids] = 0.0
         self.episode_length_buf[ids] = 0
@@ -329,8 +339,25 @@ class OracleHectorEnv:
     def feet_contact(self):
         return self.contact_forces[:, self.feet, 2] > 5.0
 
+    # ------------------------------------------------------------------ hector_env.py:90-111 / humanoid_env.py:120-142
+    def compute_ref_state(self):
+        s = torch.sin(2 * torch.pi * self.phase())
+        sl, sr = s.clone(), s.clone()
+        self.ref_dof_pos = torch.zeros_like(self.dof_pos)
+        scale_1 = self.cfg.rewards.target_joint_pos_scale
+        scale_2 = 2 * scale_1
+        sl[sl > 0] = 0
+        for j, sc in zip(self.layout.ref_left, (scale_1, scale_2, scale_1)):
+            self.ref_dof_pos[:, j] = sl * sc
+        sr[sr < 0] = 0
+        for j, sc in zip(self.layout.ref_right, (scale_1, scale_2, scale_1)):
+            self.ref_dof_pos[:, j] = sr * sc
+        self.ref_dof_pos[torch.abs(s) < 0.1] = 0
+
     # ------------------------------------------------------------------ hector_env.py:172-254
     def compute_observations(self, noise):
+        from isaac_b200._lib import HB_TASK_XBOT
+        self.compute_ref_state()
         ph = self.phase()
         s = torch.sin(2 * torch.pi * ph).unsqueeze(1)
         c = torch.cos(2 * torch.pi * ph).unsqueeze(1)
@@ -339,12 +366,18 @@ class OracleHectorEnv:
         cmd_in = torch.cat((s, c, self.commands[:, :3] * self.commands_scale), dim=1)
         qd = (self.dof_pos - self.default_dof_pos) * os_.dof_pos
         dq = self.dof_vel * os_.dof_vel
-        priv = torch.cat((cmd_in, qd, dq, self.actions,
-                          self.base_lin_vel * os_.lin_vel, self.base_ang_vel * os_.ang_vel,
-                          self.base_euler_xyz * os_.quat,
-                          self.rigid_state[:, self.feet, :3].flatten(1), self.rigid_state[:, self.feet, 7:10].flatten(1),
-                          self.root_states[:, :3], self.rand_push_force[:, :2], self.rand_push_torque,
-                          self.env_frictions, self.body_mass / 30.0, stance, contact), dim=-1)
+        if self.layout.kind == HB_TASK_XBOT:        # humanoid_env.py:217-234
+            priv = torch.cat((cmd_in, qd, dq, self.actions, self.dof_pos - self.ref_dof_pos,
+                              self.base_lin_vel * os_.lin_vel, self.base_ang_vel * os_.ang_vel,
+                              self.base_euler_xyz * os_.quat, self.rand_push_force[:, :2], self.rand_push_torque,
+                              self.env_frictions, self.body_mass / 30.0, stance, contact), dim=-1)
+        else:
+            priv = torch.cat((cmd_in, qd, dq, self.actions,
+                              self.base_lin_vel * os_.lin_vel, self.base_ang_vel * os_.ang_vel,
+                              self.base_euler_xyz * os_.quat,
+                              self.rigid_state[:, self.feet, :3].flatten(1), self.rigid_state[:, self.feet, 7:10].flatten(1),
+                              self.root_states[:, :3], self.rand_push_force[:, :2], self.rand_push_torque,
+                              self.env_frictions, self.body_mass / 30.0, stance, contact), dim=-1)
         frame = torch.cat((cmd_in, qd, dq, self.actions, self.base_ang_vel * os_.ang_vel,
                            self.base_euler_xyz * os_.quat), dim=-1)
         if self.cfg.noise.add_noise:
@@ -419,12 +452,51 @@ def _r_feet_contact_forces(e):
     return torch.sum((f - e.cfg.rewards.max_contact_force).clip(0, 400), dim=1)
 
 
-@_reward("default_joint_pos")      # :357-367
+@_reward("default_joint_pos")      # :357-367; hector_w_arm_env.py:361-378 adds the arm term
 def _r_default_joint_pos(e):
     d = e.dof_pos - e.default_dof_pos
-    yr = torch.norm(d[:, :2], dim=1) + torch.norm(d[:, 5:7], dim=1)
+    l, r = e.layout.yaw_roll
+    yr = torch.norm(d[:, l:l + 2], dim=1) + torch.norm(d[:, r:r + 2], dim=1)
     yr = torch.clamp(yr - 0.1, 0, 50)
-    return torch.exp(-yr * 100) - 0.01 * torch.norm(d, dim=1)
+    out = torch.exp(-yr * 100)
+    if e.layout.arm_pair[0] >= 0:
+        la, ra = e.layout.arm_pair
+        arm = torch.norm(d[:, la:la + 2], dim=1) + torch.norm(d[:, ra:ra + 2], dim=1)
+        arm = torch.clamp(arm - 0.1, 0, 25)
+        out = out + torch.exp(-arm * 2)
+    return out - 0.01 * torch.norm(d, dim=1)
+
+
+@_reward("joint_pos")              # :264-275 (ref_dof_pos is what the previous compute_observations left)
+def _r_joint_pos(e):
+    nrm = torch.norm(e.dof_pos - e.ref_dof_pos, dim=1)
+    return torch.exp(-2 * nrm) - 0.2 * nrm.clamp(0, 0.5)
+
+
+@_reward("vel_mismatch_exp")       # :395-405
+def _r_vel_mismatch_exp(e):
+    lin = torch.exp(-torch.square(e.base_lin_vel[:, 2]) * 10)
+    ang = torch.exp(-torch.norm(e.base_ang_vel[:, :2], dim=1) * 5.0)
+    return (lin + ang) / 2.0
+
+
+@_reward("track_vel_hard")         # :407-424
+def _r_track_vel_hard(e):
+    lin_err = torch.norm(e.commands[:, :2] - e.base_lin_vel[:, :2], dim=1)
+    ang_err = torch.abs(e.commands[:, 2] - e.base_ang_vel[:, 2])
+    return (torch.exp(-lin_err * 10) + torch.exp(-ang_err * 10)) / 2.0 - 0.2 * (lin_err + ang_err)
+
+
+@_reward("low_speed")              # :468-499
+def _r_low_speed(e):
+    speed, cmd = torch.abs(e.base_lin_vel[:, 0]), torch.abs(e.commands[:, 0])
+    low, high = speed < 0.5 * cmd, speed > 1.2 * cmd
+    r = torch.zeros_like(speed)
+    r[low] = -1.0
+    r[high] = 0.0
+    r[~(low | high)] = 1.2
+    r[torch.sign(e.base_lin_vel[:, 0]) != torch.sign(e.commands[:, 0])] = -2.0
+    return r * (e.commands[:, 0].abs() > 0.1)
 
 
 @_reward("base_height")            # :369-383

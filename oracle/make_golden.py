@@ -67,11 +67,12 @@ ENV_STATE_KEYS = ("torques", "commands", "feet_air_time", "feet_height", "last_c
                   "actions")
 
 
-def record_env_step(rec, env_like, out, root_states, dof_state):
-    """Append one step's observable results (same recorder for reference, oracle and CUDA path)."""
+def record_env_step(rec, env_like, out, root_states, dof_state, frames=(41, 70)):
+    """Append one step's observable results (same recorder for reference, oracle and CUDA path); `frames` = the task's
+    (num_single_obs, single_num_privileged_obs)."""
     obs, priv, rew, reset, extras = out
-    rec.setdefault("obs_frame", []).append(obs[:, -41:].numpy().copy())
-    rec.setdefault("priv_frame", []).append(priv[:, -70:].numpy().copy())
+    rec.setdefault("obs_frame", []).append(obs[:, -frames[0]:].numpy().copy())
+    rec.setdefault("priv_frame", []).append(priv[:, -frames[1]:].numpy().copy())
     rec.setdefault("rew", []).append(rew.numpy().copy())
     rec.setdefault("reset", []).append(reset.numpy().astype(np.uint8))
     rec.setdefault("time_outs", []).append(extras["time_outs"].numpy().astype(np.uint8))
@@ -97,20 +98,43 @@ def delay_cfg(cfg):
     return cfg
 
 
-def _run_reference_env(tape, steps, step_counter0, configure=None):
+def _run_reference_env(tape, steps, step_counter0, configure=None, task="hector"):
     from oracle.ref_harness import ReferenceEnv
-    ref = ReferenceEnv(tape.statics, tape.physics[0], tape.noise[0], configure=configure)
+    ref = ReferenceEnv(tape.statics, tape.physics[0], tape.noise[0], configure=configure, task=task)
     ref.env.common_step_counter = step_counter0
+    frames = (ref.env.cfg.env.num_single_obs, ref.env.cfg.env.single_num_privileged_obs)
     rec = {"obs_init": ref.env.obs_buf.numpy().copy(), "priv_init": ref.env.privileged_obs_buf.numpy().copy()}
     for t in range(1, steps):
         out = ref.step(tape.physics[t], tape.noise[t])
-        record_env_step(rec, ref.env, out, ref.root_states, ref.dof_state)
+        record_env_step(rec, ref.env, out, ref.root_states, ref.dof_state, frames)
     final = {"obs_final": out[0].numpy().copy(), "priv_final": out[1].numpy().copy()}
     arrays = {k: (np.stack(v) if isinstance(v, list) else v) for k, v in rec.items()}
     arrays.update(final)
     arrays["input_checksum"] = tape_checksum(tape)
     arrays["reward_names"] = np.array(sorted(ref.env.episode_sums))
     return arrays
+
+
+# the other two registered tasks (envs/__init__.py:46-48): short rollouts of the reference's own env classes
+TASK_CASE = dict(n=24, steps=14, seed=777, fall_prob=0.03, step_counter0=394)
+TASK_EP0 = [2399, 2400, 798, 799, 1599, 0]
+
+
+def task_golden_tape(task):
+    from isaac_b200.envs.tasks import TASKS
+    c = TASK_CASE
+    tape = make_tape(c["n"], c["steps"], seed=c["seed"], fall_prob=c["fall_prob"], randomize_gains=True, cfg=TASKS[task][1]())
+    tape.statics.episode_length0[:len(TASK_EP0)] = torch.tensor(TASK_EP0)
+    return tape
+
+
+def make_task_goldens():
+    for task in ("hector_full", "humanoid_ppo"):
+        arrays = _run_reference_env(task_golden_tape(task), TASK_CASE["steps"], TASK_CASE["step_counter0"], task=task)
+        path = os.path.join(GOLDEN_DIR, f"env_rollout_{task}_ref.npz")
+        np.savez_compressed(path, **arrays)
+        print(f"wrote {path}: {os.path.getsize(path) / 1e6:.2f} MB, resets={int(arrays['reset'].sum())}, "
+              f"time_outs={int(arrays['time_outs'].sum())}, frames {arrays['obs_frame'].shape[-1]} / {arrays['priv_frame'].shape[-1]}")
 
 
 def make_env_golden():
@@ -229,5 +253,6 @@ def make_ppo_golden():
 if __name__ == "__main__":
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     make_env_golden()
+    make_task_goldens()
     make_ppo_golden()
     make_height_golden()

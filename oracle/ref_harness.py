@@ -157,15 +157,28 @@ EFFORT = [33.5, 33.5, 33.5, 67.0, 33.5] * 2     # robot.urdf:124,166,217,291,320
 class ReferenceEnv:
     """The reference HectorFreeEnv, stepping on supplied physics frames and noise tapes."""
 
-    def __init__(self, statics, first_frame, first_noise, configure=None):
-        """`configure(cfg)`: optional edits of the reference's HectorCfg before the env parses it (e.g. a non-zero
-        `domain_rand.action_delay`)."""
+    # task -> (env module, env class, config module, config class): what envs/__init__.py:46-48 registers
+    TASKS = {"hector": ("hector_env", "HectorFreeEnv", "hector_config", "HectorCfg"),
+             "hector_full": ("hector_w_arm_env", "HectorFullFreeEnv", "hector_w_arm_config", "HectorFullCfg"),
+             "humanoid_ppo": ("humanoid_env", "XBotLFreeEnv", "humanoid_config", "XBotLCfg")}
+
+    def __init__(self, statics, first_frame, first_noise, configure=None, task="hector"):
+        """`configure(cfg)`: optional edits of the reference's config before the env parses it (e.g. a non-zero
+        `domain_rand.action_delay`).  `task`: which of the reference's registered envs to build; the robot description
+        (body / joint names, effort limits) that `_create_envs` would read from the URDF comes from this repo's config of
+        the same task (isaac_b200.envs.tasks)."""
         install_isaacgym_stub()
-        from humanoid.envs.custom.hector_env import HectorFreeEnv
-        from humanoid.envs.custom.hector_config import HectorCfg
+        import importlib
+        env_mod, env_cls, cfg_mod, cfg_cls = self.TASKS[task]
+        he_mod = importlib.import_module(f"humanoid.envs.custom.{env_mod}")
+        HectorFreeEnv = getattr(he_mod, env_cls)
+        HectorCfg = getattr(importlib.import_module(f"humanoid.envs.custom.{cfg_mod}"), cfg_cls)
         import humanoid.envs.base.legged_robot as lr_mod
-        import humanoid.envs.custom.hector_env as he_mod
         self._mods = (lr_mod, he_mod)
+        from isaac_b200.envs.tasks import TASKS as OUR_TASKS
+        from isaac_b200.synthetic import task_dims
+        asset = OUR_TASKS[task][1]().asset
+        dims = task_dims(OUR_TASKS[task][1]())
 
         n = statics.p_gains.shape[0]
         e = HectorFreeEnv.__new__(HectorFreeEnv)
@@ -198,17 +211,18 @@ class ReferenceEnv:
         e.extras = {}
         # --- what create_sim/_create_envs produce (hector_env.py:114-132, legged_robot.py:587-681) ---
         e.up_axis_idx = 2
-        e.num_dof = e.num_dofs = 10
-        e.num_bodies = 11
-        e.dof_names = list(DOF_NAMES)
-        e.feet_indices = torch.tensor([5, 10], dtype=torch.long)
-        e.knee_indices = torch.tensor([4, 9], dtype=torch.long)
-        e.penalised_contact_indices = torch.tensor([0, 3, 8], dtype=torch.long)
-        e.termination_contact_indices = torch.tensor([0, 3, 8], dtype=torch.long)
-        e.torque_limits = torch.tensor(EFFORT) * cfg.safety.torque_limit
+        e.num_dof = e.num_dofs = dims.ndof
+        e.num_bodies = dims.nbody
+        e.dof_names = list(asset.dof_names)
+        find = lambda pats: [i for p in pats for i, nm in enumerate(asset.body_names) if p in nm]      # legged_robot.py:627-634
+        e.feet_indices = torch.tensor(find([cfg.asset.foot_name]), dtype=torch.long)
+        e.knee_indices = torch.tensor(find([cfg.asset.knee_name]), dtype=torch.long)
+        e.penalised_contact_indices = torch.tensor(find(cfg.asset.penalize_contacts_on), dtype=torch.long)
+        e.termination_contact_indices = torch.tensor(find(cfg.asset.terminate_after_contacts_on), dtype=torch.long)
+        e.torque_limits = torch.tensor(asset.dof_effort) * cfg.safety.torque_limit
         e.env_frictions = statics.env_frictions.clone()
         e.body_mass = statics.body_mass.clone()
-        e.custom_origins = True
+        e.custom_origins = cfg.terrain.mesh_type in ("heightfield", "trimesh")      # legged_robot.py:687-688
         e.env_origins = statics.env_origins.clone()
         e.terrain_levels = torch.zeros(n, dtype=torch.long)
         base_init = cfg.init_state.pos + cfg.init_state.rot + cfg.init_state.lin_vel + cfg.init_state.ang_vel
@@ -264,7 +278,8 @@ class ReferenceEnv:
                 harness._ctx = ("u_cmd", env_ids, 0)
                 orig_resample(env_ids)
                 harness._ctx = None
-            else:                               # called from reset_idx (ctx continues at column 12)
+            else:                               # called from reset_idx: the command draws sit behind the dof and xy draws
+                harness._ctx = ("u_reset", env_ids, e.num_dof + 2)      # (also when the xy jitter was not drawn: mesh 'plane')
                 orig_resample(env_ids)
 
         def reset_dofs(env_ids):

@@ -58,8 +58,8 @@ def test_bad_arguments_return_status_not_crash(lib):
     p, b = _lib.EnvParams(), _lib.EnvBuffers()
     p.abi_version, p.num_envs, p.resample_interval, p.num_dof = _lib.HB_ABI_VERSION + 1, 4, 1, 10
     assert lib.hb_env_compute_torques(ctypes.byref(p), ctypes.byref(b), None) == -1 and b"ABI version" in lib.hb_last_error()
-    p.abi_version, p.num_dof = _lib.HB_ABI_VERSION, 12
-    assert lib.hb_env_compute_torques(ctypes.byref(p), ctypes.byref(b), None) == -1 and b"10-DOF" in lib.hb_last_error()
+    p.abi_version, p.num_dof = _lib.HB_ABI_VERSION, _lib.HB_MAX_DOF + 1
+    assert lib.hb_env_compute_torques(ctypes.byref(p), ctypes.byref(b), None) == -1 and b"num_dof" in lib.hb_last_error()
 
 
 def test_only_sm100a_is_embedded(lib):

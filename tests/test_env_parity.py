@@ -22,8 +22,10 @@ EXACT = ("reset", "time_outs", "episode_length_buf", "last_contacts")
 def make_cuda_env(tape, dev, cfg=None, cls=None):
     from isaac_b200.envs.hector_env import HectorFreeEnvB200
     from isaac_b200.physics import SyntheticPhysics
+    from isaac_b200.synthetic import task_dims
     n = tape.statics.p_gains.shape[0]
-    phys = SyntheticPhysics(n, device=dev)
+    dims = task_dims(cfg or HectorCfg())
+    phys = SyntheticPhysics(n, num_dof=dims.ndof, num_bodies=dims.nbody, device=dev)
     phys.load_frame(tape.physics[0].to(dev))
     env = (cls or HectorFreeEnvB200)(cfg or HectorCfg(), sim_device=str(dev), physics=phys, statics=tape.statics,
                                      initial_noise=tape.noise[0].to(dev))
@@ -52,13 +54,14 @@ class _View:
 def run_cuda_case(tape, dev, step_counter0=0, cfg=None, cls=None):
     env, phys = make_cuda_env(tape, dev, cfg=cfg, cls=cls)
     env.common_step_counter = step_counter0
+    frames = (env.cfg.env.num_single_obs, env.cfg.env.single_num_privileged_obs)
     rec = {"obs_init": to_np(env.obs_buf), "priv_init": to_np(env.privileged_obs_buf)}
     ids_per_step, out = [], None
     for t in range(1, len(tape.physics)):
         out = cuda_step(env, phys, tape.physics[t], tape.noise[t], dev)
         cpu_out = tuple(o.cpu() for o in out[:4]) + ({"time_outs": out[4]["time_outs"].cpu(),
                                                      "episode": {k: v.cpu() for k, v in out[4]["episode"].items()}},)
-        mg.record_env_step(rec, _View(env), cpu_out, env.root_states.cpu(), env.dof_state.cpu())
+        mg.record_env_step(rec, _View(env), cpu_out, env.root_states.cpu(), env.dof_state.cpu(), frames)
         n = int(env._reset_count.item())
         ids_per_step.append(env.reset_env_ids[:n].cpu().numpy().copy())
     rec = {k: (np.stack(v) if isinstance(v, list) else v) for k, v in rec.items()}
@@ -116,6 +119,71 @@ def test_env_matches_oracle_ragged(lib, cuda_device, n, bulk):
         assert_equal(f"reset_env_ids@{t}", a, b)
     assert sum(len(i) for i in want_ids) > 0 or n < 8
     lib.hb_set_option(b"env_bulk_staging", 1)
+
+
+@pytest.mark.parametrize("bulk", [1, 0])
+@pytest.mark.parametrize("task", ["hector_full", "humanoid_ppo"])
+def test_other_tasks_match_reference_golden(lib, cuda_device, task, bulk):
+    """the reference's other two registered tasks (envs/__init__.py:46-48) on the same kernels,
+    instantiated for their layouts - hector_full (18 DOF, frames 65 / 94, the arm term of default_joint_pos, 21 active
+    reward terms) and humanoid_ppo / XBot-L (12 DOF, frames 47 / 73, critic history of 3, action delay 0.5, the
+    reference-trajectory error in the privileged frame, the joint_pos reward on last step's reference) - against rollouts
+    of the reference's own env classes (resets, time-outs, command resampling, a push step)."""
+    from isaac_b200.envs import TASKS
+    import isaac_b200.envs as envs
+    assert lib.hb_set_option(b"env_bulk_staging", bulk) == 0
+    cls_name, cfg_cls, _ = TASKS[task]
+    g = dict(np.load(f"{GOLDEN}/env_rollout_{task}_ref.npz"))
+    tape = mg.task_golden_tape(task)
+    np.testing.assert_array_equal(mg.tape_checksum(tape), g["input_checksum"])
+    rec, ids, env, phys = run_cuda_case(tape, cuda_device, mg.TASK_CASE["step_counter0"], cfg=cfg_cls(), cls=getattr(envs, cls_name))
+    compare_records(rec, g)
+    for t, got in enumerate(ids):
+        assert_equal(f"reset_env_ids@{t}", got, np.nonzero(g["reset"][t])[0].astype(np.int32))
+    assert phys.calls["set_root_state"] >= 1 and env.obs_buf.shape[1] == cfg_cls().env.num_observations
+    assert set(env.episode_sums) == set(str(k) for k in g["reward_names"])
+    lib.hb_set_option(b"env_bulk_staging", 1)
+
+
+@pytest.mark.parametrize("task,n", [("hector_full", 257), ("hector_full", 4096), ("humanoid_ppo", 1003), ("humanoid_ppo", 4096)])
+def test_other_tasks_match_oracle(lib, cuda_device, task, n):
+    """... and against the oracle (bit-equal to the reference on these tasks: tests/test_oracle_pinning.py) at ragged and
+    BASELINE shard sizes, with the CUDA-graph replay of the step checked against the eager launches at the end."""
+    from oracle.hector_oracle import OracleHectorEnv
+    from isaac_b200.envs import TASKS
+    import isaac_b200.envs as envs
+    cls_name, cfg_cls, _ = TASKS[task]
+    steps = 8
+    tape = make_tape(n, steps, seed=2000 + n, fall_prob=0.02, randomize_gains=True, cfg=cfg_cls())
+    tape.statics.episode_length0[:5] = torch.tensor([2399, 2400, 798, 799, 1599])
+    ora = OracleHectorEnv(cfg_cls(), tape.statics, tape.physics[0], tape.noise[0])
+    ora.common_step_counter = 396
+    frames = (cfg_cls().env.num_single_obs, cfg_cls().env.single_num_privileged_obs)
+    want = {"obs_init": ora.obs_buf.numpy().copy(), "priv_init": ora.privileged_obs_buf.numpy().copy()}
+    want_ids, out = [], None
+    for t in range(1, steps):
+        out = ora.step(tape.physics[t], tape.noise[t])
+        mg.record_env_step(want, ora, out, ora.root_states, ora.dof_state, frames)
+        want_ids.append(ora.last_reset_ids.numpy().astype(np.int32))
+    want = {k: (np.stack(v) if isinstance(v, list) else v) for k, v in want.items()}
+    want["obs_final"], want["priv_final"] = out[0].numpy(), out[1].numpy()
+    rec, ids, env, _ = run_cuda_case(tape, cuda_device, 396, cfg=cfg_cls(), cls=getattr(envs, cls_name))
+    compare_records(rec, want)
+    for t, (a, b) in enumerate(zip(ids, want_ids)):
+        assert_equal(f"reset_env_ids@{t}", a, b)
+    assert_close("ref_dof_pos", env.ref_dof_pos.cpu().numpy(), ora.ref_dof_pos.numpy())
+    # graph replay == eager on this task's kernels (device generator, same seed)
+    env_g, phys_g = make_cuda_env(tape, cuda_device, cfg=cfg_cls(), cls=getattr(envs, cls_name))
+    env_e, phys_e = make_cuda_env(tape, cuda_device, cfg=cfg_cls(), cls=getattr(envs, cls_name))
+    env_g.seed(4), env_e.seed(4)
+    env_g.enable_cuda_graph()
+    for t in range(1, 4):
+        fr = tape.physics[t].to(cuda_device)
+        phys_g.load_frame(fr), phys_e.load_frame(fr)
+        a = tape.noise[t].actions.to(cuda_device)
+        og, oe = env_g.step(a), env_e.step(a)
+        for x, y, name in zip(og[:4], oe[:4], ("obs", "priv", "rew", "reset")):
+            assert torch.equal(x, y), f"{task}: graph replay vs eager: {name} at step {t}"
 
 
 def test_env_action_delay_matches_reference_golden(lib, cuda_device):

@@ -102,6 +102,70 @@ def test_height_oracle_equal_to_live_reference():
     assert torch.equal(got, want)
 
 
+@pytest.mark.skipif(not HAVE_REFERENCE, reason="/root/reference only exists in the build container")
+def test_task_configs_equal_the_reference_configs():
+    """isaac_b200.envs.tasks restates the three registered tasks' configs (envs/__init__.py:46-48) as deltas over
+    HectorCfg: every hot-path field must equal the reference's own config object, env and PPO side."""
+    import importlib
+    from oracle import ref_harness
+    from isaac_b200.envs import tasks
+    from isaac_b200.envs.hector_config import HectorCfgPPO, class_to_dict
+    ref_harness.install_isaacgym_stub()
+    ours_only = {"body_names", "dof_names", "dof_effort", "num_envs", "horizontal_scale", "vertical_scale", "border_size",
+                 "measured_points_x", "measured_points_y"}
+
+    def diff(a, b, path=""):
+        out = []
+        for k, v in a.items():
+            if k in ours_only:
+                continue
+            if k not in b:
+                out.append(path + k + " (absent in the reference)")
+            elif isinstance(v, dict):
+                out += diff(v, b[k], path + k + ".")
+            elif v != b[k]:
+                out.append(f"{path}{k}: {v} != {b[k]}")
+        return out
+
+    for mod, name, mine in (("hector_config", "HectorCfg", HectorCfg), ("hector_config", "HectorCfgPPO", HectorCfgPPO),
+                            ("hector_w_arm_config", "HectorFullCfg", tasks.HectorFullCfg),
+                            ("hector_w_arm_config", "HectorFullCfgPPO", tasks.HectorFullCfgPPO),
+                            ("humanoid_config", "XBotLCfg", tasks.XBotLCfg), ("humanoid_config", "XBotLCfgPPO", tasks.XBotLCfgPPO)):
+        ref = getattr(importlib.import_module(f"humanoid.envs.custom.{mod}"), name)()
+        assert diff(class_to_dict(mine()), class_to_dict(ref)) == [], name
+
+
+@pytest.mark.skipif(not HAVE_REFERENCE, reason="/root/reference only exists in the build container")
+@pytest.mark.parametrize("task", ["hector_full", "humanoid_ppo"])
+def test_env_oracle_bit_equal_to_live_reference_other_tasks(task):
+    """The other two registered tasks (hector_w_arm_env.py, humanoid_env.py) through the same oracle class: side by side
+    with the unmodified reference env on one tape - 30 steps with falls, time-outs, command resampling and a push step."""
+    from oracle.ref_harness import ReferenceEnv
+    from isaac_b200.envs.tasks import TASKS
+    from isaac_b200.synthetic import make_tape
+    cfg_cls = TASKS[task][1]
+    tape = make_tape(48, 30, seed=123, fall_prob=0.02, cfg=cfg_cls(), randomize_gains=True)
+    tape.statics.episode_length0[:6] = torch.tensor([2398, 2400, 797, 799, 1599, 0])
+    ref = ReferenceEnv(tape.statics, tape.physics[0], tape.noise[0], task=task)
+    ora = OracleHectorEnv(cfg_cls(), tape.statics, tape.physics[0], tape.noise[0])
+    ref.env.common_step_counter = ora.common_step_counter = 390
+    assert torch.equal(ref.env.obs_buf, ora.obs_buf) and torch.equal(ref.env.privileged_obs_buf, ora.privileged_obs_buf)
+    assert torch.equal(ref.env.noise_scale_vec, ora.noise_scale_vec)
+    resets = 0
+    for t in range(1, 30):
+        a = ref.step(tape.physics[t], tape.noise[t])
+        b = ora.step(tape.physics[t], tape.noise[t])
+        for x, y, name in zip(a[:4], b[:4], ("obs", "priv", "rew", "reset")):
+            assert torch.equal(x, y), f"{task}: {name} differs at step {t}"
+        assert torch.equal(ref.env.episode_length_buf, ora.episode_length_buf) and torch.equal(ref.env.torques, ora.torques)
+        for k in ora.episode_sums:
+            assert torch.equal(ref.env.episode_sums[k], ora.episode_sums[k]), (k, t)
+        assert torch.equal(ref.env.ref_dof_pos, ora.ref_dof_pos) and torch.equal(ref.root_states, ora.root_states)
+        resets += int(b[3].sum())
+    assert resets > 10 and set(ora.episode_sums) == set(ref.env.episode_sums)
+    assert a[0].shape[1] == cfg_cls().env.num_observations and a[1].shape[1] == cfg_cls().env.num_privileged_obs
+
+
 def rec_names():
     env_scales = {k: v for k, v in vars(type(HectorCfg().rewards.scales)).items() if not k.startswith("_") and v != 0}
     return list(env_scales)
