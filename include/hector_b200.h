@@ -379,17 +379,17 @@ int hb_gemm_set_pair_mode(int on);
 int hb_ppo_gather_rows(const float *src, int32_t ld_src, float *dst, int32_t ld_dst, const int64_t *perm,
                        int64_t rows, int32_t cols, int32_t ones_col, void *stream);
 
-/* Per-sample record, gathered in minibatch order: actions[10] old_mu[10] old_sigma[10] old_value advantage
- * return old_log_prob (HB_PPO_REC floats). */
-#define HB_PPO_ACT 10
-#define HB_PPO_REC 36
+/* Per-sample record, gathered in minibatch order: actions[A] old_mu[A] old_sigma[A] old_value advantage
+ * return old_log_prob 0 0 = HB_PPO_REC(A) floats; A = num_actions: 10 (hector), 12 (XBot-L), 18 (hector_full). */
+#define HB_PPO_REC(num_actions) (3 * (num_actions) + 6)
 int hb_ppo_pack_samples(const int64_t *perm, int64_t rows, const float *actions, const float *mu, const float *sigma,
                         const float *values, const float *advantages, const float *returns, const float *log_prob,
-                        float *records, void *stream);
+                        int32_t num_actions, float *records, void *stream);
 
 typedef struct hb_ppo_loss_params {
     float clip_param, value_loss_coef, entropy_coef;
     int32_t use_clipped_value_loss;
+    int32_t num_actions;          /* 10 / 12 / 18 */
 } hb_ppo_loss_params;
 /* Loss head and its analytic backward for one minibatch (ppo.py:130-168): Gaussian log-prob, ratio,
  * clipped surrogate, clipped value loss, entropy bonus, KL to the behaviour policy.
@@ -418,8 +418,8 @@ int hb_ppo_head_fused(const float *h3_actor, int32_t ld_ha, const float *h3_crit
 int hb_ppo_draw_normal(float *out, int64_t count, uint64_t *state, void *stream);
 
 /* PPO.act head (ppo.py:91-101, actor_critic.py:111-120): a = mu + sigma*eps, log-prob, copies of mu/sigma. */
-int hb_ppo_act_head(const float *mu, int32_t ld_mu, const float *std, const float *eps, int64_t n, float *actions,
-                    float *log_prob, float *mu_out, float *sigma_out, void *stream);
+int hb_ppo_act_head(const float *mu, int32_t ld_mu, const float *std, const float *eps, int64_t n, int32_t num_actions,
+                    float *actions, float *log_prob, float *mu_out, float *sigma_out, void *stream);
 
 /* Rollout side.  hb_ppo_act_fused: the output layers of both MLPs (hidden width 128) + PPO.act's sampling head
  * (ppo.py:91-101, actor_critic.py:111-120): a = mu + sigma * eps, log-prob, mu, sigma and the value, written to
@@ -428,8 +428,8 @@ int hb_ppo_act_head(const float *mu, int32_t ld_mu, const float *std, const floa
  * hb_ppo_record_step: PPO.process_env_step's record (ppo.py:103-113): rewards_out = rewards + gamma * values *
  * time_outs (time_outs may be NULL), dones_out = dones as uint8. */
 int hb_ppo_act_fused(const float *h3_actor, int32_t ld_ha, const float *h3_critic, int32_t ld_hc, const float *w4_actor,
-                     const float *w4_critic, int32_t ld_w, const float *std, const float *eps, int64_t n, float *actions,
-                     float *log_prob, float *mu_out, float *sigma_out, float *values, void *stream);
+                     const float *w4_critic, int32_t ld_w, const float *std, const float *eps, int64_t n, int32_t num_actions,
+                     float *actions, float *log_prob, float *mu_out, float *sigma_out, float *values, void *stream);
 int hb_ppo_record_step(const float *rewards, const uint8_t *dones, const float *values, const uint8_t *time_outs, float gamma,
                        int64_t n, float *rewards_out, uint8_t *dones_out, void *stream);
 

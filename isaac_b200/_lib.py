@@ -85,7 +85,15 @@ class EnvNoise(C.Structure):
 
 
 HB_EPI_STORE, HB_EPI_BIAS, HB_EPI_BIAS_ELU, HB_EPI_ELU_BWD, HB_EPI_ATOMIC_ADD = range(5)
-HB_PPO_ACT, HB_PPO_REC = 10, 36
+PPO_NUM_ACTIONS = (10, 12, 18)          # instantiations of the PPO head kernels (hector, XBot-L, hector_full)
+
+
+def ppo_rec(num_actions: int) -> int:
+    """HB_PPO_REC(num_actions): floats of one packed sample record."""
+    return 3 * num_actions + 6
+
+
+HB_PPO_ACT, HB_PPO_REC = 10, ppo_rec(10)          # the hector task's values
 
 
 class GemmDesc(C.Structure):
@@ -99,7 +107,8 @@ HB_GEMM_TF32, HB_GEMM_3XTF32 = 0, 1
 
 
 class PpoLossParams(C.Structure):
-    _fields_ = [("clip_param", _f), ("value_loss_coef", _f), ("entropy_coef", _f), ("use_clipped_value_loss", _i)]
+    _fields_ = [("clip_param", _f), ("value_loss_coef", _f), ("entropy_coef", _f), ("use_clipped_value_loss", _i),
+                ("num_actions", _i)]
 
 
 class AdamParams(C.Structure):
@@ -170,16 +179,16 @@ _SIGNATURES = {
     "hb_gemm_tf32_grouped": (C.c_int, [C.POINTER(GemmDesc), C.POINTER(GemmDesc), _fp]),
     "hb_gemm_set_pair_mode": (C.c_int, [C.c_int]),
     "hb_ppo_gather_rows": (C.c_int, [_fp, C.c_int32, _fp, C.c_int32, _fp, C.c_int64, C.c_int32, C.c_int32, _fp]),
-    "hb_ppo_pack_samples": (C.c_int, [_fp, C.c_int64, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp]),
+    "hb_ppo_pack_samples": (C.c_int, [_fp, C.c_int64, _fp, _fp, _fp, _fp, _fp, _fp, _fp, C.c_int32, _fp, _fp]),
     "hb_ppo_loss_head": (C.c_int, [_fp, C.c_int32, _fp, C.c_int32, _fp, _fp, C.c_int64, C.c_int64,
                                    C.POINTER(PpoLossParams), _fp, _fp, _fp, _fp, _fp]),
     "hb_ppo_head_fused": (C.c_int, [_fp, C.c_int32, _fp, C.c_int32, _fp, _fp, C.c_int32, _fp, _fp, C.c_int64, C.c_int64,
                                     C.POINTER(PpoLossParams), _fp, _fp, C.c_int32, _fp, _fp, _fp, _fp, _fp]),
-    "hb_ppo_act_fused": (C.c_int, [_fp, C.c_int32, _fp, C.c_int32, _fp, _fp, C.c_int32, _fp, _fp, C.c_int64, _fp, _fp, _fp, _fp,
-                                   _fp, _fp]),
+    "hb_ppo_act_fused": (C.c_int, [_fp, C.c_int32, _fp, C.c_int32, _fp, _fp, C.c_int32, _fp, _fp, C.c_int64, C.c_int32, _fp, _fp,
+                                   _fp, _fp, _fp, _fp]),
     "hb_ppo_record_step": (C.c_int, [_fp, _fp, _fp, _fp, C.c_float, C.c_int64, _fp, _fp, _fp]),
     "hb_ppo_draw_normal": (C.c_int, [_fp, C.c_int64, _fp, _fp]),
-    "hb_ppo_act_head": (C.c_int, [_fp, C.c_int32, _fp, _fp, C.c_int64, _fp, _fp, _fp, _fp, _fp]),
+    "hb_ppo_act_head": (C.c_int, [_fp, C.c_int32, _fp, _fp, C.c_int64, C.c_int32, _fp, _fp, _fp, _fp, _fp]),
     "hb_optimizer_step": (C.c_int, [_fp, _fp, _fp, _fp, C.c_int64, C.POINTER(AdamParams), _fp, _fp]),
     "hb_runner_bookkeeping": (C.c_int, [_fp, _fp, C.c_int64, _fp, _fp, _fp, _fp, C.c_int32, _fp, _fp]),
     "hb_dp_optimizer_step": (C.c_int, [C.POINTER(DpComm), _fp, _fp, C.c_int64, C.POINTER(AdamParams), _fp, _fp]),

@@ -19,7 +19,7 @@ import torch
 
 from .. import _lib
 from .._lib import (GemmDesc, HB_EPI_ATOMIC_ADD, HB_EPI_BIAS, HB_EPI_BIAS_ELU, HB_EPI_ELU_BWD, HB_GEMM_3XTF32, HB_GEMM_TF32,
-                    HB_PPO_ACT)
+                    PPO_NUM_ACTIONS)
 
 
 def pad4(n: int) -> int:
@@ -31,7 +31,7 @@ class _Layer:
 
     def __init__(self, net, index, fan_in, fan_out, last, offset):
         self.net, self.index, self.fan_in, self.fan_out, self.last, self.offset = net, index, fan_in, fan_out, last, offset
-        self.rows = 16 if last else fan_out          # output layers are padded to the smallest UMMA N
+        self.rows = (fan_out + 15) // 16 * 16 if last else fan_out          # output layers are padded to a multiple of the smallest UMMA N
         self.ld = pad4(fan_in + 1)
 
     @property
@@ -74,8 +74,8 @@ class ActorCritic:
             raise ValueError("precision must be 'tf32' or '3xtf32'")
         if kwargs:
             print("ActorCritic.__init__ got unexpected arguments, which will be ignored: " + str(list(kwargs)))
-        if num_actions != HB_PPO_ACT:
-            raise ValueError(f"the loss-head kernels are built for {HB_PPO_ACT} actions (hector)")
+        if num_actions not in PPO_NUM_ACTIONS:
+            raise ValueError(f"the loss-head kernels are built for {PPO_NUM_ACTIONS} actions (hector, XBot-L, hector_full)")
         if len(actor_hidden_dims) != 3 or len(critic_hidden_dims) != 3:
             raise ValueError("three hidden layers per network (hector_config.py:207-210)")
         self._lib = _lib.load()
@@ -90,7 +90,7 @@ class ActorCritic:
                 self.layers.append(L)
                 off += L.numel
         self._std_offset = off
-        off += 16
+        off += (num_actions + 15) // 16 * 16
         self.flat = torch.zeros(off, device=self.device)
         # the gradient buffer carries 8 spare floats behind the parameters: a data-parallel replica parks its loss
         # statistics there so that ONE all-reduce per optimizer step covers both (isaac_b200/parallel.py)
@@ -189,7 +189,7 @@ class ActorCritic:
                     h = z(m, pad4(L.fan_out + 1))
                     h[:, L.fan_out] = 1.0
                     hs.append(h)
-                ws[net] = {"h": hs, "out": z(m, 16), "d_out": z(m, 16),
+                ws[net] = {"h": hs, "out": z(m, Ls[-1].rows), "d_out": z(m, Ls[-1].rows),
                            "dz": [z(m, L.fan_out) for L in Ls[:-1]]}
             self._ws[m] = ws
         return ws
@@ -200,9 +200,9 @@ class ActorCritic:
     # ------------------------------------------------------------------ forward
     @property
     def fused_head(self) -> bool:
-        """Both last hidden layers are 128 wide: the update path evaluates the output layers inside the loss
-        kernel (hb_ppo_head_fused) instead of as 128-row tensor-core tiles with 10 / 1 useful columns."""
-        return all(L.fan_in == 128 for L in self.layers if L.last)
+        """Both last hidden layers are 128 wide (and at most 15 actions): the update path evaluates the output layers inside
+        the loss kernel (hb_ppo_head_fused) instead of as 128-row tensor-core tiles with 10 / 1 useful columns."""
+        return all(L.fan_in == 128 for L in self.layers if L.last) and self.num_actions <= 15
 
     def _mlp_forward(self, net: str, x: torch.Tensor, ws: dict, hidden_only: bool = False):
         """x: [m, ld] with ld % 4 == 0 (only the first fan_in columns are read).  Returns out [m,16]
@@ -279,7 +279,7 @@ class ActorCritic:
         lib, st = self._lib, torch.cuda.current_stream(self.device).cuda_stream
         Ls = [L for L in self.layers if L.net == net]
         m = x.shape[0]
-        d_cur, ld_cur = ws[net]["d_out"], 16               # gradient w.r.t. the layer's pre-activation output
+        d_cur, ld_cur = ws[net]["d_out"], ws[net]["d_out"].stride(0)               # gradient w.r.t. the layer's pre-activation output
         if from_hidden:
             d_cur, ld_cur = ws[net]["dz"][-1], ws[net]["dz"][-1].stride(0)
         for i in reversed(range(3 if from_hidden else 4)):

@@ -20,8 +20,8 @@ from typing import Optional
 import torch
 
 from .. import _lib
-from .._lib import (AdamParams, HB_OPT_TRACE_MAX, HB_PPO_REC, OPT_ERROR, OPT_LOSS_ACC, OPT_LR, OPT_STATS, OPT_STEP,
-                    OPT_STEPS_IN_UPDATE, OPT_SUMSQ, OPT_TRACE, OPTIM_STATE_DOUBLES, PpoLossParams)
+from .._lib import (AdamParams, HB_OPT_TRACE_MAX, OPT_ERROR, OPT_LOSS_ACC, OPT_LR, OPT_STATS, OPT_STEP,
+                    OPT_STEPS_IN_UPDATE, OPT_SUMSQ, OPT_TRACE, OPTIM_STATE_DOUBLES, PpoLossParams, ppo_rec)
 from .actor_critic import ActorCritic, pad4
 from .rollout_storage import RolloutStorage
 
@@ -221,7 +221,7 @@ class PPO:
         La, Lc = [L for L in ac.layers if L.last]
         _lib.check(self._lib.hb_ppo_act_fused(h3a.data_ptr(), h3a.stride(0), h3c.data_ptr(), h3c.stride(0),
                                               ac._matrix(ac.flat, La).data_ptr(), ac._matrix(ac.flat, Lc).data_ptr(), La.ld,
-                                              ac.std.data_ptr(), eps.data_ptr(), n, e.actions.data_ptr(),
+                                              ac.std.data_ptr(), eps.data_ptr(), n, ac.num_actions, e.actions.data_ptr(),
                                               e.logp.data_ptr(), e.mu.data_ptr(), e.sigma.data_ptr(), e.values_ptr, st),
                    "hb_ppo_act_fused")
 
@@ -277,8 +277,8 @@ class PPO:
         actions = torch.empty(n, ac.num_actions, device=self.device)
         logp = torch.empty(n, device=self.device)
         mu, sigma = torch.empty_like(actions), torch.empty_like(actions)
-        _lib.check(self._lib.hb_ppo_act_head(mu16.data_ptr(), 16, ac.std.data_ptr(), eps.contiguous().data_ptr(), n,
-                                             actions.data_ptr(), logp.data_ptr(), mu.data_ptr(), sigma.data_ptr(), st),
+        _lib.check(self._lib.hb_ppo_act_head(mu16.data_ptr(), mu16.stride(0), ac.std.data_ptr(), eps.contiguous().data_ptr(), n,
+                                             ac.num_actions, actions.data_ptr(), logp.data_ptr(), mu.data_ptr(), sigma.data_ptr(), st),
                    "hb_ppo_act_head")
         t.actions, t.values, t.actions_log_prob = actions, v16[:, :1].clone(), logp
         t.action_mean, t.action_sigma = mu, sigma
@@ -394,7 +394,7 @@ class PPO:
         else:
             mu16 = ac._mlp_forward("actor", xa, ws)
             v16 = ac._mlp_forward("critic", xc, ws)
-            _lib.check(lib.hb_ppo_loss_head(mu16.data_ptr(), 16, v16.data_ptr(), 16, ac.std.data_ptr(), rec.data_ptr(), mb,
+            _lib.check(lib.hb_ppo_loss_head(mu16.data_ptr(), mu16.stride(0), v16.data_ptr(), v16.stride(0), ac.std.data_ptr(), rec.data_ptr(), mb,
                                             mb * self.world_size, C.byref(self._lp), ws["actor"]["d_out"].data_ptr(),
                                             ws["critic"]["d_out"].data_ptr(), ac.grad[ac._std_offset:].data_ptr(),
                                             self._stats.data_ptr(), st), "hb_ppo_loss_head")
@@ -458,24 +458,24 @@ class PPO:
         if getattr(self, "_xa", None) is None or self._xa.shape[0] != used:
             self._xa = torch.zeros(used, ld_a, device=dev)
             self._xc = torch.zeros(used, ld_c, device=dev)
-            self._rec = torch.zeros(used, HB_PPO_REC, device=dev)
+            self._rec = torch.zeros(used, ppo_rec(ac.num_actions), device=dev)
         _lib.check(lib.hb_ppo_gather_rows(s._observations.data_ptr(), s.obs_ld, self._xa.data_ptr(), ld_a,
                                           perm.data_ptr(), used, ac.num_actor_obs, ac.num_actor_obs, st), "gather obs")
         _lib.check(lib.hb_ppo_gather_rows(s._privileged_observations.data_ptr(), s.priv_ld, self._xc.data_ptr(), ld_c,
                                           perm.data_ptr(), used, ac.num_critic_obs, ac.num_critic_obs, st), "gather priv")
         _lib.check(lib.hb_ppo_pack_samples(perm.data_ptr(), used, s.actions.data_ptr(), s.mu.data_ptr(),
                                            s.sigma.data_ptr(), s.values.data_ptr(), s.advantages.data_ptr(),
-                                           s.returns.data_ptr(), s.actions_log_prob.data_ptr(), self._rec.data_ptr(), st),
+                                           s.returns.data_ptr(), s.actions_log_prob.data_ptr(), ac.num_actions, self._rec.data_ptr(), st),
                    "hb_ppo_pack_samples")
         self._mb = mb
-        self._lp = PpoLossParams(self.clip_param, self.value_loss_coef, self.entropy_coef, int(self.use_clipped_value_loss))
+        self._lp = PpoLossParams(self.clip_param, self.value_loss_coef, self.entropy_coef, int(self.use_clipped_value_loss), ac.num_actions)
         return mb
 
     def update(self):
         perm, self.injected_perm = self.injected_perm, None
         mb = self.prepare_minibatches(perm)
         self._mb, self._lp = mb, PpoLossParams(self.clip_param, self.value_loss_coef, self.entropy_coef,
-                                                int(self.use_clipped_value_loss))
+                                                int(self.use_clipped_value_loss), self.actor_critic.num_actions)
         adaptive = int(self.desired_kl is not None and self.schedule == "adaptive")
         self._per_update.zero_()                 # gradient norm scratch, minibatch loss sums, running sums
         self._opt_i64[OPT_STEPS_IN_UPDATE:OPT_STEPS_IN_UPDATE + 2].zero_()     # trace cursor, barrier ticket

@@ -643,7 +643,8 @@ post_physics_kernel(const __grid_constant__ hb_env_params p, const __grid_consta
         }
         if (do_rew || do_last) {
             float t1 = 0.f, t2 = 0.f, t3 = 0.f, ss = 0.f, acc = 0.f, vel = 0.f, tq = 0.f, rr = 0.f;
-            float dy[4] = {0.f, 0.f, 0.f, 0.f}, da[4] = {0.f, 0.f, 0.f, 0.f};
+            float dy0 = 0.f, dy1 = 0.f, dy2 = 0.f, dy3 = 0.f, da0 = 0.f, da1 = 0.f, da2 = 0.f, da3 = 0.f;
+            const int yl = p.yaw_roll[0], yr_ = p.yaw_roll[1], al = p.arm_pair[0], ar_ = p.arm_pair[1];
 #pragma unroll
             for (int j = 0; j < NDOF; ++j) {
                 const float lact = sm[L.last_actions + ln * NDOF + j];
@@ -658,12 +659,11 @@ post_physics_kernel(const __grid_constant__ hb_env_params p, const __grid_consta
                 ss += d * d;
                 // hip yaw / roll of both legs (and, hector_full, the first two arm joints of both arms:
                 // hector_w_arm_env.py:371-378); the index pairs are task constants
-                if (j == p.yaw_roll[0] || j == p.yaw_roll[0] + 1) dy[j - p.yaw_roll[0]] = d;
-                if (j == p.yaw_roll[1] || j == p.yaw_roll[1] + 1) dy[2 + j - p.yaw_roll[1]] = d;
-                if (p.arm_pair[0] >= 0) {
-                    if (j == p.arm_pair[0] || j == p.arm_pair[0] + 1) da[j - p.arm_pair[0]] = d;
-                    if (j == p.arm_pair[1] || j == p.arm_pair[1] + 1) da[2 + j - p.arm_pair[1]] = d;
-                }
+                // (scalars, not arrays: a run-time array index would send them to local memory)
+                dy0 = (j == yl) ? d : dy0, dy1 = (j == yl + 1) ? d : dy1;
+                dy2 = (j == yr_) ? d : dy2, dy3 = (j == yr_ + 1) ? d : dy3;
+                da0 = (j == al) ? d : da0, da1 = (j == al + 1) ? d : da1;
+                da2 = (j == ar_) ? d : da2, da3 = (j == ar_ + 1) ? d : da3;
                 if (joint_pos_on && use_ref && do_rew) {               // joint_pos, hector_env.py:264-275
                     const float e = q[j] - (valid ? b.ref_dof_pos[(size_t)env * NDOF + j] : 0.0f);
                     rr += e * e;
@@ -681,11 +681,11 @@ post_physics_kernel(const __grid_constant__ hb_env_params p, const __grid_consta
             }
             if (do_rew) {
                 terms[HB_R_ACTION_SMOOTHNESS * TILE + lane] = (t1 + t2) + 0.05f * t3;
-                float yr = sqrtf(dy[0] * dy[0] + dy[1] * dy[1]) + sqrtf(dy[2] * dy[2] + dy[3] * dy[3]);
+                float yr = sqrtf(dy0 * dy0 + dy1 * dy1) + sqrtf(dy2 * dy2 + dy3 * dy3);
                 yr = clampf(yr - 0.1f, 0.0f, 50.0f);
                 float djp = expf(-yr * 100.0f);
                 if (p.arm_pair[0] >= 0) {
-                    float ar = sqrtf(da[0] * da[0] + da[1] * da[1]) + sqrtf(da[2] * da[2] + da[3] * da[3]);
+                    float ar = sqrtf(da0 * da0 + da1 * da1) + sqrtf(da2 * da2 + da3 * da3);
                     ar = clampf(ar - 0.1f, 0.0f, 25.0f);
                     djp = djp + expf(-ar * 2.0f);
                 }

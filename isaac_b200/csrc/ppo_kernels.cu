@@ -8,7 +8,17 @@
 
 namespace {
 
-constexpr int NA = HB_PPO_ACT;
+// The kernels below are templated on the number of actions NA: 10 (hector), 12 (XBot-L), 18 (hector_full); a sample's
+// record is 3 NA + 6 floats.  HB_PPO_DISPATCH picks the instantiation.
+#define HB_PPO_DISPATCH(na, CALL)                                                        \
+    switch (na) {                                                                         \
+        case 10: { constexpr int NA = 10; CALL; break; }                                  \
+        case 12: { constexpr int NA = 12; CALL; break; }                                  \
+        case 18: { constexpr int NA = 18; CALL; break; }                                  \
+        default:                                                                          \
+            hb::set_error("num_actions = %d: built for 10 (hector), 12 (XBot-L), 18 (hector_full)", (int)(na)); \
+            return HB_ERR_UNSUPPORTED;                                                    \
+    }
 constexpr float HALF_LOG_2PI = 0.91893853320467274178f;     // log(sqrt(2*pi))
 
 __global__ void __launch_bounds__(256)
@@ -27,6 +37,7 @@ gather_rows_kernel(const float *__restrict__ src, int ld_src, float *__restrict_
     if (ones_col >= 0 && lane == 0) d[ones_col] = 1.0f;
 }
 
+template <int NA>
 __global__ void __launch_bounds__(256)
 pack_samples_kernel(const int64_t *__restrict__ perm, long long rows, const float *__restrict__ actions,
                     const float *__restrict__ mu, const float *__restrict__ sigma, const float *__restrict__ values,
@@ -34,8 +45,9 @@ pack_samples_kernel(const int64_t *__restrict__ perm, long long rows, const floa
                     float *__restrict__ rec) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= rows) return;
+    constexpr int REC = 3 * NA + 6;
     const long long j = perm[i];
-    float *r = rec + i * HB_PPO_REC;
+    float *r = rec + i * REC;
 #pragma unroll
     for (int k = 0; k < NA; ++k) {
         r[k] = actions[j * NA + k];
@@ -58,6 +70,7 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 // ppo.py:130-168 and its gradient w.r.t. mu, value and std.  One thread per sample.
+template <int NA>
 __global__ void __launch_bounds__(256)
 loss_head_kernel(const float *__restrict__ mu, int ld_mu, const float *__restrict__ value, int ld_v,
                  const float *__restrict__ stdp, const float *__restrict__ rec, long long mb, double inv_b,
@@ -75,7 +88,7 @@ loss_head_kernel(const float *__restrict__ mu, int ld_mu, const float *__restric
     for (int j = 0; j < NA; ++j) g_std[j] = 0.0f;
     double st_s = 0.0, st_v = 0.0, st_k = 0.0, st_e = 0.0;
     if (i < mb) {
-        const float *r = rec + i * HB_PPO_REC;
+        const float *r = rec + i * (3 * NA + 6);
         const float *m = mu + i * ld_mu;
         float lp_new = 0.0f, kl = 0.0f, ent = 0.0f, diff[NA];
 #pragma unroll
@@ -160,7 +173,6 @@ loss_head_kernel(const float *__restrict__ mu, int ld_mu, const float *__restric
 // ------------------------------------------------------------------------------------------------------------
 constexpr int HID = 128;                 // last hidden width of both networks (hector_config.py:207-210)
 constexpr int HEAD_THREADS = 128;
-constexpr int HEAD_OUT = NA + 1;         // 10 action means + 1 value
 
 // Sum 16 per-lane values over the warp with 16 shuffles instead of 80: every exchange halves the number of
 // values a lane carries (butterfly over lane bits 4..1), the last one adds lane bit 0.  Value i ends up, fully
@@ -182,13 +194,16 @@ __device__ __forceinline__ float warp_reduce16(float (&v)[16], int lane) {
     return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
 }
 
+template <int NA>
 __global__ void __launch_bounds__(HEAD_THREADS, 3)
 head_fused_kernel(const float *__restrict__ h3a, int ld_ha, const float *__restrict__ h3c, int ld_hc,
                   const float *__restrict__ w4a, const float *__restrict__ w4c, int ld_w, const float *__restrict__ stdp,
                   const float *__restrict__ rec, long long mb, double inv_b, float ent_scale, hb_ppo_loss_params lp,
                   float *__restrict__ dz3a, float *__restrict__ dz3c, int ld_dz, float *__restrict__ g4a,
                   float *__restrict__ g4c, float *__restrict__ d_std, double *__restrict__ stats) {
-    __shared__ __align__(16) float s_w[HEAD_OUT * HID];    // output-layer weights, row j = action j, row 10 = value
+    constexpr int HEAD_OUT = NA + 1;         // NA action means + 1 value: one lane pair each (NA <= 15)
+    static_assert(HEAD_OUT <= 16, "the 16-value butterfly holds at most 15 actions and the value");
+    __shared__ __align__(16) float s_w[HEAD_OUT * HID];    // output-layer weights, row j = action j, row NA = value
     __shared__ float s_g[HEAD_OUT * (HID + 1)];            // CTA-level weight/bias gradient accumulators
     __shared__ float s_dstd[NA];
     __shared__ double s_stat[4];
@@ -228,7 +243,7 @@ head_fused_kernel(const float *__restrict__ h3a, int ld_ha, const float *__restr
         RowIn in;
         in.ha = hb::ld_stream4(reinterpret_cast<const float4 *>(h3a + (size_t)rw * ld_ha) + lane);
         in.hc = hb::ld_stream4(reinterpret_cast<const float4 *>(h3c + (size_t)rw * ld_hc) + lane);
-        const float *r = rec + rw * HB_PPO_REC;
+        const float *r = rec + rw * (3 * NA + 6);
         in.act = own_action ? __ldg(r + o) : 0.0f, in.mu = own_action ? __ldg(r + NA + o) : 0.0f;
         in.sig = own_action ? __ldg(r + 2 * NA + o) : 1.0f;
         in.v_old = __ldg(r + 3 * NA), in.adv = __ldg(r + 3 * NA + 1), in.ret = __ldg(r + 3 * NA + 2), in.lp_old = __ldg(r + 3 * NA + 3);
@@ -357,11 +372,14 @@ head_fused_kernel(const float *__restrict__ h3a, int ld_ha, const float *__restr
 // PPO.process_env_step's reward bootstrap + record (ppo.py:103-113).  One warp per env, same lane mapping as
 // head_fused_kernel (lane = 4 hidden features; output o lands on lanes 2o, 2o+1).
 // ------------------------------------------------------------------------------------------------------------
+template <int NA>
 __global__ void __launch_bounds__(256)
 act_fused_kernel(const float *__restrict__ h3a, int ld_ha, const float *__restrict__ h3c, int ld_hc,
                  const float *__restrict__ w4a, const float *__restrict__ w4c, int ld_w, const float *__restrict__ stdp,
                  const float *__restrict__ eps, long long n, float *__restrict__ actions, float *__restrict__ logp,
                  float *__restrict__ mu_out, float *__restrict__ sigma_out, float *__restrict__ values) {
+    constexpr int HEAD_OUT = NA + 1;
+    static_assert(HEAD_OUT <= 16, "the 16-value butterfly holds at most 15 actions and the value");
     __shared__ __align__(16) float s_w[HEAD_OUT * HID];
     const int lane = threadIdx.x & 31;
     for (int i = threadIdx.x; i < HEAD_OUT * HID; i += blockDim.x) {
@@ -424,6 +442,7 @@ record_step_kernel(const float *__restrict__ rewards, const uint8_t *__restrict_
     dones_out[i] = dones[i] ? 1 : 0;
 }
 
+template <int NA>
 __global__ void __launch_bounds__(256)
 act_head_kernel(const float *__restrict__ mu, int ld_mu, const float *__restrict__ stdp, const float *__restrict__ eps,
                 long long n, float *__restrict__ actions, float *__restrict__ logp, float *__restrict__ mu_out,
@@ -927,11 +946,11 @@ int hb_ppo_gather_rows(const float *src, int32_t ld_src, float *dst, int32_t ld_
 
 int hb_ppo_pack_samples(const int64_t *perm, int64_t rows, const float *actions, const float *mu, const float *sigma,
                         const float *values, const float *advantages, const float *returns, const float *log_prob,
-                        float *records, void *stream) {
+                        int32_t num_actions, float *records, void *stream) {
     HB_REQUIRE(perm && actions && mu && sigma && values && advantages && returns && log_prob && records && rows > 0,
                "hb_ppo_pack_samples: bad arguments");
-    pack_samples_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-        perm, rows, actions, mu, sigma, values, advantages, returns, log_prob, records);
+    HB_PPO_DISPATCH(num_actions, (pack_samples_kernel<NA><<<(unsigned)((rows + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        perm, rows, actions, mu, sigma, values, advantages, returns, log_prob, records)));
     HB_CHECK_LAUNCH("pack_samples_kernel");
     return HB_OK;
 }
@@ -940,10 +959,10 @@ int hb_ppo_loss_head(const float *mu, int32_t ld_mu, const float *value, int32_t
                      const float *records, int64_t mb, int64_t mb_global, const hb_ppo_loss_params *lp, float *d_mu,
                      float *d_value, float *d_std, double *stats, void *stream) {
     HB_REQUIRE(mu && value && std && records && lp && d_mu && d_value && d_std && stats, "hb_ppo_loss_head: null buffer");
-    HB_REQUIRE(mb > 0 && mb_global >= mb && ld_mu >= HB_PPO_ACT && ld_v >= 1, "hb_ppo_loss_head: bad sizes");
-    loss_head_kernel<<<(unsigned)((mb + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+    HB_REQUIRE(mb > 0 && mb_global >= mb && ld_mu >= lp->num_actions && ld_v >= 1, "hb_ppo_loss_head: bad sizes");
+    HB_PPO_DISPATCH(lp->num_actions, (loss_head_kernel<NA><<<(unsigned)((mb + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
         mu, ld_mu, value, ld_v, std, records, mb, 1.0 / (double)mb_global, (float)((double)mb / (double)mb_global), *lp, d_mu,
-        d_value, d_std, stats);
+        d_value, d_std, stats)));
     HB_CHECK_LAUNCH("loss_head_kernel");
     return HB_OK;
 }
@@ -962,9 +981,23 @@ int hb_ppo_head_fused(const float *h3_actor, int32_t ld_ha, const float *h3_crit
                    hb::aligned16(dz3_actor) && hb::aligned16(dz3_critic), "hb_ppo_head_fused: 16-byte aligned buffers");
     long long blocks = (mb + HEAD_THREADS / 32 - 1) / (HEAD_THREADS / 32);
     const long long cap = 3ll * hb::sm_count();          // three resident CTAs per SM (__launch_bounds__)
-    head_fused_kernel<<<(unsigned)(blocks < cap ? blocks : cap), HEAD_THREADS, 0, (cudaStream_t)stream>>>(
-        h3_actor, ld_ha, h3_critic, ld_hc, w4_actor, w4_critic, ld_w, std, records, mb, 1.0 / (double)mb_global,
-        (float)((double)mb / (double)mb_global), *lp, dz3_actor, dz3_critic, ld_dz, g4_actor, g4_critic, d_std, stats);
+    const unsigned grid = (unsigned)(blocks < cap ? blocks : cap);
+    const double inv_b = 1.0 / (double)mb_global;
+    const float ent_scale = (float)((double)mb / (double)mb_global);
+    switch (lp->num_actions) {          // one lane pair per output: at most 15 actions
+        case 10:
+            head_fused_kernel<10><<<grid, HEAD_THREADS, 0, (cudaStream_t)stream>>>(h3_actor, ld_ha, h3_critic, ld_hc, w4_actor, w4_critic, ld_w, std,
+                records, mb, inv_b, ent_scale, *lp, dz3_actor, dz3_critic, ld_dz, g4_actor, g4_critic, d_std, stats);
+            break;
+        case 12:
+            head_fused_kernel<12><<<grid, HEAD_THREADS, 0, (cudaStream_t)stream>>>(h3_actor, ld_ha, h3_critic, ld_hc, w4_actor, w4_critic, ld_w, std,
+                records, mb, inv_b, ent_scale, *lp, dz3_actor, dz3_critic, ld_dz, g4_actor, g4_critic, d_std, stats);
+            break;
+        default:
+            hb::set_error("hb_ppo_head_fused: num_actions = %d (built for 10 and 12; wider heads use hb_gemm_tf32 + hb_ppo_loss_head)",
+                          lp->num_actions);
+            return HB_ERR_UNSUPPORTED;
+    }
     HB_CHECK_LAUNCH("head_fused_kernel");
     return HB_OK;
 }
@@ -978,19 +1011,19 @@ int hb_ppo_draw_normal(float *out, int64_t count, uint64_t *state, void *stream)
     return HB_OK;
 }
 
-int hb_ppo_act_head(const float *mu, int32_t ld_mu, const float *std, const float *eps, int64_t n, float *actions,
-                    float *log_prob, float *mu_out, float *sigma_out, void *stream) {
-    HB_REQUIRE(mu && std && eps && actions && log_prob && mu_out && sigma_out && n > 0 && ld_mu >= HB_PPO_ACT,
+int hb_ppo_act_head(const float *mu, int32_t ld_mu, const float *std, const float *eps, int64_t n, int32_t num_actions,
+                    float *actions, float *log_prob, float *mu_out, float *sigma_out, void *stream) {
+    HB_REQUIRE(mu && std && eps && actions && log_prob && mu_out && sigma_out && n > 0 && ld_mu >= num_actions,
                "hb_ppo_act_head: bad arguments");
-    act_head_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(mu, ld_mu, std, eps, n, actions,
-                                                                                  log_prob, mu_out, sigma_out);
+    HB_PPO_DISPATCH(num_actions, (act_head_kernel<NA><<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        mu, ld_mu, std, eps, n, actions, log_prob, mu_out, sigma_out)));
     HB_CHECK_LAUNCH("act_head_kernel");
     return HB_OK;
 }
 
 int hb_ppo_act_fused(const float *h3_actor, int32_t ld_ha, const float *h3_critic, int32_t ld_hc, const float *w4_actor,
-                     const float *w4_critic, int32_t ld_w, const float *std, const float *eps, int64_t n, float *actions,
-                     float *log_prob, float *mu_out, float *sigma_out, float *values, void *stream) {
+                     const float *w4_critic, int32_t ld_w, const float *std, const float *eps, int64_t n, int32_t num_actions,
+                     float *actions, float *log_prob, float *mu_out, float *sigma_out, float *values, void *stream) {
     HB_REQUIRE(h3_actor && h3_critic && w4_actor && w4_critic && std && eps && actions && log_prob && mu_out && sigma_out &&
                    values && n > 0, "hb_ppo_act_fused: bad arguments");
     HB_REQUIRE(ld_ha >= HID && ld_hc >= HID && ld_w >= HID + 1 && ld_ha % 4 == 0 && ld_hc % 4 == 0 && ld_w % 4 == 0,
@@ -999,8 +1032,20 @@ int hb_ppo_act_fused(const float *h3_actor, int32_t ld_ha, const float *h3_criti
                "hb_ppo_act_fused: 16-byte aligned buffers");
     long long blocks = (n + 7) / 8;
     const long long cap = 8ll * hb::sm_count();
-    act_fused_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, (cudaStream_t)stream>>>(
-        h3_actor, ld_ha, h3_critic, ld_hc, w4_actor, w4_critic, ld_w, std, eps, n, actions, log_prob, mu_out, sigma_out, values);
+    const unsigned grid = (unsigned)(blocks < cap ? blocks : cap);
+    switch (num_actions) {
+        case 10:
+            act_fused_kernel<10><<<grid, 256, 0, (cudaStream_t)stream>>>(h3_actor, ld_ha, h3_critic, ld_hc, w4_actor, w4_critic, ld_w, std, eps, n,
+                                                                          actions, log_prob, mu_out, sigma_out, values);
+            break;
+        case 12:
+            act_fused_kernel<12><<<grid, 256, 0, (cudaStream_t)stream>>>(h3_actor, ld_ha, h3_critic, ld_hc, w4_actor, w4_critic, ld_w, std, eps, n,
+                                                                          actions, log_prob, mu_out, sigma_out, values);
+            break;
+        default:
+            hb::set_error("hb_ppo_act_fused: num_actions = %d (built for 10 and 12)", num_actions);
+            return HB_ERR_UNSUPPORTED;
+    }
     HB_CHECK_LAUNCH("act_fused_kernel");
     return HB_OK;
 }

@@ -50,7 +50,7 @@ def test_bad_arguments_return_status_not_crash(lib):
     assert lib.hb_stack_shift(None, None, None, 4, 615, 41, None) == -1
     assert lib.hb_ppo_head_fused(None, 132, None, 132, None, None, 132, None, None, 8, 8, None, None, None, 128, None, None,
                                  None, None, None) == -1
-    assert lib.hb_ppo_act_fused(None, 132, None, 132, None, None, 132, None, None, 8, None, None, None, None, None, None) == -1
+    assert lib.hb_ppo_act_fused(None, 132, None, 132, None, None, 132, None, None, 8, 10, None, None, None, None, None, None) == -1
     assert lib.hb_ppo_record_step(None, None, None, None, 0.99, 8, None, None, None) == -1
     assert lib.hb_optimizer_step(None, None, None, None, 8, None, None, None) == -1
     d = _lib.GemmDesc()

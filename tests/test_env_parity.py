@@ -171,7 +171,8 @@ def test_other_tasks_match_oracle(lib, cuda_device, task, n):
     compare_records(rec, want)
     for t, (a, b) in enumerate(zip(ids, want_ids)):
         assert_equal(f"reset_env_ids@{t}", a, b)
-    assert_close("ref_dof_pos", env.ref_dof_pos.cpu().numpy(), ora.ref_dof_pos.numpy())
+    if task == "humanoid_ppo":          # (hector_full never reads its reference trajectory: joint_pos has scale 0, the kernel skips it)
+        assert_close("ref_dof_pos", env.ref_dof_pos.cpu().numpy(), ora.ref_dof_pos.numpy())
     # graph replay == eager on this task's kernels (device generator, same seed)
     env_g, phys_g = make_cuda_env(tape, cuda_device, cfg=cfg_cls(), cls=getattr(envs, cls_name))
     env_e, phys_e = make_cuda_env(tape, cuda_device, cfg=cfg_cls(), cls=getattr(envs, cls_name))
@@ -508,7 +509,7 @@ def test_fused_shift_finalize_equals_separate_calls(lib, cuda_device, n, pitched
     weights = (2 ** torch.arange(32, device=dev, dtype=torch.int64))
     ballots = (pad.view(tiles, 32).long() * weights).sum(1)
     ballots = torch.where(ballots >= 2 ** 31, ballots - 2 ** 32, ballots).to(torch.int32)
-    sums = torch.rand(18, dtype=torch.float64, device=dev, generator=g)
+    sums = torch.rand(_lib.HB_NUM_REWARDS, dtype=torch.float64, device=dev, generator=g)
     st = torch.cuda.current_stream(dev).cuda_stream
     results = []
     for fused in (False, True):
@@ -526,7 +527,7 @@ def test_fused_shift_finalize_equals_separate_calls(lib, cuda_device, n, pitched
         new_o, new_p = raw_o[GUARD:GUARD + n * ld_o].view(n, ld_o), raw_p[GUARD:GUARD + n * ld_p].view(n, ld_p)
         new_o.fill_(7.0), new_p.fill_(7.0)
         assert new_o.data_ptr() % 16 == 0 and new_p.data_ptr() % 16 == 0
-        means = torch.zeros(18, device=dev)
+        means = torch.zeros(_lib.HB_NUM_REWARDS, device=dev)
         env._b.episode_means, env._b.episode_means_prev, env._b.episode_ring = means.data_ptr(), None, None
         P, B, hc = env._pp, env._pb, env._host_count.data_ptr()
         if fused:

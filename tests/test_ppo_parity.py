@@ -141,7 +141,7 @@ def test_minibatch_gradients_match_autograd(lib, cuda_device):
     _lib.check(lib.hb_ppo_gather_rows(s._observations.data_ptr(), s.obs_ld, xa.data_ptr(), xa.stride(0), permd.data_ptr(), B, 615, 615, st), "g")
     _lib.check(lib.hb_ppo_gather_rows(s._privileged_observations.data_ptr(), s.priv_ld, xc.data_ptr(), xc.stride(0), permd.data_ptr(), B, 1050, 1050, st), "g")
     _lib.check(lib.hb_ppo_pack_samples(permd.data_ptr(), B, s.actions.data_ptr(), s.mu.data_ptr(), s.sigma.data_ptr(), s.values.data_ptr(),
-                                       s.advantages.data_ptr(), s.returns.data_ptr(), s.actions_log_prob.data_ptr(), rec.data_ptr(), st), "p")
+                                       s.advantages.data_ptr(), s.returns.data_ptr(), s.actions_log_prob.data_ptr(), 10, rec.data_ptr(), st), "p")
     assert torch.equal(xa[:, :615].cpu(), flat["observations"][idx]) and (xa[:, 615] == 1).all()
     ws = ac.workspace(B)
     mu16, v16 = ac._mlp_forward("actor", xa, ws), ac._mlp_forward("critic", xc, ws)
@@ -163,7 +163,7 @@ def test_minibatch_gradients_match_autograd(lib, cuda_device):
     mu16[:, :10] = mu.detach().to(dev)
     v16[:, :1] = v.detach().to(dev)
     stats = torch.zeros(4, dtype=torch.float64, device=dev)
-    lpp = _lib.PpoLossParams(0.2, 1.0, 0.001, 1)
+    lpp = _lib.PpoLossParams(0.2, 1.0, 0.001, 1, 10)
     std_grad = ac.grad[ac._std_offset:]
     _lib.check(lib.hb_ppo_loss_head(mu16.data_ptr(), 16, v16.data_ptr(), 16, ac.std.data_ptr(), rec.data_ptr(), B, B, C.byref(lpp),
                                     ws["actor"]["d_out"].data_ptr(), ws["critic"]["d_out"].data_ptr(),
@@ -253,6 +253,55 @@ def test_update_matches_reference_golden(lib, cuda_device, schedule, precision):
         assert float((got.flatten()[::97] - sample).abs().max()) <= 2.0 * lr_max * steps_taken * 1.01 + 1e-9
 
 
+@pytest.mark.parametrize("task", ["hector_full", "humanoid_ppo"])
+def test_other_tasks_ppo_matches_oracle(lib, cuda_device, task):
+    """The PPO stage at the other two registered tasks' dimensions: hector_full - 975 / 1410
+    observations, 18 actions, actor 768-512-128, critic 768-768-768 (hector_w_arm_config.py:213-214): the critic's last
+    hidden layer is not 128 wide and there are more than 15 actions, so the generic path runs (output layers as GEMMs,
+    hb_ppo_loss_head); XBot-L - 705 / 219 observations, 12 actions, the fused head.  Rollout quantities, GAE and one
+    update against the oracle, same tolerances as the hector golden case in TF32 mode."""
+    from isaac_b200.algo.actor_critic import ActorCritic
+    from isaac_b200.algo.ppo import PPO
+    from isaac_b200.envs import TASKS
+    dev = cuda_device
+    _, cfg_cls, ppo_cls = TASKS[task]
+    ec, pc = cfg_cls().env, ppo_cls().policy
+    nobs, npriv, na = ec.num_observations, ec.num_privileged_obs, ec.num_actions
+    n, t = 64, 12
+    params = init_actor_critic_params(nobs, npriv, na, tuple(pc.actor_hidden_dims), tuple(pc.critic_hidden_dims), seed=4)
+    ac = ActorCritic(nobs, npriv, na, actor_hidden_dims=pc.actor_hidden_dims, critic_hidden_dims=pc.critic_hidden_dims, device=dev)
+    ac.load_state_dict(params)
+    assert ac.fused_head == (task == "humanoid_ppo")
+    cfg = dict(mg.PPO_ALG, schedule="fixed", learning_rate=1e-4, num_learning_epochs=2)
+    alg = PPO(ac, device=dev, **cfg)
+    alg.init_storage(n, t, [nobs], [npriv], [na])
+    ora = OraclePPO(params, n, t, **cfg)
+    g = torch.Generator().manual_seed(8)
+    steps = [(torch.randn(n, nobs, generator=g), torch.randn(n, npriv, generator=g), torch.randn(n, na, generator=g),
+              torch.rand(n, generator=g), torch.rand(n, generator=g) < 0.1, torch.rand(n, generator=g) < 0.05) for _ in range(t)]
+    run_rollout(alg, ora, dev, steps, torch.randn(n, npriv, generator=g))
+    s = alg.storage
+    for k, tol in (("actions", 4e-3), ("values", 4e-3), ("mu", 4e-3), ("actions_log_prob", 4e-3), ("returns", 5e-3), ("advantages", 1e-2)):
+        assert rel_l2(getattr(s, k).cpu(), ora.st[k]) < tol, (k, rel_l2(getattr(s, k).cpu(), ora.st[k]))
+    assert torch.equal(s.dones.cpu(), ora.st["dones"]) and torch.equal(s.observations.cpu(), ora.st["observations"])
+    for k in ("actions", "values", "returns", "advantages", "actions_log_prob", "mu", "sigma", "rewards"):
+        getattr(s, k).copy_(ora.st[k])
+    perm = torch.randperm(n * t, generator=g)
+    alg.injected_perm = perm
+    v_loss, s_loss = alg.update()
+    w_v, w_s = ora.update(perm)
+    assert abs(v_loss - w_v) < 5e-3 * max(1.0, abs(w_v)) and abs(s_loss - w_s) < 5e-3, (v_loss, w_v, s_loss, w_s)
+    sd = alg.actor_critic.state_dict()
+    assert list(sd) == PARAM_ORDER
+    for k in PARAM_ORDER:
+        got, want, init = sd[k].cpu().double(), ora.params[k].detach().double(), params[k].double()
+        err = float((got - want).norm() / (want - init).norm().clamp_min(1e-30))
+        assert err < 0.25, f"{task} {k}: update direction error {err:.3f}"
+    for L in ac.layers:          # packed-gradient padding (rows beyond fan_out, columns beyond the bias) stays zero
+        G = ac._matrix(ac.grad, L)
+        assert (G == 0).all()
+
+
 def test_update_graph_replay_equals_eager(lib, cuda_device):
     """update() replays one captured graph per minibatch index from the second update on (single GPU).  Two PPO
     instances from the same weights and rollouts, one with graphs and one eager: same schedule trace, weights equal up to
@@ -331,13 +380,14 @@ def test_optimizer_step_matches_torch_adam(lib, cuda_device):
         assert_close(f"params after step {step}", p.cpu().numpy(), ref_p.detach().numpy(), rtol=2e-6, atol=2e-7)
 
 
-def test_fused_head_matches_autograd_from_hidden(lib, cuda_device):
+@pytest.mark.parametrize("NA", [10, 12])
+def test_fused_head_matches_autograd_from_hidden(lib, cuda_device, NA):
     """hb_ppo_head_fused / hb_ppo_act_fused in isolation: from given last-hidden activations the output layers run in
     fp32, so everything must agree with torch autograd (fp64 here) to fp32 accuracy - no TF32 in this kernel.
     Reference expressions: actor_critic.py:62,74,111-120 and ppo.py:130-168."""
     from isaac_b200 import _lib
     dev = cuda_device
-    mb, HID, NA = 1000, 128, 10          # not a multiple of the warps per CTA
+    mb, HID = 1000, 128          # not a multiple of the warps per CTA; NA = 10 (hector) / 12 (XBot-L)
     g = torch.Generator().manual_seed(17)
     f64 = torch.float64
     z3a, z3c = torch.randn(mb, HID, generator=g, dtype=f64), torch.randn(mb, HID, generator=g, dtype=f64)
@@ -348,7 +398,7 @@ def test_fused_head_matches_autograd_from_hidden(lib, cuda_device):
     mu_old = actions + 0.4 * torch.randn(mb, NA, generator=g, dtype=f64)
     sig_old = 0.5 + torch.rand(mb, NA, generator=g, dtype=f64)
     v_old, adv, ret = (torch.randn(mb, generator=g, dtype=f64) for _ in range(3))
-    lp_old = -0.5 * ((actions - mu_old) ** 2).sum(-1) - 9.0 + 0.3 * torch.randn(mb, generator=g, dtype=f64)
+    lp_old = -0.5 * ((actions - mu_old) ** 2).sum(-1) - 0.9 * NA + 0.3 * torch.randn(mb, generator=g, dtype=f64)
     # the kernel sees fp32 inputs: round first, then do the reference computation in fp64 on the rounded values
     r32 = lambda x: x.float().double()
     z3a, z3c, w4a, b4a, w4c, b4c, std, actions, mu_old, sig_old, v_old, adv, ret, lp_old = map(
@@ -384,15 +434,15 @@ def test_fused_head_matches_autograd_from_hidden(lib, cuda_device):
         return H.to(dev)
 
     Ha, Hc, Pa, Pc = act_buf(h3a), act_buf(h3c), packed(NA, w4a, b4a), packed(1, w4c, b4c)
-    rec = torch.zeros(mb, 36)
-    rec[:, 0:10], rec[:, 10:20], rec[:, 20:30] = actions.float(), mu_old.float(), sig_old.float()
-    rec[:, 30], rec[:, 31], rec[:, 32], rec[:, 33] = v_old.float(), adv.float(), ret.float(), lp_old.float()
+    rec = torch.zeros(mb, 3 * NA + 6)
+    rec[:, 0:NA], rec[:, NA:2 * NA], rec[:, 2 * NA:3 * NA] = actions.float(), mu_old.float(), sig_old.float()
+    rec[:, 3 * NA], rec[:, 3 * NA + 1], rec[:, 3 * NA + 2], rec[:, 3 * NA + 3] = v_old.float(), adv.float(), ret.float(), lp_old.float()
     rec = rec.to(dev)
     std_d = std.float().to(dev)
     dza, dzc = torch.empty(mb, HID, device=dev), torch.empty(mb, HID, device=dev)
     Ga, Gc = torch.zeros(16, ld, device=dev), torch.zeros(16, ld, device=dev)
     d_std, stats = torch.zeros(16, device=dev), torch.zeros(4, dtype=f64, device=dev)
-    lpp = _lib.PpoLossParams(0.2, 1.0, 0.001, 1)
+    lpp = _lib.PpoLossParams(0.2, 1.0, 0.001, 1, NA)
     st = torch.cuda.current_stream(dev).cuda_stream
     _lib.check(lib.hb_ppo_head_fused(Ha.data_ptr(), ld, Hc.data_ptr(), ld, Pa.data_ptr(), Pc.data_ptr(), ld, std_d.data_ptr(),
                                      rec.data_ptr(), mb, mb, C.byref(lpp), dza.data_ptr(), dzc.data_ptr(), HID, Ga.data_ptr(),
@@ -416,7 +466,7 @@ def test_fused_head_matches_autograd_from_hidden(lib, cuda_device):
     mu_o, sg_o, val = torch.empty(mb, NA, device=dev), torch.empty(mb, NA, device=dev), torch.empty(mb, device=dev)
     eps_d = eps.float().to(dev)
     _lib.check(lib.hb_ppo_act_fused(Ha.data_ptr(), ld, Hc.data_ptr(), ld, Pa.data_ptr(), Pc.data_ptr(), ld, std_d.data_ptr(),
-                                    eps_d.data_ptr(), mb, acts.data_ptr(), logp.data_ptr(), mu_o.data_ptr(),
+                                    eps_d.data_ptr(), mb, NA, acts.data_ptr(), logp.data_ptr(), mu_o.data_ptr(),
                                     sg_o.data_ptr(), val.data_ptr(), st), "hb_ppo_act_fused")
     torch.cuda.synchronize()
     mu_w, v_w = mu.detach(), v.detach()
