@@ -901,9 +901,12 @@ post_physics_kernel(const __grid_constant__ hb_env_params p, const __grid_consta
         }
     } else {
         // ================================ ledger ================================
+        // (terms with scale 0 are not part of the task: the reference has no episode sum for them - their rows stay zero
+        // and are neither read nor written)
         float sums[HB_NUM_REWARDS];
 #pragma unroll
-        for (int k = 0; k < HB_NUM_REWARDS; ++k) sums[k] = valid ? b.episode_sums[(size_t)k * N + env] : 0.0f;
+        for (int k = 0; k < HB_NUM_REWARDS; ++k)
+            sums[k] = (valid && p.reward_scale[k] != 0.0f) ? b.episode_sums[(size_t)k * N + env] : 0.0f;
         if (with_noise && !tape_noise && emit_obs) {
             // the tile's observation noise, drawn by this otherwise idle warp while the other roles are in phase A:
             // 11 Philox calls of 4 normals per env; calls whose four columns all have zero noise scale are skipped
@@ -942,9 +945,11 @@ post_physics_kernel(const __grid_constant__ hb_env_params p, const __grid_consta
         __syncwarp();
 #pragma unroll
         for (int k = 0; k < HB_NUM_REWARDS; ++k) {
-            terms[k * TILE + lane] = reset ? sums[k] : 0.0f;        // episode sums of the envs being reset (:198-201)
-            if (reset) sums[k] = 0.0f;
-            if (valid) b.episode_sums[(size_t)k * N + env] = sums[k];
+            if (p.reward_scale[k] != 0.0f) {
+                terms[k * TILE + lane] = reset ? sums[k] : 0.0f;    // episode sums of the envs being reset (:198-201)
+                if (reset) sums[k] = 0.0f;
+                if (valid) b.episode_sums[(size_t)k * N + env] = sums[k];
+            }
         }
         __syncwarp();
         // ---------------- reset ids + episode means ----------------
@@ -952,7 +957,7 @@ post_physics_kernel(const __grid_constant__ hb_env_params p, const __grid_consta
         // list (like reset_buf.nonzero()) and the count.  The per-term sums of the reset envs
         // (legged_robot.py:198-201) go straight into 18 fp64 accumulators: fp64 addition of these
         // fp32 values is order-independent far below fp32 resolution.
-        if (ballot && lane < HB_NUM_REWARDS) {
+        if (ballot && lane < HB_NUM_REWARDS && p.reward_scale[lane] != 0.0f) {
             float v = 0.0f;
 #pragma unroll 8
             for (int e = 0; e < TILE; ++e) v += terms[lane * TILE + ((e + lane) & 31)];
