@@ -75,7 +75,7 @@ class ClockSampler(threading.Thread):
                 self.sm.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
                 r = get_reasons(h)
                 self.reasons |= {n for bit, n in names.items() if r & bit}
-                self.stop_flag.wait(0.02)
+                self.stop_flag.wait(0.005)
         except Exception as e:          # no NVML: report it instead of inventing clocks
             self.error = repr(e)
 
@@ -386,7 +386,10 @@ def bench_ppo(args, dev, n, world, rank, env=None, phys=None, phys_frames=None):
         b.synchronize()
         roll_ms = a.elapsed_time(b) / T_GAE
     reps = max(2, args.ppo_updates)
+    upd_sampler = ClockSampler(dev.index or 0)          # SM clock under the update's GEMM load (the power cap acts here)
+    upd_sampler.start()
     ms = time_updates(alg, args, dev, n, world, rank, last, reps)
+    update_clocks = upd_sampler.summary()
     samples = n * T_GAE * world
     passes = samples * PPO_CFG["num_learning_epochs"]
     tflops = passes * PPO_FLOP_PER_SAMPLE_PASS / (ms * 1e-3) / 1e12
@@ -413,7 +416,7 @@ def bench_ppo(args, dev, n, world, rank, env=None, phys=None, phys_frames=None):
                                  ("hb_dp_optimizer_step over peer memory" + (" (NVLS multimem)" if alg._peer.multicast else " (peer loads / stores)")
                                   if alg._peer is not None else "NCCL all-reduce of the flat gradient + local optimizer step")),
            "mean_kl": mean_kl, "learning_rate": lr_after,
-           "rollout_act_and_record_ms_per_step": roll_ms}
+           "rollout_act_and_record_ms_per_step": roll_ms, "update_clocks": update_clocks}
     if peak is not None:
         # a whole update is a seconds-scale loop under the power cap: the sustained figure is the denominator
         out.update({"tensor_peak_tflops": peak["sustained_tflops"] * world, "tensor_frac": tflops / (peak["sustained_tflops"] * world),
@@ -588,8 +591,13 @@ def run_b200(args, rank, world):
     lib.hb_set_option(b"coop_launch", 0)
     k_gae_two = gae_chain(stats=gae_stats)               # memset + scan + normalise
     del gsets
+    clocks = sampler.summary()          # the env-stage measurement (the headline value and its roofline) ends here
+    ppo_sampler = ClockSampler(local)   # the GEMM-heavy PPO legs draw more power: their clocks are reported with them
+    ppo_sampler.start()
     ppo = None if args.skip_ppo else bench_ppo(args, dev, n, world, rank, env, phys, phys_frames)
-    clocks = sampler.summary()
+    ppo_clocks = ppo_sampler.summary()
+    if ppo is not None:
+        ppo["clocks"] = ppo_clocks
 
     # ---- e2e: host buffers in, host buffers out, env's own noise ----
     # Pipelined like a host consumer would run it: the two big results of step k (obs, privileged obs: 27 MB at 4096

@@ -269,13 +269,6 @@ int hb_env_stack_observations(const hb_env_params *p, const hb_env_buffers *buf,
                               const float *obs_prev, const float *priv_prev,
                               float *obs_new, float *priv_new, void *stream);
 
-/* The same shift as a background task: `ctas` CTAs (0 = one per SM) walk the copy, so that it can run on a parallel stream /
- * graph branch beside the step's latency-bound chain (PD sub-steps, post-physics) of a small shard without taking the
- * SMs' CTA slots away from it.  Follow with hb_env_reset_finalize(obs_new, priv_new) once both branches have joined (it
- * zeroes the carried frames of the envs just reset). */
-int hb_env_stack_observations_background(const hb_env_params *p, const hb_env_buffers *buf, const float *obs_prev,
-                                         const float *priv_prev, float *obs_new, float *priv_new, int32_t ctas, void *stream);
-
 /* The shard-wide half of reset_idx (envs/base/legged_robot.py:142,162-214; hector_env.py:256-261), after
  * hb_env_post_physics and hb_env_stack_observations of the same step:
  *   reset_env_ids / reset_count = reset_buf.nonzero() in ascending order (+ *host_count, an optional

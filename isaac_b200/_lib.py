@@ -169,7 +169,6 @@ _SIGNATURES = {
     "hb_env_post_physics": (C.c_int, [C.POINTER(EnvParams), C.POINTER(EnvBuffers), C.POINTER(EnvNoise), _fp, _fp,
                                       C.c_int32, _fp]),
     "hb_env_stack_observations": (C.c_int, [C.POINTER(EnvParams), C.POINTER(EnvBuffers), _fp, _fp, _fp, _fp, _fp]),
-    "hb_env_stack_observations_background": (C.c_int, [C.POINTER(EnvParams), C.POINTER(EnvBuffers), _fp, _fp, _fp, _fp, C.c_int32, _fp]),
     "hb_env_reset_finalize": (C.c_int, [C.POINTER(EnvParams), C.POINTER(EnvBuffers), _fp, _fp, _fp, _fp, _fp]),
     "hb_env_stack_finalize": (C.c_int, [C.POINTER(EnvParams), C.POINTER(EnvBuffers), _fp, _fp, _fp, _fp, _fp, _fp, _fp]),
     "hb_env_get_heights": (C.c_int, [_fp, _fp, C.c_int32, _fp, C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_float, _fp,

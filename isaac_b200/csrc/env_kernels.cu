@@ -1116,21 +1116,6 @@ stack_shift_pair_kernel(const float *__restrict__ prev_a, float *__restrict__ ne
         stack_shift_fixed<ROW_B, LD_B, FRAME_B, UNROLL>(prev_b, next_b, total_b, blockIdx.x - blocks_a);
 }
 
-// The same shift as a background task: a fixed number of CTAs (one per SM) walk the block list, so that the copy can run on
-// a parallel graph branch beside the latency-bound PD / post-physics chain of a small shard and leave most of every SM's
-// CTA slots to it (the full-width launch above would fill them all and delay each of the chain's tiny kernels).
-template <int ROW_A, int LD_A, int FRAME_A, int ROW_B, int LD_B, int FRAME_B, int UNROLL>
-__global__ void __launch_bounds__(256)
-stack_shift_pair_background_kernel(const float *__restrict__ prev_a, float *__restrict__ next_a, uint32_t total_a, uint32_t blocks_a,
-                                   const float *__restrict__ prev_b, float *__restrict__ next_b, uint32_t total_b, uint32_t blocks_b) {
-    for (uint32_t blk = blockIdx.x; blk < blocks_a + blocks_b; blk += gridDim.x) {
-        if (blk < blocks_a)
-            stack_shift_fixed<ROW_A, LD_A, FRAME_A, UNROLL>(prev_a, next_a, total_a, blk);
-        else
-            stack_shift_fixed<ROW_B, LD_B, FRAME_B, UNROLL>(prev_b, next_b, total_b, blk - blocks_a);
-    }
-}
-
 template <int ROW, int FRAME, int UNROLL>
 __global__ void __launch_bounds__(256)
 stack_shift_fixed_kernel(const float *__restrict__ prev, float *__restrict__ next, uint32_t total) {
@@ -1627,34 +1612,6 @@ int hb_env_stack_observations(const hb_env_params *p, const hb_env_buffers *buf,
     }
     if (int rc = shift_any(obs_prev, obs_new, nullptr, p->num_envs, row_a, ld_a, p->num_single_obs, st)) return rc;
     return shift_any(priv_prev, priv_new, nullptr, p->num_envs, row_b, ld_b, p->num_single_priv, st);
-}
-
-int hb_env_stack_observations_background(const hb_env_params *p, const hb_env_buffers *buf, const float *obs_prev,
-                                         const float *priv_prev, float *obs_new, float *priv_new, int32_t ctas, void *stream) {
-    if (int rc = check_params(p, buf, "hb_env_stack_observations_background")) return rc;
-    HB_REQUIRE(obs_prev && priv_prev && obs_new && priv_new && obs_prev != obs_new && priv_prev != priv_new,
-               "hb_env_stack_observations_background: null or aliasing buffers");
-    const int ld_a = p->obs_ld ? p->obs_ld : p->frame_stack * p->num_single_obs;
-    const int ld_b = p->priv_ld ? p->priv_ld : p->c_frame_stack * p->num_single_priv;
-    int shape = -1;
-    const int layout = stack_layout(p, &shape);
-    const bool fast = hb::aligned16(obs_prev) && hb::aligned16(obs_new) && hb::aligned16(priv_prev) &&
-                      hb::aligned16(priv_new) && layout != 0 && fits_u32(p->num_envs, ld_a > ld_b ? ld_a : ld_b);
-    if (!fast) return hb_env_stack_observations(p, buf, obs_prev, priv_prev, obs_new, priv_new, stream);
-    const uint32_t total_a = (uint32_t)p->num_envs * ld_a, total_b = (uint32_t)p->num_envs * ld_b;
-    constexpr uint32_t PER = 4 * 256;
-    const uint32_t blocks_a = ((total_a + 3u) / 4u + PER - 1) / PER, blocks_b = ((total_b + 3u) / 4u + PER - 1) / PER;
-    using BgKernel = void (*)(const float *, float *, uint32_t, uint32_t, const float *, float *, uint32_t, uint32_t);
-#define HB_BG(S, PITCH) (PITCH ? (BgKernel)stack_shift_pair_background_kernel<S::ROW_A, S::LD_A, S::FRAME_A, S::ROW_B, S::LD_B, S::FRAME_B, 4> \
-                               : (BgKernel)stack_shift_pair_background_kernel<S::ROW_A, S::ROW_A, S::FRAME_A, S::ROW_B, S::ROW_B, S::FRAME_B, 4>)
-    const bool pitch = layout == 2;
-    BgKernel kernel = shape == 0 ? HB_BG(ShapeHector, pitch) : (shape == 1 ? HB_BG(ShapeHectorFull, pitch) : HB_BG(ShapeXBot, pitch));
-#undef HB_BG
-    uint32_t grid = ctas > 0 ? (uint32_t)ctas : (uint32_t)hb::sm_count();
-    if (grid > blocks_a + blocks_b) grid = blocks_a + blocks_b;
-    kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(obs_prev, obs_new, total_a, blocks_a, priv_prev, priv_new, total_b, blocks_b);
-    HB_CHECK_LAUNCH("stack_shift_pair_background_kernel");
-    return HB_OK;
 }
 
 int hb_env_stack_finalize(const hb_env_params *p, const hb_env_buffers *buf, const float *obs_prev, const float *priv_prev,

@@ -32,7 +32,21 @@ gather_rows_kernel(const float *__restrict__ src, int ld_src, float *__restrict_
     const int vec = cols >> 2;
     const float4 *s4 = reinterpret_cast<const float4 *>(s);
     float4 *d4 = reinterpret_cast<float4 *>(d);
-    for (int i = lane; i < vec; i += 32) hb::st_stream4(d4 + i, hb::ld_stream4(s4 + i));
+    // a row is a few KB at a random place: all of a lane's 16-byte loads are issued before the first store
+    constexpr int INFLIGHT = 9;          // 9 x 32 lanes x 4 floats = rows of up to 1152 floats in one round
+    for (int base = 0; base < vec; base += INFLIGHT * 32) {
+        float4 v[INFLIGHT];
+#pragma unroll
+        for (int u = 0; u < INFLIGHT; ++u) {
+            const int i = base + u * 32 + lane;
+            if (i < vec) v[u] = hb::ld_stream4(s4 + i);
+        }
+#pragma unroll
+        for (int u = 0; u < INFLIGHT; ++u) {
+            const int i = base + u * 32 + lane;
+            if (i < vec) hb::st_stream4(d4 + i, v[u]);
+        }
+    }
     for (int i = (vec << 2) + lane; i < cols; i += 32) d[i] = s[i];
     if (ones_col >= 0 && lane == 0) d[ones_col] = 1.0f;
 }
@@ -172,7 +186,7 @@ loss_head_kernel(const float *__restrict__ mu, int ld_mu, const float *__restric
 // so H3 is read once and mu / value / d_out never touch HBM.
 // ------------------------------------------------------------------------------------------------------------
 constexpr int HID = 128;                 // last hidden width of both networks (hector_config.py:207-210)
-constexpr int HEAD_THREADS = 128;
+constexpr int HEAD_THREADS = 384;       // 12 warps x 168 registers = one CTA per SM: a third of the per-CTA gradient atomics of 3 x 128
 
 // Sum 16 per-lane values over the warp with 16 shuffles instead of 80: every exchange halves the number of
 // values a lane carries (butterfly over lane bits 4..1), the last one adds lane bit 0.  Value i ends up, fully
@@ -195,7 +209,7 @@ __device__ __forceinline__ float warp_reduce16(float (&v)[16], int lane) {
 }
 
 template <int NA>
-__global__ void __launch_bounds__(HEAD_THREADS, 3)
+__global__ void __launch_bounds__(HEAD_THREADS, 1)
 head_fused_kernel(const float *__restrict__ h3a, int ld_ha, const float *__restrict__ h3c, int ld_hc,
                   const float *__restrict__ w4a, const float *__restrict__ w4c, int ld_w, const float *__restrict__ stdp,
                   const float *__restrict__ rec, long long mb, double inv_b, float ent_scale, hb_ppo_loss_params lp,
@@ -980,7 +994,7 @@ int hb_ppo_head_fused(const float *h3_actor, int32_t ld_ha, const float *h3_crit
     HB_REQUIRE(hb::aligned16(h3_actor) && hb::aligned16(h3_critic) && hb::aligned16(w4_actor) && hb::aligned16(w4_critic) &&
                    hb::aligned16(dz3_actor) && hb::aligned16(dz3_critic), "hb_ppo_head_fused: 16-byte aligned buffers");
     long long blocks = (mb + HEAD_THREADS / 32 - 1) / (HEAD_THREADS / 32);
-    const long long cap = 3ll * hb::sm_count();          // three resident CTAs per SM (__launch_bounds__)
+    const long long cap = hb::sm_count();                // one resident CTA per SM (__launch_bounds__)
     const unsigned grid = (unsigned)(blocks < cap ? blocks : cap);
     const double inv_b = 1.0 / (double)mb_global;
     const float ent_scale = (float)((double)mb / (double)mb_global);

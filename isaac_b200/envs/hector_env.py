@@ -282,7 +282,6 @@ class HectorFreeEnvB200:
         self._step_index = 0
         self._pending_event: Optional[torch.cuda.Event] = None
         self._graphs = None
-        self.overlap_shift_max_envs = 8192          # graph replay: frame-stack shift on a parallel branch up to this shard width
         self._injected = initial_noise      # draws consumed by the constructor's reset_idx(all)
         # device generator state {step counter, key}: both in device memory, so captured step graphs follow seed()
         self._rng_state = torch.zeros(2, dtype=torch.int64, device=dev)
@@ -430,7 +429,6 @@ class HectorFreeEnvB200:
         if self.device.type != "cuda":
             raise ValueError("CUDA graphs need a CUDA device")
         self._g_actions = torch.zeros(self.num_envs, self.num_actions, device=self.device)   # staging for odd inputs
-        self._shift_stream = torch.cuda.Stream(self.device)
         self._apply_pending_resets()
         torch.cuda.synchronize(self.device)
         self._g_nz = EnvNoise()
@@ -438,9 +436,7 @@ class HectorFreeEnvB200:
         self._graphs_a, self._graphs = {}, {}
         self._graph_a(self._g_actions)
         self._graph_b(self._own[0], self._own[1]), self._graph_b(self._own[1], self._own[0])
-        # this library's kernels per replayed step: prologue+PD, PD x9, post-physics, then stack+finalize in one launch - or,
-        # for small shards, the background shift on its own branch and the finalisation kernel behind the join
-        self.graph_launches_per_step = self.cfg.control.decimation + (3 if self.num_envs <= self.overlap_shift_max_envs else 2)
+        self.graph_launches_per_step = self.cfg.control.decimation + 2     # this library's kernels per replayed step (prologue+PD, PD x9, post, stack+finalize)
 
     def prepare_action_buffers(self, *tensors) -> None:
         """Capture the step's first graph for each of these action tensors now ([N, num_actions] fp32, contiguous, on
@@ -472,29 +468,9 @@ class HectorFreeEnvB200:
             if len(self._graphs) >= 256:      # buffers keep changing (new storage): drop the stale graphs
                 self._graphs.clear()
             def launches(st):
-                overlap = self.num_envs <= self.overlap_shift_max_envs
-                if overlap:
-                    # small shards: the step is a chain of latency-bound launches - the frame-stack shift (which does not
-                    # depend on this step's physics) runs beside it on a parallel branch, as a background task of one CTA
-                    # per SM; the finalisation kernel behind the join zeroes the carried frames of the envs just reset
-                    main = torch.cuda.current_stream(self.device)          # the capture stream
-                    side = self._shift_stream
-                    side.wait_stream(main)
-                    _lib.check(self._lib.hb_env_stack_observations_background(
-                        self._pp, self._pb, prev[0].data_ptr(), prev[1].data_ptr(), out[0].data_ptr(), out[1].data_ptr(), 0,
-                        side.cuda_stream), "hb_env_stack_observations_background")
                 for _ in range(self.cfg.control.decimation - 1):
                     _lib.check(self._lib.hb_env_compute_torques(self._pp, self._pb, st), "hb_env_compute_torques")
-                if not overlap:
-                    self._launch_post_kernels(HB_STAGE_STEP, C.byref(self._g_nz), prev, out, True, st)
-                    return
-                self._measure_heights(st)
-                _lib.check(self._lib.hb_env_post_physics(self._pp, self._pb, C.byref(self._g_nz), out[0].data_ptr(),
-                                                         out[1].data_ptr(), HB_STAGE_STEP, st), "hb_env_post_physics")
-                main.wait_stream(side)
-                _lib.check(self._lib.hb_env_reset_finalize(self._pp, self._pb, out[0].data_ptr(), out[1].data_ptr(),
-                                                           self._host_count.data_ptr(), self._g_nz.rng_counter, st),
-                           "hb_env_reset_finalize")
+                self._launch_post_kernels(HB_STAGE_STEP, C.byref(self._g_nz), prev, out, True, st)
             gb = _lib.LaunchGraph(self.device).record(launches)
             entry = self._graphs[key] = (gb, prev, out)      # the graph keeps its buffers alive
         return entry[0]
