@@ -514,7 +514,7 @@ int make_map(CUtensorMap *map, const float *base, int rows, int cols, int ld, in
 
 // tensor maps + tile list of one problem
 template <int BN, bool A_MN, bool B_MN, int EPI, bool PAIR>
-int setup_problem(const hb_gemm_desc *d, CUtensorMap *ma, CUtensorMap *mb, GemmArgs *gp, int sharing) {
+int setup_problem(const hb_gemm_desc *d, CUtensorMap *ma, CUtensorMap *mb, GemmArgs *gp, int auto_splits) {
     constexpr int BN_CTA = PAIR ? BN / 2 : BN;
     int rc;
     // A: K-major  -> memory [M, K] ;  MN-major -> memory [K, M]
@@ -526,16 +526,7 @@ int setup_problem(const hb_gemm_desc *d, CUtensorMap *ma, CUtensorMap *mb, GemmA
     g.M = d->M, g.N = d->N, g.K = d->K;
     const int kb_total = (d->K + BK - 1) / BK;
     int splits = d->split_k > 0 ? d->split_k : 1;
-    if (d->split_k == 0 && EPI == EPI_ATOMIC) {
-        // automatic split-K: about two rounds of tiles over the SMs (SM pairs in pair mode); one round when the output
-        // has only a few tiles, where the atomic accumulation of a second round costs more than the shorter k ranges save
-        // (`sharing` problems ride in the launch: each aims at its share of the SMs)
-        const int slots = (PAIR ? hb::sm_count() / 2 : hb::sm_count()) / sharing;
-        const int rows = PAIR ? 2 * BM : BM;
-        const int tiles = ((d->M + rows - 1) / rows) * ((d->N + BN - 1) / BN);
-        splits = (tiles <= 2 ? slots : 2 * slots) / tiles;
-        if (splits < 1) splits = 1;
-    }
+    if (d->split_k == 0 && EPI == EPI_ATOMIC) splits = auto_splits;      // chosen for the launch as a whole (launch())
     if (splits > kb_total) splits = kb_total > 0 ? kb_total : 1;
     g.kb_per_split = (kb_total + splits - 1) / splits;
     splits = g.kb_per_split > 0 ? (kb_total + g.kb_per_split - 1) / g.kb_per_split : 1;
@@ -559,9 +550,28 @@ int launch(const hb_gemm_desc *d, const hb_gemm_desc *d1, cudaStream_t st) {
     }
     alignas(64) CUtensorMap ma, mb, ma1, mb1;
     GemmArgs g, g1;
-    if (int rc = setup_problem<BN, A_MN, B_MN, EPI, PAIR>(d, &ma, &mb, &g, d1 ? 2 : 1)) return rc;
+    // Automatic split-K (weight gradients): k ranges of about equal length over BOTH problems of the launch, about two
+    // rounds of tile jobs over the SMs (SM pairs in pair mode) - one round when the outputs have only a few tiles, where
+    // the atomic accumulation of a second round costs more than the shorter k ranges save.
+    int auto_splits[2] = {1, 1};
+    {
+        const hb_gemm_desc *ds[2] = {d, d1};
+        const int count = d1 ? 2 : 1, slots = PAIR ? hb::sm_count() / 2 : hb::sm_count(), rows = PAIR ? 2 * BM : BM;
+        long long tiles_all = 0, work = 0;
+        for (int i = 0; i < count; ++i) {
+            const long long tiles = (long long)((ds[i]->M + rows - 1) / rows) * ((ds[i]->N + BN - 1) / BN);
+            tiles_all += tiles, work += tiles * ((ds[i]->K + BK - 1) / BK);
+        }
+        const long long jobs = (tiles_all <= 2 * count ? 1 : 2) * slots;
+        const double target = (double)work / (double)jobs;               // k-blocks per tile job
+        for (int i = 0; i < count; ++i) {
+            const int sp = (int)((double)((ds[i]->K + BK - 1) / BK) / (target > 1.0 ? target : 1.0) + 0.5);
+            auto_splits[i] = sp < 1 ? 1 : sp;
+        }
+    }
+    if (int rc = setup_problem<BN, A_MN, B_MN, EPI, PAIR>(d, &ma, &mb, &g, auto_splits[0])) return rc;
     if (d1) {
-        if (int rc = setup_problem<BN, A_MN, B_MN, EPI, PAIR>(d1, &ma1, &mb1, &g1, 2)) return rc;
+        if (int rc = setup_problem<BN, A_MN, B_MN, EPI, PAIR>(d1, &ma1, &mb1, &g1, auto_splits[1])) return rc;
     } else {
         ma1 = ma, mb1 = mb, g1 = g;
         g1.total_tiles = 0;
