@@ -19,6 +19,7 @@ void set_error(const char *fmt, ...) {
 
 int g_use_pdl = -1;
 int g_gemm_pdl = 1;
+int g_gemm_snake = 1;
 int g_coop_launch = 0;
 int g_gae_serial_min_envs = 8192;
 

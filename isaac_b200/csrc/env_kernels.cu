@@ -1437,6 +1437,10 @@ int hb_set_option(const char *name, int value) {
         hb::g_gemm_pdl = value != 0;
         return HB_OK;
     }
+    if (name && !strcmp(name, "gemm_tile_snake")) {
+        hb::g_gemm_snake = value != 0;
+        return HB_OK;
+    }
     if (name && !strcmp(name, "gae_serial_min_envs")) {
         hb::g_gae_serial_min_envs = value;
         return HB_OK;

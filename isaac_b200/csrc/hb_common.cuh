@@ -51,6 +51,7 @@ extern int g_use_pdl;   // "pdl" option: programmatic stream serialization of th
 extern int g_gae_serial_min_envs;   // "gae_serial_min_envs" option: shards at least this wide run GAE one thread per env (default 8192)
 extern int g_coop_launch;   // "coop_launch" option: 1 = kernels with a grid barrier (optimizer step, single-launch GAE) are launched with the
                             // cooperative attribute; 0 (default) = plain launches of a grid that fits the device (see hector_b200.h)
+extern int g_gemm_snake;  // "gemm_tile_snake" option: 1 (default) = rounds of the GEMM tile list are dealt to the CTAs in alternating direction
 extern int g_gemm_pdl;  // "gemm_pdl" option: 1 (default) = GEMM launches overlap their set-up with the previous kernel's tail
 inline bool use_pdl(int num_envs) { (void)num_envs; return g_use_pdl == 1; }
 inline bool use_pdl_small_kernel(int num_envs) { return g_use_pdl == 2 || g_use_pdl < 0 || use_pdl(num_envs); }

@@ -43,6 +43,7 @@ struct GemmArgs {
     int bias_stride;
     const float *H;               // EPI_ELU_BWD: forward activations [M, ldh]
     int ldh;
+    int snake;                    // rounds of the tile list dealt in alternating direction (problem 0's value counts)
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------
@@ -208,6 +209,10 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
     const uint32_t rank = PAIR ? cluster_ctarank() : 0u;     // 0 = leader (issues the MMAs, owns full / acc_empty barriers)
     const int first_tile = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
     const int tile_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    // Round r of the tile list goes to the CTAs in alternating direction (boustrophedon): the CTAs that take the extra
+    // tiles of a partial last round are then the ones whose earlier tiles came from the END of the previous round - in a
+    // grouped launch the second, smaller problem - instead of the ones already holding the longest tiles.
+    auto tile_at = [&](int round) { return round * tile_step + (((round & 1) && g0.snake) ? tile_step - 1 - first_tile : first_tile); };
 
     if (threadIdx.x == 0) {
 #pragma unroll
@@ -251,7 +256,9 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
         // ===================== TMA producer =====================
         if (lane == 0) {
             uint32_t it = 0;
-            for (int t = first_tile; t < all_tiles; t += tile_step) {
+            for (int round = 0; round * tile_step < all_tiles; ++round) {
+                const int t = tile_at(round);
+                if (t >= all_tiles) break;           // (only in the last round)
                 const bool second = t >= g0.total_tiles;
                 const GemmArgs &g = second ? g1 : g0;
                 const CUtensorMap *pmap_a = second ? &map_a1 : &map_a0, *pmap_b = second ? &map_b1 : &map_b0;
@@ -300,7 +307,9 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
         // ===================== MMA issuer =====================
         constexpr uint32_t idesc = make_idesc(BN < 16 ? 16 : BN, A_MN, B_MN, PAIR ? 2 * BM : BM);
         uint32_t it = 0, acc_it = 0;
-        for (int t = first_tile; t < all_tiles && rank == 0; t += tile_step, ++acc_it) {
+        for (int round = 0; round * tile_step < all_tiles && rank == 0; ++round, ++acc_it) {
+            const int t = tile_at(round);
+            if (t >= all_tiles) break;
             const bool second = t >= g0.total_tiles;
             int m0, n0, kb_begin, nkb;
             tile_coords(second ? t - g0.total_tiles : t, second ? g1 : g0, m0, n0, kb_begin, nkb);
@@ -348,7 +357,9 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
         const int c_end = (BN >= 64 || half == 0) ? c_begin + HALF_COLS : 0;
         float *tile = epi_smem + warp * EPI_TILE_FLOATS;
         uint32_t acc_it = 0;
-        for (int t = first_tile; t < all_tiles; t += tile_step, ++acc_it) {
+        for (int round = 0; round * tile_step < all_tiles; ++round, ++acc_it) {
+            const int t = tile_at(round);
+            if (t >= all_tiles) break;
             const bool second = t >= g0.total_tiles;
             const GemmArgs &g = second ? g1 : g0;
             int m0, n0, kb_begin, nkb;
@@ -531,6 +542,7 @@ int setup_problem(const hb_gemm_desc *d, CUtensorMap *ma, CUtensorMap *mb, GemmA
     g.kb_per_split = (kb_total + splits - 1) / splits;
     splits = g.kb_per_split > 0 ? (kb_total + g.kb_per_split - 1) / g.kb_per_split : 1;
     g.D = d->D, g.ldd = d->ldd, g.bias = d->bias, g.bias_stride = d->bias_stride, g.H = d->H, g.ldh = d->ldh;
+    g.snake = hb::g_gemm_snake;
     const int rows_per_tile = PAIR ? 2 * BM : BM;
     const int tiles_m = (d->M + rows_per_tile - 1) / rows_per_tile;
     g.tiles_m = tiles_m, g.tiles_n = (d->N + BN - 1) / BN, g.splits = splits;
