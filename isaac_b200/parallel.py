@@ -7,13 +7,19 @@ One process per GPU (torchrun), `torch.distributed` over NCCL/NVLink for the plu
   * advantage normalisation is global in the reference (rollout_storage.py:136): (sum, sum of squares) of
     the raw advantages, 2 doubles, are all-reduced between the two GAE passes;
   * PPO update: every rank runs minibatches of mb/G local samples; gradients are scaled by 1/(global
-    minibatch) in the loss head, so ONE all-reduce(sum) of the flat packed gradient buffer (1.52 M floats,
-    6.1 MB) per optimizer step gives the global-batch gradient; clip + Adam are then identical on all ranks;
-  * the KL sum that drives the adaptive learning rate (ppo.py:140-148) is all-reduced with the loss
-    statistics (4 doubles), so every rank takes the same branch.
+    minibatch) in the loss head, so the SUM over ranks of the flat packed gradient buffer (1.52 M floats,
+    6.1 MB) is the global-batch gradient.  Default on CUDA (`PeerOptimizer`): the parameter and gradient buffers
+    live in symmetric memory and ONE kernel per rank (hb_dp_optimizer_step) reduces the rank's 1/G slice over
+    NVLink (multimem.ld_reduce where the switch offers multicast, peer loads otherwise), exchanges the norm and
+    the loss / KL sums through peer mailboxes, applies clip + Adam to the slice (optimizer state sharded) and
+    writes the new parameters to every replica.  Fallback (`GradReducer`, also what gloo tests run): one NCCL
+    all-reduce of the gradient with the four loss sums riding behind it, then the local optimizer step;
+  * either way the KL sum that drives the adaptive learning rate (ppo.py:140-148) is global, so every rank takes
+    the same branch, and every rank's generators are re-keyed (`rank_seed`) so that shards draw different noise.
 
 The reducers only need `dist.all_reduce`, so the same code is exercised on CPU tensors with the gloo
-backend in tests/test_parallel.py.
+backend in tests/test_parallel.py; the peer-memory kernel is covered by tests/test_multi_gpu.py (2 and 8 GPUs)
+and, for its arithmetic, tests/test_dp_emulation.py on one GPU.
 """
 from __future__ import annotations
 
