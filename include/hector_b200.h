@@ -225,6 +225,9 @@ void hb_launch_count_reset(void);
  * these kernels - true for stream-ordered use in one process per GPU. */
 /* "gemm_pdl" 1 (default) / 0: hb_gemm_tf32 launches with programmatic stream serialization (a GEMM's set-up - tensor-map
  * prefetch, barriers, TMEM allocation, cluster rendezvous - overlaps the previous kernel's last tiles). */
+/* "gemm_tile_snake" 1 (default) / 0: the rounds of a GEMM launch's tile list are dealt to the persistent CTAs in alternating
+ * direction, so the extra tiles of a partial last round land on the CTAs that hold the shortest earlier tiles (results do
+ * not depend on it; the order of split-K float atomics does). */
 int hb_set_option(const char *name, int value);
 
 /* CUDA graphs of hb_* launch sequences (one env step, one PPO.act) without the framework's graph object:

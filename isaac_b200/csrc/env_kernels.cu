@@ -25,9 +25,18 @@ namespace {
 //                 friction | mass/30 | stance 2 | contact 2]                                        = 4 N + 25
 // The observation frame is [cmd 5 | q-q0 N | dq N | a N | ang 3 | euler 3] = 3 N + 11 for all of them.
 constexpr int KIND_HECTOR = 0, KIND_XBOT = 1;
-template <int NDOF_, int KIND_>
+// OPT_: the optional reward terms (joint_pos with the reference trajectory, vel_mismatch_exp, track_vel_hard, low_speed:
+// zero-scale in hector_config.py) are compiled in.  A config that scales none of them runs the kernel without their code:
+// the four-role kernel is bound by instruction latency and its footprint (6.5 k SASS instructions with them, 5.5 k without).
+template <int NDOF_, int KIND_, bool OPT_ = true>
 struct Task {
     static constexpr int NDOF = NDOF_, KIND = KIND_;
+    static constexpr bool OPT = OPT_ || KIND_ == 1;                 // XBot-L always maintains the reference trajectory
+    // default_joint_pos (hector_env.py:357-367, hector_w_arm_env.py:371-378, humanoid_env.py:368-369): first joint of each
+    // leg's (yaw, roll) pair and, with arms, of each arm's pair - joint-order constants of the three robots
+    static constexpr int YAW_L = 0, YAW_R = NDOF_ / 2;
+    static constexpr bool HAS_ARMS = NDOF_ == 18;
+    static constexpr int ARM_L = HAS_ARMS ? 5 : -1, ARM_R = HAS_ARMS ? NDOF_ / 2 + 5 : -1;
     static constexpr int OBS = 5 + 3 * NDOF + 6;
     static constexpr int B0 = 5 + 3 * NDOF;                         // end of the joint columns
     static constexpr int B1 = KIND == KIND_XBOT ? B0 + NDOF : B0;   // start of the base-velocity columns
@@ -518,17 +527,17 @@ post_physics_kernel(const __grid_constant__ hb_env_params p, const __grid_consta
                 const float ex = cmd[0] - lin.x, ey = cmd[1] - lin.y;
                 terms[HB_R_TRACKING_LIN_VEL * TILE + lane] = expf(-(ex * ex + ey * ey) * p.tracking_sigma);
             }
-            if (p.reward_scale[HB_R_VEL_MISMATCH_EXP] != 0.0f) {      // hector_env.py:395-405
+            if (T::OPT && p.reward_scale[HB_R_VEL_MISMATCH_EXP] != 0.0f) {      // hector_env.py:395-405
                 const float lm = expf(-(lin.z * lin.z) * 10.0f);
                 const float am = expf(-sqrtf(ang.x * ang.x + ang.y * ang.y) * 5.0f);
                 terms[HB_R_VEL_MISMATCH_EXP * TILE + lane] = (lm + am) / 2.0f;
             }
-            if (p.reward_scale[HB_R_TRACK_VEL_HARD] != 0.0f) {        // :407-424
+            if (T::OPT && p.reward_scale[HB_R_TRACK_VEL_HARD] != 0.0f) {        // :407-424
                 const float ex = cmd[0] - lin.x, ey = cmd[1] - lin.y;
                 const float le = sqrtf(ex * ex + ey * ey), ae = fabsf(cmd[2] - ang.z);
                 terms[HB_R_TRACK_VEL_HARD * TILE + lane] = (expf(-le * 10.0f) + expf(-ae * 10.0f)) / 2.0f - 0.2f * (le + ae);
             }
-            if (p.reward_scale[HB_R_LOW_SPEED] != 0.0f) {             // :468-499
+            if (T::OPT && p.reward_scale[HB_R_LOW_SPEED] != 0.0f) {             // :468-499
                 const float sp_abs = fabsf(lin.x), cm_abs = fabsf(cmd[0]);
                 const bool too_low = sp_abs < 0.5f * cm_abs, too_high = sp_abs > 1.2f * cm_abs;
                 const float sgn_v = (lin.x > 0.0f) ? 1.0f : ((lin.x < 0.0f) ? -1.0f : 0.0f);
@@ -630,8 +639,8 @@ post_physics_kernel(const __grid_constant__ hb_env_params p, const __grid_consta
         // (and, on a step, rolled forward: legged_robot.py:146-148) joint by joint before it.
         // The reference trajectory (compute_ref_state, hector_env.py:90-111 / humanoid_env.py:120-142) is STATE: it is
         // refreshed inside compute_observations, so the joint_pos reward of a step sees the one the previous step left.
-        const bool joint_pos_on = p.reward_scale[HB_R_JOINT_POS] != 0.0f;
-        const bool use_ref = (KIND == KIND_XBOT || joint_pos_on) && b.ref_dof_pos != nullptr;
+        const bool joint_pos_on = T::OPT && p.reward_scale[HB_R_JOINT_POS] != 0.0f;
+        const bool use_ref = T::OPT && (KIND == KIND_XBOT || joint_pos_on) && b.ref_dof_pos != nullptr;
         long long ep_len = 0;
         if (use_ref && valid) ep_len = b.episode_length_buf[env] + (do_prepare ? 1 : 0);
         float q[NDOF], qd[NDOF], act[NDOF];
@@ -644,7 +653,7 @@ post_physics_kernel(const __grid_constant__ hb_env_params p, const __grid_consta
         if (do_rew || do_last) {
             float t1 = 0.f, t2 = 0.f, t3 = 0.f, ss = 0.f, acc = 0.f, vel = 0.f, tq = 0.f, rr = 0.f;
             float dy0 = 0.f, dy1 = 0.f, dy2 = 0.f, dy3 = 0.f, da0 = 0.f, da1 = 0.f, da2 = 0.f, da3 = 0.f;
-            const int yl = p.yaw_roll[0], yr_ = p.yaw_roll[1], al = p.arm_pair[0], ar_ = p.arm_pair[1];
+            constexpr int yl = T::YAW_L, yr_ = T::YAW_R, al = T::ARM_L, ar_ = T::ARM_R;      // (checked against p by the launcher)
 #pragma unroll
             for (int j = 0; j < NDOF; ++j) {
                 const float lact = sm[L.last_actions + ln * NDOF + j];
@@ -659,11 +668,13 @@ post_physics_kernel(const __grid_constant__ hb_env_params p, const __grid_consta
                 ss += d * d;
                 // hip yaw / roll of both legs (and, hector_full, the first two arm joints of both arms:
                 // hector_w_arm_env.py:371-378); the index pairs are task constants
-                // (scalars, not arrays: a run-time array index would send them to local memory)
+                // (j is a compile-time value in the unrolled loop: these are plain register copies)
                 dy0 = (j == yl) ? d : dy0, dy1 = (j == yl + 1) ? d : dy1;
                 dy2 = (j == yr_) ? d : dy2, dy3 = (j == yr_ + 1) ? d : dy3;
-                da0 = (j == al) ? d : da0, da1 = (j == al + 1) ? d : da1;
-                da2 = (j == ar_) ? d : da2, da3 = (j == ar_ + 1) ? d : da3;
+                if (T::HAS_ARMS) {
+                    da0 = (j == al) ? d : da0, da1 = (j == al + 1) ? d : da1;
+                    da2 = (j == ar_) ? d : da2, da3 = (j == ar_ + 1) ? d : da3;
+                }
                 if (joint_pos_on && use_ref && do_rew) {               // joint_pos, hector_env.py:264-275
                     const float e = q[j] - (valid ? b.ref_dof_pos[(size_t)env * NDOF + j] : 0.0f);
                     rr += e * e;
@@ -684,7 +695,7 @@ post_physics_kernel(const __grid_constant__ hb_env_params p, const __grid_consta
                 float yr = sqrtf(dy0 * dy0 + dy1 * dy1) + sqrtf(dy2 * dy2 + dy3 * dy3);
                 yr = clampf(yr - 0.1f, 0.0f, 50.0f);
                 float djp = expf(-yr * 100.0f);
-                if (p.arm_pair[0] >= 0) {
+                if (T::HAS_ARMS) {
                     float ar = sqrtf(da0 * da0 + da1 * da1) + sqrtf(da2 * da2 + da3 * da3);
                     ar = clampf(ar - 0.1f, 0.0f, 25.0f);
                     djp = djp + expf(-ar * 2.0f);
@@ -1540,8 +1551,13 @@ int hb_env_post_physics(const hb_env_params *p, const hb_env_buffers *buf, const
                    p->n_pen <= HB_MAX_CONTACT_BODIES, "hb_env_post_physics: too many contact bodies");
     HB_REQUIRE(noise->u_reset || noise->rng_counter, "hb_env_post_physics: u_reset or the device generator is required (any env may reset)");
     HB_REQUIRE(buf->scratch_ballots && buf->scratch_sums, "hb_env_post_physics: null scratch buffers");
-    HB_REQUIRE(p->yaw_roll[0] >= 0 && p->yaw_roll[0] + 1 < p->num_dof && p->yaw_roll[1] >= 0 && p->yaw_roll[1] + 1 < p->num_dof,
-               "hb_env_post_physics: yaw_roll joint pairs out of range");
+    {   // the joint pairs of default_joint_pos are constants of the three robots, compiled into the kernels
+        const bool arms = p->num_dof == 18;
+        HB_REQUIRE(p->yaw_roll[0] == 0 && p->yaw_roll[1] == p->num_dof / 2 && p->arm_pair[0] == (arms ? 5 : -1) &&
+                       p->arm_pair[1] == (arms ? p->num_dof / 2 + 5 : -1),
+                   "hb_env_post_physics: yaw_roll / arm_pair (%d, %d / %d, %d) are not the built robots' joint pairs (0, num_dof/2 / "
+                   "5, num_dof/2 + 5 with arms, -1 without)", p->yaw_roll[0], p->yaw_roll[1], p->arm_pair[0], p->arm_pair[1]);
+    }
     HB_REQUIRE((p->reward_scale[HB_R_JOINT_POS] == 0.0f && p->task_kind != HB_TASK_XBOT) || buf->ref_dof_pos,
                "hb_env_post_physics: ref_dof_pos is required (joint_pos reward / XBot-L privileged frame)");
     // bulk staging needs 16-byte aligned slabs: base pointers aligned and 32-env tiles (128-byte multiples)
@@ -1555,14 +1571,23 @@ int hb_env_post_physics(const hb_env_params *p, const hb_env_buffers *buf, const
     if (p->add_noise && noise->z_obs && !hb::aligned16(noise->z_obs)) bulk = false;      // caller-supplied draws at an odd offset: plain loads
     cudaStream_t st = (cudaStream_t)stream;
     // the three registered tasks (envs/__init__.py:46-48)
-    using Hector = Task<10, KIND_HECTOR>;
-    using HectorFull = Task<18, KIND_HECTOR>;
-    using XBot = Task<12, KIND_XBOT>;
+    using Hector = Task<10, KIND_HECTOR, true>;
+    using HectorSlim = Task<10, KIND_HECTOR, false>;
+    using HectorFull = Task<18, KIND_HECTOR, true>;
+    using HectorFullSlim = Task<18, KIND_HECTOR, false>;
+    using XBot = Task<12, KIND_XBOT, true>;
     auto matches = [&](int ndof, int kind, int obs, int priv) {
         return p->num_dof == ndof && p->task_kind == kind && p->num_single_obs == obs && p->num_single_priv == priv;
     };
-    if (matches(10, HB_TASK_HECTOR, Hector::OBS, Hector::PRIV)) return launch_post_physics<Hector>(p, buf, noise, obs_new, priv_new, stages, bulk, st);
-    if (matches(18, HB_TASK_HECTOR, HectorFull::OBS, HectorFull::PRIV)) return launch_post_physics<HectorFull>(p, buf, noise, obs_new, priv_new, stages, bulk, st);
+    // a config that scales none of the optional terms runs the kernel compiled without them
+    const bool opt = p->reward_scale[HB_R_JOINT_POS] != 0.0f || p->reward_scale[HB_R_VEL_MISMATCH_EXP] != 0.0f ||
+                     p->reward_scale[HB_R_TRACK_VEL_HARD] != 0.0f || p->reward_scale[HB_R_LOW_SPEED] != 0.0f;
+    if (matches(10, HB_TASK_HECTOR, Hector::OBS, Hector::PRIV))
+        return opt ? launch_post_physics<Hector>(p, buf, noise, obs_new, priv_new, stages, bulk, st)
+                   : launch_post_physics<HectorSlim>(p, buf, noise, obs_new, priv_new, stages, bulk, st);
+    if (matches(18, HB_TASK_HECTOR, HectorFull::OBS, HectorFull::PRIV))
+        return opt ? launch_post_physics<HectorFull>(p, buf, noise, obs_new, priv_new, stages, bulk, st)
+                   : launch_post_physics<HectorFullSlim>(p, buf, noise, obs_new, priv_new, stages, bulk, st);
     if (matches(12, HB_TASK_XBOT, XBot::OBS, XBot::PRIV)) return launch_post_physics<XBot>(p, buf, noise, obs_new, priv_new, stages, bulk, st);
     hb::set_error("hb_env_post_physics: no kernel for num_dof=%d task_kind=%d frames %d/%d (built: hector 10/41/70, hector_full "
                   "18/65/94, XBot-L 12/47/73)", p->num_dof, p->task_kind, p->num_single_obs, p->num_single_priv);
