@@ -92,7 +92,9 @@ typedef struct hb_env_params {
     /* joint index constants of the reward terms, as the task's env file spells them */
     int32_t yaw_roll[2];            /* first joint of the (yaw, roll) pair of the left / right leg: default_joint_pos
                                        (hector_env.py:363-364 -> 0, 5; hector_w_arm_env.py:370-373 -> 0, 9; humanoid_env.py -> 0, 6) */
-    int32_t arm_pair[2];            /* hector_full: first joint of the left / right arm pair (5, 14; :371-378); else -1 */
+    int32_t arm_pair[2];            /* hector_full: first joint of the left / right arm pair (5, 14; :371-378); else -1.
+                                       Both pairs are joint-order constants of the three robots (0, num_dof/2 and 5, num_dof/2 + 5)
+                                       and are compiled into the kernels: other values are refused (HB_ERR_BAD_ARG) */
     int32_t ref_left[3], ref_right[3];   /* compute_ref_state: joints driven by the left / right half of the gait sine
                                        (hector_env.py:100-107 -> 2,3,4 / 7,8,9; humanoid_env.py:131-138 -> 2,3,4 / 8,9,10) */
     /* control (legged_robot.py:339-355) */
