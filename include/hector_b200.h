@@ -342,6 +342,8 @@ enum hb_gemm_epilogue {
     HB_EPI_ELU_BWD = 3,    /* D = acc * elu'(z) with H = elu(z)       autograd of the above */
     HB_EPI_ATOMIC_ADD = 4  /* D += acc (split-K weight gradients; D must be zeroed by the caller) */
 };
+/* A, B (and, for every epilogue but HB_EPI_ATOMIC_ADD, D and H) are moved by TMA: 16-byte aligned bases, leading dimensions
+ * that are multiples of 4 floats (HB_ERR_BAD_ARG otherwise).  Ragged M / N are clipped by the tensor maps. */
 typedef struct hb_gemm_desc {
     const float *A, *B;
     float *D;

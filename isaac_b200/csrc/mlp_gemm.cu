@@ -7,8 +7,9 @@
 //   warp 9      allocates TMEM (two accumulators) and issues tcgen05.mma.cta_group::1.kind::tf32 (one elected
 //               lane); tcgen05.commit releases smem stages and hands finished accumulators to the epilogue
 //   warps 0-7   epilogue: tcgen05.ld the accumulator quarter / column half that belongs to the warp
-//               (lane = row) and apply the fused tail: bias + ELU (forward), ELU' (dgrad), plain store, or
-//               vector red.add (split-K wgrad)
+//               (lane = row), apply the fused tail in registers - bias + ELU (forward), ELU' (dgrad: the forward
+//               activations arrive by TMA, one 32 x 32 block ahead) - write the block into a 128-byte-swizzled
+//               shared-memory tile and hand it to a TMA store; split-K wgrad tiles leave as vector red.add instead
 // The kernel is persistent: one CTA per SM walks a static tile list, so barrier / TMEM setup is paid once and
 // the epilogue of one tile overlaps the main loop of the next.
 //
@@ -141,6 +142,30 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float *v) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float *v) {      // 32 consecutive columns of this warp's 32 lanes
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]),
+          "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]),
+          "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+// TMA store of a shared-memory box (written by this warp with ordinary stores, then fenced into the async proxy)
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, int c0, int c1, const void *smem) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(map), "r"(c0), "r"(c1),
+                 "r"(hb::smem_u32(smem))
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 // UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor): start address, leading / stride byte
 // offsets in 16-byte units, version 1 (Blackwell), layout type in bits [61,64).
 //   K-major operands : LayoutType SWIZZLE_128B (2): rows of 32 tf32 = 128 bytes, 16-byte chunks XOR-ed with
@@ -170,14 +195,23 @@ __host__ __device__ constexpr uint32_t make_idesc(int n, bool a_mn, bool b_mn, i
 // its own 128 rows of A but only HALF of the B tile (the tensor core reads the other half from the peer's shared
 // memory).  These TF32 GEMMs are bound by operand delivery (L2 -> SMEM, ~12 TB/s chip-wide), not by the tensor
 // pipe: per CTA and k-block a pair moves 32 KB instead of 48 KB for the same 128 x 256 x 32 MACs.
-template <int BN, bool PAIR>
-__host__ __device__ constexpr int stages_for() { return PAIR ? 6 : (BN >= 256 ? 4 : (BN >= 128 ? 6 : 8)); }
+constexpr int H_TILE_BYTES = 4096;                // ELU' epilogue: per warp, one TMA-loaded 32 x 32 block of forward activations
+template <int BN, bool PAIR, int EPI = 0>
+__host__ __device__ constexpr int stages_for() {
+    // the ELU' kernels give one stage to the epilogue warps' activation tiles (their K is a layer width: few k-blocks)
+    return (PAIR ? 6 : (BN >= 256 ? 4 : (BN >= 128 ? 6 : 8))) - (EPI != 3 ? 0 : (BN >= 128 ? 1 : (BN >= 64 ? 2 : 0)));
+}
 
 constexpr int EPI_TILE_FLOATS = 32 * 33;          // per epilogue warp: one padded 32 x 32 transpose tile
-template <int BN, bool PAIR>
+template <int BN, bool PAIR, int EPI = 0>
 __host__ __device__ constexpr size_t smem_bytes_for() {
-    return (size_t)stages_for<BN, PAIR>() * (BM * BK * 4 + (PAIR ? BN / 2 : BN) * BK * 4) + EPI_WARPS * EPI_TILE_FLOATS * 4 + 1024;
+    return (size_t)stages_for<BN, PAIR, EPI>() * (BM * BK * 4 + (PAIR ? BN / 2 : BN) * BK * 4) + EPI_WARPS * EPI_TILE_FLOATS * 4 +
+           (EPI == 3 ? EPI_WARPS * H_TILE_BYTES : 0) + 1024;
 }
+static_assert(smem_bytes_for<256, true, 3>() <= 227 * 1024 && smem_bytes_for<256, false, 3>() <= 227 * 1024 &&
+                  smem_bytes_for<128, false, 3>() <= 227 * 1024 && smem_bytes_for<64, false, 3>() <= 227 * 1024,
+              "ELU' kernels: stages + output tiles + activation tiles must fit in shared memory");
+static_assert((EPI_WARPS * EPI_TILE_FLOATS * 4) % 1024 == 0, "the activation tiles behind the output tiles stay 1024-byte aligned");
 
 // Persistent, warp-specialised: one CTA per SM walks a static list of output tiles
 //   tile t = blockIdx.x + i * gridDim.x  ->  (k split, m tile, n tile), n fastest so that the CTAs running at the
@@ -191,8 +225,10 @@ template <int BN, bool A_MN, bool B_MN, int EPI, bool PAIR>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_b0,
                  const __grid_constant__ GemmArgs g0, const __grid_constant__ CUtensorMap map_a1,
-                 const __grid_constant__ CUtensorMap map_b1, const __grid_constant__ GemmArgs g1) {
-    constexpr int NSTAGE = stages_for<BN, PAIR>();
+                 const __grid_constant__ CUtensorMap map_b1, const __grid_constant__ GemmArgs g1,
+                 const __grid_constant__ CUtensorMap map_d0, const __grid_constant__ CUtensorMap map_d1,
+                 const __grid_constant__ CUtensorMap map_h0, const __grid_constant__ CUtensorMap map_h1) {
+    constexpr int NSTAGE = stages_for<BN, PAIR, EPI>();
     constexpr int BN_CTA = PAIR ? BN / 2 : BN;               // B rows staged by this CTA
     constexpr int A_BYTES = BM * BK * 4, B_BYTES = BN_CTA * BK * 4;
     constexpr uint32_t ACC_COLS = BN < 32 ? 32 : BN;          // TMEM columns of one accumulator
@@ -201,7 +237,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t *sa = smem, *sb = smem + NSTAGE * A_BYTES;
     float *epi_smem = reinterpret_cast<float *>(smem + NSTAGE * (A_BYTES + B_BYTES));
-    __shared__ __align__(8) uint64_t full_bar[NSTAGE], empty_bar[NSTAGE], acc_full[2], acc_empty[2];
+    __shared__ __align__(8) uint64_t full_bar[NSTAGE], empty_bar[NSTAGE], acc_full[2], acc_empty[2], h_bar[EPI_WARPS];
     __shared__ uint32_t tmem_base_smem;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -219,11 +255,19 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
         for (int s = 0; s < NSTAGE; ++s) hb::mbar_init(&full_bar[s], 1), hb::mbar_init(&empty_bar[s], 1);
 #pragma unroll
         for (int a = 0; a < 2; ++a) hb::mbar_init(&acc_full[a], 1), hb::mbar_init(&acc_empty[a], PAIR ? 2 * EPI_WARPS : EPI_WARPS);
+#pragma unroll
+        for (int w = 0; w < EPI_WARPS; ++w) hb::mbar_init(&h_bar[w], 1);
         hb::fence_mbar_init();
     }
     if (warp == PRODUCER_WARP && lane == 0) {
         prefetch_tmap(&map_a0), prefetch_tmap(&map_b0);
-        if (g1.total_tiles > 0) prefetch_tmap(&map_a1), prefetch_tmap(&map_b1);
+        if (EPI != EPI_ATOMIC) prefetch_tmap(&map_d0);
+        if (EPI == EPI_ELU_BWD) prefetch_tmap(&map_h0);
+        if (g1.total_tiles > 0) {
+            prefetch_tmap(&map_a1), prefetch_tmap(&map_b1);
+            if (EPI != EPI_ATOMIC) prefetch_tmap(&map_d1);
+            if (EPI == EPI_ELU_BWD) prefetch_tmap(&map_h1);
+        }
     }
     if (warp == MMA_WARP) {
         if (PAIR) tmem_alloc_pair(&tmem_base_smem, TMEM_COLS);
@@ -356,7 +400,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
         const int c_begin = BN >= 64 ? half * HALF_COLS : 0;
         const int c_end = (BN >= 64 || half == 0) ? c_begin + HALF_COLS : 0;
         float *tile = epi_smem + warp * EPI_TILE_FLOATS;
-        uint32_t acc_it = 0;
+        uint32_t acc_it = 0, h_phase = 0;
         for (int round = 0; round * tile_step < all_tiles; ++round, ++acc_it) {
             const int t = tile_at(round);
             if (t >= all_tiles) break;
@@ -366,17 +410,106 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
             tile_coords(second ? t - g0.total_tiles : t, g, m0, n0, kb_begin, nkb);
             const uint32_t a = acc_it & 1, aph = (acc_it >> 1) & 1;
             const int mw = m0 + quarter * 32;                  // first row of this warp
-            if (EPI == EPI_ELU_BWD) {                          // pull the warp's block of H towards L2 meanwhile
-                const int row = mw + lane, n_lo = n0 + c_begin;
-                if (row < g.M && n_lo < g.N) {
-                    const float *hrow = g.H + (size_t)row * g.ldh + n_lo;
-                    const int bytes = min(c_end - c_begin, g.N - n_lo) * 4;
-                    for (int o = 0; o < bytes; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(hrow) + o));
+            // ELU': the warp's 32 x 32 blocks of the forward activations arrive by TMA in its second tile, one block ahead
+            // of their use (the first while the accumulator is still being computed), with the same 128-byte swizzle
+            uint8_t *htile = reinterpret_cast<uint8_t *>(epi_smem) + EPI_WARPS * EPI_TILE_FLOATS * 4 + warp * H_TILE_BYTES;
+            const CUtensorMap *pmap_h = second ? &map_h1 : &map_h0;
+            auto fetch_h = [&](int c) {                        // block at tile column c (one lane issues)
+                if (lane == 0) {
+                    hb::mbar_expect_tx(&h_bar[warp], H_TILE_BYTES);
+                    tma_load_2d(htile, pmap_h, n0 + c, mw, &h_bar[warp]);
                 }
+            };
+            if (EPI == EPI_ELU_BWD && c_begin < c_end && n0 + c_begin < g.N && mw < g.M) {
+                if (g.N - (n0 + c_begin) > 32 && c_begin + 32 < c_end) {       // pull the blocks after the first towards L2 meanwhile
+                    const int row = mw + lane, n_lo = n0 + c_begin + 32;
+                    if (row < g.M) {
+                        const float *hrow = g.H + (size_t)row * g.ldh + n_lo;
+                        const int bytes = min(c_end - c_begin - 32, g.N - n_lo) * 4;
+                        for (int o = 0; o < bytes; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(hrow) + o));
+                    }
+                }
+                fetch_h(c_begin);
             }
             hb::mbar_wait(&acc_full[a], aph);
             tc_fence_after();
             const uint32_t tmem_acc = tmem_base + a * ACC_COLS + ((uint32_t)(quarter * 32) << 16);
+            if constexpr (EPI != EPI_ATOMIC) {
+                // Plain / bias / ELU / ELU' results leave through the TMA: the warp applies the tail in registers (lane = row,
+                // as TMEM delivers it), writes its 32 x 32 block into a 128-byte-swizzled 4 KB tile with eight conflict-free
+                // 16-byte stores per lane and hands the tile to one cp.async.bulk.tensor store - no transposing read-back, no
+                // per-lane global stores, ragged edges clipped by the tensor map.
+                uint8_t *stile = reinterpret_cast<uint8_t *>(epi_smem) + warp * 4096;
+                const CUtensorMap *pmap_d = second ? &map_d1 : &map_d0;
+                bool handed_back = false;
+#pragma unroll 1
+                for (int c = c_begin; c < c_end; c += 32) {
+                    const int n = n0 + c;
+                    if (n >= g.N || mw >= g.M) break;
+                    float4 h4[8];
+                    if (EPI == EPI_ELU_BWD) {                    // this lane's row of the block, chunk j at j ^ (lane % 8)
+                        hb::mbar_wait(&h_bar[warp], h_phase);
+                        h_phase ^= 1u;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) h4[j] = *reinterpret_cast<const float4 *>(htile + lane * 128 + ((j ^ (lane & 7)) << 4));
+                        if (c + 32 < c_end && n + 32 < g.N) {    // next block's activations: in flight behind this block's work
+                            fence_async_smem();                  // (the reads above before the async-proxy overwrite)
+                            __syncwarp();
+                            fetch_h(c + 32);
+                        }
+                    }
+                    float bias_l = 0.0f;
+                    if (EPI == EPI_BIAS || EPI == EPI_BIAS_ELU) bias_l = (n + lane < g.N) ? __ldg(g.bias + (size_t)(n + lane) * g.bias_stride) : 0.0f;
+                    float v[32];
+                    if (BN > 16) {
+                        tmem_ld32(tmem_acc + (uint32_t)c, v);
+                    } else {                                     // 16-wide tiles: the upper half of the block is clipped by the store
+                        tmem_ld16(tmem_acc + (uint32_t)c, v);
+#pragma unroll
+                        for (int i = 16; i < 32; ++i) v[i] = 0.0f;
+                    }
+                    if (c + 32 >= c_end || n + 32 >= g.N) {      // last read of this accumulator: the MMA warp may reuse it
+                        tc_fence_before();
+                        if (lane == 0) {
+                            if (PAIR) mbar_arrive_cluster(mapa_shared(hb::smem_u32(&acc_empty[a]), 0));
+                            else hb::mbar_arrive(&acc_empty[a]);
+                        }
+                        handed_back = true;
+                    }
+                    if (EPI == EPI_BIAS || EPI == EPI_BIAS_ELU) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            float x = v[i] + __shfl_sync(0xffffffffu, bias_l, i);
+                            if (EPI == EPI_BIAS_ELU) x = x > 0.0f ? x : __expf(x) - 1.0f;       // nn.ELU(alpha=1)
+                            v[i] = x;
+                        }
+                    } else if (EPI == EPI_ELU_BWD) {            // h = elu(z): elu'(z) = z > 0 ? 1 : h + 1
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float h[4] = {h4[j].x, h4[j].y, h4[j].z, h4[j].w};
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) v[4 * j + k] *= (h[k] > 0.0f ? 1.0f : h[k] + 1.0f);
+                        }
+                    }
+                    if (lane == 0) tma_store_wait_read();        // the previous block's store has read the tile
+                    __syncwarp();
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)                  // 16-byte chunk j of row `lane` sits at chunk j ^ (lane % 8)
+                        *reinterpret_cast<float4 *>(stile + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+                            make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    fence_async_smem();
+                    __syncwarp();
+                    if (lane == 0) tma_store_2d(pmap_d, n, mw, stile);
+                }
+                if (!handed_back) {
+                    tc_fence_before();
+                    if (lane == 0) {
+                        if (PAIR) mbar_arrive_cluster(mapa_shared(hb::smem_u32(&acc_empty[a]), 0));
+                        else hb::mbar_arrive(&acc_empty[a]);
+                    }
+                }
+                continue;
+            }
 #pragma unroll 1
             for (int c = c_begin; c < c_end; c += 32) {
                 const int n = n0 + c;
@@ -464,6 +597,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
             }
         }
     }
+    if (EPI != EPI_ATOMIC && warp < EPI_WARPS && lane == 0) tma_store_wait_all();      // this warp's last stores have left its tile
     __syncwarp();                    // single-lane roles (producer, MMA issuer) rejoin their warps before the aligned barrier
     tc_fence_before();
     if (PAIR) cluster_sync();        // the leader's MMAs read the peer's shared memory: leave together
@@ -525,9 +659,21 @@ int make_map(CUtensorMap *map, const float *base, int rows, int cols, int ld, in
 
 // tensor maps + tile list of one problem
 template <int BN, bool A_MN, bool B_MN, int EPI, bool PAIR>
-int setup_problem(const hb_gemm_desc *d, CUtensorMap *ma, CUtensorMap *mb, GemmArgs *gp, int auto_splits) {
+int setup_problem(const hb_gemm_desc *d, CUtensorMap *ma, CUtensorMap *mb, CUtensorMap *md, CUtensorMap *mh, GemmArgs *gp,
+                  int auto_splits) {
     constexpr int BN_CTA = PAIR ? BN / 2 : BN;
     int rc;
+    *mh = CUtensorMap{};
+    if (EPI == EPI_ELU_BWD) {     // forward activations, read in the same 32 x 32 boxes as the output is written
+        rc = make_map(mh, d->H, d->M, d->N, d->ldh, 32, 32, false);
+        if (rc) return rc;
+    }
+    if (EPI != EPI_ATOMIC) {      // the output leaves through TMA stores of 32 x 32 boxes (clipped at M, N)
+        rc = make_map(md, d->D, d->M, d->N, d->ldd, 32, 32, false);
+        if (rc) return rc;
+    } else {
+        *md = CUtensorMap{};
+    }
     // A: K-major  -> memory [M, K] ;  MN-major -> memory [K, M]
     rc = A_MN ? make_map(ma, d->A, d->K, d->M, d->lda, 32, 32, true) : make_map(ma, d->A, d->M, d->K, d->lda, BK, BM, false);
     if (rc) return rc;
@@ -553,14 +699,14 @@ int setup_problem(const hb_gemm_desc *d, CUtensorMap *ma, CUtensorMap *mb, GemmA
 // d1 may be null (one problem)
 template <int BN, bool A_MN, bool B_MN, int EPI, bool PAIR>
 int launch(const hb_gemm_desc *d, const hb_gemm_desc *d1, cudaStream_t st) {
-    constexpr size_t SMEM = smem_bytes_for<BN, PAIR>();
+    constexpr size_t SMEM = smem_bytes_for<BN, PAIR, EPI>();
     static bool attr = false;
     auto kern = gemm_tf32_kernel<BN, A_MN, B_MN, EPI, PAIR>;
     if (!attr) {
         HB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
         attr = true;
     }
-    alignas(64) CUtensorMap ma, mb, ma1, mb1;
+    alignas(64) CUtensorMap ma, mb, ma1, mb1, md, md1, mh, mh1;
     GemmArgs g, g1;
     // Automatic split-K (weight gradients): k ranges of about equal length over BOTH problems of the launch, about two
     // rounds of tile jobs over the SMs (SM pairs in pair mode) - one round when the outputs have only a few tiles, where
@@ -581,11 +727,11 @@ int launch(const hb_gemm_desc *d, const hb_gemm_desc *d1, cudaStream_t st) {
             auto_splits[i] = sp < 1 ? 1 : sp;
         }
     }
-    if (int rc = setup_problem<BN, A_MN, B_MN, EPI, PAIR>(d, &ma, &mb, &g, auto_splits[0])) return rc;
+    if (int rc = setup_problem<BN, A_MN, B_MN, EPI, PAIR>(d, &ma, &mb, &md, &mh, &g, auto_splits[0])) return rc;
     if (d1) {
-        if (int rc = setup_problem<BN, A_MN, B_MN, EPI, PAIR>(d1, &ma1, &mb1, &g1, auto_splits[1])) return rc;
+        if (int rc = setup_problem<BN, A_MN, B_MN, EPI, PAIR>(d1, &ma1, &mb1, &md1, &mh1, &g1, auto_splits[1])) return rc;
     } else {
-        ma1 = ma, mb1 = mb, g1 = g;
+        ma1 = ma, mb1 = mb, md1 = md, mh1 = mh, g1 = g;
         g1.total_tiles = 0;
     }
     const int total_tiles = g.total_tiles + g1.total_tiles;
@@ -607,7 +753,7 @@ int launch(const hb_gemm_desc *d, const hb_gemm_desc *d1, cudaStream_t st) {
     }
     cfg.gridDim = dim3(grid), cfg.blockDim = dim3(GEMM_THREADS), cfg.dynamicSmemBytes = SMEM, cfg.stream = st;
     cfg.attrs = at, cfg.numAttrs = nat;
-    HB_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, mb, g, ma1, mb1, g1));
+    HB_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, mb, g, ma1, mb1, g1, md, md1, mh, mh1));
     HB_CHECK_LAUNCH("gemm_tf32_kernel");
     return HB_OK;
 }
