@@ -1,7 +1,7 @@
 """`ActorCritic` with the reference's interface (algo/ppo/actor_critic.py:36-128) on the tcgen05 GEMM path.
 
 Parameters live in ONE flat fp32 buffer so that gradient all-reduce, clip_grad_norm_ and Adam are single
-passes.  Each `nn.Linear` is a packed matrix `P[out_pad, ld]` = `[W | b | 0-pad]` with `ld = pad4(in + 1)`:
+passes.  Each `nn.Linear` is a packed matrix `P[out_pad, ld]` = `[W | b | 0-pad]` with `ld = pitch(in + 1)` (whole 128-byte rows):
   * the forward GEMM reads `W` through a TMA tensor map with K extent `in` and takes the bias from column `in`;
   * the weight-gradient GEMM multiplies by the activations extended with a constant ones column, so the bias
     gradient is simply column `in` of the packed gradient — no separate reduction kernel;
@@ -22,6 +22,13 @@ from .._lib import (GemmDesc, HB_EPI_ATOMIC_ADD, HB_EPI_BIAS, HB_EPI_BIAS_ELU, H
                     PPO_NUM_ACTIONS)
 
 
+def pitch(n: int) -> int:
+    """Row pitch (floats) of the buffers the TMA reads and writes here: whole 128-byte lines.  A 16-byte-aligned pitch is
+    all the TMA asks for, but every 128-byte box row then straddles two lines and five 32-byte sectors instead of four:
+    measured on the layer-1 forward GEMM (K = 1050), 79.9 us at a pitch of 1052 floats against 68.2 us at 1056."""
+    return (n + 31) // 32 * 32
+
+
 def pad4(n: int) -> int:
     return (n + 3) // 4 * 4
 
@@ -32,7 +39,7 @@ class _Layer:
     def __init__(self, net, index, fan_in, fan_out, last, offset):
         self.net, self.index, self.fan_in, self.fan_out, self.last, self.offset = net, index, fan_in, fan_out, last, offset
         self.rows = (fan_out + 15) // 16 * 16 if last else fan_out          # output layers are padded to a multiple of the smallest UMMA N
-        self.ld = pad4(fan_in + 1)
+        self.ld = pitch(fan_in + 1)
 
     @property
     def numel(self):
@@ -186,11 +193,11 @@ class ActorCritic:
                 Ls = [L for L in self.layers if L.net == net]
                 hs = []
                 for L in Ls[:-1]:
-                    h = z(m, pad4(L.fan_out + 1))
+                    h = z(m, pitch(L.fan_out + 1))
                     h[:, L.fan_out] = 1.0
                     hs.append(h)
                 ws[net] = {"h": hs, "out": z(m, Ls[-1].rows), "d_out": z(m, Ls[-1].rows),
-                           "dz": [z(m, L.fan_out) for L in Ls[:-1]]}
+                           "dz": [z(m, pitch(L.fan_out)) for L in Ls[:-1]]}
             self._ws[m] = ws
         return ws
 
@@ -206,7 +213,7 @@ class ActorCritic:
 
     def _mlp_forward(self, net: str, x: torch.Tensor, ws: dict, hidden_only: bool = False):
         """x: [m, ld] with ld % 4 == 0 (only the first fan_in columns are read).  Returns out [m,16]
-        (or, with hidden_only, the last hidden activations [m, pad4(width + 1)])."""
+        (or, with hidden_only, the last hidden activations [m, pitch(width + 1)])."""
         lib, st = self._lib, torch.cuda.current_stream(self.device).cuda_stream
         Ls = [L for L in self.layers if L.net == net]
         a, lda = x, x.stride(0)
@@ -304,7 +311,7 @@ class ActorCritic:
         """TMA needs 16-byte aligned rows: use x in place when its row stride allows, else stage a padded copy."""
         if x.is_cuda and x.dtype == torch.float32 and x.stride(-1) == 1 and x.stride(0) % 4 == 0 and x.data_ptr() % 16 == 0:
             return x
-        buf = torch.zeros(x.shape[0], pad4(width + 1), device=self.device)
+        buf = torch.zeros(x.shape[0], pitch(width + 1), device=self.device)
         buf[:, :width] = x
         return buf
 

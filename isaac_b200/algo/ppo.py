@@ -22,7 +22,7 @@ import torch
 from .. import _lib
 from .._lib import (AdamParams, HB_OPT_TRACE_MAX, OPT_ERROR, OPT_LOSS_ACC, OPT_LR, OPT_STATS, OPT_STEP,
                     OPT_STEPS_IN_UPDATE, OPT_SUMSQ, OPT_TRACE, OPTIM_STATE_DOUBLES, PpoLossParams, ppo_rec)
-from .actor_critic import ActorCritic, pad4
+from .actor_critic import ActorCritic, pad4, pitch
 from .rollout_storage import RolloutStorage
 
 
@@ -454,7 +454,7 @@ class PPO:
         if perm is None:
             perm = torch.randperm(used, device=dev)
         perm = perm.to(dev, dtype=torch.int64).contiguous()
-        ld_a, ld_c = pad4(ac.num_actor_obs + 1), pad4(ac.num_critic_obs + 1)
+        ld_a, ld_c = pitch(ac.num_actor_obs + 1), pitch(ac.num_critic_obs + 1)      # 128-byte rows for the layer-1 GEMMs
         if getattr(self, "_xa", None) is None or self._xa.shape[0] != used:
             self._xa = torch.zeros(used, ld_a, device=dev)
             self._xc = torch.zeros(used, ld_c, device=dev)
