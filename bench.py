@@ -543,7 +543,7 @@ def run_b200(args, rank, world):
                 tot += a.elapsed_time(b)
         return tot / reps / len(fns)
 
-    (o_prev, p_prev), (o_cur, p_cur) = env._own[0][:2], env._own[1][:2]      # the env's own pair; rows at the 616 / 1052-float pitch
+    (o_prev, p_prev), (o_cur, p_cur) = env._own[0][:2], env._own[1][:2]      # the env's own pair; rows at the 640 / 1056-float pitch
     P, B = env._pp, env._pb
     rb = None            # unconditional shift (reset envs are zeroed by hb_env_reset_finalize)
     dense = [torch.randn(n, w, device=dev) for w in (STACK_PRIV * FRAME_PRIV, STACK_PRIV * FRAME_PRIV,
@@ -608,8 +608,8 @@ def run_b200(args, rank, world):
     host_frames = [type(f)(*(t.cpu().pin_memory() for t in (f.root_states, f.dof_state, f.contact_forces, f.rigid_state)))
                    for f in tape.physics]
     host_actions = [f.actions.pin_memory() for f in tape.noise]
-    # host images keep the device row pitch (616 / 1052 floats: one padding column), so each result is ONE copy
-    out_host = [[torch.empty(n, env._p.obs_ld).pin_memory(), torch.empty(n, env._p.priv_ld).pin_memory(),
+    # dense host images; each observation tensor (rows at the device's 128-byte pitch) leaves as ONE 2-D DMA copy (hb_copy_rows)
+    out_host = [[torch.empty(n, env.num_obs).pin_memory(), torch.empty(n, env.num_privileged_obs).pin_memory(),
                  torch.empty(n).pin_memory(), torch.empty(n, dtype=torch.bool).pin_memory()] for _ in range(2)]
     act_dev = torch.empty(n, 10, device=dev)
     copy_stream = torch.cuda.Stream(dev)
@@ -617,8 +617,9 @@ def run_b200(args, rank, world):
     ev_copied = [torch.cuda.Event() for _ in range(2)]
     checksum = [0.0]
 
-    def whole_rows(t):          # [n, width] view at a pitch -> the [n, pitch] block it lives in
-        return t if t.dim() < 2 or t.is_contiguous() else torch.as_strided(t, (t.shape[0], t.stride(0)), (t.stride(0), 1))
+    def copy_rows(dst, src, st):          # [n, width] view of pitched device rows -> dense pinned host rows
+        _lib.check(lib.hb_copy_rows(dst.data_ptr(), dst.stride(0) * 4, src.data_ptr(), src.stride(0) * 4, src.shape[1] * 4,
+                                    src.shape[0], st.cuda_stream), "hb_copy_rows")
 
     def consume(slot):          # the caller's read of a finished step: waits for that buffer set only
         ev_copied[slot].synchronize()
@@ -636,8 +637,8 @@ def run_b200(args, rank, world):
         ev_step[slot].record(stream)
         copy_stream.wait_event(ev_step[slot])
         with torch.cuda.stream(copy_stream):
-            out_host[slot][0].copy_(whole_rows(out[0]), non_blocking=True)
-            out_host[slot][1].copy_(whole_rows(out[1]), non_blocking=True)
+            copy_rows(out_host[slot][0], out[0], copy_stream)
+            copy_rows(out_host[slot][1], out[1], copy_stream)
             ev_copied[slot].record(copy_stream)
         if i >= 1:
             consume(slot ^ 1)                        # hand step i-1's results to the caller

@@ -75,8 +75,10 @@ typedef struct hb_env_params {
     int32_t c_frame_stack;          /* 15 / 15 / 3 */
     int32_t obs_ld, priv_ld;        /* row pitch, in floats, of every obs / privileged-obs buffer handed to the calls
                                        below; 0 = dense (frame_stack * num_single_obs).  A pitch that is a multiple of
-                                       4 (616 / 1052) makes the rows TMA-addressable: the buffers can be the rollout
-                                       storage's own slots (rollout_storage.py:60-61), SURVEY.md §8(f) rank 1 */
+                                       4 makes the rows TMA-addressable: the buffers can be the rollout storage's own
+                                       slots (rollout_storage.py:60-61), SURVEY.md §8(f) rank 1.  The host classes use
+                                       whole 128-byte rows (640 / 1056 floats for hector): a TMA box row then covers 4
+                                       sectors instead of 5 (layer-1 GEMM 15 % faster) */
     int32_t feet[2];                /* rigid-body rows of the feet   (legged_robot.py:668-671) */
     int32_t knees[2];               /* rigid-body rows of the knees  (:672-674) */
     int32_t n_term;                 /* termination_contact_indices   (:680-682) */
@@ -231,6 +233,11 @@ void hb_launch_count_reset(void);
  * direction, so the extra tiles of a partial last round land on the CTAs that hold the shortest earlier tiles (results do
  * not depend on it; the order of split-K float atomics does). */
 int hb_set_option(const char *name, int value);
+/* dst[r, 0:width] = src[r, 0:width] for `rows` rows at the given byte pitches: ONE 2-D DMA transfer (device or pinned host
+ * memory on either side).  How a host consumer reads step()'s observation tensors ([N, width] views of pitched rows)
+ * without moving the padding. */
+int hb_copy_rows(void *dst, int64_t dst_pitch_bytes, const void *src, int64_t src_pitch_bytes, int64_t width_bytes, int64_t rows,
+                 void *stream);
 
 /* CUDA graphs of hb_* launch sequences (one env step, one PPO.act) without the framework's graph object:
  * begin capture on `stream` (not the legacy default stream), issue hb_* calls on it, end -> an executable graph;

@@ -2,7 +2,7 @@
 in the CUDA scan kernel `hb_gae_returns` + `hb_gae_normalize` (C ABI, include/hector_b200.h).
 
 Layout: time-major `[T, N, ·]` fp32 tensors in HBM like the reference.  The observation
-buffers keep a padded leading dimension (616 / 1052 floats) so that every row starts on a
+buffers keep a padded leading dimension (640 / 1056 floats: whole 128-byte rows) so that every row starts on a
 16-byte boundary — the alignment TMA tensor maps need for the MLP GEMMs — and expose
 `[T, N, 615]` / `[T, N, 1050]` views under the reference's attribute names.
 """
@@ -15,8 +15,8 @@ import torch
 from .. import _lib
 
 
-def _pad4(n: int) -> int:
-    return (n + 3) // 4 * 4
+def _pitch(n: int) -> int:
+    return (n + 31) // 32 * 32          # whole 128-byte rows (actor_critic.pitch)
 
 
 _FUSED_SCRATCH = {}
@@ -89,12 +89,12 @@ class RolloutStorage:
         # rows at a 16-byte pitch (TMA operands), and one slot more than the reference's [T, N, *]: slot T receives the
         # observations that follow the last transition when the env writes straight into the storage
         # (PPO.attach_env; they become slot 0 of the next rollout)
-        # (pitch = pad4(width + 1): there is always room for the constant ones column the weight-gradient GEMM reads)
-        self.obs_ld = _pad4(obs_shape[0] + 1)
+        # (pitch = ceil32(width + 1): there is always room for the constant ones column the weight-gradient GEMM reads)
+        self.obs_ld = _pitch(obs_shape[0] + 1)
         self._observations = z(T + 1, N, self.obs_ld)
         self.observations = self._observations[:T, :, :obs_shape[0]]
         if privileged_obs_shape[0] is not None:
-            self.priv_ld = _pad4(privileged_obs_shape[0] + 1)
+            self.priv_ld = _pitch(privileged_obs_shape[0] + 1)
             self._privileged_observations = z(T + 1, N, self.priv_ld)
             self.privileged_observations = self._privileged_observations[:T, :, :privileged_obs_shape[0]]
         else:

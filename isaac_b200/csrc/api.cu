@@ -56,6 +56,17 @@ int hb_sizeof_adam_params(void) { return (int)sizeof(hb_adam_params); }
 int hb_sizeof_optim_state(void) { return (int)sizeof(hb_optim_state); }
 int hb_sizeof_dp_comm(void) { return (int)sizeof(hb_dp_comm); }
 
+// Observation tensors are [N, width] views of rows at a 128-byte pitch: a host (or dense-buffer) consumer copies the valid
+// columns of all rows with one 2-D DMA transfer instead of the whole pitched block.
+int hb_copy_rows(void *dst, int64_t dst_pitch_bytes, const void *src, int64_t src_pitch_bytes, int64_t width_bytes, int64_t rows,
+                 void *stream) {
+    HB_REQUIRE(dst && src && rows > 0 && width_bytes > 0 && dst_pitch_bytes >= width_bytes && src_pitch_bytes >= width_bytes,
+               "hb_copy_rows: bad arguments");
+    HB_CUDA(cudaMemcpy2DAsync(dst, (size_t)dst_pitch_bytes, src, (size_t)src_pitch_bytes, (size_t)width_bytes, (size_t)rows,
+                              cudaMemcpyDefault, (cudaStream_t)stream));
+    return HB_OK;
+}
+
 // The kernels are sm_100a-only (no other cubin or PTX is embedded): refuse anything else loudly.
 int hb_check_device(void) {
     int dev = 0;

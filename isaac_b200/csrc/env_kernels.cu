@@ -1333,12 +1333,12 @@ get_heights_kernel(const float *__restrict__ root_states, const float *__restric
 int g_use_bulk = 1;
 
 // Frame stacks of the three tasks (hector_config.py:8-20, hector_w_arm_config.py:8-20, humanoid_config.py:42-52): rows
-// either dense or at the 16-byte pitch pad4(row + 1) (TMA-addressable: the rollout storage's slots)
-constexpr int pad4c(int v) { return (v + 3) / 4 * 4; }
+// either dense or at the 128-byte pitch ceil32(row + 1) (TMA-addressable: the rollout storage's slots)
+constexpr int pitchc(int v) { return (v + 31) / 32 * 32; }      // whole 128-byte lines: TMA box rows then touch 4 sectors, not 5
 template <int OBS_, int S_, int PRIV_, int CS_>
 struct StackShape {
-    static constexpr int FRAME_A = OBS_, ROW_A = S_ * OBS_, LD_A = pad4c(ROW_A + 1);
-    static constexpr int FRAME_B = PRIV_, ROW_B = CS_ * PRIV_, LD_B = pad4c(ROW_B + 1);
+    static constexpr int FRAME_A = OBS_, ROW_A = S_ * OBS_, LD_A = pitchc(ROW_A + 1);
+    static constexpr int FRAME_B = PRIV_, ROW_B = CS_ * PRIV_, LD_B = pitchc(ROW_B + 1);
 };
 using ShapeHector = StackShape<41, 15, 70, 15>;
 using ShapeHectorFull = StackShape<65, 15, 94, 15>;

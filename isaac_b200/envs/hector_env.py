@@ -20,7 +20,7 @@ The per-step work is four kinds of kernel launch through the C ABI (include/hect
                                      count, episode means, time_outs) - the fused form of
                                      hb_env_stack_observations + hb_env_reset_finalize
 
-Observation tensors are `[N, 615]` / `[N, 1050]` views of rows at a 16-byte pitch (616 / 1052 floats); the caller may
+Observation tensors are `[N, 615]` / `[N, 1050]` views of rows at a 128-byte pitch (640 / 1056 floats); the caller may
 supply the buffers of the next step (`set_next_observation_buffers`, what `PPO.attach_env` does with the rollout slots).
 `enable_cuda_graph()` replays the step from two graphs of these launches (hb_graph_*), with no staging copy around them.
 
@@ -86,9 +86,9 @@ def build_env_params(cfg, num_envs: int, num_bodies: int, body_names, dof_names,
     p.ref_scale[0], p.ref_scale[1] = scale_1, 2 * scale_1
     p.num_single_obs, p.frame_stack = cfg.env.num_single_obs, cfg.env.frame_stack
     p.num_single_priv, p.c_frame_stack = cfg.env.single_num_privileged_obs, cfg.env.c_frame_stack
-    # rows at a 16-byte pitch: the observation buffers can then be rollout-storage slots and TMA operands
-    p.obs_ld = (p.num_single_obs * p.frame_stack + 1 + 3) // 4 * 4          # pad4(width + 1), like RolloutStorage
-    p.priv_ld = (p.num_single_priv * p.c_frame_stack + 1 + 3) // 4 * 4
+    # rows at a 128-byte pitch: the observation buffers can then be rollout-storage slots and TMA operands
+    p.obs_ld = (p.num_single_obs * p.frame_stack + 1 + 31) // 32 * 32       # ceil32(width + 1), like RolloutStorage
+    p.priv_ld = (p.num_single_priv * p.c_frame_stack + 1 + 31) // 32 * 32
     feet = _find(body_names, [cfg.asset.foot_name])
     knees = _find(body_names, [cfg.asset.knee_name])
     term = _find(body_names, cfg.asset.terminate_after_contacts_on)
@@ -249,7 +249,7 @@ class HectorFreeEnvB200:
         self.forward_vec = torch.tensor([1.0, 0.0, 0.0], **f32).repeat(N, 1)
         # ping-pong observation buffers: the tensor returned by step() stays valid until the step
         # after next (PPO.act keeps references until process_env_step, ppo.py:99-100,111).  Rows sit at a
-        # 16-byte pitch (616 / 1052 floats); a caller may hand the env the buffers of the NEXT step
+        # 128-byte pitch (640 / 1056 floats); a caller may hand the env the buffers of the NEXT step
         # (set_next_observation_buffers: the rollout storage's slots), else it alternates between its own two.
         # Each buffer pair travels as (obs, priv, (obs address, priv address)): the addresses key the step graphs.
         self._own = [self._buffer_pair(z(N, self._p.obs_ld)[:, :self.num_obs],
@@ -326,7 +326,7 @@ class HectorFreeEnvB200:
     def set_next_observation_buffers(self, obs: torch.Tensor, privileged_obs: torch.Tensor) -> None:
         """The next step() writes its observations into these tensors instead of the env's own ping-pong pair
         (one step only).  They are what step() then returns; rows must sit at the env's pitch
-        (`[N, num_obs]` views of `[N, 616]` / `[N, 1052]` fp32 buffers, 16-byte aligned) and must not be the
+        (`[N, num_obs]` views of `[N, 640]` / `[N, 1056]` fp32 buffers, 16-byte aligned) and must not be the
         buffers the current observations live in.  PPO.act points this at the rollout storage's next slot, so
         that `add_transitions`' observation copies (rollout_storage.py:90-92) never happen."""
         for t, width, ld in ((obs, self.num_obs, self._p.obs_ld), (privileged_obs, self.num_privileged_obs, self._p.priv_ld)):

@@ -1,4 +1,4 @@
-"""A/B of the frame-stack + finalize launch on dense rows (615 / 1050 floats) and on the 16-byte pitch (616 / 1052):
+"""A/B of the frame-stack + finalize launch on dense rows (615 / 1050 floats) and on the 128-byte pitch (640 / 1056):
 CUDA events around a graph of 4 launches on 4 cold buffer sets, L2 flushed before each replay."""
 import argparse
 import os
@@ -28,7 +28,7 @@ def main():
         phys.load_frame(tape.physics[0].to(dev))
         env = HectorFreeEnvB200(HectorCfg(), sim_device=str(dev), physics=phys, statics=tape.statics)
         env.reset_buf.copy_(torch.rand(n, device=dev) < 0.005)
-        for name, (ld_o, ld_p) in (("dense", (615, 1050)), ("pitched", (616, 1052))):
+        for name, (ld_o, ld_p) in (("dense", (615, 1050)), ("pitched", (640, 1056))):
             env._p.obs_ld, env._p.priv_ld = (0, 0) if name == "dense" else (ld_o, ld_p)
             sets = [(torch.randn(n, ld_o, device=dev), torch.randn(n, ld_p, device=dev), torch.empty(n, ld_o, device=dev),
                      torch.empty(n, ld_p, device=dev)) for _ in range(4)]

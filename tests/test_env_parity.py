@@ -491,12 +491,12 @@ def test_fused_shift_finalize_equals_separate_calls(lib, cuda_device, n, pitched
     """hb_env_stack_finalize (what step() launches) against hb_env_stack_observations + hb_env_reset_finalize on the
     same inputs: identical frame stacks, id lists, counts, episode means and time-out latch (ragged sizes included:
     615 n is not a multiple of 4 for n = 1003, the last ballot word is partial for n = 37).  Both row layouts:
-    dense [n,615] / [n,1050] and the 16-byte pitch the env and the rollout storage use (616 / 1052)."""
+    dense [n,615] / [n,1050] and the 128-byte pitch the env and the rollout storage use (640 / 1056)."""
     from isaac_b200 import _lib
     dev = cuda_device
     tape = make_tape(n, 2, seed=3 + n, fall_prob=0.2)
     env, phys = make_cuda_env(tape, dev)
-    ld_o, ld_p = (616, 1052) if pitched else (615, 1050)
+    ld_o, ld_p = (640, 1056) if pitched else (615, 1050)
     env._p.obs_ld, env._p.priv_ld = (ld_o, ld_p) if pitched else (0, 0)
     g = torch.Generator(device=dev).manual_seed(n)
     prev_o, prev_p = torch.randn(n, ld_o, device=dev, generator=g), torch.randn(n, ld_p, device=dev, generator=g)
@@ -626,7 +626,7 @@ def test_caller_supplied_observation_buffers(lib, cuda_device):
     env_a, phys_a = make_cuda_env(tape, dev)
     env_b, phys_b = make_cuda_env(tape, dev)
     env_a.seed(5), env_b.seed(5)
-    ext = [(torch.full((n, 616), 9.0, device=dev), torch.full((n, 1052), 9.0, device=dev)) for _ in range(2)]
+    ext = [(torch.full((n, 640), 9.0, device=dev), torch.full((n, 1056), 9.0, device=dev)) for _ in range(2)]
     actions = torch.zeros(n, 10, device=dev)
     for k in range(3):
         frame = tape.physics[k + 1].to(dev)

@@ -8,9 +8,9 @@ from isaac_b200.algo.rollout_storage import RolloutStorage
 def test_layout_and_extra_slot():
     s = RolloutStorage(8, 4, [615], [1050], [10], device="cpu")
     assert s.observations.shape == (4, 8, 615) and s.privileged_observations.shape == (4, 8, 1050)
-    assert s._observations.shape == (5, 8, 616) and s._privileged_observations.shape == (5, 8, 1052)   # T + 1 slots, 16-byte rows
+    assert s._observations.shape == (5, 8, 640) and s._privileged_observations.shape == (5, 8, 1056)   # T + 1 slots, 128-byte rows
     o, p = s.observation_slot(4)
-    assert o.shape == (8, 615) and o.stride() == (616, 1) and p.shape == (8, 1050) and p.stride() == (1052, 1)
+    assert o.shape == (8, 615) and o.stride() == (640, 1) and p.shape == (8, 1050) and p.stride() == (1056, 1)
     o.fill_(3.0)
     assert float(s.observations.abs().sum()) == 0.0, "slot T lies outside the [T, N, *] view the update reads"
     for name in ("actions", "mu", "sigma"):
