@@ -1407,14 +1407,14 @@ int launch_post_physics(const hb_env_params *p, const hb_env_buffers *buf, const
             HB_CUDA(cudaFuncSetAttribute(post_physics_kernel<true, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
             attr_set[1] = true;
         }
-        HB_CUDA(hb::launch_pdl(hb::use_pdl(p->num_envs), post_physics_kernel<true, T>, dim3(tiles), dim3(4 * TILE), smem, st, *p, *buf,
+        HB_CUDA(hb::launch_pdl(hb::use_pdl_post(p->num_envs), post_physics_kernel<true, T>, dim3(tiles), dim3(4 * TILE), smem, st, *p, *buf,
                                *noise, obs_new, priv_new, (int)stages));
     } else {
         if (!attr_set[0]) {
             HB_CUDA(cudaFuncSetAttribute(post_physics_kernel<false, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
             attr_set[0] = true;
         }
-        HB_CUDA(hb::launch_pdl(hb::use_pdl(p->num_envs), post_physics_kernel<false, T>, dim3(tiles), dim3(4 * TILE), smem, st, *p, *buf,
+        HB_CUDA(hb::launch_pdl(hb::use_pdl_post(p->num_envs), post_physics_kernel<false, T>, dim3(tiles), dim3(4 * TILE), smem, st, *p, *buf,
                                *noise, obs_new, priv_new, (int)stages));
     }
     HB_CHECK_LAUNCH("post_physics_kernel");
@@ -1674,7 +1674,7 @@ int hb_env_stack_finalize(const hb_env_params *p, const hb_env_buffers *buf, con
     const bool pitch = layout == 2;
     FinKernel kernel = shape == 0 ? HB_FIN(ShapeHector, pitch) : (shape == 1 ? HB_FIN(ShapeHectorFull, pitch) : HB_FIN(ShapeXBot, pitch));
 #undef HB_FIN
-    HB_CUDA(hb::launch_pdl(hb::use_pdl(p->num_envs), kernel,
+    HB_CUDA(hb::launch_pdl(hb::use_pdl_stack(p->num_envs), kernel,
                            dim3(blocks_a + blocks_b + fin_blocks), dim3(256), 0, (cudaStream_t)stream, obs_prev, obs_new, total_a,
                            blocks_a, priv_prev, priv_new, total_b, blocks_b, *p, *buf, tiles, seg, host_count,
                            reinterpret_cast<unsigned long long *>(rng_counter)));

@@ -47,14 +47,18 @@ extern int g_use_pdl;   // "pdl" option: programmatic stream serialization of th
                         // 2 or -1 (default) = only the PD-torque launches.  On the large kernels (post-physics, frame
                         // stack) the early-resident dependents and the completion flush behind griddepcontrol.wait
                         // cost more than the overlap gains at every shard size measured (52.0 vs 60.4 us per step at
-                        // 4096 envs, -13 % at 65 536)
+                        // 4096 envs, -13 % at 65 536).  3 = PD launches + post-physics, 4 = PD launches + frame stack:
+                        // round 2, 4096 envs: 43.1 (default) / 49.2 (3) / 43.4 (4) / 49.4 (1) us per step; 16 384 envs:
+                        // 73.0 / 77.5 / 78.7 / 79.4
 extern int g_gae_serial_min_envs;   // "gae_serial_min_envs" option: shards at least this wide run GAE one thread per env (default 8192)
 extern int g_coop_launch;   // "coop_launch" option: 1 = kernels with a grid barrier (optimizer step, single-launch GAE) are launched with the
                             // cooperative attribute; 0 (default) = plain launches of a grid that fits the device (see hector_b200.h)
 extern int g_gemm_snake;  // "gemm_tile_snake" option: 1 (default) = rounds of the GEMM tile list are dealt to the CTAs in alternating direction
 extern int g_gemm_pdl;  // "gemm_pdl" option: 1 (default) = GEMM launches overlap their set-up with the previous kernel's tail
 inline bool use_pdl(int num_envs) { (void)num_envs; return g_use_pdl == 1; }
-inline bool use_pdl_small_kernel(int num_envs) { return g_use_pdl == 2 || g_use_pdl < 0 || use_pdl(num_envs); }
+inline bool use_pdl_post(int num_envs) { return g_use_pdl == 3 || use_pdl(num_envs); }      // 3: PD launches + post-physics
+inline bool use_pdl_stack(int num_envs) { return g_use_pdl == 4 || use_pdl(num_envs); }     // 4: PD launches + frame stack / finalize
+inline bool use_pdl_small_kernel(int num_envs) { return g_use_pdl >= 2 || g_use_pdl < 0 || use_pdl(num_envs); }
 
 #ifdef __CUDACC__
 // <<<grid, block, smem, stream>>> with the programmatic-dependent-launch attribute (kernels call hb::pdl_wait()).
