@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define HB_ABI_VERSION 4
+#define HB_ABI_VERSION 5
 
 typedef enum hb_status {
     HB_OK = 0,
@@ -326,9 +326,12 @@ int hb_gae_normalize(float *advantages, const double *stats, int64_t count, void
 int hb_gae_normalize_n(float *advantages, const double *stats, int64_t stat_count, int64_t count, void *stream);
 /* Single-GPU form of the whole of compute_returns in ONE launch: one thread per env, the raw advantages stay in
  * shared memory across a grid barrier on (sum, sum sq) and are written once, normalised - 17 instead of 25 bytes per sample
- * and one launch instead of memset + two kernels.  scratch: 4 doubles of device memory, zero before the first call (the
- * launch re-arms them).  Falls back to hb_gae_returns + hb_gae_normalize for longer rollouts or shards too wide for one
- * co-resident grid.  Multi-GPU callers use the two-call form (the statistics are all-reduced between the passes). */
+ * and one launch instead of memset + two kernels.  scratch: HB_GAE_SCRATCH_DOUBLES doubles of device memory (8 slots of
+ * sums, 8 of sums of squares, a ticket), zero before the first call (the launch re-arms them).  Falls back to
+ * hb_gae_returns + hb_gae_normalize for longer rollouts or shards too wide for one co-resident grid.  Multi-GPU callers
+ * use the two-call form (the statistics are all-reduced between the passes).
+ * Option "gae_threads": block width, 0 (default: 64 up to 8192 envs, else 256) / 32 / 64 / 128 / 256. */
+#define HB_GAE_SCRATCH_DOUBLES 32
 int hb_gae_fused(const float *rewards, const float *values, const uint8_t *dones, const float *last_values, float *returns,
                  float *advantages, double *scratch, int32_t T, int32_t N, float gamma, float lam, void *stream);
 

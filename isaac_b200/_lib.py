@@ -10,7 +10,7 @@ import ctypes as C
 import os
 from typing import Optional
 
-HB_ABI_VERSION = 4
+HB_ABI_VERSION = 5
 HB_MAX_DOF = 24
 HB_MAX_OBS = 80
 HB_NUM_REWARDS = 22

@@ -38,8 +38,8 @@ def gae_compute_returns(rewards, values, dones, last_values, returns, advantages
     st = torch.cuda.current_stream(rewards.device).cuda_stream
     if fused and reduce_stats is None and stats is None and T * N > 1:
         scratch = _FUSED_SCRATCH.get(rewards.device)
-        if scratch is None:          # {sum, sum sq, ticket, -}: zeroed once, re-armed by every launch
-            scratch = _FUSED_SCRATCH[rewards.device] = torch.zeros(4, dtype=torch.float64, device=rewards.device)
+        if scratch is None:          # HB_GAE_SCRATCH_DOUBLES {8 sums, 8 sums of squares, ticket}: zeroed once, re-armed by every launch
+            scratch = _FUSED_SCRATCH[rewards.device] = torch.zeros(32, dtype=torch.float64, device=rewards.device)
         _lib.check(lib.hb_gae_fused(rewards.data_ptr(), values.data_ptr(), dones.data_ptr(), last_values.data_ptr(),
                                     returns.data_ptr(), advantages.data_ptr(), scratch.data_ptr(), T, N,
                                     float(gamma), float(lam), st), "hb_gae_fused")

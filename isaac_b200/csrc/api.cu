@@ -22,6 +22,7 @@ int g_gemm_pdl = 1;
 int g_gemm_snake = 1;
 int g_coop_launch = 0;
 int g_gae_serial_min_envs = 8192;
+int g_gae_threads = 0;
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 

@@ -1456,6 +1456,11 @@ int hb_set_option(const char *name, int value) {
         hb::g_gae_serial_min_envs = value;
         return HB_OK;
     }
+    if (name && !strcmp(name, "gae_threads")) {
+        HB_REQUIRE(value == 0 || value == 32 || value == 64 || value == 128 || value == 256, "hb_set_option: gae_threads must be 0, 32, 64, 128 or 256");
+        hb::g_gae_threads = value;
+        return HB_OK;
+    }
     if (name && !strcmp(name, "pdl")) {
         hb::g_use_pdl = value;
         return HB_OK;

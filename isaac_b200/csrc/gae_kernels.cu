@@ -206,6 +206,38 @@ __device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long
     return v;
 }
 
+
+// The grid agrees on (sum, sum of squares): every block adds its pair to one of GAE_SLOTS slot pairs (blocks spread over the
+// slots, so that hundreds of fp64 atomics do not queue on one address), takes a ticket, spins until all blocks have (every
+// block is resident: the launch is sized to one wave), reads the slots and derives mean / unbiased std
+// (rollout_storage.py:136).  The last reader re-arms the scratch for the next launch.
+// scratch (HB_GAE_SCRATCH_DOUBLES = 32): [0..7] sums, [8..15] sums of squares, [16] ticket.  Called by one thread per block.
+constexpr int GAE_SLOTS = 8;
+__device__ __forceinline__ void grid_statistics(double *__restrict__ scratch, double a, double q, double n, float *s_norm) {
+    unsigned long long *ticket = reinterpret_cast<unsigned long long *>(scratch + 2 * GAE_SLOTS);
+    const int slot = blockIdx.x & (GAE_SLOTS - 1);
+    atomicAdd(scratch + slot, a);
+    atomicAdd(scratch + GAE_SLOTS + slot, q);
+    __threadfence();
+    atomicAdd(ticket, 1ull);
+    while (ld_acquire_u64(ticket) < (unsigned long long)gridDim.x) { }           // ---- grid barrier ----
+    const volatile double *sv = scratch;
+    double s1 = 0.0, s2 = 0.0;
+#pragma unroll
+    for (int k = 0; k < GAE_SLOTS; ++k) s1 += sv[k], s2 += sv[GAE_SLOTS + k];
+    const double mean = s1 / n;
+    double var = (s2 - n * mean * mean) / (n - 1.0);                             // unbiased (rollout_storage.py:136)
+    if (var < 0.0) var = 0.0;
+    s_norm[0] = (float)mean, s_norm[1] = (float)sqrt(var) + 1e-8f;
+    __threadfence();
+    if (atomicAdd(ticket, 1ull) == 2ull * gridDim.x - 1ull) {                    // every block has read: re-arm
+#pragma unroll
+        for (int k = 0; k < 2 * GAE_SLOTS; ++k) scratch[k] = 0.0;
+        __threadfence();
+        *ticket = 0ull;
+    }
+}
+
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS)
 gae_fused_kernel(const float *__restrict__ rewards, const float *__restrict__ values, const uint8_t *__restrict__ dones,
@@ -269,24 +301,7 @@ gae_fused_kernel(const float *__restrict__ rewards, const float *__restrict__ va
         double a = 0.0, q = 0.0;
 #pragma unroll
         for (int w = 0; w < THREADS / 32; ++w) a += red[0][w], q += red[1][w];
-        unsigned long long *ticket = reinterpret_cast<unsigned long long *>(scratch + 2);
-        atomicAdd(scratch, a);
-        atomicAdd(scratch + 1, q);
-        __threadfence();
-        atomicAdd(ticket, 1ull);
-        while (ld_acquire_u64(ticket) < (unsigned long long)gridDim.x) { }       // ---- grid barrier ----
-        const volatile double *sv = scratch;
-        const double n = (double)T * (double)N;
-        const double mean = sv[0] / n;
-        double var = (sv[1] - n * mean * mean) / (n - 1.0);                      // unbiased (rollout_storage.py:136)
-        if (var < 0.0) var = 0.0;
-        s_norm[0] = (float)mean, s_norm[1] = (float)sqrt(var) + 1e-8f;
-        __threadfence();
-        if (atomicAdd(ticket, 1ull) == 2ull * gridDim.x - 1ull) {                // every block has read: re-arm
-            scratch[0] = 0.0, scratch[1] = 0.0;
-            __threadfence();
-            *ticket = 0ull;
-        }
+        grid_statistics(scratch, a, q, (double)T * (double)N, s_norm);
     }
     __syncthreads();
     const float m = s_norm[0], denom = s_norm[1];
@@ -383,16 +398,23 @@ int hb_gae_fused(const float *rewards, const float *values, const uint8_t *dones
     cudaStream_t st = (cudaStream_t)stream;
     bool fits = false;
     int rc = HB_OK;
-    // narrow shards get narrow blocks so that the grid still covers the SMs
-    if (N <= 8192) rc = launch_gae_fused<32>(rewards, values, dones, last_values, returns, advantages, scratch, T, N, gamma, lam, st, &fits);
-    else if (N <= 16384) rc = launch_gae_fused<64>(rewards, values, dones, last_values, returns, advantages, scratch, T, N, gamma, lam, st, &fits);
-    else rc = launch_gae_fused<128>(rewards, values, dones, last_values, returns, advantages, scratch, T, N, gamma, lam, st, &fits);
+    // Block width: the launch's fixed cost is the grid barrier (two fp64 atomics, a ticket and a spin per block), so wide
+    // shards take wide blocks (65 536 envs: 13.6 us with 256 threads, 15.1 with 128, 19.8 with 64; 16 384 envs: 10.0 / 10.1 /
+    // 10.9), narrow ones enough blocks to spread the loads over the SMs (4096 envs: 9.1 us with 64 or 128, 9.6 with 32)
+    const int threads = hb::g_gae_threads ? hb::g_gae_threads : (N <= 8192 ? 64 : 256);
+#define HB_GAE(TH) launch_gae_fused<TH>(rewards, values, dones, last_values, returns, advantages, scratch, T, N, gamma, lam, st, &fits)
+    if (threads == 32) rc = HB_GAE(32);
+    else if (threads == 64) rc = HB_GAE(64);
+    else if (threads == 256) rc = HB_GAE(256);
+    else rc = HB_GAE(128);
+    if (!rc && !fits && threads == 256) rc = HB_GAE(128);      // long rollouts: 256 threads x T floats may not fit in shared memory
+#undef HB_GAE
     if (rc) return rc;
     if (fits) return HB_OK;
     // long rollouts / shards too wide for one co-resident grid: the two-kernel form (scratch doubles as the statistics)
     if (int rc2 = hb_gae_returns(rewards, values, dones, last_values, returns, advantages, scratch, T, N, gamma, lam, stream)) return rc2;
     if (int rc2 = hb_gae_normalize_n(advantages, scratch, (int64_t)T * N, (int64_t)T * N, stream)) return rc2;
-    HB_CUDA(cudaMemsetAsync(scratch, 0, 4 * sizeof(double), st));
+    HB_CUDA(cudaMemsetAsync(scratch, 0, HB_GAE_SCRATCH_DOUBLES * sizeof(double), st));
     return HB_OK;
 }
 

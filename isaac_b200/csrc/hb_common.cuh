@@ -51,6 +51,7 @@ extern int g_use_pdl;   // "pdl" option: programmatic stream serialization of th
                         // round 2, 4096 envs: 43.1 (default) / 49.2 (3) / 43.4 (4) / 49.4 (1) us per step; 16 384 envs:
                         // 73.0 / 77.5 / 78.7 / 79.4
 extern int g_gae_serial_min_envs;   // "gae_serial_min_envs" option: shards at least this wide run GAE one thread per env (default 8192)
+extern int g_gae_threads;   // "gae_threads" option: block width of the single-launch GAE (0 = by shard width; 32 / 64 / 128 / 256)
 extern int g_coop_launch;   // "coop_launch" option: 1 = kernels with a grid barrier (optimizer step, single-launch GAE) are launched with the
                             // cooperative attribute; 0 (default) = plain launches of a grid that fits the device (see hector_b200.h)
 extern int g_gemm_snake;  // "gemm_tile_snake" option: 1 (default) = rounds of the GEMM tile list are dealt to the CTAs in alternating direction
