@@ -76,14 +76,16 @@ for k in range(1, total + 1):
     g = _lib.LaunchGraph(dev).record(lambda st: step())
     for _ in range(3):
         g.replay(stream.cuda_stream)
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    reps = 30
-    a.record(stream)
-    for _ in range(reps):
-        g.replay(stream.cuda_stream)
-    b.record(stream)
-    b.synchronize()
-    times.append(a.elapsed_time(b) * 1e3 / reps)
+    reps, best = 30, 1e9
+    for _ in range(4):                          # best of 4 series: a series that starts on ramping clocks reads long
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        for _ in range(reps):
+            g.replay(stream.cuda_stream)
+        b.record(stream)
+        b.synchronize()
+        best = min(best, a.elapsed_time(b) * 1e3 / reps)
+    times.append(best)
 prev = 0.0
 print(f"one minibatch step at {n} envs x {bench.T_GAE} steps ({n * bench.T_GAE // 4} rows): marginal time of each launch in place")
 for k, (nm, t) in enumerate(zip(names, times), 1):
