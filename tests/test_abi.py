@@ -53,6 +53,9 @@ def test_bad_arguments_return_status_not_crash(lib):
     assert lib.hb_ppo_act_fused(None, 132, None, 132, None, None, 132, None, None, 8, 10, None, None, None, None, None, None) == -1
     assert lib.hb_ppo_record_step(None, None, None, None, 0.99, 8, None, None, None) == -1
     assert lib.hb_optimizer_step(None, None, None, None, 8, None, None, None) == -1
+    assert lib.hb_copy_rows(None, 64, None, 64, 32, 4, None) == -1 and b"hb_copy_rows" in lib.hb_last_error()
+    assert lib.hb_gae_fused(None, None, None, None, None, None, None, 4, 4, 0.99, 0.95, None) == -1
+    assert lib.hb_set_option(b"gae_threads", 48) == -1 and lib.hb_set_option(b"gae_threads", 0) == 0
     d = _lib.GemmDesc()
     assert lib.hb_gemm_tf32(ctypes.byref(d), None) == -1 and b"null" in lib.hb_last_error()
     p, b = _lib.EnvParams(), _lib.EnvBuffers()

@@ -76,3 +76,23 @@ def test_gae_properties_full_size(lib, cuda_device):
     assert abs(float(adv.double().mean())) < 1e-5 and abs(float(adv.double().std()) - 1.0) < 1e-4
     term = dones.bool()
     assert_close("terminal step return", ret[term].numpy(), rewards[term].numpy(), rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize("threads", [32, 64, 128, 256])
+def test_gae_block_widths_agree(lib, cuda_device, threads):
+    """The single-launch kernel at every block width ("gae_threads"; the library picks 64 or 256 by shard width): returns
+    are the same bits (one thread per env, the reference's operation order), the normalised advantages agree to fp32
+    rounding of the statistics (fp64 atomics in a different order).  Ragged shard (N not a multiple of any width)."""
+    T, N = 24, 4096 + 37
+    g = torch.Generator().manual_seed(threads)
+    rewards, values = torch.rand(T, N, 1, generator=g), torch.randn(T, N, 1, generator=g)
+    dones, last = (torch.rand(T, N, 1, generator=g) < 0.05).byte(), torch.randn(N, 1, generator=g)
+    want_ret, want_adv = gae_returns(rewards, values, dones, last, 0.994, 0.9)
+    assert lib.hb_set_option(b"gae_threads", threads) == 0
+    try:
+        for rep in range(2):          # twice: the launch re-arms its own scratch (8 slot pairs + ticket)
+            ret, adv = run_cuda_gae(lib, cuda_device, rewards, values, dones, last, 0.994, 0.9, fused=True)
+            assert torch.equal(ret, want_ret)
+            assert_close("advantages", adv.numpy(), want_adv.numpy(), rtol=1e-5, atol=1e-5)
+    finally:
+        lib.hb_set_option(b"gae_threads", 0)
