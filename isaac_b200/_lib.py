@@ -251,15 +251,25 @@ class LaunchGraph:
         self._stream = s
 
     def record(self, fn) -> "LaunchGraph":
+        import gc
         import torch
         torch.cuda.synchronize(self._device)
         handle = self._stream.cuda_stream
-        with torch.cuda.stream(self._stream):       # code that asks torch for the current stream lands on the capture stream
-            check(self._lib.hb_graph_begin(handle), "hb_graph_begin")
-            try:
-                fn(handle)
-            finally:
-                rc = self._lib.hb_graph_end(handle, C.byref(self._exec))
+        # No cyclic garbage collection while the stream is capturing: a collection that happens to run inside the capture
+        # destroys whatever unreachable CUDA objects earlier code left behind (graphs, streams, pinned buffers) from this
+        # thread, and a call that is not capturable invalidates the capture ("previous error during capture").
+        gc_was_on = gc.isenabled()
+        gc.disable()
+        try:
+            with torch.cuda.stream(self._stream):       # code that asks torch for the current stream lands on the capture stream
+                check(self._lib.hb_graph_begin(handle), "hb_graph_begin")
+                try:
+                    fn(handle)
+                finally:
+                    rc = self._lib.hb_graph_end(handle, C.byref(self._exec))
+        finally:
+            if gc_was_on:
+                gc.enable()
         check(rc, "hb_graph_end")
         return self
 
