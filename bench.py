@@ -643,10 +643,11 @@ def run_b200(args, rank, world):
         if i >= 1:
             consume(slot ^ 1)                        # hand step i-1's results to the caller
 
-    def e2e_run(k):
+    def e2e_run(k, step_fn=None, last=None):
+        step_fn = step_fn or e2e_step
         for i in range(k):
-            e2e_step(i)
-        consume((k - 1) & 1)                         # the last step's results
+            step_fn(i)
+        (last or consume)((k - 1) & 1)               # the last step's results
         torch.cuda.synchronize(dev)
 
     e2e_run(max(4, args.warmup))
@@ -654,17 +655,79 @@ def run_b200(args, rank, world):
     t0 = time.perf_counter()
     e2e_run(args.steps)
     barrier()
+    e2e_full_wall = time.perf_counter() - t0
+
+    # ---- e2e through the host mirror (isaac_b200.envs.host_mirror): the same host-visible results - obs / privileged obs
+    # as [N, 615] / [N, 1050] host tensors, rewards, resets - but only the NEWEST frames cross PCIe: a step's stack is the
+    # previous one shifted by a frame, so the GPU appends the new frames to per-env rings in pinned memory and the
+    # stacked observations are strided views of those rings.  Same pipeline: step k+1 is enqueued before the caller
+    # reads step k; the mirror's views are valid until the next update, so step k is consumed before update k+1 is enqueued.
+    from isaac_b200.envs.host_mirror import HostObservationMirror
+    mirror = HostObservationMirror(env, use_dma=os.environ.get("HB_MIRROR_DMA", "1") != "0")
+    small_host = [[torch.empty(n).pin_memory(), torch.empty(n, dtype=torch.bool).pin_memory()] for _ in range(2)]
+    reset_snap = [torch.empty(n, dtype=torch.bool, device=dev) for _ in range(2)]
+    views = [None, None]
+
+    def consume_mirror(slot):
+        mirror.synchronize()
+        ho, hp = views[slot]
+        checksum[0] += float(small_host[slot][0][0]) + float(ho[0, -1]) + float(hp[n - 1, 0])
+
+    trace = [0.0] * 6 if os.environ.get("HB_E2E_TRACE") else None
+
+    def e2e_mirror_step(i):
+        f, slot = i % frames, i & 1
+        t_0 = time.perf_counter()
+        if i >= 2:
+            stream.wait_event(ev_copied[slot])       # step i reuses the observation buffers update i-2 read
+        phys.load_frame(host_frames[f])
+        act_dev.copy_(host_actions[f], non_blocking=True)
+        t_1 = time.perf_counter()
+        out = env.step(act_dev)
+        t_2 = time.perf_counter()
+        small_host[slot][0].copy_(out[2], non_blocking=True)
+        small_host[slot][1].copy_(out[3], non_blocking=True)
+        reset_snap[slot].copy_(out[3], non_blocking=True)      # the next step overwrites reset_buf while the mirror still reads it
+        ev_step[slot].record(stream)
+        t_3 = time.perf_counter()
+        if i >= 1:
+            consume_mirror(slot ^ 1)                 # the caller reads step i-1 (its views die with the next update)
+        t_4 = time.perf_counter()
+        copy_stream.wait_event(ev_step[slot])
+        torch.cuda.set_stream(copy_stream)
+        views[slot] = mirror.update(out[0], out[1], reset_snap[slot])
+        ev_copied[slot].record(copy_stream)
+        torch.cuda.set_stream(stream)
+        if trace is not None:
+            t_5 = time.perf_counter()
+            for q, (a_, b_) in enumerate(((t_0, t_1), (t_1, t_2), (t_2, t_3), (t_3, t_4), (t_4, t_5))):
+                trace[q] += b_ - a_
+            trace[5] += 1
+
+    torch.cuda.synchronize(dev)
+    mirror.resync(env.get_observations(), env.get_privileged_observations())
+    e2e_run(max(4, args.warmup), e2e_mirror_step, consume_mirror)
+    # the mirrored views equal the device tensors (checked here on the last warm-up step, and step by step in tests/test_host_mirror.py)
+    assert torch.equal(views[(max(4, args.warmup) - 1) & 1][0], env.get_observations().cpu()), "host mirror differs from the device stack"
+    barrier()
+    t0 = time.perf_counter()
+    e2e_run(args.steps, e2e_mirror_step, consume_mirror)
+    barrier()
     e2e_wall = time.perf_counter() - t0
+    if trace is not None and rank == 0:
+        print("e2e host time per step (us): inputs %.1f | env.step %.1f | small copies %.1f | consume (wait) %.1f | mirror.update %.1f" %
+              tuple(1e6 * v / trace[5] for v in trace[:5]), file=sys.stderr, flush=True)
     h2d = sum(t.numel() * t.element_size() for t in (host_frames[0].root_states, host_frames[0].dof_state,
                                                       host_frames[0].contact_forces, host_frames[0].rigid_state,
                                                       host_actions[0]))
-    d2h = sum(t.numel() * t.element_size() for t in out_host[0])
+    d2h_full = sum(t.numel() * t.element_size() for t in out_host[0])
+    d2h = mirror.bytes_per_update + sum(t.numel() * t.element_size() for t in small_host[0])
 
-    t = torch.tensor([dev_ms, wall, e2e_wall, k_priv, k_obs, k_pd, k_gae, k_post, k_stack, k_fin, k_stack_single],
+    t = torch.tensor([dev_ms, wall, e2e_wall, k_priv, k_obs, k_pd, k_gae, k_post, k_stack, k_fin, k_stack_single, e2e_full_wall],
                      dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, wall, e2e_wall, k_priv, k_obs, k_pd, k_gae, k_post, k_stack, k_fin, k_stack_single = t.tolist()
+    dev_ms, wall, e2e_wall, k_priv, k_obs, k_pd, k_gae, k_post, k_stack, k_fin, k_stack_single, e2e_full_wall = t.tolist()
     if rank != 0:
         return
     peak, peak_src = peaks()
@@ -714,8 +777,18 @@ def run_b200(args, rank, world):
     line["e2e"] = {"value": total_envs * args.steps / e2e_wall, "unit": "env-steps/s", "h2d_bytes_per_step": h2d,
                    "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_wall / args.steps,
                    "d2h_gbs_per_gpu": d2h * args.steps / e2e_wall / 1e9,
-                   "pipeline": "obs / privileged obs of step k leave on a copy stream into double-buffered pinned memory "
-                               "while step k+1 runs; the host waits per buffer set; CPU affinity = the GPU's NUMA node"}
+                   "pipeline": "HostObservationMirror (isaac_b200/envs/host_mirror.py): every step's inputs come from pinned host "
+                               "memory, its results are host tensors - rewards / resets copied, obs [N,615] / privileged obs "
+                               "[N,1050] as strided views of pinned per-env frame rings to which the GPU appends only the step's "
+                               "NEWEST frames (hb_env_mirror_frames, 2-D DMA copies: a stack is the previous one shifted by a frame); bit-equal to "
+                               "the device tensors (asserted in this run, tests/test_host_mirror.py); step k+1 is enqueued before "
+                               "the caller reads step k; CPU affinity = the GPU's NUMA node",
+                   "full_stack_copy": {"value": total_envs * args.steps / e2e_full_wall, "unit": "env-steps/s",
+                                       "d2h_bytes_per_step": d2h_full, "ms_per_step": 1e3 * e2e_full_wall / args.steps,
+                                       "d2h_gbs_per_gpu": d2h_full * args.steps / e2e_full_wall / 1e9,
+                                       "pipeline": "the whole obs / privileged-obs stacks of step k leave by DMA (hb_copy_rows) into "
+                                                   "double-buffered dense pinned tensors while step k+1 runs (what the reference's "
+                                                   "obs.to(rl_device) moves, on_policy_runner.py:136)"}}
     print(json.dumps(line), flush=True)
 
 

@@ -308,6 +308,23 @@ int hb_env_get_heights(const float *root_states, const float *points_xy, int32_t
                        int32_t rows, int32_t cols, float border_size, float horizontal_scale, float vertical_scale,
                        const int32_t *env_ids, int64_t count, float *heights, void *stream);
 
+/* Host mirror of the stacked observations for a consumer on the CPU (rl_device = cpu; on_policy_runner.py:136 moves obs
+ * and critic_obs to the learner's device every step).  Only the newest frame of a step's [N, S*F] stack is new, so the
+ * GPU sends just that: host_*_ring are PINNED HOST buffers [N, slots + S - 1, frame] (device-accessible: cudaHostAlloc /
+ * torch pin_memory under unified addressing); the kernel stores the newest frame of every env - the last `frame` columns
+ * of its row - at ring slot `slot` and, when slot < S - 1, also at `slot + slots`, so that the last S frames of an env
+ * are one contiguous run and its stacked observation is a strided view of the ring (row pitch (slots + S - 1) * frame
+ * floats; the caller advances slot = k mod slots and needs slots >= S + 1; the window of the last S frames starts at slot
+ * a - (S - 1) if a >= S - 1, else a + slots - (S - 1), a = the slot just written).  Envs whose reset_buf byte is set get
+ * the rest of their rings zeroed first (reset_idx clears the history, hector_env.py:256-261); reset_buf may be NULL.
+ * use_dma != 0: the frames travel as 2-D copies of the copy engine (one or two per history) and the kernel only zeroes
+ * the rings of reset envs; 0: the kernel stores the frames itself.  1.8 - 3.6 MB per step over PCIe instead of 27 MB at
+ * 4096 hector envs.  The views of a step are valid until the next call. */
+int hb_env_mirror_frames(const float *obs, int32_t obs_ld, int32_t obs_row, int32_t obs_frame, const float *priv, int32_t priv_ld,
+                         int32_t priv_row, int32_t priv_frame, const uint8_t *reset_buf, int32_t num_envs, float *host_obs_ring,
+                         int32_t obs_slots, int32_t obs_slot, float *host_priv_ring, int32_t priv_slots, int32_t priv_slot, int32_t use_dma,
+                         void *stream);
+
 /* One frame-stack shift on its own, dense rows: next[:, 0:row-frame] = prev[:, frame:row] (zeros for envs whose
  * reset_buf byte is set, if reset_buf is not NULL); next[:, row-frame:row] is left alone. */
 int hb_stack_shift(const float *prev, float *next, const uint8_t *reset_buf, int32_t num_envs, int32_t row,

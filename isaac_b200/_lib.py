@@ -175,6 +175,8 @@ _SIGNATURES = {
                                      C.c_int64, _fp, _fp]),
     "hb_stack_shift": (C.c_int, [_fp, _fp, _fp, C.c_int32, C.c_int32, C.c_int32, _fp]),
     "hb_copy_rows": (C.c_int, [_fp, C.c_int64, _fp, C.c_int64, C.c_int64, C.c_int64, _fp]),
+    "hb_env_mirror_frames": (C.c_int, [_fp, C.c_int32, C.c_int32, C.c_int32, _fp, C.c_int32, C.c_int32, C.c_int32, _fp, C.c_int32, _fp,
+                                       C.c_int32, C.c_int32, _fp, C.c_int32, C.c_int32, C.c_int32, _fp]),
     "hb_gemm_tf32": (C.c_int, [C.POINTER(GemmDesc), _fp]),
     "hb_gemm_workspace_floats": (C.c_int64, [C.POINTER(GemmDesc)]),
     "hb_gemm_tf32_grouped": (C.c_int, [C.POINTER(GemmDesc), C.POINTER(GemmDesc), _fp]),

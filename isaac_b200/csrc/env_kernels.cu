@@ -1330,6 +1330,51 @@ get_heights_kernel(const float *__restrict__ root_states, const float *__restric
     out[i] = (float)h * vscale;
 }
 
+// ------------------------------------------------------------------------------------------
+// Host mirror of the stacked observations (a consumer on the CPU, rl_device = cpu: on_policy_runner.py:136 moves obs and
+// critic_obs to the learner's device every step).  Of a step's [N, S*F] stack only the newest frame is new - the rest is
+// the previous stack shifted by one frame - so instead of 27 MB per step (4096 hector envs) the GPU sends the newest
+// frames: per env a ring of C + S - 1 frame slots in PINNED HOST memory (C >= S + 1); frame k goes to slot k mod C and,
+// when that slot is one of the first S - 1, also to slot k mod C + C, so that the last S frames are always one contiguous
+// run of S*F floats: the stacked observation of env n is a strided VIEW of the ring (row pitch (C + S - 1) * F floats),
+// with nothing to move on the host.  The kernel stores straight into the mapped host rings over PCIe (one warp per env);
+// for an env that the step reset, the other slots of its rings are zeroed first (reset_idx clears the history:
+// hector_env.py:256-261).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+mirror_frames_kernel(const float *__restrict__ obs, int obs_ld, int row_a, int fa, const float *__restrict__ priv, int priv_ld, int row_b,
+                     int fb, const uint8_t *__restrict__ reset_buf, int n, float *__restrict__ ring_a, int ca, int slot_a,
+                     float *__restrict__ ring_b, int cb, int slot_b, int zero_only) {
+    const int lane = threadIdx.x & 31, env = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (env >= n) return;
+    const int sa = row_a / fa, sb = row_b / fb;                      // frames per stack
+    const int na = ca + sa - 1, nb = cb + sb - 1;                    // slots per ring
+    const int dup_a = slot_a < sa - 1 ? slot_a + ca : -1, dup_b = slot_b < sb - 1 ? slot_b + cb : -1;
+    float *ra = ring_a + (size_t)env * na * fa, *rb = ring_b + (size_t)env * nb * fb;
+    if (reset_buf && reset_buf[env]) {          // every slot but those that receive the new frame (disjoint addresses: no ordering needed)
+        for (int i = lane; i < na * fa; i += 32) {
+            const int sl = i / fa;
+            if (sl != slot_a && sl != dup_a) ra[i] = 0.0f;
+        }
+        for (int i = lane; i < nb * fb; i += 32) {
+            const int sl = i / fb;
+            if (sl != slot_b && sl != dup_b) rb[i] = 0.0f;
+        }
+    }
+    if (zero_only) return;                      // the frames travel by DMA (hb_copy_rows) in this mode
+    const float *oa = obs + (size_t)env * obs_ld + (row_a - fa), *ob = priv + (size_t)env * priv_ld + (row_b - fb);
+    for (int i = lane; i < fa; i += 32) {
+        const float v = oa[i];
+        ra[slot_a * fa + i] = v;
+        if (dup_a >= 0) ra[dup_a * fa + i] = v;
+    }
+    for (int i = lane; i < fb; i += 32) {
+        const float v = ob[i];
+        rb[slot_b * fb + i] = v;
+        if (dup_b >= 0) rb[dup_b * fb + i] = v;
+    }
+}
+
 int g_use_bulk = 1;
 
 // Frame stacks of the three tasks (hector_config.py:8-20, hector_w_arm_config.py:8-20, humanoid_config.py:42-52): rows
@@ -1684,6 +1729,44 @@ int hb_env_stack_finalize(const hb_env_params *p, const hb_env_buffers *buf, con
                            blocks_a, priv_prev, priv_new, total_b, blocks_b, *p, *buf, tiles, seg, host_count,
                            reinterpret_cast<unsigned long long *>(rng_counter)));
     HB_CHECK_LAUNCH("stack_finalize_kernel");
+    return HB_OK;
+}
+
+int hb_env_mirror_frames(const float *obs, int32_t obs_ld, int32_t obs_row, int32_t obs_frame, const float *priv, int32_t priv_ld,
+                         int32_t priv_row, int32_t priv_frame, const uint8_t *reset_buf, int32_t num_envs, float *host_obs_ring,
+                         int32_t obs_slots, int32_t obs_slot, float *host_priv_ring, int32_t priv_slots, int32_t priv_slot, int32_t use_dma,
+                         void *stream) {
+    HB_REQUIRE(obs && priv && host_obs_ring && host_priv_ring && num_envs > 0, "hb_env_mirror_frames: null buffer");
+    HB_REQUIRE(obs_frame > 0 && obs_row >= obs_frame && obs_ld >= obs_row && priv_frame > 0 && priv_row >= priv_frame && priv_ld >= priv_row,
+               "hb_env_mirror_frames: bad row shapes");
+    HB_REQUIRE(obs_row % obs_frame == 0 && priv_row % priv_frame == 0, "hb_env_mirror_frames: a row is a whole number of frames");
+    HB_REQUIRE(obs_slots * obs_frame > obs_row && priv_slots * priv_frame > priv_row && obs_slot >= 0 && obs_slot < obs_slots &&
+                   priv_slot >= 0 && priv_slot < priv_slots,
+               "hb_env_mirror_frames: a ring needs more slots than the stack has frames (C >= S + 1), slot index inside [0, C)");
+    const int warps = 8;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (use_dma) {          // frames by the copy engine (2-D copies with frame-wide rows), the kernel only zeroes the rings of reset envs
+        if (reset_buf) {
+            mirror_frames_kernel<<<(num_envs + warps - 1) / warps, warps * 32, 0, st>>>(
+                obs, obs_ld, obs_row, obs_frame, priv, priv_ld, priv_row, priv_frame, reset_buf, num_envs, host_obs_ring, obs_slots, obs_slot,
+                host_priv_ring, priv_slots, priv_slot, 1);
+        }
+        const int sa = obs_row / obs_frame, sb = priv_row / priv_frame;
+        const size_t pitch_a = (size_t)(obs_slots + sa - 1) * obs_frame * 4, pitch_b = (size_t)(priv_slots + sb - 1) * priv_frame * 4;
+        auto dma = [&](float *ring, size_t pitch, int slot, int frame, const float *src, int ld, int row) {
+            return cudaMemcpy2DAsync(ring + (size_t)slot * frame, pitch, src + (row - frame), (size_t)ld * 4, (size_t)frame * 4, (size_t)num_envs,
+                                     cudaMemcpyDeviceToHost, st);
+        };
+        HB_CUDA(dma(host_obs_ring, pitch_a, obs_slot, obs_frame, obs, obs_ld, obs_row));
+        if (obs_slot < sa - 1) HB_CUDA(dma(host_obs_ring, pitch_a, obs_slot + obs_slots, obs_frame, obs, obs_ld, obs_row));
+        HB_CUDA(dma(host_priv_ring, pitch_b, priv_slot, priv_frame, priv, priv_ld, priv_row));
+        if (priv_slot < sb - 1) HB_CUDA(dma(host_priv_ring, pitch_b, priv_slot + priv_slots, priv_frame, priv, priv_ld, priv_row));
+        return HB_OK;
+    }
+    mirror_frames_kernel<<<(num_envs + warps - 1) / warps, warps * 32, 0, st>>>(
+        obs, obs_ld, obs_row, obs_frame, priv, priv_ld, priv_row, priv_frame, reset_buf, num_envs, host_obs_ring, obs_slots, obs_slot,
+        host_priv_ring, priv_slots, priv_slot, 0);
+    HB_CHECK_LAUNCH("mirror_frames_kernel");
     return HB_OK;
 }
 
