@@ -660,17 +660,17 @@ def run_b200(args, rank, world):
     # ---- e2e through the host mirror (isaac_b200.envs.host_mirror): the same host-visible results - obs / privileged obs
     # as [N, 615] / [N, 1050] host tensors, rewards, resets - but only the NEWEST frames cross PCIe: a step's stack is the
     # previous one shifted by a frame, so the GPU appends the new frames to per-env rings in pinned memory and the
-    # stacked observations are strided views of those rings.  Same pipeline: step k+1 is enqueued before the caller
-    # reads step k; the mirror's views are valid until the next update, so step k is consumed before update k+1 is enqueued.
+    # stacked observations are strided views of those rings.  Same pipeline: step k+1 and its frame copies are enqueued
+    # before the caller reads step k (the GPU never rewrites slots that an earlier step's views still show).
     from isaac_b200.envs.host_mirror import HostObservationMirror
     mirror = HostObservationMirror(env, use_dma=os.environ.get("HB_MIRROR_DMA", "1") != "0")
     small_host = [[torch.empty(n).pin_memory(), torch.empty(n, dtype=torch.bool).pin_memory()] for _ in range(2)]
     reset_snap = [torch.empty(n, dtype=torch.bool, device=dev) for _ in range(2)]
-    views = [None, None]
+    tickets = [None, None]
+    last_views = [None]
 
-    def consume_mirror(slot):
-        mirror.synchronize()
-        ho, hp = views[slot]
+    def consume_mirror(slot):          # the caller's read of a finished step: waits for that step's frames only
+        ho, hp = last_views[0] = mirror.views(tickets[slot])
         checksum[0] += float(small_host[slot][0][0]) + float(ho[0, -1]) + float(hp[n - 1, 0])
 
     trace = [0.0] * 6 if os.environ.get("HB_E2E_TRACE") else None
@@ -687,17 +687,17 @@ def run_b200(args, rank, world):
         t_2 = time.perf_counter()
         small_host[slot][0].copy_(out[2], non_blocking=True)
         small_host[slot][1].copy_(out[3], non_blocking=True)
-        reset_snap[slot].copy_(out[3], non_blocking=True)      # the next step overwrites reset_buf while the mirror still reads it
+        reset_snap[slot].copy_(out[3], non_blocking=True)      # the next step overwrites reset_buf while the copy stream still reads it
         ev_step[slot].record(stream)
         t_3 = time.perf_counter()
-        if i >= 1:
-            consume_mirror(slot ^ 1)                 # the caller reads step i-1 (its views die with the next update)
-        t_4 = time.perf_counter()
         copy_stream.wait_event(ev_step[slot])
         torch.cuda.set_stream(copy_stream)
-        views[slot] = mirror.update(out[0], out[1], reset_snap[slot])
+        tickets[slot] = mirror.update(out[0], out[1], reset_snap[slot])
         ev_copied[slot].record(copy_stream)
         torch.cuda.set_stream(stream)
+        t_4 = time.perf_counter()
+        if i >= 1:
+            consume_mirror(slot ^ 1)                 # the caller reads step i-1 while step i's frames are on their way
         if trace is not None:
             t_5 = time.perf_counter()
             for q, (a_, b_) in enumerate(((t_0, t_1), (t_1, t_2), (t_2, t_3), (t_3, t_4), (t_4, t_5))):
@@ -708,14 +708,14 @@ def run_b200(args, rank, world):
     mirror.resync(env.get_observations(), env.get_privileged_observations())
     e2e_run(max(4, args.warmup), e2e_mirror_step, consume_mirror)
     # the mirrored views equal the device tensors (checked here on the last warm-up step, and step by step in tests/test_host_mirror.py)
-    assert torch.equal(views[(max(4, args.warmup) - 1) & 1][0], env.get_observations().cpu()), "host mirror differs from the device stack"
+    assert torch.equal(last_views[0][0], env.get_observations().cpu()), "host mirror differs from the device stack"
     barrier()
     t0 = time.perf_counter()
     e2e_run(args.steps, e2e_mirror_step, consume_mirror)
     barrier()
     e2e_wall = time.perf_counter() - t0
     if trace is not None and rank == 0:
-        print("e2e host time per step (us): inputs %.1f | env.step %.1f | small copies %.1f | consume (wait) %.1f | mirror.update %.1f" %
+        print("e2e host time per step (us): inputs %.1f | env.step %.1f | small copies %.1f | mirror.update %.1f | consume (wait) %.1f" %
               tuple(1e6 * v / trace[5] for v in trace[:5]), file=sys.stderr, flush=True)
     h2d = sum(t.numel() * t.element_size() for t in (host_frames[0].root_states, host_frames[0].dof_state,
                                                       host_frames[0].contact_forces, host_frames[0].rigid_state,
@@ -781,8 +781,8 @@ def run_b200(args, rank, world):
                                "memory, its results are host tensors - rewards / resets copied, obs [N,615] / privileged obs "
                                "[N,1050] as strided views of pinned per-env frame rings to which the GPU appends only the step's "
                                "NEWEST frames (hb_env_mirror_frames, 2-D DMA copies: a stack is the previous one shifted by a frame); bit-equal to "
-                               "the device tensors (asserted in this run, tests/test_host_mirror.py); step k+1 is enqueued before "
-                               "the caller reads step k; CPU affinity = the GPU's NUMA node",
+                               "the device tensors (asserted in this run, tests/test_host_mirror.py); step k+1 and its frame copies are "
+                               "enqueued before the caller reads step k; CPU affinity = the GPU's NUMA node",
                    "full_stack_copy": {"value": total_envs * args.steps / e2e_full_wall, "unit": "env-steps/s",
                                        "d2h_bytes_per_step": d2h_full, "ms_per_step": 1e3 * e2e_full_wall / args.steps,
                                        "d2h_gbs_per_gpu": d2h_full * args.steps / e2e_full_wall / 1e9,

@@ -10,8 +10,10 @@ from test_env_parity import make_cuda_env
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("n,steps", [(257, 40), (4096, 6)])
-def test_host_views_equal_device_stacks(lib, cuda_device, n, steps):
+@pytest.mark.parametrize("n,steps,lag", [(257, 40, 0), (257, 40, 3), (4096, 6, 1)])
+def test_host_views_equal_device_stacks(lib, cuda_device, n, steps, lag):
+    """`lag` updates stay outstanding before their views are read (a pipelined consumer): the views of a step must still
+    equal that step's device tensors although later steps' frames - and later resets - are already on their way."""
     from isaac_b200.envs.host_mirror import HostObservationMirror
     dev = cuda_device
     tape = make_tape(n, 8, seed=5 + n, fall_prob=0.1)
@@ -21,17 +23,22 @@ def test_host_views_equal_device_stacks(lib, cuda_device, n, steps):
     ho, hp = mirror.views()
     assert torch.equal(ho, env.get_observations().cpu()) and torch.equal(hp, env.get_privileged_observations().cpu())
     assert ho.shape == (n, 615) and ho.stride(1) == 1 and ho.stride(0) > 615, "a strided view of the ring, not a copy"
-    resets = 0
+    resets, pending = 0, []
     for k in range(steps):
         phys.load_frame(tape.physics[1 + k % 7].to(dev))
         obs, priv, rew, reset, _ = env.step(tape.noise[1 + k % 7].actions.to(dev))
-        ho, hp = mirror.update(obs, priv)
-        mirror.synchronize()
-        assert torch.equal(ho, obs.cpu()), f"step {k}"
-        assert torch.equal(hp, priv.cpu()), f"step {k}"
+        pending.append((mirror.update(obs, priv), obs.cpu(), priv.cpu()))
         resets += int(reset.sum())
+        while len(pending) > lag:
+            ticket, want_o, want_p = pending.pop(0)
+            ho, hp = mirror.views(ticket)
+            assert torch.equal(ho, want_o), f"step {k}, ticket {ticket}"
+            assert torch.equal(hp, want_p), f"step {k}, ticket {ticket}"
     assert resets > 0, "the case must exercise resets"
-    assert n * 111 * 4 < mirror.bytes_per_update < 2 * n * 111 * 4
+    assert n * 111 * 4 < mirror.bytes_per_update < 2 * n * 111 * 4 + n + 1
+    with pytest.raises(RuntimeError):
+        for _ in range(40):
+            mirror.update(obs, priv)
 
 
 def test_short_critic_stack_and_generic_shapes(lib, cuda_device):
