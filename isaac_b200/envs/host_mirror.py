@@ -28,6 +28,23 @@ import torch
 from .. import _lib
 
 
+def window_start(a: int, c: int, s: int) -> int:
+    """First slot of the contiguous run that holds the last s frames when the newest one sits in slot a of a ring of c
+    (+ s - 1 duplicated head slots)."""
+    return a - (s - 1) if a >= s - 1 else a + c - (s - 1)
+
+
+def history_slots(k: int, c: int, s: int) -> list:
+    """Every ring slot (both copies) that holds one of the s - 1 frames before frame number k - 1: what a reset zeroes."""
+    slots = []
+    for j in range(1, s):
+        sl = (k - 1 - j) % c
+        slots.append(sl)
+        if sl < s - 1:
+            slots.append(sl + c)
+    return slots
+
+
 class HostObservationMirror:
     def __init__(self, env, spare: int = 17, use_dma: bool = True):
         if spare < 2:
@@ -61,8 +78,7 @@ class HostObservationMirror:
     # ------------------------------------------------------------------ views
     def _window(self, ring, c, s, f, k):
         """The strided [N, s*f] view of the last s frames after k appended frames (k >= 1)."""
-        a = (k - 1) % c
-        start = a - (s - 1) if a >= s - 1 else a + c - (s - 1)
+        start = window_start((k - 1) % c, c, s)
         return torch.as_strided(ring, (self.num_envs, s * f), ((c + s - 1) * f, 1), storage_offset=start * f)
 
     def _views_at(self, k):
@@ -76,13 +92,7 @@ class HostObservationMirror:
     def _zero_history(self, ids, k):
         """Rows `ids` were reset by the step whose frame is number k - 1: the S - 1 frames before it become zeros (both copies)."""
         for ring, c, s in ((self._ring_a, self._ca, self._sa), (self._ring_b, self._cb, self._sb)):
-            slots = []
-            for j in range(1, s):
-                sl = (k - 1 - j) % c
-                slots.append(sl)
-                if sl < s - 1:
-                    slots.append(sl + c)
-            ring[ids[:, None], torch.tensor(slots)[None, :]] = 0.0
+            ring[ids[:, None], torch.tensor(history_slots(k, c, s))[None, :]] = 0.0
 
     def views(self, ticket: int | None = None):
         """(obs, privileged_obs) host tensors of the step behind `ticket` (default: the latest update): waits for its frames,
