@@ -317,7 +317,8 @@ int hb_env_get_heights(const float *root_states, const float *points_xy, int32_t
  * floats; the caller advances slot = k mod slots and needs slots >= S + 1; the window of the last S frames starts at slot
  * a - (S - 1) if a >= S - 1, else a + slots - (S - 1), a = the slot just written).  Envs whose reset_buf byte is set get
  * the rest of their rings zeroed first (reset_idx clears the history, hector_env.py:256-261); reset_buf may be NULL.
- * use_dma != 0: the frames travel as 2-D copies of the copy engine (one or two per history) and the kernel only zeroes
+ * obs or priv may be NULL: that history is left to another call (e.g. one by the copy engine, one by a kernel on a second
+ * stream).  use_dma != 0: the frames travel as 2-D copies of the copy engine (one or two per history) and the kernel only zeroes
  * the rings of reset envs; 0: the kernel stores the frames itself.  1.8 - 3.6 MB per step over PCIe instead of 27 MB at
  * 4096 hector envs.  The views of a step are valid until the next call. */
 int hb_env_mirror_frames(const float *obs, int32_t obs_ld, int32_t obs_row, int32_t obs_frame, const float *priv, int32_t priv_ld,

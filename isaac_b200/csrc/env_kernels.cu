@@ -1352,26 +1352,31 @@ mirror_frames_kernel(const float *__restrict__ obs, int obs_ld, int row_a, int f
     const int dup_a = slot_a < sa - 1 ? slot_a + ca : -1, dup_b = slot_b < sb - 1 ? slot_b + cb : -1;
     float *ra = ring_a + (size_t)env * na * fa, *rb = ring_b + (size_t)env * nb * fb;
     if (reset_buf && reset_buf[env]) {          // every slot but those that receive the new frame (disjoint addresses: no ordering needed)
-        for (int i = lane; i < na * fa; i += 32) {
+        for (int i = lane; obs && i < na * fa; i += 32) {
             const int sl = i / fa;
             if (sl != slot_a && sl != dup_a) ra[i] = 0.0f;
         }
-        for (int i = lane; i < nb * fb; i += 32) {
+        for (int i = lane; priv && i < nb * fb; i += 32) {
             const int sl = i / fb;
             if (sl != slot_b && sl != dup_b) rb[i] = 0.0f;
         }
     }
     if (zero_only) return;                      // the frames travel by DMA (hb_copy_rows) in this mode
-    const float *oa = obs + (size_t)env * obs_ld + (row_a - fa), *ob = priv + (size_t)env * priv_ld + (row_b - fb);
-    for (int i = lane; i < fa; i += 32) {
-        const float v = oa[i];
-        ra[slot_a * fa + i] = v;
-        if (dup_a >= 0) ra[dup_a * fa + i] = v;
+    if (obs) {                                  // (either history may be left to another call)
+        const float *oa = obs + (size_t)env * obs_ld + (row_a - fa);
+        for (int i = lane; i < fa; i += 32) {
+            const float v = oa[i];
+            ra[slot_a * fa + i] = v;
+            if (dup_a >= 0) ra[dup_a * fa + i] = v;
+        }
     }
-    for (int i = lane; i < fb; i += 32) {
-        const float v = ob[i];
-        rb[slot_b * fb + i] = v;
-        if (dup_b >= 0) rb[dup_b * fb + i] = v;
+    if (priv) {
+        const float *ob = priv + (size_t)env * priv_ld + (row_b - fb);
+        for (int i = lane; i < fb; i += 32) {
+            const float v = ob[i];
+            rb[slot_b * fb + i] = v;
+            if (dup_b >= 0) rb[dup_b * fb + i] = v;
+        }
     }
 }
 
@@ -1736,7 +1741,7 @@ int hb_env_mirror_frames(const float *obs, int32_t obs_ld, int32_t obs_row, int3
                          int32_t priv_row, int32_t priv_frame, const uint8_t *reset_buf, int32_t num_envs, float *host_obs_ring,
                          int32_t obs_slots, int32_t obs_slot, float *host_priv_ring, int32_t priv_slots, int32_t priv_slot, int32_t use_dma,
                          void *stream) {
-    HB_REQUIRE(obs && priv && host_obs_ring && host_priv_ring && num_envs > 0, "hb_env_mirror_frames: null buffer");
+    HB_REQUIRE((obs || priv) && host_obs_ring && host_priv_ring && num_envs > 0, "hb_env_mirror_frames: null buffer");
     HB_REQUIRE(obs_frame > 0 && obs_row >= obs_frame && obs_ld >= obs_row && priv_frame > 0 && priv_row >= priv_frame && priv_ld >= priv_row,
                "hb_env_mirror_frames: bad row shapes");
     HB_REQUIRE(obs_row % obs_frame == 0 && priv_row % priv_frame == 0, "hb_env_mirror_frames: a row is a whole number of frames");
@@ -1757,10 +1762,14 @@ int hb_env_mirror_frames(const float *obs, int32_t obs_ld, int32_t obs_row, int3
             return cudaMemcpy2DAsync(ring + (size_t)slot * frame, pitch, src + (row - frame), (size_t)ld * 4, (size_t)frame * 4, (size_t)num_envs,
                                      cudaMemcpyDeviceToHost, st);
         };
-        HB_CUDA(dma(host_obs_ring, pitch_a, obs_slot, obs_frame, obs, obs_ld, obs_row));
-        if (obs_slot < sa - 1) HB_CUDA(dma(host_obs_ring, pitch_a, obs_slot + obs_slots, obs_frame, obs, obs_ld, obs_row));
-        HB_CUDA(dma(host_priv_ring, pitch_b, priv_slot, priv_frame, priv, priv_ld, priv_row));
-        if (priv_slot < sb - 1) HB_CUDA(dma(host_priv_ring, pitch_b, priv_slot + priv_slots, priv_frame, priv, priv_ld, priv_row));
+        if (obs) {
+            HB_CUDA(dma(host_obs_ring, pitch_a, obs_slot, obs_frame, obs, obs_ld, obs_row));
+            if (obs_slot < sa - 1) HB_CUDA(dma(host_obs_ring, pitch_a, obs_slot + obs_slots, obs_frame, obs, obs_ld, obs_row));
+        }
+        if (priv) {
+            HB_CUDA(dma(host_priv_ring, pitch_b, priv_slot, priv_frame, priv, priv_ld, priv_row));
+            if (priv_slot < sb - 1) HB_CUDA(dma(host_priv_ring, pitch_b, priv_slot + priv_slots, priv_frame, priv, priv_ld, priv_row));
+        }
         return HB_OK;
     }
     mirror_frames_kernel<<<(num_envs + warps - 1) / warps, warps * 32, 0, st>>>(
