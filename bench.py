@@ -663,7 +663,7 @@ def run_b200(args, rank, world):
     # stacked observations are strided views of those rings.  Same pipeline: step k+1 and its frame copies are enqueued
     # before the caller reads step k (the GPU never rewrites slots that an earlier step's views still show).
     from isaac_b200.envs.host_mirror import HostObservationMirror
-    mirror = HostObservationMirror(env, use_dma=os.environ.get("HB_MIRROR_DMA", "1") != "0")
+    mirror = HostObservationMirror(env, spare=int(os.environ.get("HB_MIRROR_SPARE", "17")), use_dma=os.environ.get("HB_MIRROR_DMA", "1") != "0")
     small_host = [[torch.empty(n).pin_memory(), torch.empty(n, dtype=torch.bool).pin_memory()] for _ in range(2)]
     reset_snap = [torch.empty(n, dtype=torch.bool, device=dev) for _ in range(2)]
     tickets = [None, None]
